@@ -1,0 +1,206 @@
+/* l3d.h -- C-ABI of the B200-native Light-3D-Unet hot path (libl3d.so).
+ *
+ * The reference (xxxxxxyp/Light-3D-Unet-Front) is pure Python/PyTorch and has no
+ * FFI layer; its boundary for this path is the Python API of light_unet.models,
+ * light_unet.utils and light_unet.core.inferencer.  The
+ * drop-in Python package keeps that API and drives these entry points; each one
+ * replaces the stock ATen/cuDNN/NumPy/SciPy call sequence issued by the cited
+ * reference lines.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host;
+ *  - activations are channels-last NDHWC ("voxel rows"): element (n,z,y,x,c) of a
+ *    view lives at ptr[(((n*D+z)*H+y)*W+x)*ldc + c], ldc >= C (ldc > C lets a
+ *    producer write straight into one half of a skip-concat buffer);
+ *  - parameters and their gradients use the reference's own (PyTorch) layouts in
+ *    fp32, so state_dict tensors are passed without repacking;
+ *  - functions are asynchronous on `stream` (a cudaStream_t passed as void*),
+ *    allocate nothing, and return 0 on success or a non-zero code whose text is
+ *    available from l3d_last_error();
+ *  - InstanceNorm statistics travel as double[2][N][C] = {sum, sum of squares} of
+ *    the raw (pre-norm) tensor, accumulated by the producer's epilogue and
+ *    turned into scale/shift by each consumer's prologue (no standalone norm pass).
+ */
+#ifndef L3D_H_
+#define L3D_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define L3D_ABI_VERSION 1
+
+enum { L3D_F32 = 0, L3D_BF16 = 1 };
+
+/* A channels-last activation view (spatial dims are passed per call). */
+typedef struct {
+    void   *ptr;
+    int32_t C;      /* channels in this view */
+    int32_t ldc;    /* elements between consecutive voxels */
+    int32_t dtype;  /* L3D_F32 | L3D_BF16 */
+    int32_t pad_;
+} l3d_act;
+
+/* How a consumer must read a raw tensor: y = lrelu((x-mean)*rstd*gamma+beta)*drop.
+ * stats == NULL means "already activated" (identity).  Mirrors
+ * InstanceNorm3d(affine) -> LeakyReLU(0.01) -> Dropout3d of unet3d.py:80-85. */
+typedef struct {
+    const double *stats;  /* [2][N][C] sum, sumsq; NULL => identity */
+    const float  *gamma;  /* [C] */
+    const float  *beta;   /* [C] */
+    const float  *drop;   /* [N][C] keep-mask already scaled by 1/(1-p), or NULL */
+    float   eps;          /* 1e-5 */
+    float   slope;        /* LeakyReLU negative slope; 1.0f => no activation */
+    int32_t count;        /* voxels per (n,c) the stats were reduced over */
+    int32_t pad_;
+} l3d_norm;
+
+const char *l3d_last_error(void);
+int l3d_abi_version(void);
+/* number of kernel launches issued through this library since load (for bench.py's gpu_launches) */
+int64_t l3d_launch_count(void);
+
+/* ---------------------------------------------------------------- forward -- */
+
+/* Fused depthwise 3x3x3 (pad 1) -> pointwise 1x1x1, optionally with the block's
+ * 1x1x1 shortcut conv computed from the same input tile.
+ *   replaces DepthwiseSeparableConv3d.forward (unet3d.py:20-23) + the shortcut
+ *   conv (unet3d.py:70-71) + the stat pass of the InstanceNorm3d that follows
+ *   (unet3d.py:51,62,72), with the preceding norm/LeakyReLU/Dropout3d applied on
+ *   load (xn).
+ * dw_w: [Cin][1][3][3][3] or NULL (pointwise only); pw_w: [Cout][Cin];
+ * sc_w: [Cout][Cin] or NULL.  t/r: raw outputs (Cout channels) with their stats
+ * buffers (must be zeroed by the caller); r may be {NULL}.  u: optional save of the
+ * depthwise output (Cin channels) for the backward pass, may be {NULL}. */
+int l3d_dwpw_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int W,
+                 const float *dw_w, const float *pw_w, const float *sc_w,
+                 const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats,
+                 const l3d_act *u, void *stream);
+
+/* Dense / grouped 3x3x3 convolution, pad 1, no bias (nn.Conv3d at unet3d.py:30,49,60).
+ * w: [Cout][Cin/groups][3][3][3]. */
+int l3d_conv3_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int W,
+                  const float *w, int groups, const l3d_act *t, double *t_stats, void *stream);
+
+/* Residual merge: out = lrelu(IN2(t2) + (INs(r) | r)) (unet3d.py:87-91), optionally also
+ * emitting MaxPool3d(2,2) of out (unet3d.py:109) and/or the 1x1x1 head + sigmoid
+ * (unet3d.py:220-221).  out / pooled may be {NULL}.  head_w: [OC][C] or NULL; prob and
+ * logits are fp32 NCDHW [N][OC][D][H][W]; logits may be NULL. */
+int l3d_merge_fwd(const l3d_act *t2, const l3d_norm *n2, const l3d_act *r, const l3d_norm *nr,
+                  int N, int D, int H, int W, float slope,
+                  const l3d_act *out, const l3d_act *pooled,
+                  const float *head_w, const float *head_b, int OC, float *prob, float *logits,
+                  void *stream);
+
+/* ConvTranspose3d(Cin, Cout, k=2, s=2) + bias (unet3d.py:119,127), written at spatial
+ * offset (oz,oy,ox) of an [N][OD][OH][OW] channels-last buffer (the centre pad of
+ * unet3d.py:130-138; the caller zeroes the buffer when the offsets/sizes leave a rim).
+ * w: [Cin][Cout][2][2][2]. */
+int l3d_convt_fwd(const l3d_act *x, int N, int d, int h, int w_, const float *w, const float *b,
+                  const l3d_act *out, int OD, int OH, int OW, int oz, int oy, int ox, void *stream);
+
+/* --------------------------------------------------------------- backward -- */
+
+/* Backward of l3d_merge_fwd.  gz = g_out * lrelu'(out) (+ head gradient when head_w given:
+ * g_out += g_logit * head_w; g_logit = g_prob * p * (1-p)).  Emits
+ *   gz (C channels, raw gradient w.r.t. the pre-activation sum),
+ *   red2/redr: double[2][N][C] = {sum gz, sum gz*xhat} for norm2 / the shortcut norm
+ *   (must be zeroed), and head parameter gradients (accumulated, fp32).
+ * g_out may be {NULL} when the only consumer is the head.  pooled_g: gradient arriving
+ * through the fused max-pool (routed to the arg-max voxel, first max in z,y,x scan order as
+ * ATen does), may be {NULL}. */
+int l3d_merge_bwd(const l3d_act *g_out, const l3d_act *pooled_g, const l3d_act *out, const l3d_act *pooled,
+                  const l3d_act *t2, const l3d_norm *n2, const l3d_act *r, const l3d_norm *nr,
+                  int N, int D, int H, int W, float slope,
+                  const float *head_w, int OC, const float *g_prob, const float *prob,
+                  float *g_head_w, float *g_head_b,
+                  const l3d_act *gz, double *red2, double *redr, void *stream);
+
+/* Backward of the pointwise stage: given gz (gradient w.r.t. the normalised output y of a
+ * raw tensor t = u . W^T), applies the InstanceNorm backward on the fly
+ *   g_t = gamma*rstd*(gz - mean(gz) - xhat*mean(gz*xhat))
+ * and produces g_u = g_t . W (Cin channels) and accumulates g_W += g_t^T . u.
+ * For the identity norm (nt.stats == NULL) g_t = gz.  u is the saved depthwise output
+ * (or the activated block input for a shortcut / pointwise-only conv, read through un). */
+int l3d_pw_bwd(const l3d_act *gz, const l3d_act *t, const l3d_norm *nt, const double *red,
+               const l3d_act *u, const l3d_norm *un, int N, int D, int H, int W,
+               const float *w, float *g_w, const l3d_act *g_u, int accumulate_gu, void *stream);
+
+/* Backward of the depthwise stage: g_a = dw^T(g_u) (flipped 27-tap stencil), g_dw += sum g_u*a,
+ * then through Dropout3d/LeakyReLU of the producer: gy = g_a * drop * lrelu'(y) written to
+ * `gy` (raw gradient w.r.t. the producer's normalised output) together with its reduction
+ * redx = {sum gy, sum gy*xhat} (zeroed by caller).  With xn.stats == NULL the input was a
+ * materialised activation: gy = g_a is accumulated/written as the gradient of that tensor. */
+int l3d_dw_bwd(const l3d_act *g_u, const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int W,
+               const float *dw_w, float *g_dw_w, const l3d_act *gy, int accumulate_gy, double *redx,
+               void *stream);
+
+/* Backward of l3d_conv3_fwd (dense / grouped): g_x (through the producer's activation, like
+ * l3d_dw_bwd) and g_w. */
+int l3d_conv3_bwd(const l3d_act *gz, const l3d_act *t, const l3d_norm *nt, const double *red,
+                  const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int W,
+                  const float *w, int groups, float *g_w,
+                  const l3d_act *gy, int accumulate_gy, double *redx, void *stream);
+
+/* Backward of l3d_convt_fwd: g_x = sum_taps g_out . W^T, g_w += x^T . g_out, g_b += sum g_out. */
+int l3d_convt_bwd(const l3d_act *g_out, int OD, int OH, int OW, int oz, int oy, int ox,
+                  const l3d_act *x, int N, int d, int h, int w_, const float *w,
+                  float *g_w, float *g_b, const l3d_act *g_x, int accumulate_gx, void *stream);
+
+/* InstanceNorm affine gradients from the reductions: g_gamma[c] += sum_n red[1][n][c],
+ * g_beta[c] += sum_n red[0][n][c]. */
+int l3d_norm_param_grad(const double *red, int N, int C, float *g_gamma, float *g_beta, void *stream);
+
+/* ------------------------------------------------------------------- loss -- */
+
+/* Focal Tversky (losses.py:40-52): sums[0..2] += {sum p*t, sum p, sum t} (double, zeroed by caller). */
+int l3d_ftl_sums(const float *pred, const float *target, int64_t n, double *sums, void *stream);
+/* loss = (1-TI)^gamma from (possibly all-reduced) sums; coef[0..1] = dL/dp for t=0 and the slope in t
+ * (dL/dp_i = coef[0] + coef[1]*t_i). */
+int l3d_ftl_finish(const double *sums, float alpha, float beta, float gamma, float smooth,
+                   float *loss, float *coef, void *stream);
+/* grad[i] = g_loss[0] * (coef[0] + coef[1]*target[i]) */
+int l3d_ftl_grad(const float *target, int64_t n, const float *coef, const float *g_loss, float *grad,
+                 void *stream);
+
+/* --------------------------------------------------------- sliding window -- */
+
+/* Cut windows out of a [D][H][W] fp32 volume (zero-padded at the far end, utils.py:91-112) into a
+ * [nwin][pd][ph][pw] single-channel batch of `dtype`.  pos: int32 [nwin][3] (z,y,x). */
+int l3d_gather_windows(const float *vol, int D, int H, int W, const int32_t *pos, int nwin,
+                       int pd, int ph, int pw, void *out, int dtype, void *stream);
+
+/* Gaussian-weighted overlap stitching (utils.py:126-137) as a per-voxel gather over the window
+ * grid, adding contributions in the reference's z->y->x window order with separately rounded
+ * fp32 multiply and add, then prob/cnt.  preds: fp32 [nz*ny*nx][pd][ph][pw] in window order.
+ * importance: fp32 [pd][ph][pw].  body_mask (uint8 [D][H][W]) or NULL multiplies the result
+ * (inferencer.py:161-162).  mask_out (int32 [D][H][W]) or NULL receives prob >= threshold
+ * (inferencer.py:64). */
+int l3d_stitch(const float *preds, const int32_t *zpos, int nz, const int32_t *ypos, int ny,
+               const int32_t *xpos, int nx, int pd, int ph, int pw, const float *importance,
+               int D, int H, int W, const uint8_t *body_mask, float *prob,
+               float threshold, int32_t *mask_out, void *stream);
+
+/* mask[i] = prob[i] >= threshold (inferencer.py:64). */
+int l3d_threshold(const float *prob, int64_t n, float threshold, int32_t *mask, void *stream);
+
+/* 6-connected component labelling with minimum-size filter and raster-order renumbering
+ * (metrics.py:50-61; replaces scipy.ndimage.label x2 + bincount).  labels: int32 [D][H][W] out.
+ * work: int32 scratch of l3d_ccl_workspace_elems(D*H*W) elements.  n_out: device int32. */
+int64_t l3d_ccl_workspace_elems(int64_t nvox);
+int l3d_ccl_label(const int32_t *mask, int D, int H, int W, int min_size, int32_t *labels,
+                  int32_t *n_out, int32_t *work, void *stream);
+
+/* Per-component reduction (inferencer.py:74-100): table[id-1] = {zmin,zmax,ymin,ymax,xmin,xmax,count,
+ * bits(max prob)} for ids 1..cap (components beyond cap are ignored).  table must be initialised by
+ * l3d_bbox_init. */
+int l3d_bbox_init(int32_t *table, int cap, void *stream);
+int l3d_bbox_reduce(const int32_t *labels, const float *prob, int D, int H, int W, int32_t *table, int cap,
+                    void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* L3D_H_ */

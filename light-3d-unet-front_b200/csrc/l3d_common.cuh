@@ -1,0 +1,162 @@
+// Shared device/host helpers for libl3d (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/l3d.h"
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------ errors --
+void l3d_set_error(const char *fmt, ...);
+void l3d_count_launch(int n = 1);
+
+#define L3D_REQUIRE(cond, ...)                  \
+    do {                                        \
+        if (!(cond)) {                          \
+            l3d_set_error(__VA_ARGS__);         \
+            return 1;                           \
+        }                                       \
+    } while (0)
+
+#define L3D_CUDA_OK(what)                                                            \
+    do {                                                                             \
+        cudaError_t e_ = cudaGetLastError();                                         \
+        if (e_ != cudaSuccess) {                                                     \
+            l3d_set_error("%s: %s", what, cudaGetErrorString(e_));                   \
+            return 2;                                                                \
+        }                                                                            \
+    } while (0)
+
+// Dispatch a templated launch on the activation dtype.
+#define L3D_DISPATCH_DTYPE(dt, T, ...)                        \
+    do {                                                      \
+        if ((dt) == L3D_F32) { typedef float T; __VA_ARGS__; } \
+        else { typedef bf16 T; __VA_ARGS__; }                 \
+    } while (0)
+
+static inline bool act_null(const l3d_act *a) { return a == nullptr || a->ptr == nullptr; }
+
+// ------------------------------------------------------------ element I/O --
+__device__ __forceinline__ float ld1(const float *p) { return *p; }
+__device__ __forceinline__ float ld1(const bf16 *p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void st1(float *p, float v) { *p = v; }
+__device__ __forceinline__ void st1(bf16 *p, float v) { *p = __float2bfloat16_rn(v); }
+
+// 4 consecutive channels; p must be aligned to 4 elements.
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ float4 ld4(const bf16 *p) {
+    const uint2 r = *reinterpret_cast<const uint2 *>(p);
+    float4 f;
+    f.x = __uint_as_float(r.x << 16);
+    f.y = __uint_as_float(r.x & 0xffff0000u);
+    f.z = __uint_as_float(r.y << 16);
+    f.w = __uint_as_float(r.y & 0xffff0000u);
+    return f;
+}
+__device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+__device__ __forceinline__ void st4(bf16 *p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<uint32_t *>(&a);
+    r.y = *reinterpret_cast<uint32_t *>(&b);
+    *reinterpret_cast<uint2 *>(p) = r;
+}
+// value as it will be read back from storage (bf16 rounding), used so that statistics and
+// arg-max decisions are taken on exactly the stored numbers
+__device__ __forceinline__ float round_as(const float *, float v) { return v; }
+__device__ __forceinline__ float round_as(const bf16 *, float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+__device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+// ----------------------------------------------------- norm prologue setup --
+// scale/shift so that activated = lrelu(x*scale + shift, slope) reproduces
+// InstanceNorm(affine) -> LeakyReLU -> Dropout3d (the keep-scale m >= 0 commutes with lrelu).
+struct NormDev {
+    const double *stats;
+    const float *gamma, *beta, *drop;
+    float eps, slope;
+    int count;
+};
+static inline NormDev norm_dev(const l3d_norm *n) {
+    NormDev d;
+    if (n == nullptr || n->stats == nullptr) {
+        d.stats = nullptr; d.gamma = d.beta = d.drop = nullptr; d.eps = 0.f; d.slope = 1.f; d.count = 1;
+    } else {
+        d.stats = n->stats; d.gamma = n->gamma; d.beta = n->beta; d.drop = n->drop;
+        d.eps = n->eps; d.slope = n->slope; d.count = n->count;
+    }
+    return d;
+}
+// mean / rstd of channel c of sample n from the {sum, sumsq} buffer ([2][N][C])
+__device__ __forceinline__ void norm_mean_rstd(const NormDev &nd, int N, int C, int n, int c, float &mean, float &rstd) {
+    const double s = nd.stats[(size_t)n * C + c];
+    const double q = nd.stats[(size_t)N * C + (size_t)n * C + c];
+    const double m = s / (double)nd.count;
+    double var = q / (double)nd.count - m * m;
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    rstd = (float)(1.0 / sqrt(var + (double)nd.eps));
+}
+__device__ __forceinline__ void norm_scale_shift(const NormDev &nd, int N, int C, int n, int c, float &scale, float &shift) {
+    if (nd.stats == nullptr) { scale = 1.f; shift = 0.f; return; }
+    float mean, rstd;
+    norm_mean_rstd(nd, N, C, n, c, mean, rstd);
+    float g = nd.gamma[c] * rstd;
+    float b = nd.beta[c] - mean * g;
+    if (nd.drop != nullptr) { const float m = nd.drop[(size_t)n * C + c]; g *= m; b *= m; }
+    scale = g; shift = b;
+}
+
+// ------------------------------------------------------- warp reductions --
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    return v;
+}
+
+// Transposing butterfly: every lane holds NV values (NV power of two <= 32); on return
+// vals[0] of lane l holds the warp-wide total of value index (l / (32/NV)) ... i.e. lane l owns
+// index l >> log2(32/NV); lanes sharing an index hold identical totals.  NV-1 + log2(32/NV) shuffles.
+template <int NV>
+__device__ __forceinline__ void warp_transpose_sum(float (&vals)[NV], int lane) {
+    int cnt = NV;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        if (cnt > 1) {
+            const int h = cnt >> 1;
+            const bool up = (lane & s) != 0;
+#pragma unroll
+            for (int i = 0; i < NV / 2; ++i) {
+                if (i < h) {
+                    const float send = up ? vals[i] : vals[i + h];
+                    const float keep = up ? vals[i + h] : vals[i];
+                    vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+                }
+            }
+            cnt = h;
+        } else {
+            vals[0] += __shfl_xor_sync(0xffffffffu, vals[0], s);
+        }
+    }
+}
+// index owned by `lane` after warp_transpose_sum<NV>: the exchange steps consumed the top log2(NV)
+// lane bits, most significant first, each selecting the upper half.
+template <int NV>
+__device__ __forceinline__ int warp_transpose_owner(int lane) {
+    int idx = 0, cnt = NV;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        if (cnt > 1) { cnt >>= 1; if (lane & s) idx += cnt; }
+    }
+    return idx;
+}

@@ -1,0 +1,320 @@
+// Sliding-window gather / stitch, threshold, 6-connected labelling and bounding-box reduction.
+//   utils.py:86-137 (window loop + normalisation), inferencer.py:62-109 (extract_bboxes),
+//   metrics.py:50-61 (get_connected_components; scipy.ndimage.label semantics).
+#include "l3d_common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------- windows ------------------
+template <typename T>
+__global__ void __launch_bounds__(256) gather_windows_kernel(const float *__restrict__ vol, int D, int H, int W,
+                                                             const int32_t *__restrict__ pos, int nwin,
+                                                             int pd, int ph, int pw, T *__restrict__ out) {
+    const size_t per = (size_t)pd * ph * pw;
+    const size_t total = per * nwin;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int wi = (int)(i / per);
+        size_t rem = i % per;
+        const int x = (int)(rem % pw); rem /= pw;
+        const int y = (int)(rem % ph);
+        const int z = (int)(rem / ph);
+        const int gz = pos[wi * 3] + z, gy = pos[wi * 3 + 1] + y, gx = pos[wi * 3 + 2] + x;
+        float v = 0.f;  // zero padding at the far end (utils.py:102-112)
+        if (gz < D && gy < H && gx < W) v = vol[((size_t)gz * H + gy) * W + gx];
+        st1(out + i, v);
+    }
+}
+
+// Per-voxel gather over the windows that cover it, in the reference's z -> y -> x window order.
+// The multiply and the add are rounded separately (numpy computes `pred * weights` into a temporary
+// and then `+=`), so the accumulation is bit-identical to utils.py:133-134 for identical predictions.
+__global__ void __launch_bounds__(256) stitch_kernel(const float *__restrict__ preds,
+                                                     const int32_t *__restrict__ zpos, int nz,
+                                                     const int32_t *__restrict__ ypos, int ny,
+                                                     const int32_t *__restrict__ xpos, int nx,
+                                                     int pd, int ph, int pw, const float *__restrict__ imp,
+                                                     int D, int H, int W, const uint8_t *__restrict__ body,
+                                                     float *__restrict__ prob, float thr, int32_t *__restrict__ mask) {
+    const size_t total = (size_t)D * H * W;
+    const size_t per = (size_t)pd * ph * pw;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t rem = i;
+        const int x = (int)(rem % W); rem /= W;
+        const int y = (int)(rem % H);
+        const int z = (int)(rem / H);
+        float acc = 0.f, cnt = 0.f;
+        for (int a = 0; a < nz; ++a) {
+            const int lz = z - zpos[a];
+            if (lz < 0 || lz >= pd) continue;
+            for (int b = 0; b < ny; ++b) {
+                const int ly = y - ypos[b];
+                if (ly < 0 || ly >= ph) continue;
+                for (int c = 0; c < nx; ++c) {
+                    const int lx = x - xpos[c];
+                    if (lx < 0 || lx >= pw) continue;
+                    const size_t wi = ((size_t)a * ny + b) * nx + c;
+                    const size_t li = ((size_t)lz * ph + ly) * pw + lx;
+                    const float wgt = imp[li];
+                    acc = __fadd_rn(acc, __fmul_rn(preds[wi * per + li], wgt));
+                    cnt = __fadd_rn(cnt, wgt);
+                }
+            }
+        }
+        float pr = cnt > 0.f ? __fdiv_rn(acc, cnt) : acc;   // np.divide(..., where=cnt>0) (utils.py:137)
+        if (body != nullptr) pr = __fmul_rn(pr, body[i] ? 1.f : 0.f);  // inferencer.py:161-162
+        prob[i] = pr;
+        if (mask != nullptr) mask[i] = pr >= thr ? 1 : 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) threshold_kernel(const float *__restrict__ prob, int64_t n, float thr,
+                                                        int32_t *__restrict__ mask) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        mask[i] = prob[i] >= thr ? 1 : 0;
+}
+
+// ------------------------------------------------------------------- CCL --------------------
+// Union-find over linear voxel indices; the root of a set is always its smallest index, so ranking the
+// roots by index reproduces scipy.ndimage.label's raster numbering.
+__device__ __forceinline__ int32_t uf_find(const int32_t *parent, int32_t i) {
+    // L2 loads: L1 is not coherent across SMs, and although a stale (older, larger) link is still a valid
+    // member of the chain, reading at L2 keeps the retry count low
+    int32_t p = __ldcg(parent + i);
+    while (p != i) { i = p; p = __ldcg(parent + i); }
+    return i;
+}
+__device__ __forceinline__ void uf_union(int32_t *parent, int32_t a, int32_t b) {
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) { const int32_t t = a; a = b; b = t; }   // a > b: hook a under b
+        const int32_t old = atomicMin(&parent[a], b);
+        if (old == a) return;
+        a = old;                                             // someone else hooked a first; retry with its new parent
+    }
+}
+
+__global__ void __launch_bounds__(256) ccl_init_kernel(const int32_t *__restrict__ mask, int32_t n, int32_t *__restrict__ parent,
+                                                       int32_t *__restrict__ size) {
+    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        parent[i] = mask[i] != 0 ? i : -1;
+        size[i] = 0;
+    }
+}
+__global__ void __launch_bounds__(256) ccl_merge_kernel(int32_t *__restrict__ parent, int D, int H, int W) {
+    const int32_t n = D * H * W;
+    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (parent[i] < 0) continue;
+        const int x = i % W, y = (i / W) % H, z = i / (W * H);
+        if (x > 0 && parent[i - 1] >= 0) uf_union(parent, i, i - 1);
+        if (y > 0 && parent[i - W] >= 0) uf_union(parent, i, i - W);
+        if (z > 0 && parent[i - W * H] >= 0) uf_union(parent, i, i - W * H);
+    }
+}
+__global__ void __launch_bounds__(256) ccl_flatten_count_kernel(int32_t *__restrict__ parent, int32_t n, int32_t *__restrict__ size) {
+    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (parent[i] < 0) continue;
+        const int32_t r = uf_find(parent, i);
+        // roots keep parent[r] == r; non-roots may point at the root directly (no thread still needs the chain:
+        // every chain ends at r and a concurrent reader following a shortened link still arrives at r)
+        if (r != i) parent[i] = r;
+        atomicAdd(&size[r], 1);
+    }
+}
+// flag[i] = 1 iff voxel i is the root of a surviving component
+__global__ void __launch_bounds__(256) ccl_flag_kernel(const int32_t *__restrict__ parent, const int32_t *__restrict__ size,
+                                                       int32_t n, int min_size, int32_t *__restrict__ flag) {
+    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        flag[i] = (parent[i] == i && size[i] >= min_size) ? 1 : 0;
+}
+// three-kernel exclusive scan of flag -> rank (int32), SCAN_BLOCK elements per CTA
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
+__device__ __forceinline__ int block_exclusive_scan(int v, int *s_warp, int &total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int w = lane < (SCAN_THREADS / 32) ? s_warp[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += t; }
+        if (lane < SCAN_THREADS / 32) s_warp[lane] = winc - w;  // exclusive per-warp offsets
+        if (lane == SCAN_THREADS / 32 - 1) s_warp[SCAN_THREADS / 32] = winc;
+    }
+    __syncthreads();
+    total = s_warp[SCAN_THREADS / 32];
+    const int res = s_warp[wid] + inc - v;
+    __syncthreads();
+    return res;
+}
+__global__ void __launch_bounds__(SCAN_THREADS) scan_block_sums_kernel(const int32_t *__restrict__ flag, int32_t n, int32_t *__restrict__ bsum) {
+    __shared__ int s_warp[SCAN_THREADS / 32 + 1];
+    const int32_t base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+    int v = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) if (base + k < n) v += flag[base + k];
+    int total;
+    block_exclusive_scan(v, s_warp, total);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = total;
+}
+// single CTA: exclusive scan of the block sums in place; writes the grand total to *n_out
+__global__ void __launch_bounds__(SCAN_THREADS) scan_top_kernel(int32_t *__restrict__ bsum, int32_t nb, int32_t *__restrict__ n_out) {
+    __shared__ int s_warp[SCAN_THREADS / 32 + 1];
+    int carry = 0;
+    for (int32_t start = 0; start < nb; start += SCAN_THREADS) {
+        const int32_t i = start + threadIdx.x;
+        const int v = i < nb ? bsum[i] : 0;
+        int total;
+        const int ex = block_exclusive_scan(v, s_warp, total);
+        if (i < nb) bsum[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *n_out = carry;
+}
+// rank[i] = exclusive prefix of flag (only meaningful where flag[i] == 1); written over `flag`
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(int32_t *__restrict__ flag, int32_t n, const int32_t *__restrict__ bsum) {
+    __shared__ int s_warp[SCAN_THREADS / 32 + 1];
+    const int32_t base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+    int f[SCAN_ITEMS];
+    int v = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { f[k] = (base + k < n) ? flag[base + k] : 0; v += f[k]; }
+    int total;
+    int run = bsum[blockIdx.x] + block_exclusive_scan(v, s_warp, total);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) flag[base + k] = f[k] ? run + 1 : 0;   // 1-based id at surviving roots, 0 elsewhere
+        run += f[k];
+    }
+}
+__global__ void __launch_bounds__(256) ccl_relabel_kernel(const int32_t *__restrict__ parent, const int32_t *__restrict__ rootid,
+                                                          int32_t n, int32_t *__restrict__ labels) {
+    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int32_t p = parent[i];
+        labels[i] = p < 0 ? 0 : rootid[p];
+    }
+}
+
+// ------------------------------------------------------------------ bbox --------------------
+__global__ void bbox_init_kernel(int32_t *__restrict__ table, int cap) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+        int32_t *t = table + (size_t)i * 8;
+        t[0] = t[2] = t[4] = 0x7fffffff;
+        t[1] = t[3] = t[5] = -1;
+        t[6] = 0;
+        t[7] = 0;  // bits of +0.0f; probabilities are >= 0 so the int ordering equals the float ordering
+    }
+}
+__global__ void __launch_bounds__(256) bbox_reduce_kernel(const int32_t *__restrict__ labels, const float *__restrict__ prob,
+                                                          int D, int H, int W, int32_t *__restrict__ table, int cap) {
+    const int32_t n = D * H * W;
+    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int32_t l = labels[i];
+        if (l <= 0 || l > cap) continue;
+        const int x = i % W, y = (i / W) % H, z = i / (W * H);
+        int32_t *t = table + (size_t)(l - 1) * 8;
+        atomicMin(&t[0], z); atomicMax(&t[1], z);
+        atomicMin(&t[2], y); atomicMax(&t[3], y);
+        atomicMin(&t[4], x); atomicMax(&t[5], x);
+        atomicAdd(&t[6], 1);
+        atomicMax(&t[7], __float_as_int(fmaxf(prob[i], 0.f)));
+    }
+}
+
+static unsigned grid_for(int64_t n, int threads, int cap_blocks) {
+    int64_t b = (n + threads - 1) / threads;
+    if (b > cap_blocks) b = cap_blocks;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+
+}  // namespace
+
+extern "C" int l3d_gather_windows(const float *vol, int D, int H, int W, const int32_t *pos, int nwin,
+                                  int pd, int ph, int pw, void *out, int dtype, void *stream) {
+    L3D_REQUIRE(vol && pos && out && nwin > 0 && pd > 0 && ph > 0 && pw > 0, "l3d_gather_windows: bad argument");
+    const int64_t total = (int64_t)nwin * pd * ph * pw;
+    const unsigned blocks = grid_for(total, 256, 148 * 32);
+    L3D_DISPATCH_DTYPE(dtype, T, {
+        gather_windows_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>(vol, D, H, W, pos, nwin, pd, ph, pw, (T *)out);
+    });
+    l3d_count_launch();
+    L3D_CUDA_OK("l3d_gather_windows launch");
+    return 0;
+}
+
+extern "C" int l3d_stitch(const float *preds, const int32_t *zpos, int nz, const int32_t *ypos, int ny,
+                          const int32_t *xpos, int nx, int pd, int ph, int pw, const float *importance,
+                          int D, int H, int W, const uint8_t *body_mask, float *prob,
+                          float threshold, int32_t *mask_out, void *stream) {
+    L3D_REQUIRE(preds && zpos && ypos && xpos && importance && prob, "l3d_stitch: null argument");
+    L3D_REQUIRE(nz > 0 && ny > 0 && nx > 0 && D > 0 && H > 0 && W > 0, "l3d_stitch: bad dims");
+    const unsigned blocks = grid_for((int64_t)D * H * W, 256, 148 * 32);
+    stitch_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(preds, zpos, nz, ypos, ny, xpos, nx, pd, ph, pw, importance,
+                                                           D, H, W, body_mask, prob, threshold, mask_out);
+    l3d_count_launch();
+    L3D_CUDA_OK("l3d_stitch launch");
+    return 0;
+}
+
+extern "C" int l3d_threshold(const float *prob, int64_t n, float threshold, int32_t *mask, void *stream) {
+    L3D_REQUIRE(prob && mask && n >= 0, "l3d_threshold: null argument");
+    if (n == 0) return 0;
+    threshold_kernel<<<grid_for(n, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(prob, n, threshold, mask);
+    l3d_count_launch();
+    L3D_CUDA_OK("l3d_threshold launch");
+    return 0;
+}
+
+extern "C" int64_t l3d_ccl_workspace_elems(int64_t nvox) {
+    const int64_t nb = (nvox + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    return 3 * nvox + nb + 16;   // parent, size, flag/rootid, block sums
+}
+
+extern "C" int l3d_ccl_label(const int32_t *mask, int D, int H, int W, int min_size, int32_t *labels,
+                             int32_t *n_out, int32_t *work, void *stream) {
+    L3D_REQUIRE(mask && labels && n_out && work, "l3d_ccl_label: null argument");
+    const int64_t n64 = (int64_t)D * H * W;
+    L3D_REQUIRE(n64 > 0 && n64 < (1ll << 31) - SCAN_BLOCK, "l3d_ccl_label: volume too large for int32 indices");
+    const int32_t n = (int32_t)n64;
+    const int32_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    int32_t *parent = work, *size = work + n64, *flag = work + 2 * n64, *bsum = work + 3 * n64;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned g = grid_for(n, 256, 148 * 32);
+    ccl_init_kernel<<<g, 256, 0, st>>>(mask, n, parent, size);
+    ccl_merge_kernel<<<g, 256, 0, st>>>(parent, D, H, W);
+    ccl_flatten_count_kernel<<<g, 256, 0, st>>>(parent, n, size);
+    // metrics.py:52-58 drops components with size < min_size only when min_size > 0; with min_size <= 0 every
+    // component (size >= 1) survives, which `size >= min_size` also yields.
+    ccl_flag_kernel<<<g, 256, 0, st>>>(parent, size, n, min_size, flag);
+    scan_block_sums_kernel<<<nb, SCAN_THREADS, 0, st>>>(flag, n, bsum);
+    scan_top_kernel<<<1, SCAN_THREADS, 0, st>>>(bsum, nb, n_out);
+    scan_apply_kernel<<<nb, SCAN_THREADS, 0, st>>>(flag, n, bsum);
+    ccl_relabel_kernel<<<g, 256, 0, st>>>(parent, flag, n, labels);
+    l3d_count_launch(8);
+    L3D_CUDA_OK("l3d_ccl_label launch");
+    return 0;
+}
+
+extern "C" int l3d_bbox_init(int32_t *table, int cap, void *stream) {
+    L3D_REQUIRE(table && cap > 0, "l3d_bbox_init: bad argument");
+    bbox_init_kernel<<<grid_for(cap, 256, 1024), 256, 0, (cudaStream_t)stream>>>(table, cap);
+    l3d_count_launch();
+    L3D_CUDA_OK("l3d_bbox_init launch");
+    return 0;
+}
+
+extern "C" int l3d_bbox_reduce(const int32_t *labels, const float *prob, int D, int H, int W, int32_t *table, int cap,
+                               void *stream) {
+    L3D_REQUIRE(labels && prob && table && cap > 0, "l3d_bbox_reduce: bad argument");
+    const int64_t n = (int64_t)D * H * W;
+    L3D_REQUIRE(n > 0 && n < (1ll << 31), "l3d_bbox_reduce: volume too large");
+    bbox_reduce_kernel<<<grid_for(n, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(labels, prob, D, H, W, table, cap);
+    l3d_count_launch();
+    L3D_CUDA_OK("l3d_bbox_reduce launch");
+    return 0;
+}

@@ -1,0 +1,150 @@
+"""ctypes binding of libl3d.so (the C-ABI declared in include/l3d.h).
+
+There is NO fallback: if the library is missing or a CUDA device is not used,
+the product path raises.  torch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, byref, c_double, c_float, c_int, c_int32, c_int64, c_void_p
+
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.environ.get("L3D_LIB", os.path.join(_PKG_DIR, "libl3d.so"))
+
+L3D_F32, L3D_BF16 = 0, 1
+ABI_VERSION = 1
+
+
+class Act(Structure):
+    _fields_ = [("ptr", c_void_p), ("C", c_int32), ("ldc", c_int32), ("dtype", c_int32), ("pad_", c_int32)]
+
+
+class Norm(Structure):
+    _fields_ = [("stats", c_void_p), ("gamma", c_void_p), ("beta", c_void_p), ("drop", c_void_p),
+                ("eps", c_float), ("slope", c_float), ("count", c_int32), ("pad_", c_int32)]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# name -> argtypes ; every function returns int status except the ones listed in _SPECIAL
+_P = c_void_p
+_SIGS = {
+    "l3d_dwpw_fwd": [POINTER(Act), POINTER(Norm), c_int, c_int, c_int, c_int, _P, _P, _P,
+                     POINTER(Act), _P, POINTER(Act), _P, POINTER(Act), _P],
+    "l3d_conv3_fwd": [POINTER(Act), POINTER(Norm), c_int, c_int, c_int, c_int, _P, c_int, POINTER(Act), _P, _P],
+    "l3d_merge_fwd": [POINTER(Act), POINTER(Norm), POINTER(Act), POINTER(Norm), c_int, c_int, c_int, c_int, c_float,
+                      POINTER(Act), POINTER(Act), _P, _P, c_int, _P, _P, _P],
+    "l3d_convt_fwd": [POINTER(Act), c_int, c_int, c_int, c_int, _P, _P, POINTER(Act), c_int, c_int, c_int,
+                      c_int, c_int, c_int, _P],
+    "l3d_merge_bwd": [POINTER(Act), POINTER(Act), POINTER(Act), POINTER(Act), POINTER(Act), POINTER(Norm),
+                      POINTER(Act), POINTER(Norm), c_int, c_int, c_int, c_int, c_float,
+                      _P, c_int, _P, _P, _P, _P, POINTER(Act), _P, _P, _P],
+    "l3d_pw_bwd": [POINTER(Act), POINTER(Act), POINTER(Norm), _P, POINTER(Act), POINTER(Norm),
+                   c_int, c_int, c_int, c_int, _P, _P, POINTER(Act), c_int, _P],
+    "l3d_dw_bwd": [POINTER(Act), POINTER(Act), POINTER(Norm), c_int, c_int, c_int, c_int, _P, _P,
+                   POINTER(Act), c_int, _P, _P],
+    "l3d_conv3_bwd": [POINTER(Act), POINTER(Act), POINTER(Norm), _P, POINTER(Act), POINTER(Norm),
+                      c_int, c_int, c_int, c_int, _P, c_int, _P, POINTER(Act), c_int, _P, _P],
+    "l3d_convt_bwd": [POINTER(Act), c_int, c_int, c_int, c_int, c_int, c_int, POINTER(Act), c_int, c_int, c_int, c_int,
+                      _P, _P, _P, POINTER(Act), c_int, _P],
+    "l3d_norm_param_grad": [_P, c_int, c_int, _P, _P, _P],
+    "l3d_ftl_sums": [_P, _P, c_int64, _P, _P],
+    "l3d_ftl_finish": [_P, c_float, c_float, c_float, c_float, _P, _P, _P],
+    "l3d_ftl_grad": [_P, c_int64, _P, _P, _P, _P],
+    "l3d_gather_windows": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, _P],
+    "l3d_stitch": [_P, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P, _P,
+                   c_float, _P, _P],
+    "l3d_threshold": [_P, c_int64, c_float, _P, _P],
+    "l3d_ccl_label": [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
+    "l3d_bbox_init": [_P, c_int, _P],
+    "l3d_bbox_reduce": [_P, _P, c_int, c_int, c_int, _P, c_int, _P],
+}
+EXPORTS = sorted(list(_SIGS) + ["l3d_last_error", "l3d_abi_version", "l3d_launch_count", "l3d_ccl_workspace_elems"])
+
+
+def lib():
+    """Load libl3d.so (once).  Raises NativeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(
+            f"{LIB_PATH} not found: build it with `python __graft_entry__.py` (or "
+            f"`python light-3d-unet-front_b200/build.py`). There is no CPU / PyTorch fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    L.l3d_last_error.restype = ctypes.c_char_p
+    L.l3d_last_error.argtypes = []
+    L.l3d_abi_version.restype = c_int
+    L.l3d_launch_count.restype = c_int64
+    L.l3d_ccl_workspace_elems.restype = c_int64
+    L.l3d_ccl_workspace_elems.argtypes = [c_int64]
+    for name, sig in _SIGS.items():
+        fn = getattr(L, name)
+        fn.restype = c_int
+        fn.argtypes = sig
+    if L.l3d_abi_version() != ABI_VERSION:
+        raise NativeError(f"libl3d ABI {L.l3d_abi_version()} != binding {ABI_VERSION}; rebuild")
+    _lib = L
+    return L
+
+
+def call(name: str, *args):
+    """Invoke an entry point; non-zero status -> NativeError(l3d_last_error())."""
+    L = lib()
+    rc = getattr(L, name)(*args)
+    if rc != 0:
+        raise NativeError(f"{name} failed ({rc}): {L.l3d_last_error().decode(errors='replace')}")
+
+
+def launch_count() -> int:
+    return int(lib().l3d_launch_count())
+
+
+def stream_ptr(device=None) -> c_void_p:
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise NativeError(
+            f"{what}: tensor is on {t.device}; the B200-native path runs on CUDA only (no CPU fallback)")
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return L3D_F32
+    if dt == torch.bfloat16:
+        return L3D_BF16
+    raise NativeError(f"unsupported activation dtype {dt}")
+
+
+def ptr(t) -> c_void_p:
+    return c_void_p(0) if t is None else c_void_p(t.data_ptr())
+
+
+_NULL_ACT = Act(None, 0, 0, 0, 0)
+
+
+def act(t: torch.Tensor | None, ch_off: int = 0, C: int | None = None) -> Act:
+    """View of a channels-last [N, D, H, W, Ctot] tensor restricted to channels [ch_off, ch_off+C)."""
+    if t is None:
+        return Act(None, 0, 0, 0, 0)
+    assert t.is_contiguous(), "activation buffers must be contiguous NDHWC"
+    ctot = t.shape[-1]
+    if C is None:
+        C = ctot - ch_off
+    return Act(c_void_p(t.data_ptr() + ch_off * t.element_size()), C, ctot, dtype_code(t.dtype), 0)
+
+
+def norm(stats=None, gamma=None, beta=None, drop=None, eps=1e-5, slope=1.0, count=1) -> Norm:
+    if stats is None:
+        return Norm(None, None, None, None, 0.0, 1.0, 1, 0)
+    return Norm(c_void_p(stats.data_ptr()), c_void_p(gamma.data_ptr()), c_void_p(beta.data_ptr()),
+                c_void_p(drop.data_ptr()) if drop is not None else None, eps, slope, int(count), 0)

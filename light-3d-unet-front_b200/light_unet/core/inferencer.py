@@ -1,0 +1,178 @@
+"""Inferencer -- drop-in for light_unet/core/inferencer.py.
+
+Same constructor, `extract_bboxes`, `infer_case` and `infer_split` contract as the
+reference; the sliding window, threshold, connected components and per-component
+reductions run on the GPU (libl3d).  `infer_volume` is the device-resident core
+(volume in -> probability map + candidate boxes out) that `infer_case` wraps with
+the NIfTI / JSON file I/O of the reference (inferencer.py:122-134,164-180; needs
+nibabel, imported lazily because file I/O is off the accelerated path).
+"""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from .. import _native as nv
+from ..models.metrics import label_device
+from ..models.unet3d import Lightweight3DUNet
+from ..utils import find_case_files, sliding_window_device, sliding_window_inference_3d
+from .config import ConfigManager
+
+BBOX_TABLE_CAP = 1 << 16
+
+
+class Inferencer:
+    """Inference class for generating predictions (reference: inferencer.py:18-60)."""
+
+    def __init__(self, config_or_path, model_path):
+        if isinstance(config_or_path, (str, Path)):
+            self.config = ConfigManager.load(str(config_or_path))
+        elif isinstance(config_or_path, dict):
+            self.config = config_or_path
+        else:
+            raise TypeError(f"config_or_path must be str, Path or dict, got {type(config_or_path)}")
+        if not torch.cuda.is_available():
+            raise nv.NativeError("Inferencer: the B200-native path needs a CUDA device (no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        print(f"Using device: {self.device}")
+        m = self.config["model"]
+        self.model = Lightweight3DUNet(
+            in_channels=1, out_channels=m["output_channels"], start_channels=m["start_channels"],
+            encoder_channels=m["encoder_channels"], use_depthwise_separable=m["use_depthwise_separable"],
+            use_grouped=m["use_grouped_conv"], groups=m["groups"], dropout_p=0.0).to(self.device)
+        checkpoint = torch.load(model_path, map_location=self.device)
+        self.model.load_state_dict(checkpoint["model_state_dict"])
+        self.model.eval()
+        print(f"Loaded model from {model_path}")
+        print(f"Best epoch: {checkpoint.get('best_epoch', 'N/A')}")
+        print(f"Best metric: {checkpoint.get('best_metric', 'N/A'):.4f}")
+        self.prob_maps_dir = Path(self.config["output"]["prob_maps_dir"])
+        self.bboxes_dir = Path(self.config["output"]["bboxes_dir"])
+        self.prob_maps_dir.mkdir(parents=True, exist_ok=True)
+        self.bboxes_dir.mkdir(parents=True, exist_ok=True)
+
+    # ------------------------------------------------------------------ boxes
+    def _bboxes_from_device(self, prob_d: torch.Tensor, mask_d: torch.Tensor, min_volume_cc, spacing):
+        """threshold mask -> labels -> per-component table on the device, then the reference's host-side
+        arithmetic on the resulting integers (inferencer.py:66-108)."""
+        D, H, W = prob_d.shape
+        voxel_volume_cc = spacing[0] * spacing[1] * spacing[2] / 1000.0
+        min_voxels = int(np.ceil(min_volume_cc / voxel_volume_cc))
+        labels, n_d = label_device(mask_d, min_voxels if min_voxels > 0 else 0)
+        st = nv.stream_ptr(prob_d.device)
+        table = torch.empty(BBOX_TABLE_CAP, 8, dtype=torch.int32, device=prob_d.device)
+        nv.call("l3d_bbox_init", nv.ptr(table), BBOX_TABLE_CAP, st)
+        nv.call("l3d_bbox_reduce", nv.ptr(labels), nv.ptr(prob_d), D, H, W, nv.ptr(table), BBOX_TABLE_CAP, st)
+        n = int(n_d.item())
+        if n > BBOX_TABLE_CAP:
+            cap = n
+            table = torch.empty(cap, 8, dtype=torch.int32, device=prob_d.device)
+            nv.call("l3d_bbox_init", nv.ptr(table), cap, st)
+            nv.call("l3d_bbox_reduce", nv.ptr(labels), nv.ptr(prob_d), D, H, W, nv.ptr(table), cap, st)
+        rows = table[:n].cpu().numpy()
+        expansion = self.config["data"]["bbox_expansion_voxels"]
+        shape = (D, H, W)
+        out = []
+        for i in range(n):
+            row = rows[i]
+            if row[6] == 0:
+                continue
+            lo = [np.int64(row[0]), np.int64(row[2]), np.int64(row[4])]
+            hi = [np.int64(row[1]), np.int64(row[3]), np.int64(row[5])]
+            box = []
+            for ax in range(3):
+                box.append(max(0, lo[ax] - expansion))
+                box.append(min(shape[ax] - 1, hi[ax] + expansion))
+            mm = [box[2 * ax + k] * spacing[ax] for ax in range(3) for k in range(2)]
+            volume_cc = np.int64(row[6]) * voxel_volume_cc
+            confidence = np.array([row[7]], dtype=np.int32).view(np.float32)[0]
+            out.append({"mask_id": i + 1,
+                        "bbox_voxel": [int(v) for v in box],
+                        "bbox_mm": [float(v) for v in mm],
+                        "volume_cc": float(volume_cc),
+                        "confidence": float(confidence)})
+        return out
+
+    def extract_bboxes(self, prob_map, threshold=0.3, min_volume_cc=0.5, spacing=(4.0, 4.0, 4.0)):
+        """Extract bounding boxes from a probability map (reference signature, inferencer.py:62)."""
+        if isinstance(prob_map, torch.Tensor):
+            prob_d = prob_map.to(self.device, dtype=torch.float32).contiguous()
+        else:
+            prob_d = torch.from_numpy(np.ascontiguousarray(prob_map, dtype=np.float32)).to(self.device)
+        if prob_d.dim() != 3:
+            raise ValueError(f"Expected 3D probability map, got shape {tuple(prob_d.shape)}")
+        mask_d = torch.empty(prob_d.shape, dtype=torch.int32, device=self.device)
+        # `prob_map >= threshold` compares float32 values with the python float converted to float32
+        nv.call("l3d_threshold", nv.ptr(prob_d), prob_d.numel(), float(np.float32(threshold)), nv.ptr(mask_d),
+                nv.stream_ptr(self.device))
+        return self._bboxes_from_device(prob_d, mask_d, min_volume_cc, spacing)
+
+    # ----------------------------------------------------------------- volume
+    def infer_volume(self, image, threshold=0.3, spacing=(4.0, 4.0, 4.0), body_mask=None, return_device=False):
+        """Device-resident case pipeline: sliding window -> (body mask) -> threshold -> CC -> boxes.
+        `image` is a host ndarray or CUDA tensor [D,H,W].  Returns (prob_map, bboxes)."""
+        if isinstance(image, torch.Tensor):
+            vol = image.to(self.device, dtype=torch.float32)
+        else:
+            vol = torch.from_numpy(np.ascontiguousarray(image, dtype=np.float32)).to(self.device, non_blocking=True)
+        bm = None
+        if body_mask is not None:
+            bm = body_mask if isinstance(body_mask, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(body_mask).astype(np.uint8))
+        prob_d, mask_d = sliding_window_device(vol, self.model, tuple(self.config["data"]["patch_size"]), 0.5, True,
+                                               body_mask=bm, threshold=threshold)
+        bboxes = self._bboxes_from_device(prob_d, mask_d, self.config["data"]["volume_threshold"]["inference_cc"], spacing)
+        return (prob_d if return_device else prob_d.cpu().numpy()), bboxes
+
+    # ------------------------------------------------------------- file level
+    def infer_case(self, case_id, data_dir, threshold=0.3):
+        """Single-case inference with the reference's file layout (inferencer.py:113-183)."""
+        import nibabel as nib   # NIfTI I/O (not part of the accelerated path)
+        data_dir = Path(data_dir)
+        image_files = find_case_files(data_dir, case_id, file_type="image")
+        if len(image_files) == 0:
+            print(f"Warning: No image files found for {case_id}")
+            return False
+        image_nii = nib.load(image_files[0])
+        image = image_nii.get_fdata().astype(np.float32)
+        affine, header = image_nii.affine, image_nii.header
+        spacing = [float(s) for s in header.get_zooms()[:3]]
+        bm_cfg = self.config.get("data", {}).get("body_mask", {})
+        apply_bm = bm_cfg.get("apply_to_inference", False) and bm_cfg.get("enabled", False)
+        body_mask = None
+        if apply_bm:
+            bm_path = data_dir / "body_masks" / f"{case_id}.nii.gz"
+            if bm_path.exists():
+                body_mask = nib.load(bm_path).get_fdata().astype(bool)
+            else:
+                print(f"Warning: Body mask not found for {case_id}")
+        print(f"Running inference on {case_id}...")
+        try:
+            prob_map, bboxes = self.infer_volume(image, threshold=threshold, spacing=spacing, body_mask=body_mask)
+        except Exception as e:   # the reference swallows sliding-window failures and reports the case as failed
+            print(f"Error during inference execution for {case_id}: {e}")
+            return False
+        nib.save(nib.Nifti1Image(prob_map, affine, header), self.prob_maps_dir / f"{case_id}_prob.nii.gz")
+        bbox_json = {"case_id": case_id, "processing_path": "B", "orig_spacing": spacing, "threshold": threshold,
+                     "num_candidates": len(bboxes), "candidates": bboxes}
+        bbox_path = self.bboxes_dir / f"{case_id}_bboxes.json"
+        with open(bbox_path, "w") as f:
+            json.dump(bbox_json, f, indent=2)
+        print(f"Found {len(bboxes)} candidates, saved to {bbox_path}")
+        return True
+
+    def infer_split(self, split_file, data_dir):
+        """All cases of a split file (inferencer.py:185-201)."""
+        with open(split_file, "r") as f:
+            case_ids = [line.strip() for line in f if line.strip()]
+        print(f"Performing inference on {len(case_ids)} cases...")
+        successful, failed = 0, []
+        threshold = self.config["validation"]["default_threshold"]
+        for case_id in case_ids:
+            if self.infer_case(case_id, data_dir, threshold=threshold):
+                successful += 1
+            else:
+                failed.append(case_id)
+        print(f"\nInference complete: Successful: {successful}/{len(case_ids)}")

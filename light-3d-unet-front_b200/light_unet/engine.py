@@ -1,0 +1,217 @@
+"""Launch plan of the B200-native U-Net: sequences the libl3d kernels for one
+forward (and backward) pass of Lightweight3DUNet.
+
+Host-side only: shape bookkeeping, workspace (HBM) layout and kernel ordering.
+All arithmetic happens in libl3d.so; there is no PyTorch fallback.
+
+HBM layout (per workspace, i.e. per (N, D, H, W, dtype, training) key):
+  * activations are channels-last NDHWC, bf16 by default (fp32 optional);
+  * the output of the three encoder blocks that feed a skip connection is
+    written straight into the upper channel half of the decoder's concat buffer
+    (`cat`), the transposed conv writes the lower half -> torch.cat / F.pad of
+    unet3d.py:130-141 never materialise;
+  * each block keeps three raw (pre-norm) tensors t1, t2, r plus double
+    {sum, sumsq} statistics; norm/LeakyReLU/dropout are applied by the consumer;
+  * in training mode the depthwise outputs u1, u2 are also kept for wgrad.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _native as nv
+
+LEAKY_SLOPE = 0.01   # unet3d.py:52,63
+IN_EPS = 1e-5        # nn.InstanceNorm3d default
+
+
+@dataclass
+class BlockSpec:
+    name: str          # init_conv, down1, ...
+    prefix: str        # state_dict prefix of the residual block
+    cin: int
+    cout: int
+    level: int
+    kind1: str         # "dws" | "grouped" | "dense"
+    kind2: str
+
+
+def _conv_kind(dws: bool, grouped: bool, groups: int, cin: int, cout: int, which: int) -> str:
+    """Branch selection of ResidualBlock.__init__ (unet3d.py:44-49, :55-60)."""
+    if dws:
+        return "dws"
+    if which == 1:
+        ok = grouped and groups > 1 and cin >= groups and cout >= groups
+    else:
+        ok = grouped and groups > 1 and cout >= groups
+    return "grouped" if ok else "dense"
+
+
+def make_block_specs(in_channels: int, enc: Sequence[int], dws: bool, grouped: bool, groups: int) -> List[BlockSpec]:
+    e = list(enc)
+    rows = [("init_conv", "init_conv", in_channels, e[0], 0, False),
+            ("down1", "down1.res_block", e[0], e[1], 1, grouped),
+            ("down2", "down2.res_block", e[1], e[2], 2, grouped),
+            ("down3", "down3.res_block", e[2], e[3], 3, grouped),
+            ("bottleneck", "bottleneck", e[3], e[3], 3, grouped),
+            ("up1", "up1.res_block", e[3], e[2], 2, grouped),
+            ("up2", "up2.res_block", e[2], e[1], 1, grouped),
+            ("up3", "up3.res_block", e[1], e[0], 0, grouped)]
+    return [BlockSpec(n, p, ci, co, lv, _conv_kind(dws, g, groups, ci, co, 1), _conv_kind(dws, g, groups, co, co, 2))
+            for n, p, ci, co, lv, g in rows]
+
+
+class Workspace:
+    """All HBM buffers of one forward(/backward) pass for a fixed problem shape."""
+
+    def __init__(self, plan: "UNetPlan", N: int, dims: Tuple[int, int, int], dtype: torch.dtype, device,
+                 training: bool):
+        self.N, self.dims, self.dtype, self.device, self.training = N, dims, dtype, device, training
+        e = plan.enc
+        lv = [tuple(dims)]
+        for _ in range(3):
+            lv.append(tuple(d // 2 for d in lv[-1]))
+        if min(lv[3]) < 1:
+            raise ValueError(f"input spatial size {dims} is too small for three 2x poolings")
+        self.level_dims = lv
+        z = lambda *s: torch.zeros(*s, dtype=dtype, device=device)
+        emp = lambda *s: torch.empty(*s, dtype=dtype, device=device)
+        # concat buffers [up | skip]; zero-initialised once: the centre-pad rim (odd sizes) stays zero
+        self.cat = {0: z(N, *lv[0], 2 * e[0]), 1: z(N, *lv[1], 2 * e[1]), 2: z(N, *lv[2], 2 * e[2])}
+        self.pooled = {0: emp(N, *lv[1], e[0]), 1: emp(N, *lv[2], e[1]), 2: emp(N, *lv[3], e[2])}
+        self.blocks: Dict[str, dict] = {}
+        n_stats = 0
+        for b in plan.blocks:
+            d = lv[b.level]
+            buf = {"t1": emp(N, *d, b.cout), "t2": emp(N, *d, b.cout)}
+            if b.cin != b.cout:
+                buf["r"] = emp(N, *d, b.cout)
+            if training and b.kind1 == "dws":
+                buf["u1"] = emp(N, *d, b.cin)
+            if training and b.kind2 == "dws":
+                buf["u2"] = emp(N, *d, b.cout)
+            if b.name in ("down3", "bottleneck", "up1", "up2") or (b.name == "up3" and training):
+                buf["out"] = emp(N, *d, b.cout)
+            buf["stats_off"] = n_stats
+            n_stats += 3 * 2 * N * b.cout
+            self.blocks[b.name] = buf
+        self.stats = torch.zeros(n_stats, dtype=torch.float64, device=device)
+        self.generation = 0
+        self.prob_out = None
+        self.logits = None
+
+    def stats_of(self, name: str, which: int, cout: int) -> torch.Tensor:
+        off = self.blocks[name]["stats_off"] + which * 2 * self.N * cout
+        return self.stats[off: off + 2 * self.N * cout]
+
+
+class UNetPlan:
+    def __init__(self, in_channels: int, out_channels: int, enc: Sequence[int], dws: bool, grouped: bool, groups: int):
+        if len(enc) != 4:
+            raise ValueError("encoder_channels must have 4 entries")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.enc = list(enc)
+        self.dws, self.grouped, self.groups = dws, grouped, groups
+        self.blocks = make_block_specs(in_channels, enc, dws, grouped, groups)
+        self._ws: Dict[tuple, Workspace] = {}
+
+    # ------------------------------------------------------------------ workspace
+    def workspace(self, N, dims, dtype, device, training) -> Workspace:
+        key = (N, tuple(dims), dtype, str(device), training)
+        ws = self._ws.get(key)
+        if ws is None:
+            if len(self._ws) > 8:
+                self._ws.clear()
+            ws = Workspace(self, N, tuple(dims), dtype, device, training)
+            self._ws[key] = ws
+        return ws
+
+    # -------------------------------------------------------------------- forward
+    def _conv(self, P, b: BlockSpec, which: int, x_act, xn, N, dims, t, t_stats, sc_w, r, r_stats, u, st):
+        """conv1 / conv2 of a residual block (+ fused shortcut where the kernel supports it)."""
+        kind = b.kind1 if which == 1 else b.kind2
+        pre = f"{b.prefix}.conv{which}"
+        D, H, W = dims
+        if kind == "dws":
+            nv.call("l3d_dwpw_fwd", x_act, xn, N, D, H, W, nv.ptr(P[f"{pre}.depthwise.weight"]),
+                    nv.ptr(P[f"{pre}.pointwise.weight"]), nv.ptr(sc_w), nv.act(t), nv.ptr(t_stats),
+                    nv.act(r), nv.ptr(r_stats), nv.act(u), st)
+        else:
+            w = P[f"{pre}.conv.weight"] if kind == "grouped" else P[f"{pre}.weight"]
+            g = self.groups if kind == "grouped" else 1
+            nv.call("l3d_conv3_fwd", x_act, xn, N, D, H, W, nv.ptr(w), g, nv.act(t), nv.ptr(t_stats), st)
+            if sc_w is not None:   # pointwise-only launch for the shortcut
+                nv.call("l3d_dwpw_fwd", x_act, xn, N, D, H, W, None, nv.ptr(sc_w), None, nv.act(r), nv.ptr(r_stats),
+                        nv.act(None), None, nv.act(None), st)
+
+    def forward(self, P: Dict[str, torch.Tensor], x_cl: torch.Tensor, training: bool,
+                masks: Optional[List[Optional[torch.Tensor]]] = None,
+                prob_out: Optional[torch.Tensor] = None) -> Workspace:
+        """x_cl: [N, D, H, W, Cin] channels-last activation-dtype tensor.  Returns the workspace holding
+        `prob` ([N, OC, D, H, W] fp32) and, in training mode, everything the backward pass needs."""
+        nv.require_cuda(x_cl, "UNetPlan.forward")
+        N, D, H, W, _ = x_cl.shape
+        ws = self.workspace(N, (D, H, W), x_cl.dtype, x_cl.device, training)
+        ws.x = x_cl
+        ws.masks = masks
+        ws.generation += 1
+        # fresh output tensors every call: the caller owns them (workspace buffers are reused by the next forward)
+        if prob_out is None:
+            prob_out = torch.empty(N, self.out_channels, D, H, W, dtype=torch.float32, device=x_cl.device)
+        assert prob_out.is_contiguous() and prob_out.dtype == torch.float32 and prob_out.numel() == N * self.out_channels * D * H * W
+        ws.prob_out = prob_out
+        ws.logits = torch.empty_like(ws.prob_out) if training else None
+        ws.stats.zero_()
+        st = nv.stream_ptr(x_cl.device)
+        ident = nv.norm()
+        cur = x_cl                       # materialised activation feeding the next block
+        cur_off, cur_C = 0, x_cl.shape[-1]
+        for i, b in enumerate(self.blocks):
+            dims = ws.level_dims[b.level]
+            vox = dims[0] * dims[1] * dims[2]
+            buf = ws.blocks[b.name]
+            mask = masks[i] if (masks is not None and masks[i] is not None) else None
+            if b.name.startswith("up"):
+                # transposed conv into the lower half of the concat buffer, then the block reads the whole buffer
+                cat = ws.cat[b.level]
+                lo = ws.level_dims[b.level + 1]
+                off = [(dims[k] - 2 * lo[k]) // 2 for k in range(3)]
+                nv.call("l3d_convt_fwd", nv.act(cur, cur_off, cur_C), N, lo[0], lo[1], lo[2],
+                        nv.ptr(P[f"{b.name}.up.weight"]), nv.ptr(P[f"{b.name}.up.bias"]),
+                        nv.act(cat, 0, b.cin // 2), dims[0], dims[1], dims[2], off[0], off[1], off[2], st)
+                cur, cur_off, cur_C = cat, 0, b.cin
+            x_act = nv.act(cur, cur_off, cur_C)
+            has_sc = b.cin != b.cout
+            s1, s2, sr = (ws.stats_of(b.name, k, b.cout) for k in range(3))
+            sc_w = P[f"{b.prefix}.shortcut.0.weight"] if has_sc else None
+            # conv1 (+ shortcut conv) on the block input
+            self._conv(P, b, 1, x_act, ident, N, dims, buf["t1"], s1, sc_w, buf.get("r"), sr if has_sc else None,
+                       buf.get("u1"), st)
+            # conv2 on lrelu(IN1(t1)) * dropout-mask, applied on load
+            n1 = nv.norm(s1, P[f"{b.prefix}.norm1.weight"], P[f"{b.prefix}.norm1.bias"], mask, IN_EPS, LEAKY_SLOPE, vox)
+            self._conv(P, b, 2, nv.act(buf["t1"]), n1, N, dims, buf["t2"], s2, None, None, None, buf.get("u2"), st)
+            # residual merge (+ pool / head)
+            n2 = nv.norm(s2, P[f"{b.prefix}.norm2.weight"], P[f"{b.prefix}.norm2.bias"], None, IN_EPS, 1.0, vox)
+            if has_sc:
+                r_act = nv.act(buf["r"])
+                nr = nv.norm(sr, P[f"{b.prefix}.shortcut.1.weight"], P[f"{b.prefix}.shortcut.1.bias"], None, IN_EPS, 1.0, vox)
+            else:
+                r_act, nr = x_act, ident
+            if b.name in ("init_conv", "down1", "down2"):
+                cat = ws.cat[b.level]
+                out_t, out_off = cat, b.cout                      # upper half of the concat buffer
+                nv.call("l3d_merge_fwd", nv.act(buf["t2"]), n2, r_act, nr, N, *dims, LEAKY_SLOPE,
+                        nv.act(cat, b.cout, b.cout), nv.act(ws.pooled[b.level]), None, None, 0, None, None, st)
+                cur, cur_off, cur_C = ws.pooled[b.level], 0, b.cout
+            elif b.name == "up3":
+                out = buf.get("out")
+                nv.call("l3d_merge_fwd", nv.act(buf["t2"]), n2, r_act, nr, N, *dims, LEAKY_SLOPE,
+                        nv.act(out), nv.act(None), nv.ptr(P["out_conv.weight"]), nv.ptr(P["out_conv.bias"]),
+                        self.out_channels, nv.ptr(ws.prob_out), nv.ptr(ws.logits), st)
+            else:
+                nv.call("l3d_merge_fwd", nv.act(buf["t2"]), n2, r_act, nr, N, *dims, LEAKY_SLOPE,
+                        nv.act(buf["out"]), nv.act(None), None, None, 0, None, None, st)
+                cur, cur_off, cur_C = buf["out"], 0, b.cout
+        return ws

@@ -1,0 +1,162 @@
+"""Sliding-window inference -- drop-in for light_unet/utils.py.
+
+sliding_window_inference_3d keeps the reference signature and return type
+(utils.py:11-139) but runs as a device-resident pipeline:
+
+  volume H2D once -> window gather kernel (zero-padded batches) -> batched
+  U-Net forward (libl3d) -> per-voxel Gaussian-weighted gather-stitch kernel
+  (same z->y->x accumulation order and fp32 rounding as utils.py:133-137)
+  -> one D2H copy of the stitched map.
+
+The reference does one H2D, ~100 launches, one blocking D2H and a NumPy
+read-modify-write per window (utils.py:115-134).
+"""
+from __future__ import annotations
+
+from pathlib import Path
+from typing import List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _native as nv
+
+WINDOW_BATCH = 16          # windows per forward launch sequence (workspace is sized for this)
+_GAUSS_CACHE = {}
+
+
+def _axis_positions(dim: int, patch: int, overlap: float) -> List[int]:
+    """Window start offsets along one axis: stride max(1, int(p*(1-overlap))) (utils.py:47-49), regular grid
+    plus a tail window flush with the far edge when uncovered (:63-73), [0] when dim < patch (:76-81)."""
+    stride = max(1, int(patch * (1 - overlap)))
+    pos = list(range(0, max(0, dim - patch + 1), stride)) if dim >= patch else []
+    if dim > patch and (not pos or pos[-1] + patch < dim):
+        pos.append(dim - patch)
+    return pos or [0]
+
+
+def window_positions(shape: Sequence[int], patch_size: Sequence[int], overlap: float):
+    return tuple(_axis_positions(int(d), int(p), overlap) for d, p in zip(shape, patch_size))
+
+
+def _get_gaussian_importance_map(patch_size: Tuple[int, int, int]) -> np.ndarray:
+    """Separable Gaussian blending weights, float64 math then fp32 (utils.py:142-173): per axis
+    exp(-(i - L/2)^2 / (2 (L/6)^2)), outer product, divided by its maximum."""
+    axes = []
+    for length in patch_size:
+        i = np.arange(length)
+        axes.append(np.exp(-((i - length / 2.0) ** 2) / (2 * (length / 6.0) ** 2)))
+    m = axes[0][:, None, None] * axes[1][None, :, None] * axes[2][None, None, :]
+    return (m / m.max()).astype(np.float32)
+
+
+def _importance_on_device(patch_size, use_gaussian: bool, device) -> torch.Tensor:
+    key = (tuple(int(p) for p in patch_size), bool(use_gaussian), str(device))
+    t = _GAUSS_CACHE.get(key)
+    if t is None:
+        host = _get_gaussian_importance_map(key[0]) if use_gaussian else np.ones(key[0], dtype=np.float32)
+        t = torch.from_numpy(host).to(device)
+        _GAUSS_CACHE[key] = t
+    return t
+
+
+def _is_native_model(model) -> bool:
+    from .models.unet3d import Lightweight3DUNet
+    return isinstance(model, Lightweight3DUNet)
+
+
+@torch.no_grad()
+def sliding_window_device(volume: torch.Tensor, model, patch_size=(48, 48, 48), overlap: float = 0.5,
+                          use_gaussian: bool = True, body_mask: Optional[torch.Tensor] = None,
+                          threshold: Optional[float] = None, window_batch: Optional[int] = None):
+    """Device-resident core: `volume` is a CUDA fp32 [D, H, W] tensor; returns (prob [D,H,W] fp32 CUDA,
+    mask int32 [D,H,W] or None).  `threshold` fuses `prob >= threshold` (inferencer.py:64) into the stitch."""
+    nv.require_cuda(volume, "sliding_window_device")
+    dev = volume.device
+    D, H, W = volume.shape
+    pd, ph, pw = (int(p) for p in patch_size)
+    zpos, ypos, xpos = window_positions((D, H, W), (pd, ph, pw), overlap)
+    pos = torch.tensor([(z, y, x) for z in zpos for y in ypos for x in xpos], dtype=torch.int32)
+    nwin = pos.shape[0]
+    pos_d = pos.to(dev, non_blocking=True)
+    zp = torch.tensor(zpos, dtype=torch.int32).to(dev, non_blocking=True)
+    yp = torch.tensor(ypos, dtype=torch.int32).to(dev, non_blocking=True)
+    xp = torch.tensor(xpos, dtype=torch.int32).to(dev, non_blocking=True)
+    imp = _importance_on_device((pd, ph, pw), use_gaussian, dev)
+    st = nv.stream_ptr(dev)
+    vol = volume.contiguous()
+    native = _is_native_model(model)
+    if native and model.out_channels != 1:
+        raise ValueError("Expected 3D model output, got a multi-channel prediction")     # utils.py:122-123
+    preds = torch.empty(nwin, 1, pd, ph, pw, dtype=torch.float32, device=dev)
+    wb = int(window_batch or WINDOW_BATCH)
+    model.eval()                                     # utils.py:84 (the reference leaves the model in eval mode)
+    if native:
+        P = dict(model.named_parameters())
+        dt = model.compute_dtype
+        for p in P.values():
+            nv.require_cuda(p, "sliding_window_inference_3d: model parameters")
+        for s in range(0, nwin, wb):
+            n = min(wb, nwin - s)
+            batch = torch.empty(n, pd, ph, pw, 1, dtype=dt, device=dev)
+            nv.call("l3d_gather_windows", nv.ptr(vol), D, H, W, nv.ptr(pos_d[s:]), n, pd, ph, pw, nv.ptr(batch),
+                    nv.dtype_code(dt), st)
+            model._plan.forward(P, batch, False, None, prob_out=preds[s:s + n])
+    else:
+        # any other torch module: batched forward on the device, stitched by the same kernel
+        for s in range(0, nwin, wb):
+            n = min(wb, nwin - s)
+            batch = torch.empty(n, pd, ph, pw, 1, dtype=torch.float32, device=dev)
+            nv.call("l3d_gather_windows", nv.ptr(vol), D, H, W, nv.ptr(pos_d[s:]), n, pd, ph, pw, nv.ptr(batch),
+                    nv.L3D_F32, st)
+            out = model(batch.view(n, 1, pd, ph, pw))
+            if out.dim() != 5 or out.shape[1] != 1:
+                raise ValueError(f"Expected 3D model output, got shape {tuple(out.shape[1:])}")
+            preds[s:s + n] = out.float()
+    prob = torch.empty(D, H, W, dtype=torch.float32, device=dev)
+    mask = torch.empty(D, H, W, dtype=torch.int32, device=dev) if threshold is not None else None
+    bm = None
+    if body_mask is not None:
+        bm = body_mask.to(device=dev, dtype=torch.uint8).contiguous()
+    nv.call("l3d_stitch", nv.ptr(preds), nv.ptr(zp), len(zpos), nv.ptr(yp), len(ypos), nv.ptr(xp), len(xpos),
+            pd, ph, pw, nv.ptr(imp), D, H, W, nv.ptr(bm), nv.ptr(prob),
+            float(np.float32(threshold)) if threshold is not None else 0.0, nv.ptr(mask), st)
+    return prob, mask
+
+
+def sliding_window_inference_3d(image: np.ndarray, model: torch.nn.Module, patch_size: Tuple[int, int, int] = (48, 48, 48),
+                                overlap: float = 0.5, device: torch.device = None,
+                                use_gaussian: bool = True) -> np.ndarray:
+    """Reference-compatible entry point (utils.py:11-139): host ndarray in, host fp32 [D,H,W] ndarray out."""
+    if device is None:
+        device = next(model.parameters()).device                                         # utils.py:33-34
+    device = torch.device(device)
+    if isinstance(image, torch.Tensor):
+        image = image.detach().cpu().numpy()
+    if len(image.shape) == 4 and image.shape[0] == 1:                                     # utils.py:37-38
+        image = image[0]
+    if len(image.shape) != 3:
+        raise ValueError(f"Expected 3D image [D, H, W], got shape {image.shape}")        # utils.py:40-41
+    if device.type != "cuda":
+        raise nv.NativeError("sliding_window_inference_3d: the B200-native path needs a CUDA device (no CPU fallback)")
+    host = torch.from_numpy(np.ascontiguousarray(image, dtype=np.float32))
+    vol = host.to(device, non_blocking=True)
+    prob, _ = sliding_window_device(vol, model, patch_size, overlap, use_gaussian)
+    return prob.cpu().numpy()
+
+
+def find_case_files(base_dir: Union[Path, str], case_id: str, file_type: str = "image") -> List[Path]:
+    """Filesystem helper kept for API compatibility (utils.py:176-207): sorted image (`<id>_*.nii[.gz]` under
+    images/) or label (`<id>.nii[.gz]` under labels/) paths."""
+    base = Path(base_dir)
+    if file_type == "image":
+        sub, pats = base / "images", [f"{case_id}_*.nii.gz", f"{case_id}_*.nii"]
+    elif file_type == "label":
+        sub, pats = base / "labels", [f"{case_id}.nii.gz", f"{case_id}.nii"]
+    else:
+        raise ValueError(f"Invalid file_type: {file_type}. Must be 'image' or 'label'")
+    found: List[Path] = []
+    if sub.exists():
+        for pat in pats:
+            found.extend(sub.glob(pat))
+    return sorted(found)

@@ -301,7 +301,22 @@ def bbox_cases():
     print("bbox: ok")
 
 
+def default_init_case():
+    """Seeded default initialisation of the reference module tree: the drop-in creates the same torch.nn layers
+    in the same order, so its parameters must be identical under the same seed."""
+    rec = {}
+    for tag, kw in [("dws", {}), ("grouped", dict(use_depthwise_separable=False)),
+                    ("dense", dict(use_depthwise_separable=False, use_grouped=False))]:
+        torch.manual_seed(1234)
+        m = RefUNet(**kw)
+        rec[tag] = {k: [float(v.double().sum()), float(v.double().abs().sum())] for k, v in m.state_dict().items()}
+    with open(os.path.join(HERE, "default_init.json"), "w") as f:
+        json.dump(rec, f)
+    print("default init: ok")
+
+
 def main():
+    default_init_case()
     C = unet_ref.UNetCfg
     unet_case("dws_16", C(dropout_p=0.3), 16, 2, wseed=1, xseed=11, train_seed=123)
     unet_case("dws_24", C(dropout_p=0.0), 24, 1, wseed=2, xseed=12, train_seed=5)

@@ -1,0 +1,206 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the oracle and the reference fixtures.
+
+Tolerances (BASELINE.json north_star): probabilities / logits within 1e-2 relative in bf16 storage mode and 1e-4
+in fp32 storage mode; loss within 1e-4; masks, labels and bounding boxes bit-exact given identical probabilities.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, UNET_CASES, load_unet_case, sub
+from oracle import bbox_ref, loss_ref, stitch_ref, synth, unet_ref
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def build_model(cfg, sd_np, dtype):
+    from light_unet.models import Lightweight3DUNet
+    m = Lightweight3DUNet(in_channels=cfg.in_channels, out_channels=cfg.out_channels,
+                          encoder_channels=list(cfg.encoder_channels),
+                          use_depthwise_separable=cfg.use_depthwise_separable, use_grouped=cfg.use_grouped,
+                          groups=cfg.groups, dropout_p=cfg.dropout_p)
+    m.load_state_dict(unet_ref.to_torch(sd_np))
+    return m.to(DEV).set_compute_dtype(dtype)
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.sqrt(((a - b) ** 2).sum()) / (np.sqrt((b ** 2).sum()) + 1e-30))
+
+
+def logit(p):
+    p = np.clip(np.asarray(p, dtype=np.float64), 1e-12, 1 - 1e-12)
+    return np.log(p / (1 - p))
+
+
+@pytest.mark.parametrize("dtype,tol_rel,tol_abs", [("f32", 1e-4, 2e-4), ("bf16", 1e-2, 4e-2)])
+@pytest.mark.parametrize("name", UNET_CASES)
+def test_unet_eval_forward(name, dtype, tol_rel, tol_abs):
+    z, meta, cfg, sd_np, x, t = load_unet_case(name)
+    model = build_model(cfg, sd_np, dtype).eval()
+    with torch.no_grad():
+        y = model(torch.from_numpy(x).to(DEV))
+    assert y.dtype == torch.float32 and tuple(y.shape) == x.shape and y.is_contiguous()
+    y = y.cpu().numpy()
+    s = meta["subsample"]
+    ref = z["prob_eval_sub"] if s else z["prob_eval"]
+    ref_logit = z["logit_eval_sub"] if s else z["logit_eval"]
+    got = sub(y, s)
+    e_rel, e_abs, e_logit = rel_l2(got, ref), np.abs(got - ref).max(), rel_l2(logit(got), ref_logit)
+    print(f"{name}/{dtype}: prob rel-L2 {e_rel:.3e} max-abs {e_abs:.3e} logit rel-L2 {e_logit:.3e}")
+    assert e_rel < tol_rel and e_logit < tol_rel * 2 and e_abs < tol_abs
+    # loss through the CUDA loss kernel on the CUDA probabilities
+    from light_unet.models import FocalTverskyLoss
+    loss = FocalTverskyLoss()(torch.from_numpy(y).to(DEV), torch.from_numpy(t).to(DEV)).item()
+    assert abs(loss - float(z["loss_eval"])) < 1e-4
+
+
+def test_focal_tversky_loss_and_grad():
+    from light_unet.models import FocalTverskyLoss
+    z = np.load(os.path.join(GOLDEN, "loss.npz"))
+    rng = np.random.default_rng(5)
+    p_np = rng.random((2, 1, 12, 10, 14), dtype=np.float32)
+    t_np = (rng.random((2, 1, 12, 10, 14)) > 0.9).astype(np.float32)
+    for i in range(3):
+        a, b, g = (float(v) for v in z[f"abg{i}"])
+        p = torch.from_numpy(p_np).to(DEV).requires_grad_(True)
+        loss = FocalTverskyLoss(alpha=a, beta=b, gamma=g)(p, torch.from_numpy(t_np).to(DEV))
+        assert loss.dim() == 0
+        loss.backward()
+        assert abs(loss.item() - float(z[f"loss{i}"])) < 1e-6
+        ref_g = z[f"grad{i}"]
+        assert np.abs(p.grad.cpu().numpy() - ref_g).max() < 1e-5 * np.abs(ref_g).max()
+    for j, tv in enumerate((0.0, 1.0)):
+        pp = torch.from_numpy(z[f"edge_p{j}"]).to(DEV)
+        l = FocalTverskyLoss()(pp, torch.full_like(pp, tv)).item()
+        assert abs(l - float(z[f"edge_loss{j}"])) < 1e-6
+    # large, odd-sized, unaligned view: sums against float64 numpy
+    n = 3 * 110592 + 13
+    p_np = rng.random(n + 1, dtype=np.float32)[1:]
+    t_np = (rng.random(n) > 0.98).astype(np.float32)
+    l64, g64 = loss_ref.focal_tversky_closed_form_grad(p_np, t_np)
+    p = torch.from_numpy(np.concatenate([[0.0], p_np]).astype(np.float32)).to(DEV)[1:].requires_grad_(True)
+    loss = FocalTverskyLoss()(p, torch.from_numpy(t_np).to(DEV))
+    loss.backward()
+    assert abs(loss.item() - l64) < 1e-6
+    assert np.abs(p.grad.cpu().numpy() - g64).max() < 1e-5 * np.abs(g64).max()
+
+
+def test_stitch_is_bit_exact_given_identical_predictions():
+    from light_unet import _native as nv
+    from light_unet.utils import window_positions, _get_gaussian_importance_map
+    rng = np.random.default_rng(3)
+    for shape, patch, ov, gauss in [((20, 28, 36), (16, 16, 16), 0.5, True), ((12, 28, 20), (16, 16, 16), 0.5, True),
+                                    ((33, 17, 40), (16, 16, 16), 0.75, True), ((24, 24, 24), (16, 16, 16), 0.25, False),
+                                    ((50, 48, 100), (48, 48, 48), 0.5, True)]:
+        pos = window_positions(shape, patch, ov)
+        nwin = len(pos[0]) * len(pos[1]) * len(pos[2])
+        preds = rng.random((nwin,) + patch, dtype=np.float32)
+        want = stitch_ref.stitch(shape, patch, pos, preds, gauss)
+        imp = _get_gaussian_importance_map(patch) if gauss else np.ones(patch, np.float32)
+        d = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(DEV)
+        prob = torch.empty(shape, dtype=torch.float32, device=DEV)
+        mask = torch.empty(shape, dtype=torch.int32, device=DEV)
+        zp, yp, xp = (d(p, np.int32) for p in pos)
+        nv.call("l3d_stitch", nv.ptr(d(preds, np.float32)), nv.ptr(zp), len(pos[0]), nv.ptr(yp), len(pos[1]), nv.ptr(xp),
+                len(pos[2]), *patch, nv.ptr(d(imp, np.float32)), *shape, None, nv.ptr(prob), float(np.float32(0.5)),
+                nv.ptr(mask), nv.stream_ptr(torch.device(DEV)))
+        got = prob.cpu().numpy()
+        assert np.array_equal(got, want), (shape, np.abs(got - want).max())
+        assert np.array_equal(mask.cpu().numpy(), (want >= np.float32(0.5)).astype(np.int32))
+
+
+@pytest.mark.parametrize("dtype,tol", [("f32", 1e-4), ("bf16", 2e-2)])
+def test_sliding_window_matches_reference_fixture(dtype, tol):
+    from light_unet.utils import sliding_window_inference_3d
+    z = np.load(os.path.join(GOLDEN, "sliding_window.npz"))
+    cfg = unet_ref.UNetCfg(dropout_p=0.0)
+    model = build_model(cfg, synth.synth_state_dict(unet_ref.param_shapes(cfg), 3), dtype)
+    model.train()
+    for tag in "abc":
+        c = z[f"cfg_{tag}"]
+        shape, patch, ov, gauss = tuple(int(v) for v in c[:3]), tuple(int(v) for v in c[3:6]), float(c[6]), bool(c[7])
+        vol = synth.synth_volume(shape, seed=9, n_blobs=2)
+        got = sliding_window_inference_3d(vol, model, patch, ov, torch.device(DEV), gauss)
+        assert isinstance(got, np.ndarray) and got.dtype == np.float32 and got.shape == shape
+        err = np.abs(got - z[f"prob_{tag}"]).max()
+        print(f"sliding window {tag}/{dtype}: max abs err {err:.3e}")
+        assert err < tol
+    assert not model.training          # the reference leaves the model in eval mode (utils.py:84)
+    got4 = sliding_window_inference_3d(synth.synth_volume((20, 28, 36), seed=9, n_blobs=2)[None], model, (16, 16, 16), 0.5)
+    assert got4.shape == (20, 28, 36)
+
+
+def test_connected_components_bit_exact():
+    from light_unet.models.metrics import get_connected_components
+    rng = np.random.default_rng(0)
+    for shape, dens, min_size in [((9, 10, 11), 0.5, 0), ((17, 5, 23), 0.35, 3), ((1, 1, 7), 0.6, 0), ((4, 4, 4), 1.0, 8),
+                                  ((6, 6, 6), 0.0, 0), ((20, 21, 22), 0.45, 5), ((64, 64, 64), 0.3, 8),
+                                  ((40, 130, 70), 0.55, 20), ((128, 128, 320), 0.25, 8)]:
+        m = (rng.random(shape) < dens).astype(np.int32)
+        want, n_want = bbox_ref.connected_components(m.copy(), min_size)
+        got, n_got = get_connected_components(m, min_size=min_size)
+        assert got.dtype == np.int32 and n_got == n_want and np.array_equal(got, want), (shape, n_got, n_want)
+    # 2-D input keeps its shape (face connectivity)
+    m2 = (rng.random((30, 40)) < 0.5).astype(np.int32)
+    got, n = get_connected_components(m2)
+    want, n_want = bbox_ref.label6(m2[None])
+    assert n == n_want and np.array_equal(got, want[0])
+
+
+def test_extract_bboxes_bit_exact():
+    from light_unet.core.inferencer import Inferencer
+    with open(os.path.join(GOLDEN, "bbox.json")) as f:
+        fx = json.load(f)
+    inf = Inferencer.__new__(Inferencer)
+    inf.device = torch.device(DEV)
+    inf.config = {"data": {"bbox_expansion_voxels": 3}}
+    prob = np.zeros((20, 24, 28), dtype=np.float32)
+    prob[2:5, 3:6, 4:7] = 0.9
+    prob[10:12, 10:12, 10:12] = 0.31
+    prob[15, 15, 15] = 0.99
+    prob[18:20, 20:24, 25:28] = 0.3
+    prob[6, 6, 6] = 0.5
+    prob[7, 7, 7] = 0.5
+    assert inf.extract_bboxes(prob, threshold=0.3, min_volume_cc=0.5, spacing=(4.0, 4.0, 4.0)) == fx["kat"]
+    for tag, c in fx.items():
+        if tag == "kat":
+            continue
+        inf.config = {"data": {"bbox_expansion_voxels": c["expansion"]}}
+        prob = synth.synth_prob_map(tuple(c["shape"]), c["seed"])
+        got = inf.extract_bboxes(prob, threshold=c["threshold"], min_volume_cc=c["min_volume_cc"], spacing=tuple(c["spacing"]))
+        assert got == c["bboxes"], tag
+    # empty map
+    assert inf.extract_bboxes(np.zeros((8, 8, 8), np.float32)) == []
+    # full-size volume against the oracle
+    inf.config = {"data": {"bbox_expansion_voxels": 3}}
+    prob = synth.synth_prob_map((128, 128, 320), 21, n_blobs=40)
+    assert inf.extract_bboxes(prob, 0.3, 0.5, (4.0, 4.0, 4.0)) == bbox_ref.extract_bboxes(prob, 0.3, 0.5, (4.0, 4.0, 4.0), 3)
+
+
+def test_inferencer_end_to_end(tmp_path):
+    """Checkpoint written the way the reference's Trainer writes it -> Inferencer -> prob map + boxes."""
+    from light_unet.core.inferencer import Inferencer
+    cfg = unet_ref.UNetCfg(dropout_p=0.0)
+    sd_np = synth.synth_state_dict(unet_ref.param_shapes(cfg), 3)
+    ckpt = tmp_path / "best_model.pth"
+    torch.save({"epoch": 3, "model_state_dict": unet_ref.to_torch(sd_np), "best_epoch": 3, "best_metric": 0.5}, ckpt)
+    config = {"model": {"output_channels": 1, "start_channels": 16, "encoder_channels": [16, 32, 64, 128],
+                        "use_depthwise_separable": True, "use_grouped_conv": True, "groups": 8},
+              "output": {"prob_maps_dir": str(tmp_path / "prob"), "bboxes_dir": str(tmp_path / "bbox")},
+              "data": {"patch_size": [16, 16, 16], "bbox_expansion_voxels": 3, "volume_threshold": {"inference_cc": 0.5}},
+              "validation": {"default_threshold": 0.3}}
+    inf = Inferencer(config, str(ckpt))
+    inf.model.set_compute_dtype("f32")
+    vol = synth.synth_volume((20, 28, 36), seed=9, n_blobs=2)
+    prob, boxes = inf.infer_volume(vol, threshold=0.5, spacing=(4.0, 4.0, 4.0))
+    ref = np.load(os.path.join(GOLDEN, "sliding_window.npz"))["prob_a"]
+    assert np.abs(prob - ref).max() < 1e-4
+    # boxes must be exactly what the reference algorithm extracts from OUR probability map
+    assert boxes == bbox_ref.extract_bboxes(prob, 0.5, 0.5, (4.0, 4.0, 4.0), 3)
+    assert (tmp_path / "prob").is_dir() and (tmp_path / "bbox").is_dir()
