@@ -95,10 +95,45 @@ def lib():
     return L
 
 
+class KernelTimer:
+    """Optional per-entry-point device timing (CUDA events on the launching stream).  Used by bench.py to
+    measure the dominant kernel's average launch duration inside a profiled pass; off by default."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []   # (name, tag, start_event, stop_event)
+        self.tag = ""
+
+    def start(self):
+        self.records.clear()
+        self.enabled = True
+
+    def stop(self):
+        """-> {(name, tag): (launches, total_ms)}"""
+        self.enabled = False
+        torch.cuda.synchronize()
+        out = {}
+        for name, tag, e0, e1 in self.records:
+            n, ms = out.get((name, tag), (0, 0.0))
+            out[(name, tag)] = (n + 1, ms + e0.elapsed_time(e1))
+        self.records.clear()
+        return out
+
+
+TIMER = KernelTimer()
+
+
 def call(name: str, *args):
     """Invoke an entry point; non-zero status -> NativeError(l3d_last_error())."""
     L = lib()
-    rc = getattr(L, name)(*args)
+    if TIMER.enabled:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(L, name)(*args)
+        e1.record()
+        TIMER.records.append((name, TIMER.tag, e0, e1))
+    else:
+        rc = getattr(L, name)(*args)
     if rc != 0:
         raise NativeError(f"{name} failed ({rc}): {L.l3d_last_error().decode(errors='replace')}")
 

@@ -169,6 +169,7 @@ class UNetPlan:
         cur = x_cl                       # materialised activation feeding the next block
         cur_off, cur_C = 0, x_cl.shape[-1]
         for i, b in enumerate(self.blocks):
+            nv.TIMER.tag = b.name
             dims = ws.level_dims[b.level]
             vox = dims[0] * dims[1] * dims[2]
             buf = ws.blocks[b.name]
