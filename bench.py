@@ -1,0 +1,445 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native Light-3D-Unet hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--variant dws|grouped|dense] [--dtype bf16|f32] [--skip-train] [--skip-cpu]
+
+One JSON line on stdout (rank 0).  Metric (BASELINE.json): sliding-window inference volume-voxels/s on the
+synthetic whole-body 4 mm PET volume (128x128x320, 48^3 windows, 50 % overlap, Gaussian stitching, threshold
+-> connected components -> bounding boxes); the 48^3-patch training step (fwd + Focal Tversky + bwd + AdamW,
+batch 8 per GPU) is reported in the same line under "train".
+
+A "step" of the headline metric is one whole volume through the hot path.
+  value : volume-voxels/s with the volume already resident in HBM (device-timed, CUDA events, max over ranks)
+  e2e   : the same through the reference-facing API, Inferencer.infer_volume(host array): pinned H2D copy of the
+          volume and D2H read of the probability map + box table inside the timed region
+N > 1: one process per GPU (torchrun), volumes are independent -> every rank runs its own volumes, no data-path
+collective ("weak" scaling); training is data parallel with the gradient all-reduce over NCCL.
+--impl reference: the oracle's CPU restatement of the reference path (torch-CPU ATen kernels, all host threads)
+on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "light-3d-unet-front_b200")
+for p in (PKG, ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+VOLUME = (128, 128, 320)
+PATCH = (48, 48, 48)
+NVOX = VOLUME[0] * VOLUME[1] * VOLUME[2]
+NWIN = 5 * 5 * 13
+TRAIN_BATCH = 8
+VARIANTS = {"dws": dict(use_depthwise_separable=True, use_grouped=True),
+            "grouped": dict(use_depthwise_separable=False, use_grouped=True),
+            "dense": dict(use_depthwise_separable=False, use_grouped=False)}
+# compulsory activation elements per 48^3 patch (each tensor crossing an InstanceNorm
+# reduction written once + read once) and forward FLOP per patch
+ELEMS_PER_PATCH = 21.32e6
+FWD_FLOP = {"dws": 1.402e9, "grouped": 3.354e9, "dense": 12.47e9}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops_sustained"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 7:
+                    continue
+                sm.append(float(f[0]))
+                mx = float(f[1])
+                for nme, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def max_over_ranks(ms: float, world: int, device) -> float:
+    if world == 1:
+        return ms
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def timed(fn, steps, world, device):
+    """barrier+sync | K x fn on the current stream between two CUDA events | sync+barrier -> max-over-ranks ms"""
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    barrier(world)
+    return max_over_ranks(ms, world, device)
+
+
+# ------------------------------------------------------------------------------------------ ours
+def make_inferencer(variant, dtype, device):
+    from light_unet.core.inferencer import Inferencer
+    from oracle import synth, unet_ref   # synthetic weights only (shared seeded generator); not on the timed path
+    kw = VARIANTS[variant]
+    cfg = unet_ref.UNetCfg(dropout_p=0.0, **kw)
+    sd = unet_ref.to_torch(synth.synth_state_dict(unet_ref.param_shapes(cfg), 3))
+    d = tempfile.mkdtemp(prefix="l3d_bench_")
+    ckpt = os.path.join(d, "model.pth")
+    torch.save({"epoch": 0, "model_state_dict": sd, "best_epoch": 0, "best_metric": 0.0}, ckpt)
+    config = {"model": {"output_channels": 1, "start_channels": 16, "encoder_channels": [16, 32, 64, 128],
+                        "use_depthwise_separable": kw["use_depthwise_separable"], "use_grouped_conv": kw["use_grouped"],
+                        "groups": 8},
+              "output": {"prob_maps_dir": os.path.join(d, "prob"), "bboxes_dir": os.path.join(d, "bbox")},
+              "data": {"patch_size": list(PATCH), "bbox_expansion_voxels": 3, "volume_threshold": {"inference_cc": 0.5}},
+              "validation": {"default_threshold": 0.3}}
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        inf = Inferencer(config, ckpt)
+    inf.model.set_compute_dtype(dtype)
+    return inf
+
+
+def bench_ours(args):
+    from light_unet import _native as nv
+    from oracle import synth
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    inf = make_inferencer(args.variant, args.dtype, device)
+    # 8 distinct volumes (168 MB > the 126 MB L2) rotated between steps; every step also streams > 10 GB of
+    # activations through HBM, so no input survives in L2 from one step to the next
+    base = synth.synth_volume(VOLUME, seed=42 + rank, n_blobs=6)
+    host_vols = [torch.from_numpy(np.roll(base, 7 * i, axis=2).copy()).pin_memory() for i in range(8)]
+    dev_vols = [h.to(device) for h in host_vols]
+    nboxes = [0]
+
+    def step_resident(i):
+        prob, boxes = inf.infer_volume(dev_vols[i % 8], threshold=0.3, return_device=True)
+        nboxes[0] = len(boxes)
+
+    host_out = torch.empty(VOLUME, dtype=torch.float32).pin_memory()
+
+    def step_e2e(i):
+        prob, boxes = inf.infer_volume(host_vols[i % 8], threshold=0.3, return_device=True)
+        host_out.copy_(prob, non_blocking=False)
+        nboxes[0] = len(boxes)
+
+    for i in range(args.warmup):
+        step_resident(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = nv.launch_count()
+    ms = timed(step_resident, args.steps, world, device)
+    launches = nv.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    for i in range(max(1, args.warmup // 2)):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps, world, device)
+
+    # per-kernel device time (CUDA events around every libl3d launch, same stream) over one more volume
+    nv.TIMER.start()
+    step_resident(0)
+    rec = nv.TIMER.stop()
+    tot_ms = sum(v[1] for v in rec.values())
+    by_name = {}
+    for (name, tag), (n, t, b) in rec.items():
+        a = by_name.setdefault(name, [0, 0.0, 0])
+        a[0] += n; a[1] += t; a[2] += b
+    top = max(by_name.items(), key=lambda kv: kv[1][1])
+    pk = peaks()
+    es = 2 if args.dtype == "bf16" else 4
+    achieved = top[1][2] / (top[1][1] * 1e-3) / 1e9 if top[1][1] > 0 else 0.0
+    step_ms = ms / args.steps
+    roofline = {"bound": "hbm", "kernel": top[0], "achieved": round(achieved, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": None, "peak_source": pk["source"],
+                "launches_per_step": top[1][0], "avg_launch_us": round(1e3 * top[1][1] / top[1][0], 1),
+                "share_of_step": round(top[1][1] / tot_ms, 3),
+                "algorithmic_bytes_per_launch": int(top[1][2] / top[1][0]),
+                # whole-network view: compulsory activation bytes per volume / step time
+                "network": {"algorithmic_gb_per_step": round(NWIN * ELEMS_PER_PATCH * es / 1e9, 2),
+                            "achieved_gbs": round(NWIN * ELEMS_PER_PATCH * es / (step_ms * 1e-3) / 1e9, 1),
+                            "frac_hbm": round(NWIN * ELEMS_PER_PATCH * es / (step_ms * 1e-3) / 1e9 / pk["hbm_gbs"], 4),
+                            "tflops": round(NWIN * FWD_FLOP[args.variant] / (step_ms * 1e-3) / 1e12, 2),
+                            "frac_tensor": round(NWIN * FWD_FLOP[args.variant] / (step_ms * 1e-3) / 1e12 / pk["bf16_tflops"], 4)},
+                "kernels": {k: {"launches": v[0], "ms": round(v[1], 3), "share": round(v[1] / tot_ms, 3),
+                                "gbs": round(v[2] / max(v[1], 1e-9) / 1e6, 1)} for k, v in
+                            sorted(by_name.items(), key=lambda kv: -kv[1][1])}}
+
+    train = None
+    if not args.skip_train:
+        train = bench_train(args, device, rank, world)
+
+    cpu = None
+    if rank == 0 and not args.skip_cpu:
+        cpu = cpu_baseline(args.variant, target_s=12.0)
+
+    if rank == 0:
+        line = {"metric": "sliding-window inference volume-voxels/s", "value": round(world * NVOX * args.steps / (ms * 1e-3), 1),
+                "unit": "voxels/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": round(step_ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": "configs[2]: sliding-window inference, synthetic whole-body PET 128x128x320 @4mm, "
+                                       "48^3 windows, 50% overlap (325 windows), Gaussian stitch, threshold 0.3 -> CC -> bbox",
+                           "variant": args.variant, "params": {"dws": 217228, "grouped": 391521, "dense": 2308737}[args.variant],
+                           "volumes_per_step_per_gpu": 1, "window_batch": window_batch(),
+                           "l2": "inputs rotate over 8 volumes (168 MB) and each step streams >10 GB of activations (> 126 MB L2)",
+                           "parallelism": f"volume-sharded x{world}", "boxes_found": nboxes[0]},
+                "e2e": {"value": round(world * NVOX * args.steps / (ms_e2e * 1e-3), 1), "unit": "voxels/s",
+                        "ms_per_step": round(ms_e2e / args.steps, 3),
+                        "h2d_bytes_per_step": NVOX * 4, "d2h_bytes_per_step": NVOX * 4 + 4 + 32 * max(nboxes[0], 1)},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+        if train is not None:
+            line["train"] = train
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def window_batch():
+    import light_unet.utils as lu
+    return lu.WINDOW_BATCH
+
+
+def bench_train(args, device, rank, world):
+    """configs[1]/[3]: training step on 48^3 patches, batch 8 per GPU, data parallel over NCCL when world > 1."""
+    from light_unet.models import Lightweight3DUNet, FocalTverskyLoss
+    from light_unet.engine import UNetPlan
+    if not hasattr(UNetPlan, "backward"):
+        return {"unavailable": "backward kernels not built in this revision"}
+    from light_unet.parallel import DataParallelStep
+    from oracle import synth, unet_ref
+    kw = VARIANTS[args.variant]
+    cfg = unet_ref.UNetCfg(dropout_p=0.1, **kw)
+    model = Lightweight3DUNet(dropout_p=0.1, **kw)
+    model.load_state_dict(unet_ref.to_torch(synth.synth_state_dict(unet_ref.param_shapes(cfg), 1)))
+    model = model.to(device).set_compute_dtype(args.dtype).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5, fused=True)     # trainer.py:75-79
+    stepper = DataParallelStep(model, FocalTverskyLoss(), opt, world_size=world)
+    B = TRAIN_BATCH
+    hx, ht = [], []
+    for i in range(4):
+        x, t = synth.synth_patches(B, 48, seed=100 + 17 * rank + i)
+        hx.append(torch.from_numpy(x).pin_memory())
+        ht.append(torch.from_numpy(t).pin_memory())
+    dx, dtg = [h.to(device) for h in hx], [h.to(device) for h in ht]
+    last = [None]
+
+    def step_resident(i):
+        last[0] = stepper.step(dx[i % 4], dtg[i % 4])
+
+    def step_e2e(i):
+        x = hx[i % 4].to(device, non_blocking=True)
+        t = ht[i % 4].to(device, non_blocking=True)
+        last[0] = stepper.step(x, t).item()         # trainer.py:234 reads the loss every step
+
+    steps = max(args.steps * 4, 10)
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    ms = timed(step_resident, steps, world, device)
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, steps, world, device)
+    pk = peaks()
+    es = 2 if args.dtype == "bf16" else 4
+    per_step_s = ms * 1e-3 / steps
+    return {"metric": "train 48^3 patches/s", "value": round(world * B * steps / (ms * 1e-3), 1), "unit": "patches/s",
+            "ms_per_step": round(ms / steps, 3), "steps": steps, "global_batch": world * B,
+            "workload": "configs[1]: fwd + FocalTversky + bwd + AdamW(lr 1e-4, wd 1e-5), dropout 0.1, batch 8 of 48^3 per GPU",
+            "parallelism": f"dp{world}", "loss": float(last[0]) if last[0] is not None else None,
+            "e2e": {"value": round(world * B * steps / (ms_e2e * 1e-3), 1), "unit": "patches/s",
+                    "h2d_bytes_per_step": 2 * B * 48 ** 3 * 4, "d2h_bytes_per_step": 4},
+            # forward compulsory traffic x3 (fwd + ~2x for bwd), SURVEY 8(d)
+            "frac_hbm": round(3 * B * ELEMS_PER_PATCH * es / per_step_s / 1e9 / pk["hbm_gbs"], 4)}
+
+
+# ----------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_setup(variant):
+    from oracle import synth, unet_ref
+    cfg = unet_ref.UNetCfg(dropout_p=0.0, **VARIANTS[variant])
+    sd = unet_ref.to_torch(synth.synth_state_dict(unet_ref.param_shapes(cfg), 3))
+    return cfg, sd
+
+
+def cpu_sample(cfg, sd, vol):
+    """The reference algorithm (utils.py:86-137, one batch-1 forward per window; inferencer.py:62-111) on a
+    sub-volume, through the oracle's restatement (torch CPU ATen kernels, all host threads)."""
+    from oracle import bbox_ref, stitch_ref, unet_ref
+
+    def predict(chunk):
+        with torch.no_grad():
+            return unet_ref.forward(sd, torch.from_numpy(chunk), cfg).numpy()
+    prob = stitch_ref.sliding_window(vol, predict, PATCH, 0.5, True, batch=1)
+    boxes = bbox_ref.extract_bboxes(prob, 0.3, 0.5, (4.0, 4.0, 4.0), 3)
+    return prob, boxes
+
+
+def cpu_baseline(variant, target_s=12.0):
+    from oracle import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg, sd = cpu_reference_setup(variant)
+    full = synth.synth_volume(VOLUME, seed=42, n_blobs=6)
+    small = np.ascontiguousarray(full[:48, :48, :96])          # 1 x 1 x 3 windows: warm-up + rate estimate
+    cpu_sample(cfg, sd, small)
+    t0 = time.perf_counter()
+    cpu_sample(cfg, sd, small)
+    per_win = (time.perf_counter() - t0) / 3
+    # bounded sample: a z-slab of the same volume holding ~target_s of work (full y/x extent when affordable)
+    nwin_target = max(3, int(target_s / per_win))
+    if nwin_target >= 65:
+        sub, nwin = full[:48], 65                                # 1 x 5 x 13 windows
+    elif nwin_target >= 13:
+        ny = min(5, nwin_target // 13)
+        ext = 48 + 24 * (ny - 1) if ny < 5 else 128
+        sub, nwin = full[:48, :ext], ny * 13
+    else:
+        nx = max(3, nwin_target)
+        sub, nwin = full[:48, :48, :48 + 24 * (nx - 1)], nx
+    sub = np.ascontiguousarray(sub)
+    t0 = time.perf_counter()
+    cpu_sample(cfg, sd, sub)
+    dt = time.perf_counter() - t0
+    vox_per_win = NVOX / NWIN                                    # the full volume costs 325 windows for 5.24 M voxels
+    return {"value": round(nwin / dt * vox_per_win, 1), "unit": "voxels/s", "cores": cores, "kind": "port",
+            "windows_per_s": round(nwin / dt, 2),
+            "sample": f"{nwin} of the 325 windows (sub-volume {tuple(sub.shape)} of the same synthetic volume), batch-1 "
+                      f"forward per window + stitch + bbox, torch CPU fp32 with {cores} threads, {dt:.1f} s; "
+                      f"voxels/s = windows/s x {vox_per_win:.0f} volume-voxels per window"}
+
+
+def bench_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    from oracle import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg, sd = cpu_reference_setup(args.variant)
+    full = synth.synth_volume(VOLUME, seed=42, n_blobs=6)
+    sub = np.ascontiguousarray(full[:48, :48, :144])            # 1 x 1 x 5 = 5 windows per step
+    nwin = 5
+    for _ in range(args.warmup):
+        cpu_sample(cfg, sd, sub)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_sample(cfg, sd, sub)
+    dt = time.perf_counter() - t0
+    vox_per_win = NVOX / NWIN
+    v = round(args.steps * nwin / dt * vox_per_win, 1)
+    sample = (f"each step = {nwin} of the 325 windows (sub-volume {tuple(sub.shape)}), batch-1 forward per window + stitch + "
+              f"bbox through the oracle port of the reference CPU path, torch CPU fp32, {cores} threads; voxels/s = "
+              f"windows/s x {vox_per_win:.0f}")
+    line = {"impl": "reference", "metric": "sliding-window inference volume-voxels/s", "value": v, "unit": "voxels/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * dt / args.steps, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[2]: sliding-window inference, synthetic whole-body PET 128x128x320 @4mm, "
+                                   "48^3 windows, 50% overlap (325 windows), Gaussian stitch, threshold 0.3 -> CC -> bbox",
+                       "variant": args.variant, "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--variant", default="dws", choices=sorted(VARIANTS))
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--skip-train", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        bench_reference(args)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback); use --impl reference for the CPU arm")
+    _, world, _ = dist_env()
+    if world != args.gpus:
+        if args.gpus > 1 and world == 1:
+            raise SystemExit("bench.py: launch N>1 with torchrun (python -m torch.distributed.run --nproc-per-node N ...)")
+    bench_ours(args)
+
+
+if __name__ == "__main__":
+    main()

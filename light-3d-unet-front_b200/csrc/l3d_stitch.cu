@@ -113,13 +113,19 @@ __global__ void __launch_bounds__(256) ccl_merge_kernel(int32_t *__restrict__ pa
     }
 }
 __global__ void __launch_bounds__(256) ccl_flatten_count_kernel(int32_t *__restrict__ parent, int32_t n, int32_t *__restrict__ size) {
-    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        if (parent[i] < 0) continue;
-        const int32_t r = uf_find(parent, i);
-        // roots keep parent[r] == r; non-roots may point at the root directly (no thread still needs the chain:
-        // every chain ends at r and a concurrent reader following a shortened link still arrives at r)
-        if (r != i) parent[i] = r;
-        atomicAdd(&size[r], 1);
+    // warp-uniform trip count so that the lanes can aggregate their size increments per root (a large
+    // component would otherwise serialise millions of atomics on one address)
+    const int32_t n_round = (n + 31) & ~31;
+    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        int32_t r = -1;
+        if (i < n && parent[i] >= 0) {
+            r = uf_find(parent, i);
+            // roots keep parent[r] == r; non-roots may point at the root directly (no thread still needs the chain:
+            // every chain ends at r and a concurrent reader following a shortened link still arrives at r)
+            if (r != i) parent[i] = r;
+        }
+        const unsigned peers = __match_any_sync(0xffffffffu, r);
+        if (r >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&size[r], __popc(peers));
     }
 }
 // flag[i] = 1 iff voxel i is the root of a surviving component
@@ -209,19 +215,60 @@ __global__ void bbox_init_kernel(int32_t *__restrict__ table, int cap) {
         t[7] = 0;  // bits of +0.0f; probabilities are >= 0 so the int ordering equals the float ordering
     }
 }
+// One thread walks BB_RUN consecutive voxels and keeps a private accumulator while the label does not change;
+// accumulators are merged across the warp per label (match.any + redux) before touching the table, so a large
+// component costs ~1/256th of the per-voxel atomics.
+constexpr int BB_RUN = 8;
+struct BoxAcc {
+    int32_t l, z0, z1, y0, y1, x0, x1, cnt, pb;
+};
+__device__ __forceinline__ void box_flush_warp(const BoxAcc &a, int32_t *__restrict__ table, int cap) {
+    const int32_t key = (a.l > 0 && a.l <= cap) ? a.l : 0;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int z0 = __reduce_min_sync(peers, a.z0), z1 = __reduce_max_sync(peers, a.z1);
+    const int y0 = __reduce_min_sync(peers, a.y0), y1 = __reduce_max_sync(peers, a.y1);
+    const int x0 = __reduce_min_sync(peers, a.x0), x1 = __reduce_max_sync(peers, a.x1);
+    const int cnt = __reduce_add_sync(peers, a.cnt), pb = __reduce_max_sync(peers, a.pb);
+    if (key > 0 && (threadIdx.x & 31) == __ffs(peers) - 1) {
+        int32_t *t = table + (size_t)(key - 1) * 8;
+        atomicMin(&t[0], z0); atomicMax(&t[1], z1);
+        atomicMin(&t[2], y0); atomicMax(&t[3], y1);
+        atomicMin(&t[4], x0); atomicMax(&t[5], x1);
+        atomicAdd(&t[6], cnt);
+        atomicMax(&t[7], pb);
+    }
+}
 __global__ void __launch_bounds__(256) bbox_reduce_kernel(const int32_t *__restrict__ labels, const float *__restrict__ prob,
                                                           int D, int H, int W, int32_t *__restrict__ table, int cap) {
-    const int32_t n = D * H * W;
-    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int32_t l = labels[i];
-        if (l <= 0 || l > cap) continue;
-        const int x = i % W, y = (i / W) % H, z = i / (W * H);
-        int32_t *t = table + (size_t)(l - 1) * 8;
-        atomicMin(&t[0], z); atomicMax(&t[1], z);
-        atomicMin(&t[2], y); atomicMax(&t[3], y);
-        atomicMin(&t[4], x); atomicMax(&t[5], x);
-        atomicAdd(&t[6], 1);
-        atomicMax(&t[7], __float_as_int(fmaxf(prob[i], 0.f)));
+    const int64_t n = (int64_t)D * H * W;
+    const int64_t nruns = (n + BB_RUN - 1) / BB_RUN;
+    const int64_t nruns_round = (nruns + 31) & ~(int64_t)31;
+    for (int64_t run = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; run < nruns_round; run += (int64_t)gridDim.x * blockDim.x) {
+        BoxAcc a;
+        a.l = 0; a.z0 = a.y0 = a.x0 = 0x7fffffff; a.z1 = a.y1 = a.x1 = -1; a.cnt = 0; a.pb = 0;
+        const int64_t i0 = run * BB_RUN;
+        for (int k = 0; k < BB_RUN; ++k) {           // same trip count on every lane: the flush is warp-collective
+            const int64_t i = i0 + k;
+            const int32_t l = (i < n) ? labels[i] : 0;
+            const bool change = (l != a.l) && a.cnt > 0;
+            if (__any_sync(0xffffffffu, change)) {
+                BoxAcc f = a;
+                if (!change) { f.l = 0; }
+                box_flush_warp(f, table, cap);
+                if (change) { a.z0 = a.y0 = a.x0 = 0x7fffffff; a.z1 = a.y1 = a.x1 = -1; a.cnt = 0; a.pb = 0; }
+            }
+            a.l = l;
+            if (l > 0) {
+                const int x = (int)(i % W), y = (int)((i / W) % H), z = (int)(i / ((int64_t)W * H));
+                a.z0 = min(a.z0, z); a.z1 = max(a.z1, z);
+                a.y0 = min(a.y0, y); a.y1 = max(a.y1, y);
+                a.x0 = min(a.x0, x); a.x1 = max(a.x1, x);
+                a.cnt += 1;
+                a.pb = max(a.pb, __float_as_int(fmaxf(prob[i], 0.f)));
+            }
+        }
+        if (a.cnt == 0) a.l = 0;
+        box_flush_warp(a, table, cap);
     }
 }
 
@@ -313,7 +360,7 @@ extern "C" int l3d_bbox_reduce(const int32_t *labels, const float *prob, int D, 
     L3D_REQUIRE(labels && prob && table && cap > 0, "l3d_bbox_reduce: bad argument");
     const int64_t n = (int64_t)D * H * W;
     L3D_REQUIRE(n > 0 && n < (1ll << 31), "l3d_bbox_reduce: volume too large");
-    bbox_reduce_kernel<<<grid_for(n, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(labels, prob, D, H, W, table, cap);
+    bbox_reduce_kernel<<<grid_for((n + BB_RUN - 1) / BB_RUN, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(labels, prob, D, H, W, table, cap);
     l3d_count_launch();
     L3D_CUDA_OK("l3d_bbox_reduce launch");
     return 0;

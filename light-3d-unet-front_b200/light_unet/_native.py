@@ -101,7 +101,7 @@ class KernelTimer:
 
     def __init__(self):
         self.enabled = False
-        self.records = []   # (name, tag, start_event, stop_event)
+        self.records = []   # (name, tag, start_event, stop_event, algorithmic bytes)
         self.tag = ""
 
     def start(self):
@@ -109,13 +109,13 @@ class KernelTimer:
         self.enabled = True
 
     def stop(self):
-        """-> {(name, tag): (launches, total_ms)}"""
+        """-> {(name, tag): (launches, total_ms, total algorithmic bytes)}"""
         self.enabled = False
         torch.cuda.synchronize()
         out = {}
-        for name, tag, e0, e1 in self.records:
-            n, ms = out.get((name, tag), (0, 0.0))
-            out[(name, tag)] = (n + 1, ms + e0.elapsed_time(e1))
+        for name, tag, e0, e1, nbytes in self.records:
+            n, ms, b = out.get((name, tag), (0, 0.0, 0))
+            out[(name, tag)] = (n + 1, ms + e0.elapsed_time(e1), b + nbytes)
         self.records.clear()
         return out
 
@@ -123,15 +123,16 @@ class KernelTimer:
 TIMER = KernelTimer()
 
 
-def call(name: str, *args):
-    """Invoke an entry point; non-zero status -> NativeError(l3d_last_error())."""
+def call(name: str, *args, algo_bytes: int = 0):
+    """Invoke an entry point; non-zero status -> NativeError(l3d_last_error()).  `algo_bytes` (the launch's
+    algorithmic HBM bytes: every operand read once, every result written once) is only recorded by TIMER."""
     L = lib()
     if TIMER.enabled:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = getattr(L, name)(*args)
         e1.record()
-        TIMER.records.append((name, TIMER.tag, e0, e1))
+        TIMER.records.append((name, TIMER.tag, e0, e1, int(algo_bytes)))
     else:
         rc = getattr(L, name)(*args)
     if rc != 0:

@@ -134,17 +134,21 @@ class UNetPlan:
         kind = b.kind1 if which == 1 else b.kind2
         pre = f"{b.prefix}.conv{which}"
         D, H, W = dims
+        es, nvx = t.element_size(), N * D * H * W
+        cin, cout = x_act.C, t.shape[-1]
         if kind == "dws":
             nv.call("l3d_dwpw_fwd", x_act, xn, N, D, H, W, nv.ptr(P[f"{pre}.depthwise.weight"]),
                     nv.ptr(P[f"{pre}.pointwise.weight"]), nv.ptr(sc_w), nv.act(t), nv.ptr(t_stats),
-                    nv.act(r), nv.ptr(r_stats), nv.act(u), st)
+                    nv.act(r), nv.ptr(r_stats), nv.act(u), st,
+                    algo_bytes=es * nvx * (cin + cout * (2 if sc_w is not None else 1) + (cin if u is not None else 0)))
         else:
             w = P[f"{pre}.conv.weight"] if kind == "grouped" else P[f"{pre}.weight"]
             g = self.groups if kind == "grouped" else 1
-            nv.call("l3d_conv3_fwd", x_act, xn, N, D, H, W, nv.ptr(w), g, nv.act(t), nv.ptr(t_stats), st)
+            nv.call("l3d_conv3_fwd", x_act, xn, N, D, H, W, nv.ptr(w), g, nv.act(t), nv.ptr(t_stats), st,
+                    algo_bytes=es * nvx * (cin + cout))
             if sc_w is not None:   # pointwise-only launch for the shortcut
                 nv.call("l3d_dwpw_fwd", x_act, xn, N, D, H, W, None, nv.ptr(sc_w), None, nv.act(r), nv.ptr(r_stats),
-                        nv.act(None), None, nv.act(None), st)
+                        nv.act(None), None, nv.act(None), st, algo_bytes=es * nvx * (cin + cout))
 
     def forward(self, P: Dict[str, torch.Tensor], x_cl: torch.Tensor, training: bool,
                 masks: Optional[List[Optional[torch.Tensor]]] = None,
@@ -172,6 +176,8 @@ class UNetPlan:
             nv.TIMER.tag = b.name
             dims = ws.level_dims[b.level]
             vox = dims[0] * dims[1] * dims[2]
+            es = x_cl.element_size()
+            mbytes = es * N * vox * b.cout            # one tensor of this block's output shape
             buf = ws.blocks[b.name]
             mask = masks[i] if (masks is not None and masks[i] is not None) else None
             if b.name.startswith("up"):
@@ -181,7 +187,8 @@ class UNetPlan:
                 off = [(dims[k] - 2 * lo[k]) // 2 for k in range(3)]
                 nv.call("l3d_convt_fwd", nv.act(cur, cur_off, cur_C), N, lo[0], lo[1], lo[2],
                         nv.ptr(P[f"{b.name}.up.weight"]), nv.ptr(P[f"{b.name}.up.bias"]),
-                        nv.act(cat, 0, b.cin // 2), dims[0], dims[1], dims[2], off[0], off[1], off[2], st)
+                        nv.act(cat, 0, b.cin // 2), dims[0], dims[1], dims[2], off[0], off[1], off[2], st,
+                        algo_bytes=es * N * (lo[0] * lo[1] * lo[2] * cur_C + vox * (b.cin // 2)))
                 cur, cur_off, cur_C = cat, 0, b.cin
             x_act = nv.act(cur, cur_off, cur_C)
             has_sc = b.cin != b.cout
@@ -204,15 +211,17 @@ class UNetPlan:
                 cat = ws.cat[b.level]
                 out_t, out_off = cat, b.cout                      # upper half of the concat buffer
                 nv.call("l3d_merge_fwd", nv.act(buf["t2"]), n2, r_act, nr, N, *dims, LEAKY_SLOPE,
-                        nv.act(cat, b.cout, b.cout), nv.act(ws.pooled[b.level]), None, None, 0, None, None, st)
+                        nv.act(cat, b.cout, b.cout), nv.act(ws.pooled[b.level]), None, None, 0, None, None, st,
+                        algo_bytes=3 * mbytes + mbytes // 8)
                 cur, cur_off, cur_C = ws.pooled[b.level], 0, b.cout
             elif b.name == "up3":
                 out = buf.get("out")
                 nv.call("l3d_merge_fwd", nv.act(buf["t2"]), n2, r_act, nr, N, *dims, LEAKY_SLOPE,
                         nv.act(out), nv.act(None), nv.ptr(P["out_conv.weight"]), nv.ptr(P["out_conv.bias"]),
-                        self.out_channels, nv.ptr(ws.prob_out), nv.ptr(ws.logits), st)
+                        self.out_channels, nv.ptr(ws.prob_out), nv.ptr(ws.logits), st,
+                        algo_bytes=(3 if out is not None else 2) * mbytes + 4 * N * vox * self.out_channels * (2 if training else 1))
             else:
                 nv.call("l3d_merge_fwd", nv.act(buf["t2"]), n2, r_act, nr, N, *dims, LEAKY_SLOPE,
-                        nv.act(buf["out"]), nv.act(None), None, None, 0, None, None, st)
+                        nv.act(buf["out"]), nv.act(None), None, None, 0, None, None, st, algo_bytes=3 * mbytes)
                 cur, cur_off, cur_C = buf["out"], 0, b.cout
         return ws

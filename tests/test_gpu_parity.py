@@ -38,7 +38,7 @@ def logit(p):
     return np.log(p / (1 - p))
 
 
-@pytest.mark.parametrize("dtype,tol_rel,tol_abs", [("f32", 1e-4, 2e-4), ("bf16", 1e-2, 4e-2)])
+@pytest.mark.parametrize("dtype,tol_rel,tol_abs", [("f32", 1e-4, 2e-4), ("bf16", 1e-2, 6e-2)])
 @pytest.mark.parametrize("name", UNET_CASES)
 def test_unet_eval_forward(name, dtype, tol_rel, tol_abs):
     z, meta, cfg, sd_np, x, t = load_unet_case(name)

@@ -44,7 +44,7 @@ def main():
             m(x)
         rec = nv.TIMER.stop()
         tot = sum(v[1] for v in rec.values())
-        for (name, tag), (n, t) in sorted(rec.items(), key=lambda kv: -kv[1][1]):
+        for (name, tag), (n, t, _b) in sorted(rec.items(), key=lambda kv: -kv[1][1]):
             print(f"   {name:18s} {tag:10s} n={n:3d} avg {t / n * 1e3:9.1f} us  {100 * t / tot:5.1f}%")
         print(f"   sum of kernels {tot / 5:.3f} ms per forward")
         if len(sys.argv) > 3:
