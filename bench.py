@@ -362,8 +362,11 @@ def cpu_baseline(variant, target_s=12.0):
     per_win = (time.perf_counter() - t0) / 3
     # bounded sample: a z-slab of the same volume holding ~target_s of work (full y/x extent when affordable)
     nwin_target = max(3, int(target_s / per_win))
-    if nwin_target >= 65:
-        sub, nwin = full[:48], 65                                # 1 x 5 x 13 windows
+    if nwin_target >= NWIN:
+        sub, nwin = full, NWIN                                   # the whole volume
+    elif nwin_target >= 65:
+        nz = min(4, nwin_target // 65)
+        sub, nwin = full[:48 + 24 * (nz - 1)], nz * 65           # nz x 5 x 13 windows
     elif nwin_target >= 13:
         ny = min(5, nwin_target // 13)
         ext = 48 + 24 * (ny - 1) if ny < 5 else 128

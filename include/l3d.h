@@ -138,11 +138,13 @@ int l3d_dw_bwd(const l3d_act *g_u, const l3d_act *x, const l3d_norm *xn, int N, 
                void *stream);
 
 /* Backward of l3d_conv3_fwd (dense / grouped): g_x (through the producer's activation, like
- * l3d_dw_bwd) and g_w. */
+ * l3d_dw_bwd) and g_w.  work: device scratch of l3d_conv3_bwd_workspace_bytes(...) bytes (holds the
+ * materialised g_t, the raw input gradient, the flipped weights and a channel-block table). */
+int64_t l3d_conv3_bwd_workspace_bytes(int N, int D, int H, int W, int Cin, int Cout, int elem_size);
 int l3d_conv3_bwd(const l3d_act *gz, const l3d_act *t, const l3d_norm *nt, const double *red,
                   const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int W,
                   const float *w, int groups, float *g_w,
-                  const l3d_act *gy, int accumulate_gy, double *redx, void *stream);
+                  const l3d_act *gy, int accumulate_gy, double *redx, void *work, int64_t work_bytes, void *stream);
 
 /* Backward of l3d_convt_fwd: g_x = sum_taps g_out . W^T, g_w += x^T . g_out, g_b += sum g_out. */
 int l3d_convt_bwd(const l3d_act *g_out, int OD, int OH, int OW, int oz, int oy, int ox,

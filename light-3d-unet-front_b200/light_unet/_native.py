@@ -51,7 +51,7 @@ _SIGS = {
     "l3d_dw_bwd": [POINTER(Act), POINTER(Act), POINTER(Norm), c_int, c_int, c_int, c_int, _P, _P,
                    POINTER(Act), c_int, _P, _P],
     "l3d_conv3_bwd": [POINTER(Act), POINTER(Act), POINTER(Norm), _P, POINTER(Act), POINTER(Norm),
-                      c_int, c_int, c_int, c_int, _P, c_int, _P, POINTER(Act), c_int, _P, _P],
+                      c_int, c_int, c_int, c_int, _P, c_int, _P, POINTER(Act), c_int, _P, _P, c_int64, _P],
     "l3d_convt_bwd": [POINTER(Act), c_int, c_int, c_int, c_int, c_int, c_int, POINTER(Act), c_int, c_int, c_int, c_int,
                       _P, _P, _P, POINTER(Act), c_int, _P],
     "l3d_norm_param_grad": [_P, c_int, c_int, _P, _P, _P],
@@ -66,7 +66,8 @@ _SIGS = {
     "l3d_bbox_init": [_P, c_int, _P],
     "l3d_bbox_reduce": [_P, _P, c_int, c_int, c_int, _P, c_int, _P],
 }
-EXPORTS = sorted(list(_SIGS) + ["l3d_last_error", "l3d_abi_version", "l3d_launch_count", "l3d_ccl_workspace_elems"])
+EXPORTS = sorted(list(_SIGS) + ["l3d_last_error", "l3d_abi_version", "l3d_launch_count", "l3d_ccl_workspace_elems",
+                                "l3d_conv3_bwd_workspace_bytes"])
 
 
 def lib():
@@ -85,6 +86,8 @@ def lib():
     L.l3d_launch_count.restype = c_int64
     L.l3d_ccl_workspace_elems.restype = c_int64
     L.l3d_ccl_workspace_elems.argtypes = [c_int64]
+    L.l3d_conv3_bwd_workspace_bytes.restype = c_int64
+    L.l3d_conv3_bwd_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int, c_int, c_int]
     for name, sig in _SIGS.items():
         fn = getattr(L, name)
         fn.restype = c_int

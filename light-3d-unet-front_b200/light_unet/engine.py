@@ -98,6 +98,22 @@ class Workspace:
             n_stats += 3 * 2 * N * b.cout
             self.blocks[b.name] = buf
         self.stats = torch.zeros(n_stats, dtype=torch.float64, device=device)
+        if training:
+            # backward: {sum g, sum g*xhat} per norm (same layout as stats), gradient tensors per level / block
+            self.red = torch.zeros(n_stats, dtype=torch.float64, device=device)
+            cmax = [2 * e[0], 2 * e[1], 2 * e[2], e[3]]
+            # gradient tensors are fp32 whatever the activation storage type: the InstanceNorm backward subtracts
+            # the per-(n,c) mean of the incoming gradient, and the Focal Tversky gradient is almost constant over
+            # the voxels, so bf16 rounding of the gradient (relative to its magnitude) swamps the centred signal
+            emp = lambda *s: torch.empty(*s, dtype=torch.float32, device=device)
+            self.g_cat = {k: emp(N, *lv[k], 2 * e[k]) for k in range(3)}      # grad of [up | skip]
+            self.g_pooled = {k: emp(N, *lv[k + 1], e[k]) for k in range(3)}   # grad of the pooled block inputs
+            self.g_out = {b.name: emp(N, *lv[b.level], b.cout) for b in plan.blocks
+                          if b.name in ("down3", "bottleneck", "up1", "up2")}
+            self.gz = {k: emp(N, *lv[k], e[k]) for k in range(4)}             # grad of the pre-activation merge sum
+            self.gy = {k: emp(N, *lv[k], e[k]) for k in range(4)}             # grad of norm1's output
+            self.gu = {k: emp(N, *lv[k], cmax[k]) for k in range(4)}          # grad of a depthwise output
+            self._conv3_work = None
         self.generation = 0
         self.prob_out = None
         self.logits = None
@@ -105,6 +121,22 @@ class Workspace:
     def stats_of(self, name: str, which: int, cout: int) -> torch.Tensor:
         off = self.blocks[name]["stats_off"] + which * 2 * self.N * cout
         return self.stats[off: off + 2 * self.N * cout]
+
+    def red_of(self, name: str, which: int, cout: int) -> torch.Tensor:
+        off = self.blocks[name]["stats_off"] + which * 2 * self.N * cout
+        return self.red[off: off + 2 * self.N * cout]
+
+    def conv3_work(self, plan: "UNetPlan") -> torch.Tensor:
+        """Scratch of the dense / grouped 3x3x3 backward: two activation-sized tensors at the widest level plus
+        the repacked weights (see l3d_conv3_bwd_workspace_bytes)."""
+        if self._conv3_work is None:
+            need = 0
+            for b in plan.blocks:
+                d = self.level_dims[b.level]
+                need = max(need, int(nv.lib().l3d_conv3_bwd_workspace_bytes(self.N, d[0], d[1], d[2], max(b.cin, b.cout), b.cout,
+                                                                            4)))
+            self._conv3_work = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._conv3_work
 
 
 class UNetPlan:
@@ -225,3 +257,114 @@ class UNetPlan:
                         nv.act(buf["out"]), nv.act(None), None, None, 0, None, None, st, algo_bytes=3 * mbytes)
                 cur, cur_off, cur_C = buf["out"], 0, b.cout
         return ws
+
+    # ------------------------------------------------------------------- backward
+    def _conv_bwd(self, P, G, b: BlockSpec, which: int, ws: Workspace, g, t, nt, red, x_act, xn, u, gy, acc_gy, redx,
+                  N, dims, st):
+        """Backward of conv1 / conv2: g is the gradient w.r.t. the normalised output of raw tensor t."""
+        kind = b.kind1 if which == 1 else b.kind2
+        pre = f"{b.prefix}.conv{which}"
+        D, H, W = dims
+        if kind == "dws":
+            cin = x_act.C
+            gu = nv.act(ws.gu[b.level], 0, cin)
+            nv.call("l3d_pw_bwd", nv.act(g), nv.act(t), nt, nv.ptr(red), nv.act(u), nv.norm(), N, D, H, W,
+                    nv.ptr(P[f"{pre}.pointwise.weight"]), nv.ptr(G[f"{pre}.pointwise.weight"]), gu, 0, st)
+            nv.call("l3d_dw_bwd", gu, x_act, xn, N, D, H, W, nv.ptr(P[f"{pre}.depthwise.weight"]),
+                    nv.ptr(G[f"{pre}.depthwise.weight"]), gy, acc_gy, nv.ptr(redx), st)
+        else:
+            key = f"{pre}.conv.weight" if kind == "grouped" else f"{pre}.weight"
+            g_ = self.groups if kind == "grouped" else 1
+            work = ws.conv3_work(self)
+            nv.call("l3d_conv3_bwd", nv.act(g), nv.act(t), nt, nv.ptr(red), x_act, xn, N, D, H, W, nv.ptr(P[key]), g_,
+                    nv.ptr(G[key]), gy, acc_gy, nv.ptr(redx), nv.ptr(work), work.numel(), st)
+
+    def backward(self, P: Dict[str, torch.Tensor], ws: Workspace, g_prob: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Kernel sequence of the backward pass for the forward recorded in `ws`.  Returns fp32 gradients in the
+        parameters' own (PyTorch) layouts, keyed by state_dict name."""
+        nv.require_cuda(g_prob, "UNetPlan.backward")
+        N = ws.N
+        dev = ws.device
+        st = nv.stream_ptr(dev)
+        G = {k: torch.zeros_like(v, dtype=torch.float32) for k, v in P.items()}
+        ws.red.zero_()
+        g_prob = g_prob.to(torch.float32).contiguous()
+        ident = nv.norm()
+        masks = ws.masks
+        nblk = len(self.blocks)
+        for i in range(nblk - 1, -1, -1):
+            b = self.blocks[i]
+            nv.TIMER.tag = b.name
+            dims = ws.level_dims[b.level]
+            vox = dims[0] * dims[1] * dims[2]
+            buf = ws.blocks[b.name]
+            has_sc = b.cin != b.cout
+            mask = masks[i] if (masks is not None and masks[i] is not None) else None
+            s1, s2, sr = (ws.stats_of(b.name, k, b.cout) for k in range(3))
+            r1, r2, rr = (ws.red_of(b.name, k, b.cout) for k in range(3))
+            n1 = nv.norm(s1, P[f"{b.prefix}.norm1.weight"], P[f"{b.prefix}.norm1.bias"], mask, IN_EPS, LEAKY_SLOPE, vox)
+            n2 = nv.norm(s2, P[f"{b.prefix}.norm2.weight"], P[f"{b.prefix}.norm2.bias"], None, IN_EPS, 1.0, vox)
+            # ---- where the block input lives, and where its gradient goes
+            if b.name == "init_conv":
+                x_act, g_in = nv.act(ws.x), nv.act(None)
+            elif b.name.startswith("down"):
+                x_act, g_in = nv.act(ws.pooled[b.level - 1]), nv.act(ws.g_pooled[b.level - 1])
+            elif b.name == "bottleneck":
+                x_act, g_in = nv.act(ws.blocks["down3"]["out"]), nv.act(ws.g_out["down3"])
+            else:
+                x_act, g_in = nv.act(ws.cat[b.level]), nv.act(ws.g_cat[b.level])
+            if has_sc:
+                r_act = nv.act(buf["r"])
+                nr = nv.norm(sr, P[f"{b.prefix}.shortcut.1.weight"], P[f"{b.prefix}.shortcut.1.bias"], None, IN_EPS, 1.0, vox)
+            else:
+                r_act, nr = x_act, ident
+            gz = ws.gz[b.level]
+            # ---- 1. residual merge (+ pool / head) backward
+            if b.name in ("init_conv", "down1", "down2"):
+                cat = ws.cat[b.level]
+                nv.call("l3d_merge_bwd", nv.act(ws.g_cat[b.level], b.cout, b.cout), nv.act(ws.g_pooled[b.level]),
+                        nv.act(cat, b.cout, b.cout), nv.act(ws.pooled[b.level]), nv.act(buf["t2"]), n2, r_act, nr,
+                        N, *dims, LEAKY_SLOPE, None, 0, None, None, None, None, nv.act(gz), nv.ptr(r2),
+                        nv.ptr(rr) if has_sc else None, st)
+            elif b.name == "up3":
+                nv.call("l3d_merge_bwd", nv.act(None), nv.act(None), nv.act(buf["out"]), nv.act(None), nv.act(buf["t2"]), n2,
+                        r_act, nr, N, *dims, LEAKY_SLOPE, nv.ptr(P["out_conv.weight"]), self.out_channels, nv.ptr(g_prob),
+                        nv.ptr(ws.prob_out), nv.ptr(G["out_conv.weight"]), nv.ptr(G["out_conv.bias"]), nv.act(gz),
+                        nv.ptr(r2), nv.ptr(rr) if has_sc else None, st)
+            else:
+                nv.call("l3d_merge_bwd", nv.act(ws.g_out[b.name]), nv.act(None), nv.act(buf["out"]), nv.act(None),
+                        nv.act(buf["t2"]), n2, r_act, nr, N, *dims, LEAKY_SLOPE, None, 0, None, None, None, None,
+                        nv.act(gz), nv.ptr(r2), nv.ptr(rr) if has_sc else None, st)
+            # ---- 2. conv2 backward: gz -> gy (gradient of norm1's output, through dropout / LeakyReLU)
+            gy = ws.gy[b.level]
+            self._conv_bwd(P, G, b, 2, ws, gz, buf["t2"], n2, r2, nv.act(buf["t1"]), n1, buf.get("u2"), nv.act(gy), 0, r1,
+                           N, dims, st)
+            # ---- 3. shortcut backward writes g_in, conv1 backward accumulates into it
+            need_gin = bool(g_in.ptr)
+            if has_sc:
+                nv.call("l3d_pw_bwd", nv.act(gz), r_act, nr, nv.ptr(rr), x_act, ident, N, *dims,
+                        nv.ptr(P[f"{b.prefix}.shortcut.0.weight"]), nv.ptr(G[f"{b.prefix}.shortcut.0.weight"]),
+                        g_in, 0, st)
+            elif need_gin:
+                ws.g_out["down3"].copy_(gz)      # identity shortcut (bottleneck): d(out)/d(x) passes gz through
+            n1b = nv.norm(s1, P[f"{b.prefix}.norm1.weight"], P[f"{b.prefix}.norm1.bias"], None, IN_EPS, 1.0, vox)
+            self._conv_bwd(P, G, b, 1, ws, gy, buf["t1"], n1b, r1, x_act, ident, buf.get("u1"), g_in, 1, None,
+                           N, dims, st)
+            # ---- 4. InstanceNorm affine gradients
+            nv.call("l3d_norm_param_grad", nv.ptr(r1), N, b.cout, nv.ptr(G[f"{b.prefix}.norm1.weight"]),
+                    nv.ptr(G[f"{b.prefix}.norm1.bias"]), st)
+            nv.call("l3d_norm_param_grad", nv.ptr(r2), N, b.cout, nv.ptr(G[f"{b.prefix}.norm2.weight"]),
+                    nv.ptr(G[f"{b.prefix}.norm2.bias"]), st)
+            if has_sc:
+                nv.call("l3d_norm_param_grad", nv.ptr(rr), N, b.cout, nv.ptr(G[f"{b.prefix}.shortcut.1.weight"]),
+                        nv.ptr(G[f"{b.prefix}.shortcut.1.bias"]), st)
+            # ---- 5. transposed conv backward: lower half of g_cat -> gradient of the previous block's output
+            if b.name.startswith("up"):
+                prev = self.blocks[i - 1]
+                lo = ws.level_dims[b.level + 1]
+                off = [(dims[k] - 2 * lo[k]) // 2 for k in range(3)]
+                nv.call("l3d_convt_bwd", nv.act(ws.g_cat[b.level], 0, b.cin // 2), dims[0], dims[1], dims[2],
+                        off[0], off[1], off[2], nv.act(ws.blocks[prev.name]["out"]), N, lo[0], lo[1], lo[2],
+                        nv.ptr(P[f"{b.name}.up.weight"]), nv.ptr(G[f"{b.name}.up.weight"]), nv.ptr(G[f"{b.name}.up.bias"]),
+                        nv.act(ws.g_out[prev.name]), 0, st)
+        return G

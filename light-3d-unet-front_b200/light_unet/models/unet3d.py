@@ -100,7 +100,7 @@ class _UNetFunction(torch.autograd.Function):
     """Whole-network autograd node: forward and backward are kernel sequences in libl3d."""
 
     @staticmethod
-    def forward(ctx, model, masks, x, *params):
+    def forward(ctx, model, masks, training, x, *params):
         names = model._param_names
         P = dict(zip(names, params))
         B, C, D, H, W = x.shape
@@ -109,7 +109,6 @@ class _UNetFunction(torch.autograd.Function):
             x_cl = x.reshape(B, D, H, W, 1).to(dt)
         else:
             x_cl = x.permute(0, 2, 3, 4, 1).contiguous().to(dt)
-        training = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         ws = model._plan.forward(P, x_cl, training, masks)
         ctx.model, ctx.ws, ctx.P = model, ws, P
         ctx.generation = ws.generation
@@ -122,7 +121,7 @@ class _UNetFunction(torch.autograd.Function):
             raise RuntimeError("Lightweight3DUNet: the activation workspace of this forward pass was overwritten by a "
                                "later forward of the same shape before backward() ran (or the pass ran without grad)")
         grads = ctx.model._plan.backward(ctx.P, ws, g_prob.contiguous())
-        return (None, None, None) + tuple(grads[n] for n in ctx.model._param_names)
+        return (None, None, None, None) + tuple(grads[n] for n in ctx.model._param_names)
 
 
 class Lightweight3DUNet(nn.Module):
@@ -188,7 +187,9 @@ class Lightweight3DUNet(nn.Module):
             masks = self.draw_dropout_masks(x.shape[0], x.device)
         if masks is not None:
             masks = [None if m is None else m.reshape(m.shape[0], -1).float().contiguous() for m in masks]
-        return _UNetFunction.apply(self, masks, x.float().contiguous(), *params)
+        # activations are only kept for a backward pass when autograd will actually ask for one
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        return _UNetFunction.apply(self, masks, need_grad, x.float().contiguous(), *params)
 
     def count_parameters(self):
         total = sum(p.numel() for p in self.parameters())

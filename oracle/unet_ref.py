@@ -134,18 +134,27 @@ def _inorm(sd, prefix, x):
                            use_input_stats=True, eps=IN_EPS)
 
 
-def residual_block(sd, cfg, prefix, x, cin, cout, allow_grouped, mask, taps=None):
-    """ResidualBlock.forward (unet3d.py:77-93)."""
+def bf16_storage(x: torch.Tensor) -> torch.Tensor:
+    """Round to bf16 with a straight-through gradient: models a tensor that the CUDA path *stores* in bf16
+    between kernels (all arithmetic stays fp32).  Used only to separate "kernel bug" from "precision policy"
+    when checking the bf16 storage mode: the CUDA backward is the exact gradient of this rounded forward."""
+    return x + (x.detach().to(torch.bfloat16).to(torch.float32) - x.detach())
+
+
+def residual_block(sd, cfg, prefix, x, cin, cout, allow_grouped, mask, taps=None, quant=None):
+    """ResidualBlock.forward (unet3d.py:77-93).  ``quant`` (None = the reference's plain fp32) is applied to
+    the tensors the CUDA path materialises in HBM: both raw conv outputs, the raw shortcut and the block output."""
+    q = quant if quant is not None else (lambda v: v)
     if cin != cout:
-        r = _inorm(sd, f"{prefix}.shortcut.1", F.conv3d(x, sd[f"{prefix}.shortcut.0.weight"]))
+        r = _inorm(sd, f"{prefix}.shortcut.1", q(F.conv3d(x, sd[f"{prefix}.shortcut.0.weight"])))
     else:
         r = x
-    t1 = _conv3(sd, f"{prefix}.conv1", x, conv_kind(cfg, cin, cout, 1, allow_grouped), cfg.groups)
+    t1 = q(_conv3(sd, f"{prefix}.conv1", x, conv_kind(cfg, cin, cout, 1, allow_grouped), cfg.groups))
     a = F.leaky_relu(_inorm(sd, f"{prefix}.norm1", t1), LEAKY_SLOPE)
     if mask is not None:
         a = a * mask
-    t2 = _conv3(sd, f"{prefix}.conv2", a, conv_kind(cfg, cout, cout, 2, allow_grouped), cfg.groups)
-    out = F.leaky_relu(_inorm(sd, f"{prefix}.norm2", t2) + r, LEAKY_SLOPE)
+    t2 = q(_conv3(sd, f"{prefix}.conv2", a, conv_kind(cfg, cout, cout, 2, allow_grouped), cfg.groups))
+    out = q(F.leaky_relu(_inorm(sd, f"{prefix}.norm2", t2) + r, LEAKY_SLOPE))
     if taps is not None:
         taps[prefix + ".t1"] = t1
         taps[prefix + ".t2"] = t2
@@ -153,10 +162,12 @@ def residual_block(sd, cfg, prefix, x, cin, cout, allow_grouped, mask, taps=None
     return out
 
 
-def up_merge(sd, name, x, skip):
+def up_merge(sd, name, x, skip, quant=None):
     """UpBlock.forward up to the concat (unet3d.py:126-141): transposed conv,
     centre pad to the skip's size, concat [upsampled, skip]."""
     x = F.conv_transpose3d(x, sd[f"{name}.up.weight"], sd[f"{name}.up.bias"], stride=2)
+    if quant is not None:
+        x = quant(x)
     if x.shape != skip.shape:
         dd = skip.size(2) - x.size(2)
         dh = skip.size(3) - x.size(3)
@@ -167,20 +178,20 @@ def up_merge(sd, name, x, skip):
 
 def forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, cfg: UNetCfg,
             masks: Optional[List[Optional[torch.Tensor]]] = None,
-            taps: Optional[dict] = None, return_logits: bool = False) -> torch.Tensor:
+            taps: Optional[dict] = None, return_logits: bool = False, quant=None) -> torch.Tensor:
     """Lightweight3DUNet.forward (unet3d.py:204-223).  Returns probabilities
     (sigmoid already applied, :220-221) unless ``return_logits``."""
     specs = block_specs(cfg)
     if masks is None:
         masks = [None] * len(specs)
     feats = []
-    h = x
+    h = x if quant is None else quant(x)
     for i, (name, prefix, cin, cout, ag) in enumerate(specs):
         if name.startswith("down"):
             h = F.max_pool3d(h, 2, 2)                       # unet3d.py:109
         elif name.startswith("up"):
-            h = up_merge(sd, name, h, feats[3 - int(name[-1])])  # up1<-x3, up2<-x2, up3<-x1
-        h = residual_block(sd, cfg, prefix, h, cin, cout, ag, masks[i], taps)
+            h = up_merge(sd, name, h, feats[3 - int(name[-1])], quant)  # up1<-x3, up2<-x2, up3<-x1
+        h = residual_block(sd, cfg, prefix, h, cin, cout, ag, masks[i], taps, quant)
         if name in ("init_conv", "down1", "down2"):
             feats.append(h)
     logits = F.conv3d(h, sd["out_conv.weight"], sd["out_conv.bias"])
