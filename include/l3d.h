@@ -202,6 +202,12 @@ int l3d_bbox_init(int32_t *table, int cap, void *stream);
 int l3d_bbox_reduce(const int32_t *labels, const float *prob, int D, int H, int W, int32_t *table, int cap,
                     void *stream);
 
+/* ------------------------------------------------------------- diagnostics -- */
+
+/* Self-test of the tcgen05 building blocks: D[128*MT][N] (fp32) = A[128*MT][K] . Wt[N][K]^T with fp16 operands
+ * and fp32 accumulation in TMEM.  A, Wt, D are fp32 device arrays. */
+int l3d_tc_selftest(const float *A, const float *Wt, int MT, int K, int N, float *D, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
