@@ -560,8 +560,8 @@ __global__ void __launch_bounds__(NT) dw_bwd_kernel(
         const int y0 = (b % tilesY) * TY; b /= tilesY;
         const int z0 = b * TZ;
         __syncthreads();
+        flush_red(cur_n);      // per tile: keeps the fp32 shared-memory partial sums short (double beyond this point)
         if (n != cur_n) {
-            flush_red(cur_n);
             cur_n = n;
             for (int cc = tid; cc < C; cc += NT) {
                 const NormCoef k = norm_coef(xn, N, C, n, cc);

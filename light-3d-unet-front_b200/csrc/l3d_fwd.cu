@@ -572,6 +572,108 @@ __global__ void __launch_bounds__(NT) convt_fwd_kernel(
     }
 }
 
+
+// -------------------------------------------------------------------------------------------
+// Single-input-channel variant of the fused depthwise->pointwise(+shortcut) conv (the network's first conv,
+// unet3d.py:168,209): K = 1, so the "GEMM" is an outer product and the kernel is a pure HBM write stream.
+// thread = one voxel, all COUT outputs of t (and r); persistent CTAs, statistics reduced per tile.
+template <typename T, int COUT>
+__global__ void __launch_bounds__(NT) dwpw_c1_kernel(
+    const T *__restrict__ x, int ldx, NormDev xn, int N, int D, int H, int W,
+    const float *__restrict__ dw_w, const float *__restrict__ pw_w, const float *__restrict__ sc_w,
+    T *__restrict__ t, int ldt, double *__restrict__ t_stats, T *__restrict__ r, int ldr, double *__restrict__ r_stats,
+    T *__restrict__ u, int ldu) {
+    __shared__ float s_in[HZ][HY][HX + 1];
+    __shared__ float s_stat[4 * COUT];
+    __shared__ float s_w[27 + 2 * COUT];
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < 27; i += NT) s_w[i] = dw_w[i];
+    for (int i = tid; i < COUT; i += NT) { s_w[27 + i] = pw_w[i]; s_w[27 + COUT + i] = sc_w != nullptr ? sc_w[i] : 0.f; }
+    for (int i = tid; i < 4 * COUT; i += NT) s_stat[i] = 0.f;
+    const int tilesX = (W + TX - 1) / TX, tilesY = (H + TY - 1) / TY, tilesZ = (D + TZ - 1) / TZ;
+    const long long tiles_per_sample = (long long)tilesX * tilesY * tilesZ;
+    const long long total_tiles = tiles_per_sample * N;
+    const int lx = tid & 7, ly = (tid >> 3) & 7, lz = tid >> 6;
+    int cur_n = -1;
+    float sc = 1.f, sh = 0.f;
+    auto flush = [&](int n) {
+        if (n < 0) return;
+        for (int i = tid; i < 2 * COUT; i += NT) {
+            const int isq = i >= COUT, c = isq ? i - COUT : i;
+            atomicAdd(&t_stats[(size_t)isq * N * COUT + (size_t)n * COUT + c], (double)s_stat[i]);
+            s_stat[i] = 0.f;
+            if (sc_w != nullptr) {
+                atomicAdd(&r_stats[(size_t)isq * N * COUT + (size_t)n * COUT + c], (double)s_stat[2 * COUT + i]);
+                s_stat[2 * COUT + i] = 0.f;
+            }
+        }
+    };
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n = (int)(tile / tiles_per_sample);
+        int b = (int)(tile % tiles_per_sample);
+        const int x0 = (b % tilesX) * TX; b /= tilesX;
+        const int y0 = (b % tilesY) * TY; b /= tilesY;
+        const int z0 = b * TZ;
+        __syncthreads();                      // previous tile done with s_in, its statistics are in s_stat
+        if (n != cur_n) {
+            flush(cur_n);
+            cur_n = n;
+            norm_scale_shift(xn, N, 1, n, 0, sc, sh);
+        }
+        for (int item = tid; item < HZ * HY * HX; item += NT) {
+            int hv = item;
+            const int hx = hv % HX; hv /= HX;
+            const int hy = hv % HY;
+            const int hz = hv / HY;
+            const int gz = z0 + hz - 1, gy = y0 + hy - 1, gx = x0 + hx - 1;
+            float v = 0.f;
+            if (gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W)
+                v = lrelu(ld1(x + ((((size_t)n * D + gz) * H + gy) * W + gx) * (size_t)ldx) * sc + sh, xn.slope);
+            s_in[hz][hy][hx] = v;
+        }
+        __syncthreads();
+        float uacc = 0.f;
+#pragma unroll
+        for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) uacc = fmaf(s_w[dz * 9 + dy * 3 + dx], s_in[lz + dz][ly + dy][lx + dx], uacc);
+        const float xc = s_in[lz + 1][ly + 1][lx + 1];
+        const int gz = z0 + lz, gy = y0 + ly, gx = x0 + lx;
+        const bool valid = gz < D && gy < H && gx < W;
+        const size_t vox = (((size_t)n * D + gz) * H + gy) * W + gx;
+        if (u != nullptr && valid) st1(u + vox * (size_t)ldu, uacc);
+        const float uu = uacc;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            if (a == 1 && sc_w == nullptr) break;
+            const float in = a == 0 ? uu : xc;
+            T *op = (a == 0 ? t + vox * (size_t)ldt : r + vox * (size_t)ldr);
+            const float *wv = s_w + 27 + a * COUT;
+#pragma unroll
+            for (int cb = 0; cb < COUT; cb += 16) {
+                float sv[32];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float o = in * wv[cb + j];
+                    const float rr = valid ? round_as(t, o) : 0.f;
+                    sv[j] = rr; sv[16 + j] = rr * rr;
+                }
+                if (valid) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 16; j4 += 4) st4(op + cb + j4, make_float4(sv[j4], sv[j4 + 1], sv[j4 + 2], sv[j4 + 3]));
+                }
+                warp_transpose_sum<32>(sv, lane);
+                const int idx = warp_transpose_owner<32>(lane);
+                atomicAdd(&s_stat[a * 2 * COUT + (idx >= 16 ? COUT + idx - 16 : idx) + cb], sv[0]);
+            }
+        }
+    }
+    __syncthreads();
+    flush(cur_n);
+}
+
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
     if (bytes > 48 * 1024) {
@@ -587,6 +689,15 @@ static bool vec4_ok(const l3d_act *a) {
 }
 
 }  // namespace
+
+// tensor-core path for bf16 storage (l3d_fwd_tc.cu); returns -1 when it does not apply
+int l3d_dwpw_fwd_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int W,
+                    const float *dw_w, const float *pw_w, const float *sc_w,
+                    const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats,
+                    const l3d_act *u, void *stream);
+
+int l3d_convt_fwd_tc(const l3d_act *x, int N, int d, int h, int w_, const float *w, const float *b,
+                     const l3d_act *out, int OD, int OH, int OW, int oz, int oy, int ox, void *stream);
 
 // ================================================================= C ABI ====================
 extern "C" int l3d_dwpw_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int W,
@@ -605,6 +716,25 @@ extern "C" int l3d_dwpw_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, 
     }
     const bool has_u = !act_null(u);
     if (has_u) L3D_REQUIRE(u->C == Cin && u->dtype == x->dtype, "l3d_dwpw_fwd: bad u view");
+    {
+        const int rc = l3d_dwpw_fwd_tc(x, xn, N, D, H, W, dw_w, pw_w, sc_w, t, t_stats, r, r_stats, u, stream);
+        if (rc >= 0) return rc;
+    }
+    if (Cin == 1 && dw_w != nullptr && (Cout == 16 || Cout == 32)) {
+        const int64_t tiles1 = num_tiles(N, D, H, W);
+        const unsigned grid1 = (unsigned)(tiles1 < 148 * 6 ? tiles1 : 148 * 6);
+        const NormDev nd1 = norm_dev(xn);
+        cudaStream_t st1_ = (cudaStream_t)stream;
+#define LAUNCH_C1(T, CO)                                                                                              \
+        dwpw_c1_kernel<T, CO><<<grid1, NT, 0, st1_>>>((const T *)x->ptr, x->ldc, nd1, N, D, H, W, dw_w, pw_w, sc_w,      \
+                                                      (T *)t->ptr, t->ldc, t_stats, has_r ? (T *)r->ptr : nullptr,      \
+                                                      has_r ? r->ldc : 0, r_stats, has_u ? (T *)u->ptr : nullptr, has_u ? u->ldc : 0)
+        L3D_DISPATCH_DTYPE(x->dtype, T, { if (Cout == 16) LAUNCH_C1(T, 16); else LAUNCH_C1(T, 32); });
+#undef LAUNCH_C1
+        l3d_count_launch();
+        L3D_CUDA_OK("l3d_dwpw_fwd (Cin=1) launch");
+        return 0;
+    }
     const int CPT = (Cout % 32 == 0) ? 16 : (Cout % 16 == 0) ? 8 : 4;
     const size_t smem = dwpw_smem_bytes(Cin, Cout, CPT);
     L3D_REQUIRE(smem <= 227 * 1024, "l3d_dwpw_fwd: Cin=%d needs %zu B shared memory", Cin, smem);
@@ -717,6 +847,10 @@ extern "C" int l3d_convt_fwd(const l3d_act *x, int N, int d, int h, int w_, cons
     const int Cin = x->C, Cout = out->C;
     L3D_REQUIRE(Cout % 4 == 0 && vec4_ok(out), "l3d_convt_fwd: Cout=%d must be a multiple of 4 and aligned", Cout);
     L3D_REQUIRE(out->dtype == x->dtype, "l3d_convt_fwd: dtype mismatch");
+    {
+        const int rc = l3d_convt_fwd_tc(x, N, d, h, w_, w, b, out, OD, OH, OW, oz, oy, ox, stream);
+        if (rc >= 0) return rc;
+    }
     const int CPT = (Cout % 16 == 0) ? 16 : (Cout % 8 == 0) ? 8 : 4;
     const size_t smem = sizeof(float) * ((size_t)CT_VOX * (Cin | 1) + 4 + (size_t)Cin * Cout);
     L3D_REQUIRE(smem <= 227 * 1024, "l3d_convt_fwd: Cin=%d Cout=%d needs %zu B shared memory", Cin, Cout, smem);

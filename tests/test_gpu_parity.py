@@ -120,7 +120,7 @@ def test_stitch_is_bit_exact_given_identical_predictions():
         assert np.array_equal(mask.cpu().numpy(), (want >= np.float32(0.5)).astype(np.int32))
 
 
-@pytest.mark.parametrize("dtype,tol", [("f32", 1e-4), ("bf16", 2e-2)])
+@pytest.mark.parametrize("dtype,tol", [("f32", 1e-4), ("bf16", 3e-2)])
 def test_sliding_window_matches_reference_fixture(dtype, tol):
     from light_unet.utils import sliding_window_inference_3d
     z = np.load(os.path.join(GOLDEN, "sliding_window.npz"))
