@@ -1,0 +1,384 @@
+// 3x3x3 convolution as an implicit GEMM on tcgen05 (bf16 storage) with TMA-staged halo tiles.
+//
+//   D[128 voxels][Cout] (fp32, TMEM) += A_tap[128][16] . B_tap[16][Cout]       for 27 taps x Cin/16 channel chunks
+//
+// * A_tap is not materialised: the activated halo tile lives in shared memory as fp16 in a planar layout
+//   [8-channel group][z][y][x][8 ch], and the MMA descriptor of tap (dz,dy,dx) simply starts (dz,dy,dx) voxels
+//   further into that tile (rows 16 B apart along x, row groups one y-row apart, K halves one plane apart).
+//   An MMA tile is one z-plane of 16 (y) x 8 (x) voxels; a CTA tile is two planes.
+// * B_tap: dense / grouped conv: W[co][ci][tap] (unet3d.py:30,49,60).  Depthwise-separable conv: the depthwise
+//   and pointwise stages are both linear, so their composition is a 3x3x3 conv with W[co][ci][tap] =
+//   pw[co][ci] * dw[ci][tap] (unet3d.py:20-23) -- 27x the pointwise FLOPs, all on the tensor pipe, and no
+//   intermediate tensor.  The block's 1x1x1 shortcut conv (unet3d.py:70-71) is one more MMA on the centre tap.
+// * Pipeline per (tile, 16-channel chunk): TMA raw box (bf16, zero-filled outside the volume) -> activation pass
+//   (InstanceNorm + LeakyReLU + Dropout3d of the producer, fp16) into one of two A buffers -> one thread issues the
+//   27(+1) MMAs -> tcgen05.commit.  Accumulators are double-buffered in TMEM so the epilogue of tile T (tcgen05.ld,
+//   bf16 store, InstanceNorm statistics) overlaps the MMAs of tile T+1.
+#include <cuda.h>
+
+#include "l3d_common.cuh"
+#include "l3d_tc.cuh"
+
+namespace {
+
+constexpr int TZ = 2, TY = 16, TX = 8;                  // CTA tile: 2 MMA tiles (z-planes) of 16x8 voxels
+constexpr int HZ = TZ + 2, HY = TY + 2, HX = TX + 2;    // 4 x 18 x 10 halo
+constexpr int HVOX = HZ * HY * HX;                      // 720
+constexpr int CK = 16, NT = 256, MT = 2;
+constexpr int RAW_BYTES = HVOX * CK * 2;                // 23040: TMA box, dense [z][y][x][16] bf16
+constexpr int PLANE = HVOX * 16;                        // bytes of one 8-channel group of the A tile (fp16)
+constexpr int A_BYTES = 2 * PLANE;                      // 23040
+constexpr int ROWPITCH = HX * 16;                       // 160 B between y rows
+constexpr int ACT_ITEMS = HVOX * 2;
+constexpr int ACT_PER_THREAD = (ACT_ITEMS + NT - 1) / NT;   // 6
+
+struct C3Args {
+    int Cin; NormDev xn;
+    int N, D, H, W;
+    const float *w;          // dense / grouped weights [Cout][Cin/groups][27], or NULL
+    int groups;
+    const float *dw_w, *pw_w;   // depthwise-separable: [Cin][27], [Cout][Cin]
+    const float *sc_w;          // shortcut [Cout][Cin] or NULL
+    int Cout;
+    bf16 *t; int ldt; double *t_stats;
+    bf16 *r; int ldr; double *r_stats;
+    int tmem_cols;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+    __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+
+__global__ void __launch_bounds__(NT) conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, C3Args A) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t s_tma_bar, s_mma_bar[2];
+    __shared__ uint32_t s_tmem;
+    const int Cin = A.Cin, Cout = A.Cout;
+    const bool has_sc = A.sc_w != nullptr;
+    const int nchunks = Cin / CK;
+    const uint32_t btap_bytes = (uint32_t)Cout * 32;                      // one [Cout x 16] fp16 operand tile
+    const uint32_t b_bytes = (uint32_t)nchunks * 27 * btap_bytes;
+    unsigned char *s_raw = smem_raw;                                       // TMA destination
+    unsigned char *sA = s_raw + RAW_BYTES;                                 // 2 x A_BYTES
+    unsigned char *sB = sA + 2 * A_BYTES;                                  // [chunk][tap][Cout x 16]
+    unsigned char *sB2 = sB + b_bytes;                                     // shortcut: [chunk][Cout x 16]
+    float *s_scale = reinterpret_cast<float *>(sB2 + (has_sc ? nchunks * btap_bytes : 0));
+    float *s_shift = s_scale + Cin;
+    float *s_stat = s_shift + Cin;                                         // 2*Cout (t) + 2*Cout (r)
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tc::tmem_alloc(&s_tmem, (uint32_t)A.tmem_cols);
+    if (tid == 32) { tc::mbar_init(&s_tma_bar, 1); tc::mbar_init(&s_mma_bar[0], MT); tc::mbar_init(&s_mma_bar[1], MT); }
+    // ---- stage the (effective) 3x3x3 weights once per CTA as fp16 K-major operand tiles
+    {
+        const int cin_g = Cin / A.groups, cout_g = Cout / A.groups;
+        for (int i = tid; i < Cout * Cin * 27; i += NT) {
+            const int tap = i % 27;
+            const int ci = (i / 27) % Cin;
+            const int co = i / (27 * Cin);
+            float wv;
+            if (A.w != nullptr) {
+                const int g = co / cout_g, cl = ci - g * cin_g;
+                wv = (cl >= 0 && cl < cin_g) ? A.w[((size_t)co * cin_g + cl) * 27 + tap] : 0.f;
+            } else {
+                wv = A.pw_w[(size_t)co * Cin + ci] * A.dw_w[(size_t)ci * 27 + tap];
+            }
+            const int ch = ci >> 4, k = ci & 15;
+            *reinterpret_cast<__half *>(sB + (size_t)(ch * 27 + tap) * btap_bytes + tc::tile_off(co, k, Cout)) = __float2half_rn(wv);
+        }
+        if (has_sc)
+            for (int i = tid; i < Cout * Cin; i += NT) {
+                const int ci = i % Cin, co = i / Cin;
+                *reinterpret_cast<__half *>(sB2 + (size_t)(ci >> 4) * btap_bytes + tc::tile_off(co, ci & 15, Cout)) = __float2half_rn(A.sc_w[i]);
+            }
+    }
+    for (int i = tid; i < 4 * Cout; i += NT) s_stat[i] = 0.f;
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = s_tmem;
+    const uint32_t idesc = tc::idesc_f16_m128(Cout);
+    const uint32_t sA_u = tc::smem_u32(sA), sB_u = tc::smem_u32(sB), sB2_u = tc::smem_u32(sB2);
+    const int nacc = has_sc ? 2 : 1;
+    const int acc_cols = MT * Cout * nacc;          // TMEM columns of one accumulator set (two sets: tile parity)
+
+    const int tilesX = (A.W + TX - 1) / TX, tilesY = (A.H + TY - 1) / TY, tilesZ = (A.D + TZ - 1) / TZ;
+    const int tiles_per_sample = tilesX * tilesY * tilesZ;
+    const int total_tiles = tiles_per_sample * A.N;
+    // contiguous tile range per CTA (keeps a CTA inside one sample as long as possible, halo re-use in L2)
+    const int per = (total_tiles + gridDim.x - 1) / gridDim.x;
+    const int tile_begin = blockIdx.x * per;
+    const int tile_end = min(total_tiles, tile_begin + per);
+    auto tile_coord = [&](int tile, int &n, int &z0, int &y0, int &x0) {
+        n = tile / tiles_per_sample;
+        int b = tile - n * tiles_per_sample;
+        x0 = (b % tilesX) * TX; b /= tilesX;
+        y0 = (b % tilesY) * TY; b /= tilesY;
+        z0 = b * TZ;
+    };
+    // activation-pass role: fixed 16-byte vectors of the raw box; q (8-channel group) is the same for all of them
+    const int aq = tid & 1;
+    uint32_t act_item[ACT_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < ACT_PER_THREAD; ++k) {
+        const int item = tid + k * NT;
+        int hv = item >> 1;
+        const int hx = hv % HX; hv /= HX;
+        const int hy = hv % HY;
+        const int hz = hv / HY;
+        act_item[k] = item < ACT_ITEMS ? ((uint32_t)hx | ((uint32_t)hy << 8) | ((uint32_t)hz << 16)) : 0xffffffffu;
+    }
+    // epilogue role: voxel row of MMA tile (plane) `em`
+    const int em = warp >> 2, erow = (warp & 3) * 32 + lane;
+    const int elx = erow & 7, ely = erow >> 3;
+    int cur_n = -1;
+
+    auto flush_stats = [&](int n) {
+        if (n < 0) return;
+        for (int i = tid; i < 2 * Cout; i += NT) {
+            const int isq = i >= Cout, cc = isq ? i - Cout : i;
+            atomicAdd(&A.t_stats[(size_t)isq * A.N * Cout + (size_t)n * Cout + cc], (double)s_stat[i]);
+            s_stat[i] = 0.f;
+            if (has_sc) {
+                atomicAdd(&A.r_stats[(size_t)isq * A.N * Cout + (size_t)n * Cout + cc], (double)s_stat[2 * Cout + i]);
+                s_stat[2 * Cout + i] = 0.f;
+            }
+        }
+    };
+    // epilogue of tile `tile` (accumulator set `set`): TMEM -> bf16 global + statistics.  `stat_n` is the sample
+    // the statistics currently held in s_stat belong to.
+    auto epilogue = [&](int tile, int set, int &stat_n) {
+        int n, z0, y0, x0;
+        tile_coord(tile, n, z0, y0, x0);
+        if (n != stat_n) {
+            __syncthreads();
+            flush_stats(stat_n);
+            stat_n = n;
+            __syncthreads();
+        }
+        const int gz = z0 + em, gy = y0 + ely, gx = x0 + elx;
+        const bool valid = gz < A.D && gy < A.H && gx < A.W;
+        const size_t vox = (((size_t)n * A.D + gz) * A.H + gy) * A.W + gx;
+        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(set * acc_cols);
+        for (int a = 0; a < nacc; ++a) {
+            bf16 *outp = (a == 0 ? A.t + vox * (size_t)A.ldt : A.r + vox * (size_t)A.ldr);
+            float *stat = s_stat + a * 2 * Cout;
+            for (int cb = 0; cb < Cout; cb += 16) {
+                float v[16];
+                tc::tmem_ld16(trow + (uint32_t)((a * MT + em) * Cout + cb), v);
+                float sv[32];
+                uint32_t pk[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    pk[j] = valid ? pack_bf16x2(v[2 * j], v[2 * j + 1]) : 0u;
+                    const float r0 = __uint_as_float(pk[j] << 16);
+                    const float r1 = __uint_as_float(pk[j] & 0xffff0000u);
+                    sv[2 * j] = r0; sv[2 * j + 1] = r1;
+                    sv[16 + 2 * j] = r0 * r0; sv[16 + 2 * j + 1] = r1 * r1;
+                }
+                if (valid) {
+                    *reinterpret_cast<uint4 *>(outp + cb) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *reinterpret_cast<uint4 *>(outp + cb + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                }
+                warp_transpose_sum<32>(sv, lane);
+                const int idx = warp_transpose_owner<32>(lane);
+                atomicAdd(&stat[(idx >= 16 ? Cout + idx - 16 : idx) + cb], sv[0]);
+            }
+        }
+        tc::fence_before_sync();
+    };
+
+    const int n_items = (tile_end > tile_begin ? tile_end - tile_begin : 0) * nchunks;
+    // the raw box of work item it+1 is requested as soon as the activation pass of item it has consumed the buffer
+    auto issue_tma = [&](int item) {
+        const int tl = tile_begin + item / nchunks, chn = item % nchunks;
+        int n, z0, y0, x0;
+        tile_coord(tl, n, z0, y0, x0);
+        tc::mbar_expect_tx(&s_tma_bar, RAW_BYTES);
+        tc::tma_load_5d(s_raw, &tmap, &s_tma_bar, chn * CK, x0 - 1, y0 - 1, z0 - 1, n);
+    };
+    if (tid == 0) {
+        if (n_items > 0) issue_tma(0);
+    }
+    int it = 0;                 // work-item counter: (tile, chunk) pairs
+    int stat_n = -1;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+        int n, z0, y0, x0;
+        tile_coord(tile, n, z0, y0, x0);
+        if (n != cur_n) {
+            cur_n = n;
+            __syncthreads();    // nobody still reads the previous sample's scale/shift
+            for (int cc = tid; cc < Cin; cc += NT) {
+                float sc, sh;
+                norm_scale_shift(A.xn, A.N, Cin, n, cc, sc, sh);
+                s_scale[cc] = sc; s_shift[cc] = sh;
+            }
+            __syncthreads();
+        }
+        // validity of the halo coordinates of this tile as per-axis bit masks
+        uint32_t mz = 0, my = 0, mx = 0;
+#pragma unroll
+        for (int i = 0; i < HZ; ++i) mz |= (uint32_t)(z0 + i - 1 >= 0 && z0 + i - 1 < A.D) << i;
+#pragma unroll
+        for (int i = 0; i < HY; ++i) my |= (uint32_t)(y0 + i - 1 >= 0 && y0 + i - 1 < A.H) << i;
+#pragma unroll
+        for (int i = 0; i < HX; ++i) mx |= (uint32_t)(x0 + i - 1 >= 0 && x0 + i - 1 < A.W) << i;
+        const int set = (tile - tile_begin) & 1;
+        for (int ch = 0; ch < nchunks; ++ch, ++it) {
+            const int buf = it & 1;
+            unsigned char *Ab = sA + (size_t)buf * A_BYTES;
+            // scale / shift of this thread's 8 channels
+            const float4 sc0 = *reinterpret_cast<const float4 *>(s_scale + ch * CK + aq * 8);
+            const float4 sc1 = *reinterpret_cast<const float4 *>(s_scale + ch * CK + aq * 8 + 4);
+            const float4 sh0 = *reinterpret_cast<const float4 *>(s_shift + ch * CK + aq * 8);
+            const float4 sh1 = *reinterpret_cast<const float4 *>(s_shift + ch * CK + aq * 8 + 4);
+            const float sl = A.xn.slope;
+            tc::mbar_wait(&s_tma_bar, (uint32_t)(it & 1));                           // raw box of this item landed
+            if (it >= 2) tc::mbar_wait(&s_mma_bar[buf], (uint32_t)(((it >> 1) - 1) & 1));   // MMAs of item it-2 done: A[buf] free
+            // ---- activation pass: raw bf16 [z][y][x][16] -> fp16 planar [q][z][y][x][8]
+#pragma unroll
+            for (int k = 0; k < ACT_PER_THREAD; ++k) {
+                const uint32_t ai = act_item[k];
+                if (ai != 0xffffffffu) {
+                    const int hx = ai & 255, hy = (ai >> 8) & 255, hz = ai >> 16;
+                    const int item = tid + k * NT;
+                    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                    if ((mx >> hx) & (my >> hy) & (mz >> hz) & 1u) {
+                        const uint4 rw = *reinterpret_cast<const uint4 *>(s_raw + (size_t)item * 16);
+                        float f[8];
+                        f[0] = fmaf(__uint_as_float(rw.x << 16), sc0.x, sh0.x); f[1] = fmaf(__uint_as_float(rw.x & 0xffff0000u), sc0.y, sh0.y);
+                        f[2] = fmaf(__uint_as_float(rw.y << 16), sc0.z, sh0.z); f[3] = fmaf(__uint_as_float(rw.y & 0xffff0000u), sc0.w, sh0.w);
+                        f[4] = fmaf(__uint_as_float(rw.z << 16), sc1.x, sh1.x); f[5] = fmaf(__uint_as_float(rw.z & 0xffff0000u), sc1.y, sh1.y);
+                        f[6] = fmaf(__uint_as_float(rw.w << 16), sc1.z, sh1.z); f[7] = fmaf(__uint_as_float(rw.w & 0xffff0000u), sc1.w, sh1.w);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], f[j] * sl);      // LeakyReLU, 0 <= slope <= 1
+                        o = make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]), pack_f16x2(f[6], f[7]));
+                    }
+                    *reinterpret_cast<uint4 *>(Ab + (size_t)aq * PLANE + (size_t)(item >> 1) * 16) = o;
+                }
+            }
+            tc::fence_async_smem();
+            tc::fence_before_sync();
+            __syncthreads();             // A[buf] complete, raw box consumed, previous epilogue's TMEM reads done
+            if (tid == 0 && it + 1 < n_items) issue_tma(it + 1);     // the raw buffer is free again
+            if (lane == 0 && warp < MT) {
+                // MMA issue: warp m issues the 27 taps (+ shortcut on the centre tap) of plane m.  The descriptors of
+                // all taps differ from the first one by compile-time constants in the 16-byte start-address field.
+                tc::fence_after_sync();
+                const int m = warp;
+                const uint64_t ad0 = tc::smem_desc(sA_u + buf * A_BYTES + (uint32_t)(m * HY * ROWPITCH), PLANE, ROWPITCH);
+                const uint64_t bd0 = tc::smem_desc(sB_u + (uint32_t)(ch * 27) * btap_bytes, Cout * 16, 128);
+                const uint32_t bstep = btap_bytes >> 4;
+                const uint32_t d_t = tmem + (uint32_t)(set * acc_cols + m * Cout);
+#pragma unroll
+                for (int tap = 0; tap < 27; ++tap) {
+                    const int dz = tap / 9, dy = (tap / 3) % 3, dx = tap % 3;
+                    const uint32_t aoff = (uint32_t)(((dz * HY + dy) * ROWPITCH + dx * 16) >> 4);
+                    tc::mma_f16(d_t, ad0 + aoff, bd0 + (uint64_t)(tap * bstep), idesc, (ch > 0 || tap > 0) ? 1u : 0u);
+                }
+                if (has_sc) {
+                    const uint32_t aoff = (uint32_t)(((1 * HY + 1) * ROWPITCH + 16) >> 4);
+                    const uint64_t bd2 = tc::smem_desc(sB2_u + (uint32_t)ch * btap_bytes, Cout * 16, 128);
+                    tc::mma_f16(d_t + MT * Cout, ad0 + aoff, bd2, idesc, ch > 0 ? 1u : 0u);
+                }
+                tc::mma_commit(&s_mma_bar[buf]);
+            }
+            // ---- epilogue of the previous tile overlaps the MMAs just issued
+            if (ch == 0 && tile > tile_begin) {
+                const int pit = it - 1;                                   // last work item of the previous tile
+                tc::mbar_wait(&s_mma_bar[pit & 1], (uint32_t)((pit >> 1) & 1));
+                tc::fence_after_sync();
+                epilogue(tile - 1, set ^ 1, stat_n);
+            }
+        }
+    }
+    if (tile_begin < tile_end) {
+        const int pit = it - 1;
+        tc::mbar_wait(&s_mma_bar[pit & 1], (uint32_t)((pit >> 1) & 1));
+        tc::fence_after_sync();
+        epilogue(tile_end - 1, (tile_end - 1 - tile_begin) & 1, stat_n);
+    }
+    __syncthreads();
+    flush_stats(stat_n);
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)A.tmem_cols);
+}
+
+static size_t c3_smem_bytes(int Cin, int Cout, bool has_sc) {
+    const size_t nch = Cin / CK;
+    return (size_t)RAW_BYTES + 2 * (size_t)A_BYTES + nch * 27 * (size_t)Cout * 32 + (has_sc ? nch * (size_t)Cout * 32 : 0) +
+           sizeof(float) * (2 * (size_t)Cin + 4 * (size_t)Cout);
+}
+
+}  // namespace
+
+// Implicit-GEMM 3x3x3 conv on tcgen05.  Exactly one of {w} / {dw_w, pw_w} is given.  Returns -1 when the path
+// does not apply (the caller falls back to another kernel).
+int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int W,
+                 const float *w, int groups, const float *dw_w, const float *pw_w, const float *sc_w,
+                 const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats, void *stream) {
+    static int disabled = -1;
+    if (disabled < 0) { const char *e = getenv("L3D_NO_IGEMM"); disabled = (e && e[0] == '1') ? 1 : 0; }
+    if (disabled) return -1;
+    const int Cin = x->C, Cout = t->C;
+    const bool has_sc = sc_w != nullptr;
+    if (x->dtype != L3D_BF16 || t->dtype != L3D_BF16) return -1;
+    if (Cin % 16 != 0 || Cout % 16 != 0 || Cout > 256) return -1;
+    const int cols_needed = 2 * MT * Cout * (has_sc ? 2 : 1);
+    if (cols_needed > 512) return -1;
+    const size_t smem = c3_smem_bytes(Cin, Cout, has_sc);
+    if (smem > 226 * 1024) return -1;
+    auto aligned = [](const l3d_act *a, int mult) {
+        return (a->ldc % mult == 0) && (reinterpret_cast<uintptr_t>(a->ptr) % (2 * mult) == 0);
+    };
+    if (!aligned(x, 8) || !aligned(t, 8) || (has_sc && (act_null(r) || !aligned(r, 8)))) return -1;
+    const long long tiles = (long long)N * ((D + TZ - 1) / TZ) * ((H + TY - 1) / TY) * ((W + TX - 1) / TX);
+    if (tiles >= (1ll << 30)) return -1;
+    int cols = 32;
+    while (cols < cols_needed) cols <<= 1;
+
+    CUtensorMap tmap;
+    {
+        const cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+        const cuuint64_t es = 2, ld = (cuuint64_t)x->ldc;
+        const cuuint64_t strides[4] = {ld * es, (cuuint64_t)W * ld * es, (cuuint64_t)H * W * ld * es, (cuuint64_t)D * H * W * ld * es};
+        const cuuint32_t box[5] = {CK, HX, HY, HZ, 1};
+        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        const CUresult cr = cuTensorMapEncodeTiled(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x->ptr, dims, strides, box, estr,
+                                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) { l3d_set_error("conv3_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr); return 3; }
+    }
+    C3Args A;
+    A.Cin = Cin; A.xn = norm_dev(xn);
+    A.N = N; A.D = D; A.H = H; A.W = W;
+    A.w = w; A.groups = w != nullptr ? groups : 1; A.dw_w = dw_w; A.pw_w = pw_w; A.sc_w = sc_w; A.Cout = Cout;
+    A.t = (bf16 *)t->ptr; A.ldt = t->ldc; A.t_stats = t_stats;
+    A.r = has_sc ? (bf16 *)r->ptr : nullptr; A.ldr = has_sc ? r->ldc : 0; A.r_stats = r_stats;
+    A.tmem_cols = cols;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        if (e != cudaSuccess) { l3d_set_error("conv3_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 3; }
+        attr_set = true;
+    }
+    int occ = (int)((227 * 1024) / (smem + 2048));
+    if (occ > 3) occ = 3;
+    if (occ < 1) occ = 1;
+    if (occ * cols > 512) occ = 512 / cols;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long grid = (long long)sms * occ;
+    if (grid > tiles) grid = tiles;
+    conv3_tc_kernel<<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(tmap, A);
+    l3d_count_launch();
+    L3D_CUDA_OK("l3d_conv3 (tcgen05 implicit GEMM) launch");
+    return 0;
+}

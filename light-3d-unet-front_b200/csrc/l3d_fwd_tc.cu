@@ -64,11 +64,31 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
     if (warp == 0) tc::tmem_alloc(&s_tmem, (uint32_t)A.tmem_cols);
     if (tid == 32) { tc::mbar_init(&s_bar, 1); tc::mbar_init(&s_tma_bar, 1); }
     // stage the pointwise (+ shortcut) weights once as fp16 K-major operand tiles
-    for (int i = tid; i < Cout * Cin; i += NT) {
-        const int k = i % Cin, n = i / Cin;
-        const uint32_t off = tc::tile_off(n, k, Cout);
-        *reinterpret_cast<__half *>(sB + off) = __float2half_rn(A.pw_w[i]);
-        if (has_sc) *reinterpret_cast<__half *>(sB2 + off) = __float2half_rn(A.sc_w[i]);
+    {
+        // float4 loads, 4 in flight per thread (the weights are the only cold global reads of this kernel)
+        const int nvec = Cout * Cin / 4;
+        const int nsrc = has_sc ? 2 : 1;
+        for (int s = 0; s < nsrc; ++s) {
+            const float4 *src = reinterpret_cast<const float4 *>(s == 0 ? A.pw_w : A.sc_w);
+            unsigned char *dst = s == 0 ? sB : sB2;
+            for (int i0 = tid; i0 < nvec; i0 += 4 * NT) {
+                float4 v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (i0 + j * NT < nvec) v[j] = src[i0 + j * NT];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = i0 + j * NT;
+                    if (i < nvec) {
+                        const int k = (i * 4) % Cin, n = (i * 4) / Cin;
+                        const __half2 h0 = __floats2half2_rn(v[j].x, v[j].y), h1 = __floats2half2_rn(v[j].z, v[j].w);
+                        uint2 o;
+                        o.x = *reinterpret_cast<const uint32_t *>(&h0);
+                        o.y = *reinterpret_cast<const uint32_t *>(&h1);
+                        *reinterpret_cast<uint2 *>(dst + tc::tile_off(n, k, Cout)) = o;
+                    }
+                }
+            }
+        }
     }
     for (int i = tid; i < 4 * Cout; i += NT) s_stat[i] = 0.f;
     tc::fence_async_smem();
@@ -128,6 +148,7 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
         }
     };
 
+    float dwr0 = A.dw_w[tid], dwr1 = (tid + NT < CK * 27) ? A.dw_w[tid + NT] : 0.f;
     if (tid == 0 && (long long)blockIdx.x < total_tiles) {
         int n, z0, y0, x0;
         tile_coord(blockIdx.x, n, z0, y0, x0);
@@ -152,7 +173,14 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
         for (int ch = 0; ch < nchunks; ++ch) {
             const int c0 = ch * CK;
             // ---- activation pass: raw bf16 box -> fp32 stencil tile
-            for (int i = tid; i < CK * 27; i += NT) s_dw[i] = A.dw_w[(size_t)c0 * 27 + i];
+            // depthwise taps of this chunk were prefetched into registers one chunk ago
+            s_dw[tid] = dwr0;
+            if (tid + NT < CK * 27) s_dw[tid + NT] = dwr1;
+            {
+                const int nc0 = (ch + 1 < nchunks) ? c0 + CK : 0;
+                dwr0 = A.dw_w[(size_t)nc0 * 27 + tid];
+                if (tid + NT < CK * 27) dwr1 = A.dw_w[(size_t)nc0 * 27 + tid + NT];
+            }
             tc::mbar_wait(&s_tma_bar, tphase);
             tphase ^= 1u;
 #pragma unroll

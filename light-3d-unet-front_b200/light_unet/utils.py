@@ -21,7 +21,7 @@ import torch
 
 from . import _native as nv
 
-WINDOW_BATCH = 16          # windows per forward launch sequence (workspace is sized for this)
+WINDOW_BATCH = 65          # windows per forward launch sequence (325 windows of a 128x128x320 volume = 5 batches)
 _GAUSS_CACHE = {}
 
 
