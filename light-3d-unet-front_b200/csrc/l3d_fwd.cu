@@ -39,6 +39,46 @@ static inline int64_t num_tiles(int N, int D, int H, int W) {
     return (int64_t)N * ((D + TZ - 1) / TZ) * ((H + TY - 1) / TY) * ((W + TX - 1) / TX);
 }
 
+// 16-byte channel vectors: 8 bf16 or 4 fp32
+template <typename T> struct VecW;
+template <> struct VecW<float> { static constexpr int V = 4; };
+template <> struct VecW<bf16> { static constexpr int V = 8; };
+__device__ __forceinline__ void ldv(const float *p, float (&v)[4]) {
+    const float4 f = *reinterpret_cast<const float4 *>(p);
+    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+}
+__device__ __forceinline__ void ldv(const bf16 *p, float (&v)[8]) {
+    const uint4 r = *reinterpret_cast<const uint4 *>(p);
+    v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+    v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+    v[4] = __uint_as_float(r.z << 16); v[5] = __uint_as_float(r.z & 0xffff0000u);
+    v[6] = __uint_as_float(r.w << 16); v[7] = __uint_as_float(r.w & 0xffff0000u);
+}
+// raw 16-byte loads (conversion deferred, keeps the register footprint of in-flight loads small)
+__device__ __forceinline__ uint4 ldraw(const float *p) { return *reinterpret_cast<const uint4 *>(p); }
+__device__ __forceinline__ uint4 ldraw(const bf16 *p) { return *reinterpret_cast<const uint4 *>(p); }
+__device__ __forceinline__ void cvt_raw(const float *, const uint4 &r, float (&v)[4]) {
+    v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
+}
+__device__ __forceinline__ void cvt_raw(const bf16 *, const uint4 &r, float (&v)[8]) {
+    v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+    v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+    v[4] = __uint_as_float(r.z << 16); v[5] = __uint_as_float(r.z & 0xffff0000u);
+    v[6] = __uint_as_float(r.w << 16); v[7] = __uint_as_float(r.w & 0xffff0000u);
+}
+__device__ __forceinline__ void stv(float *p, const float (&v)[4]) {
+    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void stv(bf16 *p, const float (&v)[8]) {
+    uint4 r;
+    __nv_bfloat162 a;
+    a = __floats2bfloat162_rn(v[0], v[1]); r.x = *reinterpret_cast<uint32_t *>(&a);
+    a = __floats2bfloat162_rn(v[2], v[3]); r.y = *reinterpret_cast<uint32_t *>(&a);
+    a = __floats2bfloat162_rn(v[4], v[5]); r.z = *reinterpret_cast<uint32_t *>(&a);
+    a = __floats2bfloat162_rn(v[6], v[7]); r.w = *reinterpret_cast<uint32_t *>(&a);
+    *reinterpret_cast<uint4 *>(p) = r;
+}
+
 // per-channel prologue scale/shift into shared memory
 __device__ __forceinline__ void setup_prologue(const NormDev &nd, int N, int C, int n, float *s_scale, float *s_shift) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -406,51 +446,70 @@ __global__ void __launch_bounds__(NT) conv3_fwd_kernel(
 }
 
 // -------------------------------------------------------------------------------------------
-// Residual merge (+ optional 2x2x2 max-pool of the result).  One thread = one 2x2x2 cell x 4 channels.
+// Residual merge (+ optional 2x2x2 max-pool of the result).  One thread = one 2x2x2 cell x one 16-byte channel
+// vector; grid.y = sample, per-(n,c) scale/shift tables in shared memory; all loads of a cell are issued first.
 template <typename T>
 __global__ void __launch_bounds__(256) merge_fwd_kernel(
     const T *__restrict__ t2, int ld2, NormDev n2, const T *__restrict__ r, int ldr, NormDev nr,
     int N, int C, int D, int H, int W, float slope,
     T *__restrict__ out, int ldo, T *__restrict__ pooled, int ldp) {
-    const int CD = (D + 1) / 2, CH = (H + 1) / 2, CW = (W + 1) / 2, CQ = C / 4;
+    constexpr int V = VecW<T>::V;
+    extern __shared__ float sm[];
+    float *s_sc2 = sm, *s_sh2 = sm + C, *s_scr = sm + 2 * C, *s_shr = sm + 3 * C;
+    const int n = blockIdx.y;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        norm_scale_shift(n2, N, C, n, c, s_sc2[c], s_sh2[c]);
+        norm_scale_shift(nr, N, C, n, c, s_scr[c], s_shr[c]);
+    }
+    __syncthreads();
+    const int CD = (D + 1) / 2, CH = (H + 1) / 2, CW = (W + 1) / 2, CQ = C / V;
     const int PD = D / 2, PH = H / 2, PW = W / 2;
-    const size_t total = (size_t)N * CD * CH * CW * CQ;
+    const size_t total = (size_t)CD * CH * CW * CQ;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         size_t rem = idx;
         const int q = (int)(rem % CQ); rem /= CQ;
         const int cx = (int)(rem % CW); rem /= CW;
-        const int cy = (int)(rem % CH); rem /= CH;
-        const int cz = (int)(rem % CD);
-        const int n = (int)(rem / CD);
-        const int c = q * 4;
-        float sc2[4], sh2[4], scr[4], shr[4];
+        const int cy = (int)(rem % CH);
+        const int cz = (int)(rem / CH);
+        const int c = q * V;
+        float sc2[V], sh2[V], scr[V], mx[V];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            norm_scale_shift(n2, N, C, n, c + j, sc2[j], sh2[j]);
-            norm_scale_shift(nr, N, C, n, c + j, scr[j], shr[j]);
+        for (int j = 0; j < V; ++j) {
+            sc2[j] = s_sc2[c + j]; sh2[j] = s_sh2[c + j] + s_shr[c + j]; scr[j] = s_scr[c + j];
+            mx[j] = -INFINITY;
         }
-        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int z = cz * 2 + (k >> 2), y = cy * 2 + ((k >> 1) & 1), xx = cx * 2 + (k & 1);
-            if (z < D && y < H && xx < W) {
-                const size_t vox = (((size_t)n * D + z) * H + y) * W + xx;
-                const float4 a = ld4(t2 + vox * ld2 + c);
-                const float4 b = ld4(r + vox * ldr + c);
-                float4 o;
-                o.x = lrelu(a.x * sc2[0] + sh2[0] + (b.x * scr[0] + shr[0]), slope);
-                o.y = lrelu(a.y * sc2[1] + sh2[1] + (b.y * scr[1] + shr[1]), slope);
-                o.z = lrelu(a.z * sc2[2] + sh2[2] + (b.z * scr[2] + shr[2]), slope);
-                o.w = lrelu(a.w * sc2[3] + sh2[3] + (b.w * scr[3] + shr[3]), slope);
-                if (out != nullptr) st4(out + vox * ldo + c, o);
-                // pool the values as stored, so the backward arg-max sees the same numbers
-                mx[0] = fmaxf(mx[0], round_as(t2, o.x)); mx[1] = fmaxf(mx[1], round_as(t2, o.y));
-                mx[2] = fmaxf(mx[2], round_as(t2, o.z)); mx[3] = fmaxf(mx[3], round_as(t2, o.w));
+        for (int half = 0; half < 2; ++half) {        // one z-plane of the cell at a time: 8 raw loads in flight
+            uint4 ra[4], rb[4];
+            bool ok[4];
+            size_t vox[4];
+            const int z = cz * 2 + half;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int y = cy * 2 + (k >> 1), xx = cx * 2 + (k & 1);
+                ok[k] = z < D && y < H && xx < W;
+                vox[k] = (((size_t)n * D + z) * H + y) * W + xx;
+                if (ok[k]) { ra[k] = ldraw(t2 + vox[k] * ld2 + c); rb[k] = ldraw(r + vox[k] * ldr + c); }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (ok[k]) {
+                    float a[V], b[V], o[V];
+                    cvt_raw(t2, ra[k], a);
+                    cvt_raw(t2, rb[k], b);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) {
+                        o[j] = lrelu(fmaf(a[j], sc2[j], fmaf(b[j], scr[j], sh2[j])), slope);
+                        // pool the values as stored, so the backward arg-max sees the same numbers
+                        mx[j] = fmaxf(mx[j], round_as(t2, o[j]));
+                    }
+                    if (out != nullptr) stv(out + vox[k] * ldo + c, o);
+                }
             }
         }
         if (pooled != nullptr && cz < PD && cy < PH && cx < PW) {
             const size_t pv = (((size_t)n * PD + cz) * PH + cy) * PW + cx;
-            st4(pooled + pv * ldp + c, make_float4(mx[0], mx[1], mx[2], mx[3]));
+            stv(pooled + pv * ldp + c, mx);
         }
     }
 }
@@ -462,33 +521,52 @@ __global__ void __launch_bounds__(256) merge_head_fwd_kernel(
     int N, int C, size_t nvox, float slope, T *__restrict__ out, int ldo,
     const float *__restrict__ head_w, const float *__restrict__ head_b, int OC,
     float *__restrict__ prob, float *__restrict__ logits) {
-    __shared__ float s_sc2[CMAX], s_sh2[CMAX], s_scr[CMAX], s_shr[CMAX];
+    constexpr int V = VecW<T>::V;
+    __shared__ float s_sc2[CMAX], s_sh2[CMAX], s_scr[CMAX], s_hw[4 * CMAX];
     const int n = blockIdx.y;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        norm_scale_shift(n2, N, C, n, c, s_sc2[c], s_sh2[c]);
-        norm_scale_shift(nr, N, C, n, c, s_scr[c], s_shr[c]);
+    for (int c = threadIdx.x; c < CMAX; c += blockDim.x) {
+        float a = 0.f, b = 0.f, cc = 0.f, d = 0.f;
+        if (c < C) {
+            norm_scale_shift(n2, N, C, n, c, a, b);
+            norm_scale_shift(nr, N, C, n, c, cc, d);
+        }
+        s_sc2[c] = a; s_sh2[c] = b + d; s_scr[c] = cc;
+        for (int oc = 0; oc < 4; ++oc) s_hw[oc * CMAX + c] = (c < C && oc < OC) ? head_w[(size_t)oc * C + c] : 0.f;
     }
     __syncthreads();
     for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (size_t)gridDim.x * blockDim.x) {
         const size_t vox = (size_t)n * nvox + v;
         float o[CMAX];
+        uint4 ra[CMAX / V], rb[CMAX / V];
 #pragma unroll
-        for (int c4 = 0; c4 < CMAX; c4 += 4) {
-            if (c4 < C) {
-                const float4 a = ld4(t2 + vox * ld2 + c4);
-                const float4 b = ld4(r + vox * ldr + c4);
-                o[c4 + 0] = lrelu(a.x * s_sc2[c4 + 0] + s_sh2[c4 + 0] + (b.x * s_scr[c4 + 0] + s_shr[c4 + 0]), slope);
-                o[c4 + 1] = lrelu(a.y * s_sc2[c4 + 1] + s_sh2[c4 + 1] + (b.y * s_scr[c4 + 1] + s_shr[c4 + 1]), slope);
-                o[c4 + 2] = lrelu(a.z * s_sc2[c4 + 2] + s_sh2[c4 + 2] + (b.z * s_scr[c4 + 2] + s_shr[c4 + 2]), slope);
-                o[c4 + 3] = lrelu(a.w * s_sc2[c4 + 3] + s_sh2[c4 + 3] + (b.w * s_scr[c4 + 3] + s_shr[c4 + 3]), slope);
-                if (out != nullptr) st4(out + vox * ldo + c4, make_float4(o[c4], o[c4 + 1], o[c4 + 2], o[c4 + 3]));
+        for (int i = 0; i < CMAX / V; ++i) {
+            if (i * V < C) { ra[i] = ldraw(t2 + vox * ld2 + i * V); rb[i] = ldraw(r + vox * ldr + i * V); }
+        }
+#pragma unroll
+        for (int i = 0; i < CMAX / V; ++i) {
+            if (i * V < C) {
+                float a[V], b[V], ov[V];
+                cvt_raw(t2, ra[i], a);
+                cvt_raw(t2, rb[i], b);
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    ov[j] = lrelu(fmaf(a[j], s_sc2[i * V + j], fmaf(b[j], s_scr[i * V + j], s_sh2[i * V + j])), slope);
+                    o[i * V + j] = ov[j];
+                }
+                if (out != nullptr) stv(out + vox * ldo + i * V, ov);
             }
         }
         for (int oc = 0; oc < OC; ++oc) {
             float acc = head_b[oc];
+            if (oc < 4) {
 #pragma unroll
-            for (int c = 0; c < CMAX; ++c)
-                if (c < C) acc += round_as(t2, o[c]) * head_w[(size_t)oc * C + c];
+                for (int c = 0; c < CMAX; ++c)
+                    if (c < C) acc = fmaf(round_as(t2, o[c]), s_hw[oc * CMAX + c], acc);
+            } else {
+#pragma unroll
+                for (int c = 0; c < CMAX; ++c)
+                    if (c < C) acc = fmaf(round_as(t2, o[c]), head_w[(size_t)oc * C + c], acc);
+            }
             const size_t oi = ((size_t)n * OC + oc) * nvox + v;
             if (logits != nullptr) logits[oi] = acc;
             prob[oi] = 1.f / (1.f + expf(-acc));
@@ -575,8 +653,11 @@ __global__ void __launch_bounds__(NT) convt_fwd_kernel(
 
 // -------------------------------------------------------------------------------------------
 // Single-input-channel variant of the fused depthwise->pointwise(+shortcut) conv (the network's first conv,
-// unet3d.py:168,209): K = 1, so the "GEMM" is an outer product and the kernel is a pure HBM write stream.
-// thread = one voxel, all COUT outputs of t (and r); persistent CTAs, statistics reduced per tile.
+// unet3d.py:168,209): K = 1, so the "GEMM" is an outer product t[v][co] = pw[co] * u[v] and the kernel is a pure
+// HBM write stream.  thread = one voxel, all COUT outputs of t (and r); persistent CTAs.
+// InstanceNorm statistics: sum_v t[v][co] = pw[co] * sum_v u[v] and sum_v t^2 = pw[co]^2 * sum_v u^2, so only the
+// four scalars {sum u, sum u^2, sum x, sum x^2} are reduced per tile (in fp32 storage this is exact; in bf16 storage
+// it ignores the zero-mean rounding of the stored values, a < 1e-5 relative effect on mean / variance).
 template <typename T, int COUT>
 __global__ void __launch_bounds__(NT) dwpw_c1_kernel(
     const T *__restrict__ x, int ldx, NormDev xn, int N, int D, int H, int W,
@@ -584,15 +665,17 @@ __global__ void __launch_bounds__(NT) dwpw_c1_kernel(
     T *__restrict__ t, int ldt, double *__restrict__ t_stats, T *__restrict__ r, int ldr, double *__restrict__ r_stats,
     T *__restrict__ u, int ldu) {
     __shared__ float s_in[HZ][HY][HX + 1];
-    __shared__ float s_stat[4 * COUT];
+    __shared__ float s_sum[4];
     __shared__ float s_w[27 + 2 * COUT];
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < 27; i += NT) s_w[i] = dw_w[i];
     for (int i = tid; i < COUT; i += NT) { s_w[27 + i] = pw_w[i]; s_w[27 + COUT + i] = sc_w != nullptr ? sc_w[i] : 0.f; }
-    for (int i = tid; i < 4 * COUT; i += NT) s_stat[i] = 0.f;
+    if (tid < 4) s_sum[tid] = 0.f;
     const int tilesX = (W + TX - 1) / TX, tilesY = (H + TY - 1) / TY, tilesZ = (D + TZ - 1) / TZ;
-    const long long tiles_per_sample = (long long)tilesX * tilesY * tilesZ;
-    const long long total_tiles = tiles_per_sample * N;
+    const int tiles_per_sample = tilesX * tilesY * tilesZ;
+    const int total_tiles = tiles_per_sample * N;
+    const int per = (total_tiles + gridDim.x - 1) / gridDim.x;      // contiguous tile range: few sample changes
+    const int tile_begin = blockIdx.x * per, tile_end = min(total_tiles, tile_begin + per);
     const int lx = tid & 7, ly = (tid >> 3) & 7, lz = tid >> 6;
     int cur_n = -1;
     float sc = 1.f, sh = 0.f;
@@ -600,21 +683,21 @@ __global__ void __launch_bounds__(NT) dwpw_c1_kernel(
         if (n < 0) return;
         for (int i = tid; i < 2 * COUT; i += NT) {
             const int isq = i >= COUT, c = isq ? i - COUT : i;
-            atomicAdd(&t_stats[(size_t)isq * N * COUT + (size_t)n * COUT + c], (double)s_stat[i]);
-            s_stat[i] = 0.f;
-            if (sc_w != nullptr) {
-                atomicAdd(&r_stats[(size_t)isq * N * COUT + (size_t)n * COUT + c], (double)s_stat[2 * COUT + i]);
-                s_stat[2 * COUT + i] = 0.f;
-            }
+            const float wt = s_w[27 + c], wr = s_w[27 + COUT + c];
+            atomicAdd(&t_stats[(size_t)isq * N * COUT + (size_t)n * COUT + c], isq ? (double)wt * wt * s_sum[1] : (double)wt * s_sum[0]);
+            if (sc_w != nullptr)
+                atomicAdd(&r_stats[(size_t)isq * N * COUT + (size_t)n * COUT + c], isq ? (double)wr * wr * s_sum[3] : (double)wr * s_sum[2]);
         }
+        __syncthreads();
+        if (tid < 4) s_sum[tid] = 0.f;
     };
-    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n = (int)(tile / tiles_per_sample);
-        int b = (int)(tile % tiles_per_sample);
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int n = tile / tiles_per_sample;
+        int b = tile - n * tiles_per_sample;
         const int x0 = (b % tilesX) * TX; b /= tilesX;
         const int y0 = (b % tilesY) * TY; b /= tilesY;
         const int z0 = b * TZ;
-        __syncthreads();                      // previous tile done with s_in, its statistics are in s_stat
+        __syncthreads();                      // previous tile done with s_in, its sums are in s_sum
         if (n != cur_n) {
             flush(cur_n);
             cur_n = n;
@@ -644,31 +727,27 @@ __global__ void __launch_bounds__(NT) dwpw_c1_kernel(
         const bool valid = gz < D && gy < H && gx < W;
         const size_t vox = (((size_t)n * D + gz) * H + gy) * W + gx;
         if (u != nullptr && valid) st1(u + vox * (size_t)ldu, uacc);
-        const float uu = uacc;
+        if (valid) {
+            constexpr int V = VecW<T>::V;
 #pragma unroll
-        for (int a = 0; a < 2; ++a) {
-            if (a == 1 && sc_w == nullptr) break;
-            const float in = a == 0 ? uu : xc;
-            T *op = (a == 0 ? t + vox * (size_t)ldt : r + vox * (size_t)ldr);
-            const float *wv = s_w + 27 + a * COUT;
+            for (int a = 0; a < 2; ++a) {
+                if (a == 1 && sc_w == nullptr) break;
+                const float in = a == 0 ? uacc : xc;
+                T *op = (a == 0 ? t + vox * (size_t)ldt : r + vox * (size_t)ldr);
+                const float *wv = s_w + 27 + a * COUT;
 #pragma unroll
-            for (int cb = 0; cb < COUT; cb += 16) {
-                float sv[32];
+                for (int cb = 0; cb < COUT; cb += V) {
+                    float o[V];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float o = in * wv[cb + j];
-                    const float rr = valid ? round_as(t, o) : 0.f;
-                    sv[j] = rr; sv[16 + j] = rr * rr;
+                    for (int j = 0; j < V; ++j) o[j] = in * wv[cb + j];
+                    stv(op + cb, o);
                 }
-                if (valid) {
-#pragma unroll
-                    for (int j4 = 0; j4 < 16; j4 += 4) st4(op + cb + j4, make_float4(sv[j4], sv[j4 + 1], sv[j4 + 2], sv[j4 + 3]));
-                }
-                warp_transpose_sum<32>(sv, lane);
-                const int idx = warp_transpose_owner<32>(lane);
-                atomicAdd(&s_stat[a * 2 * COUT + (idx >= 16 ? COUT + idx - 16 : idx) + cb], sv[0]);
             }
         }
+        float s0 = valid ? uacc : 0.f, s2 = valid ? xc : 0.f;
+        float s1 = s0 * s0, s3 = s2 * s2;
+        s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+        if (lane == 0) { atomicAdd(&s_sum[0], s0); atomicAdd(&s_sum[1], s1); atomicAdd(&s_sum[2], s2); atomicAdd(&s_sum[3], s3); }
     }
     __syncthreads();
     flush(cur_n);
@@ -731,7 +810,7 @@ extern "C" int l3d_dwpw_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, 
     }
     if (Cin == 1 && dw_w != nullptr && (Cout == 16 || Cout == 32)) {
         const int64_t tiles1 = num_tiles(N, D, H, W);
-        const unsigned grid1 = (unsigned)(tiles1 < 148 * 6 ? tiles1 : 148 * 6);
+        const unsigned grid1 = (unsigned)(tiles1 < 148 * 8 ? tiles1 : 148 * 8);
         const NormDev nd1 = norm_dev(xn);
         cudaStream_t st1_ = (cudaStream_t)stream;
 #define LAUNCH_C1(T, CO)                                                                                              \
@@ -824,6 +903,13 @@ extern "C" int l3d_merge_fwd(const l3d_act *t2, const l3d_norm *n2, const l3d_ac
     if (head_w != nullptr) {
         L3D_REQUIRE(!has_pool, "l3d_merge_fwd: head and pool cannot be combined");
         L3D_REQUIRE(C <= 64 && OC >= 1 && prob && head_b, "l3d_merge_fwd: head needs C <= 64 (got %d)", C);
+        {
+            const int V = t2->dtype == L3D_F32 ? 4 : 8;
+            auto vec_ok = [V](const l3d_act *a) {
+                return a->C % V == 0 && a->ldc % V == 0 && (reinterpret_cast<uintptr_t>(a->ptr) % 16) == 0;
+            };
+            L3D_REQUIRE(vec_ok(t2) && vec_ok(r) && (!has_out || vec_ok(out)), "l3d_merge_fwd: views must be 16-byte aligned with C a multiple of %d", V);
+        }
         const size_t nvox = (size_t)D * H * W;
         const unsigned gx = (unsigned)((nvox + 255) / 256);
         dim3 grid(gx, (unsigned)N);
@@ -840,11 +926,19 @@ extern "C" int l3d_merge_fwd(const l3d_act *t2, const l3d_norm *n2, const l3d_ac
         });
     } else {
         L3D_REQUIRE(has_out || has_pool, "l3d_merge_fwd: nothing to write");
-        const size_t total = (size_t)N * ((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
+        const int V = t2->dtype == L3D_F32 ? 4 : 8;
+        auto vec_ok = [V](const l3d_act *a) {
+            return a->C % V == 0 && a->ldc % V == 0 && (reinterpret_cast<uintptr_t>(a->ptr) % 16) == 0;
+        };
+        L3D_REQUIRE(vec_ok(t2) && vec_ok(r) && (!has_out || vec_ok(out)) && (!has_pool || vec_ok(pooled)),
+                    "l3d_merge_fwd: views must be 16-byte aligned with C a multiple of %d", V);
+        const size_t total = (size_t)((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2) * (C / V);
         size_t blocks = (total + 255) / 256;
-        if (blocks > 148 * 64) blocks = 148 * 64;
+        const size_t cap = (148 * 32 + N - 1) / N;
+        if (blocks > cap) blocks = cap;
+        dim3 grid((unsigned)blocks, (unsigned)N);
         L3D_DISPATCH_DTYPE(t2->dtype, T, {
-            merge_fwd_kernel<T><<<(unsigned)blocks, 256, 0, st>>>((const T *)t2->ptr, t2->ldc, d2, (const T *)r->ptr, r->ldc, dr, N, C, D, H, W, slope,
+            merge_fwd_kernel<T><<<grid, 256, sizeof(float) * 4 * C, st>>>((const T *)t2->ptr, t2->ldc, d2, (const T *)r->ptr, r->ldc, dr, N, C, D, H, W, slope,
                                                                    has_out ? (T *)out->ptr : nullptr, has_out ? out->ldc : 0,
                                                                    has_pool ? (T *)pooled->ptr : nullptr, has_pool ? pooled->ldc : 0);
         });

@@ -165,6 +165,7 @@ class UNetPlan:
         """conv1 / conv2 of a residual block (+ fused shortcut where the kernel supports it)."""
         kind = b.kind1 if which == 1 else b.kind2
         pre = f"{b.prefix}.conv{which}"
+        nv.TIMER.tag = f"{b.name}.c{which}"
         D, H, W = dims
         es, nvx = t.element_size(), N * D * H * W
         cin, cout = x_act.C, t.shape[-1]
@@ -233,6 +234,7 @@ class UNetPlan:
             n1 = nv.norm(s1, P[f"{b.prefix}.norm1.weight"], P[f"{b.prefix}.norm1.bias"], mask, IN_EPS, LEAKY_SLOPE, vox)
             self._conv(P, b, 2, nv.act(buf["t1"]), n1, N, dims, buf["t2"], s2, None, None, None, buf.get("u2"), st)
             # residual merge (+ pool / head)
+            nv.TIMER.tag = b.name
             n2 = nv.norm(s2, P[f"{b.prefix}.norm2.weight"], P[f"{b.prefix}.norm2.bias"], None, IN_EPS, 1.0, vox)
             if has_sc:
                 r_act = nv.act(buf["r"])
