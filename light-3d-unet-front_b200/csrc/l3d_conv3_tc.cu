@@ -24,13 +24,14 @@ namespace {
 constexpr int TZ = 2, TY = 16, TX = 8;                  // CTA tile: 2 MMA tiles (z-planes) of 16x8 voxels
 constexpr int HZ = TZ + 2, HY = TY + 2, HX = TX + 2;    // 4 x 18 x 10 halo
 constexpr int HVOX = HZ * HY * HX;                      // 720
-constexpr int CK = 16, NT = 256, MT = 2;
+constexpr int CK = 16, NW = 256, NT = NW + 32, MT = 2;   // 8 worker warps + 1 issuer warp
 constexpr int RAW_BYTES = HVOX * CK * 2;                // 23040: TMA box, dense [z][y][x][16] bf16
-constexpr int PLANE = HVOX * 16;                        // bytes of one 8-channel group of the A tile (fp16)
-constexpr int A_BYTES = 2 * PLANE;                      // 23040
+constexpr int PLANE = HVOX * 16 + 64;                   // bytes of one 8-channel group of the A tile (fp16); +64 so that the two
+                                                        // groups written by a lane pair land in different bank halves
+constexpr int A_BYTES = 2 * PLANE;                      // 23168
 constexpr int ROWPITCH = HX * 16;                       // 160 B between y rows
 constexpr int ACT_ITEMS = HVOX * 2;
-constexpr int ACT_PER_THREAD = (ACT_ITEMS + NT - 1) / NT;   // 6
+constexpr int ACT_PER_THREAD = (ACT_ITEMS + NW - 1) / NW;   // 6
 
 struct C3Args {
     int Cin; NormDev xn;
@@ -42,7 +43,7 @@ struct C3Args {
     int Cout;
     bf16 *t; int ldt; double *t_stats;
     bf16 *r; int ldr; double *r_stats;
-    int tmem_cols;
+    int tmem_cols, nraw;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -54,17 +55,29 @@ __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
     return *reinterpret_cast<uint32_t *>(&v);
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NW) : "memory"); }
+
+// Warp-specialised: warps 0..7 (256 threads) are workers (activation pass + epilogue), warp 8 is the issuer (TMA
+// loads and tcgen05.mma).  Hand-offs are mbarriers only, so the tensor pipe, the TMA unit and the CUDA cores run
+// concurrently on different work items:
+//   tma_full[r]   issuer -> workers   raw box r landed (complete_tx)
+//   a_full[b]     workers -> issuer   operand tile b written (8 warp arrivals); also: raw box consumed
+//   mma_done[b]   issuer -> workers   MMAs that read operand tile b finished (tcgen05.commit)
+//   acc_free[s]   workers -> issuer   epilogue drained accumulator set s (8 warp arrivals)
 __global__ void __launch_bounds__(NT) conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, C3Args A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t s_tma_bar, s_mma_bar[2];
+    __shared__ __align__(8) uint64_t s_tma_full[2], s_a_full[2], s_mma_done[2], s_acc_free[2];
     __shared__ uint32_t s_tmem;
     const int Cin = A.Cin, Cout = A.Cout;
     const bool has_sc = A.sc_w != nullptr;
-    const int nchunks = Cin / CK;
+    const int nchunks = Cin / CK, nraw = A.nraw;
     const uint32_t btap_bytes = (uint32_t)Cout * 32;                      // one [Cout x 16] fp16 operand tile
     const uint32_t b_bytes = (uint32_t)nchunks * 27 * btap_bytes;
-    unsigned char *s_raw = smem_raw;                                       // TMA destination
-    unsigned char *sA = s_raw + RAW_BYTES;                                 // 2 x A_BYTES
+    unsigned char *s_raw = smem_raw;                                       // nraw x RAW_BYTES (TMA destinations)
+    unsigned char *sA = s_raw + (size_t)nraw * RAW_BYTES;                  // 2 x A_BYTES
     unsigned char *sB = sA + 2 * A_BYTES;                                  // [chunk][tap][Cout x 16]
     unsigned char *sB2 = sB + b_bytes;                                     // shortcut: [chunk][Cout x 16]
     float *s_scale = reinterpret_cast<float *>(sB2 + (has_sc ? nchunks * btap_bytes : 0));
@@ -72,8 +85,13 @@ __global__ void __launch_bounds__(NT) conv3_tc_kernel(const __grid_constant__ CU
     float *s_stat = s_shift + Cin;                                         // 2*Cout (t) + 2*Cout (r)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (warp == 0) tc::tmem_alloc(&s_tmem, (uint32_t)A.tmem_cols);
-    if (tid == 32) { tc::mbar_init(&s_tma_bar, 1); tc::mbar_init(&s_mma_bar[0], MT); tc::mbar_init(&s_mma_bar[1], MT); }
+    if (warp == NW / 32) tc::tmem_alloc(&s_tmem, (uint32_t)A.tmem_cols);
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&s_tma_full[i], 1); tc::mbar_init(&s_a_full[i], NW / 32);
+            tc::mbar_init(&s_mma_done[i], 1); tc::mbar_init(&s_acc_free[i], NW / 32);
+        }
+    }
     // ---- stage the (effective) 3x3x3 weights once per CTA as fp16 K-major operand tiles
     {
         const int cin_g = Cin / A.groups, cout_g = Cout / A.groups;
@@ -115,6 +133,7 @@ __global__ void __launch_bounds__(NT) conv3_tc_kernel(const __grid_constant__ CU
     const int per = (total_tiles + gridDim.x - 1) / gridDim.x;
     const int tile_begin = blockIdx.x * per;
     const int tile_end = min(total_tiles, tile_begin + per);
+    const int n_items = (tile_end > tile_begin ? tile_end - tile_begin : 0) * nchunks;
     auto tile_coord = [&](int tile, int &n, int &z0, int &y0, int &x0) {
         n = tile / tiles_per_sample;
         int b = tile - n * tiles_per_sample;
@@ -122,197 +141,214 @@ __global__ void __launch_bounds__(NT) conv3_tc_kernel(const __grid_constant__ CU
         y0 = (b % tilesY) * TY; b /= tilesY;
         z0 = b * TZ;
     };
-    // activation-pass role: fixed 16-byte vectors of the raw box; q (8-channel group) is the same for all of them
-    const int aq = tid & 1;
-    uint32_t act_item[ACT_PER_THREAD];
-#pragma unroll
-    for (int k = 0; k < ACT_PER_THREAD; ++k) {
-        const int item = tid + k * NT;
-        int hv = item >> 1;
-        const int hx = hv % HX; hv /= HX;
-        const int hy = hv % HY;
-        const int hz = hv / HY;
-        act_item[k] = item < ACT_ITEMS ? ((uint32_t)hx | ((uint32_t)hy << 8) | ((uint32_t)hz << 16)) : 0xffffffffu;
-    }
-    // epilogue role: voxel row of MMA tile (plane) `em`
-    const int em = warp >> 2, erow = (warp & 3) * 32 + lane;
-    const int elx = erow & 7, ely = erow >> 3;
-    int cur_n = -1;
 
-    auto flush_stats = [&](int n) {
-        if (n < 0) return;
-        for (int i = tid; i < 2 * Cout; i += NT) {
-            const int isq = i >= Cout, cc = isq ? i - Cout : i;
-            atomicAdd(&A.t_stats[(size_t)isq * A.N * Cout + (size_t)n * Cout + cc], (double)s_stat[i]);
-            s_stat[i] = 0.f;
-            if (has_sc) {
-                atomicAdd(&A.r_stats[(size_t)isq * A.N * Cout + (size_t)n * Cout + cc], (double)s_stat[2 * Cout + i]);
-                s_stat[2 * Cout + i] = 0.f;
-            }
-        }
-    };
-    // epilogue of tile `tile` (accumulator set `set`): TMEM -> bf16 global + statistics.  `stat_n` is the sample
-    // the statistics currently held in s_stat belong to.
-    auto epilogue = [&](int tile, int set, int &stat_n) {
-        int n, z0, y0, x0;
-        tile_coord(tile, n, z0, y0, x0);
-        if (n != stat_n) {
-            __syncthreads();
-            flush_stats(stat_n);
-            stat_n = n;
-            __syncthreads();
-        }
-        const int gz = z0 + em, gy = y0 + ely, gx = x0 + elx;
-        const bool valid = gz < A.D && gy < A.H && gx < A.W;
-        const size_t vox = (((size_t)n * A.D + gz) * A.H + gy) * A.W + gx;
-        const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(set * acc_cols);
-        for (int a = 0; a < nacc; ++a) {
-            bf16 *outp = (a == 0 ? A.t + vox * (size_t)A.ldt : A.r + vox * (size_t)A.ldr);
-            float *stat = s_stat + a * 2 * Cout;
-            for (int cb = 0; cb < Cout; cb += 16) {
-                float v[16];
-                tc::tmem_ld16(trow + (uint32_t)((a * MT + em) * Cout + cb), v);
-                float sv[32];
-                uint32_t pk[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    pk[j] = valid ? pack_bf16x2(v[2 * j], v[2 * j + 1]) : 0u;
-                    const float r0 = __uint_as_float(pk[j] << 16);
-                    const float r1 = __uint_as_float(pk[j] & 0xffff0000u);
-                    sv[2 * j] = r0; sv[2 * j + 1] = r1;
-                    sv[16 + 2 * j] = r0 * r0; sv[16 + 2 * j + 1] = r1 * r1;
-                }
-                if (valid) {
-                    *reinterpret_cast<uint4 *>(outp + cb) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    *reinterpret_cast<uint4 *>(outp + cb + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                }
-                warp_transpose_sum<32>(sv, lane);
-                const int idx = warp_transpose_owner<32>(lane);
-                atomicAdd(&stat[(idx >= 16 ? Cout + idx - 16 : idx) + cb], sv[0]);
-            }
-        }
-        tc::fence_before_sync();
-    };
-
-    const int n_items = (tile_end > tile_begin ? tile_end - tile_begin : 0) * nchunks;
-    // the raw box of work item it+1 is requested as soon as the activation pass of item it has consumed the buffer
-    auto issue_tma = [&](int item) {
-        const int tl = tile_begin + item / nchunks, chn = item % nchunks;
-        int n, z0, y0, x0;
-        tile_coord(tl, n, z0, y0, x0);
-        tc::mbar_expect_tx(&s_tma_bar, RAW_BYTES);
-        tc::tma_load_5d(s_raw, &tmap, &s_tma_bar, chn * CK, x0 - 1, y0 - 1, z0 - 1, n);
-    };
-    if (tid == 0) {
-        if (n_items > 0) issue_tma(0);
-    }
-    int it = 0;                 // work-item counter: (tile, chunk) pairs
-    int stat_n = -1;
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
-        int n, z0, y0, x0;
-        tile_coord(tile, n, z0, y0, x0);
-        if (n != cur_n) {
-            cur_n = n;
-            __syncthreads();    // nobody still reads the previous sample's scale/shift
-            for (int cc = tid; cc < Cin; cc += NT) {
-                float sc, sh;
-                norm_scale_shift(A.xn, A.N, Cin, n, cc, sc, sh);
-                s_scale[cc] = sc; s_shift[cc] = sh;
-            }
-            __syncthreads();
-        }
-        // validity of the halo coordinates of this tile as per-axis bit masks
-        uint32_t mz = 0, my = 0, mx = 0;
-#pragma unroll
-        for (int i = 0; i < HZ; ++i) mz |= (uint32_t)(z0 + i - 1 >= 0 && z0 + i - 1 < A.D) << i;
-#pragma unroll
-        for (int i = 0; i < HY; ++i) my |= (uint32_t)(y0 + i - 1 >= 0 && y0 + i - 1 < A.H) << i;
-#pragma unroll
-        for (int i = 0; i < HX; ++i) mx |= (uint32_t)(x0 + i - 1 >= 0 && x0 + i - 1 < A.W) << i;
-        const int set = (tile - tile_begin) & 1;
-        for (int ch = 0; ch < nchunks; ++ch, ++it) {
-            const int buf = it & 1;
-            unsigned char *Ab = sA + (size_t)buf * A_BYTES;
-            // scale / shift of this thread's 8 channels
-            const float4 sc0 = *reinterpret_cast<const float4 *>(s_scale + ch * CK + aq * 8);
-            const float4 sc1 = *reinterpret_cast<const float4 *>(s_scale + ch * CK + aq * 8 + 4);
-            const float4 sh0 = *reinterpret_cast<const float4 *>(s_shift + ch * CK + aq * 8);
-            const float4 sh1 = *reinterpret_cast<const float4 *>(s_shift + ch * CK + aq * 8 + 4);
-            const float sl = A.xn.slope;
-            tc::mbar_wait(&s_tma_bar, (uint32_t)(it & 1));                           // raw box of this item landed
-            if (it >= 2) tc::mbar_wait(&s_mma_bar[buf], (uint32_t)(((it >> 1) - 1) & 1));   // MMAs of item it-2 done: A[buf] free
-            // ---- activation pass: raw bf16 [z][y][x][16] -> fp16 planar [q][z][y][x][8]
-#pragma unroll
-            for (int k = 0; k < ACT_PER_THREAD; ++k) {
-                const uint32_t ai = act_item[k];
-                if (ai != 0xffffffffu) {
-                    const int hx = ai & 255, hy = (ai >> 8) & 255, hz = ai >> 16;
-                    const int item = tid + k * NT;
-                    uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                    if ((mx >> hx) & (my >> hy) & (mz >> hz) & 1u) {
-                        const uint4 rw = *reinterpret_cast<const uint4 *>(s_raw + (size_t)item * 16);
-                        float f[8];
-                        f[0] = fmaf(__uint_as_float(rw.x << 16), sc0.x, sh0.x); f[1] = fmaf(__uint_as_float(rw.x & 0xffff0000u), sc0.y, sh0.y);
-                        f[2] = fmaf(__uint_as_float(rw.y << 16), sc0.z, sh0.z); f[3] = fmaf(__uint_as_float(rw.y & 0xffff0000u), sc0.w, sh0.w);
-                        f[4] = fmaf(__uint_as_float(rw.z << 16), sc1.x, sh1.x); f[5] = fmaf(__uint_as_float(rw.z & 0xffff0000u), sc1.y, sh1.y);
-                        f[6] = fmaf(__uint_as_float(rw.w << 16), sc1.z, sh1.z); f[7] = fmaf(__uint_as_float(rw.w & 0xffff0000u), sc1.w, sh1.w);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], f[j] * sl);      // LeakyReLU, 0 <= slope <= 1
-                        o = make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]), pack_f16x2(f[6], f[7]));
-                    }
-                    *reinterpret_cast<uint4 *>(Ab + (size_t)aq * PLANE + (size_t)(item >> 1) * 16) = o;
-                }
-            }
-            tc::fence_async_smem();
-            tc::fence_before_sync();
-            __syncthreads();             // A[buf] complete, raw box consumed, previous epilogue's TMEM reads done
-            if (tid == 0 && it + 1 < n_items) issue_tma(it + 1);     // the raw buffer is free again
-            if (lane == 0 && warp < MT) {
-                // MMA issue: warp m issues the 27 taps (+ shortcut on the centre tap) of plane m.  The descriptors of
-                // all taps differ from the first one by compile-time constants in the 16-byte start-address field.
+    if (warp == NW / 32) {
+        // =============================== issuer warp (one lane) ===============================
+        if (lane == 0) {
+            auto issue_tma = [&](int item) {
+                const int tl = tile_begin + item / nchunks, chn = item % nchunks;
+                int n, z0, y0, x0;
+                tile_coord(tl, n, z0, y0, x0);
+                const int rb = item % nraw;
+                tc::mbar_expect_tx(&s_tma_full[rb], RAW_BYTES);
+                tc::tma_load_5d(s_raw + (size_t)rb * RAW_BYTES, &tmap, &s_tma_full[rb], chn * CK, x0 - 1, y0 - 1, z0 - 1, n);
+            };
+            for (int i = 0; i < nraw && i < n_items; ++i) issue_tma(i);
+            int tj = 0, ch = 0;                       // tile index within this CTA's range, chunk
+            for (int it = 0; it < n_items; ++it) {
+                const int buf = it & 1, set = tj & 1;
+                tc::mbar_wait(&s_a_full[buf], (uint32_t)((it >> 1) & 1));        // operand tile written, raw box consumed
                 tc::fence_after_sync();
-                const int m = warp;
-                const uint64_t ad0 = tc::smem_desc(sA_u + buf * A_BYTES + (uint32_t)(m * HY * ROWPITCH), PLANE, ROWPITCH);
+                if (it + nraw < n_items) issue_tma(it + nraw);
+                if (ch == 0 && tj >= 2) tc::mbar_wait(&s_acc_free[set], (uint32_t)(((tj >> 1) - 1) & 1));   // epilogue of tile tj-2 done
+                tc::fence_after_sync();
+                const uint64_t ad0 = tc::smem_desc(sA_u + buf * A_BYTES, PLANE, ROWPITCH);
                 const uint64_t bd0 = tc::smem_desc(sB_u + (uint32_t)(ch * 27) * btap_bytes, Cout * 16, 128);
                 const uint32_t bstep = btap_bytes >> 4;
-                const uint32_t d_t = tmem + (uint32_t)(set * acc_cols + m * Cout);
+                const uint32_t d_t = tmem + (uint32_t)(set * acc_cols);
+                // consecutive MMAs alternate between the two planes: two independent accumulation chains in flight
 #pragma unroll
                 for (int tap = 0; tap < 27; ++tap) {
                     const int dz = tap / 9, dy = (tap / 3) % 3, dx = tap % 3;
-                    const uint32_t aoff = (uint32_t)(((dz * HY + dy) * ROWPITCH + dx * 16) >> 4);
-                    tc::mma_f16(d_t, ad0 + aoff, bd0 + (uint64_t)(tap * bstep), idesc, (ch > 0 || tap > 0) ? 1u : 0u);
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+                        const uint32_t aoff = (uint32_t)((((m + dz) * HY + dy) * ROWPITCH + dx * 16) >> 4);
+                        tc::mma_f16(d_t + m * Cout, ad0 + aoff, bd0 + (uint64_t)(tap * bstep), idesc, (ch > 0 || tap > 0) ? 1u : 0u);
+                    }
                 }
                 if (has_sc) {
-                    const uint32_t aoff = (uint32_t)(((1 * HY + 1) * ROWPITCH + 16) >> 4);
                     const uint64_t bd2 = tc::smem_desc(sB2_u + (uint32_t)ch * btap_bytes, Cout * 16, 128);
-                    tc::mma_f16(d_t + MT * Cout, ad0 + aoff, bd2, idesc, ch > 0 ? 1u : 0u);
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+                        const uint32_t aoff = (uint32_t)((((m + 1) * HY + 1) * ROWPITCH + 16) >> 4);
+                        tc::mma_f16(d_t + (MT + m) * Cout, ad0 + aoff, bd2, idesc, ch > 0 ? 1u : 0u);
+                    }
                 }
-                tc::mma_commit(&s_mma_bar[buf]);
-            }
-            // ---- epilogue of the previous tile overlaps the MMAs just issued
-            if (ch == 0 && tile > tile_begin) {
-                const int pit = it - 1;                                   // last work item of the previous tile
-                tc::mbar_wait(&s_mma_bar[pit & 1], (uint32_t)((pit >> 1) & 1));
-                tc::fence_after_sync();
-                epilogue(tile - 1, set ^ 1, stat_n);
+                tc::mma_commit(&s_mma_done[buf]);
+                if (++ch == nchunks) { ch = 0; ++tj; }
             }
         }
+    } else {
+        // ===================================== workers =====================================
+        // activation-pass role: fixed 16-byte vectors of the raw box; q (8-channel group) is the same for all of them
+        const int aq = tid & 1;
+        uint32_t act_item[ACT_PER_THREAD];
+#pragma unroll
+        for (int k = 0; k < ACT_PER_THREAD; ++k) {
+            const int item = tid + k * NW;
+            int hv = item >> 1;
+            const int hx = hv % HX; hv /= HX;
+            const int hy = hv % HY;
+            const int hz = hv / HY;
+            act_item[k] = item < ACT_ITEMS ? ((uint32_t)hx | ((uint32_t)hy << 8) | ((uint32_t)hz << 16)) : 0xffffffffu;
+        }
+        // epilogue role: voxel row of MMA tile (plane) `em`
+        const int em = warp >> 2, erow = (warp & 3) * 32 + lane;
+        const int elx = erow & 7, ely = erow >> 3;
+        int stat_n = -1;
+
+        auto flush_stats = [&](int n) {
+            if (n < 0) return;
+            for (int i = tid; i < 2 * Cout; i += NW) {
+                const int isq = i >= Cout, cc = isq ? i - Cout : i;
+                atomicAdd(&A.t_stats[(size_t)isq * A.N * Cout + (size_t)n * Cout + cc], (double)s_stat[i]);
+                s_stat[i] = 0.f;
+                if (has_sc) {
+                    atomicAdd(&A.r_stats[(size_t)isq * A.N * Cout + (size_t)n * Cout + cc], (double)s_stat[2 * Cout + i]);
+                    s_stat[2 * Cout + i] = 0.f;
+                }
+            }
+        };
+        // epilogue of tile `tile` (accumulator set `set`): TMEM -> bf16 global + statistics
+        auto epilogue = [&](int tile, int set) {
+            int n, z0, y0, x0;
+            tile_coord(tile, n, z0, y0, x0);
+            if (n != stat_n) {
+                worker_bar();
+                flush_stats(stat_n);
+                stat_n = n;
+                worker_bar();
+            }
+            const int gz = z0 + em, gy = y0 + ely, gx = x0 + elx;
+            const bool valid = gz < A.D && gy < A.H && gx < A.W;
+            const size_t vox = (((size_t)n * A.D + gz) * A.H + gy) * A.W + gx;
+            const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(set * acc_cols);
+            for (int a = 0; a < nacc; ++a) {
+                bf16 *outp = (a == 0 ? A.t + vox * (size_t)A.ldt : A.r + vox * (size_t)A.ldr);
+                float *stat = s_stat + a * 2 * Cout;
+                for (int cb = 0; cb < Cout; cb += 16) {
+                    float v[16];
+                    tc::tmem_ld16(trow + (uint32_t)((a * MT + em) * Cout + cb), v);
+                    float sv[32];
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        pk[j] = valid ? pack_bf16x2(v[2 * j], v[2 * j + 1]) : 0u;
+                        const float r0 = __uint_as_float(pk[j] << 16);
+                        const float r1 = __uint_as_float(pk[j] & 0xffff0000u);
+                        sv[2 * j] = r0; sv[2 * j + 1] = r1;
+                        sv[16 + 2 * j] = r0 * r0; sv[16 + 2 * j + 1] = r1 * r1;
+                    }
+                    if (valid) {
+                        *reinterpret_cast<uint4 *>(outp + cb) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4 *>(outp + cb + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    }
+                    warp_transpose_sum<32>(sv, lane);
+                    const int idx = warp_transpose_owner<32>(lane);
+                    atomicAdd(&stat[(idx >= 16 ? Cout + idx - 16 : idx) + cb], sv[0]);
+                }
+            }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_acc_free[set]);
+        };
+
+        int cur_n = -1, it = 0;
+        for (int tile = tile_begin; tile < tile_end; ++tile) {
+            int n, z0, y0, x0;
+            tile_coord(tile, n, z0, y0, x0);
+            if (n != cur_n) {
+                cur_n = n;
+                worker_bar();    // nobody still reads the previous sample's scale/shift
+                for (int cc = tid; cc < Cin; cc += NW) {
+                    float sc, sh;
+                    norm_scale_shift(A.xn, A.N, Cin, n, cc, sc, sh);
+                    s_scale[cc] = sc; s_shift[cc] = sh;
+                }
+                worker_bar();
+            }
+            // validity of the halo coordinates of this tile as per-axis bit masks
+            uint32_t mz = 0, my = 0, mx = 0;
+#pragma unroll
+            for (int i = 0; i < HZ; ++i) mz |= (uint32_t)(z0 + i - 1 >= 0 && z0 + i - 1 < A.D) << i;
+#pragma unroll
+            for (int i = 0; i < HY; ++i) my |= (uint32_t)(y0 + i - 1 >= 0 && y0 + i - 1 < A.H) << i;
+#pragma unroll
+            for (int i = 0; i < HX; ++i) mx |= (uint32_t)(x0 + i - 1 >= 0 && x0 + i - 1 < A.W) << i;
+            const int set = (tile - tile_begin) & 1;
+            for (int ch = 0; ch < nchunks; ++ch, ++it) {
+                const int buf = it & 1, rb = it % nraw;
+                unsigned char *Ab = sA + (size_t)buf * A_BYTES;
+                const unsigned char *Rb = s_raw + (size_t)rb * RAW_BYTES;
+                // scale / shift of this thread's 8 channels
+                const float4 sc0 = *reinterpret_cast<const float4 *>(s_scale + ch * CK + aq * 8);
+                const float4 sc1 = *reinterpret_cast<const float4 *>(s_scale + ch * CK + aq * 8 + 4);
+                const float4 sh0 = *reinterpret_cast<const float4 *>(s_shift + ch * CK + aq * 8);
+                const float4 sh1 = *reinterpret_cast<const float4 *>(s_shift + ch * CK + aq * 8 + 4);
+                const float sl = A.xn.slope;
+                tc::mbar_wait(&s_tma_full[rb], (uint32_t)((it / nraw) & 1));               // raw box of this item landed
+                if (it >= 2) tc::mbar_wait(&s_mma_done[buf], (uint32_t)(((it >> 1) - 1) & 1));   // MMAs of item it-2 done: A[buf] free
+                // ---- activation pass: raw bf16 [z][y][x][16] -> fp16 planar [q][z][y][x][8]
+#pragma unroll
+                for (int k = 0; k < ACT_PER_THREAD; ++k) {
+                    const uint32_t ai = act_item[k];
+                    if (ai != 0xffffffffu) {
+                        const int hx = ai & 255, hy = (ai >> 8) & 255, hz = ai >> 16;
+                        const int item = tid + k * NW;
+                        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                        if ((mx >> hx) & (my >> hy) & (mz >> hz) & 1u) {
+                            const uint4 rw = *reinterpret_cast<const uint4 *>(Rb + (size_t)item * 16);
+                            float f[8];
+                            f[0] = fmaf(__uint_as_float(rw.x << 16), sc0.x, sh0.x); f[1] = fmaf(__uint_as_float(rw.x & 0xffff0000u), sc0.y, sh0.y);
+                            f[2] = fmaf(__uint_as_float(rw.y << 16), sc0.z, sh0.z); f[3] = fmaf(__uint_as_float(rw.y & 0xffff0000u), sc0.w, sh0.w);
+                            f[4] = fmaf(__uint_as_float(rw.z << 16), sc1.x, sh1.x); f[5] = fmaf(__uint_as_float(rw.z & 0xffff0000u), sc1.y, sh1.y);
+                            f[6] = fmaf(__uint_as_float(rw.w << 16), sc1.z, sh1.z); f[7] = fmaf(__uint_as_float(rw.w & 0xffff0000u), sc1.w, sh1.w);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], f[j] * sl);      // LeakyReLU, 0 <= slope <= 1
+                            o = make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]), pack_f16x2(f[6], f[7]));
+                        }
+                        *reinterpret_cast<uint4 *>(Ab + (size_t)aq * PLANE + (size_t)(item >> 1) * 16) = o;
+                    }
+                }
+                tc::fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_a_full[buf]);
+                // ---- epilogue of the previous tile (its MMAs were issued one work item ago)
+                if (ch == 0 && tile > tile_begin) {
+                    const int pit = it - 1;
+                    tc::mbar_wait(&s_mma_done[pit & 1], (uint32_t)((pit >> 1) & 1));
+                    tc::fence_after_sync();
+                    epilogue(tile - 1, set ^ 1);
+                }
+            }
+        }
+        if (tile_begin < tile_end) {
+            const int pit = it - 1;
+            tc::mbar_wait(&s_mma_done[pit & 1], (uint32_t)((pit >> 1) & 1));
+            tc::fence_after_sync();
+            epilogue(tile_end - 1, (tile_end - 1 - tile_begin) & 1);
+        }
+        worker_bar();
+        flush_stats(stat_n);
     }
-    if (tile_begin < tile_end) {
-        const int pit = it - 1;
-        tc::mbar_wait(&s_mma_bar[pit & 1], (uint32_t)((pit >> 1) & 1));
-        tc::fence_after_sync();
-        epilogue(tile_end - 1, (tile_end - 1 - tile_begin) & 1, stat_n);
-    }
+    tc::fence_before_sync();
     __syncthreads();
-    flush_stats(stat_n);
-    __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)A.tmem_cols);
+    if (warp == NW / 32) tc::tmem_dealloc(tmem, (uint32_t)A.tmem_cols);
 }
 
-static size_t c3_smem_bytes(int Cin, int Cout, bool has_sc) {
+static size_t c3_smem_bytes(int Cin, int Cout, bool has_sc, int nraw) {
     const size_t nch = Cin / CK;
-    return (size_t)RAW_BYTES + 2 * (size_t)A_BYTES + nch * 27 * (size_t)Cout * 32 + (has_sc ? nch * (size_t)Cout * 32 : 0) +
+    return (size_t)nraw * RAW_BYTES + 2 * (size_t)A_BYTES + nch * 27 * (size_t)Cout * 32 + (has_sc ? nch * (size_t)Cout * 32 : 0) +
            sizeof(float) * (2 * (size_t)Cin + 4 * (size_t)Cout);
 }
 
@@ -332,7 +368,12 @@ int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int 
     if (Cin % 16 != 0 || Cout % 16 != 0 || Cout > 256) return -1;
     const int cols_needed = 2 * MT * Cout * (has_sc ? 2 : 1);
     if (cols_needed > 512) return -1;
-    const size_t smem = c3_smem_bytes(Cin, Cout, has_sc);
+    auto occ_of = [](size_t bytes) { int o = (int)((227 * 1024) / (bytes + 2048)); return o > 3 ? 3 : o; };
+    // two TMA buffers (prefetch two work items ahead) unless that costs a resident CTA
+    int nraw = 2;
+    if (c3_smem_bytes(Cin, Cout, has_sc, 2) > 226 * 1024 || occ_of(c3_smem_bytes(Cin, Cout, has_sc, 2)) < occ_of(c3_smem_bytes(Cin, Cout, has_sc, 1)))
+        nraw = 1;
+    const size_t smem = c3_smem_bytes(Cin, Cout, has_sc, nraw);
     if (smem > 226 * 1024) return -1;
     auto aligned = [](const l3d_act *a, int mult) {
         return (a->ldc % mult == 0) && (reinterpret_cast<uintptr_t>(a->ptr) % (2 * mult) == 0);
@@ -361,15 +402,14 @@ int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int 
     A.w = w; A.groups = w != nullptr ? groups : 1; A.dw_w = dw_w; A.pw_w = pw_w; A.sc_w = sc_w; A.Cout = Cout;
     A.t = (bf16 *)t->ptr; A.ldt = t->ldc; A.t_stats = t_stats;
     A.r = has_sc ? (bf16 *)r->ptr : nullptr; A.ldr = has_sc ? r->ldc : 0; A.r_stats = r_stats;
-    A.tmem_cols = cols;
+    A.tmem_cols = cols; A.nraw = nraw;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) { l3d_set_error("conv3_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 3; }
         attr_set = true;
     }
-    int occ = (int)((227 * 1024) / (smem + 2048));
-    if (occ > 3) occ = 3;
+    int occ = occ_of(smem);
     if (occ < 1) occ = 1;
     if (occ * cols > 512) occ = 512 / cols;
     int dev = 0, sms = 148;
