@@ -267,6 +267,7 @@ struct PwBwdArgs {
     void *g_u; int ldgu; int accumulate;
     // convT geometry
     int d, h, w_, OD, OH, OW, oz, oy, ox;
+    int tap_split;   // convT: blockIdx.y selects one tap; its weight-gradient slice is accumulated over all tiles of the CTA
 };
 
 template <typename T, int KC, int MAXT, bool CONVT>
@@ -291,6 +292,8 @@ __global__ void __launch_bounds__(NT) pw_bwd_kernel(PwBwdArgs A) {
     const long long tiles_per_sample = (A.vox + PB_V - 1) / PB_V;
     const long long total_tiles = tiles_per_sample * A.N;
     constexpr int NTAP = CONVT ? 8 : 1;
+    const int tap0 = (CONVT && A.tap_split) ? (int)blockIdx.y : 0;
+    const int tap1 = (CONVT && A.tap_split) ? tap0 + 1 : NTAP;
 
     float wacc[MAXT][4][TK];
 #pragma unroll
@@ -323,22 +326,37 @@ __global__ void __launch_bounds__(NT) pw_bwd_kernel(PwBwdArgs A) {
             }
             __syncthreads();
         }
-        // ---- stage u tile (activated)
+        // ---- stage u tile (activated); 4 independent loads in flight per thread
         {
             const int groups = (Cu + 3) / 4;
             const bool vec = (Cu % 4 == 0) && (A.ldu % 4 == 0);
-            for (int item = tid; item < PB_V * groups; item += NT) {
-                const int q = item % groups, lv = item / groups;
-                const int k = q * 4;
-                float val[4] = {0.f, 0.f, 0.f, 0.f};
-                if (v0 + lv < A.vox) {
-                    const T *p = uu + ((size_t)n * A.vox + v0 + lv) * (size_t)A.ldu + k;
-                    if (vec) ld4a(p, val);
-                    else for (int j = 0; j < 4; ++j) if (k + j < Cu) val[j] = ld1(p + j);
-                    for (int j = 0; j < 4; ++j)
-                        if (k + j < Cu) val[j] = lrelu(val[j] * s_us[k + j] + s_uh[k + j], A.un.slope);
+            const int nitem = PB_V * groups;
+            for (int item0 = tid; item0 < nitem; item0 += 4 * NT) {
+                float val[4][4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int item = item0 + b * NT;
+                    val[b][0] = val[b][1] = val[b][2] = val[b][3] = 0.f;
+                    if (item < nitem) {
+                        const int q = item % groups, lv = item / groups;
+                        if (v0 + lv < A.vox) {
+                            const T *p = uu + ((size_t)n * A.vox + v0 + lv) * (size_t)A.ldu + q * 4;
+                            if (vec) ld4a(p, val[b]);
+                            else for (int j = 0; j < 4; ++j) if (q * 4 + j < Cu) val[b][j] = ld1(p + j);
+                        }
+                    }
                 }
-                for (int j = 0; j < 4; ++j) if (k + j < Cu) s_u[(size_t)lv * PU + k + j] = val[j];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int item = item0 + b * NT;
+                    if (item < nitem) {
+                        const int q = item % groups, lv = item / groups;
+                        const int k = q * 4;
+                        const bool inb = v0 + lv < A.vox;
+                        for (int j = 0; j < 4; ++j)
+                            if (k + j < Cu) s_u[(size_t)lv * PU + k + j] = inb ? lrelu(val[b][j] * s_us[k + j] + s_uh[k + j], A.un.slope) : 0.f;
+                    }
+                }
             }
         }
         float dacc[PB_MAXKC][KC];
@@ -347,7 +365,7 @@ __global__ void __launch_bounds__(NT) pw_bwd_kernel(PwBwdArgs A) {
 #pragma unroll
             for (int j = 0; j < KC; ++j) dacc[i][j] = 0.f;
 #pragma unroll 1
-        for (int tap = 0; tap < NTAP; ++tap) {
+        for (int tap = tap0; tap < tap1; ++tap) {
             if (CONVT) {
                 __syncthreads();   // previous tap's s_g / s_w consumed
                 for (int i = tid; i < Cg * Cu; i += NT) {
@@ -355,36 +373,51 @@ __global__ void __launch_bounds__(NT) pw_bwd_kernel(PwBwdArgs A) {
                     s_w[i] = A.w[((size_t)k * Cg + c) * 8 + tap];
                 }
             }
-            // ---- stage g tile
+            // ---- stage g tile; 4 independent (gz, t) load pairs in flight per thread
             {
                 const int groups = Cg / 4;
-                for (int item = tid; item < PB_V * groups; item += NT) {
-                    const int q = item % groups, lv = item / groups;
-                    const int c = q * 4;
-                    float val[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (v0 + lv < A.vox) {
-                        if (CONVT) {
-                            long long rem = v0 + lv;
-                            const int ix = (int)(rem % A.w_); rem /= A.w_;
-                            const int iy = (int)(rem % A.h);
-                            const int iz = (int)(rem / A.h);
-                            const int Z = A.oz + 2 * iz + (tap >> 2), Y = A.oy + 2 * iy + ((tap >> 1) & 1), X = A.ox + 2 * ix + (tap & 1);
-                            if (Z >= 0 && Z < A.OD && Y >= 0 && Y < A.OH && X >= 0 && X < A.OW)
-                                ld4a(gz + ((((size_t)n * A.OD + Z) * A.OH + Y) * A.OW + X) * (size_t)A.ldg + c, val);
-                        } else {
-                            const size_t gv = (size_t)n * A.vox + v0 + lv;
-                            float g4[4];
-                            ld4a(gz + gv * (size_t)A.ldg + c, g4);
-                            if (A.nt.stats != nullptr) {
-                                float t4[4];
-                                ld4a(tt + gv * (size_t)A.ldt + c, t4);
-                                for (int j = 0; j < 4; ++j) val[j] = s_ca[c + j] * g4[j] + s_cb[c + j] * t4[j] + s_cd[c + j];
-                            } else {
-                                for (int j = 0; j < 4; ++j) val[j] = g4[j];
+                const int nitem = PB_V * groups;
+                for (int item0 = tid; item0 < nitem; item0 += 4 * NT) {
+                    float g4[4][4], t4[4][4];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int item = item0 + b * NT;
+                        g4[b][0] = g4[b][1] = g4[b][2] = g4[b][3] = 0.f;
+                        t4[b][0] = t4[b][1] = t4[b][2] = t4[b][3] = 0.f;
+                        if (item < nitem) {
+                            const int q = item % groups, lv = item / groups;
+                            const int c = q * 4;
+                            if (v0 + lv < A.vox) {
+                                if (CONVT) {
+                                    long long rem = v0 + lv;
+                                    const int ix = (int)(rem % A.w_); rem /= A.w_;
+                                    const int iy = (int)(rem % A.h);
+                                    const int iz = (int)(rem / A.h);
+                                    const int Z = A.oz + 2 * iz + (tap >> 2), Y = A.oy + 2 * iy + ((tap >> 1) & 1), X = A.ox + 2 * ix + (tap & 1);
+                                    if (Z >= 0 && Z < A.OD && Y >= 0 && Y < A.OH && X >= 0 && X < A.OW)
+                                        ld4a(gz + ((((size_t)n * A.OD + Z) * A.OH + Y) * A.OW + X) * (size_t)A.ldg + c, g4[b]);
+                                } else {
+                                    const size_t gv = (size_t)n * A.vox + v0 + lv;
+                                    ld4a(gz + gv * (size_t)A.ldg + c, g4[b]);
+                                    if (A.nt.stats != nullptr) ld4a(tt + gv * (size_t)A.ldt + c, t4[b]);
+                                }
                             }
                         }
                     }
-                    for (int j = 0; j < 4; ++j) s_g[(size_t)lv * PG + c + j] = val[j];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int item = item0 + b * NT;
+                        if (item < nitem) {
+                            const int q = item % groups, lv = item / groups;
+                            const int c = q * 4;
+                            const bool inb = v0 + lv < A.vox;
+                            for (int j = 0; j < 4; ++j) {
+                                float val = g4[b][j];
+                                if (!CONVT && A.nt.stats != nullptr) val = s_ca[c + j] * g4[b][j] + s_cb[c + j] * t4[b][j] + s_cd[c + j];
+                                s_g[(size_t)lv * PG + c + j] = inb ? val : 0.f;
+                            }
+                        }
+                    }
                 }
             }
             __syncthreads();
@@ -441,7 +474,7 @@ __global__ void __launch_bounds__(NT) pw_bwd_kernel(PwBwdArgs A) {
                         }
                     }
                 }
-                if (CONVT) {   // per-tap flush: the weight slice changes with the tap
+                if (CONVT && !A.tap_split) {   // per-tap flush: the weight slice changes with the tap
 #pragma unroll
                     for (int i = 0; i < MAXT; ++i) {
                         const int tl = ntile <= NT ? tid % ntile : tid + i * NT;
@@ -486,8 +519,11 @@ __global__ void __launch_bounds__(NT) pw_bwd_kernel(PwBwdArgs A) {
             }
         }
     }
-    // ---- flush weight gradients
-    if (!CONVT && A.g_w != nullptr) {
+    // ---- flush weight gradients: reduce the voxel groups of this CTA in shared memory, then one atomic per output
+    if ((!CONVT || A.tap_split) && A.g_w != nullptr) {
+        __syncthreads();                                   // s_w (the weights) is no longer needed
+        for (int i = tid; i < Cg * Cu; i += NT) s_w[i] = 0.f;
+        __syncthreads();
 #pragma unroll
         for (int i = 0; i < MAXT; ++i) {
             const int tl = ntile <= NT ? tid % ntile : tid + i * NT;
@@ -497,8 +533,20 @@ __global__ void __launch_bounds__(NT) pw_bwd_kernel(PwBwdArgs A) {
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int b = 0; b < TK; ++b) atomicAdd(&A.g_w[(size_t)(ct * 4 + a) * Cu + kt * TK + b], wacc[i][a][b]);
+                    for (int b = 0; b < TK; ++b) {
+                        if (G > 1) atomicAdd(&s_w[(size_t)(ct * 4 + a) * Cu + kt * TK + b], wacc[i][a][b]);
+                        else s_w[(size_t)(ct * 4 + a) * Cu + kt * TK + b] = wacc[i][a][b];
+                    }
             }
+        }
+        __syncthreads();
+        if (CONVT) {
+            for (int i = tid; i < Cg * Cu; i += NT) {
+                const int c = i / Cu, k = i % Cu;
+                atomicAdd(&A.g_w[((size_t)k * Cg + c) * 8 + tap0], s_w[i]);
+            }
+        } else {
+            for (int i = tid; i < Cg * Cu; i += NT) atomicAdd(&A.g_w[i], s_w[i]);
         }
     }
     if (CONVT && A.g_b != nullptr) {
@@ -573,23 +621,64 @@ __global__ void __launch_bounds__(NT) dw_bwd_kernel(
         }
         for (int c0 = 0; c0 < C; c0 += CK) {
             if (c0 > 0) __syncthreads();
-            // stage halo tiles of g_u and of the activated input a
-            for (int item = tid; item < HZ * HY * HX * CK; item += NT) {
-                const int cc = item & (CK - 1);
-                int hv = item / CK;
-                const int hx = hv % HX; hv /= HX;
-                const int hy = hv % HY;
-                const int hz = hv / HY;
-                const int gz_ = z0 + hz - 1, gy_ = y0 + hy - 1, gx_ = x0 + hx - 1;
-                float gv = 0.f, av = 0.f;
-                if (gz_ >= 0 && gz_ < D && gy_ >= 0 && gy_ < H && gx_ >= 0 && gx_ < W && c0 + cc < C) {
-                    const size_t vox = (((size_t)n * D + gz_) * H + gy_) * W + gx_;
-                    gv = ld1(g_u + vox * (size_t)ldgu + c0 + cc);
-                    av = lrelu(ld1(x + vox * (size_t)ldx + c0 + cc) * s_scale[c0 + cc] + s_shift[c0 + cc], xn.slope);
+            // stage halo tiles of g_u and of the activated input a: (voxel, 4-channel quad) items, 4 in flight per thread
+            {
+                const bool vec = (C % 4 == 0) && (ldx % 4 == 0) && (ldgu % 4 == 0);
+                constexpr int NITEM = HZ * HY * HX * (CK / 4);
+                for (int item0 = tid; item0 < NITEM; item0 += 4 * NT) {
+                    float gv[4][4], xv[4][4];
+                    bool inb[4];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int item = item0 + b * NT;
+                        gv[b][0] = gv[b][1] = gv[b][2] = gv[b][3] = 0.f;
+                        xv[b][0] = xv[b][1] = xv[b][2] = xv[b][3] = 0.f;
+                        inb[b] = false;
+                        if (item < NITEM) {
+                            const int q = item & (CK / 4 - 1);
+                            int hv = item / (CK / 4);
+                            const int hx = hv % HX; hv /= HX;
+                            const int hy = hv % HY;
+                            const int hz = hv / HY;
+                            const int gz_ = z0 + hz - 1, gy_ = y0 + hy - 1, gx_ = x0 + hx - 1;
+                            const int cc = c0 + q * 4;
+                            if (gz_ >= 0 && gz_ < D && gy_ >= 0 && gy_ < H && gx_ >= 0 && gx_ < W && cc < C) {
+                                inb[b] = true;
+                                const size_t vox = (((size_t)n * D + gz_) * H + gy_) * W + gx_;
+                                if (vec) {
+                                    ld4a(g_u + vox * (size_t)ldgu + cc, gv[b]);
+                                    ld4a(x + vox * (size_t)ldx + cc, xv[b]);
+                                } else {
+                                    for (int j = 0; j < 4; ++j)
+                                        if (cc + j < C) { gv[b][j] = ld1(g_u + vox * (size_t)ldgu + cc + j); xv[b][j] = ld1(x + vox * (size_t)ldx + cc + j); }
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int item = item0 + b * NT;
+                        if (item < NITEM) {
+                            const int q = item & (CK / 4 - 1);
+                            int hv = item / (CK / 4);
+                            const int hx = hv % HX; hv /= HX;
+                            const int hy = hv % HY;
+                            const int hz = hv / HY;
+                            const int cc = c0 + q * 4;
+                            float4 go = make_float4(0.f, 0.f, 0.f, 0.f), ao = go;
+                            if (inb[b]) {
+                                float av[4];
+                                for (int j = 0; j < 4; ++j)
+                                    av[j] = (cc + j < C) ? lrelu(xv[b][j] * s_scale[min(cc + j, C - 1)] + s_shift[min(cc + j, C - 1)], xn.slope) : 0.f;
+                                go = make_float4(gv[b][0], gv[b][1], gv[b][2], gv[b][3]);
+                                ao = make_float4(av[0], av[1], av[2], av[3]);
+                            }
+                            const int so = (hz * HPLANE + hy * HXP + hx) * CK + q * 4;
+                            *reinterpret_cast<float4 *>(s_gu + so) = go;
+                            *reinterpret_cast<float4 *>(s_a + so) = ao;
+                        }
+                    }
                 }
-                const int so = (hz * HPLANE + hy * HXP + hx) * CK + cc;
-                s_gu[so] = gv;
-                s_a[so] = av;
             }
             __syncthreads();
             float ga0[TX], ga1[TX];
@@ -677,12 +766,15 @@ __global__ void __launch_bounds__(NT) dw_bwd_kernel(
                     }
                 }
                 __syncthreads();
-                // thread -> (voxel, 4-channel group)
+                // thread -> (voxel, 4-channel group); the group is the same for all items of a thread (NT % 4 == 0), so
+                // the norm reductions are kept in registers and combined across the 8 lanes sharing a group
+                float rs[4] = {0.f, 0.f, 0.f, 0.f}, rx[4] = {0.f, 0.f, 0.f, 0.f};
+                const int q = tid & (CK / 4 - 1);
+                const int cc = c0 + q * 4;
                 for (int item = tid; item < TV * (CK / 4); item += NT) {
-                    const int q = item & (CK / 4 - 1), lv = item / (CK / 4);
+                    const int lv = item / (CK / 4);
                     const int lx = lv & 7, ly = (lv >> 3) & 7, lzz = lv >> 6;
                     const int gz_ = z0 + lzz, gy_ = y0 + ly, gx_ = x0 + lx;
-                    const int cc = c0 + q * 4;
                     if (gz_ < D && gy_ < H && gx_ < W && cc < C) {
                         const size_t vox = (((size_t)n * D + gz_) * H + gy_) * W + gx_;
                         float val[4];
@@ -703,12 +795,31 @@ __global__ void __launch_bounds__(NT) dw_bwd_kernel(
                         }
                         if (has_norm && redx != nullptr) {
                             const T *xp = x + vox * (size_t)ldx + cc;
+                            float xr[4] = {0.f, 0.f, 0.f, 0.f};
+                            if ((cc + 3 < C) && (ldx % 4 == 0)) ld4a(xp, xr);
+                            else for (int j = 0; j < 4; ++j) if (cc + j < C) xr[j] = ld1(xp + j);
+#pragma unroll
                             for (int j = 0; j < 4; ++j) if (cc + j < C) {
-                                const float gr = round_as(gy, val[j]);
-                                const float xh = (ld1(xp + j) - s_mean[cc + j]) * s_rstd[cc + j];
-                                atomicAdd(&s_red[cc + j], gr);
-                                atomicAdd(&s_red[C + cc + j], gr * xh);
+                                rs[j] += val[j];
+                                rx[j] += val[j] * ((xr[j] - s_mean[cc + j]) * s_rstd[cc + j]);
                             }
+                        }
+                    }
+                }
+                if (has_norm && redx != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                        for (int sft = 4; sft <= 16; sft <<= 1) {
+                            rs[j] += __shfl_xor_sync(0xffffffffu, rs[j], sft);
+                            rx[j] += __shfl_xor_sync(0xffffffffu, rx[j], sft);
+                        }
+                    }
+                    if ((tid & 31) < 4) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (cc + j < C) {
+                            atomicAdd(&s_red[cc + j], rs[j]);
+                            atomicAdd(&s_red[C + cc + j], rx[j]);
                         }
                     }
                 }
@@ -932,14 +1043,16 @@ static int launch_pw_bwd(const PwBwdArgs &A, cudaStream_t st) {
     const size_t smem = pw_bwd_smem(Cg, Cu);
     L3D_REQUIRE(smem <= 227 * 1024, "pointwise backward: Cout=%d Cin=%d needs %zu B shared memory", Cg, Cu, smem);
     const long long tiles = ((A.vox + PB_V - 1) / PB_V) * A.N;
-    const int ctas_per_sm = smem > 110 * 1024 ? 1 : smem > 70 * 1024 ? 2 : 3;
+    const int ctas_per_sm = smem > 110 * 1024 ? 1 : 2;     // 256 threads x up to 128 registers
     long long grid = tiles < 148ll * ctas_per_sm ? tiles : 148ll * ctas_per_sm;
+    if (A.tap_split) grid = (grid + 7) / 8;                // 8 taps share the machine
     if (grid < 1) grid = 1;
+    const dim3 grid3((unsigned)grid, A.tap_split ? 8u : 1u);
 #define L3D_PWB(KCV, MT)                                                             \
     do {                                                                             \
         auto kern = pw_bwd_kernel<T, KCV, MT, CONVT>;                                \
         if (set_smem(kern, smem)) return 3;                                          \
-        kern<<<(unsigned)grid, NT, smem, st>>>(A);                                   \
+        kern<<<grid3, NT, smem, st>>>(A);                                            \
     } while (0)
     if (KC == 16) { if (MAXT == 1) L3D_PWB(16, 1); else L3D_PWB(16, 4); }
     else if (KC == 4) { if (MAXT == 1) L3D_PWB(4, 1); else L3D_PWB(4, 4); }
@@ -1056,9 +1169,21 @@ extern "C" int l3d_convt_bwd(const l3d_act *g_out, int OD, int OH, int OW, int o
     A.g_u = has_gx ? g_x->ptr : nullptr; A.ldgu = has_gx ? g_x->ldc : 0; A.accumulate = accumulate_gx;
     A.d = d; A.h = h; A.w_ = w_; A.OD = OD; A.OH = OH; A.OW = OW; A.oz = oz; A.oy = oy; A.ox = ox;
     int rc = 0;
-    L3D_DISPATCH_DTYPE(x->dtype, T, { rc = launch_pw_bwd<T, true>(A, (cudaStream_t)stream); });
-    if (rc) return rc;
-    l3d_count_launch();
+    // launch 1: input gradient (all taps) + bias gradient; launch 2: weight gradient, one tap per blockIdx.y with the
+    // slice accumulated in registers over all tiles of the CTA (one atomic per output per CTA)
+    float *gw_saved = A.g_w;
+    if (has_gx || g_b != nullptr) {
+        A.g_w = nullptr; A.tap_split = 0;
+        L3D_DISPATCH_DTYPE(x->dtype, T, { rc = launch_pw_bwd<T, true>(A, (cudaStream_t)stream); });
+        if (rc) return rc;
+        l3d_count_launch();
+    }
+    if (gw_saved != nullptr) {
+        A.g_w = gw_saved; A.g_b = nullptr; A.g_u = nullptr; A.tap_split = 1;
+        L3D_DISPATCH_DTYPE(x->dtype, T, { rc = launch_pw_bwd<T, true>(A, (cudaStream_t)stream); });
+        if (rc) return rc;
+        l3d_count_launch();
+    }
     L3D_CUDA_OK("l3d_convt_bwd launch");
     return 0;
 }

@@ -13,6 +13,9 @@ typedef __nv_bfloat16 bf16;
 // ------------------------------------------------------------------ errors --
 void l3d_set_error(const char *fmt, ...);
 void l3d_count_launch(int n = 1);
+// tiled CUtensorMap encode through a runtime-resolved driver entry point (no libcuda link dependency)
+int l3d_encode_tiled(void *tmap, int dtype, unsigned rank, void *base, const unsigned long long *dims,
+                     const unsigned long long *strides, const unsigned *box, const unsigned *estr);
 
 #define L3D_REQUIRE(cond, ...)                  \
     do {                                        \

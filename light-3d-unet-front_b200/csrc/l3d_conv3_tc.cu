@@ -391,10 +391,8 @@ int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int 
         const cuuint64_t strides[4] = {ld * es, (cuuint64_t)W * ld * es, (cuuint64_t)H * W * ld * es, (cuuint64_t)D * H * W * ld * es};
         const cuuint32_t box[5] = {CK, HX, HY, HZ, 1};
         const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-        const CUresult cr = cuTensorMapEncodeTiled(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x->ptr, dims, strides, box, estr,
-                                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (cr != CUDA_SUCCESS) { l3d_set_error("conv3_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr); return 3; }
+        if (l3d_encode_tiled(&tmap, (int)CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x->ptr, (const unsigned long long *)dims,
+                             (const unsigned long long *)strides, (const unsigned *)box, (const unsigned *)estr)) return 3;
     }
     C3Args A;
     A.Cin = Cin; A.xn = norm_dev(xn);

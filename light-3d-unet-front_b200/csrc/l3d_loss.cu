@@ -2,6 +2,7 @@
 #include <stdarg.h>
 
 #include "l3d_common.cuh"
+#include <cuda.h>
 
 // ------------------------------------------------------------ bookkeeping --
 static thread_local char g_err[512] = "";
@@ -14,6 +15,32 @@ void l3d_set_error(const char *fmt, ...) {
     va_end(ap);
 }
 void l3d_count_launch(int n) { __atomic_fetch_add(&g_launches, (int64_t)n, __ATOMIC_RELAXED); }
+
+
+// cuTensorMapEncodeTiled is resolved through the runtime at first use, so libl3d.so has no link-time dependency on
+// libcuda.so.1 (it must load -- symbols only -- on hosts without a driver).
+int l3d_encode_tiled(void *tmap, int dtype, unsigned rank, void *base, const unsigned long long *dims,
+                     const unsigned long long *strides, const unsigned *box, const unsigned *estr) {
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn fn = nullptr;
+    if (fn == nullptr) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || p == nullptr) {
+            l3d_set_error("cuTensorMapEncodeTiled is not available from the driver");
+            return 3;
+        }
+        fn = (encode_fn)p;
+    }
+    const CUresult cr = fn((CUtensorMap *)tmap, (CUtensorMapDataType)dtype, rank, base, (const cuuint64_t *)dims,
+                           (const cuuint64_t *)strides, (const cuuint32_t *)box, (const cuuint32_t *)estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { l3d_set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return 3; }
+    return 0;
+}
 
 extern "C" const char *l3d_last_error(void) { return g_err; }
 extern "C" int l3d_abi_version(void) { return L3D_ABI_VERSION; }
