@@ -21,17 +21,23 @@
 
 namespace {
 
-constexpr int TZ = 2, TY = 16, TX = 8;                  // CTA tile: 2 MMA tiles (z-planes) of 16x8 voxels
-constexpr int HZ = TZ + 2, HY = TY + 2, HX = TX + 2;    // 4 x 18 x 10 halo
-constexpr int HVOX = HZ * HY * HX;                      // 720
-constexpr int CK = 16, NW = 256, NT = NW + 32, MT = 2;   // 8 worker warps + 1 issuer warp
-constexpr int RAW_BYTES = HVOX * CK * 2;                // 23040: TMA box, dense [z][y][x][16] bf16
-constexpr int PLANE = HVOX * 16 + 64;                   // bytes of one 8-channel group of the A tile (fp16); +64 so that the two
-                                                        // groups written by a lane pair land in different bank halves
-constexpr int A_BYTES = 2 * PLANE;                      // 23168
-constexpr int ROWPITCH = HX * 16;                       // 160 B between y rows
-constexpr int ACT_ITEMS = HVOX * 2;
-constexpr int ACT_PER_THREAD = (ACT_ITEMS + NW - 1) / NW;   // 6
+constexpr int TY = 16, TX = 8;                          // one MMA tile (128 rows) = one z-plane of 16 (y) x 8 (x) voxels
+constexpr int HY = TY + 2, HX = TX + 2;                 // 18 x 10 halo plane
+constexpr int CK = 16, NW = 256, NT = NW + 32;          // 8 worker warps + 1 issuer warp
+constexpr int ROWPITCH = HX * 16;                       // 160 B between y rows of one 8-channel group
+
+// CTA tile: TZ output planes; the halo tile has TZ + 2 planes
+template <int TZ>
+struct Geo {
+    static constexpr int HZ = TZ + 2;
+    static constexpr int HVOX = HZ * HY * HX;
+    static constexpr int RAW_BYTES = HVOX * CK * 2;          // TMA box, dense [z][y][x][16] bf16
+    static constexpr int PLANE = HVOX * 16 + 64;             // bytes of one 8-channel group of the A tile (fp16); +64 so that the
+                                                             // two groups written by a lane pair land in different bank halves
+    static constexpr int A_BYTES = 2 * PLANE;
+    static constexpr int ACT_ITEMS = HVOX * 2;
+    static constexpr int ACT_PER_THREAD = (ACT_ITEMS + NW - 1) / NW;
+};
 
 struct C3Args {
     int Cin; NormDev xn;
@@ -43,7 +49,7 @@ struct C3Args {
     int Cout;
     bf16 *t; int ldt; double *t_stats;
     bf16 *r; int ldr; double *r_stats;
-    int tmem_cols, nraw;
+    int tmem_cols, nraw, nsets, merge;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -67,20 +73,29 @@ __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::
 //   a_full[b]     workers -> issuer   operand tile b written (8 warp arrivals); also: raw box consumed
 //   mma_done[b]   issuer -> workers   MMAs that read operand tile b finished (tcgen05.commit)
 //   acc_free[s]   workers -> issuer   epilogue drained accumulator set s (8 warp arrivals)
-__global__ void __launch_bounds__(NT) conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, C3Args A) {
+//
+// z-merged MMAs: a tcgen05.mma (M=128, K=16) costs ~44 cycles for any N <= 48 (measured, tools/ub_mma.cu), so the
+// three z-taps of one input plane are issued as ONE instruction: the accumulators of consecutive output planes sit
+// in consecutive TMEM column blocks, and the weight tile of (chunk, dy, dx) holds the rows [dz=2 | dz=1 | dz=0], so
+// input plane zi updates output planes zi-2, zi-1, zi with a single N = 3*Cout MMA.  9*(TZ+2) MMAs per 16-channel
+// chunk instead of 27*TZ.
+template <int TZ, bool MERGE>
+__global__ void __launch_bounds__(NT, (TZ >= 6 ? 1 : 2)) conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, C3Args A) {
+    using G = Geo<TZ>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_tma_full[2], s_a_full[2], s_mma_done[2], s_acc_free[2];
     __shared__ uint32_t s_tmem;
     const int Cin = A.Cin, Cout = A.Cout;
     const bool has_sc = A.sc_w != nullptr;
-    const int nchunks = Cin / CK, nraw = A.nraw;
-    const uint32_t btap_bytes = (uint32_t)Cout * 32;                      // one [Cout x 16] fp16 operand tile
-    const uint32_t b_bytes = (uint32_t)nchunks * 27 * btap_bytes;
+    const int nchunks = Cin / CK, nraw = A.nraw, nsets = A.nsets;
+    const uint32_t btile_bytes = (uint32_t)Cout * 3 * 32;                 // one [3*Cout x 16] fp16 operand tile: (chunk, dy, dx)
+    const uint32_t bsc_bytes = (uint32_t)Cout * 32;
+    const uint32_t b_bytes = (uint32_t)nchunks * 9 * btile_bytes;
     unsigned char *s_raw = smem_raw;                                       // nraw x RAW_BYTES (TMA destinations)
-    unsigned char *sA = s_raw + (size_t)nraw * RAW_BYTES;                  // 2 x A_BYTES
-    unsigned char *sB = sA + 2 * A_BYTES;                                  // [chunk][tap][Cout x 16]
+    unsigned char *sA = s_raw + (size_t)nraw * G::RAW_BYTES;               // 2 x A_BYTES
+    unsigned char *sB = sA + 2 * G::A_BYTES;                               // [chunk][dy*3+dx][3*Cout x 16]
     unsigned char *sB2 = sB + b_bytes;                                     // shortcut: [chunk][Cout x 16]
-    float *s_scale = reinterpret_cast<float *>(sB2 + (has_sc ? nchunks * btap_bytes : 0));
+    float *s_scale = reinterpret_cast<float *>(sB2 + (has_sc ? nchunks * bsc_bytes : 0));
     float *s_shift = s_scale + Cin;
     float *s_stat = s_shift + Cin;                                         // 2*Cout (t) + 2*Cout (r)
 
@@ -95,6 +110,7 @@ __global__ void __launch_bounds__(NT) conv3_tc_kernel(const __grid_constant__ CU
     // ---- stage the (effective) 3x3x3 weights once per CTA as fp16 K-major operand tiles
     {
         const int cin_g = Cin / A.groups, cout_g = Cout / A.groups;
+        const int rows = 3 * Cout;
         for (int i = tid; i < Cout * Cin * 27; i += NT) {
             const int tap = i % 27;
             const int ci = (i / 27) % Cin;
@@ -106,13 +122,13 @@ __global__ void __launch_bounds__(NT) conv3_tc_kernel(const __grid_constant__ CU
             } else {
                 wv = A.pw_w[(size_t)co * Cin + ci] * A.dw_w[(size_t)ci * 27 + tap];
             }
-            const int ch = ci >> 4, k = ci & 15;
-            *reinterpret_cast<__half *>(sB + (size_t)(ch * 27 + tap) * btap_bytes + tc::tile_off(co, k, Cout)) = __float2half_rn(wv);
+            const int ch = ci >> 4, k = ci & 15, dz = tap / 9, t9 = tap - dz * 9;
+            *reinterpret_cast<__half *>(sB + (size_t)(ch * 9 + t9) * btile_bytes + tc::tile_off((2 - dz) * Cout + co, k, rows)) = __float2half_rn(wv);
         }
         if (has_sc)
             for (int i = tid; i < Cout * Cin; i += NT) {
                 const int ci = i % Cin, co = i / Cin;
-                *reinterpret_cast<__half *>(sB2 + (size_t)(ci >> 4) * btap_bytes + tc::tile_off(co, ci & 15, Cout)) = __float2half_rn(A.sc_w[i]);
+                *reinterpret_cast<__half *>(sB2 + (size_t)(ci >> 4) * bsc_bytes + tc::tile_off(co, ci & 15, Cout)) = __float2half_rn(A.sc_w[i]);
             }
     }
     for (int i = tid; i < 4 * Cout; i += NT) s_stat[i] = 0.f;
@@ -121,10 +137,9 @@ __global__ void __launch_bounds__(NT) conv3_tc_kernel(const __grid_constant__ CU
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = s_tmem;
-    const uint32_t idesc = tc::idesc_f16_m128(Cout);
     const uint32_t sA_u = tc::smem_u32(sA), sB_u = tc::smem_u32(sB), sB2_u = tc::smem_u32(sB2);
     const int nacc = has_sc ? 2 : 1;
-    const int acc_cols = MT * Cout * nacc;          // TMEM columns of one accumulator set (two sets: tile parity)
+    const int acc_cols = TZ * Cout * nacc;          // TMEM columns of one accumulator set: [plane][Cout] main, then shortcut
 
     const int tilesX = (A.W + TX - 1) / TX, tilesY = (A.H + TY - 1) / TY, tilesZ = (A.D + TZ - 1) / TZ;
     const int tiles_per_sample = tilesX * tilesY * tilesZ;
@@ -143,66 +158,98 @@ __global__ void __launch_bounds__(NT) conv3_tc_kernel(const __grid_constant__ CU
     };
 
     if (warp == NW / 32) {
-        // =============================== issuer warp (one lane) ===============================
-        if (lane == 0) {
-            auto issue_tma = [&](int item) {
-                const int tl = tile_begin + item / nchunks, chn = item % nchunks;
-                int n, z0, y0, x0;
-                tile_coord(tl, n, z0, y0, x0);
-                const int rb = item % nraw;
-                tc::mbar_expect_tx(&s_tma_full[rb], RAW_BYTES);
-                tc::tma_load_5d(s_raw + (size_t)rb * RAW_BYTES, &tmap, &s_tma_full[rb], chn * CK, x0 - 1, y0 - 1, z0 - 1, n);
-            };
-            for (int i = 0; i < nraw && i < n_items; ++i) issue_tma(i);
-            int tj = 0, ch = 0;                       // tile index within this CTA's range, chunk
-            for (int it = 0; it < n_items; ++it) {
-                const int buf = it & 1, set = tj & 1;
-                tc::mbar_wait(&s_a_full[buf], (uint32_t)((it >> 1) & 1));        // operand tile written, raw box consumed
-                tc::fence_after_sync();
-                if (it + nraw < n_items) issue_tma(it + nraw);
-                if (ch == 0 && tj >= 2) tc::mbar_wait(&s_acc_free[set], (uint32_t)(((tj >> 1) - 1) & 1));   // epilogue of tile tj-2 done
-                tc::fence_after_sync();
-                const uint64_t ad0 = tc::smem_desc(sA_u + buf * A_BYTES, PLANE, ROWPITCH);
-                const uint64_t bd0 = tc::smem_desc(sB_u + (uint32_t)(ch * 27) * btap_bytes, Cout * 16, 128);
-                const uint32_t bstep = btap_bytes >> 4;
-                const uint32_t d_t = tmem + (uint32_t)(set * acc_cols);
-                // consecutive MMAs alternate between the two planes: two independent accumulation chains in flight
+        // =============================== issuer warp ===============================
+        // The whole warp runs this loop converged (every value is warp-uniform, so descriptors and TMEM addresses
+        // live in uniform registers); one elected lane issues the TMA loads and the tcgen05.mma / commit.  A
+        // single-lane branch around the loop makes ptxas wrap every MMA in an ELECT / R2UR.BROADCAST waterfall.
+        const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem);    // TMEM base (from shared memory) as a uniform value
+        auto issue_tma = [&](int item) {
+            const int tl = tile_begin + item / nchunks, chn = item % nchunks;
+            int n, z0, y0, x0;
+            tile_coord(tl, n, z0, y0, x0);
+            const int rb = item % nraw;
+            if (tc::elect_one()) {
+                tc::mbar_expect_tx(&s_tma_full[rb], G::RAW_BYTES);
+                tc::tma_load_5d(s_raw + (size_t)rb * G::RAW_BYTES, &tmap, &s_tma_full[rb], chn * CK, x0 - 1, y0 - 1, z0 - 1, n);
+            }
+        };
+        for (int i = 0; i < nraw && i < n_items; ++i) issue_tma(i);
+        const uint32_t idesc1 = tc::idesc_f16_m128(Cout), idesc2 = tc::idesc_f16_m128(2 * Cout), idesc3 = tc::idesc_f16_m128(3 * Cout);
+        const uint32_t brow = (uint32_t)(Cout >> 3) * 128 >> 4;     // descriptor units (16 B) per Cout rows of a weight tile
+        const uint32_t bstep = btile_bytes >> 4;
+        int tj = 0, ch = 0;                       // tile index within this CTA's range, chunk
+        for (int it = 0; it < n_items; ++it) {
+            const int buf = it & 1, set = tj % nsets;
+            tc::mbar_wait(&s_a_full[buf], (uint32_t)((it >> 1) & 1));        // operand tile written, raw box consumed
+            if (it + nraw < n_items) issue_tma(it + nraw);
+            if (ch == 0 && tj >= nsets) tc::mbar_wait(&s_acc_free[set], (uint32_t)(((tj / nsets) - 1) & 1));   // epilogue of tile tj-nsets done
+            tc::fence_after_sync();
+            const uint64_t ad0 = tc::smem_desc(sA_u + buf * G::A_BYTES, G::PLANE, ROWPITCH);
+            const uint64_t bd0 = tc::smem_desc(sB_u + (uint32_t)(ch * 9) * btile_bytes, 3 * Cout * 16, 128);
+            const uint32_t d_t = tmem_u + (uint32_t)(set * acc_cols);
+            const bool first = ch == 0;
+            if (tc::elect_one()) {
 #pragma unroll
-                for (int tap = 0; tap < 27; ++tap) {
-                    const int dz = tap / 9, dy = (tap / 3) % 3, dx = tap % 3;
+                for (int zi = 0; zi < TZ + 2; ++zi) {
+                    const int lo = zi >= 2 ? zi - 2 : 0, hi = zi <= TZ - 1 ? zi : TZ - 1;     // output planes fed by input plane zi
+                    const int np = hi - lo + 1;
+                    const uint64_t bdz = bd0 + (uint64_t)((uint32_t)(lo - zi + 2) * brow);     // first weight row block: dz = zi - lo
+                    const uint64_t adz = ad0 + (uint64_t)((uint32_t)(zi * HY * ROWPITCH) >> 4);
+                    const uint32_t d_lo = d_t + (uint32_t)(lo * Cout);
+                    if (MERGE) {
+                        const uint32_t idn = np == 3 ? idesc3 : np == 2 ? idesc2 : idesc1;
+                        if (zi <= TZ - 1 && first) {
+                            // plane zi gets its first contribution (dz = 0): overwrite it, accumulate into the other planes
+                            if (np > 1) tc::mma_f16(d_lo, adz, bdz, np == 3 ? idesc2 : idesc1, 1u);
+                            tc::mma_f16(d_t + (uint32_t)(zi * Cout), adz, bdz + (uint64_t)((uint32_t)(np - 1) * brow), idesc1, 0u);
+                        } else {
+                            tc::mma_f16(d_lo, adz, bdz, idn, 1u);
+                        }
 #pragma unroll
-                    for (int m = 0; m < MT; ++m) {
-                        const uint32_t aoff = (uint32_t)((((m + dz) * HY + dy) * ROWPITCH + dx * 16) >> 4);
-                        tc::mma_f16(d_t + m * Cout, ad0 + aoff, bd0 + (uint64_t)(tap * bstep), idesc, (ch > 0 || tap > 0) ? 1u : 0u);
+                        for (int t9 = 1; t9 < 9; ++t9) {
+                            const int dy = t9 / 3, dx = t9 % 3;
+                            tc::mma_f16(d_lo, adz + (uint64_t)((uint32_t)(dy * ROWPITCH + dx * 16) >> 4), bdz + (uint64_t)(t9 * bstep), idn, 1u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int t9 = 0; t9 < 9; ++t9) {
+                            const int dy = t9 / 3, dx = t9 % 3;
+                            const uint64_t ad = adz + (uint64_t)((uint32_t)(dy * ROWPITCH + dx * 16) >> 4);
+#pragma unroll
+                            for (int p = lo; p <= hi; ++p)
+                                tc::mma_f16(d_t + (uint32_t)(p * Cout), ad, bdz + (uint64_t)(t9 * bstep + (uint32_t)(p - lo) * brow), idesc1,
+                                            (t9 == 0 && p == zi && first) ? 0u : 1u);
+                        }
                     }
                 }
                 if (has_sc) {
-                    const uint64_t bd2 = tc::smem_desc(sB2_u + (uint32_t)ch * btap_bytes, Cout * 16, 128);
+                    const uint64_t bd2 = tc::smem_desc(sB2_u + (uint32_t)ch * bsc_bytes, Cout * 16, 128);
 #pragma unroll
-                    for (int m = 0; m < MT; ++m) {
-                        const uint32_t aoff = (uint32_t)((((m + 1) * HY + 1) * ROWPITCH + 16) >> 4);
-                        tc::mma_f16(d_t + (MT + m) * Cout, ad0 + aoff, bd2, idesc, ch > 0 ? 1u : 0u);
+                    for (int p = 0; p < TZ; ++p) {
+                        const uint32_t aoff = (uint32_t)((((p + 1) * HY + 1) * ROWPITCH + 16) >> 4);
+                        tc::mma_f16(d_t + (uint32_t)((TZ + p) * Cout), ad0 + aoff, bd2, idesc1, ch > 0 ? 1u : 0u);
                     }
                 }
                 tc::mma_commit(&s_mma_done[buf]);
-                if (++ch == nchunks) { ch = 0; ++tj; }
             }
+            __syncwarp();
+            if (++ch == nchunks) { ch = 0; ++tj; }
         }
     } else {
         // ===================================== workers =====================================
         // activation-pass role: fixed 16-byte vectors of the raw box; q (8-channel group) is the same for all of them
         const int aq = tid & 1;
-        uint32_t act_item[ACT_PER_THREAD];
+        uint32_t act_item[G::ACT_PER_THREAD];
 #pragma unroll
-        for (int k = 0; k < ACT_PER_THREAD; ++k) {
+        for (int k = 0; k < G::ACT_PER_THREAD; ++k) {
             const int item = tid + k * NW;
             int hv = item >> 1;
             const int hx = hv % HX; hv /= HX;
             const int hy = hv % HY;
             const int hz = hv / HY;
-            act_item[k] = item < ACT_ITEMS ? ((uint32_t)hx | ((uint32_t)hy << 8) | ((uint32_t)hz << 16)) : 0xffffffffu;
+            act_item[k] = item < G::ACT_ITEMS ? ((uint32_t)hx | ((uint32_t)hy << 8) | ((uint32_t)hz << 16)) : 0xffffffffu;
         }
-        // epilogue role: voxel row of MMA tile (plane) `em`
+        // epilogue role: voxel row of the MMA tiles (planes) em, em + 2, ...
         const int em = warp >> 2, erow = (warp & 3) * 32 + lane;
         const int elx = erow & 7, ely = erow >> 3;
         int stat_n = -1;
@@ -229,29 +276,38 @@ __global__ void __launch_bounds__(NT) conv3_tc_kernel(const __grid_constant__ CU
                 stat_n = n;
                 worker_bar();
             }
-            const int gz = z0 + em, gy = y0 + ely, gx = x0 + elx;
-            const bool valid = gz < A.D && gy < A.H && gx < A.W;
-            const size_t vox = (((size_t)n * A.D + gz) * A.H + gy) * A.W + gx;
+            const int gy = y0 + ely, gx = x0 + elx;
+            const bool valid_yx = gy < A.H && gx < A.W;
+            const size_t vox0 = (((size_t)n * A.D + z0) * A.H + gy) * A.W + gx;
+            const size_t zstride = (size_t)A.H * A.W;
             const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(set * acc_cols);
             for (int a = 0; a < nacc; ++a) {
-                bf16 *outp = (a == 0 ? A.t + vox * (size_t)A.ldt : A.r + vox * (size_t)A.ldr);
+                bf16 *outb = a == 0 ? A.t : A.r;
+                const int ldo = a == 0 ? A.ldt : A.ldr;
                 float *stat = s_stat + a * 2 * Cout;
                 for (int cb = 0; cb < Cout; cb += 16) {
-                    float v[16];
-                    tc::tmem_ld16(trow + (uint32_t)((a * MT + em) * Cout + cb), v);
                     float sv[32];
-                    uint32_t pk[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        pk[j] = valid ? pack_bf16x2(v[2 * j], v[2 * j + 1]) : 0u;
-                        const float r0 = __uint_as_float(pk[j] << 16);
-                        const float r1 = __uint_as_float(pk[j] & 0xffff0000u);
-                        sv[2 * j] = r0; sv[2 * j + 1] = r1;
-                        sv[16 + 2 * j] = r0 * r0; sv[16 + 2 * j + 1] = r1 * r1;
-                    }
-                    if (valid) {
-                        *reinterpret_cast<uint4 *>(outp + cb) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        *reinterpret_cast<uint4 *>(outp + cb + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    for (int j = 0; j < 32; ++j) sv[j] = 0.f;
+#pragma unroll 1
+                    for (int p = em; p < TZ; p += 2) {
+                        float v[16];
+                        tc::tmem_ld16(trow + (uint32_t)((a * TZ + p) * Cout + cb), v);
+                        const bool valid = valid_yx && (z0 + p < A.D);
+                        uint32_t pk[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            pk[j] = valid ? pack_bf16x2(v[2 * j], v[2 * j + 1]) : 0u;
+                            const float r0 = __uint_as_float(pk[j] << 16);
+                            const float r1 = __uint_as_float(pk[j] & 0xffff0000u);
+                            sv[2 * j] += r0; sv[2 * j + 1] += r1;
+                            sv[16 + 2 * j] = fmaf(r0, r0, sv[16 + 2 * j]); sv[16 + 2 * j + 1] = fmaf(r1, r1, sv[16 + 2 * j + 1]);
+                        }
+                        if (valid) {
+                            bf16 *outp = outb + (vox0 + (size_t)p * zstride) * (size_t)ldo + cb;
+                            *reinterpret_cast<uint4 *>(outp) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                            *reinterpret_cast<uint4 *>(outp + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        }
                     }
                     warp_transpose_sum<32>(sv, lane);
                     const int idx = warp_transpose_owner<32>(lane);
@@ -280,16 +336,16 @@ __global__ void __launch_bounds__(NT) conv3_tc_kernel(const __grid_constant__ CU
             // validity of the halo coordinates of this tile as per-axis bit masks
             uint32_t mz = 0, my = 0, mx = 0;
 #pragma unroll
-            for (int i = 0; i < HZ; ++i) mz |= (uint32_t)(z0 + i - 1 >= 0 && z0 + i - 1 < A.D) << i;
+            for (int i = 0; i < G::HZ; ++i) mz |= (uint32_t)(z0 + i - 1 >= 0 && z0 + i - 1 < A.D) << i;
 #pragma unroll
             for (int i = 0; i < HY; ++i) my |= (uint32_t)(y0 + i - 1 >= 0 && y0 + i - 1 < A.H) << i;
 #pragma unroll
             for (int i = 0; i < HX; ++i) mx |= (uint32_t)(x0 + i - 1 >= 0 && x0 + i - 1 < A.W) << i;
-            const int set = (tile - tile_begin) & 1;
+            const int tj = tile - tile_begin;
             for (int ch = 0; ch < nchunks; ++ch, ++it) {
                 const int buf = it & 1, rb = it % nraw;
-                unsigned char *Ab = sA + (size_t)buf * A_BYTES;
-                const unsigned char *Rb = s_raw + (size_t)rb * RAW_BYTES;
+                unsigned char *Ab = sA + (size_t)buf * G::A_BYTES;
+                const unsigned char *Rb = s_raw + (size_t)rb * G::RAW_BYTES;
                 // scale / shift of this thread's 8 channels
                 const float4 sc0 = *reinterpret_cast<const float4 *>(s_scale + ch * CK + aq * 8);
                 const float4 sc1 = *reinterpret_cast<const float4 *>(s_scale + ch * CK + aq * 8 + 4);
@@ -300,7 +356,7 @@ __global__ void __launch_bounds__(NT) conv3_tc_kernel(const __grid_constant__ CU
                 if (it >= 2) tc::mbar_wait(&s_mma_done[buf], (uint32_t)(((it >> 1) - 1) & 1));   // MMAs of item it-2 done: A[buf] free
                 // ---- activation pass: raw bf16 [z][y][x][16] -> fp16 planar [q][z][y][x][8]
 #pragma unroll
-                for (int k = 0; k < ACT_PER_THREAD; ++k) {
+                for (int k = 0; k < G::ACT_PER_THREAD; ++k) {
                     const uint32_t ai = act_item[k];
                     if (ai != 0xffffffffu) {
                         const int hx = ai & 255, hy = (ai >> 8) & 255, hz = ai >> 16;
@@ -317,7 +373,7 @@ __global__ void __launch_bounds__(NT) conv3_tc_kernel(const __grid_constant__ CU
                             for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], f[j] * sl);      // LeakyReLU, 0 <= slope <= 1
                             o = make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]), pack_f16x2(f[6], f[7]));
                         }
-                        *reinterpret_cast<uint4 *>(Ab + (size_t)aq * PLANE + (size_t)(item >> 1) * 16) = o;
+                        *reinterpret_cast<uint4 *>(Ab + (size_t)aq * G::PLANE + (size_t)(item >> 1) * 16) = o;
                     }
                 }
                 tc::fence_async_smem();
@@ -328,7 +384,7 @@ __global__ void __launch_bounds__(NT) conv3_tc_kernel(const __grid_constant__ CU
                     const int pit = it - 1;
                     tc::mbar_wait(&s_mma_done[pit & 1], (uint32_t)((pit >> 1) & 1));
                     tc::fence_after_sync();
-                    epilogue(tile - 1, set ^ 1);
+                    epilogue(tile - 1, (tj - 1) % nsets);
                 }
             }
         }
@@ -336,7 +392,7 @@ __global__ void __launch_bounds__(NT) conv3_tc_kernel(const __grid_constant__ CU
             const int pit = it - 1;
             tc::mbar_wait(&s_mma_done[pit & 1], (uint32_t)((pit >> 1) & 1));
             tc::fence_after_sync();
-            epilogue(tile_end - 1, (tile_end - 1 - tile_begin) & 1);
+            epilogue(tile_end - 1, (tile_end - 1 - tile_begin) % nsets);
         }
         worker_bar();
         flush_stats(stat_n);
@@ -346,10 +402,17 @@ __global__ void __launch_bounds__(NT) conv3_tc_kernel(const __grid_constant__ CU
     if (warp == NW / 32) tc::tmem_dealloc(tmem, (uint32_t)A.tmem_cols);
 }
 
-static size_t c3_smem_bytes(int Cin, int Cout, bool has_sc, int nraw) {
+static size_t c3_smem_bytes(int TZ, int Cin, int Cout, bool has_sc, int nraw) {
     const size_t nch = Cin / CK;
-    return (size_t)nraw * RAW_BYTES + 2 * (size_t)A_BYTES + nch * 27 * (size_t)Cout * 32 + (has_sc ? nch * (size_t)Cout * 32 : 0) +
+    const size_t hvox = (size_t)(TZ + 2) * HY * HX;
+    const size_t raw = hvox * CK * 2, a_bytes = 2 * (hvox * 16 + 64);
+    return (size_t)nraw * raw + 2 * a_bytes + nch * 27 * (size_t)Cout * 32 + (has_sc ? nch * (size_t)Cout * 32 : 0) +
            sizeof(float) * (2 * (size_t)Cin + 4 * (size_t)Cout);
+}
+
+static int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return (e && e[0]) ? atoi(e) : dflt;
 }
 
 }  // namespace
@@ -366,30 +429,47 @@ int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int 
     const bool has_sc = sc_w != nullptr;
     if (x->dtype != L3D_BF16 || t->dtype != L3D_BF16) return -1;
     if (Cin % 16 != 0 || Cout % 16 != 0 || Cout > 256) return -1;
-    const int cols_needed = 2 * MT * Cout * (has_sc ? 2 : 1);
-    if (cols_needed > 512) return -1;
-    auto occ_of = [](size_t bytes) { int o = (int)((227 * 1024) / (bytes + 2048)); return o > 3 ? 3 : o; };
-    // two TMA buffers (prefetch two work items ahead) unless that costs a resident CTA
-    int nraw = 2;
-    if (c3_smem_bytes(Cin, Cout, has_sc, 2) > 226 * 1024 || occ_of(c3_smem_bytes(Cin, Cout, has_sc, 2)) < occ_of(c3_smem_bytes(Cin, Cout, has_sc, 1)))
-        nraw = 1;
-    const size_t smem = c3_smem_bytes(Cin, Cout, has_sc, nraw);
-    if (smem > 226 * 1024) return -1;
     auto aligned = [](const l3d_act *a, int mult) {
         return (a->ldc % mult == 0) && (reinterpret_cast<uintptr_t>(a->ptr) % (2 * mult) == 0);
     };
     if (!aligned(x, 8) || !aligned(t, 8) || (has_sc && (act_null(r) || !aligned(r, 8)))) return -1;
+    // ---- tile height: the tallest tile (fewest halo planes and MMAs per voxel) whose accumulators fit TMEM and whose
+    // buffers fit shared memory; two accumulator sets (epilogue of tile T under the MMAs of tile T+1) when they fit
+    const int force_tz = env_int("L3D_C3_TZ", 0), force_nraw = env_int("L3D_C3_NRAW", 0), force_sets = env_int("L3D_C3_SETS", 0);   // tuning / test knobs
+    const int nacc = has_sc ? 2 : 1;
+    int TZ = 0, nraw = 0, nsets = 0;
+    for (int tz : {8, 6, 4, 2}) {
+        if (force_tz && tz != force_tz) continue;
+        if (!force_tz && tz > 2 && tz > D) continue;                 // no taller than the volume
+        const int cols1 = tz * Cout * nacc;
+        if (cols1 > 512) continue;
+        int ns = 2 * cols1 <= 512 ? 2 : 1;
+        if (force_sets) ns = force_sets;
+        if (ns * cols1 > 512) continue;
+        int nr = c3_smem_bytes(tz, Cin, Cout, has_sc, 2) <= 226 * 1024 ? 2 : 1;
+        if (force_nraw) nr = force_nraw;
+        if (c3_smem_bytes(tz, Cin, Cout, has_sc, nr) > 226 * 1024) continue;
+        // prefer a shorter tile with double-buffered accumulators over a taller single-buffered one
+        if (ns == 1 && tz > 2 && !force_tz && !force_sets) {
+            const int cols_half = (tz / 2) * Cout * nacc;
+            if (2 * cols_half <= 512 && tz / 2 >= 2) continue;
+        }
+        TZ = tz; nraw = nr; nsets = ns;
+        break;
+    }
+    if (TZ == 0) return -1;
+    const size_t smem = c3_smem_bytes(TZ, Cin, Cout, has_sc, nraw);
     const long long tiles = (long long)N * ((D + TZ - 1) / TZ) * ((H + TY - 1) / TY) * ((W + TX - 1) / TX);
     if (tiles >= (1ll << 30)) return -1;
     int cols = 32;
-    while (cols < cols_needed) cols <<= 1;
+    while (cols < nsets * TZ * Cout * nacc) cols <<= 1;
 
     CUtensorMap tmap;
     {
         const cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
         const cuuint64_t es = 2, ld = (cuuint64_t)x->ldc;
         const cuuint64_t strides[4] = {ld * es, (cuuint64_t)W * ld * es, (cuuint64_t)H * W * ld * es, (cuuint64_t)D * H * W * ld * es};
-        const cuuint32_t box[5] = {CK, HX, HY, HZ, 1};
+        const cuuint32_t box[5] = {CK, HX, HY, (cuuint32_t)(TZ + 2), 1};
         const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
         if (l3d_encode_tiled(&tmap, (int)CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x->ptr, (const unsigned long long *)dims,
                              (const unsigned long long *)strides, (const unsigned *)box, (const unsigned *)estr)) return 3;
@@ -400,14 +480,10 @@ int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int 
     A.w = w; A.groups = w != nullptr ? groups : 1; A.dw_w = dw_w; A.pw_w = pw_w; A.sc_w = sc_w; A.Cout = Cout;
     A.t = (bf16 *)t->ptr; A.ldt = t->ldc; A.t_stats = t_stats;
     A.r = has_sc ? (bf16 *)r->ptr : nullptr; A.ldr = has_sc ? r->ldc : 0; A.r_stats = r_stats;
-    A.tmem_cols = cols; A.nraw = nraw;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-        if (e != cudaSuccess) { l3d_set_error("conv3_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 3; }
-        attr_set = true;
-    }
-    int occ = occ_of(smem);
+    A.tmem_cols = cols; A.nraw = nraw; A.nsets = nsets;
+    A.merge = (3 * Cout <= 256 && env_int("L3D_C3_NOMERGE", 0) == 0) ? 1 : 0;
+    int occ = (int)((227 * 1024) / (smem + 2048));
+    if (occ > 3) occ = 3;
     if (occ < 1) occ = 1;
     if (occ * cols > 512) occ = 512 / cols;
     int dev = 0, sms = 148;
@@ -415,7 +491,32 @@ int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     long long grid = (long long)sms * occ;
     if (grid > tiles) grid = tiles;
-    conv3_tc_kernel<<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(tmap, A);
+#define L3D_C3_LAUNCH(TZV, MG)                                                                                                 \
+    do {                                                                                                                    \
+        static bool attr_set = false;                                                                                       \
+        if (!attr_set) {                                                                                                    \
+            cudaError_t e = cudaFuncSetAttribute(conv3_tc_kernel<TZV, MG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
+            if (e != cudaSuccess) { l3d_set_error("conv3_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 3; } \
+            attr_set = true;                                                                                                \
+        }                                                                                                                   \
+        conv3_tc_kernel<TZV, MG><<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(tmap, A);                              \
+    } while (0)
+    if (A.merge) {
+        switch (TZ) {
+            case 8: L3D_C3_LAUNCH(8, true); break;
+            case 6: L3D_C3_LAUNCH(6, true); break;
+            case 4: L3D_C3_LAUNCH(4, true); break;
+            default: L3D_C3_LAUNCH(2, true); break;
+        }
+    } else {
+        switch (TZ) {
+            case 8: L3D_C3_LAUNCH(8, false); break;
+            case 6: L3D_C3_LAUNCH(6, false); break;
+            case 4: L3D_C3_LAUNCH(4, false); break;
+            default: L3D_C3_LAUNCH(2, false); break;
+        }
+    }
+#undef L3D_C3_LAUNCH
     l3d_count_launch();
     L3D_CUDA_OK("l3d_conv3 (tcgen05 implicit GEMM) launch");
     return 0;

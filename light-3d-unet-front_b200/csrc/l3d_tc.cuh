@@ -27,6 +27,13 @@ __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence
 // make st.shared writes visible to the async proxy (tcgen05.mma reads its operands through it)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// one lane of a converged warp (elect.sync): the idiom ptxas recognises as "single thread active"
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier --------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

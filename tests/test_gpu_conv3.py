@@ -1,0 +1,128 @@
+"""Layer-level GPU parity of the tcgen05 implicit-GEMM 3x3x3 conv (csrc/l3d_conv3_tc.cu) through the C-ABI:
+every tile height / accumulator-set / TMA-buffer configuration, ragged volumes, dense, grouped and composed
+depthwise-separable (+ shortcut) weights, against torch conv3d in fp32 on the same bf16-stored inputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+EPS, SLOPE = 1e-5, 0.01
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _inputs(N, dims, Cin, seed):
+    g = torch.Generator().manual_seed(seed)
+    D, H, W = dims
+    x = torch.randn(N, D, H, W, Cin, generator=g).to(torch.bfloat16)
+    vox = D * H * W
+    xf = x.float()
+    # statistics of the stored tensor, as the producer's epilogue would have accumulated them: {sum, sumsq}[N][C]
+    stats = torch.stack([xf.sum(dim=(1, 2, 3)), (xf * xf).sum(dim=(1, 2, 3))]).double()
+    gamma = torch.rand(Cin, generator=g) + 0.5
+    beta = torch.randn(Cin, generator=g) * 0.3
+    mean = stats[0] / vox
+    var = stats[1] / vox - mean * mean
+    rstd = 1.0 / torch.sqrt(var + EPS)
+    scale = (gamma.double() * rstd).float()                       # [N][C]
+    shift = (beta.double() - mean * gamma.double() * rstd).float()
+    a = F.leaky_relu(xf * scale[:, None, None, None, :] + shift[:, None, None, None, :], SLOPE)
+    return x, stats, gamma, beta, a, vox
+
+
+def _run(case, env):
+    from light_unet import _native as nv
+    kind, N, dims, Cin, Cout, groups, use_norm = case
+    D, H, W = dims
+    x, stats, gamma, beta, a, vox = _inputs(N, dims, Cin, 7)
+    if not use_norm:
+        a = x.float()
+    g = torch.Generator().manual_seed(11)
+    st = nv.stream_ptr(torch.device(DEV))
+    xd = x.to(DEV)
+    keep = [xd]
+    xn = nv.norm()
+    if use_norm:
+        sd, gd, bd = stats.to(DEV).contiguous(), gamma.to(DEV), beta.to(DEV)
+        keep += [sd, gd, bd]
+        xn = nv.norm(sd, gd, bd, None, EPS, SLOPE, vox)
+    t = torch.zeros(N, D, H, W, Cout, dtype=torch.bfloat16, device=DEV)
+    t_stats = torch.zeros(2 * N * Cout, dtype=torch.float64, device=DEV)
+    a_ncdhw = a.permute(0, 4, 1, 2, 3).contiguous()
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        before = nv.launch_count()
+        if kind == "dense":
+            w = torch.randn(Cout, Cin // groups, 3, 3, 3, generator=g) / np.sqrt(27 * Cin / groups)
+            wd = w.to(DEV)
+            nv.call("l3d_conv3_fwd", nv.act(xd), xn, N, D, H, W, nv.ptr(wd), groups, nv.act(t), nv.ptr(t_stats), st)
+            ref_t = F.conv3d(a_ncdhw, w, padding=1, groups=groups)
+            ref_r, r = None, None
+        else:
+            dw = torch.randn(Cin, 1, 3, 3, 3, generator=g) / np.sqrt(27.0)
+            pw = torch.randn(Cout, Cin, 1, 1, 1, generator=g) / np.sqrt(Cin)
+            sc = torch.randn(Cout, Cin, 1, 1, 1, generator=g) / np.sqrt(Cin)
+            dwd, pwd, scd = dw.to(DEV), pw.to(DEV), sc.to(DEV)
+            r = torch.zeros(N, D, H, W, Cout, dtype=torch.bfloat16, device=DEV)
+            r_stats = torch.zeros(2 * N * Cout, dtype=torch.float64, device=DEV)
+            nv.call("l3d_dwpw_fwd", nv.act(xd), xn, N, D, H, W, nv.ptr(dwd), nv.ptr(pwd), nv.ptr(scd), nv.act(t),
+                    nv.ptr(t_stats), nv.act(r), nv.ptr(r_stats), nv.act(None), st)
+            ref_t = F.conv3d(F.conv3d(a_ncdhw, dw, padding=1, groups=Cin), pw)
+            ref_r = F.conv3d(a_ncdhw, sc)
+        torch.cuda.synchronize()
+        assert nv.launch_count() - before == 1
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    outs = [(t, t_stats, ref_t)] + ([(r, r_stats, ref_r)] if r is not None else [])
+    for got, gstats, ref in outs:
+        got_f = got.float().cpu()
+        e = _rel(got_f.permute(0, 4, 1, 2, 3), ref)
+        assert e < 4e-3, (case, env, e)
+        # the statistics are sums over exactly the stored (bf16-rounded) values
+        want = torch.stack([got_f.double().sum(dim=(1, 2, 3)), (got_f.double() ** 2).sum(dim=(1, 2, 3))]).reshape(-1)
+        gs = gstats.cpu()
+        assert float((gs - want).abs().max() / (want.abs().max() + 1e-30)) < 2e-4, (case, env)
+
+
+CASES = [
+    ("dense", 2, (20, 19, 21), 16, 16, 1, True),
+    ("dense", 1, (9, 33, 8), 32, 32, 1, True),
+    ("dense", 2, (8, 16, 24), 16, 64, 1, False),
+    ("dense", 1, (7, 18, 10), 16, 128, 1, True),       # 3*Cout > 256: per-plane (unmerged) MMAs
+    ("dense", 1, (12, 16, 16), 32, 16, 8, True),       # grouped weights
+    ("dws", 2, (20, 19, 21), 16, 16, 1, True),
+    ("dws", 1, (24, 24, 24), 32, 16, 1, False),
+    ("dws", 1, (13, 16, 9), 16, 32, 1, True),
+    ("dws", 1, (12, 12, 12), 64, 32, 1, True),
+]
+
+
+@pytest.mark.parametrize("tz", [0, 2, 4, 6, 8])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"{c[0]}-{c[3]}to{c[4]}-{'x'.join(map(str, c[2]))}")
+def test_conv3_tc_tile_heights(case, tz):
+    env = {"L3D_DWS_IGEMM_MAX": 1 << 20}
+    if tz:
+        nacc = 2 if case[0] == "dws" else 1
+        if tz * case[4] * nacc > 512:
+            pytest.skip("accumulators of this tile height do not fit TMEM")
+        env["L3D_C3_TZ"] = tz
+    _run(case, env)
+
+
+@pytest.mark.parametrize("knobs", [{"L3D_C3_SETS": 1}, {"L3D_C3_NRAW": 1}, {"L3D_C3_NOMERGE": 1},
+                                   {"L3D_C3_TZ": 4, "L3D_C3_SETS": 1, "L3D_C3_NRAW": 1}])
+def test_conv3_tc_pipeline_variants(knobs):
+    for case in (CASES[0], CASES[5], CASES[6]):
+        _run(case, dict(knobs, L3D_DWS_IGEMM_MAX=1 << 20))
