@@ -208,6 +208,11 @@ int l3d_bbox_reduce(const int32_t *labels, const float *prob, int D, int H, int 
  * and fp32 accumulation in TMEM.  A, Wt, D are fp32 device arrays. */
 int l3d_tc_selftest(const float *A, const float *Wt, int MT, int K, int N, float *D, void *stream);
 
+/* Development aid: per-work-item clock64 stamps of CTA 0 of the last implicit-GEMM conv launched with
+ * L3D_C3_DEBUG_SKIP & 8 ({worker: box landed, operand buffer free, operand written, accumulators ready, epilogue
+ * done; issuer: operand ready, accumulators free, MMAs issued} x up to 128 items); n int64 values are copied. */
+int l3d_conv3_debug_read(long long *host, int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,7 +23,7 @@ namespace {
 
 constexpr int TY = 16, TX = 8;                          // one MMA tile (128 rows) = one z-plane of 16 (y) x 8 (x) voxels
 constexpr int HY = TY + 2, HX = TX + 2;                 // 18 x 10 halo plane
-constexpr int CK = 16, NW = 256, NT = NW + 32;          // 8 worker warps + 1 issuer warp
+constexpr int CK = 16;
 constexpr int ROWPITCH = HX * 16;                       // 160 B between y rows of one 8-channel group
 
 // CTA tile: TZ output planes; the halo tile has TZ + 2 planes
@@ -36,8 +36,10 @@ struct Geo {
                                                              // two groups written by a lane pair land in different bank halves
     static constexpr int A_BYTES = 2 * PLANE;
     static constexpr int ACT_ITEMS = HVOX * 2;
-    static constexpr int ACT_PER_THREAD = (ACT_ITEMS + NW - 1) / NW;
 };
+
+// development aid: per-tile clock64 stamps of CTA 0 (L3D_C3_DEBUG_SKIP & 8), read back with l3d_conv3_debug_read
+__device__ long long g_c3_dbg[128 * 8];
 
 struct C3Args {
     int Cin; NormDev xn;
@@ -49,7 +51,7 @@ struct C3Args {
     int Cout;
     bf16 *t; int ldt; double *t_stats;
     bf16 *r; int ldr; double *r_stats;
-    int tmem_cols, nraw, nsets, merge;
+    int tmem_cols, nraw, nsets, merge, merged_cx, dbg;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -64,7 +66,8 @@ __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NW) : "memory"); }
+template <int NW>
+__device__ __forceinline__ void worker_bar_n() { asm volatile("bar.sync 1, %0;" ::"n"(NW) : "memory"); }
 
 // Warp-specialised: warps 0..7 (256 threads) are workers (activation pass + epilogue), warp 8 is the issuer (TMA
 // loads and tcgen05.mma).  Hand-offs are mbarriers only, so the tensor pipe, the TMA unit and the CUDA cores run
@@ -79,9 +82,13 @@ __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::
 // in consecutive TMEM column blocks, and the weight tile of (chunk, dy, dx) holds the rows [dz=2 | dz=1 | dz=0], so
 // input plane zi updates output planes zi-2, zi-1, zi with a single N = 3*Cout MMA.  9*(TZ+2) MMAs per 16-channel
 // chunk instead of 27*TZ.
-template <int TZ, bool MERGE>
-__global__ void __launch_bounds__(NT, (TZ >= 6 ? 1 : 2)) conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, C3Args A) {
+template <int TZ, bool MERGE, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 : 2)) conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, C3Args A) {
     using G = Geo<TZ>;
+    constexpr int NW = NWARPS * 32, NT = NW + 32;          // worker warps + 1 issuer warp
+    constexpr int ACT_PER_THREAD = (G::ACT_ITEMS + NW - 1) / NW;
+    constexpr int EPG = NWARPS / 4;                        // worker warps per TMEM lane quarter: plane stride of the epilogue
+    auto worker_bar = [] { worker_bar_n<NW>(); };
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_tma_full[2], s_a_full[2], s_mma_done[2], s_acc_free[2];
     __shared__ uint32_t s_tmem;
@@ -170,7 +177,8 @@ __global__ void __launch_bounds__(NT, (TZ >= 6 ? 1 : 2)) conv3_tc_kernel(const _
             const int rb = item % nraw;
             if (tc::elect_one()) {
                 tc::mbar_expect_tx(&s_tma_full[rb], G::RAW_BYTES);
-                tc::tma_load_5d(s_raw + (size_t)rb * G::RAW_BYTES, &tmap, &s_tma_full[rb], chn * CK, x0 - 1, y0 - 1, z0 - 1, n);
+                if (A.merged_cx) tc::tma_load_4d(s_raw + (size_t)rb * G::RAW_BYTES, &tmap, &s_tma_full[rb], (x0 - 1) * CK, y0 - 1, z0 - 1, n);
+                else tc::tma_load_5d(s_raw + (size_t)rb * G::RAW_BYTES, &tmap, &s_tma_full[rb], chn * CK, x0 - 1, y0 - 1, z0 - 1, n);
             }
         };
         for (int i = 0; i < nraw && i < n_items; ++i) issue_tma(i);
@@ -181,14 +189,18 @@ __global__ void __launch_bounds__(NT, (TZ >= 6 ? 1 : 2)) conv3_tc_kernel(const _
         for (int it = 0; it < n_items; ++it) {
             const int buf = it & 1, set = tj % nsets;
             tc::mbar_wait(&s_a_full[buf], (uint32_t)((it >> 1) & 1));        // operand tile written, raw box consumed
+            const bool stamp = (A.dbg & 8) && blockIdx.x == 0 && it < 128;
+            if (stamp && lane == 0) g_c3_dbg[it * 8 + 5] = clock64();
             if (it + nraw < n_items) issue_tma(it + nraw);
             if (ch == 0 && tj >= nsets) tc::mbar_wait(&s_acc_free[set], (uint32_t)(((tj / nsets) - 1) & 1));   // epilogue of tile tj-nsets done
             tc::fence_after_sync();
+            if (stamp && lane == 0) g_c3_dbg[it * 8 + 6] = clock64();
             const uint64_t ad0 = tc::smem_desc(sA_u + buf * G::A_BYTES, G::PLANE, ROWPITCH);
             const uint64_t bd0 = tc::smem_desc(sB_u + (uint32_t)(ch * 9) * btile_bytes, 3 * Cout * 16, 128);
             const uint32_t d_t = tmem_u + (uint32_t)(set * acc_cols);
             const bool first = ch == 0;
             if (tc::elect_one()) {
+              if (!(A.dbg & 4)) {
 #pragma unroll
                 for (int zi = 0; zi < TZ + 2; ++zi) {
                     const int lo = zi >= 2 ? zi - 2 : 0, hi = zi <= TZ - 1 ? zi : TZ - 1;     // output planes fed by input plane zi
@@ -230,18 +242,20 @@ __global__ void __launch_bounds__(NT, (TZ >= 6 ? 1 : 2)) conv3_tc_kernel(const _
                         tc::mma_f16(d_t + (uint32_t)((TZ + p) * Cout), ad0 + aoff, bd2, idesc1, ch > 0 ? 1u : 0u);
                     }
                 }
+              }
                 tc::mma_commit(&s_mma_done[buf]);
             }
             __syncwarp();
+            if (stamp && lane == 0) g_c3_dbg[it * 8 + 7] = clock64();
             if (++ch == nchunks) { ch = 0; ++tj; }
         }
     } else {
         // ===================================== workers =====================================
         // activation-pass role: fixed 16-byte vectors of the raw box; q (8-channel group) is the same for all of them
         const int aq = tid & 1;
-        uint32_t act_item[G::ACT_PER_THREAD];
+        uint32_t act_item[ACT_PER_THREAD];
 #pragma unroll
-        for (int k = 0; k < G::ACT_PER_THREAD; ++k) {
+        for (int k = 0; k < ACT_PER_THREAD; ++k) {
             const int item = tid + k * NW;
             int hv = item >> 1;
             const int hx = hv % HX; hv /= HX;
@@ -249,7 +263,7 @@ __global__ void __launch_bounds__(NT, (TZ >= 6 ? 1 : 2)) conv3_tc_kernel(const _
             const int hz = hv / HY;
             act_item[k] = item < G::ACT_ITEMS ? ((uint32_t)hx | ((uint32_t)hy << 8) | ((uint32_t)hz << 16)) : 0xffffffffu;
         }
-        // epilogue role: voxel row of the MMA tiles (planes) em, em + 2, ...
+        // epilogue role: voxel row of the MMA tiles (planes) em, em + EPG, ...
         const int em = warp >> 2, erow = (warp & 3) * 32 + lane;
         const int elx = erow & 7, ely = erow >> 3;
         int stat_n = -1;
@@ -281,6 +295,7 @@ __global__ void __launch_bounds__(NT, (TZ >= 6 ? 1 : 2)) conv3_tc_kernel(const _
             const size_t vox0 = (((size_t)n * A.D + z0) * A.H + gy) * A.W + gx;
             const size_t zstride = (size_t)A.H * A.W;
             const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(set * acc_cols);
+            if (!(A.dbg & 2))
             for (int a = 0; a < nacc; ++a) {
                 bf16 *outb = a == 0 ? A.t : A.r;
                 const int ldo = a == 0 ? A.ldt : A.ldr;
@@ -290,7 +305,7 @@ __global__ void __launch_bounds__(NT, (TZ >= 6 ? 1 : 2)) conv3_tc_kernel(const _
 #pragma unroll
                     for (int j = 0; j < 32; ++j) sv[j] = 0.f;
 #pragma unroll 1
-                    for (int p = em; p < TZ; p += 2) {
+                    for (int p = em; p < TZ; p += EPG) {
                         float v[16];
                         tc::tmem_ld16(trow + (uint32_t)((a * TZ + p) * Cout + cb), v);
                         const bool valid = valid_yx && (z0 + p < A.D);
@@ -351,40 +366,77 @@ __global__ void __launch_bounds__(NT, (TZ >= 6 ? 1 : 2)) conv3_tc_kernel(const _
                 const float4 sc1 = *reinterpret_cast<const float4 *>(s_scale + ch * CK + aq * 8 + 4);
                 const float4 sh0 = *reinterpret_cast<const float4 *>(s_shift + ch * CK + aq * 8);
                 const float4 sh1 = *reinterpret_cast<const float4 *>(s_shift + ch * CK + aq * 8 + 4);
-                const float sl = A.xn.slope;
+                const __half2 sl2 = __float2half2_rn(A.xn.slope);
+                const bool ident = A.xn.stats == nullptr;
+                const bool stamp = (A.dbg & 8) && blockIdx.x == 0 && it < 128 && tid == 0;
                 tc::mbar_wait(&s_tma_full[rb], (uint32_t)((it / nraw) & 1));               // raw box of this item landed
+                if (stamp) g_c3_dbg[it * 8 + 0] = clock64();
                 if (it >= 2) tc::mbar_wait(&s_mma_done[buf], (uint32_t)(((it >> 1) - 1) & 1));   // MMAs of item it-2 done: A[buf] free
-                // ---- activation pass: raw bf16 [z][y][x][16] -> fp16 planar [q][z][y][x][8]
+                if (stamp) g_c3_dbg[it * 8 + 1] = clock64();
+                // ---- activation pass: raw bf16 [z][y][x][16] -> fp16 planar [q][z][y][x][8]; the shared-memory loads of a
+                // batch of vectors are issued before any of them is used
+                constexpr int ACT_BATCH = 4;
+                if (!(A.dbg & 1))
 #pragma unroll
-                for (int k = 0; k < G::ACT_PER_THREAD; ++k) {
-                    const uint32_t ai = act_item[k];
-                    if (ai != 0xffffffffu) {
-                        const int hx = ai & 255, hy = (ai >> 8) & 255, hz = ai >> 16;
-                        const int item = tid + k * NW;
-                        uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                        if ((mx >> hx) & (my >> hy) & (mz >> hz) & 1u) {
-                            const uint4 rw = *reinterpret_cast<const uint4 *>(Rb + (size_t)item * 16);
-                            float f[8];
-                            f[0] = fmaf(__uint_as_float(rw.x << 16), sc0.x, sh0.x); f[1] = fmaf(__uint_as_float(rw.x & 0xffff0000u), sc0.y, sh0.y);
-                            f[2] = fmaf(__uint_as_float(rw.y << 16), sc0.z, sh0.z); f[3] = fmaf(__uint_as_float(rw.y & 0xffff0000u), sc0.w, sh0.w);
-                            f[4] = fmaf(__uint_as_float(rw.z << 16), sc1.x, sh1.x); f[5] = fmaf(__uint_as_float(rw.z & 0xffff0000u), sc1.y, sh1.y);
-                            f[6] = fmaf(__uint_as_float(rw.w << 16), sc1.z, sh1.z); f[7] = fmaf(__uint_as_float(rw.w & 0xffff0000u), sc1.w, sh1.w);
+                for (int k0 = 0; k0 < ACT_PER_THREAD; k0 += ACT_BATCH) {
+                    uint4 rw[ACT_BATCH];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], f[j] * sl);      // LeakyReLU, 0 <= slope <= 1
-                            o = make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]), pack_f16x2(f[6], f[7]));
+                    for (int kk = 0; kk < ACT_BATCH; ++kk) {
+                        const int k = k0 + kk;
+                        if (k < ACT_PER_THREAD) {
+                            const int item = tid + k * NW;
+                            rw[kk] = make_uint4(0u, 0u, 0u, 0u);
+                            if ((k + 1) * NW <= G::ACT_ITEMS || item < G::ACT_ITEMS) rw[kk] = *reinterpret_cast<const uint4 *>(Rb + (size_t)item * 16);
                         }
-                        *reinterpret_cast<uint4 *>(Ab + (size_t)aq * G::PLANE + (size_t)(item >> 1) * 16) = o;
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < ACT_BATCH; ++kk) {
+                        const int k = k0 + kk;
+                        if (k < ACT_PER_THREAD) {
+                            const uint32_t ai = act_item[k];
+                            const int item = tid + k * NW;
+                            if ((k + 1) * NW <= G::ACT_ITEMS || ai != 0xffffffffu) {
+                                const int hx = ai & 255, hy = (ai >> 8) & 255, hz = ai >> 16;
+                                const uint4 r4 = rw[kk];
+                                float f[8];
+                                f[0] = __uint_as_float(r4.x << 16); f[1] = __uint_as_float(r4.x & 0xffff0000u);
+                                f[2] = __uint_as_float(r4.y << 16); f[3] = __uint_as_float(r4.y & 0xffff0000u);
+                                f[4] = __uint_as_float(r4.z << 16); f[5] = __uint_as_float(r4.z & 0xffff0000u);
+                                f[6] = __uint_as_float(r4.w << 16); f[7] = __uint_as_float(r4.w & 0xffff0000u);
+                                uint4 o;
+                                if (ident) {        // already-activated input (a block's first conv): bf16 -> fp16 only
+                                    o = make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]), pack_f16x2(f[6], f[7]));
+                                } else {
+                                    f[0] = fmaf(f[0], sc0.x, sh0.x); f[1] = fmaf(f[1], sc0.y, sh0.y); f[2] = fmaf(f[2], sc0.z, sh0.z); f[3] = fmaf(f[3], sc0.w, sh0.w);
+                                    f[4] = fmaf(f[4], sc1.x, sh1.x); f[5] = fmaf(f[5], sc1.y, sh1.y); f[6] = fmaf(f[6], sc1.z, sh1.z); f[7] = fmaf(f[7], sc1.w, sh1.w);
+                                    // LeakyReLU on the packed fp16 values (0 <= slope <= 1): max(v, slope * v)
+                                    __half2 h[4];
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        h[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+                                        h[j] = __hmax2(h[j], __hmul2(h[j], sl2));
+                                    }
+                                    o = make_uint4(*reinterpret_cast<uint32_t *>(&h[0]), *reinterpret_cast<uint32_t *>(&h[1]),
+                                                   *reinterpret_cast<uint32_t *>(&h[2]), *reinterpret_cast<uint32_t *>(&h[3]));
+                                }
+                                if (!((mx >> hx) & (my >> hy) & (mz >> hz) & 1u)) o = make_uint4(0u, 0u, 0u, 0u);   // conv zero padding
+                                *reinterpret_cast<uint4 *>(Ab + (size_t)aq * G::PLANE + (size_t)(item >> 1) * 16) = o;
+                            }
+                        }
                     }
                 }
                 tc::fence_async_smem();
                 __syncwarp();
+                if (stamp) g_c3_dbg[it * 8 + 2] = clock64();
                 if (lane == 0) mbar_arrive(&s_a_full[buf]);
                 // ---- epilogue of the previous tile (its MMAs were issued one work item ago)
                 if (ch == 0 && tile > tile_begin) {
                     const int pit = it - 1;
                     tc::mbar_wait(&s_mma_done[pit & 1], (uint32_t)((pit >> 1) & 1));
                     tc::fence_after_sync();
+                    if (stamp) g_c3_dbg[it * 8 + 3] = clock64();
                     epilogue(tile - 1, (tj - 1) % nsets);
+                    if (stamp) g_c3_dbg[it * 8 + 4] = clock64();
                 }
             }
         }
@@ -416,6 +468,10 @@ static int env_int(const char *name, int dflt) {
 }
 
 }  // namespace
+
+extern "C" int l3d_conv3_debug_read(long long *host, int n) {
+    return cudaMemcpyFromSymbol(host, g_c3_dbg, sizeof(long long) * (size_t)(n < 1024 ? n : 1024)) == cudaSuccess ? 0 : 2;
+}
 
 // Implicit-GEMM 3x3x3 conv on tcgen05.  Exactly one of {w} / {dw_w, pw_w} is given.  Returns -1 when the path
 // does not apply (the caller falls back to another kernel).
@@ -464,8 +520,20 @@ int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int 
     int cols = 32;
     while (cols < nsets * TZ * Cout * nacc) cols <<= 1;
 
+    // TMA moves one request per innermost box row, and a 16-channel voxel is only 32 B: when the view is a whole
+    // 16-channel tensor the (C, W) axes are contiguous and merge into one axis, so a box row is a 320-B x-row
+    // (10 voxels) instead of ten 32-B rows (measured: the 5-D box is TMA-issue bound).
+    const bool merged_cx = Cin == CK && x->ldc == CK && env_int("L3D_C3_NOMERGECX", 0) == 0;
     CUtensorMap tmap;
-    {
+    if (merged_cx) {
+        const cuuint64_t dims[4] = {(cuuint64_t)W * CK, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+        const cuuint64_t rowb = (cuuint64_t)W * CK * 2;
+        const cuuint64_t strides[3] = {rowb, (cuuint64_t)H * rowb, (cuuint64_t)D * H * rowb};
+        const cuuint32_t box[4] = {HX * CK, HY, (cuuint32_t)(TZ + 2), 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        if (l3d_encode_tiled(&tmap, (int)CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x->ptr, (const unsigned long long *)dims,
+                             (const unsigned long long *)strides, (const unsigned *)box, (const unsigned *)estr)) return 3;
+    } else {
         const cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
         const cuuint64_t es = 2, ld = (cuuint64_t)x->ldc;
         const cuuint64_t strides[4] = {ld * es, (cuuint64_t)W * ld * es, (cuuint64_t)H * W * ld * es, (cuuint64_t)D * H * W * ld * es};
@@ -480,7 +548,7 @@ int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int 
     A.w = w; A.groups = w != nullptr ? groups : 1; A.dw_w = dw_w; A.pw_w = pw_w; A.sc_w = sc_w; A.Cout = Cout;
     A.t = (bf16 *)t->ptr; A.ldt = t->ldc; A.t_stats = t_stats;
     A.r = has_sc ? (bf16 *)r->ptr : nullptr; A.ldr = has_sc ? r->ldc : 0; A.r_stats = r_stats;
-    A.tmem_cols = cols; A.nraw = nraw; A.nsets = nsets;
+    A.tmem_cols = cols; A.nraw = nraw; A.nsets = nsets; A.merged_cx = merged_cx ? 1 : 0; A.dbg = env_int("L3D_C3_DEBUG_SKIP", 0);
     A.merge = (3 * Cout <= 256 && env_int("L3D_C3_NOMERGE", 0) == 0) ? 1 : 0;
     int occ = (int)((227 * 1024) / (smem + 2048));
     if (occ > 3) occ = 3;
@@ -491,31 +559,28 @@ int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     long long grid = (long long)sms * occ;
     if (grid > tiles) grid = tiles;
-#define L3D_C3_LAUNCH(TZV, MG)                                                                                                 \
+#define L3D_C3_LAUNCH(TZV, MG, NWV)                                                                                                 \
     do {                                                                                                                    \
         static bool attr_set = false;                                                                                       \
         if (!attr_set) {                                                                                                    \
-            cudaError_t e = cudaFuncSetAttribute(conv3_tc_kernel<TZV, MG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
+            cudaError_t e = cudaFuncSetAttribute(conv3_tc_kernel<TZV, MG, NWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
             if (e != cudaSuccess) { l3d_set_error("conv3_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 3; } \
             attr_set = true;                                                                                                \
         }                                                                                                                   \
-        conv3_tc_kernel<TZV, MG><<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(tmap, A);                              \
+        conv3_tc_kernel<TZV, MG, NWV><<<(unsigned)grid, NWV * 32 + 32, smem, (cudaStream_t)stream>>>(tmap, A);                \
     } while (0)
-    if (A.merge) {
-        switch (TZ) {
-            case 8: L3D_C3_LAUNCH(8, true); break;
-            case 6: L3D_C3_LAUNCH(6, true); break;
-            case 4: L3D_C3_LAUNCH(4, true); break;
-            default: L3D_C3_LAUNCH(2, true); break;
-        }
-    } else {
-        switch (TZ) {
-            case 8: L3D_C3_LAUNCH(8, false); break;
-            case 6: L3D_C3_LAUNCH(6, false); break;
-            case 4: L3D_C3_LAUNCH(4, false); break;
-            default: L3D_C3_LAUNCH(2, false); break;
-        }
+#define L3D_C3_TZ(MG, NWV)                                \
+    switch (TZ) {                                         \
+        case 8: L3D_C3_LAUNCH(8, MG, NWV); break;         \
+        case 6: L3D_C3_LAUNCH(6, MG, NWV); break;         \
+        case 4: L3D_C3_LAUNCH(4, MG, NWV); break;         \
+        default: L3D_C3_LAUNCH(2, MG, NWV); break;        \
     }
+    // 12 worker warps (3 per scheduler) hide the latency of the activation pass and the epilogue when one CTA owns the SM
+    const int nwarps = env_int("L3D_C3_WARPS", occ == 1 ? 12 : 8);
+    if (A.merge) { if (nwarps == 12) { L3D_C3_TZ(true, 12) } else { L3D_C3_TZ(true, 8) } }
+    else         { if (nwarps == 12) { L3D_C3_TZ(false, 12) } else { L3D_C3_TZ(false, 8) } }
+#undef L3D_C3_TZ
 #undef L3D_C3_LAUNCH
     l3d_count_launch();
     L3D_CUDA_OK("l3d_conv3 (tcgen05 implicit GEMM) launch");

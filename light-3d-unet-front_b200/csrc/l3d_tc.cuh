@@ -63,6 +63,12 @@ __device__ __forceinline__ void tma_load_5d(void *dst_smem, const void *tmap, ui
                  : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d(void *dst_smem, const void *tmap, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(dst_smem)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
 // ---- descriptors -----------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu);

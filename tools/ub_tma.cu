@@ -1,0 +1,103 @@
+// Micro-benchmark (development tool): achieved bandwidth of TMA halo-box loads from a channels-last bf16 tensor
+// [N][D][H][W][16], as a function of the box shape, the number of boxes in flight per CTA and the CTAs per SM.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I light-3d-unet-front_b200/csrc -o tools/ub_tma tools/ub_tma.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "l3d_tc.cuh"
+
+struct P { int N, D, H, W; int tz, ty, tx; int merged; int nbuf; int box_bytes; int strided; };
+
+__global__ void __launch_bounds__(128) tma_kernel(const __grid_constant__ CUtensorMap tmap, P p, unsigned long long *sink) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar[8];
+    const int tid = threadIdx.x;
+    if (tid == 0) for (int i = 0; i < p.nbuf; ++i) tc::mbar_init(&bar[i], 1);
+    __syncthreads();
+    const int tilesX = p.W / p.tx, tilesY = p.H / p.ty, tilesZ = p.D / p.tz;
+    const int tps = tilesX * tilesY * tilesZ, total = tps * p.N;
+    const int per = (total + gridDim.x - 1) / gridDim.x;
+    // strided: tile = blockIdx.x + k * gridDim.x (neighbouring CTAs read neighbouring tiles at the same time)
+    const int t0 = p.strided ? 0 : blockIdx.x * per, t1 = p.strided ? (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : min(total, t0 + per);
+    auto issue = [&](int tt, int b) {
+        const int t = p.strided ? (int)blockIdx.x + tt * (int)gridDim.x : tt;
+        const int n = t / tps; int r = t - n * tps;
+        const int x0 = (r % tilesX) * p.tx; r /= tilesX;
+        const int y0 = (r % tilesY) * p.ty; const int z0 = (r / tilesY) * p.tz;
+        tc::mbar_expect_tx(&bar[b], p.box_bytes);
+        if (p.merged) tc::tma_load_4d(smem + (size_t)b * p.box_bytes, &tmap, &bar[b], (x0 - 1) * 16, y0 - 1, z0 - 1, n);
+        else tc::tma_load_5d(smem + (size_t)b * p.box_bytes, &tmap, &bar[b], 0, x0 - 1, y0 - 1, z0 - 1, n);
+    };
+    unsigned long long acc = 0;
+    if (tid == 0) {
+        for (int i = 0; i < p.nbuf && t0 + i < t1; ++i) issue(t0 + i, i);
+        for (int t = t0; t < t1; ++t) {
+            const int i = t - t0, b = i % p.nbuf;
+            tc::mbar_wait(&bar[b], (uint32_t)((i / p.nbuf) & 1));
+            acc += *reinterpret_cast<volatile unsigned long long *>(smem + (size_t)b * p.box_bytes);
+            if (t + p.nbuf < t1) issue(t + p.nbuf, b);
+        }
+        if (acc == 0x1234567) sink[0] = acc;
+    }
+}
+
+typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                              const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int main() {
+    const int N = 96, D = 48, H = 48, W = 48, C = 16;
+    void *x; unsigned long long *sink;
+    const size_t bytes = (size_t)N * D * H * W * C * 2;
+    cudaMalloc(&x, bytes); cudaMemset(x, 0, bytes); cudaMalloc(&sink, 8);
+    void *fp = nullptr; cudaDriverEntryPointQueryResult q;
+    cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q);
+    encode_fn enc = (encode_fn)fp;
+    cudaFuncSetAttribute(tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    struct S { int tz, ty, tx; } shapes[] = {{6, 16, 8}, {8, 16, 8}};
+    for (auto s : shapes)
+      for (int strided = 0; strided <= 1; ++strided)
+        for (int merged = 0; merged <= 1; ++merged)
+            for (int nbuf : {1, 2, 3, 4})
+                for (int occ : {1}) {
+                    const int hz = s.tz + 2, hy = s.ty + 2, hx = s.tx + 2;
+                    if (!merged && hx > 256) continue;
+                    if (merged && hx * 16 > 256) continue;
+                    const int box_bytes = hz * hy * hx * 32;
+                    const size_t smem = (size_t)box_bytes * nbuf;
+                    if (smem * occ > 220 * 1024 || smem > 220 * 1024) continue;
+                    CUtensorMap tm;
+                    CUresult cr;
+                    if (merged) {
+                        const cuuint64_t dims[4] = {(cuuint64_t)W * C, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+                        const cuuint64_t rb = (cuuint64_t)W * C * 2, st[3] = {rb, H * rb, (cuuint64_t)D * H * rb};
+                        const cuuint32_t box[4] = {(cuuint32_t)hx * 16, (cuuint32_t)hy, (cuuint32_t)hz, 1}, es[4] = {1, 1, 1, 1};
+                        cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, st, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    } else {
+                        const cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+                        const cuuint64_t st[4] = {32, (cuuint64_t)W * 32, (cuuint64_t)H * W * 32, (cuuint64_t)D * H * W * 32};
+                        const cuuint32_t box[5] = {16, (cuuint32_t)hx, (cuuint32_t)hy, (cuuint32_t)hz, 1}, es[5] = {1, 1, 1, 1, 1};
+                        cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x, dims, st, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    }
+                    if (cr != CUDA_SUCCESS) { printf("encode failed %d\n", (int)cr); continue; }
+                    P p{N, D, H, W, s.tz, s.ty, s.tx, merged, nbuf, box_bytes, strided};
+                    const int grid = 148 * occ;
+                    // pad dynamic smem so that exactly `occ` CTAs fit per SM
+                    const size_t smem_launch = occ == 1 ? (smem > 120 * 1024 ? smem : 120 * 1024) : (smem > 60 * 1024 ? smem : 60 * 1024);
+                    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+                    tma_kernel<<<grid, 128, smem_launch>>>(tm, p, sink);
+                    cudaEventRecord(e0);
+                    for (int i = 0; i < 5; ++i) tma_kernel<<<grid, 128, smem_launch>>>(tm, p, sink);
+                    cudaEventRecord(e1);
+                    if (cudaDeviceSynchronize() != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
+                    float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
+                    const double tiles = (double)N * (D / s.tz) * (H / s.ty) * (W / s.tx);
+                    printf("%s tile %dx%dx%-2d %s nbuf %d occ %d box %6d B : %7.1f us  box traffic %5.2f TB/s  unique %5.2f TB/s\n", strided ? "strided" : "ranges ", s.tz, s.ty, s.tx,
+                           merged ? "merged(C*W)" : "5-D        ", nbuf, occ, box_bytes, ms * 1e3, tiles * box_bytes / (ms * 1e-3) / 1e12,
+                           (double)bytes / (ms * 1e-3) / 1e12);
+                }
+    return 0;
+}
