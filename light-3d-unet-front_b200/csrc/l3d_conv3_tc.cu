@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
     constexpr int EPG = NWARPS / 4;                        // worker warps per TMEM lane quarter: plane stride of the epilogue
     auto worker_bar = [] { worker_bar_n<NW>(); };
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t s_tma_full[2], s_a_full[2], s_mma_done[2], s_acc_free[2];
+    __shared__ __align__(8) uint64_t s_tma_full[4], s_a_full[2], s_mma_done[2], s_acc_free[2];
     __shared__ uint32_t s_tmem;
     const int Cin = A.Cin, Cout = A.Cout;
     const bool has_sc = A.sc_w != nullptr;
@@ -109,8 +109,9 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == NW / 32) tc::tmem_alloc(&s_tmem, (uint32_t)A.tmem_cols);
     if (tid == 0) {
+        for (int i = 0; i < 4; ++i) tc::mbar_init(&s_tma_full[i], 1);
         for (int i = 0; i < 2; ++i) {
-            tc::mbar_init(&s_tma_full[i], 1); tc::mbar_init(&s_a_full[i], NW / 32);
+            tc::mbar_init(&s_a_full[i], NW / 32);
             tc::mbar_init(&s_mma_done[i], 1); tc::mbar_init(&s_acc_free[i], NW / 32);
         }
     }
@@ -118,19 +119,30 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
     {
         const int cin_g = Cin / A.groups, cout_g = Cout / A.groups;
         const int rows = 3 * Cout;
-        for (int i = tid; i < Cout * Cin * 27; i += NT) {
-            const int tap = i % 27;
-            const int ci = (i / 27) % Cin;
-            const int co = i / (27 * Cin);
-            float wv;
+        // one (co, ci) pair per step: its 27 taps are contiguous in global memory and all loads are in flight together
+        for (int i = tid; i < Cout * Cin; i += NT) {
+            const int ci = i % Cin, co = i / Cin;
+            float wv[27];
             if (A.w != nullptr) {
                 const int g = co / cout_g, cl = ci - g * cin_g;
-                wv = (cl >= 0 && cl < cin_g) ? A.w[((size_t)co * cin_g + cl) * 27 + tap] : 0.f;
+                const bool in_group = cl >= 0 && cl < cin_g;
+                const float *src = A.w + ((size_t)co * cin_g + (in_group ? cl : 0)) * 27;
+#pragma unroll
+                for (int tap = 0; tap < 27; ++tap) wv[tap] = in_group ? src[tap] : 0.f;
             } else {
-                wv = A.pw_w[(size_t)co * Cin + ci] * A.dw_w[(size_t)ci * 27 + tap];
+                const float pwv = A.pw_w[(size_t)co * Cin + ci];
+                const float *src = A.dw_w + (size_t)ci * 27;
+#pragma unroll
+                for (int tap = 0; tap < 27; ++tap) wv[tap] = src[tap];
+#pragma unroll
+                for (int tap = 0; tap < 27; ++tap) wv[tap] *= pwv;
             }
-            const int ch = ci >> 4, k = ci & 15, dz = tap / 9, t9 = tap - dz * 9;
-            *reinterpret_cast<__half *>(sB + (size_t)(ch * 9 + t9) * btile_bytes + tc::tile_off((2 - dz) * Cout + co, k, rows)) = __float2half_rn(wv);
+            const int ch = ci >> 4, k = ci & 15;
+#pragma unroll
+            for (int tap = 0; tap < 27; ++tap) {
+                const int dz = tap / 9, t9 = tap - dz * 9;
+                *reinterpret_cast<__half *>(sB + (size_t)(ch * 9 + t9) * btile_bytes + tc::tile_off((2 - dz) * Cout + co, k, rows)) = __float2half_rn(wv[tap]);
+            }
         }
         if (has_sc)
             for (int i = tid; i < Cout * Cin; i += NT) {
@@ -170,18 +182,25 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
         // live in uniform registers); one elected lane issues the TMA loads and the tcgen05.mma / commit.  A
         // single-lane branch around the loop makes ptxas wrap every MMA in an ELECT / R2UR.BROADCAST waterfall.
         const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem);    // TMEM base (from shared memory) as a uniform value
-        auto issue_tma = [&](int item) {
-            const int tl = tile_begin + item / nchunks, chn = item % nchunks;
-            int n, z0, y0, x0;
-            tile_coord(tl, n, z0, y0, x0);
-            const int rb = item % nraw;
+        // TMA cursor: (tile, chunk) of the next box to request, advanced incrementally (no divisions on the issue path)
+        int pf_item = 0, pf_ch = 0, pf_n, pf_z0, pf_y0, pf_x0;
+        tile_coord(tile_begin < tile_end ? tile_begin : 0, pf_n, pf_z0, pf_y0, pf_x0);
+        auto issue_tma = [&]() {
+            if (pf_item >= n_items) return;
+            const int rb = pf_item % nraw;
             if (tc::elect_one()) {
                 tc::mbar_expect_tx(&s_tma_full[rb], G::RAW_BYTES);
-                if (A.merged_cx) tc::tma_load_4d(s_raw + (size_t)rb * G::RAW_BYTES, &tmap, &s_tma_full[rb], (x0 - 1) * CK, y0 - 1, z0 - 1, n);
-                else tc::tma_load_5d(s_raw + (size_t)rb * G::RAW_BYTES, &tmap, &s_tma_full[rb], chn * CK, x0 - 1, y0 - 1, z0 - 1, n);
+                if (A.merged_cx) tc::tma_load_4d(s_raw + (size_t)rb * G::RAW_BYTES, &tmap, &s_tma_full[rb], (pf_x0 - 1) * CK, pf_y0 - 1, pf_z0 - 1, pf_n);
+                else tc::tma_load_5d(s_raw + (size_t)rb * G::RAW_BYTES, &tmap, &s_tma_full[rb], pf_ch * CK, pf_x0 - 1, pf_y0 - 1, pf_z0 - 1, pf_n);
+            }
+            ++pf_item;
+            if (++pf_ch == nchunks) {
+                pf_ch = 0;
+                pf_x0 += TX;
+                if (pf_x0 >= A.W) { pf_x0 = 0; pf_y0 += TY; if (pf_y0 >= A.H) { pf_y0 = 0; pf_z0 += TZ; if (pf_z0 >= A.D) { pf_z0 = 0; ++pf_n; } } }
             }
         };
-        for (int i = 0; i < nraw && i < n_items; ++i) issue_tma(i);
+        for (int i = 0; i < nraw; ++i) issue_tma();
         const uint32_t idesc1 = tc::idesc_f16_m128(Cout), idesc2 = tc::idesc_f16_m128(2 * Cout), idesc3 = tc::idesc_f16_m128(3 * Cout);
         const uint32_t brow = (uint32_t)(Cout >> 3) * 128 >> 4;     // descriptor units (16 B) per Cout rows of a weight tile
         const uint32_t bstep = btile_bytes >> 4;
@@ -191,7 +210,7 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
             tc::mbar_wait(&s_a_full[buf], (uint32_t)((it >> 1) & 1));        // operand tile written, raw box consumed
             const bool stamp = (A.dbg & 8) && blockIdx.x == 0 && it < 128;
             if (stamp && lane == 0) g_c3_dbg[it * 8 + 5] = clock64();
-            if (it + nraw < n_items) issue_tma(it + nraw);
+            issue_tma();                                                     // refill the raw box just consumed
             if (ch == 0 && tj >= nsets) tc::mbar_wait(&s_acc_free[set], (uint32_t)(((tj / nsets) - 1) & 1));   // epilogue of tile tj-nsets done
             tc::fence_after_sync();
             if (stamp && lane == 0) g_c3_dbg[it * 8 + 6] = clock64();
@@ -502,9 +521,12 @@ int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int 
         int ns = 2 * cols1 <= 512 ? 2 : 1;
         if (force_sets) ns = force_sets;
         if (ns * cols1 > 512) continue;
-        int nr = c3_smem_bytes(tz, Cin, Cout, has_sc, 2) <= 226 * 1024 ? 2 : 1;
+        // raw TMA boxes in flight: a box has microseconds of latency under load, so as many as fit (up to 4)
+        int nr = 1;
+        for (int c = 4; c >= 1; --c) if (c3_smem_bytes(tz, Cin, Cout, has_sc, c) <= 226 * 1024) { nr = c; break; }
         if (force_nraw) nr = force_nraw;
         if (c3_smem_bytes(tz, Cin, Cout, has_sc, nr) > 226 * 1024) continue;
+        if (nr < 2 && tz > 2 && !force_tz && !force_nraw) continue;     // a shorter tile with >= 2 boxes in flight beats a taller one with 1
         // prefer a shorter tile with double-buffered accumulators over a taller single-buffered one
         if (ns == 1 && tz > 2 && !force_tz && !force_sets) {
             const int cols_half = (tz / 2) * Cout * nacc;

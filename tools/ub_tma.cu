@@ -42,20 +42,28 @@ __global__ void __launch_bounds__(128) tma_kernel(const __grid_constant__ CUtens
     }
 }
 
+__global__ void fill_random(uint32_t *p, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t h = (uint32_t)i * 2654435761u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+        p[i] = (h & 0x3fff3fffu) | 0x30003000u;      // two bf16 values of moderate magnitude
+    }
+}
+
 typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 int main() {
-    const int N = 96, D = 48, H = 48, W = 48, C = 16;
+    const int N = getenv("UB_N") ? atoi(getenv("UB_N")) : 32, D = 48, H = 48, W = 48, C = 16;
     void *x; unsigned long long *sink;
     const size_t bytes = (size_t)N * D * H * W * C * 2;
-    cudaMalloc(&x, bytes); cudaMemset(x, 0, bytes); cudaMalloc(&sink, 8);
+    cudaMalloc(&x, bytes); cudaMemset(x, 0, bytes);
+    if (getenv("UB_RANDOM")) { fill_random<<<1024, 256>>>((uint32_t *)x, bytes / 4); cudaDeviceSynchronize(); printf("random data\n"); } cudaMalloc(&sink, 8);
     void *fp = nullptr; cudaDriverEntryPointQueryResult q;
     cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q);
     encode_fn enc = (encode_fn)fp;
     cudaFuncSetAttribute(tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    struct S { int tz, ty, tx; } shapes[] = {{6, 16, 8}, {8, 16, 8}};
+    struct S { int tz, ty, tx; } shapes[] = {{6, 16, 8}};
     for (auto s : shapes)
       for (int strided = 0; strided <= 1; ++strided)
         for (int merged = 0; merged <= 1; ++merged)
