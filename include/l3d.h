@@ -208,6 +208,15 @@ int l3d_bbox_reduce(const int32_t *labels, const float *prob, int D, int H, int 
  * and fp32 accumulation in TMEM.  A, Wt, D are fp32 device arrays. */
 int l3d_tc_selftest(const float *A, const float *Wt, int MT, int K, int N, float *D, void *stream);
 
+/* Self-test of the kind::tf32 forms used by the tensor-core pointwise backward.  mode 0: D[128][N] = G[128][K] . WU[N][K]^T
+ * (K-major operands); mode 1: D[m][n] = sum_v G[v][m] * WU[v][n] over 128 voxels (MN-major operands, rows >= M of D are
+ * don't-care).  fp32 device arrays; operands are rounded to tf32 by the tensor core. */
+int l3d_tc_selftest_tf32(const float *G, const float *WU, int mode, int M, int K, int N, float *D, void *stream);
+
+/* Self-test of the 16-bit MN-major voxel reduction used by the tensor-core weight gradients:
+ * D[m][n] = sum_{v<128} G[v][m] * U[v][n] with bf16 operands (rows >= M of D are don't-care). */
+int l3d_tc_selftest_mn16(const float *G, const float *U, int M, int N, int var, float *D, void *stream);
+
 /* Development aid: per-work-item clock64 stamps of CTA 0 of the last implicit-GEMM conv launched with
  * L3D_C3_DEBUG_SKIP & 8 ({worker: box landed, operand buffer free, operand written, accumulators ready, epilogue
  * done; issuer: operand ready, accumulators free, MMAs issued} x up to 128 items); n int64 values are copied. */

@@ -29,21 +29,6 @@ __device__ __forceinline__ NormCoef norm_coef(const NormDev &nd, int N, int C, i
     return k;
 }
 
-// g_t = a*gz + b*t + d : InstanceNorm(affine) backward with the two reductions red = {sum gz, sum gz*xhat}
-__device__ __forceinline__ void in_bwd_coef(const NormDev &nd, const double *__restrict__ red, int N, int C, int n, int c,
-                                            float &a, float &b, float &d) {
-    if (nd.stats == nullptr) { a = 1.f; b = 0.f; d = 0.f; return; }
-    float mean, rstd;
-    norm_mean_rstd(nd, N, C, n, c, mean, rstd);
-    const double inv = 1.0 / (double)nd.count;
-    const float k1 = (float)(red[(size_t)n * C + c] * inv);
-    const float k2 = (float)(red[(size_t)N * C + (size_t)n * C + c] * inv);
-    const float gr = nd.gamma[c] * rstd;
-    a = gr;
-    b = -gr * rstd * k2;
-    d = gr * (mean * rstd * k2 - k1);
-}
-
 template <typename T>
 __device__ __forceinline__ void ld4a(const T *p, float (&v)[4]) {
     const float4 f = ld4(p);
@@ -1119,6 +1104,10 @@ extern "C" int l3d_merge_bwd(const l3d_act *g_out, const l3d_act *pooled_g, cons
     return 0;
 }
 
+int l3d_pw_bwd_tc(const l3d_act *gz, const l3d_act *t, const l3d_norm *nt, const double *red, const l3d_act *u,
+                  const l3d_norm *un, int N, long long vox, const float *w, float *g_w, const l3d_act *g_u,
+                  int accumulate_gu, void *stream);
+
 extern "C" int l3d_pw_bwd(const l3d_act *gz, const l3d_act *t, const l3d_norm *nt, const double *red,
                           const l3d_act *u, const l3d_norm *un, int N, int D, int H, int W,
                           const float *w, float *g_w, const l3d_act *g_u, int accumulate_gu, void *stream) {
@@ -1142,6 +1131,11 @@ extern "C" int l3d_pw_bwd(const l3d_act *gz, const l3d_act *t, const l3d_norm *n
     A.g_u = has_gu ? g_u->ptr : nullptr; A.ldgu = has_gu ? g_u->ldc : 0; A.accumulate = accumulate_gu;
     // the vector path of the u loader needs an aligned base as well
     if (u->C % 4 == 0 && !vec4_ok(u)) { l3d_set_error("l3d_pw_bwd: u view must be 4-channel aligned"); return 1; }
+    {   // tensor-core path (bf16 storage, 16-aligned channel counts)
+        const int rc_tc = l3d_pw_bwd_tc(gz, t, nt, red, u, un, N, A.vox, w, g_w, g_u, accumulate_gu, stream);
+        if (rc_tc == 0) { l3d_count_launch(); return 0; }
+        if (rc_tc > 0) return rc_tc;
+    }
     int rc = 0;
     L3D_DISPATCH_DTYPE(u->dtype, T, { rc = launch_pw_bwd<T, false>(A, (cudaStream_t)stream); });
     if (rc) return rc;

@@ -1,0 +1,270 @@
+// Tensor-core backward of the pointwise (1x1x1) stage for bf16 storage (unet3d.py:18, 70-72): both GEMMs of the stage
+// run on tcgen05 from the SAME two staged tiles.
+//
+//   stage   g_t[v][c] = a_c*gz[v][c] + b_c*t[v][c] + d_c   (InstanceNorm backward on load, fp32) and the activated
+//           u[v][k], for 128 voxels, as bf16 in the voxel-planar layout [channel/8][128 voxels][8 channels];
+//           g_t is split into hi + lo bf16 parts (the weights too), so the products carry ~16 mantissa bits
+//   dgrad   D1[v][k] = sum_c g_t[v][c] * W[c][k]      A = G tile read K-major  (rows = voxels, K = channels)
+//   wgrad   D2[c][k] += sum_v g_t[v][c] * u[v][k]     A = G tile read MN-major (M = channels, K = voxels),
+//                                                     B = U tile read MN-major (N = channels, K = voxels)
+//           D2 stays in TMEM over all tiles of the CTA and is flushed once with one atomic per weight.
+//
+// The MN-major reading of the planar tile (LBO = 128 B: next 8 voxels, SBO = 2048 B: next 8 channels) was validated
+// with l3d_tc_selftest_mn16; kind::tf32 accepts only K-major operands on this part (MN-major yields zeros), which is
+// why the operands are bf16 hi/lo pairs rather than tf32.
+#include "l3d_common.cuh"
+#include "l3d_tc.cuh"
+
+namespace {
+
+constexpr int NT = 256, TV = 128;
+constexpr int PLANE = TV * 16;          // bytes of one 8-channel group of a tile
+
+struct PwTcArgs {
+    const float *gz; int ldg;
+    const bf16 *t; int ldt; NormDev nt; const double *red;
+    const bf16 *u; int ldu; NormDev un;
+    int N; long long vox;
+    int Cg, Cu;
+    const float *w; float *g_w;
+    float *g_u; int ldgu; int accumulate;
+    int tmem_cols;
+};
+
+__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+// hi = bf16(x), lo = bf16(x - hi): two values at a time
+__device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t &lo) {
+    hi = pack2_bf16(a, b);
+    lo = pack2_bf16(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+}
+
+__global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    const int Cg = A.Cg, Cu = A.Cu, gq = Cg >> 3, uq = Cu >> 3;
+    unsigned char *sGh = smem;                              // gq planes
+    unsigned char *sGl = sGh + (size_t)gq * PLANE;
+    unsigned char *sU = sGl + (size_t)gq * PLANE;           // uq planes
+    unsigned char *sWh = sU + (size_t)uq * PLANE;           // dgrad B operand: [N = Cu][K = Cg] K-major
+    unsigned char *sWl = sWh + (size_t)Cg * Cu * 2;
+    float *s_ca = reinterpret_cast<float *>(sWl + (size_t)Cg * Cu * 2);
+    float *s_cb = s_ca + Cg, *s_cd = s_cb + Cg, *s_us = s_cd + Cg, *s_uh = s_us + Cu;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool has_gu = A.g_u != nullptr, has_gw = A.g_w != nullptr;
+    if (warp == 0) tc::tmem_alloc(&s_tmem, (uint32_t)A.tmem_cols);
+    if (tid == 32) tc::mbar_init(&s_bar, 1);
+    for (int i = tid; i < Cg * Cu; i += NT) {               // w[c][k]
+        const int k = i % Cu, c = i / Cu;
+        const float wv = A.w[i];
+        const bf16 hi = __float2bfloat16_rn(wv);
+        const uint32_t off = tc::tile_off(k, c, Cu);
+        *reinterpret_cast<bf16 *>(sWh + off) = hi;
+        *reinterpret_cast<bf16 *>(sWl + off) = __float2bfloat16_rn(wv - __bfloat162float(hi));
+    }
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = s_tmem;
+    const uint32_t d1 = tmem, d2 = tmem + (uint32_t)Cu;
+    const uint32_t id_k = tc::idesc_16b_m128(Cu, 1, 1, false, false), id_mn = tc::idesc_16b_m128(Cu, 1, 1, true, true);
+    const uint32_t sGh_u = tc::smem_u32(sGh), sGl_u = tc::smem_u32(sGl), sU_u = tc::smem_u32(sU), sWh_u = tc::smem_u32(sWh), sWl_u = tc::smem_u32(sWl);
+
+    const long long tiles_per_sample = (A.vox + TV - 1) / TV;
+    const long long total_tiles = tiles_per_sample * A.N;
+    const bool has_nt = A.nt.stats != nullptr, u_ident = A.un.stats == nullptr;
+    int cur_n = -1;
+    uint32_t phase = 0;
+    bool first = true;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n = (int)(tile / tiles_per_sample);
+        const long long v0 = (tile % tiles_per_sample) * TV;
+        if (n != cur_n) {
+            cur_n = n;
+            for (int c = tid; c < Cg; c += NT) {
+                float a, b, d;
+                in_bwd_coef(A.nt, A.red, A.N, Cg, n, c, a, b, d);
+                s_ca[c] = a; s_cb[c] = b; s_cd[c] = d;
+            }
+            for (int k = tid; k < Cu; k += NT) {
+                float sc, sh;
+                norm_scale_shift(A.un, A.N, Cu, n, k, sc, sh);
+                s_us[k] = sc; s_uh[k] = sh;
+            }
+            __syncthreads();
+        }
+        // ---- stage G (hi / lo): item = (8-channel group q, voxel v), consecutive threads = consecutive voxels
+        for (int item = tid; item < gq * TV; item += NT) {
+            const int v = item & (TV - 1), q = item >> 7;
+            uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+            if (v0 + v < A.vox) {
+                const size_t gv = (size_t)n * A.vox + v0 + v;
+                const float4 g0 = *reinterpret_cast<const float4 *>(A.gz + gv * (size_t)A.ldg + q * 8);
+                const float4 g1 = *reinterpret_cast<const float4 *>(A.gz + gv * (size_t)A.ldg + q * 8 + 4);
+                float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                if (has_nt) {
+                    const uint4 tr = *reinterpret_cast<const uint4 *>(A.t + gv * (size_t)A.ldt + q * 8);
+                    const uint32_t tw[4] = {tr.x, tr.y, tr.z, tr.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = q * 8 + 2 * j;
+                        g[2 * j] = fmaf(s_ca[c], g[2 * j], fmaf(s_cb[c], __uint_as_float(tw[j] << 16), s_cd[c]));
+                        g[2 * j + 1] = fmaf(s_ca[c + 1], g[2 * j + 1], fmaf(s_cb[c + 1], __uint_as_float(tw[j] & 0xffff0000u), s_cd[c + 1]));
+                    }
+                }
+                split2(g[0], g[1], hi.x, lo.x); split2(g[2], g[3], hi.y, lo.y);
+                split2(g[4], g[5], hi.z, lo.z); split2(g[6], g[7], hi.w, lo.w);
+            }
+            *reinterpret_cast<uint4 *>(sGh + (size_t)q * PLANE + (size_t)v * 16) = hi;
+            *reinterpret_cast<uint4 *>(sGl + (size_t)q * PLANE + (size_t)v * 16) = lo;
+        }
+        // ---- stage U (activated, bf16)
+        if (has_gw) {
+            for (int item = tid; item < uq * TV; item += NT) {
+                const int v = item & (TV - 1), q = item >> 7;
+                uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                if (v0 + v < A.vox) {
+                    const size_t gv = (size_t)n * A.vox + v0 + v;
+                    o = *reinterpret_cast<const uint4 *>(A.u + gv * (size_t)A.ldu + q * 8);
+                    if (!u_ident) {
+                        uint32_t w4[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int k = q * 8 + 2 * j;
+                            const float a0 = lrelu(fmaf(__uint_as_float(w4[j] << 16), s_us[k], s_uh[k]), A.un.slope);
+                            const float a1 = lrelu(fmaf(__uint_as_float(w4[j] & 0xffff0000u), s_us[k + 1], s_uh[k + 1]), A.un.slope);
+                            w4[j] = pack2_bf16(a0, a1);
+                        }
+                        o = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                    }
+                }
+                *reinterpret_cast<uint4 *>(sU + (size_t)q * PLANE + (size_t)v * 16) = o;
+            }
+        }
+        tc::fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            if (has_gu) {
+                // D1 = Gh.Wh + Gl.Wh + Gh.Wl    (K = Cg in steps of 16 = two channel-group planes)
+                for (int j = 0; j < Cg / 16; ++j) {
+                    const uint64_t agh = tc::smem_desc(sGh_u + 2 * j * PLANE, PLANE, 128), agl = tc::smem_desc(sGl_u + 2 * j * PLANE, PLANE, 128);
+                    const uint64_t bwh = tc::smem_desc(sWh_u + 2 * j * Cu * 16, Cu * 16, 128), bwl = tc::smem_desc(sWl_u + 2 * j * Cu * 16, Cu * 16, 128);
+                    tc::mma_f16(d1, agh, bwh, id_k, j > 0 ? 1u : 0u);
+                    tc::mma_f16(d1, agl, bwh, id_k, 1u);
+                    tc::mma_f16(d1, agh, bwl, id_k, 1u);
+                }
+            }
+            if (has_gw) {
+                // D2 += (Gh + Gl)^T . U        (K = 128 voxels in steps of 16 = two 8-voxel groups)
+                for (int j = 0; j < TV / 16; ++j) {
+                    const uint64_t bu = tc::smem_desc(sU_u + j * 256, 128, PLANE);
+                    tc::mma_f16(d2, tc::smem_desc(sGh_u + j * 256, 128, PLANE), bu, id_mn, (first && j == 0) ? 0u : 1u);
+                    tc::mma_f16(d2, tc::smem_desc(sGl_u + j * 256, 128, PLANE), bu, id_mn, 1u);
+                }
+            }
+            tc::mma_commit(&s_bar);
+        }
+        first = false;
+        tc::mbar_wait(&s_bar, phase);
+        phase ^= 1u;
+        tc::fence_after_sync();
+        // ---- epilogue: D1 -> g_u (fp32); thread = voxel row, the two warp groups split the column blocks
+        if (has_gu) {
+            const int v = (warp & 3) * 32 + lane;
+            const bool ok = v0 + v < A.vox;
+            float *op = A.g_u + ((size_t)n * A.vox + v0 + (ok ? v : 0)) * (size_t)A.ldgu;
+            const uint32_t trow = d1 + ((uint32_t)((warp & 3) * 32) << 16);
+            for (int cb = (warp >> 2) * 16; cb < Cu; cb += 32) {
+                float r[16];
+                tc::tmem_ld16(trow + (uint32_t)cb, r);
+                if (ok) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        float4 o = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                        if (A.accumulate) { const float4 p = *reinterpret_cast<const float4 *>(op + cb + j); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+                        *reinterpret_cast<float4 *>(op + cb + j) = o;
+                    }
+                }
+            }
+        }
+        tc::fence_before_sync();
+        __syncthreads();                 // tiles and D1 free for the next work item
+    }
+    // ---- flush the weight gradient: row = output channel c, column = input channel k
+    if (has_gw && !first) {
+        tc::fence_after_sync();
+        const int c = (warp & 3) * 32 + lane;
+        const uint32_t trow = d2 + ((uint32_t)((warp & 3) * 32) << 16);
+        if ((warp & 3) * 32 < Cg) {      // warp-uniform: this lane quarter holds valid rows
+            for (int cb = (warp >> 2) * 16; cb < Cu; cb += 32) {
+                float r[16];
+                tc::tmem_ld16(trow + (uint32_t)cb, r);
+                if (c < Cg) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) atomicAdd(&A.g_w[(size_t)c * Cu + cb + j], r[j]);
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)A.tmem_cols);
+}
+
+}  // namespace
+
+// Returns -1 when the tensor-core path does not apply (the caller falls back to the CUDA-core kernel).
+int l3d_pw_bwd_tc(const l3d_act *gz, const l3d_act *t, const l3d_norm *nt, const double *red, const l3d_act *u,
+                  const l3d_norm *un, int N, long long vox, const float *w, float *g_w, const l3d_act *g_u,
+                  int accumulate_gu, void *stream) {
+    { const char *e = getenv("L3D_NO_TC_BWD"); if (e && e[0] == '1') return -1; }
+    const int Cg = gz->C, Cu = u->C;
+    const bool has_nt = nt != nullptr && nt->stats != nullptr, has_gu = !act_null(g_u);
+    if (u->dtype != L3D_BF16 || gz->dtype != L3D_F32 || (has_nt && t->dtype != L3D_BF16)) return -1;
+    if (Cg % 16 != 0 || Cu % 16 != 0 || Cg > 128 || Cu > 256) return -1;
+    auto al = [](const l3d_act *a, int elems, int bytes) { return a->ldc % elems == 0 && reinterpret_cast<uintptr_t>(a->ptr) % bytes == 0; };
+    if (!al(gz, 4, 16) || !al(u, 8, 16) || (has_nt && !al(t, 8, 16)) || (has_gu && !al(g_u, 4, 16))) return -1;
+    if (g_w == nullptr && !has_gu) return -1;
+    // an activated u is not exactly representable in bf16 (it would need a hi/lo pair like g_t); every caller on the
+    // U-Net path passes a stored bf16 tensor with the identity norm, so the general case stays on the CUDA-core kernel
+    if (un != nullptr && un->stats != nullptr && g_w != nullptr) return -1;
+    size_t smem = (size_t)(2 * (Cg / 8) + Cu / 8) * PLANE + 2 * (size_t)Cg * Cu * 2 + sizeof(float) * (3 * (size_t)Cg + 2 * (size_t)Cu);
+    // the MN-major A operand always spans 128 rows (16 channel groups): keep its over-read inside the allocation
+    const size_t span = (size_t)(Cg / 8) * PLANE + 16 * (size_t)PLANE + 256;
+    if (smem < span) smem = span;
+    if (smem > 226 * 1024) return -1;
+    int cols = 32;
+    while (cols < 2 * Cu) cols <<= 1;
+    PwTcArgs A;
+    A.gz = (const float *)gz->ptr; A.ldg = gz->ldc;
+    A.t = has_nt ? (const bf16 *)t->ptr : nullptr; A.ldt = has_nt ? t->ldc : 0; A.nt = norm_dev(nt); A.red = red;
+    A.u = (const bf16 *)u->ptr; A.ldu = u->ldc; A.un = norm_dev(un);
+    A.N = N; A.vox = vox; A.Cg = Cg; A.Cu = Cu;
+    A.w = w; A.g_w = g_w;
+    A.g_u = has_gu ? (float *)g_u->ptr : nullptr; A.ldgu = has_gu ? g_u->ldc : 0; A.accumulate = accumulate_gu;
+    A.tmem_cols = cols;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(pw_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        if (e != cudaSuccess) { l3d_set_error("pw_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 3; }
+        attr_set = true;
+    }
+    int occ = (int)((227 * 1024) / (smem + 2048));
+    if (occ > 4) occ = 4;
+    if (occ < 1) occ = 1;
+    if (occ * cols > 512) occ = 512 / cols;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long tiles = ((vox + TV - 1) / TV) * N;
+    long long grid = (long long)sms * occ;
+    if (grid > tiles) grid = tiles;
+    pw_bwd_tc_kernel<<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(A);
+    L3D_CUDA_OK("l3d_pw_bwd (tcgen05) launch");
+    return 0;
+}

@@ -115,6 +115,21 @@ __device__ __forceinline__ void norm_scale_shift(const NormDev &nd, int N, int C
     scale = g; shift = b;
 }
 
+// g_t = a*gz + b*t + d : InstanceNorm(affine) backward with the two reductions red = {sum gz, sum gz*xhat}
+__device__ __forceinline__ void in_bwd_coef(const NormDev &nd, const double *__restrict__ red, int N, int C, int n, int c,
+                                            float &a, float &b, float &d) {
+    if (nd.stats == nullptr) { a = 1.f; b = 0.f; d = 0.f; return; }
+    float mean, rstd;
+    norm_mean_rstd(nd, N, C, n, c, mean, rstd);
+    const double inv = 1.0 / (double)nd.count;
+    const float k1 = (float)(red[(size_t)n * C + c] * inv);
+    const float k2 = (float)(red[(size_t)N * C + (size_t)n * C + c] * inv);
+    const float gr = nd.gamma[c] * rstd;
+    a = gr;
+    b = -gr * rstd * k2;
+    d = gr * (mean * rstd * k2 - k1);
+}
+
 // ------------------------------------------------------- warp reductions --
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

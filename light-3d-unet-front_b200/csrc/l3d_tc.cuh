@@ -81,9 +81,33 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 __host__ __device__ constexpr uint32_t idesc_f16_m128(int n) {
     return (1u << 4) /* D = f32 */ | (0u << 7) /* A = f16 */ | (0u << 10) /* B = f16 */ | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
+// kind::f16 with selectable 16-bit formats (0 = fp16, 1 = bf16) and operand majors (MN-major: the M / N index is the
+// contiguous one inside each 16-byte chunk), fp32 accumulate, M = 128, K = 16 per instruction
+__host__ __device__ constexpr uint32_t idesc_16b_m128(int n, int a_fmt, int b_fmt, bool a_mn, bool b_mn) {
+    return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
 __device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// kind::tf32: fp32 words in shared memory (the tensor core reads the top 19 bits), fp32 accumulate, M = 128, K = 8 per
+// instruction.  a_mn / b_mn select MN-major operands (bits 15 / 16): the operand's M (or N) index is the contiguous
+// one inside each 16-byte chunk, as in a tile stored [channel group][voxel][4 channels] and reduced over voxels.
+__host__ __device__ constexpr uint32_t idesc_tf32_m128(int n, bool a_mn, bool b_mn) {
+    return (1u << 4) /* D = f32 */ | (2u << 7) /* A = tf32 */ | (2u << 10) /* B = tf32 */ | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// byte offset of element (row r, column k) of a [rows x K] 32-bit tile in the planar layout [k/4][row][4]:
+// K-major operand (rows = M or N): LBO = rows*16 (next 4 K), SBO = 128 (next 8 rows), K = 8 per MMA = 2 LBO steps;
+// MN-major operand over the same bytes (MN = k index here, K = row index): SBO = rows*16, LBO = 128.
+__device__ __forceinline__ uint32_t tile_off32(int r, int k, int rows) {
+    return (uint32_t)((k >> 2) * rows * 16 + r * 16 + (k & 3) * 4);
 }
 
 // ---- operand tile addressing -------------------------------------------------------------------

@@ -67,6 +67,8 @@ _SIGS = {
     "l3d_bbox_reduce": [_P, _P, c_int, c_int, c_int, _P, c_int, _P],
     "l3d_tc_selftest": [_P, _P, c_int, c_int, c_int, _P, _P],
     "l3d_conv3_debug_read": [_P, c_int],
+    "l3d_tc_selftest_tf32": [_P, _P, c_int, c_int, c_int, c_int, _P, _P],
+    "l3d_tc_selftest_mn16": [_P, _P, c_int, c_int, c_int, _P, _P],
 }
 EXPORTS = sorted(list(_SIGS) + ["l3d_last_error", "l3d_abi_version", "l3d_launch_count", "l3d_ccl_workspace_elems",
                                 "l3d_conv3_bwd_workspace_bytes"])

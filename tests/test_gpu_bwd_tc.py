@@ -1,0 +1,100 @@
+"""Layer-level GPU parity of the tensor-core pointwise backward (csrc/l3d_bwd_tc.cu) through the C-ABI entry point
+l3d_pw_bwd: against a float64 torch restatement of the same math (InstanceNorm backward on load, dgrad, wgrad) and
+against the CUDA-core kernel it replaces (L3D_NO_TC_BWD=1) on identical bf16-stored inputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+EPS, SLOPE = 1e-5, 0.01
+
+
+def _case(N, dims, Cg, Cu, has_nt, u_norm, seed):
+    g = torch.Generator().manual_seed(seed)
+    D, H, W = dims
+    vox = D * H * W
+    gz = (torch.randn(N, D, H, W, Cg, generator=g) * 1e-3 + 2e-3).float()          # gradient with a common offset
+    t = torch.randn(N, D, H, W, Cg, generator=g).to(torch.bfloat16)
+    u = torch.randn(N, D, H, W, Cu, generator=g).to(torch.bfloat16)
+    w = (torch.randn(Cg, Cu, generator=g) / np.sqrt(Cu)).float()
+    gam_t, bet_t = torch.rand(Cg, generator=g) + 0.5, torch.randn(Cg, generator=g) * 0.2
+    gam_u, bet_u = torch.rand(Cu, generator=g) + 0.5, torch.randn(Cu, generator=g) * 0.2
+
+    def stats_of(x):
+        xf = x.double()
+        return torch.stack([xf.sum(dim=(1, 2, 3)), (xf * xf).sum(dim=(1, 2, 3))])
+
+    st_t, st_u = stats_of(t), stats_of(u)
+    # ---- float64 reference
+    gzd, td, ud = gz.double(), t.double(), u.double()
+    if has_nt:
+        mean = st_t[0] / vox
+        rstd = 1.0 / torch.sqrt(st_t[1] / vox - mean * mean + EPS)
+        xhat = (td - mean[:, None, None, None, :]) * rstd[:, None, None, None, :]
+        red = torch.stack([gzd.sum(dim=(1, 2, 3)), (gzd * xhat).sum(dim=(1, 2, 3))])
+        k1, k2 = red[0] / vox, red[1] / vox
+        gr = gam_t.double() * rstd
+        g_t = gr[:, None, None, None, :] * (gzd - k1[:, None, None, None, :] - xhat * k2[:, None, None, None, :])
+    else:
+        red = torch.zeros(2, N, Cg, dtype=torch.float64)
+        g_t = gzd
+    if u_norm:
+        mean_u = st_u[0] / vox
+        rstd_u = 1.0 / torch.sqrt(st_u[1] / vox - mean_u * mean_u + EPS)
+        sc = gam_u.double() * rstd_u
+        sh = bet_u.double() - mean_u * sc
+        ua = F.leaky_relu(ud * sc[:, None, None, None, :] + sh[:, None, None, None, :], SLOPE)
+    else:
+        ua = ud
+    ref_gu = g_t @ w.double()
+    ref_gw = torch.einsum("ndhwc,ndhwk->ck", g_t, ua)
+    return dict(gz=gz, t=t, u=u, w=w, st_t=st_t, st_u=st_u, red=red, gam_t=gam_t, bet_t=bet_t, gam_u=gam_u, bet_u=bet_u,
+                ref_gu=ref_gu, ref_gw=ref_gw, vox=vox)
+
+
+def _run(c, N, dims, has_nt, u_norm, accumulate, env):
+    from light_unet import _native as nv
+    D, H, W = dims
+    dev = {k: (v.to(DEV).contiguous() if torch.is_tensor(v) else v) for k, v in c.items()}
+    nt = nv.norm(dev["st_t"], dev["gam_t"], dev["bet_t"], None, EPS, 1.0, c["vox"]) if has_nt else nv.norm()
+    un = nv.norm(dev["st_u"], dev["gam_u"], dev["bet_u"], None, EPS, SLOPE, c["vox"]) if u_norm else nv.norm()
+    torch.manual_seed(3)
+    gw0 = torch.randn_like(dev["w"]) * 1e-2
+    gu0 = torch.randn(N, D, H, W, c["u"].shape[-1], device=DEV) * 1e-3
+    g_w, g_u = gw0.clone(), gu0.clone()
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        nv.call("l3d_pw_bwd", nv.act(dev["gz"]), nv.act(dev["t"]) if has_nt else nv.act(None), nt, nv.ptr(dev["red"]) if has_nt else None,
+                nv.act(dev["u"]), un, N, D, H, W, nv.ptr(dev["w"]), nv.ptr(g_w), nv.act(g_u), 1 if accumulate else 0,
+                nv.stream_ptr(torch.device(DEV)))
+        torch.cuda.synchronize()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    return (g_u - (gu0 if accumulate else 0)).double().cpu(), (g_w - gw0).double().cpu()
+
+
+def _rel(a, b):
+    return float((a - b).norm() / (b.norm() + 1e-300))
+
+
+@pytest.mark.parametrize("Cg,Cu", [(16, 16), (16, 32), (32, 16), (64, 32), (64, 128), (128, 128), (32, 64)])
+@pytest.mark.parametrize("has_nt,u_norm,accumulate", [(True, False, False), (True, True, True), (False, False, False)])
+def test_pw_bwd_tensor_core(Cg, Cu, has_nt, u_norm, accumulate):
+    N, dims = 2, (10, 9, 13)          # 1170 voxels per sample: ragged last tile
+    c = _case(N, dims, Cg, Cu, has_nt, u_norm, Cg * 131 + Cu)
+    gu_tc, gw_tc = _run(c, N, dims, has_nt, u_norm, accumulate, {})
+    gu_cc, gw_cc = _run(c, N, dims, has_nt, u_norm, accumulate, {"L3D_NO_TC_BWD": "1"})
+    e = dict(gu_tc=_rel(gu_tc, c["ref_gu"]), gw_tc=_rel(gw_tc, c["ref_gw"]), gu_cc=_rel(gu_cc, c["ref_gu"]), gw_cc=_rel(gw_cc, c["ref_gw"]))
+    print(Cg, Cu, has_nt, u_norm, accumulate, {k: f"{v:.2e}" for k, v in e.items()})
+    # hi/lo bf16 operand pairs: ~2^-16 per product; the fp32 CUDA-core kernel is the yardstick
+    assert e["gu_tc"] < 2e-4 and e["gw_tc"] < 2e-4, e
+    assert e["gu_cc"] < 2e-4 and e["gw_cc"] < 2e-4, e

@@ -17,3 +17,36 @@ def test_tcgen05_gemm_selftest(MT, K, N):
     ref = A.half().float() @ W.half().float().t()          # fp16 operands, fp32 accumulation
     err = (D - ref).abs().max().item()
     assert err < 1e-3 * max(1.0, ref.abs().max().item()), (MT, K, N, err)
+
+
+def _tf32(x):
+    return (x.view(torch.int32) & ~0x1fff).view(torch.float32)     # truncate to 10 mantissa bits
+
+
+@pytest.mark.parametrize("K,N", [(8, 16), (16, 16), (32, 64), (128, 128), (64, 256)])
+def test_tf32_kmajor_gemm(K, N):
+    from light_unet import _native as nv
+    torch.manual_seed(K + N)
+    G = torch.randn(128, K, device="cuda")
+    W = torch.randn(N, K, device="cuda")
+    D = torch.full((128, N), float("nan"), device="cuda")
+    nv.call("l3d_tc_selftest_tf32", nv.ptr(G), nv.ptr(W), 0, 128, K, N, nv.ptr(D), nv.stream_ptr(G.device))
+    torch.cuda.synchronize()
+    ref = G.double() @ W.double().t()
+    err = (D.double() - ref).abs().max().item()
+    assert err < 4e-3 * max(1.0, ref.abs().max().item()), (K, N, err)
+
+
+@pytest.mark.parametrize("M,N", [(16, 16), (32, 16), (16, 32), (64, 64), (128, 128), (128, 256), (8, 16)])
+def test_tf32_mnmajor_voxel_reduction(M, N):
+    """The weight-gradient form: both operands MN-major over voxel-planar tiles, reduction over 128 voxels."""
+    from light_unet import _native as nv
+    torch.manual_seed(M * 7 + N)
+    G = torch.randn(128, M, device="cuda")
+    U = torch.randn(128, N, device="cuda")
+    D = torch.full((128, N), float("nan"), device="cuda")
+    nv.call("l3d_tc_selftest_tf32", nv.ptr(G), nv.ptr(U), 1, M, 0, N, nv.ptr(D), nv.stream_ptr(G.device))
+    torch.cuda.synchronize()
+    ref = G.double().t() @ U.double()
+    err = (D[:M].double() - ref).abs().max().item()
+    assert err < 4e-3 * max(1.0, ref.abs().max().item()), (M, N, err)
