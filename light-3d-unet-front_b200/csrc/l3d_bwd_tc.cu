@@ -41,6 +41,9 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t 
     lo = pack2_bf16(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
 }
 
+// GI / UI: G / U staging items (one 8-channel group of one voxel) per thread, held in registers one tile ahead so the
+// global loads of tile T+1 are in flight during the MMAs and the epilogue of tile T.  GI == 0: no prefetch (wide layers).
+template <int GI, int UI>
 __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t s_bar;
@@ -80,6 +83,30 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
     int cur_n = -1;
     uint32_t phase = 0;
     bool first = true;
+    float4 pg0[GI > 0 ? GI : 1], pg1[GI > 0 ? GI : 1];
+    uint4 pt[GI > 0 ? GI : 1], pu[UI > 0 ? UI : 1];
+    auto prefetch = [&](long long tl) {
+        const int pn = (int)(tl / tiles_per_sample);
+        const long long pv0 = (tl % tiles_per_sample) * TV;
+#pragma unroll
+        for (int i = 0; i < GI; ++i) {
+            const int item = tid + i * NT, v = item & (TV - 1), q = item >> 7;
+            if (pv0 + v < A.vox) {
+                const size_t gv = (size_t)pn * A.vox + pv0 + v;
+                pg0[i] = *reinterpret_cast<const float4 *>(A.gz + gv * (size_t)A.ldg + q * 8);
+                pg1[i] = *reinterpret_cast<const float4 *>(A.gz + gv * (size_t)A.ldg + q * 8 + 4);
+                if (has_nt) pt[i] = *reinterpret_cast<const uint4 *>(A.t + gv * (size_t)A.ldt + q * 8);
+            }
+        }
+        if (has_gw) {
+#pragma unroll
+            for (int i = 0; i < UI; ++i) {
+                const int item = tid + i * NT, v = item & (TV - 1), q = item >> 7;
+                if (pv0 + v < A.vox) pu[i] = *reinterpret_cast<const uint4 *>(A.u + ((size_t)pn * A.vox + pv0 + v) * (size_t)A.ldu + q * 8);
+            }
+        }
+    };
+    if (GI > 0 && (long long)blockIdx.x < total_tiles) prefetch(blockIdx.x);
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n = (int)(tile / tiles_per_sample);
         const long long v0 = (tile % tiles_per_sample) * TV;
@@ -97,52 +124,86 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
             }
             __syncthreads();
         }
-        // ---- stage G (hi / lo): item = (8-channel group q, voxel v), consecutive threads = consecutive voxels
-        for (int item = tid; item < gq * TV; item += NT) {
-            const int v = item & (TV - 1), q = item >> 7;
-            uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
-            if (v0 + v < A.vox) {
-                const size_t gv = (size_t)n * A.vox + v0 + v;
-                const float4 g0 = *reinterpret_cast<const float4 *>(A.gz + gv * (size_t)A.ldg + q * 8);
-                const float4 g1 = *reinterpret_cast<const float4 *>(A.gz + gv * (size_t)A.ldg + q * 8 + 4);
-                float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-                if (has_nt) {
-                    const uint4 tr = *reinterpret_cast<const uint4 *>(A.t + gv * (size_t)A.ldt + q * 8);
-                    const uint32_t tw[4] = {tr.x, tr.y, tr.z, tr.w};
+        if (GI > 0) {
+            // ---- registers -> shared memory (the loads were issued one tile ago)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int c = q * 8 + 2 * j;
-                        g[2 * j] = fmaf(s_ca[c], g[2 * j], fmaf(s_cb[c], __uint_as_float(tw[j] << 16), s_cd[c]));
-                        g[2 * j + 1] = fmaf(s_ca[c + 1], g[2 * j + 1], fmaf(s_cb[c + 1], __uint_as_float(tw[j] & 0xffff0000u), s_cd[c + 1]));
-                    }
-                }
-                split2(g[0], g[1], hi.x, lo.x); split2(g[2], g[3], hi.y, lo.y);
-                split2(g[4], g[5], hi.z, lo.z); split2(g[6], g[7], hi.w, lo.w);
-            }
-            *reinterpret_cast<uint4 *>(sGh + (size_t)q * PLANE + (size_t)v * 16) = hi;
-            *reinterpret_cast<uint4 *>(sGl + (size_t)q * PLANE + (size_t)v * 16) = lo;
-        }
-        // ---- stage U (activated, bf16)
-        if (has_gw) {
-            for (int item = tid; item < uq * TV; item += NT) {
-                const int v = item & (TV - 1), q = item >> 7;
-                uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            for (int i = 0; i < GI; ++i) {
+                const int item = tid + i * NT, v = item & (TV - 1), q = item >> 7;
+                uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
                 if (v0 + v < A.vox) {
-                    const size_t gv = (size_t)n * A.vox + v0 + v;
-                    o = *reinterpret_cast<const uint4 *>(A.u + gv * (size_t)A.ldu + q * 8);
-                    if (!u_ident) {
-                        uint32_t w4[4] = {o.x, o.y, o.z, o.w};
+                    float g[8] = {pg0[i].x, pg0[i].y, pg0[i].z, pg0[i].w, pg1[i].x, pg1[i].y, pg1[i].z, pg1[i].w};
+                    if (has_nt) {
+                        const uint32_t tw[4] = {pt[i].x, pt[i].y, pt[i].z, pt[i].w};
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const int k = q * 8 + 2 * j;
-                            const float a0 = lrelu(fmaf(__uint_as_float(w4[j] << 16), s_us[k], s_uh[k]), A.un.slope);
-                            const float a1 = lrelu(fmaf(__uint_as_float(w4[j] & 0xffff0000u), s_us[k + 1], s_uh[k + 1]), A.un.slope);
-                            w4[j] = pack2_bf16(a0, a1);
+                            const int c = q * 8 + 2 * j;
+                            g[2 * j] = fmaf(s_ca[c], g[2 * j], fmaf(s_cb[c], __uint_as_float(tw[j] << 16), s_cd[c]));
+                            g[2 * j + 1] = fmaf(s_ca[c + 1], g[2 * j + 1], fmaf(s_cb[c + 1], __uint_as_float(tw[j] & 0xffff0000u), s_cd[c + 1]));
                         }
-                        o = make_uint4(w4[0], w4[1], w4[2], w4[3]);
                     }
+                    split2(g[0], g[1], hi.x, lo.x); split2(g[2], g[3], hi.y, lo.y);
+                    split2(g[4], g[5], hi.z, lo.z); split2(g[6], g[7], hi.w, lo.w);
                 }
-                *reinterpret_cast<uint4 *>(sU + (size_t)q * PLANE + (size_t)v * 16) = o;
+                *reinterpret_cast<uint4 *>(sGh + (size_t)q * PLANE + (size_t)v * 16) = hi;
+                *reinterpret_cast<uint4 *>(sGl + (size_t)q * PLANE + (size_t)v * 16) = lo;
+            }
+            if (has_gw) {
+#pragma unroll
+                for (int i = 0; i < UI; ++i) {
+                    const int item = tid + i * NT, v = item & (TV - 1), q = item >> 7;
+                    *reinterpret_cast<uint4 *>(sU + (size_t)q * PLANE + (size_t)v * 16) = (v0 + v < A.vox) ? pu[i] : make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+            // ---- issue the loads of this CTA's next tile
+            if (tile + gridDim.x < total_tiles) prefetch(tile + gridDim.x);
+        } else {
+            // ---- stage G (hi / lo): item = (8-channel group q, voxel v), consecutive threads = consecutive voxels
+            for (int item = tid; item < gq * TV; item += NT) {
+                const int v = item & (TV - 1), q = item >> 7;
+                uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+                if (v0 + v < A.vox) {
+                    const size_t gv = (size_t)n * A.vox + v0 + v;
+                    const float4 g0 = *reinterpret_cast<const float4 *>(A.gz + gv * (size_t)A.ldg + q * 8);
+                    const float4 g1 = *reinterpret_cast<const float4 *>(A.gz + gv * (size_t)A.ldg + q * 8 + 4);
+                    float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                    if (has_nt) {
+                        const uint4 tr = *reinterpret_cast<const uint4 *>(A.t + gv * (size_t)A.ldt + q * 8);
+                        const uint32_t tw[4] = {tr.x, tr.y, tr.z, tr.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int c = q * 8 + 2 * j;
+                            g[2 * j] = fmaf(s_ca[c], g[2 * j], fmaf(s_cb[c], __uint_as_float(tw[j] << 16), s_cd[c]));
+                            g[2 * j + 1] = fmaf(s_ca[c + 1], g[2 * j + 1], fmaf(s_cb[c + 1], __uint_as_float(tw[j] & 0xffff0000u), s_cd[c + 1]));
+                        }
+                    }
+                    split2(g[0], g[1], hi.x, lo.x); split2(g[2], g[3], hi.y, lo.y);
+                    split2(g[4], g[5], hi.z, lo.z); split2(g[6], g[7], hi.w, lo.w);
+                }
+                *reinterpret_cast<uint4 *>(sGh + (size_t)q * PLANE + (size_t)v * 16) = hi;
+                *reinterpret_cast<uint4 *>(sGl + (size_t)q * PLANE + (size_t)v * 16) = lo;
+            }
+            // ---- stage U (activated, bf16)
+            if (has_gw) {
+                for (int item = tid; item < uq * TV; item += NT) {
+                    const int v = item & (TV - 1), q = item >> 7;
+                    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                    if (v0 + v < A.vox) {
+                        const size_t gv = (size_t)n * A.vox + v0 + v;
+                        o = *reinterpret_cast<const uint4 *>(A.u + gv * (size_t)A.ldu + q * 8);
+                        if (!u_ident) {
+                            uint32_t w4[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int k = q * 8 + 2 * j;
+                                const float a0 = lrelu(fmaf(__uint_as_float(w4[j] << 16), s_us[k], s_uh[k]), A.un.slope);
+                                const float a1 = lrelu(fmaf(__uint_as_float(w4[j] & 0xffff0000u), s_us[k + 1], s_uh[k + 1]), A.un.slope);
+                                w4[j] = pack2_bf16(a0, a1);
+                            }
+                            o = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                        }
+                    }
+                    *reinterpret_cast<uint4 *>(sU + (size_t)q * PLANE + (size_t)v * 16) = o;
+                }
             }
         }
         tc::fence_async_smem();
@@ -248,12 +309,6 @@ int l3d_pw_bwd_tc(const l3d_act *gz, const l3d_act *t, const l3d_norm *nt, const
     A.w = w; A.g_w = g_w;
     A.g_u = has_gu ? (float *)g_u->ptr : nullptr; A.ldgu = has_gu ? g_u->ldc : 0; A.accumulate = accumulate_gu;
     A.tmem_cols = cols;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(pw_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-        if (e != cudaSuccess) { l3d_set_error("pw_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 3; }
-        attr_set = true;
-    }
     int occ = (int)((227 * 1024) / (smem + 2048));
     if (occ > 4) occ = 4;
     if (occ < 1) occ = 1;
@@ -262,9 +317,37 @@ int l3d_pw_bwd_tc(const l3d_act *gz, const l3d_act *t, const l3d_norm *nt, const
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = ((vox + TV - 1) / TV) * N;
-    long long grid = (long long)sms * occ;
-    if (grid > tiles) grid = tiles;
-    pw_bwd_tc_kernel<<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(A);
+#define L3D_PWTC(GIV, UIV)                                                                                                     \
+    do {                                                                                                                        \
+        static bool attr_set = false;                                                                                           \
+        if (!attr_set) {                                                                                                        \
+            cudaError_t e = cudaFuncSetAttribute(pw_bwd_tc_kernel<GIV, UIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
+            if (e != cudaSuccess) { l3d_set_error("pw_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 3; }    \
+            attr_set = true;                                                                                                    \
+        }                                                                                                                       \
+        static int occ_regs = 0;                                                                                                \
+        if (occ_regs == 0) {                                                                                                    \
+            cudaFuncAttributes fa;                                                                                              \
+            occ_regs = 1;                                                                                                       \
+            if (cudaFuncGetAttributes(&fa, pw_bwd_tc_kernel<GIV, UIV>) == cudaSuccess && fa.numRegs > 0)                        \
+                occ_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * NT);                                                           \
+            if (occ_regs < 1) occ_regs = 1;                                                                                     \
+        }                                                                                                                       \
+        const int occ_k = occ_regs < occ ? occ_regs : occ;                                                                      \
+        long long grid_k = (long long)sms * occ_k;                                                                              \
+        if (grid_k > tiles) grid_k = tiles;                                                                                     \
+        pw_bwd_tc_kernel<GIV, UIV><<<(unsigned)grid_k, NT, smem, (cudaStream_t)stream>>>(A);                                    \
+    } while (0)
+    const int gi = Cg / 16, ui = Cu / 16;            // staging items per thread (TV * C / 8 / NT)
+    if (gi == 1 && ui == 1) L3D_PWTC(1, 1);
+    else if (gi == 1 && ui == 2) L3D_PWTC(1, 2);
+    else if (gi == 2 && ui == 1) L3D_PWTC(2, 1);
+    else if (gi == 2 && ui == 2) L3D_PWTC(2, 2);
+    else if (gi == 2 && ui == 4) L3D_PWTC(2, 4);
+    else if (gi == 4 && ui == 2) L3D_PWTC(4, 2);
+    else if (gi == 4 && ui == 4) L3D_PWTC(4, 4);
+    else L3D_PWTC(0, 0);
+#undef L3D_PWTC
     L3D_CUDA_OK("l3d_pw_bwd (tcgen05) launch");
     return 0;
 }

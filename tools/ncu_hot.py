@@ -12,6 +12,7 @@ body = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
 ci = {h: i for i, h in enumerate(hdr)}
 S = ci["# Samples"]
 stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
+body = [r for r in body if r[S].isdigit()]
 tot = sum(int(r[S] or 0) for r in body)
 print(f"total samples {tot}, instructions {len(body)}")
 agg = {}
