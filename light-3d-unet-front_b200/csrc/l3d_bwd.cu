@@ -1108,6 +1108,9 @@ int l3d_pw_bwd_tc(const l3d_act *gz, const l3d_act *t, const l3d_norm *nt, const
                   const l3d_norm *un, int N, long long vox, const float *w, float *g_w, const l3d_act *g_u,
                   int accumulate_gu, void *stream);
 
+int l3d_convt_bwd_tc(const l3d_act *g_out, int OD, int OH, int OW, int oz, int oy, int ox, const l3d_act *x, int N, int d, int h, int w_,
+                     const float *w, float *g_w, float *g_b, const l3d_act *g_x, int accumulate_gx, void *stream);
+
 extern "C" int l3d_pw_bwd(const l3d_act *gz, const l3d_act *t, const l3d_norm *nt, const double *red,
                           const l3d_act *u, const l3d_norm *un, int N, int D, int H, int W,
                           const float *w, float *g_w, const l3d_act *g_u, int accumulate_gu, void *stream) {
@@ -1162,6 +1165,11 @@ extern "C" int l3d_convt_bwd(const l3d_act *g_out, int OD, int OH, int OW, int o
     A.w = w; A.g_w = g_w; A.g_b = g_b;
     A.g_u = has_gx ? g_x->ptr : nullptr; A.ldgu = has_gx ? g_x->ldc : 0; A.accumulate = accumulate_gx;
     A.d = d; A.h = h; A.w_ = w_; A.OD = OD; A.OH = OH; A.OW = OW; A.oz = oz; A.oy = oy; A.ox = ox;
+    {   // tensor-core path (bf16 storage, 16-aligned channel counts)
+        const int rc_tc = l3d_convt_bwd_tc(g_out, OD, OH, OW, oz, oy, ox, x, N, d, h, w_, w, g_w, g_b, g_x, accumulate_gx, stream);
+        if (rc_tc == 0) { l3d_count_launch(); return 0; }
+        if (rc_tc > 0) return rc_tc;
+    }
     int rc = 0;
     // launch 1: input gradient (all taps) + bias gradient; launch 2: weight gradient, one tap per blockIdx.y with the
     // slice accumulated in registers over all tiles of the CTA (one atomic per output per CTA)

@@ -351,3 +351,238 @@ int l3d_pw_bwd_tc(const l3d_act *gz, const l3d_act *t, const l3d_norm *nt, const
     L3D_CUDA_OK("l3d_pw_bwd (tcgen05) launch");
     return 0;
 }
+
+// =============================================================================================================
+// ConvTranspose3d(k=2, s=2) backward on tensor cores (bf16 storage; unet3d.py:119, 127-141).  The eight taps are
+// eight independent pointwise maps  out[up(v, tap)][co] = sum_ci x[v][ci] * W[ci][co][tap] + b[co],  so per tile of
+// 128 input voxels and per tap:
+//   stage   G_tap[v][co] = g_out[up(v, tap)][co] (zero outside the output volume) as bf16 hi / lo, voxel-planar
+//   dgrad   D1[v][ci]  += G_tap . W_tap            (K-major;  accumulated over the 8 taps, then stored to g_x)
+//   wgrad   D2_tap[co][ci | 1] += G_tap^T . [X | 1] (MN-major; the extra ones-column of the X tile yields the bias
+//                                                   gradient; D2 stays in TMEM over all tiles of the CTA)
+// TMEM holds D1 and TP of the eight D2 accumulators; blockIdx.y selects the group of TP taps whose weight gradient
+// this CTA owns, and only blockIdx.y == 0 computes the input gradient (over all taps).
+namespace {
+
+struct CtTcArgs {
+    const float *g; int ldg; int OD, OH, OW, oz, oy, ox;
+    const bf16 *x; int ldx; int N, d, h, w;
+    int Cin, Cout;
+    const float *wgt; float *g_w; float *g_b;
+    float *g_x; int ldgx; int accumulate;
+    int TP, w_resident, tmem_cols;
+};
+
+__global__ void __launch_bounds__(NT) convt_bwd_tc_kernel(CtTcArgs A) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    const int Cin = A.Cin, Cout = A.Cout, gq = Cout >> 3, xq = (Cin >> 3) + 2, NX = Cin + 16;
+    unsigned char *sGh = smem;                                   // gq planes
+    unsigned char *sGl = sGh + (size_t)gq * PLANE;
+    unsigned char *sX = sGl + (size_t)gq * PLANE;                // xq planes: Cin channels + [1, 0 x 15]
+    unsigned char *sWh = sX + (size_t)xq * PLANE;                // dgrad B operand per tap: [N = Cin][K = Cout] K-major
+    const size_t wtap_bytes = (size_t)Cin * Cout * 2;
+    unsigned char *sWl = sWh + (A.w_resident ? 8 : 1) * wtap_bytes;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int pass = blockIdx.y, TP = A.TP;
+    const bool do_dgrad = pass == 0 && A.g_x != nullptr;
+    const int tap_lo = pass * TP, tap_hi = tap_lo + TP;          // weight-gradient taps of this CTA
+    const int tap_begin = do_dgrad ? 0 : tap_lo, tap_end = do_dgrad ? 8 : tap_hi;
+    if (warp == 0) tc::tmem_alloc(&s_tmem, (uint32_t)A.tmem_cols);
+    if (tid == 32) tc::mbar_init(&s_bar, 1);
+    auto stage_w = [&](int tap, int slot) {                      // wgt[ci][co][tap] -> B[n = ci][k = co]
+        for (int i = tid; i < Cin * Cout; i += NT) {
+            const int co = i % Cout, ci = i / Cout;
+            const float wv = A.wgt[(size_t)i * 8 + tap];
+            const bf16 hi = __float2bfloat16_rn(wv);
+            const uint32_t off = tc::tile_off(ci, co, Cin);
+            *reinterpret_cast<bf16 *>(sWh + slot * wtap_bytes + off) = hi;
+            *reinterpret_cast<bf16 *>(sWl + slot * wtap_bytes + off) = __float2bfloat16_rn(wv - __bfloat162float(hi));
+        }
+    };
+    if (A.w_resident && do_dgrad) for (int tap = 0; tap < 8; ++tap) stage_w(tap, tap);
+    // constant part of the X tile: channel Cin = 1, channels Cin+1 .. Cin+15 = 0
+    for (int i = tid; i < 2 * TV; i += NT) {
+        const int v = i & (TV - 1), q = (Cin >> 3) + (i >> 7);
+        *reinterpret_cast<uint4 *>(sX + (size_t)q * PLANE + (size_t)v * 16) = make_uint4(i < TV ? 0x00003f80u : 0u, 0u, 0u, 0u);
+    }
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = s_tmem;
+    const uint32_t d1 = tmem;                                     // Cin columns
+    const uint32_t d2 = tmem + (uint32_t)Cin;                     // TP accumulators of NX columns
+    const uint32_t id_k = tc::idesc_16b_m128(Cin, 1, 1, false, false), id_mn = tc::idesc_16b_m128(NX, 1, 1, true, true);
+    const uint32_t sGh_u = tc::smem_u32(sGh), sGl_u = tc::smem_u32(sGl), sX_u = tc::smem_u32(sX), sWh_u = tc::smem_u32(sWh), sWl_u = tc::smem_u32(sWl);
+    const long long nvox = (long long)A.N * A.d * A.h * A.w;
+    const long long ntiles = (nvox + TV - 1) / TV;
+    uint32_t phase = 0;
+    bool first = true;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long v0 = tile * TV;
+        // ---- X tile (stored bf16, identity norm): one copy per tile
+        for (int item = tid; item < (Cin >> 3) * TV; item += NT) {
+            const int v = item & (TV - 1), q = item >> 7;
+            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            if (v0 + v < nvox) o = *reinterpret_cast<const uint4 *>(A.x + (size_t)(v0 + v) * A.ldx + q * 8);
+            *reinterpret_cast<uint4 *>(sX + (size_t)q * PLANE + (size_t)v * 16) = o;
+        }
+        for (int tap = tap_begin; tap < tap_end; ++tap) {
+            // ---- G_tap tile: gather from the up-sampled grid
+            for (int item = tid; item < gq * TV; item += NT) {
+                const int v = item & (TV - 1), q = item >> 7;
+                uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+                if (v0 + v < nvox) {
+                    long long rem = v0 + v;
+                    const int ix = (int)(rem % A.w); rem /= A.w;
+                    const int iy = (int)(rem % A.h); rem /= A.h;
+                    const int iz = (int)(rem % A.d);
+                    const int n = (int)(rem / A.d);
+                    const int Z = A.oz + 2 * iz + (tap >> 2), Y = A.oy + 2 * iy + ((tap >> 1) & 1), X = A.ox + 2 * ix + (tap & 1);
+                    if (Z >= 0 && Z < A.OD && Y >= 0 && Y < A.OH && X >= 0 && X < A.OW) {
+                        const float *gp = A.g + ((((size_t)n * A.OD + Z) * A.OH + Y) * A.OW + X) * (size_t)A.ldg + q * 8;
+                        const float4 g0 = *reinterpret_cast<const float4 *>(gp), g1 = *reinterpret_cast<const float4 *>(gp + 4);
+                        split2(g0.x, g0.y, hi.x, lo.x); split2(g0.z, g0.w, hi.y, lo.y);
+                        split2(g1.x, g1.y, hi.z, lo.z); split2(g1.z, g1.w, hi.w, lo.w);
+                    }
+                }
+                *reinterpret_cast<uint4 *>(sGh + (size_t)q * PLANE + (size_t)v * 16) = hi;
+                *reinterpret_cast<uint4 *>(sGl + (size_t)q * PLANE + (size_t)v * 16) = lo;
+            }
+            if (!A.w_resident && do_dgrad) stage_w(tap, 0);
+            tc::fence_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                tc::fence_after_sync();
+                if (do_dgrad) {
+                    const uint32_t wslot = (uint32_t)((A.w_resident ? tap : 0) * wtap_bytes);
+                    for (int j = 0; j < Cout / 16; ++j) {
+                        const uint64_t agh = tc::smem_desc(sGh_u + 2 * j * PLANE, PLANE, 128), agl = tc::smem_desc(sGl_u + 2 * j * PLANE, PLANE, 128);
+                        const uint64_t bwh = tc::smem_desc(sWh_u + wslot + 2 * j * Cin * 16, Cin * 16, 128);
+                        const uint64_t bwl = tc::smem_desc(sWl_u + wslot + 2 * j * Cin * 16, Cin * 16, 128);
+                        tc::mma_f16(d1, agh, bwh, id_k, (tap > 0 || j > 0) ? 1u : 0u);
+                        tc::mma_f16(d1, agl, bwh, id_k, 1u);
+                        tc::mma_f16(d1, agh, bwl, id_k, 1u);
+                    }
+                }
+                if (tap >= tap_lo && tap < tap_hi) {
+                    const uint32_t dacc = d2 + (uint32_t)((tap - tap_lo) * NX);
+                    for (int j = 0; j < TV / 16; ++j) {
+                        const uint64_t bx = tc::smem_desc(sX_u + j * 256, 128, PLANE);
+                        tc::mma_f16(dacc, tc::smem_desc(sGh_u + j * 256, 128, PLANE), bx, id_mn, (first && j == 0) ? 0u : 1u);
+                        tc::mma_f16(dacc, tc::smem_desc(sGl_u + j * 256, 128, PLANE), bx, id_mn, 1u);
+                    }
+                }
+                tc::mma_commit(&s_bar);
+            }
+            tc::mbar_wait(&s_bar, phase);          // G tile (and the per-tap weights) free again
+            phase ^= 1u;
+            tc::fence_after_sync();
+        }
+        first = false;
+        // ---- epilogue: D1 -> g_x (fp32)
+        if (do_dgrad) {
+            const int v = (warp & 3) * 32 + lane;
+            const bool ok = v0 + v < nvox;
+            float *op = A.g_x + (size_t)(v0 + (ok ? v : 0)) * A.ldgx;
+            const uint32_t trow = d1 + ((uint32_t)((warp & 3) * 32) << 16);
+            for (int cb = (warp >> 2) * 16; cb < Cin; cb += 32) {
+                float r[16];
+                tc::tmem_ld16(trow + (uint32_t)cb, r);
+                if (ok) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        float4 o = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                        if (A.accumulate) { const float4 pz = *reinterpret_cast<const float4 *>(op + cb + j); o.x += pz.x; o.y += pz.y; o.z += pz.z; o.w += pz.w; }
+                        *reinterpret_cast<float4 *>(op + cb + j) = o;
+                    }
+                }
+            }
+        }
+        tc::fence_before_sync();
+        __syncthreads();
+    }
+    // ---- flush: D2_tap[co][ci] -> g_w[ci][co][tap], D2_tap[co][Cin] -> g_b[co]
+    if (!first) {
+        tc::fence_after_sync();
+        const int co = (warp & 3) * 32 + lane;
+        if ((warp & 3) * 32 < Cout) {
+            for (int tl = 0; tl < TP; ++tl) {
+                const int tap = tap_lo + tl;
+                const uint32_t trow = d2 + (uint32_t)(tl * NX) + ((uint32_t)((warp & 3) * 32) << 16);
+                for (int cb = (warp >> 2) * 16; cb < NX; cb += 32) {
+                    float r[16];
+                    tc::tmem_ld16(trow + (uint32_t)cb, r);
+                    if (co < Cout) {
+                        if (cb < Cin) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) atomicAdd(&A.g_w[((size_t)(cb + j) * Cout + co) * 8 + tap], r[j]);
+                        } else if (A.g_b != nullptr) {
+                            atomicAdd(&A.g_b[co], r[0]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)A.tmem_cols);
+}
+
+}  // namespace
+
+// Returns -1 when the tensor-core path does not apply.
+int l3d_convt_bwd_tc(const l3d_act *g_out, int OD, int OH, int OW, int oz, int oy, int ox, const l3d_act *x, int N, int d, int h, int w_,
+                     const float *w, float *g_w, float *g_b, const l3d_act *g_x, int accumulate_gx, void *stream) {
+    { const char *e = getenv("L3D_NO_TC_BWD"); if (e && e[0] == '1') return -1; }
+    const int Cin = x->C, Cout = g_out->C;
+    const bool has_gx = !act_null(g_x);
+    if (x->dtype != L3D_BF16 || g_out->dtype != L3D_F32 || g_w == nullptr) return -1;
+    if (Cin % 16 != 0 || Cout % 16 != 0 || Cin > 128 || Cout > 128) return -1;
+    auto al = [](const l3d_act *a, int elems, int bytes) { return a->ldc % elems == 0 && reinterpret_cast<uintptr_t>(a->ptr) % bytes == 0; };
+    if (!al(g_out, 4, 16) || !al(x, 8, 16) || (has_gx && !al(g_x, 4, 16))) return -1;
+    const int NX = Cin + 16;
+    int TP = 8;
+    while (TP > 1 && TP * NX + Cin > 512) TP >>= 1;
+    if (TP * NX + Cin > 512) return -1;
+    const size_t wtap = (size_t)Cin * Cout * 2;
+    const size_t base = (size_t)(2 * (Cout / 8) + Cin / 8 + 2) * PLANE;
+    int w_resident = base + 16 * wtap <= 160 * 1024 ? 1 : 0;
+    size_t smem = base + (w_resident ? 16 : 2) * wtap;
+    const size_t span = (size_t)(Cout / 8) * PLANE + 16 * (size_t)PLANE + 256;     // MN-major A over-read (128 rows)
+    if (smem < span) smem = span;
+    if (smem > 226 * 1024) return -1;
+    int cols = 32;
+    while (cols < TP * NX + Cin) cols <<= 1;
+    CtTcArgs A;
+    A.g = (const float *)g_out->ptr; A.ldg = g_out->ldc; A.OD = OD; A.OH = OH; A.OW = OW; A.oz = oz; A.oy = oy; A.ox = ox;
+    A.x = (const bf16 *)x->ptr; A.ldx = x->ldc; A.N = N; A.d = d; A.h = h; A.w = w_;
+    A.Cin = Cin; A.Cout = Cout; A.wgt = w; A.g_w = g_w; A.g_b = g_b;
+    A.g_x = has_gx ? (float *)g_x->ptr : nullptr; A.ldgx = has_gx ? g_x->ldc : 0; A.accumulate = accumulate_gx;
+    A.TP = TP; A.w_resident = w_resident; A.tmem_cols = cols;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(convt_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        if (e != cudaSuccess) { l3d_set_error("convt_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 3; }
+        attr_set = true;
+    }
+    int occ = (int)((227 * 1024) / (smem + 2048));
+    if (occ > 3) occ = 3;
+    if (occ < 1) occ = 1;
+    if (occ * cols > 512) occ = 512 / cols;
+    if (occ < 1) occ = 1;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int npass = 8 / TP;
+    const long long tiles = ((long long)N * d * h * w_ + TV - 1) / TV;
+    long long gx = ((long long)sms * occ + npass - 1) / npass;
+    if (gx > tiles) gx = tiles;
+    if (gx < 1) gx = 1;
+    convt_bwd_tc_kernel<<<dim3((unsigned)gx, (unsigned)npass), NT, smem, (cudaStream_t)stream>>>(A);
+    L3D_CUDA_OK("l3d_convt_bwd (tcgen05) launch");
+    return 0;
+}

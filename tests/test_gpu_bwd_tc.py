@@ -98,3 +98,52 @@ def test_pw_bwd_tensor_core(Cg, Cu, has_nt, u_norm, accumulate):
     # hi/lo bf16 operand pairs: ~2^-16 per product; the fp32 CUDA-core kernel is the yardstick
     assert e["gu_tc"] < 2e-4 and e["gw_tc"] < 2e-4, e
     assert e["gu_cc"] < 2e-4 and e["gw_cc"] < 2e-4, e
+
+
+@pytest.mark.parametrize("Cin,Cout", [(32, 16), (64, 32), (128, 64), (16, 16)])
+@pytest.mark.parametrize("lo,out_dims,accumulate", [((5, 6, 7), (10, 12, 14), False), ((3, 4, 5), (7, 9, 10), True)])
+def test_convt_bwd_tensor_core(Cin, Cout, lo, out_dims, accumulate):
+    """ConvTranspose3d(k=2, s=2) backward: input, weight and bias gradients against torch autograd in float64, for the
+    tensor-core kernel and the CUDA-core kernel it replaces; g_out is the lower channel half of a concat-buffer gradient
+    and the output volume may be larger than 2x the input (centre-pad path, unet3d.py:130-138)."""
+    from light_unet import _native as nv
+    N = 2
+    g = torch.Generator().manual_seed(Cin * 7 + Cout + lo[0])
+    x = torch.randn(N, *lo, Cin, generator=g).to(torch.bfloat16)
+    w = (torch.randn(Cin, Cout, 2, 2, 2, generator=g) / np.sqrt(Cin)).float()
+    gcat = (torch.randn(N, *out_dims, 2 * Cout, generator=g) * 1e-3).float()
+    off = [(out_dims[k] - 2 * lo[k]) // 2 for k in range(3)]
+    # float64 reference through autograd on the un-padded up-sampled region
+    xd = x.double().permute(0, 4, 1, 2, 3).requires_grad_(True)
+    wd = w.double().requires_grad_(True)
+    bd = torch.zeros(Cout, dtype=torch.float64, requires_grad=True)
+    y = F.conv_transpose3d(xd, wd, bd, stride=2)
+    gsub = gcat[:, off[0]:off[0] + 2 * lo[0], off[1]:off[1] + 2 * lo[1], off[2]:off[2] + 2 * lo[2], :Cout].double().permute(0, 4, 1, 2, 3)
+    y.backward(gsub)
+    ref_gx = xd.grad.permute(0, 2, 3, 4, 1)
+    res = {}
+    for name, env in (("tc", {}), ("cc", {"L3D_NO_TC_BWD": "1"})):
+        xdv, wdv, gd = x.to(DEV), w.to(DEV), gcat.to(DEV)
+        torch.manual_seed(5)
+        gw0 = torch.randn_like(wdv) * 1e-2
+        gb0 = torch.randn(Cout, device=DEV) * 1e-2
+        gx0 = torch.randn(N, *lo, Cin, device=DEV) * 1e-3
+        g_w, g_b, g_x = gw0.clone(), gb0.clone(), gx0.clone()
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            nv.call("l3d_convt_bwd", nv.act(gd, 0, Cout), out_dims[0], out_dims[1], out_dims[2], off[0], off[1], off[2], nv.act(xdv), N,
+                    lo[0], lo[1], lo[2], nv.ptr(wdv), nv.ptr(g_w), nv.ptr(g_b), nv.act(g_x), 1 if accumulate else 0,
+                    nv.stream_ptr(torch.device(DEV)))
+            torch.cuda.synchronize()
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        res[name] = (_rel((g_x - (gx0 if accumulate else 0)).double().cpu(), ref_gx), _rel((g_w - gw0).double().cpu(), wd.grad),
+                     _rel((g_b - gb0).double().cpu(), bd.grad))
+    print(Cin, Cout, lo, out_dims, {k: tuple(f"{e:.1e}" for e in v) for k, v in res.items()})
+    for v in res.values():
+        assert max(v) < 2e-4, res
