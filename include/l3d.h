@@ -154,6 +154,9 @@ int l3d_convt_bwd(const l3d_act *g_out, int OD, int OH, int OW, int oz, int oy, 
 /* InstanceNorm affine gradients from the reductions: g_gamma[c] += sum_n red[1][n][c],
  * g_beta[c] += sum_n red[0][n][c]. */
 int l3d_norm_param_grad(const double *red, int N, int C, float *g_gamma, float *g_beta, void *stream);
+/* The same for `count` norms in one launch; red / C / g_gamma / g_beta are HOST arrays of `count` device pointers / sizes. */
+int l3d_norm_param_grad_batch(int count, const double *const *red, const int *C, float *const *g_gamma,
+                              float *const *g_beta, int N, void *stream);
 
 /* ------------------------------------------------------------------- loss -- */
 

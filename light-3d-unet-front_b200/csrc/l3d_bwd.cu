@@ -834,6 +834,23 @@ __global__ void norm_param_grad_kernel(const double *__restrict__ red, int N, in
     g_gamma[c] += (float)sg;
 }
 
+// all InstanceNorm affine gradients of one backward pass in a single launch: blockIdx.x = norm
+constexpr int NPG_MAX = 32;
+struct NormGradBatch {
+    const double *red[NPG_MAX];
+    float *g_gamma[NPG_MAX], *g_beta[NPG_MAX];
+    int C[NPG_MAX];
+};
+__global__ void norm_param_grad_batch_kernel(NormGradBatch B, int N) {
+    const int i = blockIdx.x, C = B.C[i];
+    const double *red = B.red[i];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double sb = 0.0, sg = 0.0;
+        for (int n = 0; n < N; ++n) { sb += red[(size_t)n * C + c]; sg += red[(size_t)N * C + (size_t)n * C + c]; }
+        B.g_beta[i][c] += (float)sb;
+        B.g_gamma[i][c] += (float)sg;
+    }
+}
 
 // ===========================================================================================
 // Dense / grouped 3x3x3 backward (generic CUDA-core path).
@@ -1222,6 +1239,23 @@ extern "C" int l3d_norm_param_grad(const double *red, int N, int C, float *g_gam
     norm_param_grad_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(red, N, C, g_gamma, g_beta);
     l3d_count_launch();
     L3D_CUDA_OK("l3d_norm_param_grad launch");
+    return 0;
+}
+
+extern "C" int l3d_norm_param_grad_batch(int count, const double *const *red, const int *C, float *const *g_gamma,
+                                         float *const *g_beta, int N, void *stream) {
+    L3D_REQUIRE(count >= 0 && red && C && g_gamma && g_beta && N > 0, "l3d_norm_param_grad_batch: bad argument");
+    for (int i0 = 0; i0 < count; i0 += NPG_MAX) {
+        NormGradBatch B;
+        const int nb = count - i0 < NPG_MAX ? count - i0 : NPG_MAX;
+        for (int i = 0; i < nb; ++i) {
+            L3D_REQUIRE(red[i0 + i] && g_gamma[i0 + i] && g_beta[i0 + i] && C[i0 + i] > 0, "l3d_norm_param_grad_batch: null entry %d", i0 + i);
+            B.red[i] = red[i0 + i]; B.g_gamma[i] = g_gamma[i0 + i]; B.g_beta[i] = g_beta[i0 + i]; B.C[i] = C[i0 + i];
+        }
+        norm_param_grad_batch_kernel<<<nb, 128, 0, (cudaStream_t)stream>>>(B, N);
+        l3d_count_launch();
+    }
+    L3D_CUDA_OK("l3d_norm_param_grad_batch launch");
     return 0;
 }
 

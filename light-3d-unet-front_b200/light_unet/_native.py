@@ -55,6 +55,7 @@ _SIGS = {
     "l3d_convt_bwd": [POINTER(Act), c_int, c_int, c_int, c_int, c_int, c_int, POINTER(Act), c_int, c_int, c_int, c_int,
                       _P, _P, _P, POINTER(Act), c_int, _P],
     "l3d_norm_param_grad": [_P, c_int, c_int, _P, _P, _P],
+    "l3d_norm_param_grad_batch": [c_int, _P, _P, _P, _P, c_int, _P],
     "l3d_ftl_sums": [_P, _P, c_int64, _P, _P],
     "l3d_ftl_finish": [_P, c_float, c_float, c_float, c_float, _P, _P, _P],
     "l3d_ftl_grad": [_P, c_int64, _P, _P, _P, _P],

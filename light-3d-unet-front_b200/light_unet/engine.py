@@ -16,6 +16,7 @@ HBM layout (per workspace, i.e. per (N, D, H, W, dtype, training) key):
 """
 from __future__ import annotations
 
+import ctypes
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -294,6 +295,7 @@ class UNetPlan:
         ident = nv.norm()
         masks = ws.masks
         nblk = len(self.blocks)
+        norm_jobs = []
         for i in range(nblk - 1, -1, -1):
             b = self.blocks[i]
             nv.TIMER.tag = b.name
@@ -352,14 +354,11 @@ class UNetPlan:
             n1b = nv.norm(s1, P[f"{b.prefix}.norm1.weight"], P[f"{b.prefix}.norm1.bias"], None, IN_EPS, 1.0, vox)
             self._conv_bwd(P, G, b, 1, ws, gy, buf["t1"], n1b, r1, x_act, ident, buf.get("u1"), g_in, 1, None,
                            N, dims, st)
-            # ---- 4. InstanceNorm affine gradients
-            nv.call("l3d_norm_param_grad", nv.ptr(r1), N, b.cout, nv.ptr(G[f"{b.prefix}.norm1.weight"]),
-                    nv.ptr(G[f"{b.prefix}.norm1.bias"]), st)
-            nv.call("l3d_norm_param_grad", nv.ptr(r2), N, b.cout, nv.ptr(G[f"{b.prefix}.norm2.weight"]),
-                    nv.ptr(G[f"{b.prefix}.norm2.bias"]), st)
+            # ---- 4. InstanceNorm affine gradients: collected, one launch after the last block
+            norm_jobs.append((r1, b.cout, G[f"{b.prefix}.norm1.weight"], G[f"{b.prefix}.norm1.bias"]))
+            norm_jobs.append((r2, b.cout, G[f"{b.prefix}.norm2.weight"], G[f"{b.prefix}.norm2.bias"]))
             if has_sc:
-                nv.call("l3d_norm_param_grad", nv.ptr(rr), N, b.cout, nv.ptr(G[f"{b.prefix}.shortcut.1.weight"]),
-                        nv.ptr(G[f"{b.prefix}.shortcut.1.bias"]), st)
+                norm_jobs.append((rr, b.cout, G[f"{b.prefix}.shortcut.1.weight"], G[f"{b.prefix}.shortcut.1.bias"]))
             # ---- 5. transposed conv backward: lower half of g_cat -> gradient of the previous block's output
             if b.name.startswith("up"):
                 prev = self.blocks[i - 1]
@@ -369,4 +368,8 @@ class UNetPlan:
                         off[0], off[1], off[2], nv.act(ws.blocks[prev.name]["out"]), N, lo[0], lo[1], lo[2],
                         nv.ptr(P[f"{b.name}.up.weight"]), nv.ptr(G[f"{b.name}.up.weight"]), nv.ptr(G[f"{b.name}.up.bias"]),
                         nv.act(ws.g_out[prev.name]), 0, st)
+        nv.TIMER.tag = "norms"
+        cnt = len(norm_jobs)
+        ptrs = lambda k: (ctypes.c_void_p * cnt)(*[j[k].data_ptr() for j in norm_jobs])
+        nv.call("l3d_norm_param_grad_batch", cnt, ptrs(0), (ctypes.c_int * cnt)(*[j[1] for j in norm_jobs]), ptrs(2), ptrs(3), N, st)
         return G

@@ -21,7 +21,9 @@ import torch
 
 from . import _native as nv
 
-WINDOW_BATCH = 65          # windows per forward launch sequence (325 windows of a 128x128x320 volume = 5 batches)
+WINDOW_BATCH = 325         # windows per forward launch sequence: the whole 128x128x320 volume (325 windows, ~20 GB of bf16
+                           # workspace out of 180 GB) in one batch -- measured 14.1 ms vs 15.7 ms at 65 per batch
+_BYTES_PER_WINDOW = 70e6   # workspace estimate per 48^3 window (bf16), used to cap the batch by the free HBM
 _GAUSS_CACHE = {}
 
 
@@ -90,6 +92,10 @@ def sliding_window_device(volume: torch.Tensor, model, patch_size=(48, 48, 48), 
         raise ValueError("Expected 3D model output, got a multi-channel prediction")     # utils.py:122-123
     preds = torch.empty(nwin, 1, pd, ph, pw, dtype=torch.float32, device=dev)
     wb = int(window_batch or WINDOW_BATCH)
+    if window_batch is None:
+        free_b, _ = torch.cuda.mem_get_info(dev)
+        scale = (pd * ph * pw) / 48.0 ** 3 * (2.0 if getattr(model, "compute_dtype", torch.bfloat16) == torch.float32 else 1.0)
+        wb = max(1, min(wb, int(0.5 * free_b / (_BYTES_PER_WINDOW * scale))))
     model.eval()                                     # utils.py:84 (the reference leaves the model in eval mode)
     if native:
         P = dict(model.named_parameters())

@@ -51,7 +51,7 @@ def main():
             return
         # sliding window on the C3 volume
         vol = torch.rand(128, 128, 320, device="cuda")
-        for wb in (8, 16, 32, 65):
+        for wb in (32, 65, 109, 163, 325):
             lu.WINDOW_BATCH = wb
             for _ in range(2):
                 sliding_window_device(vol, m, (48, 48, 48), 0.5, True, threshold=0.3)
