@@ -913,7 +913,12 @@ extern "C" int l3d_merge_fwd(const l3d_act *t2, const l3d_norm *n2, const l3d_ac
             L3D_REQUIRE(vec_ok(t2) && vec_ok(r) && (!has_out || vec_ok(out)), "l3d_merge_fwd: views must be 16-byte aligned with C a multiple of %d", V);
         }
         const size_t nvox = (size_t)D * H * W;
-        const unsigned gx = (unsigned)((nvox + 255) / 256);
+        // a few CTAs per sample, each striding over many voxels: the per-CTA prologue (norm tables in double precision,
+        // head weights) would otherwise cost more than the 256 voxels a one-shot CTA handles
+        size_t gx_ = (nvox + 255) / 256;
+        const size_t cap_ = (148 * 16 + (size_t)N - 1) / (size_t)N;
+        if (gx_ > cap_) gx_ = cap_;
+        const unsigned gx = (unsigned)gx_;
         dim3 grid(gx, (unsigned)N);
         L3D_DISPATCH_DTYPE(t2->dtype, T, {
             if (C <= 16)
