@@ -337,10 +337,20 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
                             sv[2 * j] += r0; sv[2 * j + 1] += r1;
                             sv[16 + 2 * j] = fmaf(r0, r0, sv[16 + 2 * j]); sv[16 + 2 * j + 1] = fmaf(r1, r1, sv[16 + 2 * j + 1]);
                         }
-                        if (valid) {
-                            bf16 *outp = outb + (vox0 + (size_t)p * zstride) * (size_t)ldo + cb;
-                            *reinterpret_cast<uint4 *>(outp) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                            *reinterpret_cast<uint4 *>(outp + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        {
+                            // lanes 2j / 2j+1 hold x-adjacent voxels: swap halves so that each store instruction fills whole
+                            // 32-byte sectors (even lane: channels 0-7, odd lane: channels 8-15 of the same voxel)
+                            const bool odd = (lane & 1) != 0;
+                            const uint4 h0 = make_uint4(pk[0], pk[1], pk[2], pk[3]), h1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                            const uint4 snd = odd ? h0 : h1;
+                            uint4 rcv;
+                            rcv.x = __shfl_xor_sync(0xffffffffu, snd.x, 1); rcv.y = __shfl_xor_sync(0xffffffffu, snd.y, 1);
+                            rcv.z = __shfl_xor_sync(0xffffffffu, snd.z, 1); rcv.w = __shfl_xor_sync(0xffffffffu, snd.w, 1);
+                            const bool pvalid = __shfl_xor_sync(0xffffffffu, valid ? 1 : 0, 1) != 0;
+                            bf16 *own = outb + (vox0 + (size_t)p * zstride) * (size_t)ldo + cb + (odd ? 8 : 0);
+                            bf16 *pe = odd ? own - ldo : own, *po = odd ? own : own + ldo;      // even / odd voxel of the pair
+                            if (odd ? pvalid : valid) *reinterpret_cast<uint4 *>(pe) = odd ? rcv : h0;
+                            if (odd ? valid : pvalid) *reinterpret_cast<uint4 *>(po) = odd ? h1 : rcv;
                         }
                     }
                     warp_transpose_sum<32>(sv, lane);
@@ -526,7 +536,6 @@ int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int 
         for (int c = 4; c >= 1; --c) if (c3_smem_bytes(tz, Cin, Cout, has_sc, c) <= 226 * 1024) { nr = c; break; }
         if (force_nraw) nr = force_nraw;
         if (c3_smem_bytes(tz, Cin, Cout, has_sc, nr) > 226 * 1024) continue;
-        if (nr < 2 && tz > 2 && !force_tz && !force_nraw) continue;     // a shorter tile with >= 2 boxes in flight beats a taller one with 1
         // prefer a shorter tile with double-buffered accumulators over a taller single-buffered one
         if (ns == 1 && tz > 2 && !force_tz && !force_sets) {
             const int cols_half = (tz / 2) * Cout * nacc;

@@ -799,9 +799,10 @@ extern "C" int l3d_dwpw_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, 
     const bool has_u = !act_null(u);
     if (has_u) L3D_REQUIRE(u->C == Cin && u->dtype == x->dtype, "l3d_dwpw_fwd: bad u view");
     // inference, narrow layers: depthwise o pointwise composed into one implicit GEMM (27x the pointwise MACs on the
-    // tensor pipe; measured faster than or equal to the CUDA-core stencil + GEMM kernel wherever its weights fit shared memory)
+    // tensor pipe; measured 2.2x faster than the CUDA-core stencil + GEMM kernel at 16/32 channels, on par at 32 -> 32 and
+    // slower once the 27 weight tiles (27*Cin*Cout*2 B) crowd the operand buffers out of shared memory: Cin*Cout <= 1024)
     const char *igemm_max_env = getenv("L3D_DWS_IGEMM_MAX");
-    const int igemm_max = (igemm_max_env && igemm_max_env[0]) ? atoi(igemm_max_env) : 2048;
+    const int igemm_max = (igemm_max_env && igemm_max_env[0]) ? atoi(igemm_max_env) : 1024;
     if (dw_w != nullptr && !has_u && Cin * Cout <= igemm_max) {
         const int rc = l3d_conv3_tc(x, xn, N, D, H, W, nullptr, 1, dw_w, pw_w, sc_w, t, t_stats, r, r_stats, stream);
         if (rc >= 0) return rc;
