@@ -95,21 +95,38 @@ __device__ __forceinline__ void uf_union(int32_t *parent, int32_t a, int32_t b) 
     }
 }
 
-__global__ void __launch_bounds__(256) ccl_init_kernel(const int32_t *__restrict__ mask, int32_t n, int32_t *__restrict__ parent,
+// Initial forest: every foreground voxel points at the first voxel of its x-run inside the warp's 32-voxel segment
+// (runs break at row starts), found with one ballot -- a row of foreground costs no union at all.
+__global__ void __launch_bounds__(256) ccl_init_kernel(const int32_t *__restrict__ mask, int32_t n, int W, int32_t *__restrict__ parent,
                                                        int32_t *__restrict__ size) {
-    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        parent[i] = mask[i] != 0 ? i : -1;
-        size[i] = 0;
+    const int32_t n_round = (n + 31) & ~31;
+    const int lane = threadIdx.x & 31;
+    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        const bool fg = i < n && mask[i] != 0;
+        const unsigned fgm = __ballot_sync(0xffffffffu, fg);
+        const unsigned rowstart = __ballot_sync(0xffffffffu, i < n && (i % W) == 0);
+        const unsigned starts = fgm & (~(fgm << 1) | rowstart | 1u);
+        if (i < n) {
+            int32_t p = -1;
+            if (fg) p = i - (lane - (31 - __clz(starts & (0xffffffffu >> (31 - lane)))));
+            parent[i] = p;
+            size[i] = 0;
+        }
     }
 }
+// Unions only where two runs meet for the first time: across a segment boundary in x, and for the y / z neighbour
+// only at the first voxel of an overlap (if the previous voxel in x and its y / z neighbour are both foreground, that
+// voxel has already joined the same two runs).
 __global__ void __launch_bounds__(256) ccl_merge_kernel(int32_t *__restrict__ parent, int D, int H, int W) {
     const int32_t n = D * H * W;
+    const int32_t WH = W * H;
     for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         if (parent[i] < 0) continue;
-        const int x = i % W, y = (i / W) % H, z = i / (W * H);
-        if (x > 0 && parent[i - 1] >= 0) uf_union(parent, i, i - 1);
-        if (y > 0 && parent[i - W] >= 0) uf_union(parent, i, i - W);
-        if (z > 0 && parent[i - W * H] >= 0) uf_union(parent, i, i - W * H);
+        const int x = i % W, y = (i / W) % H, z = i / WH;
+        const bool left = x > 0 && parent[i - 1] >= 0;
+        if (left && (i & 31) == 0) uf_union(parent, i, i - 1);
+        if (y > 0 && parent[i - W] >= 0 && !(left && parent[i - W - 1] >= 0)) uf_union(parent, i, i - W);
+        if (z > 0 && parent[i - WH] >= 0 && !(left && parent[i - WH - 1] >= 0)) uf_union(parent, i, i - WH);
     }
 }
 __global__ void __launch_bounds__(256) ccl_flatten_count_kernel(int32_t *__restrict__ parent, int32_t n, int32_t *__restrict__ size) {
@@ -222,7 +239,24 @@ constexpr int BB_RUN = 8;
 struct BoxAcc {
     int32_t l, z0, z1, y0, y1, x0, x1, cnt, pb;
 };
-__device__ __forceinline__ void box_flush_warp(const BoxAcc &a, int32_t *__restrict__ table, int cap) {
+// A CTA keeps a small direct-mapped cache of label -> box accumulators in shared memory: a warp merges its lanes per
+// label (match.any + redux), then folds the result into the cache slot of that label; a slot holding another label is
+// first written back to the global table.  A component of millions of voxels therefore costs a handful of global
+// atomics per CTA instead of one set per warp run.
+constexpr int BB_SLOTS = 64;
+struct BoxCache {
+    int32_t key[BB_SLOTS];
+    int32_t v[BB_SLOTS][8];
+};
+__device__ __forceinline__ void box_writeback(const int32_t *v, int32_t key, int32_t *__restrict__ table) {
+    int32_t *t = table + (size_t)(key - 1) * 8;
+    atomicMin(&t[0], v[0]); atomicMax(&t[1], v[1]);
+    atomicMin(&t[2], v[2]); atomicMax(&t[3], v[3]);
+    atomicMin(&t[4], v[4]); atomicMax(&t[5], v[5]);
+    atomicAdd(&t[6], v[6]);
+    atomicMax(&t[7], v[7]);
+}
+__device__ __forceinline__ void box_flush_warp(const BoxAcc &a, int32_t *__restrict__ table, int cap, BoxCache *cache) {
     const int32_t key = (a.l > 0 && a.l <= cap) ? a.l : 0;
     const unsigned peers = __match_any_sync(0xffffffffu, key);
     const int z0 = __reduce_min_sync(peers, a.z0), z1 = __reduce_max_sync(peers, a.z1);
@@ -230,20 +264,43 @@ __device__ __forceinline__ void box_flush_warp(const BoxAcc &a, int32_t *__restr
     const int x0 = __reduce_min_sync(peers, a.x0), x1 = __reduce_max_sync(peers, a.x1);
     const int cnt = __reduce_add_sync(peers, a.cnt), pb = __reduce_max_sync(peers, a.pb);
     if (key > 0 && (threadIdx.x & 31) == __ffs(peers) - 1) {
-        int32_t *t = table + (size_t)(key - 1) * 8;
-        atomicMin(&t[0], z0); atomicMax(&t[1], z1);
-        atomicMin(&t[2], y0); atomicMax(&t[3], y1);
-        atomicMin(&t[4], x0); atomicMax(&t[5], x1);
-        atomicAdd(&t[6], cnt);
-        atomicMax(&t[7], pb);
+        const int slot = key & (BB_SLOTS - 1);
+        // claim the slot for `key` (0 = empty); another warp may hold it for a different label
+        while (true) {
+            const int32_t cur = atomicCAS(&cache->key[slot], 0, key);
+            if (cur == 0 || cur == key) {
+                int32_t *v = cache->v[slot];
+                atomicMin(&v[0], z0); atomicMax(&v[1], z1);
+                atomicMin(&v[2], y0); atomicMax(&v[3], y1);
+                atomicMin(&v[4], x0); atomicMax(&v[5], x1);
+                atomicAdd(&v[6], cnt);
+                atomicMax(&v[7], pb);
+                break;
+            }
+            // occupied by another label: bypass the cache for this update (rare: labels colliding modulo BB_SLOTS inside one CTA)
+            const int32_t tmp[8] = {z0, z1, y0, y1, x0, x1, cnt, pb};
+            box_writeback(tmp, key, table);
+            break;
+        }
     }
 }
 __global__ void __launch_bounds__(256) bbox_reduce_kernel(const int32_t *__restrict__ labels, const float *__restrict__ prob,
                                                           int D, int H, int W, int32_t *__restrict__ table, int cap) {
+    __shared__ BoxCache cache;
+    for (int i = threadIdx.x; i < BB_SLOTS; i += blockDim.x) {
+        cache.key[i] = 0;
+        cache.v[i][0] = cache.v[i][2] = cache.v[i][4] = 0x7fffffff;
+        cache.v[i][1] = cache.v[i][3] = cache.v[i][5] = -1;
+        cache.v[i][6] = 0; cache.v[i][7] = 0;
+    }
+    __syncthreads();
     const int64_t n = (int64_t)D * H * W;
     const int64_t nruns = (n + BB_RUN - 1) / BB_RUN;
     const int64_t nruns_round = (nruns + 31) & ~(int64_t)31;
-    for (int64_t run = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; run < nruns_round; run += (int64_t)gridDim.x * blockDim.x) {
+    // contiguous range of runs per CTA: its voxels mostly share a few labels, which the cache then absorbs
+    const int64_t per_cta = ((nruns_round / 32 + gridDim.x - 1) / gridDim.x) * 32;
+    const int64_t run_begin = (int64_t)blockIdx.x * per_cta, run_end = min(nruns_round, run_begin + per_cta);
+    for (int64_t run = run_begin + threadIdx.x; run < run_end; run += blockDim.x) {
         BoxAcc a;
         a.l = 0; a.z0 = a.y0 = a.x0 = 0x7fffffff; a.z1 = a.y1 = a.x1 = -1; a.cnt = 0; a.pb = 0;
         const int64_t i0 = run * BB_RUN;
@@ -254,7 +311,7 @@ __global__ void __launch_bounds__(256) bbox_reduce_kernel(const int32_t *__restr
             if (__any_sync(0xffffffffu, change)) {
                 BoxAcc f = a;
                 if (!change) { f.l = 0; }
-                box_flush_warp(f, table, cap);
+                box_flush_warp(f, table, cap, &cache);
                 if (change) { a.z0 = a.y0 = a.x0 = 0x7fffffff; a.z1 = a.y1 = a.x1 = -1; a.cnt = 0; a.pb = 0; }
             }
             a.l = l;
@@ -268,8 +325,11 @@ __global__ void __launch_bounds__(256) bbox_reduce_kernel(const int32_t *__restr
             }
         }
         if (a.cnt == 0) a.l = 0;
-        box_flush_warp(a, table, cap);
+        box_flush_warp(a, table, cap, &cache);
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < BB_SLOTS; i += blockDim.x)
+        if (cache.key[i] > 0 && cache.v[i][6] > 0) box_writeback(cache.v[i], cache.key[i], table);
 }
 
 static unsigned grid_for(int64_t n, int threads, int cap_blocks) {
@@ -332,7 +392,7 @@ extern "C" int l3d_ccl_label(const int32_t *mask, int D, int H, int W, int min_s
     int32_t *parent = work, *size = work + n64, *flag = work + 2 * n64, *bsum = work + 3 * n64;
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned g = grid_for(n, 256, 148 * 32);
-    ccl_init_kernel<<<g, 256, 0, st>>>(mask, n, parent, size);
+    ccl_init_kernel<<<g, 256, 0, st>>>(mask, n, W, parent, size);
     ccl_merge_kernel<<<g, 256, 0, st>>>(parent, D, H, W);
     ccl_flatten_count_kernel<<<g, 256, 0, st>>>(parent, n, size);
     // metrics.py:52-58 drops components with size < min_size only when min_size > 0; with min_size <= 0 every

@@ -25,6 +25,8 @@ WINDOW_BATCH = 325         # windows per forward launch sequence: the whole 128x
                            # workspace out of 180 GB) in one batch -- measured 14.1 ms vs 15.7 ms at 65 per batch
 _BYTES_PER_WINDOW = 70e6   # workspace estimate per 48^3 window (bf16), used to cap the batch by the free HBM
 _GAUSS_CACHE = {}
+_BATCH_CAP = {}
+_POS_CACHE = {}
 
 
 def _axis_positions(dim: int, patch: int, overlap: float) -> List[int]:
@@ -78,12 +80,17 @@ def sliding_window_device(volume: torch.Tensor, model, patch_size=(48, 48, 48), 
     D, H, W = volume.shape
     pd, ph, pw = (int(p) for p in patch_size)
     zpos, ypos, xpos = window_positions((D, H, W), (pd, ph, pw), overlap)
-    pos = torch.tensor([(z, y, x) for z in zpos for y in ypos for x in xpos], dtype=torch.int32)
-    nwin = pos.shape[0]
-    pos_d = pos.to(dev, non_blocking=True)
-    zp = torch.tensor(zpos, dtype=torch.int32).to(dev, non_blocking=True)
-    yp = torch.tensor(ypos, dtype=torch.int32).to(dev, non_blocking=True)
-    xp = torch.tensor(xpos, dtype=torch.int32).to(dev, non_blocking=True)
+    pkey = (str(dev), D, H, W, pd, ph, pw, float(overlap))
+    cached = _POS_CACHE.get(pkey)
+    if cached is None:          # window grid of this volume shape: built and uploaded once
+        pos = torch.tensor([(z, y, x) for z in zpos for y in ypos for x in xpos], dtype=torch.int32)
+        cached = (pos.to(dev), torch.tensor(zpos, dtype=torch.int32).to(dev), torch.tensor(ypos, dtype=torch.int32).to(dev),
+                  torch.tensor(xpos, dtype=torch.int32).to(dev))
+        if len(_POS_CACHE) > 16:
+            _POS_CACHE.clear()
+        _POS_CACHE[pkey] = cached
+    pos_d, zp, yp, xp = cached
+    nwin = pos_d.shape[0]
     imp = _importance_on_device((pd, ph, pw), use_gaussian, dev)
     st = nv.stream_ptr(dev)
     vol = volume.contiguous()
@@ -93,9 +100,15 @@ def sliding_window_device(volume: torch.Tensor, model, patch_size=(48, 48, 48), 
     preds = torch.empty(nwin, 1, pd, ph, pw, dtype=torch.float32, device=dev)
     wb = int(window_batch or WINDOW_BATCH)
     if window_batch is None:
-        free_b, _ = torch.cuda.mem_get_info(dev)
-        scale = (pd * ph * pw) / 48.0 ** 3 * (2.0 if getattr(model, "compute_dtype", torch.bfloat16) == torch.float32 else 1.0)
-        wb = max(1, min(wb, int(0.5 * free_b / (_BYTES_PER_WINDOW * scale))))
+        f32 = getattr(model, "compute_dtype", torch.bfloat16) == torch.float32
+        key = (str(dev), pd, ph, pw, f32, wb)
+        cap = _BATCH_CAP.get(key)
+        if cap is None:         # cudaMemGetInfo is a slow call: decided once per configuration (the workspace is cached after that)
+            free_b, _ = torch.cuda.mem_get_info(dev)
+            scale = (pd * ph * pw) / 48.0 ** 3 * (2.0 if f32 else 1.0)
+            cap = max(1, min(wb, int(0.5 * free_b / (_BYTES_PER_WINDOW * scale))))
+            _BATCH_CAP[key] = cap
+        wb = cap
     model.eval()                                     # utils.py:84 (the reference leaves the model in eval mode)
     if native:
         P = dict(model.named_parameters())

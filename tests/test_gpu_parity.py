@@ -146,7 +146,8 @@ def test_connected_components_bit_exact():
     rng = np.random.default_rng(0)
     for shape, dens, min_size in [((9, 10, 11), 0.5, 0), ((17, 5, 23), 0.35, 3), ((1, 1, 7), 0.6, 0), ((4, 4, 4), 1.0, 8),
                                   ((6, 6, 6), 0.0, 0), ((20, 21, 22), 0.45, 5), ((64, 64, 64), 0.3, 8),
-                                  ((40, 130, 70), 0.55, 20), ((128, 128, 320), 0.25, 8)]:
+                                  ((40, 130, 70), 0.55, 20), ((128, 128, 320), 0.25, 8), ((48, 50, 77), 0.93, 4),
+                                  ((33, 64, 96), 1.0, 0)]:
         m = (rng.random(shape) < dens).astype(np.int32)
         want, n_want = bbox_ref.connected_components(m.copy(), min_size)
         got, n_got = get_connected_components(m, min_size=min_size)
