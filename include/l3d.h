@@ -211,9 +211,8 @@ int l3d_bbox_reduce(const int32_t *labels, const float *prob, int D, int H, int 
  * and fp32 accumulation in TMEM.  A, Wt, D are fp32 device arrays. */
 int l3d_tc_selftest(const float *A, const float *Wt, int MT, int K, int N, float *D, void *stream);
 
-/* Self-test of the kind::tf32 forms used by the tensor-core pointwise backward.  mode 0: D[128][N] = G[128][K] . WU[N][K]^T
- * (K-major operands); mode 1: D[m][n] = sum_v G[v][m] * WU[v][n] over 128 voxels (MN-major operands, rows >= M of D are
- * don't-care).  fp32 device arrays; operands are rounded to tf32 by the tensor core. */
+/* Self-test of kind::tf32 with K-major operands: D[128][N] = G[128][K] . WU[N][K]^T (mode must be 0, M is ignored).  fp32
+ * device arrays; operands are rounded to tf32 by the tensor core. */
 int l3d_tc_selftest_tf32(const float *G, const float *WU, int mode, int M, int K, int N, float *D, void *stream);
 
 /* Self-test of the 16-bit MN-major voxel reduction used by the tensor-core weight gradients:

@@ -66,10 +66,8 @@ extern "C" int l3d_tc_selftest(const float *A, const float *Wt, int MT, int K, i
     return 0;
 }
 
-// ---- kind::tf32 self-test, the two GEMM forms of the tensor-core pointwise backward --------------------------------
-//   mode 0 (dgrad form): D[128][N]  = G[128][K] . W[N][K]^T     A, B K-major:  G planar [K/4][128][4], W planar [K/4][N][4]
-//   mode 1 (wgrad form): D[128][N]  = sum_v G[v][m] * U[v][n], v < 128 (m < M <= 128; rows >= M are don't-care)
-//                        A, B MN-major over the voxel-planar tiles G [M/4][128][4], U [N/4][128][4]
+// ---- kind::tf32 self-test: D[128][N] = G[128][K] . W[N][K]^T, K-major operands in the planar layout [K/4][rows][4].
+// (MN-major tf32 operands return zeros on this part; the voxel reductions of the backward kernels use bf16, below.)
 namespace {
 __global__ void __launch_bounds__(128) tc_selftest_tf32_kernel(const float *__restrict__ G, const float *__restrict__ WU, int mode, int M,
                                                                int K, int N, float *__restrict__ D) {
@@ -83,33 +81,19 @@ __global__ void __launch_bounds__(128) tc_selftest_tf32_kernel(const float *__re
     if (tid == 32) tc::mbar_init(&s_bar, 1);
     unsigned char *sA = smem;                       // up to 64 KB: 128-row planes
     unsigned char *sB = smem + 64 * 1024;
-    if (mode == 0) {
-        for (int i = tid; i < 128 * K; i += 128) { const int k = i % K, r = i / K; *reinterpret_cast<float *>(sA + tc::tile_off32(r, k, 128)) = G[i]; }
-        for (int i = tid; i < N * K; i += 128) { const int k = i % K, n = i / K; *reinterpret_cast<float *>(sB + tc::tile_off32(n, k, N)) = WU[i]; }
-    } else {
-        for (int i = tid; i < 128 * M; i += 128) { const int m = i % M, v = i / M; *reinterpret_cast<float *>(sA + tc::tile_off32(v, m, 128)) = G[i]; }
-        for (int i = tid; i < 128 * N; i += 128) { const int n = i % N, v = i / N; *reinterpret_cast<float *>(sB + tc::tile_off32(v, n, 128)) = WU[i]; }
-    }
+    for (int i = tid; i < 128 * K; i += 128) { const int k = i % K, r = i / K; *reinterpret_cast<float *>(sA + tc::tile_off32(r, k, 128)) = G[i]; }
+    for (int i = tid; i < N * K; i += 128) { const int k = i % K, n = i / K; *reinterpret_cast<float *>(sB + tc::tile_off32(n, k, N)) = WU[i]; }
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = s_tmem;
     if (tid == 0) {
-        if (mode == 0) {
+        {
             const uint32_t idesc = tc::idesc_tf32_m128(N, false, false);
             for (int j = 0; j < K / 8; ++j) {
                 const uint64_t ad = tc::smem_desc(tc::smem_u32(sA) + 2 * j * 128 * 16, 128 * 16, 128);
                 const uint64_t bd = tc::smem_desc(tc::smem_u32(sB) + 2 * j * N * 16, N * 16, 128);
-                tc::mma_tf32(tmem, ad, bd, idesc, j > 0);
-            }
-        } else {
-            // probing variants (mode >> 4): bit0 swap LBO/SBO of A, bit1 swap of B, bit2 A K-major, bit3 B K-major
-            const int var = K;
-            const uint32_t idesc = tc::idesc_tf32_m128(N, !(var & 4), !(var & 8));
-            for (int j = 0; j < 128 / 8; ++j) {      // 8 voxels per MMA
-                const uint64_t ad = (var & 1) ? tc::smem_desc(tc::smem_u32(sA) + j * 128, 128 * 16, 128) : tc::smem_desc(tc::smem_u32(sA) + j * 128, 128, 128 * 16);
-                const uint64_t bd = (var & 2) ? tc::smem_desc(tc::smem_u32(sB) + j * 128, 128 * 16, 128) : tc::smem_desc(tc::smem_u32(sB) + j * 128, 128, 128 * 16);
                 tc::mma_tf32(tmem, ad, bd, idesc, j > 0);
             }
         }
@@ -130,9 +114,8 @@ __global__ void __launch_bounds__(128) tc_selftest_tf32_kernel(const float *__re
 }  // namespace
 
 extern "C" int l3d_tc_selftest_tf32(const float *G, const float *WU, int mode, int M, int K, int N, float *D, void *stream) {
-    L3D_REQUIRE(G && WU && D && (mode == 0 || mode == 1) && N % 16 == 0 && N >= 16 && N <= 256, "l3d_tc_selftest_tf32: bad shape");
-    if (mode == 0) L3D_REQUIRE(K % 8 == 0 && K >= 8 && K <= 128, "l3d_tc_selftest_tf32: bad K");
-    else L3D_REQUIRE(M % 4 == 0 && M >= 4 && M <= 128, "l3d_tc_selftest_tf32: bad M");
+    L3D_REQUIRE(G && WU && D && mode == 0 && N % 16 == 0 && N >= 16 && N <= 256 && K % 8 == 0 && K >= 8 && K <= 128, "l3d_tc_selftest_tf32: bad shape");
+    (void)M;
     const size_t smem = 192 * 1024;
     cudaFuncSetAttribute(tc_selftest_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     tc_selftest_tf32_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(G, WU, mode, M, K, N, D);

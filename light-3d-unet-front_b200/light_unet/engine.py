@@ -289,7 +289,12 @@ class UNetPlan:
         N = ws.N
         dev = ws.device
         st = nv.stream_ptr(dev)
-        G = {k: torch.zeros_like(v, dtype=torch.float32) for k, v in P.items()}
+        # one flat fp32 buffer (a single fill launch) viewed per parameter; autograd takes the views as .grad
+        flat = torch.zeros(sum(v.numel() for v in P.values()), dtype=torch.float32, device=dev)
+        G, off = {}, 0
+        for k, v in P.items():
+            G[k] = flat[off:off + v.numel()].view(v.shape)
+            off += v.numel()
         ws.red.zero_()
         g_prob = g_prob.to(torch.float32).contiguous()
         ident = nv.norm()

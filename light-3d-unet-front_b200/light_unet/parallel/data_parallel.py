@@ -69,7 +69,27 @@ class DataParallelStep:
                 p.copy_(flat[off:off + p.numel()].view_as(p))
                 off += p.numel()
 
+    def _shared_flat_grad(self) -> Optional[torch.Tensor]:
+        """The engine hands out every gradient as a view of one flat fp32 buffer, in parameter order: when that is what
+        .grad holds, the bucket IS that buffer (no gather / scatter copies around the all-reduce)."""
+        g0 = self.params[0].grad
+        if g0 is None or g0.dtype != torch.float32:
+            return None
+        base, off = g0.untyped_storage().data_ptr(), g0.storage_offset()
+        for p in self.params:
+            g = p.grad
+            if (g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.untyped_storage().data_ptr() != base
+                    or g.storage_offset() != off):
+                return None
+            off += g.numel()
+        total = off - g0.storage_offset()
+        return torch.empty(0, dtype=torch.float32, device=g0.device).set_(g0.untyped_storage(), g0.storage_offset(), (total,), (1,))
+
     def reduce_gradients(self) -> None:
+        shared = self._shared_flat_grad()
+        if shared is not None:
+            dist.all_reduce(shared, op=dist.ReduceOp.SUM, group=self.group)
+            return
         flat = flatten_grads(self.params)
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
         unflatten_into_grads(flat, self.params)
@@ -78,7 +98,7 @@ class DataParallelStep:
         images = images.float()                                    # trainer.py:225
         outputs = self.model(images)                               # trainer.py:227
         loss = self.loss_fn(outputs, labels)                       # trainer.py:228
-        self.optimizer.zero_grad(set_to_none=False)                # trainer.py:230
+        self.optimizer.zero_grad()                                 # trainer.py:230 (torch default: set_to_none=True)
         loss.backward()                                            # trainer.py:231
         if self.world_size > 1:
             self.reduce_gradients()

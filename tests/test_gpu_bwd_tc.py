@@ -147,3 +147,53 @@ def test_convt_bwd_tensor_core(Cin, Cout, lo, out_dims, accumulate):
     print(Cin, Cout, lo, out_dims, {k: tuple(f"{e:.1e}" for e in v) for k, v in res.items()})
     for v in res.values():
         assert max(v) < 2e-4, res
+
+
+@pytest.mark.parametrize("C,dims", [(16, (9, 11, 13)), (32, (8, 16, 8)), (64, (5, 6, 7))])
+@pytest.mark.parametrize("has_norm,accumulate", [(True, False), (True, True), (False, False)])
+def test_dw_bwd_layer(C, dims, has_norm, accumulate):
+    """Depthwise 3x3x3 backward through the C-ABI (input gradient through Dropout3d / LeakyReLU / the producer's
+    InstanceNorm prologue, depthwise weight gradient, norm reductions) against a float64 torch restatement."""
+    from light_unet import _native as nv
+    N = 2
+    D, H, W = dims
+    vox = D * H * W
+    g = torch.Generator().manual_seed(C + D)
+    gu = (torch.randn(N, D, H, W, C, generator=g) * 1e-3).float()
+    x = torch.randn(N, D, H, W, C, generator=g).to(torch.bfloat16)
+    dw = (torch.randn(C, 27, generator=g) / 5).float()
+    gam, bet = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.2
+    drop = (torch.rand(N, C, generator=g) > 0.2).float() / 0.8
+    xd = x.double()
+    stats = torch.stack([xd.sum(dim=(1, 2, 3)), (xd * xd).sum(dim=(1, 2, 3))])
+    mean = stats[0] / vox
+    rstd = 1.0 / torch.sqrt(stats[1] / vox - mean * mean + EPS)
+    xhat = (xd - mean[:, None, None, None, :]) * rstd[:, None, None, None, :]
+    if has_norm:
+        pre = xhat * gam.double() + bet.double()
+        a = F.leaky_relu(pre, SLOPE) * drop.double()[:, None, None, None, :]
+        dact = torch.where(pre > 0, 1.0, SLOPE) * drop.double()[:, None, None, None, :]
+    else:
+        a, dact = xd, torch.ones_like(xd)
+    a_n = a.permute(0, 4, 1, 2, 3).clone().requires_grad_(True)
+    wd = dw.double().view(C, 1, 3, 3, 3).clone().requires_grad_(True)
+    u = F.conv3d(a_n, wd, padding=1, groups=C)
+    u.backward(gu.double().permute(0, 4, 1, 2, 3))
+    ref_gy = a_n.grad.permute(0, 2, 3, 4, 1) * dact
+    ref_gdw = wd.grad.view(C, 27)
+    ref_red = torch.stack([ref_gy.sum(dim=(1, 2, 3)), (ref_gy * xhat).sum(dim=(1, 2, 3))])
+    dev = lambda t: t.to(DEV).contiguous()
+    gud, xdv, dwd, st, gd, bd, dd = dev(gu), dev(x), dev(dw), dev(stats), dev(gam), dev(bet), dev(drop)
+    xn = nv.norm(st, gd, bd, dd, EPS, SLOPE, vox) if has_norm else nv.norm()
+    torch.manual_seed(9)
+    gy0 = torch.randn(N, D, H, W, C, device=DEV) * 1e-3
+    gdw0 = torch.randn(C, 27, device=DEV) * 1e-2
+    gy, gdw = gy0.clone(), gdw0.clone()
+    red = torch.zeros(2, N, C, dtype=torch.float64, device=DEV)
+    nv.call("l3d_dw_bwd", nv.act(gud), nv.act(xdv), xn, N, D, H, W, nv.ptr(dwd), nv.ptr(gdw), nv.act(gy), 1 if accumulate else 0,
+            nv.ptr(red) if has_norm else None, nv.stream_ptr(torch.device(DEV)))
+    torch.cuda.synchronize()
+    got_gy = (gy - (gy0 if accumulate else 0)).double().cpu()
+    assert _rel(got_gy, ref_gy) < 1e-5 and _rel((gdw - gdw0).double().cpu(), ref_gdw) < 1e-5
+    if has_norm:
+        assert _rel(red.cpu(), ref_red) < 1e-5

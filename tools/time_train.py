@@ -15,7 +15,7 @@ loss_fn = FocalTverskyLoss()
 x = torch.rand(B, 1, 48, 48, 48, device="cuda")
 t = (torch.rand_like(x) > 0.98).float()
 def step():
-    opt.zero_grad(set_to_none=False)
+    opt.zero_grad()
     loss = loss_fn(m(x), t)
     loss.backward()
     opt.step()
