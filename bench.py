@@ -60,6 +60,16 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback"}
 
 
+def measured_traffic(kernel: str):
+    """DRAM bytes per launch of the dominant entry point (dram__bytes_read.sum + dram__bytes_write.sum) from the committed
+    ncu capture of this workload (profiles/traffic.json, measured offline: numbers taken under a profiler are never timed)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return int(json.load(f)[kernel]["bytes_per_launch"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -224,7 +234,7 @@ def bench_ours(args):
     achieved = top[1][2] / (top[1][1] * 1e-3) / 1e9 if top[1][1] > 0 else 0.0
     step_ms = ms / args.steps
     roofline = {"bound": "hbm", "kernel": top[0], "achieved": round(achieved, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": None, "peak_source": pk["source"],
+                "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": measured_traffic(top[0]), "peak_source": pk["source"],
                 "launches_per_step": top[1][0], "avg_launch_us": round(1e3 * top[1][1] / top[1][0], 1),
                 "share_of_step": round(top[1][1] / tot_ms, 3),
                 "algorithmic_bytes_per_launch": int(top[1][2] / top[1][0]),
