@@ -51,6 +51,7 @@ struct C3Args {
     int Cout;
     bf16 *t; int ldt; double *t_stats;
     bf16 *r; int ldr; double *r_stats;
+    int stat_ld;             // channels per (n) row of the statistics arrays (>= Cout: the launch may own a channel slice)
     int tmem_cols, nraw, nsets, merge, merged_cx, dbg;
 };
 
@@ -291,10 +292,10 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
             if (n < 0) return;
             for (int i = tid; i < 2 * Cout; i += NW) {
                 const int isq = i >= Cout, cc = isq ? i - Cout : i;
-                atomicAdd(&A.t_stats[(size_t)isq * A.N * Cout + (size_t)n * Cout + cc], (double)s_stat[i]);
+                atomicAdd(&A.t_stats[(size_t)isq * A.N * A.stat_ld + (size_t)n * A.stat_ld + cc], (double)s_stat[i]);
                 s_stat[i] = 0.f;
                 if (has_sc) {
-                    atomicAdd(&A.r_stats[(size_t)isq * A.N * Cout + (size_t)n * Cout + cc], (double)s_stat[2 * Cout + i]);
+                    atomicAdd(&A.r_stats[(size_t)isq * A.N * A.stat_ld + (size_t)n * A.stat_ld + cc], (double)s_stat[2 * Cout + i]);
                     s_stat[2 * Cout + i] = 0.f;
                 }
             }
@@ -506,7 +507,7 @@ extern "C" int l3d_conv3_debug_read(long long *host, int n) {
 // does not apply (the caller falls back to another kernel).
 int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int W,
                  const float *w, int groups, const float *dw_w, const float *pw_w, const float *sc_w,
-                 const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats, void *stream) {
+                 const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats, int stat_ld, void *stream) {
     static int disabled = -1;
     if (disabled < 0) { const char *e = getenv("L3D_NO_IGEMM"); disabled = (e && e[0] == '1') ? 1 : 0; }
     if (disabled) return -1;
@@ -579,6 +580,7 @@ int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int 
     A.w = w; A.groups = w != nullptr ? groups : 1; A.dw_w = dw_w; A.pw_w = pw_w; A.sc_w = sc_w; A.Cout = Cout;
     A.t = (bf16 *)t->ptr; A.ldt = t->ldc; A.t_stats = t_stats;
     A.r = has_sc ? (bf16 *)r->ptr : nullptr; A.ldr = has_sc ? r->ldc : 0; A.r_stats = r_stats;
+    A.stat_ld = stat_ld > 0 ? stat_ld : Cout;
     A.tmem_cols = cols; A.nraw = nraw; A.nsets = nsets; A.merged_cx = merged_cx ? 1 : 0; A.dbg = env_int("L3D_C3_DEBUG_SKIP", 0);
     A.merge = (3 * Cout <= 256 && env_int("L3D_C3_NOMERGE", 0) == 0) ? 1 : 0;
     int occ = (int)((227 * 1024) / (smem + 2048));

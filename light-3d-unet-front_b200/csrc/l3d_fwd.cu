@@ -777,7 +777,7 @@ int l3d_dwpw_fwd_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
 
 int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int W,
                  const float *w, int groups, const float *dw_w, const float *pw_w, const float *sc_w,
-                 const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats, void *stream);
+                 const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats, int stat_ld, void *stream);
 int l3d_convt_fwd_tc(const l3d_act *x, int N, int d, int h, int w_, const float *w, const float *b,
                      const l3d_act *out, int OD, int OH, int OW, int oz, int oy, int ox, void *stream);
 
@@ -804,7 +804,22 @@ extern "C" int l3d_dwpw_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, 
     const char *igemm_max_env = getenv("L3D_DWS_IGEMM_MAX");
     const int igemm_max = (igemm_max_env && igemm_max_env[0]) ? atoi(igemm_max_env) : 1024;
     if (dw_w != nullptr && !has_u && Cin * Cout <= igemm_max) {
-        const int rc = l3d_conv3_tc(x, xn, N, D, H, W, nullptr, 1, dw_w, pw_w, sc_w, t, t_stats, r, r_stats, stream);
+        const int rc = l3d_conv3_tc(x, xn, N, D, H, W, nullptr, 1, dw_w, pw_w, sc_w, t, t_stats, r, r_stats, Cout, stream);
+        if (rc >= 0) return rc;
+    }
+    // one size up (64 -> 32 at 24^3): two launches over output-channel halves, each with weights that fit next to the
+    // operand buffers -- measured faster than the stencil kernel although the input is read twice
+    if (dw_w != nullptr && !has_u && Cin * Cout <= 2 * igemm_max && Cout % 32 == 0 && D >= 16 && H >= 16 && x->dtype == L3D_BF16) {
+        const int Ch = Cout / 2;
+        int rc = 0;
+        for (int half = 0; half < 2 && rc == 0; ++half) {
+            l3d_act th = *t, rh;
+            th.ptr = (char *)t->ptr + (size_t)half * Ch * 2; th.C = Ch;
+            if (has_r) { rh = *r; rh.ptr = (char *)r->ptr + (size_t)half * Ch * 2; rh.C = Ch; }
+            rc = l3d_conv3_tc(x, xn, N, D, H, W, nullptr, 1, dw_w, pw_w + (size_t)half * Ch * Cin, has_r ? sc_w + (size_t)half * Ch * Cin : nullptr,
+                              &th, t_stats + half * Ch, has_r ? &rh : nullptr, has_r ? r_stats + half * Ch : nullptr, Cout, stream);
+            if (rc < 0 && half == 1) { l3d_set_error("l3d_dwpw_fwd: implicit GEMM accepted one channel half but not the other"); return 3; }
+        }
         if (rc >= 0) return rc;
     }
     {
@@ -862,7 +877,7 @@ extern "C" int l3d_conv3_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D,
     L3D_REQUIRE(Cout % 8 == 0 && vec4_ok(t), "l3d_conv3_fwd: Cout=%d must be a multiple of 8 and aligned", Cout);
     L3D_REQUIRE(t->dtype == x->dtype, "l3d_conv3_fwd: dtype mismatch");
     {
-        const int rc = l3d_conv3_tc(x, xn, N, D, H, W, w, groups, nullptr, nullptr, nullptr, t, t_stats, nullptr, nullptr, stream);
+        const int rc = l3d_conv3_tc(x, xn, N, D, H, W, w, groups, nullptr, nullptr, nullptr, t, t_stats, nullptr, nullptr, Cout, stream);
         if (rc >= 0) return rc;
     }
     const int CC = (Cout % 32 == 0) ? 32 : (Cout % 16 == 0) ? 16 : 8;

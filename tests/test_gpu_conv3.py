@@ -37,7 +37,7 @@ def _inputs(N, dims, Cin, seed):
     return x, stats, gamma, beta, a, vox
 
 
-def _run(case, env):
+def _run(case, env, launches=1):
     from light_unet import _native as nv
     kind, N, dims, Cin, Cout, groups, use_norm = case
     D, H, W = dims
@@ -78,7 +78,7 @@ def _run(case, env):
             ref_t = F.conv3d(F.conv3d(a_ncdhw, dw, padding=1, groups=Cin), pw)
             ref_r = F.conv3d(a_ncdhw, sc)
         torch.cuda.synchronize()
-        assert nv.launch_count() - before == 1
+        assert nv.launch_count() - before == launches
     finally:
         for k, v in old.items():
             if v is None:
@@ -126,3 +126,10 @@ def test_conv3_tc_tile_heights(case, tz):
 def test_conv3_tc_pipeline_variants(knobs):
     for case in (CASES[0], CASES[5], CASES[6]):
         _run(case, dict(knobs, L3D_DWS_IGEMM_MAX=1 << 20))
+
+
+def test_conv3_tc_output_channel_halves():
+    """64 -> 32 (+ shortcut) at >= 16^3: two implicit-GEMM launches over output-channel halves (default dispatch), each
+    writing its channel slice of t / r and of the statistics rows."""
+    _run(("dws", 2, (16, 17, 24), 64, 32, 1, True), {}, launches=2)
+    _run(("dws", 1, (24, 24, 24), 64, 32, 1, False), {}, launches=2)
