@@ -586,14 +586,20 @@ __global__ void __launch_bounds__(NT) dw_bwd_kernel(
             s_red[i] = 0.f;
         }
     };
-    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    // work item = (tile, 16-channel chunk): the deep layers have few tiles and many chunks, so the chunks of one tile
+    // spread over the CTAs instead of running back to back in one
+    const int nchunks = (C + CK - 1) / CK;
+    const long long total_items = total_tiles * nchunks;
+    for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const long long tile = item / nchunks;
+        const int c0 = (int)(item - tile * nchunks) * CK;
         const int n = (int)(tile / tiles_per_sample);
         int b = (int)(tile % tiles_per_sample);
         const int x0 = (b % tilesX) * TX; b /= tilesX;
         const int y0 = (b % tilesY) * TY; b /= tilesY;
         const int z0 = b * TZ;
         __syncthreads();
-        flush_red(cur_n);      // per tile: keeps the fp32 shared-memory partial sums short (double beyond this point)
+        flush_red(cur_n);      // per item: keeps the fp32 shared-memory partial sums short (double beyond this point)
         if (n != cur_n) {
             cur_n = n;
             for (int cc = tid; cc < C; cc += NT) {
@@ -604,8 +610,7 @@ __global__ void __launch_bounds__(NT) dw_bwd_kernel(
             }
             __syncthreads();
         }
-        for (int c0 = 0; c0 < C; c0 += CK) {
-            if (c0 > 0) __syncthreads();
+        {
             // stage halo tiles of g_u and of the activated input a: (voxel, 4-channel quad) items, 4 in flight per thread
             {
                 const bool vec = (C % 4 == 0) && (ldx % 4 == 0) && (ldgu % 4 == 0);
@@ -819,6 +824,50 @@ __global__ void __launch_bounds__(NT) dw_bwd_kernel(
             if (vv != 0.f) atomicAdd(&g_dw[i], vv);
         }
     }
+}
+
+// Single-channel depthwise backward without an input gradient (the network's first conv, unet3d.py:168,209: the
+// image needs no gradient): only g_dw[27] = sum_v g_u[v] * a[v + tap].  The generic kernel would run a 16-channel
+// chunk with one live lane in sixteen; here one thread owns one voxel.
+template <typename T>
+__global__ void __launch_bounds__(256) dw_bwd_c1_wgrad_kernel(const float *__restrict__ g_u, int ldgu, const T *__restrict__ x, int ldx,
+                                                              NormDev xn, int N, int D, int H, int W, float *__restrict__ g_dw) {
+    __shared__ float s_acc[27];
+    if (threadIdx.x < 27) s_acc[threadIdx.x] = 0.f;
+    __syncthreads();
+    const size_t vox_per = (size_t)D * H * W, total = vox_per * N;
+    float acc[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) acc[k] = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const float g = g_u[i * (size_t)ldgu];
+        const int n = (int)(i / vox_per);
+        size_t rem = i - (size_t)n * vox_per;
+        const int xx = (int)(rem % W); rem /= W;
+        const int yy = (int)(rem % H);
+        const int zz = (int)(rem / H);
+        float sc, sh;
+        norm_scale_shift(xn, N, 1, n, 0, sc, sh);
+#pragma unroll
+        for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const int z = zz + dz - 1, y = yy + dy - 1, xq = xx + dx - 1;
+                    if (z >= 0 && z < D && y >= 0 && y < H && xq >= 0 && xq < W) {
+                        const float a = lrelu(ld1(x + ((((size_t)n * D + z) * H + y) * W + xq) * (size_t)ldx) * sc + sh, xn.slope);
+                        acc[dz * 9 + dy * 3 + dx] = fmaf(g, a, acc[dz * 9 + dy * 3 + dx]);
+                    }
+                }
+    }
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+        const float v = warp_sum(acc[k]);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[k], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 27) atomicAdd(&g_dw[threadIdx.x], s_acc[threadIdx.x]);
 }
 
 static size_t dw_bwd_smem(int C) {
@@ -1217,9 +1266,20 @@ extern "C" int l3d_dw_bwd(const l3d_act *g_u, const l3d_act *x, const l3d_norm *
     if (has_gy) L3D_REQUIRE(gy->C == C && gy->dtype == L3D_F32 && (C % 4 != 0 || vec4_ok(gy)), "l3d_dw_bwd: bad gy view");
     const bool has_norm = xn != nullptr && xn->stats != nullptr;
     if (has_norm && has_gy) L3D_REQUIRE(redx != nullptr, "l3d_dw_bwd: normalised producer needs redx");
+    if (C == 1 && !has_gy && g_dw_w != nullptr) {
+        const NormDev nd1 = norm_dev(xn);
+        const long long nv1 = (long long)N * D * H * W;
+        const unsigned grid1 = (unsigned)(nv1 / 256 + 1 < 148 * 8 ? nv1 / 256 + 1 : 148 * 8);
+        L3D_DISPATCH_DTYPE(x->dtype, T, {
+            dw_bwd_c1_wgrad_kernel<T><<<grid1, 256, 0, (cudaStream_t)stream>>>((const float *)g_u->ptr, g_u->ldc, (const T *)x->ptr, x->ldc, nd1, N, D, H, W, g_dw_w);
+        });
+        l3d_count_launch();
+        L3D_CUDA_OK("l3d_dw_bwd (single channel) launch");
+        return 0;
+    }
     const size_t smem = dw_bwd_smem(C);
     L3D_REQUIRE(smem <= 227 * 1024, "l3d_dw_bwd: C=%d needs %zu B shared memory", C, smem);
-    const long long tiles = (long long)N * ((D + TZ - 1) / TZ) * ((H + TY - 1) / TY) * ((W + TX - 1) / TX);
+    const long long tiles = (long long)N * ((D + TZ - 1) / TZ) * ((H + TY - 1) / TY) * ((W + TX - 1) / TX) * ((C + CK - 1) / CK);
     long long grid = tiles < 148 * 2 ? tiles : 148 * 2;
     const NormDev nd = norm_dev(xn);
     cudaStream_t st = (cudaStream_t)stream;
