@@ -540,6 +540,49 @@ __global__ void __launch_bounds__(NT) pw_bwd_kernel(PwBwdArgs A) {
     }
 }
 
+// Pointwise backward with a single input channel and no input gradient (the first conv and its shortcut,
+// unet3d.py:168,209): g_w[c] = sum_v g_t[v][c] * u[v] is a plain reduction; one thread owns one voxel.
+template <typename T, int CG>
+__global__ void __launch_bounds__(256) pw_bwd_cu1_kernel(const float *__restrict__ gz, int ldg, const T *__restrict__ t, int ldt, NormDev nt,
+                                                         const double *__restrict__ red, const T *__restrict__ u, int ldu, NormDev un,
+                                                         int N, long long vox, float *__restrict__ g_w) {
+    __shared__ float s_acc[CG];
+    __shared__ float s_ca[CG], s_cb[CG], s_cd[CG];
+    const int n = blockIdx.y;
+    if (threadIdx.x < CG) {
+        s_acc[threadIdx.x] = 0.f;
+        float a, b, d;
+        in_bwd_coef(nt, red, N, CG, n, threadIdx.x, a, b, d);
+        s_ca[threadIdx.x] = a; s_cb[threadIdx.x] = b; s_cd[threadIdx.x] = d;
+    }
+    __syncthreads();
+    float usc, ush;
+    norm_scale_shift(un, N, 1, n, 0, usc, ush);
+    const bool has_nt = nt.stats != nullptr;
+    float acc[CG];
+#pragma unroll
+    for (int c = 0; c < CG; ++c) acc[c] = 0.f;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < vox; v += (long long)gridDim.x * blockDim.x) {
+        const size_t gv = (size_t)n * vox + v;
+        const float uv = lrelu(ld1(u + gv * (size_t)ldu) * usc + ush, un.slope);
+#pragma unroll
+        for (int c4 = 0; c4 < CG; c4 += 4) {
+            float g4[4], t4[4] = {0.f, 0.f, 0.f, 0.f};
+            ld4a(gz + gv * (size_t)ldg + c4, g4);
+            if (has_nt) ld4a(t + gv * (size_t)ldt + c4, t4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[c4 + j] = fmaf(fmaf(s_ca[c4 + j], g4[j], fmaf(s_cb[c4 + j], t4[j], s_cd[c4 + j])), uv, acc[c4 + j]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CG; ++c) {
+        const float s = warp_sum(acc[c]);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[c], s);
+    }
+    __syncthreads();
+    if (threadIdx.x < CG) atomicAdd(&g_w[threadIdx.x], s_acc[threadIdx.x]);
+}
+
 static size_t pw_bwd_smem(int Cg, int Cu) {
     size_t fl = (((size_t)Cg * Cu + 3) & ~(size_t)3) + (size_t)PB_V * (Cg | 1) + (size_t)PB_V * (Cu | 1) + 4 * (size_t)Cg + 2 * (size_t)Cu;
     return fl * sizeof(float);
@@ -1200,6 +1243,21 @@ extern "C" int l3d_pw_bwd(const l3d_act *gz, const l3d_act *t, const l3d_norm *n
     A.g_u = has_gu ? g_u->ptr : nullptr; A.ldgu = has_gu ? g_u->ldc : 0; A.accumulate = accumulate_gu;
     // the vector path of the u loader needs an aligned base as well
     if (u->C % 4 == 0 && !vec4_ok(u)) { l3d_set_error("l3d_pw_bwd: u view must be 4-channel aligned"); return 1; }
+    if (u->C == 1 && !has_gu && g_w != nullptr && (gz->C == 16 || gz->C == 32) && (!has_nt || vec4_ok(t))) {
+        const unsigned gx = (unsigned)((148 * 8 + N - 1) / N);
+        dim3 grid1(gx < 1 ? 1 : gx, (unsigned)N);
+        L3D_DISPATCH_DTYPE(u->dtype, T, {
+            if (gz->C == 16)
+                pw_bwd_cu1_kernel<T, 16><<<grid1, 256, 0, (cudaStream_t)stream>>>((const float *)gz->ptr, gz->ldc, has_nt ? (const T *)t->ptr : nullptr, has_nt ? t->ldc : 0,
+                                                                                    norm_dev(nt), red, (const T *)u->ptr, u->ldc, norm_dev(un), N, A.vox, g_w);
+            else
+                pw_bwd_cu1_kernel<T, 32><<<grid1, 256, 0, (cudaStream_t)stream>>>((const float *)gz->ptr, gz->ldc, has_nt ? (const T *)t->ptr : nullptr, has_nt ? t->ldc : 0,
+                                                                                    norm_dev(nt), red, (const T *)u->ptr, u->ldc, norm_dev(un), N, A.vox, g_w);
+        });
+        l3d_count_launch();
+        L3D_CUDA_OK("l3d_pw_bwd (single input channel) launch");
+        return 0;
+    }
     {   // tensor-core path (bf16 storage, 16-aligned channel counts)
         const int rc_tc = l3d_pw_bwd_tc(gz, t, nt, red, u, un, N, A.vox, w, g_w, g_u, accumulate_gu, stream);
         if (rc_tc == 0) { l3d_count_launch(); return 0; }
