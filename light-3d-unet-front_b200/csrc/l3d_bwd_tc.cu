@@ -17,6 +17,8 @@
 
 namespace {
 
+static bool env_flag_off(const char *name) { const char *e = getenv(name); return !(e && e[0] == '1'); }
+
 constexpr int NT = 256, TV = 128;
 constexpr int PLANE = TV * 16;          // bytes of one 8-channel group of a tile
 
@@ -277,6 +279,197 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
     if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)A.tmem_cols);
 }
 
+// Software-pipelined variant for the narrow layers (GI, UI >= 1; everything fits twice): the staged tiles are
+// double-buffered, so while the tensor pipe works on tile T the CTA converts tile T+1 (whose global loads were issued a
+// full iteration earlier) and issues the loads of T+2; the only exposed step per tile is the D1 epilogue.  Tiles are
+// assigned in contiguous ranges (one or two sample changes per CTA).
+template <int GI, int UI>
+__global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    const int Cg = A.Cg, Cu = A.Cu, gq = Cg >> 3, uq = Cu >> 3;
+    const uint32_t tile_bytes = (uint32_t)(2 * gq + uq) * PLANE;   // [Gh | Gl | U]
+    unsigned char *sWh = smem + 2 * tile_bytes;
+    unsigned char *sWl = sWh + (size_t)Cg * Cu * 2;
+    float *s_ca = reinterpret_cast<float *>(sWl + (size_t)Cg * Cu * 2);
+    float *s_cb = s_ca + Cg, *s_cd = s_cb + Cg;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool has_gu = A.g_u != nullptr, has_gw = A.g_w != nullptr, has_nt = A.nt.stats != nullptr;
+    if (warp == 0) tc::tmem_alloc(&s_tmem, (uint32_t)A.tmem_cols);
+    if (tid == 32) tc::mbar_init(&s_bar, 1);
+    for (int i = tid; i < Cg * Cu; i += NT) {
+        const int k = i % Cu, c = i / Cu;
+        const float wv = A.w[i];
+        const bf16 hi = __float2bfloat16_rn(wv);
+        const uint32_t off = tc::tile_off(k, c, Cu);
+        *reinterpret_cast<bf16 *>(sWh + off) = hi;
+        *reinterpret_cast<bf16 *>(sWl + off) = __float2bfloat16_rn(wv - __bfloat162float(hi));
+    }
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = s_tmem;
+    const uint32_t d1 = tmem, d2 = tmem + (uint32_t)Cu;
+    const uint32_t id_k = tc::idesc_16b_m128(Cu, 1, 1, false, false), id_mn = tc::idesc_16b_m128(Cu, 1, 1, true, true);
+    const uint32_t smem_u = tc::smem_u32(smem), sWh_u = tc::smem_u32(sWh), sWl_u = tc::smem_u32(sWl);
+    const long long tiles_per_sample = (A.vox + TV - 1) / TV;
+    const long long total_tiles = tiles_per_sample * A.N;
+    const long long per = (total_tiles + gridDim.x - 1) / gridDim.x;
+    const long long t_begin = (long long)blockIdx.x * per, t_end = t_begin + per < total_tiles ? t_begin + per : total_tiles;
+    float4 pg0[GI], pg1[GI];
+    uint4 pt[GI], pu[UI];
+    auto prefetch = [&](long long tl) {
+        const int pn = (int)(tl / tiles_per_sample);
+        const long long pv0 = (tl % tiles_per_sample) * TV;
+#pragma unroll
+        for (int i = 0; i < GI; ++i) {
+            const int item = tid + i * NT, q = item % gq, v = item / gq;      // channel group fastest: a warp reads contiguous voxel rows
+            if (pv0 + v < A.vox) {
+                const size_t gv = (size_t)pn * A.vox + pv0 + v;
+                pg0[i] = *reinterpret_cast<const float4 *>(A.gz + gv * (size_t)A.ldg + q * 8);
+                pg1[i] = *reinterpret_cast<const float4 *>(A.gz + gv * (size_t)A.ldg + q * 8 + 4);
+                if (has_nt) pt[i] = *reinterpret_cast<const uint4 *>(A.t + gv * (size_t)A.ldt + q * 8);
+            }
+        }
+        if (has_gw) {
+#pragma unroll
+            for (int i = 0; i < UI; ++i) {
+                const int item = tid + i * NT, q = item % uq, v = item / uq;
+                if (pv0 + v < A.vox) pu[i] = *reinterpret_cast<const uint4 *>(A.u + ((size_t)pn * A.vox + pv0 + v) * (size_t)A.ldu + q * 8);
+            }
+        }
+    };
+    int cur_n = -1;
+    auto stage = [&](long long tl, int b) {          // registers (tile tl) -> tile buffer b
+        const int n = (int)(tl / tiles_per_sample);
+        const long long v0 = (tl % tiles_per_sample) * TV;
+        if (n != cur_n) {                              // uniform over the CTA; the previous stage() ended before a CTA barrier
+            cur_n = n;
+            for (int c = tid; c < Cg; c += NT) {
+                float a, bb, d;
+                in_bwd_coef(A.nt, A.red, A.N, Cg, n, c, a, bb, d);
+                s_ca[c] = a; s_cb[c] = bb; s_cd[c] = d;
+            }
+            __syncthreads();
+        }
+        unsigned char *sGh = smem + (size_t)b * tile_bytes, *sGl = sGh + (size_t)gq * PLANE, *sU = sGl + (size_t)gq * PLANE;
+#pragma unroll
+        for (int i = 0; i < GI; ++i) {
+            const int item = tid + i * NT, q = item % gq, v = item / gq;
+            uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+            if (v0 + v < A.vox) {
+                float g[8] = {pg0[i].x, pg0[i].y, pg0[i].z, pg0[i].w, pg1[i].x, pg1[i].y, pg1[i].z, pg1[i].w};
+                if (has_nt) {
+                    const uint32_t tw[4] = {pt[i].x, pt[i].y, pt[i].z, pt[i].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = q * 8 + 2 * j;
+                        g[2 * j] = fmaf(s_ca[c], g[2 * j], fmaf(s_cb[c], __uint_as_float(tw[j] << 16), s_cd[c]));
+                        g[2 * j + 1] = fmaf(s_ca[c + 1], g[2 * j + 1], fmaf(s_cb[c + 1], __uint_as_float(tw[j] & 0xffff0000u), s_cd[c + 1]));
+                    }
+                }
+                split2(g[0], g[1], hi.x, lo.x); split2(g[2], g[3], hi.y, lo.y);
+                split2(g[4], g[5], hi.z, lo.z); split2(g[6], g[7], hi.w, lo.w);
+            }
+            *reinterpret_cast<uint4 *>(sGh + (size_t)q * PLANE + (size_t)v * 16) = hi;
+            *reinterpret_cast<uint4 *>(sGl + (size_t)q * PLANE + (size_t)v * 16) = lo;
+        }
+        if (has_gw) {
+#pragma unroll
+            for (int i = 0; i < UI; ++i) {
+                const int item = tid + i * NT, q = item % uq, v = item / uq;
+                *reinterpret_cast<uint4 *>(sU + (size_t)q * PLANE + (size_t)v * 16) = (v0 + v < A.vox) ? pu[i] : make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+    };
+    bool first = true;
+    auto issue = [&](int b) {                          // one thread, after a CTA barrier that followed fence_async_smem
+        tc::fence_after_sync();
+        const uint32_t sGh_u = smem_u + (uint32_t)b * tile_bytes, sGl_u = sGh_u + (uint32_t)gq * PLANE, sU_u = sGl_u + (uint32_t)gq * PLANE;
+        if (has_gu) {
+            for (int j = 0; j < Cg / 16; ++j) {
+                const uint64_t agh = tc::smem_desc(sGh_u + 2 * j * PLANE, PLANE, 128), agl = tc::smem_desc(sGl_u + 2 * j * PLANE, PLANE, 128);
+                const uint64_t bwh = tc::smem_desc(sWh_u + 2 * j * Cu * 16, Cu * 16, 128), bwl = tc::smem_desc(sWl_u + 2 * j * Cu * 16, Cu * 16, 128);
+                tc::mma_f16(d1, agh, bwh, id_k, j > 0 ? 1u : 0u);
+                tc::mma_f16(d1, agl, bwh, id_k, 1u);
+                tc::mma_f16(d1, agh, bwl, id_k, 1u);
+            }
+        }
+        if (has_gw) {
+            for (int j = 0; j < TV / 16; ++j) {
+                const uint64_t bu = tc::smem_desc(sU_u + j * 256, 128, PLANE);
+                tc::mma_f16(d2, tc::smem_desc(sGh_u + j * 256, 128, PLANE), bu, id_mn, (first && j == 0) ? 0u : 1u);
+                tc::mma_f16(d2, tc::smem_desc(sGl_u + j * 256, 128, PLANE), bu, id_mn, 1u);
+            }
+        }
+        tc::mma_commit(&s_bar);
+    };
+    uint32_t phase = 0;
+    if (t_begin < t_end) {
+        prefetch(t_begin);
+        stage(t_begin, 0);
+        if (t_begin + 1 < t_end) prefetch(t_begin + 1);
+        tc::fence_async_smem();
+        __syncthreads();
+        if (tid == 0) issue(0);
+        first = false;
+    }
+    for (long long tile = t_begin; tile < t_end; ++tile) {
+        const int b = (int)((tile - t_begin) & 1);
+        if (tile + 1 < t_end) {
+            stage(tile + 1, b ^ 1);                    // overlaps the MMAs of `tile`
+            tc::fence_async_smem();                    // here, not after the epilogue: the fence also drains this thread's global stores
+            if (tile + 2 < t_end) prefetch(tile + 2);
+        }
+        tc::mbar_wait(&s_bar, phase);
+        phase ^= 1u;
+        tc::fence_after_sync();
+        if (has_gu) {
+            const int n = (int)(tile / tiles_per_sample);
+            const long long v0 = (tile % tiles_per_sample) * TV;
+            const int v = (warp & 3) * 32 + lane;
+            const bool ok = v0 + v < A.vox;
+            float *op = A.g_u + ((size_t)n * A.vox + v0 + (ok ? v : 0)) * (size_t)A.ldgu;
+            const uint32_t trow = d1 + ((uint32_t)((warp & 3) * 32) << 16);
+            for (int cb = (warp >> 2) * 16; cb < Cu; cb += 32) {
+                float r[16];
+                tc::tmem_ld16(trow + (uint32_t)cb, r);
+                if (ok) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        float4 o = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                        if (A.accumulate) { const float4 pz = *reinterpret_cast<const float4 *>(op + cb + j); o.x += pz.x; o.y += pz.y; o.z += pz.z; o.w += pz.w; }
+                        *reinterpret_cast<float4 *>(op + cb + j) = o;
+                    }
+                }
+            }
+        }
+        tc::fence_before_sync();
+        __syncthreads();                               // D1 drained; tile buffer b^1 complete
+        if (tile + 1 < t_end && tid == 0) issue(b ^ 1);
+    }
+    if (has_gw && t_begin < t_end) {
+        tc::fence_after_sync();
+        const int c = (warp & 3) * 32 + lane;
+        const uint32_t trow = d2 + ((uint32_t)((warp & 3) * 32) << 16);
+        if ((warp & 3) * 32 < Cg) {
+            for (int cb = (warp >> 2) * 16; cb < Cu; cb += 32) {
+                float r[16];
+                tc::tmem_ld16(trow + (uint32_t)cb, r);
+                if (c < Cg) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) atomicAdd(&A.g_w[(size_t)c * Cu + cb + j], r[j]);
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)A.tmem_cols);
+}
+
 }  // namespace
 
 // Returns -1 when the tensor-core path does not apply (the caller falls back to the CUDA-core kernel).
@@ -317,26 +510,48 @@ int l3d_pw_bwd_tc(const l3d_act *gz, const l3d_act *t, const l3d_norm *nt, const
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = ((vox + TV - 1) / TV) * N;
+    // pipelined variant: two tile buffers + weights + tables, and the MN-major over-read of the second buffer's G planes
+    size_t smem_p = 2 * (size_t)(2 * (Cg / 8) + Cu / 8) * PLANE + 2 * (size_t)Cg * Cu * 2 + sizeof(float) * 3 * (size_t)Cg;
+    {
+        const size_t span_p = (size_t)(2 * (Cg / 8) + Cu / 8) * PLANE + (size_t)(Cg / 8) * PLANE + 16 * (size_t)PLANE + 256;
+        if (smem_p < span_p) smem_p = span_p;
+    }
+    const bool use_pipe = env_flag_off("L3D_NO_PWB_PIPE");
 #define L3D_PWTC(GIV, UIV)                                                                                                     \
     do {                                                                                                                        \
         static bool attr_set = false;                                                                                           \
         if (!attr_set) {                                                                                                        \
             cudaError_t e = cudaFuncSetAttribute(pw_bwd_tc_kernel<GIV, UIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
+            if (e == cudaSuccess && GIV > 0) e = cudaFuncSetAttribute(pw_bwd_tc_pipe_kernel<(GIV > 0 ? GIV : 1), (UIV > 0 ? UIV : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
             if (e != cudaSuccess) { l3d_set_error("pw_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 3; }    \
             attr_set = true;                                                                                                    \
         }                                                                                                                       \
-        static int occ_regs = 0;                                                                                                \
+        static int occ_regs = 0, occ_regs_p = 0;                                                                                \
         if (occ_regs == 0) {                                                                                                    \
             cudaFuncAttributes fa;                                                                                              \
-            occ_regs = 1;                                                                                                       \
+            occ_regs = occ_regs_p = 1;                                                                                          \
             if (cudaFuncGetAttributes(&fa, pw_bwd_tc_kernel<GIV, UIV>) == cudaSuccess && fa.numRegs > 0)                        \
                 occ_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * NT);                                                           \
+            if (cudaFuncGetAttributes(&fa, pw_bwd_tc_pipe_kernel<(GIV > 0 ? GIV : 1), (UIV > 0 ? UIV : 1)>) == cudaSuccess && fa.numRegs > 0) \
+                occ_regs_p = 65536 / (((fa.numRegs + 7) / 8 * 8) * NT);                                                         \
             if (occ_regs < 1) occ_regs = 1;                                                                                     \
+            if (occ_regs_p < 1) occ_regs_p = 1;                                                                                 \
         }                                                                                                                       \
-        const int occ_k = occ_regs < occ ? occ_regs : occ;                                                                      \
-        long long grid_k = (long long)sms * occ_k;                                                                              \
-        if (grid_k > tiles) grid_k = tiles;                                                                                     \
-        pw_bwd_tc_kernel<GIV, UIV><<<(unsigned)grid_k, NT, smem, (cudaStream_t)stream>>>(A);                                    \
+        if (GIV > 0 && use_pipe && smem_p <= 100 * 1024) {                                                                      \
+            int occ_p = (int)((227 * 1024) / (smem_p + 2048));                                                                  \
+            if (occ_p > 4) occ_p = 4;                                                                                           \
+            if (occ_p * cols > 512) occ_p = 512 / cols;                                                                         \
+            if (occ_p > occ_regs_p) occ_p = occ_regs_p;                                                                         \
+            if (occ_p < 1) occ_p = 1;                                                                                           \
+            long long grid_p = (long long)sms * occ_p;                                                                          \
+            if (grid_p > tiles) grid_p = tiles;                                                                                 \
+            pw_bwd_tc_pipe_kernel<(GIV > 0 ? GIV : 1), (UIV > 0 ? UIV : 1)><<<(unsigned)grid_p, NT, smem_p, (cudaStream_t)stream>>>(A); \
+        } else {                                                                                                                \
+            const int occ_k = occ_regs < occ ? occ_regs : occ;                                                                  \
+            long long grid_k = (long long)sms * occ_k;                                                                          \
+            if (grid_k > tiles) grid_k = tiles;                                                                                 \
+            pw_bwd_tc_kernel<GIV, UIV><<<(unsigned)grid_k, NT, smem, (cudaStream_t)stream>>>(A);                                \
+        }                                                                                                                       \
     } while (0)
     const int gi = Cg / 16, ui = Cu / 16;            // staging items per thread (TV * C / 8 / NT)
     if (gi == 1 && ui == 1) L3D_PWTC(1, 1);

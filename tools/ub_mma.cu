@@ -53,6 +53,42 @@ __global__ void __launch_bounds__(128) ub_kernel(Variant v, int iters, long long
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
+// MN-major bf16 operands over voxel-planar tiles (the weight-gradient form): cycles per MMA
+__global__ void __launch_bounds__(128) ub_mn_kernel(int n, int mn, int iters, long long *out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tc::tmem_alloc(&s_tmem, 512);
+    if (tid == 32) tc::mbar_init(&s_bar, 1);
+    for (int i = tid; i < 160 * 1024 / 4; i += 128) reinterpret_cast<uint32_t *>(smem)[i] = 0x00010001u;
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = s_tmem;
+    long long t0 = 0, t1 = 0;
+    if (tid == 0) {
+        const uint32_t idesc = tc::idesc_16b_m128(n, 1, 1, mn != 0, mn != 0);
+        const uint32_t sA = tc::smem_u32(smem), sB = sA + 96 * 1024;
+        t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint64_t ad = mn ? tc::smem_desc(sA + j * 256, 128, 2048) : tc::smem_desc(sA + 2 * j * 2048, 2048, 128);
+                const uint64_t bd = mn ? tc::smem_desc(sB + j * 256, 128, 2048) : tc::smem_desc(sB + 2 * j * n * 16, n * 16, 128);
+                tc::mma_f16(tmem, ad, bd, idesc, 1u);
+            }
+        }
+        tc::mma_commit(&s_bar);
+    }
+    tc::mbar_wait(&s_bar, 0);
+    if (tid == 0) { t1 = clock64(); out[blockIdx.x] = t1 - t0; }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
 template <int MODE>
 static double run(Variant v, int iters, long long *d_out) {
     long long h_out[148];
@@ -82,7 +118,22 @@ int main() {
         {"conv: sbo256 dz/dy only", 256, 18432, 4},
         {"conv: sbo256 no shift", 256, 18432, 0},
     };
-    for (int chains = 1; chains <= 2; ++chains)
+    cudaFuncSetAttribute(ub_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    for (int mn = 0; mn <= 1; ++mn) {
+        printf("%-40s          :", mn ? "bf16 MN-major A and B (voxel-planar)" : "bf16 K-major A and B");
+        for (int n : {16, 32, 64, 128}) {
+            long long h_out[148];
+            ub_mn_kernel<<<148, 128, 200 * 1024>>>(n, mn, 100, d_out);
+            ub_mn_kernel<<<148, 128, 200 * 1024>>>(n, mn, 100, d_out);
+            if (cudaDeviceSynchronize() != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
+            cudaMemcpy(h_out, d_out, sizeof(h_out), cudaMemcpyDeviceToHost);
+            long long mx = 0;
+            for (int i = 0; i < 148; ++i) mx = h_out[i] > mx ? h_out[i] : mx;
+            printf(" N%-3d %6.1f", n, (double)mx / 800.0);
+        }
+        printf("\n");
+    }
+    for (int chains = 1; chains <= 1; ++chains)
         for (auto &l : layouts) {
             printf("%-40s chains=%d :", l.name, chains);
             for (int n : ns) {
