@@ -122,7 +122,10 @@ def sliding_window_device(volume: torch.Tensor, model, patch_size=(48, 48, 48), 
                     nv.dtype_code(dt), st)
             model._plan.forward(P, batch, False, None, prob_out=preds[s:s + n])
     else:
-        # any other torch module: batched forward on the device, stitched by the same kernel
+        # any other torch module: batched forward on the device, stitched by the same kernel (its activation footprint is
+        # unknown, so the batch stays small unless the caller asks for more)
+        if window_batch is None:
+            wb = min(wb, 16)
         for s in range(0, nwin, wb):
             n = min(wb, nwin - s)
             batch = torch.empty(n, pd, ph, pw, 1, dtype=torch.float32, device=dev)
