@@ -37,6 +37,7 @@ class Inferencer:
         if not torch.cuda.is_available():
             raise nv.NativeError("Inferencer: the B200-native path needs a CUDA device (no CPU fallback)")
         self.device = torch.device("cuda", torch.cuda.current_device())
+        self._copy_stream = None
         print(f"Using device: {self.device}")
         m = self.config["model"]
         self.model = Lightweight3DUNet(
@@ -111,11 +112,13 @@ class Inferencer:
         return self._bboxes_from_device(prob_d, mask_d, min_volume_cc, spacing)
 
     # ----------------------------------------------------------------- volume
-    def infer_volume(self, image, threshold=0.3, spacing=(4.0, 4.0, 4.0), body_mask=None, return_device=False):
+    def infer_volume(self, image, threshold=0.3, spacing=(4.0, 4.0, 4.0), body_mask=None, return_device=False, prob_out=None):
         """Device-resident case pipeline: sliding window -> (body mask) -> threshold -> CC -> boxes.
-        `image` is a host ndarray or CUDA tensor [D,H,W].  Returns (prob_map, bboxes)."""
+        `image` is a host ndarray or CUDA tensor [D,H,W].  Returns (prob_map, bboxes).  `prob_out`: optional pinned host
+        fp32 tensor [D,H,W]; the probability map is then copied into it on a side stream while the connected-component /
+        bounding-box kernels run, and returned instead of a fresh array."""
         if isinstance(image, torch.Tensor):
-            vol = image.to(self.device, dtype=torch.float32)
+            vol = image.to(self.device, dtype=torch.float32, non_blocking=True)
         else:
             vol = torch.from_numpy(np.ascontiguousarray(image, dtype=np.float32)).to(self.device, non_blocking=True)
         bm = None
@@ -123,7 +126,24 @@ class Inferencer:
             bm = body_mask if isinstance(body_mask, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(body_mask).astype(np.uint8))
         prob_d, mask_d = sliding_window_device(vol, self.model, tuple(self.config["data"]["patch_size"]), 0.5, True,
                                                body_mask=bm, threshold=threshold)
+        copy_done = None
+        if prob_out is not None:
+            if not (isinstance(prob_out, torch.Tensor) and prob_out.device.type == "cpu" and prob_out.dtype == torch.float32
+                    and tuple(prob_out.shape) == tuple(prob_d.shape) and prob_out.is_contiguous()):
+                raise ValueError("prob_out must be a contiguous float32 CPU tensor of the volume's shape")
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            main = torch.cuda.current_stream(self.device)
+            self._copy_stream.wait_stream(main)                   # the stitched map is complete on the main stream
+            with torch.cuda.stream(self._copy_stream):
+                prob_out.copy_(prob_d, non_blocking=True)
+                prob_d.record_stream(self._copy_stream)
+                copy_done = torch.cuda.Event()
+                copy_done.record(self._copy_stream)
         bboxes = self._bboxes_from_device(prob_d, mask_d, self.config["data"]["volume_threshold"]["inference_cc"], spacing)
+        if copy_done is not None:
+            copy_done.synchronize()
+            return prob_out, bboxes
         return (prob_d if return_device else prob_d.cpu().numpy()), bboxes
 
     # ------------------------------------------------------------- file level

@@ -210,3 +210,11 @@ def test_inferencer_end_to_end(tmp_path):
     # boxes must be exactly what the reference algorithm extracts from OUR probability map
     assert boxes == bbox_ref.extract_bboxes(prob, 0.5, 0.5, (4.0, 4.0, 4.0), 3)
     assert (tmp_path / "prob").is_dir() and (tmp_path / "bbox").is_dir()
+    # pinned-host output path: the map is copied on a side stream under the labelling kernels (two forward passes agree to
+    # round-off only: the InstanceNorm statistics are accumulated with atomics)
+    out = torch.empty(vol.shape, dtype=torch.float32).pin_memory()
+    prob2, boxes2 = inf.infer_volume(torch.from_numpy(vol).pin_memory(), threshold=0.5, spacing=(4.0, 4.0, 4.0), prob_out=out)
+    assert prob2 is out and np.abs(out.numpy() - prob).max() < 1e-5
+    assert boxes2 == bbox_ref.extract_bboxes(out.numpy(), 0.5, 0.5, (4.0, 4.0, 4.0), 3)
+    with pytest.raises(ValueError):
+        inf.infer_volume(vol, threshold=0.5, prob_out=torch.empty(3, 3, 3))
