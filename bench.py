@@ -229,7 +229,13 @@ def bench_ours(args):
     for (name, tag), (n, t, b) in rec.items():
         a = by_name.setdefault(name, [0, 0.0, 0])
         a[0] += n; a[1] += t; a[2] += b
-    top = max(by_name.items(), key=lambda kv: kv[1][1])
+    # dominant KERNEL: dispatching entry points (l3d_dwpw_fwd ...) are attributed to the kernel they launched; the other
+    # entry points launch one kernel of their own name
+    by_kernel = dict(nv.TIMER.by_kernel)
+    for k, v in by_name.items():
+        if k not in nv._DISPATCHING:
+            by_kernel[k] = tuple(v)
+    top = max(by_kernel.items(), key=lambda kv: kv[1][1])
     pk = peaks()
     es = 2 if args.dtype == "bf16" else 4
     achieved = top[1][2] / (top[1][1] * 1e-3) / 1e9 if top[1][1] > 0 else 0.0
@@ -247,7 +253,9 @@ def bench_ours(args):
                             "frac_tensor": round(NWIN * FWD_FLOP[args.variant] / (step_ms * 1e-3) / 1e12 / pk["bf16_tflops"], 4)},
                 "kernels": {k: {"launches": v[0], "ms": round(v[1], 3), "share": round(v[1] / tot_ms, 3),
                                 "gbs": round(v[2] / max(v[1], 1e-9) / 1e6, 1)} for k, v in
-                            sorted(by_name.items(), key=lambda kv: -kv[1][1])}}
+                            sorted(by_kernel.items(), key=lambda kv: -kv[1][1])},
+                "entry_points": {k: {"launches": v[0], "ms": round(v[1], 3), "share": round(v[1] / tot_ms, 3)} for k, v in
+                                 sorted(by_name.items(), key=lambda kv: -kv[1][1])}}
 
     train = None
     if not args.skip_train:

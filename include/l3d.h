@@ -207,6 +207,10 @@ int l3d_bbox_reduce(const int32_t *labels, const float *prob, int D, int H, int 
 
 /* ------------------------------------------------------------- diagnostics -- */
 
+/* Name of the kernel the last dispatching entry point (l3d_dwpw_fwd, l3d_conv3_fwd, l3d_convt_fwd) launched on this
+ * thread: "conv3_tc_kernel", "dwpw_tc_kernel", "dwpw_c1_kernel", ... ("" before the first launch). */
+const char *l3d_last_kernel(void);
+
 /* Self-test of the tcgen05 building blocks: D[128*MT][N] (fp32) = A[128*MT][K] . Wt[N][K]^T with fp16 operands
  * and fp32 accumulation in TMEM.  A, Wt, D are fp32 device arrays. */
 int l3d_tc_selftest(const float *A, const float *Wt, int MT, int K, int N, float *D, void *stream);

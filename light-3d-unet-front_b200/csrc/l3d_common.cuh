@@ -13,6 +13,8 @@ typedef __nv_bfloat16 bf16;
 // ------------------------------------------------------------------ errors --
 void l3d_set_error(const char *fmt, ...);
 void l3d_count_launch(int n = 1);
+// name of the kernel a dispatching entry point launched last on this thread (l3d_last_kernel(), for per-kernel timing)
+void l3d_note_kernel(const char *name);
 // tiled CUtensorMap encode through a runtime-resolved driver entry point (no libcuda link dependency)
 int l3d_encode_tiled(void *tmap, int dtype, unsigned rank, void *base, const unsigned long long *dims,
                      const unsigned long long *strides, const unsigned *box, const unsigned *estr);

@@ -616,6 +616,7 @@ int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int 
 #undef L3D_C3_TZ
 #undef L3D_C3_LAUNCH
     l3d_count_launch();
+    l3d_note_kernel("conv3_tc_kernel");
     L3D_CUDA_OK("l3d_conv3 (tcgen05 implicit GEMM) launch");
     return 0;
 }

@@ -838,6 +838,7 @@ extern "C" int l3d_dwpw_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, 
         L3D_DISPATCH_DTYPE(x->dtype, T, { if (Cout == 16) LAUNCH_C1(T, 16); else LAUNCH_C1(T, 32); });
 #undef LAUNCH_C1
         l3d_count_launch();
+        l3d_note_kernel("dwpw_c1_kernel");
         L3D_CUDA_OK("l3d_dwpw_fwd (Cin=1) launch");
         return 0;
     }
@@ -865,6 +866,7 @@ extern "C" int l3d_dwpw_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, 
     });
 #undef LAUNCH_DWPW
     l3d_count_launch();
+    l3d_note_kernel("dwpw_fwd_kernel");
     L3D_CUDA_OK("l3d_dwpw_fwd launch");
     return 0;
 }

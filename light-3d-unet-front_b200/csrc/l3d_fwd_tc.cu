@@ -435,6 +435,7 @@ int l3d_dwpw_fwd_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
     if (grid > tiles) grid = tiles;
     dwpw_tc_kernel<<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(tmap, A);
     l3d_count_launch();
+    l3d_note_kernel("dwpw_tc_kernel");
     L3D_CUDA_OK("l3d_dwpw_fwd (tcgen05) launch");
     return 0;
 }
@@ -598,6 +599,7 @@ int l3d_convt_fwd_tc(const l3d_act *x, int N, int d, int h, int w_, const float 
     if (grid > tiles) grid = tiles;
     convt_tc_kernel<<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(A);
     l3d_count_launch();
+    l3d_note_kernel("convt_tc_kernel");
     L3D_CUDA_OK("l3d_convt_fwd (tcgen05) launch");
     return 0;
 }

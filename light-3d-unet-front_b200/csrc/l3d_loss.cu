@@ -15,6 +15,9 @@ void l3d_set_error(const char *fmt, ...) {
     va_end(ap);
 }
 void l3d_count_launch(int n) { __atomic_fetch_add(&g_launches, (int64_t)n, __ATOMIC_RELAXED); }
+static thread_local const char *g_last_kernel = "";
+void l3d_note_kernel(const char *name) { g_last_kernel = name; }
+extern "C" const char *l3d_last_kernel(void) { return g_last_kernel; }
 
 
 // cuTensorMapEncodeTiled is resolved through the runtime at first use, so libl3d.so has no link-time dependency on

@@ -71,7 +71,7 @@ _SIGS = {
     "l3d_tc_selftest_tf32": [_P, _P, c_int, c_int, c_int, c_int, _P, _P],
     "l3d_tc_selftest_mn16": [_P, _P, c_int, c_int, c_int, _P, _P],
 }
-EXPORTS = sorted(list(_SIGS) + ["l3d_last_error", "l3d_abi_version", "l3d_launch_count", "l3d_ccl_workspace_elems",
+EXPORTS = sorted(list(_SIGS) + ["l3d_last_kernel", "l3d_last_error", "l3d_abi_version", "l3d_launch_count", "l3d_ccl_workspace_elems",
                                 "l3d_conv3_bwd_workspace_bytes"])
 
 
@@ -87,6 +87,8 @@ def lib():
     L = ctypes.CDLL(LIB_PATH)
     L.l3d_last_error.restype = ctypes.c_char_p
     L.l3d_last_error.argtypes = []
+    L.l3d_last_kernel.restype = ctypes.c_char_p
+    L.l3d_last_kernel.argtypes = []
     L.l3d_abi_version.restype = c_int
     L.l3d_launch_count.restype = c_int64
     L.l3d_ccl_workspace_elems.restype = c_int64
@@ -109,7 +111,8 @@ class KernelTimer:
 
     def __init__(self):
         self.enabled = False
-        self.records = []   # (name, tag, start_event, stop_event, algorithmic bytes)
+        self.records = []   # (name, tag, start_event, stop_event, algorithmic bytes, kernel)
+        self.by_kernel = {}
         self.tag = ""
 
     def start(self):
@@ -121,13 +124,19 @@ class KernelTimer:
         self.enabled = False
         torch.cuda.synchronize()
         out = {}
-        for name, tag, e0, e1, nbytes in self.records:
+        self.by_kernel = {}     # kernel actually launched by a dispatching entry point -> (launches, ms, algorithmic bytes)
+        for name, tag, e0, e1, nbytes, kern in self.records:
+            dt = e0.elapsed_time(e1)
             n, ms, b = out.get((name, tag), (0, 0.0, 0))
-            out[(name, tag)] = (n + 1, ms + e0.elapsed_time(e1), b + nbytes)
+            out[(name, tag)] = (n + 1, ms + dt, b + nbytes)
+            if kern:
+                n, ms, b = self.by_kernel.get(kern, (0, 0.0, 0))
+                self.by_kernel[kern] = (n + 1, ms + dt, b + nbytes)
         self.records.clear()
         return out
 
 
+_DISPATCHING = {"l3d_dwpw_fwd", "l3d_conv3_fwd", "l3d_convt_fwd"}
 TIMER = KernelTimer()
 
 
@@ -140,7 +149,8 @@ def call(name: str, *args, algo_bytes: int = 0):
         e0.record()
         rc = getattr(L, name)(*args)
         e1.record()
-        TIMER.records.append((name, TIMER.tag, e0, e1, int(algo_bytes)))
+        kern = L.l3d_last_kernel().decode() if name in _DISPATCHING else ""
+        TIMER.records.append((name, TIMER.tag, e0, e1, int(algo_bytes), kern))
     else:
         rc = getattr(L, name)(*args)
     if rc != 0:
