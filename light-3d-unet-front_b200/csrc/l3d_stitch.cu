@@ -95,28 +95,37 @@ __device__ __forceinline__ void uf_union(int32_t *parent, int32_t a, int32_t b) 
     }
 }
 
-// Initial forest: every foreground voxel points at the first voxel of its x-run inside the warp's 32-voxel segment
-// (runs break at row starts), found with one ballot -- a row of foreground costs no union at all.
+// Initial forest: one warp walks one row (32 voxels per step, the open run carried across steps), so every foreground
+// voxel starts out pointing at the first voxel of its whole x-run -- a row of foreground costs no union at all.
 __global__ void __launch_bounds__(256) ccl_init_kernel(const int32_t *__restrict__ mask, int32_t n, int W, int32_t *__restrict__ parent,
                                                        int32_t *__restrict__ size) {
-    const int32_t n_round = (n + 31) & ~31;
     const int lane = threadIdx.x & 31;
-    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
-        const bool fg = i < n && mask[i] != 0;
-        const unsigned fgm = __ballot_sync(0xffffffffu, fg);
-        const unsigned rowstart = __ballot_sync(0xffffffffu, i < n && (i % W) == 0);
-        const unsigned starts = fgm & (~(fgm << 1) | rowstart | 1u);
-        if (i < n) {
-            int32_t p = -1;
-            if (fg) p = i - (lane - (31 - __clz(starts & (0xffffffffu >> (31 - lane)))));
-            parent[i] = p;
-            size[i] = 0;
+    const int32_t nrows = n / W;
+    const int32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (int32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < nrows; row += warps) {
+        const int32_t base = row * W;
+        bool carry = false;
+        int32_t carry_start = 0;
+        for (int x0 = 0; x0 < W; x0 += 32) {
+            const int x = x0 + lane;
+            const bool fg = x < W && mask[base + x] != 0;
+            const unsigned fgm = __ballot_sync(0xffffffffu, fg);
+            // run starts inside this step: foreground whose left neighbour is background (lane 0: no open run carried in)
+            const unsigned starts = fgm & ~((fgm << 1) | (carry ? 1u : 0u));
+            const unsigned below = starts & (0xffffffffu >> (31 - lane));
+            const int32_t my_start = below ? base + x0 + (31 - __clz(below)) : carry_start;
+            if (x < W) {
+                parent[base + x] = fg ? my_start : -1;
+                size[base + x] = 0;
+            }
+            carry = (fgm >> 31) != 0;
+            carry_start = __shfl_sync(0xffffffffu, my_start, 31);
         }
     }
 }
-// Unions only where two runs meet for the first time: across a segment boundary in x, and for the y / z neighbour
-// only at the first voxel of an overlap (if the previous voxel in x and its y / z neighbour are both foreground, that
-// voxel has already joined the same two runs).
+// Unions only where two runs meet for the first time: for the y / z neighbour only at the first voxel of an overlap
+// (if the previous voxel in x and its y / z neighbour are both foreground, that voxel has already joined the same two
+// runs).
 __global__ void __launch_bounds__(256) ccl_merge_kernel(int32_t *__restrict__ parent, int D, int H, int W) {
     const int32_t n = D * H * W;
     const int32_t WH = W * H;
@@ -124,7 +133,6 @@ __global__ void __launch_bounds__(256) ccl_merge_kernel(int32_t *__restrict__ pa
         if (parent[i] < 0) continue;
         const int x = i % W, y = (i / W) % H, z = i / WH;
         const bool left = x > 0 && parent[i - 1] >= 0;
-        if (left && (i & 31) == 0) uf_union(parent, i, i - 1);
         if (y > 0 && parent[i - W] >= 0 && !(left && parent[i - W - 1] >= 0)) uf_union(parent, i, i - W);
         if (z > 0 && parent[i - WH] >= 0 && !(left && parent[i - WH - 1] >= 0)) uf_union(parent, i, i - WH);
     }
