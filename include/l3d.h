@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define L3D_ABI_VERSION 1
+#define L3D_ABI_VERSION 2
 
 enum { L3D_F32 = 0, L3D_BF16 = 1 };
 
@@ -80,9 +80,11 @@ int l3d_dwpw_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int 
                  const l3d_act *u, void *stream);
 
 /* Dense / grouped 3x3x3 convolution, pad 1, no bias (nn.Conv3d at unet3d.py:30,49,60).
- * w: [Cout][Cin/groups][3][3][3]. */
+ * w: [Cout][Cin/groups][3][3][3].  Optionally also the block's 1x1x1 shortcut conv on the same activated input
+ * (unet3d.py:70-71): sc_w [Cout][Cin] -> r, r_stats (all three NULL when the block has no shortcut conv). */
 int l3d_conv3_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int W,
-                  const float *w, int groups, const l3d_act *t, double *t_stats, void *stream);
+                  const float *w, int groups, const l3d_act *t, double *t_stats,
+                  const float *sc_w, const l3d_act *r, double *r_stats, void *stream);
 
 /* Residual merge: out = lrelu(IN2(t2) + (INs(r) | r)) (unet3d.py:87-91), optionally also
  * emitting MaxPool3d(2,2) of out (unet3d.py:109) and/or the 1x1x1 head + sigmoid

@@ -1386,7 +1386,8 @@ extern "C" int64_t l3d_conv3_bwd_workspace_bytes(int N, int D, int H, int W, int
 }
 
 extern "C" int l3d_conv3_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int W,
-                             const float *w, int groups, const l3d_act *t, double *t_stats, void *stream);
+                             const float *w, int groups, const l3d_act *t, double *t_stats,
+                             const float *sc_w, const l3d_act *r, double *r_stats, void *stream);
 
 extern "C" int l3d_conv3_bwd(const l3d_act *gz, const l3d_act *t, const l3d_norm *nt, const double *red,
                              const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int W,
@@ -1458,7 +1459,7 @@ extern "C" int l3d_conv3_bwd(const l3d_act *gz, const l3d_act *t, const l3d_norm
         l3d_count_launch();
         l3d_act a_gt = {gt, Cout, Cout, L3D_F32, 0};
         l3d_act a_ga = {ga, Cin, Cin, L3D_F32, 0};
-        int rc = l3d_conv3_fwd(&a_gt, nullptr, N, D, H, W, wT, groups, &a_ga, dummy_stats, stream);
+        int rc = l3d_conv3_fwd(&a_gt, nullptr, N, D, H, W, wT, groups, &a_ga, dummy_stats, nullptr, nullptr, nullptr, stream);
         if (rc) return rc;
         size_t gx = (vox * Cin + NT - 1) / NT;
         const size_t cap = (148 * 16 + N - 1) / N;

@@ -51,6 +51,7 @@ struct C3Args {
     int Cout;
     bf16 *t; int ldt; double *t_stats;
     bf16 *r; int ldr; double *r_stats;
+    int co0, cout_total;     // dense / grouped weights: first output channel of this launch and the layer's full Cout
     int stat_ld;             // channels per (n) row of the statistics arrays (>= Cout: the launch may own a channel slice)
     int tmem_cols, nraw, nsets, merge, merged_cx, dbg;
 };
@@ -118,16 +119,17 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
     }
     // ---- stage the (effective) 3x3x3 weights once per CTA as fp16 K-major operand tiles
     {
-        const int cin_g = Cin / A.groups, cout_g = Cout / A.groups;
+        const int cin_g = Cin / A.groups, cout_g = A.cout_total / A.groups;
         const int rows = 3 * Cout;
         // one (co, ci) pair per step: its 27 taps are contiguous in global memory and all loads are in flight together
         for (int i = tid; i < Cout * Cin; i += NT) {
             const int ci = i % Cin, co = i / Cin;
             float wv[27];
             if (A.w != nullptr) {
-                const int g = co / cout_g, cl = ci - g * cin_g;
+                const int cog = A.co0 + co;
+                const int g = cog / cout_g, cl = ci - g * cin_g;
                 const bool in_group = cl >= 0 && cl < cin_g;
-                const float *src = A.w + ((size_t)co * cin_g + (in_group ? cl : 0)) * 27;
+                const float *src = A.w + ((size_t)cog * cin_g + (in_group ? cl : 0)) * 27;
 #pragma unroll
                 for (int tap = 0; tap < 27; ++tap) wv[tap] = in_group ? src[tap] : 0.f;
             } else {
@@ -507,7 +509,8 @@ extern "C" int l3d_conv3_debug_read(long long *host, int n) {
 // does not apply (the caller falls back to another kernel).
 int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int W,
                  const float *w, int groups, const float *dw_w, const float *pw_w, const float *sc_w,
-                 const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats, int stat_ld, void *stream) {
+                 const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats, int stat_ld, int co0, int cout_total,
+                 void *stream) {
     static int disabled = -1;
     if (disabled < 0) { const char *e = getenv("L3D_NO_IGEMM"); disabled = (e && e[0] == '1') ? 1 : 0; }
     if (disabled) return -1;
@@ -581,6 +584,7 @@ int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int 
     A.t = (bf16 *)t->ptr; A.ldt = t->ldc; A.t_stats = t_stats;
     A.r = has_sc ? (bf16 *)r->ptr : nullptr; A.ldr = has_sc ? r->ldc : 0; A.r_stats = r_stats;
     A.stat_ld = stat_ld > 0 ? stat_ld : Cout;
+    A.co0 = co0; A.cout_total = cout_total > 0 ? cout_total : Cout;
     A.tmem_cols = cols; A.nraw = nraw; A.nsets = nsets; A.merged_cx = merged_cx ? 1 : 0; A.dbg = env_int("L3D_C3_DEBUG_SKIP", 0);
     A.merge = (3 * Cout <= 256 && env_int("L3D_C3_NOMERGE", 0) == 0) ? 1 : 0;
     int occ = (int)((227 * 1024) / (smem + 2048));

@@ -753,6 +753,113 @@ __global__ void __launch_bounds__(NT) dwpw_c1_kernel(
     flush(cur_n);
 }
 
+// Dense 3x3x3 conv with a single input channel (the first conv of the dense / grouped variants, unet3d.py:49 with
+// in_channels = 1): 27 taps x COUT filters per voxel on CUDA cores, thread = one voxel, all COUT outputs; optionally the
+// block's 1x1x1 shortcut (r[c] = sc[c] * x) from the same staged tile.  Statistics by the transposing warp reduction.
+template <typename T, int COUT>
+__global__ void __launch_bounds__(NT) conv3_c1_kernel(
+    const T *__restrict__ x, int ldx, NormDev xn, int N, int D, int H, int W, const float *__restrict__ wgt, const float *__restrict__ sc_w,
+    T *__restrict__ t, int ldt, double *__restrict__ t_stats, T *__restrict__ r, int ldr, double *__restrict__ r_stats) {
+    __shared__ float s_in[HZ][HY][HX + 1];
+    __shared__ __align__(16) float s_w[27 * COUT + COUT];        // [tap][co], then the shortcut weights
+    __shared__ float s_stat[4 * COUT];
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < 27 * COUT; i += NT) { const int tap = i / COUT, co = i % COUT; s_w[i] = wgt[(size_t)co * 27 + tap]; }
+    for (int i = tid; i < COUT; i += NT) s_w[27 * COUT + i] = sc_w != nullptr ? sc_w[i] : 0.f;
+    for (int i = tid; i < 4 * COUT; i += NT) s_stat[i] = 0.f;
+    const int tilesX = (W + TX - 1) / TX, tilesY = (H + TY - 1) / TY, tilesZ = (D + TZ - 1) / TZ;
+    const int tiles_per_sample = tilesX * tilesY * tilesZ;
+    const int total_tiles = tiles_per_sample * N;
+    const int per = (total_tiles + gridDim.x - 1) / gridDim.x;
+    const int tile_begin = blockIdx.x * per, tile_end = min(total_tiles, tile_begin + per);
+    const int lx = tid & 7, ly = (tid >> 3) & 7, lz = tid >> 6;
+    int cur_n = -1;
+    float sc = 1.f, sh = 0.f;
+    auto flush = [&](int n) {
+        if (n < 0) return;
+        for (int i = tid; i < 2 * COUT; i += NT) {
+            const int isq = i >= COUT, c = isq ? i - COUT : i;
+            atomicAdd(&t_stats[(size_t)isq * N * COUT + (size_t)n * COUT + c], (double)s_stat[i]);
+            if (sc_w != nullptr) atomicAdd(&r_stats[(size_t)isq * N * COUT + (size_t)n * COUT + c], (double)s_stat[2 * COUT + i]);
+        }
+        __syncthreads();
+        for (int i = tid; i < 4 * COUT; i += NT) s_stat[i] = 0.f;
+    };
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const int n = tile / tiles_per_sample;
+        int b = tile - n * tiles_per_sample;
+        const int x0 = (b % tilesX) * TX; b /= tilesX;
+        const int y0 = (b % tilesY) * TY; b /= tilesY;
+        const int z0 = b * TZ;
+        __syncthreads();
+        if (n != cur_n) {
+            flush(cur_n);
+            cur_n = n;
+            norm_scale_shift(xn, N, 1, n, 0, sc, sh);
+        }
+        for (int item = tid; item < HZ * HY * HX; item += NT) {
+            int hv = item;
+            const int hx = hv % HX; hv /= HX;
+            const int hy = hv % HY;
+            const int hz = hv / HY;
+            const int gz = z0 + hz - 1, gy = y0 + hy - 1, gx = x0 + hx - 1;
+            float v = 0.f;
+            if (gz >= 0 && gz < D && gy >= 0 && gy < H && gx >= 0 && gx < W)
+                v = lrelu(ld1(x + ((((size_t)n * D + gz) * H + gy) * W + gx) * (size_t)ldx) * sc + sh, xn.slope);
+            s_in[hz][hy][hx] = v;
+        }
+        __syncthreads();
+        float acc[COUT];
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+#pragma unroll
+        for (int tap = 0; tap < 27; ++tap) {
+            const float a = s_in[lz + tap / 9][ly + (tap / 3) % 3][lx + tap % 3];
+#pragma unroll
+            for (int c4 = 0; c4 < COUT; c4 += 4) {
+                const float4 wv = *reinterpret_cast<const float4 *>(s_w + tap * COUT + c4);
+                acc[c4] = fmaf(a, wv.x, acc[c4]); acc[c4 + 1] = fmaf(a, wv.y, acc[c4 + 1]);
+                acc[c4 + 2] = fmaf(a, wv.z, acc[c4 + 2]); acc[c4 + 3] = fmaf(a, wv.w, acc[c4 + 3]);
+            }
+        }
+        const float xc = s_in[lz + 1][ly + 1][lx + 1];
+        const int gz = z0 + lz, gy = y0 + ly, gx = x0 + lx;
+        const bool valid = gz < D && gy < H && gx < W;
+        const size_t vox = (((size_t)n * D + gz) * H + gy) * W + gx;
+        constexpr int V = VecW<T>::V;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            if (a == 1 && sc_w == nullptr) break;
+            T *op = (a == 0 ? t + vox * (size_t)ldt : r + vox * (size_t)ldr);
+            float *stat = s_stat + a * 2 * COUT;
+#pragma unroll
+            for (int cb = 0; cb < COUT; cb += 16) {
+                float sv[32];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float o = a == 0 ? acc[cb + j] : xc * s_w[27 * COUT + cb + j];
+                    const float q = valid ? round_as(t, o) : 0.f;      // statistics of the stored values
+                    sv[j] = q; sv[16 + j] = q * q;
+                }
+                if (valid) {
+#pragma unroll
+                    for (int j0 = 0; j0 < 16; j0 += V) {
+                        float o[V];
+#pragma unroll
+                        for (int j = 0; j < V; ++j) o[j] = a == 0 ? acc[cb + j0 + j] : xc * s_w[27 * COUT + cb + j0 + j];
+                        stv(op + cb + j0, o);
+                    }
+                }
+                warp_transpose_sum<32>(sv, lane);
+                const int idx = warp_transpose_owner<32>(lane);
+                atomicAdd(&stat[(idx >= 16 ? COUT + idx - 16 : idx) + cb], sv[0]);
+            }
+        }
+    }
+    __syncthreads();
+    flush(cur_n);
+}
+
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
     if (bytes > 48 * 1024) {
@@ -777,7 +884,8 @@ int l3d_dwpw_fwd_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
 
 int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int W,
                  const float *w, int groups, const float *dw_w, const float *pw_w, const float *sc_w,
-                 const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats, int stat_ld, void *stream);
+                 const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats, int stat_ld, int co0, int cout_total,
+                 void *stream);
 int l3d_convt_fwd_tc(const l3d_act *x, int N, int d, int h, int w_, const float *w, const float *b,
                      const l3d_act *out, int OD, int OH, int OW, int oz, int oy, int ox, void *stream);
 
@@ -804,7 +912,7 @@ extern "C" int l3d_dwpw_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, 
     const char *igemm_max_env = getenv("L3D_DWS_IGEMM_MAX");
     const int igemm_max = (igemm_max_env && igemm_max_env[0]) ? atoi(igemm_max_env) : 1024;
     if (dw_w != nullptr && !has_u && Cin * Cout <= igemm_max) {
-        const int rc = l3d_conv3_tc(x, xn, N, D, H, W, nullptr, 1, dw_w, pw_w, sc_w, t, t_stats, r, r_stats, Cout, stream);
+        const int rc = l3d_conv3_tc(x, xn, N, D, H, W, nullptr, 1, dw_w, pw_w, sc_w, t, t_stats, r, r_stats, Cout, 0, Cout, stream);
         if (rc >= 0) return rc;
     }
     // one size up (64 -> 32 at 24^3): two launches over output-channel halves, each with weights that fit next to the
@@ -817,7 +925,7 @@ extern "C" int l3d_dwpw_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, 
             th.ptr = (char *)t->ptr + (size_t)half * Ch * 2; th.C = Ch;
             if (has_r) { rh = *r; rh.ptr = (char *)r->ptr + (size_t)half * Ch * 2; rh.C = Ch; }
             rc = l3d_conv3_tc(x, xn, N, D, H, W, nullptr, 1, dw_w, pw_w + (size_t)half * Ch * Cin, has_r ? sc_w + (size_t)half * Ch * Cin : nullptr,
-                              &th, t_stats + half * Ch, has_r ? &rh : nullptr, has_r ? r_stats + half * Ch : nullptr, Cout, stream);
+                              &th, t_stats + half * Ch, has_r ? &rh : nullptr, has_r ? r_stats + half * Ch : nullptr, Cout, 0, Ch, stream);
             if (rc < 0 && half == 1) { l3d_set_error("l3d_dwpw_fwd: implicit GEMM accepted one channel half but not the other"); return 3; }
         }
         if (rc >= 0) return rc;
@@ -872,16 +980,62 @@ extern "C" int l3d_dwpw_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, 
 }
 
 extern "C" int l3d_conv3_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int W,
-                             const float *w, int groups, const l3d_act *t, double *t_stats, void *stream) {
+                             const float *w, int groups, const l3d_act *t, double *t_stats,
+                             const float *sc_w, const l3d_act *r, double *r_stats, void *stream) {
     L3D_REQUIRE(!act_null(x) && !act_null(t) && w && t_stats, "l3d_conv3_fwd: null argument");
     const int Cin = x->C, Cout = t->C;
     L3D_REQUIRE(groups >= 1 && Cin % groups == 0 && Cout % groups == 0, "l3d_conv3_fwd: bad groups");
     L3D_REQUIRE(Cout % 8 == 0 && vec4_ok(t), "l3d_conv3_fwd: Cout=%d must be a multiple of 8 and aligned", Cout);
     L3D_REQUIRE(t->dtype == x->dtype, "l3d_conv3_fwd: dtype mismatch");
-    {
-        const int rc = l3d_conv3_tc(x, xn, N, D, H, W, w, groups, nullptr, nullptr, nullptr, t, t_stats, nullptr, nullptr, Cout, stream);
+    const bool has_sc = sc_w != nullptr;
+    if (has_sc) L3D_REQUIRE(!act_null(r) && r_stats && r->C == Cout && r->dtype == x->dtype && vec4_ok(r), "l3d_conv3_fwd: bad shortcut output");
+    const size_t w_bytes = (size_t)27 * Cin * Cout * 2;      // fp16 weight tiles of the whole layer
+    if (w_bytes <= 60 * 1024) {
+        const int rc = l3d_conv3_tc(x, xn, N, D, H, W, w, groups, nullptr, nullptr, sc_w, t, t_stats, r, r_stats, Cout, 0, Cout, stream);
         if (rc >= 0) return rc;
     }
+    // wide layers: the 27 weight tiles of all output channels would crowd the operand buffers out of shared memory, so
+    // the layer runs as several launches over output-channel slices (each re-reads the input; still tensor-core bound)
+    if (x->dtype == L3D_BF16 && Cin % 16 == 0 && Cout % 16 == 0) {
+        for (int Cs : {32, 16}) {
+            if (Cout % Cs != 0 || Cout <= Cs) continue;
+            if (Cs > 16 && (size_t)27 * Cin * Cs * 2 > 60 * 1024) continue;     // leave room for tall operand tiles
+            int rc = 0;
+            for (int c0 = 0; c0 < Cout && rc == 0; c0 += Cs) {
+                l3d_act ts = *t, rs;
+                ts.ptr = (char *)t->ptr + (size_t)c0 * 2; ts.C = Cs;
+                if (has_sc) { rs = *r; rs.ptr = (char *)r->ptr + (size_t)c0 * 2; rs.C = Cs; }
+                rc = l3d_conv3_tc(x, xn, N, D, H, W, w, groups, nullptr, nullptr, has_sc ? sc_w + (size_t)c0 * Cin : nullptr, &ts, t_stats + c0,
+                                  has_sc ? &rs : nullptr, has_sc ? r_stats + c0 : nullptr, Cout, c0, Cout, stream);
+                if (rc < 0 && c0 > 0) { l3d_set_error("l3d_conv3_fwd: implicit GEMM accepted one channel slice but not the next"); return 3; }
+            }
+            if (rc >= 0) return rc;
+        }
+    }
+    if (w_bytes > 60 * 1024) {
+        const int rc = l3d_conv3_tc(x, xn, N, D, H, W, w, groups, nullptr, nullptr, sc_w, t, t_stats, r, r_stats, Cout, 0, Cout, stream);
+        if (rc >= 0) return rc;
+    }
+    if (Cin == 1 && groups == 1 && (Cout == 16 || Cout == 32)) {
+        const int64_t tiles1 = num_tiles(N, D, H, W);
+        const unsigned grid1 = (unsigned)(tiles1 < 148 * 4 ? tiles1 : 148 * 4);
+        const NormDev nd1 = norm_dev(xn);
+        cudaStream_t st1_ = (cudaStream_t)stream;
+#define LAUNCH_C3C1(T, CO)                                                                                               \
+        conv3_c1_kernel<T, CO><<<grid1, NT, 0, st1_>>>((const T *)x->ptr, x->ldc, nd1, N, D, H, W, w, sc_w, (T *)t->ptr, t->ldc, t_stats, \
+                                                       has_sc ? (T *)r->ptr : nullptr, has_sc ? r->ldc : 0, r_stats)
+        L3D_DISPATCH_DTYPE(x->dtype, T, { if (Cout == 16) LAUNCH_C3C1(T, 16); else LAUNCH_C3C1(T, 32); });
+#undef LAUNCH_C3C1
+        l3d_count_launch();
+        l3d_note_kernel("conv3_c1_kernel");
+        L3D_CUDA_OK("l3d_conv3_fwd (Cin=1) launch");
+        return 0;
+    }
+    if (has_sc) {     // generic path: the shortcut is a separate pointwise launch
+        const int rc = l3d_dwpw_fwd(x, xn, N, D, H, W, nullptr, sc_w, nullptr, r, r_stats, nullptr, nullptr, nullptr, stream);
+        if (rc) return rc;
+    }
+    l3d_note_kernel("conv3_fwd_kernel");
     const int CC = (Cout % 32 == 0) ? 32 : (Cout % 16 == 0) ? 16 : 8;
     const size_t smem = sizeof(float) * ((size_t)C3_CK * HZ * HY * HX + 27 * C3_CK * CC + 2 * (size_t)Cin + 2 * (size_t)Cout);
     const int64_t tiles = num_tiles(N, D, H, W);

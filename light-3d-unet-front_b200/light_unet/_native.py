@@ -15,7 +15,7 @@ _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.environ.get("L3D_LIB", os.path.join(_PKG_DIR, "libl3d.so"))
 
 L3D_F32, L3D_BF16 = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class Act(Structure):
@@ -38,7 +38,7 @@ _P = c_void_p
 _SIGS = {
     "l3d_dwpw_fwd": [POINTER(Act), POINTER(Norm), c_int, c_int, c_int, c_int, _P, _P, _P,
                      POINTER(Act), _P, POINTER(Act), _P, POINTER(Act), _P],
-    "l3d_conv3_fwd": [POINTER(Act), POINTER(Norm), c_int, c_int, c_int, c_int, _P, c_int, POINTER(Act), _P, _P],
+    "l3d_conv3_fwd": [POINTER(Act), POINTER(Norm), c_int, c_int, c_int, c_int, _P, c_int, POINTER(Act), _P, _P, POINTER(Act), _P, _P],
     "l3d_merge_fwd": [POINTER(Act), POINTER(Norm), POINTER(Act), POINTER(Norm), c_int, c_int, c_int, c_int, c_float,
                       POINTER(Act), POINTER(Act), _P, _P, c_int, _P, _P, _P],
     "l3d_convt_fwd": [POINTER(Act), c_int, c_int, c_int, c_int, _P, _P, POINTER(Act), c_int, c_int, c_int,

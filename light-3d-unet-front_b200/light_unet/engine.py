@@ -178,11 +178,9 @@ class UNetPlan:
         else:
             w = P[f"{pre}.conv.weight"] if kind == "grouped" else P[f"{pre}.weight"]
             g = self.groups if kind == "grouped" else 1
-            nv.call("l3d_conv3_fwd", x_act, xn, N, D, H, W, nv.ptr(w), g, nv.act(t), nv.ptr(t_stats), st,
-                    algo_bytes=es * nvx * (cin + cout))
-            if sc_w is not None:   # pointwise-only launch for the shortcut
-                nv.call("l3d_dwpw_fwd", x_act, xn, N, D, H, W, None, nv.ptr(sc_w), None, nv.act(r), nv.ptr(r_stats),
-                        nv.act(None), None, nv.act(None), st, algo_bytes=es * nvx * (cin + cout))
+            nv.call("l3d_conv3_fwd", x_act, xn, N, D, H, W, nv.ptr(w), g, nv.act(t), nv.ptr(t_stats),
+                    nv.ptr(sc_w), nv.act(r), nv.ptr(r_stats), st,
+                    algo_bytes=es * nvx * (cin + cout * (2 if sc_w is not None else 1)))
 
     def forward(self, P: Dict[str, torch.Tensor], x_cl: torch.Tensor, training: bool,
                 masks: Optional[List[Optional[torch.Tensor]]] = None,

@@ -37,7 +37,20 @@ def _inputs(N, dims, Cin, seed):
     return x, stats, gamma, beta, a, vox
 
 
-def _run(case, env, launches=1):
+def _expected_launches(case):
+    """Dense / grouped layers whose fp16 weight tiles exceed 60 KB run as output-channel slices (l3d_conv3_fwd)."""
+    kind, _, _, Cin, Cout = case[:5]
+    if kind != "dense" or 27 * Cin * Cout * 2 <= 60 * 1024:
+        return 1
+    for cs in (32, 16):
+        if Cout % cs == 0 and Cout > cs and (cs == 16 or 27 * Cin * cs * 2 <= 60 * 1024):
+            return Cout // cs
+    return 1
+
+
+def _run(case, env, launches=None):
+    if launches is None:
+        launches = _expected_launches(case)
     from light_unet import _native as nv
     kind, N, dims, Cin, Cout, groups, use_norm = case
     D, H, W = dims
@@ -63,7 +76,7 @@ def _run(case, env, launches=1):
         if kind == "dense":
             w = torch.randn(Cout, Cin // groups, 3, 3, 3, generator=g) / np.sqrt(27 * Cin / groups)
             wd = w.to(DEV)
-            nv.call("l3d_conv3_fwd", nv.act(xd), xn, N, D, H, W, nv.ptr(wd), groups, nv.act(t), nv.ptr(t_stats), st)
+            nv.call("l3d_conv3_fwd", nv.act(xd), xn, N, D, H, W, nv.ptr(wd), groups, nv.act(t), nv.ptr(t_stats), None, nv.act(None), None, st)
             ref_t = F.conv3d(a_ncdhw, w, padding=1, groups=groups)
             ref_r, r = None, None
         else:
@@ -133,3 +146,11 @@ def test_conv3_tc_output_channel_halves():
     writing its channel slice of t / r and of the statistics rows."""
     _run(("dws", 2, (16, 17, 24), 64, 32, 1, True), {}, launches=2)
     _run(("dws", 1, (24, 24, 24), 64, 32, 1, False), {}, launches=2)
+
+
+@pytest.mark.parametrize("case,launches", [(("dense", 1, (8, 16, 16), 64, 64, 1, True), 4), (("dense", 1, (6, 16, 8), 32, 64, 1, False), 2),
+                                           (("dense", 1, (5, 12, 9), 128, 128, 1, True), 8), (("dense", 1, (8, 16, 8), 64, 64, 8, True), 4)])
+def test_conv3_tc_wide_layers_in_output_slices(case, launches):
+    """Dense / grouped layers whose 27 weight tiles do not fit shared memory run as several implicit-GEMM launches over
+    output-channel slices (grouped: the slice keeps its absolute channel index for the group lookup)."""
+    _run(case, {}, launches=launches)
