@@ -915,20 +915,28 @@ extern "C" int l3d_dwpw_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, 
         const int rc = l3d_conv3_tc(x, xn, N, D, H, W, nullptr, 1, dw_w, pw_w, sc_w, t, t_stats, r, r_stats, Cout, 0, Cout, stream);
         if (rc >= 0) return rc;
     }
-    // one size up (64 -> 32 at 24^3): two launches over output-channel halves, each with weights that fit next to the
-    // operand buffers -- measured faster than the stencil kernel although the input is read twice
-    if (dw_w != nullptr && !has_u && Cin * Cout <= 2 * igemm_max && Cout % 32 == 0 && D >= 16 && H >= 16 && x->dtype == L3D_BF16) {
-        const int Ch = Cout / 2;
-        int rc = 0;
-        for (int half = 0; half < 2 && rc == 0; ++half) {
-            l3d_act th = *t, rh;
-            th.ptr = (char *)t->ptr + (size_t)half * Ch * 2; th.C = Ch;
-            if (has_r) { rh = *r; rh.ptr = (char *)r->ptr + (size_t)half * Ch * 2; rh.C = Ch; }
-            rc = l3d_conv3_tc(x, xn, N, D, H, W, nullptr, 1, dw_w, pw_w + (size_t)half * Ch * Cin, has_r ? sc_w + (size_t)half * Ch * Cin : nullptr,
-                              &th, t_stats + half * Ch, has_r ? &rh : nullptr, has_r ? r_stats + half * Ch : nullptr, Cout, 0, Ch, stream);
-            if (rc < 0 && half == 1) { l3d_set_error("l3d_dwpw_fwd: implicit GEMM accepted one channel half but not the other"); return 3; }
+    // wider layers: several launches over output-channel slices, each with weights that fit next to the operand buffers
+    // (the input is re-read per slice).  Measured faster than the stencil kernel at 24^3 (64 -> 32: 1.57 -> 1.24 ms for
+    // 325 windows); at 12^3 / 6^3 the 16 x 8-voxel MMA tiles waste too many rows, so small volumes keep the stencil.
+    {
+        const char *md = getenv("L3D_DWS_SLICE_MIN_DIM");
+        const int min_dim = (md && md[0]) ? atoi(md) : 16;
+        if (dw_w != nullptr && !has_u && Cin * Cout > igemm_max && Cin * 16 <= 2 * igemm_max && Cout % 16 == 0 && D >= min_dim && H >= min_dim &&
+            x->dtype == L3D_BF16) {
+            for (int Cs : {32, 16}) {
+                if (Cout % Cs != 0 || Cout <= Cs || Cin * Cs > igemm_max) continue;
+                int rc = 0;
+                for (int c0 = 0; c0 < Cout && rc == 0; c0 += Cs) {
+                    l3d_act th = *t, rh;
+                    th.ptr = (char *)t->ptr + (size_t)c0 * 2; th.C = Cs;
+                    if (has_r) { rh = *r; rh.ptr = (char *)r->ptr + (size_t)c0 * 2; rh.C = Cs; }
+                    rc = l3d_conv3_tc(x, xn, N, D, H, W, nullptr, 1, dw_w, pw_w + (size_t)c0 * Cin, has_r ? sc_w + (size_t)c0 * Cin : nullptr,
+                                      &th, t_stats + c0, has_r ? &rh : nullptr, has_r ? r_stats + c0 : nullptr, Cout, 0, Cs, stream);
+                    if (rc < 0 && c0 > 0) { l3d_set_error("l3d_dwpw_fwd: implicit GEMM accepted one channel slice but not the next"); return 3; }
+                }
+                if (rc >= 0) return rc;
+            }
         }
-        if (rc >= 0) return rc;
     }
     {
         const int rc = l3d_dwpw_fwd_tc(x, xn, N, D, H, W, dw_w, pw_w, sc_w, t, t_stats, r, r_stats, u, stream);
