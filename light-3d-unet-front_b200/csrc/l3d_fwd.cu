@@ -727,20 +727,43 @@ __global__ void __launch_bounds__(NT) dwpw_c1_kernel(
         const bool valid = gz < D && gy < H && gx < W;
         const size_t vox = (((size_t)n * D + gz) * H + gy) * W + gx;
         if (u != nullptr && valid) st1(u + vox * (size_t)ldu, uacc);
-        if (valid) {
+        {
             constexpr int V = VecW<T>::V;
+            // this kernel is a pure write stream: lanes 2j / 2j+1 (x-adjacent voxels) exchange their inputs so that one store
+            // instruction covers both 16-byte halves of a voxel's 32-byte sector (even lane: first vector, odd lane: second)
+            const bool pair_ok = (V == 8) && (COUT % 16 == 0);
+            const float uacc_p = __shfl_xor_sync(0xffffffffu, uacc, 1), xc_p = __shfl_xor_sync(0xffffffffu, xc, 1);
+            const bool valid_p = __shfl_xor_sync(0xffffffffu, valid ? 1 : 0, 1) != 0;
+            const bool odd = (lane & 1) != 0;
 #pragma unroll
             for (int a = 0; a < 2; ++a) {
                 if (a == 1 && sc_w == nullptr) break;
-                const float in = a == 0 ? uacc : xc;
-                T *op = (a == 0 ? t + vox * (size_t)ldt : r + vox * (size_t)ldr);
                 const float *wv = s_w + 27 + a * COUT;
+                const int ld = a == 0 ? ldt : ldr;
+                T *own = (a == 0 ? t + vox * (size_t)ldt : r + vox * (size_t)ldr);
+                if (pair_ok) {
+                    const float in_e = odd ? (a == 0 ? uacc_p : xc_p) : (a == 0 ? uacc : xc);     // even voxel of the pair
+                    const float in_o = odd ? (a == 0 ? uacc : xc) : (a == 0 ? uacc_p : xc_p);     // odd voxel of the pair
+                    T *pe = odd ? own - ld : own, *po = odd ? own : own + ld;
+                    const bool ve = odd ? valid_p : valid, vo = odd ? valid : valid_p;
 #pragma unroll
-                for (int cb = 0; cb < COUT; cb += V) {
-                    float o[V];
+                    for (int cb = 0; cb < COUT; cb += 16) {
+                        const int c = cb + (odd ? 8 : 0);
+                        float oe[V], oo[V];
 #pragma unroll
-                    for (int j = 0; j < V; ++j) o[j] = in * wv[cb + j];
-                    stv(op + cb, o);
+                        for (int j = 0; j < V; ++j) { oe[j] = in_e * wv[c + j]; oo[j] = in_o * wv[c + j]; }
+                        if (ve) stv(pe + c, oe);
+                        if (vo) stv(po + c, oo);
+                    }
+                } else if (valid) {
+                    const float in = a == 0 ? uacc : xc;
+#pragma unroll
+                    for (int cb = 0; cb < COUT; cb += V) {
+                        float o[V];
+#pragma unroll
+                        for (int j = 0; j < V; ++j) o[j] = in * wv[cb + j];
+                        stv(own + cb, o);
+                    }
                 }
             }
         }
