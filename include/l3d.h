@@ -105,6 +105,12 @@ int l3d_convt_fwd(const l3d_act *x, int N, int d, int h, int w_, const float *w,
 
 /* --------------------------------------------------------------- backward -- */
 
+/* The same with a shortcut that is never materialised: r[v][c] = r1_w[c] * x1[v] for a single-channel tensor x1 (the
+ * first block's 1x1x1 shortcut conv of a 1-channel image, unet3d.py:70-71,168); nr holds r's statistics, which
+ * l3d_dwpw_fwd produces even when its r output is {NULL}.  Inference only (the backward pass reads a stored r). */
+int l3d_merge_fwd_rank1(const l3d_act *t2, const l3d_norm *n2, const l3d_act *x1, const float *r1_w, const l3d_norm *nr,
+                        int N, int D, int H, int W, float slope, const l3d_act *out, const l3d_act *pooled, void *stream);
+
 /* Backward of l3d_merge_fwd.  gz = g_out * lrelu'(out) (+ head gradient when head_w given:
  * g_out += g_logit * head_w; g_logit = g_prob * p * (1-p)).  Emits
  *   gz (C channels, raw gradient w.r.t. the pre-activation sum),

@@ -448,9 +448,11 @@ __global__ void __launch_bounds__(NT) conv3_fwd_kernel(
 // -------------------------------------------------------------------------------------------
 // Residual merge (+ optional 2x2x2 max-pool of the result).  One thread = one 2x2x2 cell x one 16-byte channel
 // vector; grid.y = sample, per-(n,c) scale/shift tables in shared memory; all loads of a cell are issued first.
-template <typename T>
+// R1: the shortcut tensor is not materialised -- it is the rank-1 map r[v][c] = r1_w[c] * x[v] of a single-channel
+// tensor x (the first block's 1x1x1 shortcut conv of a 1-channel image): `r` then points at x (1 channel, stride ldr).
+template <typename T, bool R1>
 __global__ void __launch_bounds__(256) merge_fwd_kernel(
-    const T *__restrict__ t2, int ld2, NormDev n2, const T *__restrict__ r, int ldr, NormDev nr,
+    const T *__restrict__ t2, int ld2, NormDev n2, const T *__restrict__ r, int ldr, NormDev nr, const float *__restrict__ r1_w,
     int N, int C, int D, int H, int W, float slope,
     T *__restrict__ out, int ldo, T *__restrict__ pooled, int ldp) {
     constexpr int V = VecW<T>::V;
@@ -460,6 +462,7 @@ __global__ void __launch_bounds__(256) merge_fwd_kernel(
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         norm_scale_shift(n2, N, C, n, c, s_sc2[c], s_sh2[c]);
         norm_scale_shift(nr, N, C, n, c, s_scr[c], s_shr[c]);
+        if (R1) s_scr[c] *= r1_w[c];
     }
     __syncthreads();
     const int CD = (D + 1) / 2, CH = (H + 1) / 2, CW = (W + 1) / 2, CQ = C / V;
@@ -481,6 +484,7 @@ __global__ void __launch_bounds__(256) merge_fwd_kernel(
 #pragma unroll
         for (int half = 0; half < 2; ++half) {        // one z-plane of the cell at a time: 8 raw loads in flight
             uint4 ra[4], rb[4];
+            float xr[4];
             bool ok[4];
             size_t vox[4];
             const int z = cz * 2 + half;
@@ -489,14 +493,22 @@ __global__ void __launch_bounds__(256) merge_fwd_kernel(
                 const int y = cy * 2 + (k >> 1), xx = cx * 2 + (k & 1);
                 ok[k] = z < D && y < H && xx < W;
                 vox[k] = (((size_t)n * D + z) * H + y) * W + xx;
-                if (ok[k]) { ra[k] = ldraw(t2 + vox[k] * ld2 + c); rb[k] = ldraw(r + vox[k] * ldr + c); }
+                if (ok[k]) {
+                    ra[k] = ldraw(t2 + vox[k] * ld2 + c);
+                    if (R1) xr[k] = ld1(r + vox[k] * ldr); else rb[k] = ldraw(r + vox[k] * ldr + c);
+                }
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (ok[k]) {
                     float a[V], b[V], o[V];
                     cvt_raw(t2, ra[k], a);
-                    cvt_raw(t2, rb[k], b);
+                    if (R1) {
+#pragma unroll
+                        for (int j = 0; j < V; ++j) b[j] = xr[k];
+                    } else {
+                        cvt_raw(t2, rb[k], b);
+                    }
 #pragma unroll
                     for (int j = 0; j < V; ++j) {
                         o[j] = lrelu(fmaf(a[j], sc2[j], fmaf(b[j], scr[j], sh2[j])), slope);
@@ -737,7 +749,7 @@ __global__ void __launch_bounds__(NT) dwpw_c1_kernel(
             const bool odd = (lane & 1) != 0;
 #pragma unroll
             for (int a = 0; a < 2; ++a) {
-                if (a == 1 && sc_w == nullptr) break;
+                if (a == 1 && (sc_w == nullptr || r == nullptr)) break;     // r == NULL: statistics only
                 const float *wv = s_w + 27 + a * COUT;
                 const int ld = a == 0 ? ldt : ldr;
                 T *own = (a == 0 ? t + vox * (size_t)ldt : r + vox * (size_t)ldr);
@@ -924,7 +936,10 @@ extern "C" int l3d_dwpw_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, 
     L3D_REQUIRE(t->dtype == x->dtype, "l3d_dwpw_fwd: dtype mismatch");
     L3D_REQUIRE(vec4_ok(t), "l3d_dwpw_fwd: output view must be 4-channel aligned");
     const bool has_r = sc_w != nullptr;
-    if (has_r) {
+    // Cin == 1: the shortcut output may be left out (r = {NULL}) -- its statistics are still produced (analytically), for
+    // consumers that evaluate the rank-1 shortcut on the fly (l3d_merge_fwd_rank1)
+    const bool r_stats_only = has_r && act_null(r) && Cin == 1 && dw_w != nullptr && r_stats != nullptr;
+    if (has_r && !r_stats_only) {
         L3D_REQUIRE(!act_null(r) && r_stats && r->C == Cout && r->dtype == x->dtype && vec4_ok(r), "l3d_dwpw_fwd: bad shortcut output");
     }
     const bool has_u = !act_null(u);
@@ -965,6 +980,7 @@ extern "C" int l3d_dwpw_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, 
         const int rc = l3d_dwpw_fwd_tc(x, xn, N, D, H, W, dw_w, pw_w, sc_w, t, t_stats, r, r_stats, u, stream);
         if (rc >= 0) return rc;
     }
+    L3D_REQUIRE(!r_stats_only || Cout == 16 || Cout == 32, "l3d_dwpw_fwd: statistics-only shortcut needs Cout of 16 or 32");
     if (Cin == 1 && dw_w != nullptr && (Cout == 16 || Cout == 32)) {
         const int64_t tiles1 = num_tiles(N, D, H, W);
         const unsigned grid1 = (unsigned)(tiles1 < 148 * 8 ? tiles1 : 148 * 8);
@@ -972,8 +988,8 @@ extern "C" int l3d_dwpw_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, 
         cudaStream_t st1_ = (cudaStream_t)stream;
 #define LAUNCH_C1(T, CO)                                                                                              \
         dwpw_c1_kernel<T, CO><<<grid1, NT, 0, st1_>>>((const T *)x->ptr, x->ldc, nd1, N, D, H, W, dw_w, pw_w, sc_w,      \
-                                                      (T *)t->ptr, t->ldc, t_stats, has_r ? (T *)r->ptr : nullptr,      \
-                                                      has_r ? r->ldc : 0, r_stats, has_u ? (T *)u->ptr : nullptr, has_u ? u->ldc : 0)
+                                                      (T *)t->ptr, t->ldc, t_stats, (has_r && !r_stats_only) ? (T *)r->ptr : nullptr, \
+                                                      (has_r && !r_stats_only) ? r->ldc : 0, r_stats, has_u ? (T *)u->ptr : nullptr, has_u ? u->ldc : 0)
         L3D_DISPATCH_DTYPE(x->dtype, T, { if (Cout == 16) LAUNCH_C1(T, 16); else LAUNCH_C1(T, 32); });
 #undef LAUNCH_C1
         l3d_count_launch();
@@ -1148,13 +1164,40 @@ extern "C" int l3d_merge_fwd(const l3d_act *t2, const l3d_norm *n2, const l3d_ac
         if (blocks > cap) blocks = cap;
         dim3 grid((unsigned)blocks, (unsigned)N);
         L3D_DISPATCH_DTYPE(t2->dtype, T, {
-            merge_fwd_kernel<T><<<grid, 256, sizeof(float) * 4 * C, st>>>((const T *)t2->ptr, t2->ldc, d2, (const T *)r->ptr, r->ldc, dr, N, C, D, H, W, slope,
+            merge_fwd_kernel<T, false><<<grid, 256, sizeof(float) * 4 * C, st>>>((const T *)t2->ptr, t2->ldc, d2, (const T *)r->ptr, r->ldc, dr, nullptr, N, C, D, H, W, slope,
                                                                    has_out ? (T *)out->ptr : nullptr, has_out ? out->ldc : 0,
                                                                    has_pool ? (T *)pooled->ptr : nullptr, has_pool ? pooled->ldc : 0);
         });
     }
     l3d_count_launch();
     L3D_CUDA_OK("l3d_merge_fwd launch");
+    return 0;
+}
+
+extern "C" int l3d_merge_fwd_rank1(const l3d_act *t2, const l3d_norm *n2, const l3d_act *x1, const float *r1_w, const l3d_norm *nr,
+                                   int N, int D, int H, int W, float slope, const l3d_act *out, const l3d_act *pooled, void *stream) {
+    L3D_REQUIRE(!act_null(t2) && !act_null(x1) && r1_w, "l3d_merge_fwd_rank1: null argument");
+    const int C = t2->C;
+    L3D_REQUIRE(x1->C == 1 && x1->dtype == t2->dtype, "l3d_merge_fwd_rank1: x1 must be a single-channel view of the same dtype");
+    const bool has_out = !act_null(out), has_pool = !act_null(pooled);
+    L3D_REQUIRE(has_out || has_pool, "l3d_merge_fwd_rank1: nothing to write");
+    const int V = t2->dtype == L3D_F32 ? 4 : 8;
+    auto vec_ok = [V](const l3d_act *a) { return a->C % V == 0 && a->ldc % V == 0 && (reinterpret_cast<uintptr_t>(a->ptr) % 16) == 0; };
+    L3D_REQUIRE(vec_ok(t2) && (!has_out || (vec_ok(out) && out->C == C && out->dtype == t2->dtype)) &&
+                (!has_pool || (vec_ok(pooled) && pooled->C == C && pooled->dtype == t2->dtype)), "l3d_merge_fwd_rank1: bad views");
+    const NormDev d2 = norm_dev(n2), dr = norm_dev(nr);
+    const size_t total = (size_t)((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2) * (C / V);
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (148 * 32 + N - 1) / N;
+    if (blocks > cap) blocks = cap;
+    dim3 grid((unsigned)blocks, (unsigned)N);
+    L3D_DISPATCH_DTYPE(t2->dtype, T, {
+        merge_fwd_kernel<T, true><<<grid, 256, sizeof(float) * 4 * C, (cudaStream_t)stream>>>(
+            (const T *)t2->ptr, t2->ldc, d2, (const T *)x1->ptr, x1->ldc, dr, r1_w, N, C, D, H, W, slope,
+            has_out ? (T *)out->ptr : nullptr, has_out ? out->ldc : 0, has_pool ? (T *)pooled->ptr : nullptr, has_pool ? pooled->ldc : 0);
+    });
+    l3d_count_launch();
+    L3D_CUDA_OK("l3d_merge_fwd_rank1 launch");
     return 0;
 }
 

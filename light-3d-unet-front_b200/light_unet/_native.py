@@ -38,6 +38,8 @@ _P = c_void_p
 _SIGS = {
     "l3d_dwpw_fwd": [POINTER(Act), POINTER(Norm), c_int, c_int, c_int, c_int, _P, _P, _P,
                      POINTER(Act), _P, POINTER(Act), _P, POINTER(Act), _P],
+    "l3d_merge_fwd_rank1": [POINTER(Act), POINTER(Norm), POINTER(Act), _P, POINTER(Norm), c_int, c_int, c_int, c_int, c_float,
+                            POINTER(Act), POINTER(Act), _P],
     "l3d_conv3_fwd": [POINTER(Act), POINTER(Norm), c_int, c_int, c_int, c_int, _P, c_int, POINTER(Act), _P, _P, POINTER(Act), _P, _P],
     "l3d_merge_fwd": [POINTER(Act), POINTER(Norm), POINTER(Act), POINTER(Norm), c_int, c_int, c_int, c_int, c_float,
                       POINTER(Act), POINTER(Act), _P, _P, c_int, _P, _P, _P],

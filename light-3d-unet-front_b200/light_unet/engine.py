@@ -174,7 +174,7 @@ class UNetPlan:
             nv.call("l3d_dwpw_fwd", x_act, xn, N, D, H, W, nv.ptr(P[f"{pre}.depthwise.weight"]),
                     nv.ptr(P[f"{pre}.pointwise.weight"]), nv.ptr(sc_w), nv.act(t), nv.ptr(t_stats),
                     nv.act(r), nv.ptr(r_stats), nv.act(u), st,
-                    algo_bytes=es * nvx * (cin + cout * (2 if sc_w is not None else 1) + (cin if u is not None else 0)))
+                    algo_bytes=es * nvx * (cin + cout * (2 if (sc_w is not None and r is not None) else 1) + (cin if u is not None else 0)))
         else:
             w = P[f"{pre}.conv.weight"] if kind == "grouped" else P[f"{pre}.weight"]
             g = self.groups if kind == "grouped" else 1
@@ -226,8 +226,11 @@ class UNetPlan:
             has_sc = b.cin != b.cout
             s1, s2, sr = (ws.stats_of(b.name, k, b.cout) for k in range(3))
             sc_w = P[f"{b.prefix}.shortcut.0.weight"] if has_sc else None
+            # inference, first block of a 1-channel image: its 1x1x1 shortcut r[v][c] = w[c] * x[v] is never written -- the
+            # conv kernel still produces r's statistics and the merge evaluates r on the fly (64 B / voxel less traffic)
+            rank1 = (not training) and has_sc and b.cin == 1 and b.kind1 == "dws" and b.cout in (16, 32) and b.name == "init_conv"
             # conv1 (+ shortcut conv) on the block input
-            self._conv(P, b, 1, x_act, ident, N, dims, buf["t1"], s1, sc_w, buf.get("r"), sr if has_sc else None,
+            self._conv(P, b, 1, x_act, ident, N, dims, buf["t1"], s1, sc_w, None if rank1 else buf.get("r"), sr if has_sc else None,
                        buf.get("u1"), st)
             # conv2 on lrelu(IN1(t1)) * dropout-mask, applied on load
             n1 = nv.norm(s1, P[f"{b.prefix}.norm1.weight"], P[f"{b.prefix}.norm1.bias"], mask, IN_EPS, LEAKY_SLOPE, vox)
@@ -243,9 +246,14 @@ class UNetPlan:
             if b.name in ("init_conv", "down1", "down2"):
                 cat = ws.cat[b.level]
                 out_t, out_off = cat, b.cout                      # upper half of the concat buffer
-                nv.call("l3d_merge_fwd", nv.act(buf["t2"]), n2, r_act, nr, N, *dims, LEAKY_SLOPE,
-                        nv.act(cat, b.cout, b.cout), nv.act(ws.pooled[b.level]), None, None, 0, None, None, st,
-                        algo_bytes=3 * mbytes + mbytes // 8)
+                if rank1:
+                    nv.call("l3d_merge_fwd_rank1", nv.act(buf["t2"]), n2, x_act, nv.ptr(sc_w), nr, N, *dims, LEAKY_SLOPE,
+                            nv.act(cat, b.cout, b.cout), nv.act(ws.pooled[b.level]), st,
+                            algo_bytes=2 * mbytes + mbytes // 8 + mbytes // b.cout)
+                else:
+                    nv.call("l3d_merge_fwd", nv.act(buf["t2"]), n2, r_act, nr, N, *dims, LEAKY_SLOPE,
+                            nv.act(cat, b.cout, b.cout), nv.act(ws.pooled[b.level]), None, None, 0, None, None, st,
+                            algo_bytes=3 * mbytes + mbytes // 8)
                 cur, cur_off, cur_C = ws.pooled[b.level], 0, b.cout
             elif b.name == "up3":
                 out = buf.get("out")
