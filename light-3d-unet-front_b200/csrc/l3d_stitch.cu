@@ -83,10 +83,23 @@ __device__ __forceinline__ int32_t uf_find(const int32_t *parent, int32_t i) {
     while (p != i) { i = p; p = __ldcg(parent + i); }
     return i;
 }
+// find with path halving: every visited node is re-pointed at its grandparent (atomicMin keeps the links monotone
+// under concurrent unions: a node only ever points at a smaller index of its own set), so the long row-over-row chains of
+// a large component collapse while the merge pass is still running
+__device__ __forceinline__ int32_t uf_find_halving(int32_t *parent, int32_t i) {
+    int32_t p = __ldcg(parent + i);
+    while (p != i) {
+        const int32_t gp = __ldcg(parent + p);
+        if (gp != p) atomicMin(&parent[i], gp);
+        i = p;
+        p = gp;
+    }
+    return i;
+}
 __device__ __forceinline__ void uf_union(int32_t *parent, int32_t a, int32_t b) {
     while (true) {
-        a = uf_find(parent, a);
-        b = uf_find(parent, b);
+        a = uf_find_halving(parent, a);
+        b = uf_find_halving(parent, b);
         if (a == b) return;
         if (a < b) { const int32_t t = a; a = b; b = t; }   // a > b: hook a under b
         const int32_t old = atomicMin(&parent[a], b);
