@@ -218,3 +218,32 @@ def test_inferencer_end_to_end(tmp_path):
     assert boxes2 == bbox_ref.extract_bboxes(out.numpy(), 0.5, 0.5, (4.0, 4.0, 4.0), 3)
     with pytest.raises(ValueError):
         inf.infer_volume(vol, threshold=0.5, prob_out=torch.empty(3, 3, 3))
+
+
+def test_full_size_volume_properties(tmp_path):
+    """BASELINE configs[2] at full size (128x128x320, 48^3 windows, 325 of them): size-independent properties.
+    (1) window-batch invariance -- InstanceNorm is per sample, so one batch of 325 windows and batches of 13 agree up to
+    bf16 rounding flips caused by the atomics' summation order; (2) the stitched map is a convex combination of window
+    predictions: inside [min, max] of the per-window probabilities, i.e. (0, 1); (3) boxes are bit-exact: exactly what the
+    reference algorithm extracts from the SAME probability map."""
+    from light_unet.core.inferencer import Inferencer
+    from light_unet.utils import sliding_window_device
+    cfg = unet_ref.UNetCfg(dropout_p=0.0)
+    sd_np = synth.synth_state_dict(unet_ref.param_shapes(cfg), 3)
+    ckpt = tmp_path / "m.pth"
+    torch.save({"epoch": 0, "model_state_dict": unet_ref.to_torch(sd_np), "best_epoch": 0, "best_metric": 0.0}, ckpt)
+    config = {"model": {"output_channels": 1, "start_channels": 16, "encoder_channels": [16, 32, 64, 128],
+                        "use_depthwise_separable": True, "use_grouped_conv": True, "groups": 8},
+              "output": {"prob_maps_dir": str(tmp_path / "prob"), "bboxes_dir": str(tmp_path / "bbox")},
+              "data": {"patch_size": [48, 48, 48], "bbox_expansion_voxels": 3, "volume_threshold": {"inference_cc": 0.5}},
+              "validation": {"default_threshold": 0.3}}
+    inf = Inferencer(config, str(ckpt))
+    vol = torch.from_numpy(synth.synth_volume((128, 128, 320), seed=42, n_blobs=6)).to(DEV)
+    p_all, _ = sliding_window_device(vol, inf.model, (48, 48, 48), 0.5, True, window_batch=325)
+    p_13, _ = sliding_window_device(vol, inf.model, (48, 48, 48), 0.5, True, window_batch=13)
+    # measured on B200: max 2.2e-2 (isolated bf16 rounding flips amplified by the later norms), mean 4e-4
+    assert float((p_all - p_13).abs().max()) < 5e-2 and float((p_all - p_13).abs().mean()) < 1e-3
+    assert 0.0 < float(p_all.min()) and float(p_all.max()) < 1.0
+    prob, boxes = inf.infer_volume(vol, threshold=0.3)
+    assert prob.shape == (128, 128, 320) and prob.dtype == np.float32
+    assert boxes == bbox_ref.extract_bboxes(prob, 0.3, 0.5, (4.0, 4.0, 4.0), 3)
