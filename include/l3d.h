@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define L3D_ABI_VERSION 2
+#define L3D_ABI_VERSION 3
 
 enum { L3D_F32 = 0, L3D_BF16 = 1 };
 
@@ -78,6 +78,22 @@ int l3d_dwpw_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int 
                  const float *dw_w, const float *pw_w, const float *sc_w,
                  const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats,
                  const l3d_act *u, void *stream);
+
+/* Depthwise stage alone of the first conv of a single-channel image (DepthwiseSeparableConv3d with in_channels = 1,
+ * unet3d.py:168,209): u[v] = (dw * act(x))[v] as one fp32 channel [N][D][H][W], plus the analytic InstanceNorm statistics
+ * of t[v][c] = pw_w[c] * u[v] (the conv's output, unet3d.py:22-23) and, when sc_w is given, of the block's shortcut
+ * r[v][c] = sc_w[c] * x[v] (unet3d.py:70-71) -- neither t nor r is written.  Inference only.  The stats buffers must be
+ * zeroed by the caller. */
+int l3d_dw_c1_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int W,
+                  const float *dw_w, const float *pw_w, const float *sc_w, int Cout,
+                  float *u, double *t_stats, double *r_stats, void *stream);
+
+/* l3d_dwpw_fwd on an input that is never materialised: x[v][c] = r1_w[c] * u[v] (Cin = 16 channels) with u from
+ * l3d_dw_c1_fwd and xn the norm of that rank-1 tensor (its statistics come from l3d_dw_c1_fwd).  Replaces the second
+ * DepthwiseSeparableConv3d of the first block (unet3d.py:55-63,82-86) without the 16-channel intermediate ever touching
+ * HBM.  bf16 output, W % 4 == 0; returns an error otherwise (the caller then uses l3d_dwpw_fwd twice). */
+int l3d_dwpw_fwd_rank1(const float *u, const float *r1_w, int Cin, const l3d_norm *xn, int N, int D, int H, int W,
+                       const float *dw_w, const float *pw_w, const l3d_act *t, double *t_stats, void *stream);
 
 /* Dense / grouped 3x3x3 convolution, pad 1, no bias (nn.Conv3d at unet3d.py:30,49,60).
  * w: [Cout][Cin/groups][3][3][3].  Optionally also the block's 1x1x1 shortcut conv on the same activated input

@@ -54,7 +54,9 @@ struct C3Args {
     int co0, cout_total;     // dense / grouped weights: first output channel of this launch and the layer's full Cout
     int stat_ld;             // channels per (n) row of the statistics arrays (>= Cout: the launch may own a channel slice)
     int tmem_cols, nraw, nsets, merge, merged_cx, dbg;
+    const float *r1_w;       // rank-1 input (template R1): x[v][c] = r1_w[c] * u[v], u = single-channel fp32 tensor behind the tensor map
 };
+constexpr int R1_BOXW = 16, R1_X0 = 4;                   // rank-1 TMA box: x0 - 4 .. x0 + 11, so that the box starts on a 16-byte boundary
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -84,7 +86,11 @@ __device__ __forceinline__ void worker_bar_n() { asm volatile("bar.sync 1, %0;" 
 // in consecutive TMEM column blocks, and the weight tile of (chunk, dy, dx) holds the rows [dz=2 | dz=1 | dz=0], so
 // input plane zi updates output planes zi-2, zi-1, zi with a single N = 3*Cout MMA.  9*(TZ+2) MMAs per 16-channel
 // chunk instead of 27*TZ.
-template <int TZ, bool MERGE, int NWARPS>
+//
+// R1 (rank-1 input): the 16-channel input is x[v][c] = r1_w[c] * u[v] with a single-channel fp32 tensor u (the first
+// block of a 1-channel image: conv1's pointwise stage has K = 1, unet3d.py:168,209), so only u is staged -- the TMA box is
+// [z][y][16] fp32 -- and the activation pass evaluates lrelu(u * (scale_c * r1_w[c]) + shift_c) for the 16 channels.
+template <int TZ, bool MERGE, int NWARPS, bool R1 = false>
 __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 : 2)) conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, C3Args A) {
     using G = Geo<TZ>;
     constexpr int NW = NWARPS * 32, NT = NW + 32;          // worker warps + 1 issuer warp
@@ -192,8 +198,9 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
             if (pf_item >= n_items) return;
             const int rb = pf_item % nraw;
             if (tc::elect_one()) {
-                tc::mbar_expect_tx(&s_tma_full[rb], G::RAW_BYTES);
-                if (A.merged_cx) tc::tma_load_4d(s_raw + (size_t)rb * G::RAW_BYTES, &tmap, &s_tma_full[rb], (pf_x0 - 1) * CK, pf_y0 - 1, pf_z0 - 1, pf_n);
+                tc::mbar_expect_tx(&s_tma_full[rb], R1 ? G::HZ * HY * R1_BOXW * 4 : G::RAW_BYTES);
+                if (R1) tc::tma_load_4d(s_raw + (size_t)rb * G::RAW_BYTES, &tmap, &s_tma_full[rb], pf_x0 - R1_X0, pf_y0 - 1, pf_z0 - 1, pf_n);
+                else if (A.merged_cx) tc::tma_load_4d(s_raw + (size_t)rb * G::RAW_BYTES, &tmap, &s_tma_full[rb], (pf_x0 - 1) * CK, pf_y0 - 1, pf_z0 - 1, pf_n);
                 else tc::tma_load_5d(s_raw + (size_t)rb * G::RAW_BYTES, &tmap, &s_tma_full[rb], pf_ch * CK, pf_x0 - 1, pf_y0 - 1, pf_z0 - 1, pf_n);
             }
             ++pf_item;
@@ -376,6 +383,7 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
                 for (int cc = tid; cc < Cin; cc += NW) {
                     float sc, sh;
                     norm_scale_shift(A.xn, A.N, Cin, n, cc, sc, sh);
+                    if (R1) sc *= A.r1_w[cc];
                     s_scale[cc] = sc; s_shift[cc] = sh;
                 }
                 worker_bar();
@@ -412,13 +420,22 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
 #pragma unroll
                 for (int k0 = 0; k0 < ACT_PER_THREAD; k0 += ACT_BATCH) {
                     uint4 rw[ACT_BATCH];
+                    float ru[ACT_BATCH];
 #pragma unroll
                     for (int kk = 0; kk < ACT_BATCH; ++kk) {
                         const int k = k0 + kk;
                         if (k < ACT_PER_THREAD) {
                             const int item = tid + k * NW;
                             rw[kk] = make_uint4(0u, 0u, 0u, 0u);
-                            if ((k + 1) * NW <= G::ACT_ITEMS || item < G::ACT_ITEMS) rw[kk] = *reinterpret_cast<const uint4 *>(Rb + (size_t)item * 16);
+                            ru[kk] = 0.f;
+                            if ((k + 1) * NW <= G::ACT_ITEMS || item < G::ACT_ITEMS) {
+                                if (R1) {
+                                    const uint32_t ai = act_item[k];
+                                    ru[kk] = reinterpret_cast<const float *>(Rb)[(((ai >> 16) * HY + ((ai >> 8) & 255)) * R1_BOXW) + (ai & 255) + (R1_X0 - 1)];
+                                } else {
+                                    rw[kk] = *reinterpret_cast<const uint4 *>(Rb + (size_t)item * 16);
+                                }
+                            }
                         }
                     }
 #pragma unroll
@@ -431,12 +448,17 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
                                 const int hx = ai & 255, hy = (ai >> 8) & 255, hz = ai >> 16;
                                 const uint4 r4 = rw[kk];
                                 float f[8];
-                                f[0] = __uint_as_float(r4.x << 16); f[1] = __uint_as_float(r4.x & 0xffff0000u);
-                                f[2] = __uint_as_float(r4.y << 16); f[3] = __uint_as_float(r4.y & 0xffff0000u);
-                                f[4] = __uint_as_float(r4.z << 16); f[5] = __uint_as_float(r4.z & 0xffff0000u);
-                                f[6] = __uint_as_float(r4.w << 16); f[7] = __uint_as_float(r4.w & 0xffff0000u);
+                                if (R1) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) f[j] = ru[kk];
+                                } else {
+                                    f[0] = __uint_as_float(r4.x << 16); f[1] = __uint_as_float(r4.x & 0xffff0000u);
+                                    f[2] = __uint_as_float(r4.y << 16); f[3] = __uint_as_float(r4.y & 0xffff0000u);
+                                    f[4] = __uint_as_float(r4.z << 16); f[5] = __uint_as_float(r4.z & 0xffff0000u);
+                                    f[6] = __uint_as_float(r4.w << 16); f[7] = __uint_as_float(r4.w & 0xffff0000u);
+                                }
                                 uint4 o;
-                                if (ident) {        // already-activated input (a block's first conv): bf16 -> fp16 only
+                                if (!R1 && ident) {        // already-activated input (a block's first conv): bf16 -> fp16 only
                                     o = make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]), pack_f16x2(f[6], f[7]));
                                 } else {
                                     f[0] = fmaf(f[0], sc0.x, sh0.x); f[1] = fmaf(f[1], sc0.y, sh0.y); f[2] = fmaf(f[2], sc0.z, sh0.z); f[3] = fmaf(f[3], sc0.w, sh0.w);
@@ -507,11 +529,24 @@ extern "C" int l3d_conv3_debug_read(long long *host, int n) {
 
 // Implicit-GEMM 3x3x3 conv on tcgen05.  Exactly one of {w} / {dw_w, pw_w} is given.  Returns -1 when the path
 // does not apply (the caller falls back to another kernel).
+// r1_w != NULL: rank-1 input -- x describes the virtual 16-channel tensor x[v][c] = r1_w[c] * u[v] and x->ptr is the
+// single-channel fp32 tensor u.
+int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int W,
+                    const float *w, int groups, const float *dw_w, const float *pw_w, const float *sc_w,
+                    const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats, int stat_ld, int co0, int cout_total,
+                    const float *r1_w, void *stream);
 int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int W,
                  const float *w, int groups, const float *dw_w, const float *pw_w, const float *sc_w,
                  const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats, int stat_ld, int co0, int cout_total,
                  void *stream) {
+    return l3d_conv3_tc_ex(x, xn, N, D, H, W, w, groups, dw_w, pw_w, sc_w, t, t_stats, r, r_stats, stat_ld, co0, cout_total, nullptr, stream);
+}
+int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int W,
+                    const float *w, int groups, const float *dw_w, const float *pw_w, const float *sc_w,
+                    const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats, int stat_ld, int co0, int cout_total,
+                    const float *r1_w, void *stream) {
     static int disabled = -1;
+    const bool rank1 = r1_w != nullptr;
     if (disabled < 0) { const char *e = getenv("L3D_NO_IGEMM"); disabled = (e && e[0] == '1') ? 1 : 0; }
     if (disabled) return -1;
     const int Cin = x->C, Cout = t->C;
@@ -521,7 +556,8 @@ int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int 
     auto aligned = [](const l3d_act *a, int mult) {
         return (a->ldc % mult == 0) && (reinterpret_cast<uintptr_t>(a->ptr) % (2 * mult) == 0);
     };
-    if (!aligned(x, 8) || !aligned(t, 8) || (has_sc && (act_null(r) || !aligned(r, 8)))) return -1;
+    if (rank1 && (Cin != CK || W % 4 != 0 || reinterpret_cast<uintptr_t>(x->ptr) % 16 != 0 || 3 * Cout > 256)) return -1;
+    if ((!rank1 && !aligned(x, 8)) || !aligned(t, 8) || (has_sc && (act_null(r) || !aligned(r, 8)))) return -1;
     // ---- tile height: the tallest tile (fewest halo planes and MMAs per voxel) whose accumulators fit TMEM and whose
     // buffers fit shared memory; two accumulator sets (epilogue of tile T under the MMAs of tile T+1) when they fit
     const int force_tz = env_int("L3D_C3_TZ", 0), force_nraw = env_int("L3D_C3_NRAW", 0), force_sets = env_int("L3D_C3_SETS", 0);   // tuning / test knobs
@@ -558,9 +594,17 @@ int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int 
     // TMA moves one request per innermost box row, and a 16-channel voxel is only 32 B: when the view is a whole
     // 16-channel tensor the (C, W) axes are contiguous and merge into one axis, so a box row is a 320-B x-row
     // (10 voxels) instead of ten 32-B rows (measured: the 5-D box is TMA-issue bound).
-    const bool merged_cx = Cin == CK && x->ldc == CK && env_int("L3D_C3_NOMERGECX", 0) == 0;
+    const bool merged_cx = !rank1 && Cin == CK && x->ldc == CK && env_int("L3D_C3_NOMERGECX", 0) == 0;
     CUtensorMap tmap;
-    if (merged_cx) {
+    if (rank1) {
+        const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+        const cuuint64_t rowb = (cuuint64_t)W * 4;
+        const cuuint64_t strides[3] = {rowb, (cuuint64_t)H * rowb, (cuuint64_t)D * H * rowb};
+        const cuuint32_t box[4] = {R1_BOXW, HY, (cuuint32_t)(TZ + 2), 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        if (l3d_encode_tiled(&tmap, (int)CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x->ptr, (const unsigned long long *)dims,
+                             (const unsigned long long *)strides, (const unsigned *)box, (const unsigned *)estr)) return 3;
+    } else if (merged_cx) {
         const cuuint64_t dims[4] = {(cuuint64_t)W * CK, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
         const cuuint64_t rowb = (cuuint64_t)W * CK * 2;
         const cuuint64_t strides[3] = {rowb, (cuuint64_t)H * rowb, (cuuint64_t)D * H * rowb};
@@ -586,6 +630,7 @@ int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int 
     A.stat_ld = stat_ld > 0 ? stat_ld : Cout;
     A.co0 = co0; A.cout_total = cout_total > 0 ? cout_total : Cout;
     A.tmem_cols = cols; A.nraw = nraw; A.nsets = nsets; A.merged_cx = merged_cx ? 1 : 0; A.dbg = env_int("L3D_C3_DEBUG_SKIP", 0);
+    A.r1_w = r1_w;
     A.merge = (3 * Cout <= 256 && env_int("L3D_C3_NOMERGE", 0) == 0) ? 1 : 0;
     int occ = (int)((227 * 1024) / (smem + 2048));
     if (occ > 3) occ = 3;
@@ -596,16 +641,17 @@ int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     long long grid = (long long)sms * occ;
     if (grid > tiles) grid = tiles;
-#define L3D_C3_LAUNCH(TZV, MG, NWV)                                                                                                 \
+#define L3D_C3_LAUNCH_R(TZV, MG, NWV, R1V)                                                                                          \
     do {                                                                                                                    \
         static bool attr_set = false;                                                                                       \
         if (!attr_set) {                                                                                                    \
-            cudaError_t e = cudaFuncSetAttribute(conv3_tc_kernel<TZV, MG, NWV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
+            cudaError_t e = cudaFuncSetAttribute(conv3_tc_kernel<TZV, MG, NWV, R1V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
             if (e != cudaSuccess) { l3d_set_error("conv3_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 3; } \
             attr_set = true;                                                                                                \
         }                                                                                                                   \
-        conv3_tc_kernel<TZV, MG, NWV><<<(unsigned)grid, NWV * 32 + 32, smem, (cudaStream_t)stream>>>(tmap, A);                \
+        conv3_tc_kernel<TZV, MG, NWV, R1V><<<(unsigned)grid, NWV * 32 + 32, smem, (cudaStream_t)stream>>>(tmap, A);          \
     } while (0)
+#define L3D_C3_LAUNCH(TZV, MG, NWV) L3D_C3_LAUNCH_R(TZV, MG, NWV, false)
 #define L3D_C3_TZ(MG, NWV)                                \
     switch (TZ) {                                         \
         case 8: L3D_C3_LAUNCH(8, MG, NWV); break;         \
@@ -615,10 +661,29 @@ int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int 
     }
     // 12 worker warps (3 per scheduler) hide the latency of the activation pass and the epilogue when one CTA owns the SM
     const int nwarps = env_int("L3D_C3_WARPS", occ == 1 ? 12 : 8);
+    if (rank1) {
+        // merged MMAs only (3 * Cout <= 256 checked above)
+        if (nwarps == 12) {
+            switch (TZ) {
+                case 8: L3D_C3_LAUNCH_R(8, true, 12, true); break;
+                case 6: L3D_C3_LAUNCH_R(6, true, 12, true); break;
+                case 4: L3D_C3_LAUNCH_R(4, true, 12, true); break;
+                default: L3D_C3_LAUNCH_R(2, true, 12, true); break;
+            }
+        } else {
+            switch (TZ) {
+                case 8: L3D_C3_LAUNCH_R(8, true, 8, true); break;
+                case 6: L3D_C3_LAUNCH_R(6, true, 8, true); break;
+                case 4: L3D_C3_LAUNCH_R(4, true, 8, true); break;
+                default: L3D_C3_LAUNCH_R(2, true, 8, true); break;
+            }
+        }
+    } else
     if (A.merge) { if (nwarps == 12) { L3D_C3_TZ(true, 12) } else { L3D_C3_TZ(true, 8) } }
     else         { if (nwarps == 12) { L3D_C3_TZ(false, 12) } else { L3D_C3_TZ(false, 8) } }
 #undef L3D_C3_TZ
 #undef L3D_C3_LAUNCH
+#undef L3D_C3_LAUNCH_R
     l3d_count_launch();
     l3d_note_kernel("conv3_tc_kernel");
     L3D_CUDA_OK("l3d_conv3 (tcgen05 implicit GEMM) launch");

@@ -788,6 +788,183 @@ __global__ void __launch_bounds__(NT) dwpw_c1_kernel(
     flush(cur_n);
 }
 
+// Depthwise stage alone of the single-input-channel first conv: u = dw * act(x) as one fp32 channel, plus the analytic
+// statistics of t[v][co] = pw[co] * u[v] and r[v][co] = sc[co] * x[v] (neither tensor is written).  For consumers that
+// evaluate the rank-1 pointwise stage on the fly (l3d_dwpw_fwd_rank1, l3d_merge_fwd_rank1): 4 B / voxel instead of 2 * Cout.
+// thread = a z-column of ZC1 output voxels at one (y, x); lanes run along the flattened (y, x) plane, so every load
+// and the store are coalesced; each input plane is loaded once (9 values) and feeds up to three output planes.
+constexpr int ZC1 = 8;
+template <typename T>
+__global__ void __launch_bounds__(256) dw_c1_kernel(const T *__restrict__ x, int ldx, NormDev xn, int N, int D, int H, int W,
+                                                    const float *__restrict__ dw_w, const float *__restrict__ pw_w,
+                                                    const float *__restrict__ sc_w, int Cout, float *__restrict__ u,
+                                                    double *__restrict__ t_stats, double *__restrict__ r_stats) {
+    __shared__ float s_w[27];
+    __shared__ float s_sum[4];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < 27) s_w[tid] = dw_w[tid];
+    if (tid < 4) s_sum[tid] = 0.f;
+    __syncthreads();
+    const int n = blockIdx.z, z0 = blockIdx.y * ZC1;
+    const int p = blockIdx.x * 256 + tid;
+    const bool pvalid = p < H * W;
+    const int y = pvalid ? p / W : 0, xx = pvalid ? p - (p / W) * W : 0;
+    float sc, sh;
+    norm_scale_shift(xn, N, 1, n, 0, sc, sh);
+    float wr[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) wr[k] = s_w[k];
+    float acc[ZC1];
+#pragma unroll
+    for (int k = 0; k < ZC1; ++k) acc[k] = 0.f;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    bool okx[3], oky[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { okx[d] = xx + d - 1 >= 0 && xx + d - 1 < W; oky[d] = y + d - 1 >= 0 && y + d - 1 < H; }
+#pragma unroll
+    for (int zi = 0; zi < ZC1 + 2; ++zi) {
+        const int gz = z0 + zi - 1;
+        float v[9];
+        const bool okz = pvalid && gz >= 0 && gz < D;
+        const T *plane = x + (((size_t)n * D + (okz ? gz : 0)) * H) * W * (size_t)ldx;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                float a = 0.f;
+                if (okz && oky[dy] && okx[dx]) a = lrelu(fmaf(ld1(plane + ((size_t)(y + dy - 1) * W + (xx + dx - 1)) * ldx), sc, sh), xn.slope);
+                v[dy * 3 + dx] = a;
+            }
+#pragma unroll
+        for (int dz = 0; dz < 3; ++dz) {
+            const int k = zi - dz;                    // output plane z0 + k reads input plane z0 + k + dz - 1 = gz
+            if (k >= 0 && k < ZC1) {
+#pragma unroll
+                for (int t9 = 0; t9 < 9; ++t9) acc[k] = fmaf(wr[dz * 9 + t9], v[t9], acc[k]);
+            }
+        }
+        if (zi >= 1 && zi <= ZC1 && okz) { s2 += v[4]; s3 = fmaf(v[4], v[4], s3); }
+    }
+    if (pvalid) {
+#pragma unroll
+        for (int k = 0; k < ZC1; ++k)
+            if (z0 + k < D) {
+                u[(((size_t)n * D + z0 + k) * H) * W + p] = acc[k];
+                s0 += acc[k]; s1 = fmaf(acc[k], acc[k], s1);
+            }
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+    if (lane == 0) { atomicAdd(&s_sum[0], s0); atomicAdd(&s_sum[1], s1); atomicAdd(&s_sum[2], s2); atomicAdd(&s_sum[3], s3); }
+    __syncthreads();
+    for (int i = tid; i < 2 * Cout; i += 256) {
+        const int isq = i >= Cout, c = isq ? i - Cout : i;
+        const float wt = pw_w[c];
+        atomicAdd(&t_stats[(size_t)isq * N * Cout + (size_t)n * Cout + c], isq ? (double)wt * wt * s_sum[1] : (double)wt * s_sum[0]);
+        if (sc_w != nullptr && r_stats != nullptr) {
+            const float wq = sc_w[c];
+            atomicAdd(&r_stats[(size_t)isq * N * Cout + (size_t)n * Cout + c], isq ? (double)wq * wq * s_sum[3] : (double)wq * s_sum[2]);
+        }
+    }
+}
+
+// bf16, W % 8 == 0, contiguous single-channel input: thread = 8 x-consecutive voxels x ZC1V planes.  One 16-byte load per
+// input row (+ the two x-halo scalars), so ~1.7 loads per voxel instead of 11; lanes run along the flattened (y, x) plane.
+constexpr int ZC1V = 4;
+__global__ void __launch_bounds__(256) dw_c1_vec_kernel(const bf16 *__restrict__ x, NormDev xn, int N, int D, int H, int W,
+                                                        const float *__restrict__ dw_w, const float *__restrict__ pw_w,
+                                                        const float *__restrict__ sc_w, int Cout, float *__restrict__ u,
+                                                        double *__restrict__ t_stats, double *__restrict__ r_stats) {
+    __shared__ float s_w[27];
+    __shared__ float s_sum[4];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < 27) s_w[tid] = dw_w[tid];
+    if (tid < 4) s_sum[tid] = 0.f;
+    __syncthreads();
+    const int n = blockIdx.z, z0 = blockIdx.y * ZC1V;
+    const int W8 = W >> 3;
+    const int q = blockIdx.x * 256 + tid;                 // 8-voxel group within the plane
+    const bool qvalid = q < H * W8;
+    const int y = qvalid ? q / W8 : 0, x0 = qvalid ? (q - (q / W8) * W8) * 8 : 0;
+    float sc, sh;
+    norm_scale_shift(xn, N, 1, n, 0, sc, sh);
+    const float slope = xn.slope;
+    float wr[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) wr[k] = s_w[k];
+    float acc[ZC1V][8];
+#pragma unroll
+    for (int k = 0; k < ZC1V; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[k][i] = 0.f;
+    float s2 = 0.f, s3 = 0.f;
+    const bool okl = x0 > 0, okr = x0 + 8 < W;
+#pragma unroll
+    for (int zi = 0; zi < ZC1V + 2; ++zi) {
+        const int gz = z0 + zi - 1;
+        const bool okz = qvalid && gz >= 0 && gz < D;
+        const bf16 *plane = x + (((size_t)n * D + (okz ? gz : 0)) * H) * W;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int gy = y + dy - 1;
+            const bool ok = okz && gy >= 0 && gy < H;
+            float v[10];
+#pragma unroll
+            for (int i = 0; i < 10; ++i) v[i] = 0.f;
+            if (ok) {
+                const bf16 *row = plane + (size_t)gy * W + x0;
+                const uint4 r4 = *reinterpret_cast<const uint4 *>(row);
+                v[1] = __uint_as_float(r4.x << 16); v[2] = __uint_as_float(r4.x & 0xffff0000u);
+                v[3] = __uint_as_float(r4.y << 16); v[4] = __uint_as_float(r4.y & 0xffff0000u);
+                v[5] = __uint_as_float(r4.z << 16); v[6] = __uint_as_float(r4.z & 0xffff0000u);
+                v[7] = __uint_as_float(r4.w << 16); v[8] = __uint_as_float(r4.w & 0xffff0000u);
+                if (okl) v[0] = __bfloat162float(row[-1]);
+                if (okr) v[9] = __bfloat162float(row[8]);
+#pragma unroll
+                for (int i = 0; i < 10; ++i) v[i] = lrelu(fmaf(v[i], sc, sh), slope);
+                if (!okl) v[0] = 0.f;
+                if (!okr) v[9] = 0.f;
+            }
+#pragma unroll
+            for (int dz = 0; dz < 3; ++dz) {
+                const int k = zi - dz;                    // output plane z0 + k reads input plane gz with tap dz
+                if (k >= 0 && k < ZC1V) {
+                    const float w0 = wr[dz * 9 + dy * 3], w1 = wr[dz * 9 + dy * 3 + 1], w2 = wr[dz * 9 + dy * 3 + 2];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[k][i] = fmaf(w2, v[i + 2], fmaf(w1, v[i + 1], fmaf(w0, v[i], acc[k][i])));
+                }
+            }
+            if (dy == 1 && zi >= 1 && zi <= ZC1V && ok) {
+#pragma unroll
+                for (int i = 1; i <= 8; ++i) { s2 += v[i]; s3 = fmaf(v[i], v[i], s3); }
+            }
+        }
+    }
+    float s0 = 0.f, s1 = 0.f;
+    if (qvalid) {
+#pragma unroll
+        for (int k = 0; k < ZC1V; ++k)
+            if (z0 + k < D) {
+                float4 *dst = reinterpret_cast<float4 *>(u + (((size_t)n * D + z0 + k) * H + y) * W + x0);
+                dst[0] = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+                dst[1] = make_float4(acc[k][4], acc[k][5], acc[k][6], acc[k][7]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { s0 += acc[k][i]; s1 = fmaf(acc[k][i], acc[k][i], s1); }
+            }
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+    if (lane == 0) { atomicAdd(&s_sum[0], s0); atomicAdd(&s_sum[1], s1); atomicAdd(&s_sum[2], s2); atomicAdd(&s_sum[3], s3); }
+    __syncthreads();
+    for (int i = tid; i < 2 * Cout; i += 256) {
+        const int isq = i >= Cout, c = isq ? i - Cout : i;
+        const float wt = pw_w[c];
+        atomicAdd(&t_stats[(size_t)isq * N * Cout + (size_t)n * Cout + c], isq ? (double)wt * wt * s_sum[1] : (double)wt * s_sum[0]);
+        if (sc_w != nullptr && r_stats != nullptr) {
+            const float wq = sc_w[c];
+            atomicAdd(&r_stats[(size_t)isq * N * Cout + (size_t)n * Cout + c], isq ? (double)wq * wq * s_sum[3] : (double)wq * s_sum[2]);
+        }
+    }
+}
+
 // Dense 3x3x3 conv with a single input channel (the first conv of the dense / grouped variants, unet3d.py:49 with
 // in_channels = 1): 27 taps x COUT filters per voxel on CUDA cores, thread = one voxel, all COUT outputs; optionally the
 // block's 1x1x1 shortcut (r[c] = sc[c] * x) from the same staged tile.  Statistics by the transposing warp reduction.
@@ -1172,6 +1349,52 @@ extern "C" int l3d_merge_fwd(const l3d_act *t2, const l3d_norm *n2, const l3d_ac
     l3d_count_launch();
     L3D_CUDA_OK("l3d_merge_fwd launch");
     return 0;
+}
+
+int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int W,
+                    const float *w, int groups, const float *dw_w, const float *pw_w, const float *sc_w,
+                    const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats, int stat_ld, int co0, int cout_total,
+                    const float *r1_w, void *stream);
+
+extern "C" int l3d_dw_c1_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int W,
+                             const float *dw_w, const float *pw_w, const float *sc_w, int Cout,
+                             float *u, double *t_stats, double *r_stats, void *stream) {
+    L3D_REQUIRE(!act_null(x) && dw_w && pw_w && u && t_stats, "l3d_dw_c1_fwd: null argument");
+    L3D_REQUIRE(x->C == 1, "l3d_dw_c1_fwd: the input view must have one channel");
+    L3D_REQUIRE(N > 0 && N <= 65535 && D > 0 && H > 0 && W > 0 && Cout > 0, "l3d_dw_c1_fwd: bad dims");
+    L3D_REQUIRE(sc_w == nullptr || r_stats != nullptr, "l3d_dw_c1_fwd: shortcut weights without a statistics buffer");
+    const NormDev nd = norm_dev(xn);
+    if (x->dtype == L3D_BF16 && W % 8 == 0 && x->ldc == 1 && reinterpret_cast<uintptr_t>(x->ptr) % 16 == 0 &&
+        reinterpret_cast<uintptr_t>(u) % 16 == 0) {
+        dim3 gridv((unsigned)(((size_t)H * (W / 8) + 255) / 256), (unsigned)((D + ZC1V - 1) / ZC1V), (unsigned)N);
+        dw_c1_vec_kernel<<<gridv, 256, 0, (cudaStream_t)stream>>>((const bf16 *)x->ptr, nd, N, D, H, W, dw_w, pw_w, sc_w, Cout, u, t_stats, r_stats);
+        l3d_count_launch();
+        l3d_note_kernel("dw_c1_vec_kernel");
+        L3D_CUDA_OK("l3d_dw_c1_fwd launch");
+        return 0;
+    }
+    dim3 grid((unsigned)(((size_t)H * W + 255) / 256), (unsigned)((D + ZC1 - 1) / ZC1), (unsigned)N);
+    L3D_DISPATCH_DTYPE(x->dtype, T, {
+        dw_c1_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T *)x->ptr, x->ldc, nd, N, D, H, W, dw_w, pw_w, sc_w, Cout, u,
+                                                                 t_stats, r_stats);
+    });
+    l3d_count_launch();
+    l3d_note_kernel("dw_c1_kernel");
+    L3D_CUDA_OK("l3d_dw_c1_fwd launch");
+    return 0;
+}
+
+extern "C" int l3d_dwpw_fwd_rank1(const float *u, const float *r1_w, int Cin, const l3d_norm *xn, int N, int D, int H, int W,
+                                  const float *dw_w, const float *pw_w, const l3d_act *t, double *t_stats, void *stream) {
+    L3D_REQUIRE(u && r1_w && dw_w && pw_w && !act_null(t) && t_stats, "l3d_dwpw_fwd_rank1: null argument");
+    L3D_REQUIRE(N > 0 && D > 0 && H > 0 && W > 0, "l3d_dwpw_fwd_rank1: bad dims");
+    L3D_REQUIRE(Cin == 16 && W % 4 == 0 && t->dtype == L3D_BF16 && t->C % 16 == 0 && t->C <= 64,
+                "l3d_dwpw_fwd_rank1: needs Cin = 16, W %% 4 == 0, bf16 output with 16..64 channels (got Cin=%d W=%d Cout=%d)", Cin, W, t->C);
+    l3d_act xv;
+    xv.ptr = const_cast<float *>(u); xv.C = Cin; xv.ldc = Cin; xv.dtype = L3D_BF16; xv.pad_ = 0;
+    const int rc = l3d_conv3_tc_ex(&xv, xn, N, D, H, W, nullptr, 1, dw_w, pw_w, nullptr, t, t_stats, nullptr, nullptr, t->C, 0, t->C, r1_w, stream);
+    if (rc < 0) { l3d_set_error("l3d_dwpw_fwd_rank1: the implicit-GEMM kernel does not take this shape / alignment"); return 3; }
+    return rc;
 }
 
 extern "C" int l3d_merge_fwd_rank1(const l3d_act *t2, const l3d_norm *n2, const l3d_act *x1, const float *r1_w, const l3d_norm *nr,

@@ -15,7 +15,7 @@ _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.environ.get("L3D_LIB", os.path.join(_PKG_DIR, "libl3d.so"))
 
 L3D_F32, L3D_BF16 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class Act(Structure):
@@ -40,6 +40,8 @@ _SIGS = {
                      POINTER(Act), _P, POINTER(Act), _P, POINTER(Act), _P],
     "l3d_merge_fwd_rank1": [POINTER(Act), POINTER(Norm), POINTER(Act), _P, POINTER(Norm), c_int, c_int, c_int, c_int, c_float,
                             POINTER(Act), POINTER(Act), _P],
+    "l3d_dw_c1_fwd": [POINTER(Act), POINTER(Norm), c_int, c_int, c_int, c_int, _P, _P, _P, c_int, _P, _P, _P, _P],
+    "l3d_dwpw_fwd_rank1": [_P, _P, c_int, POINTER(Norm), c_int, c_int, c_int, c_int, _P, _P, POINTER(Act), _P, _P],
     "l3d_conv3_fwd": [POINTER(Act), POINTER(Norm), c_int, c_int, c_int, c_int, _P, c_int, POINTER(Act), _P, _P, POINTER(Act), _P, _P],
     "l3d_merge_fwd": [POINTER(Act), POINTER(Norm), POINTER(Act), POINTER(Norm), c_int, c_int, c_int, c_int, c_float,
                       POINTER(Act), POINTER(Act), _P, _P, c_int, _P, _P, _P],
@@ -138,7 +140,7 @@ class KernelTimer:
         return out
 
 
-_DISPATCHING = {"l3d_dwpw_fwd", "l3d_conv3_fwd", "l3d_convt_fwd"}
+_DISPATCHING = {"l3d_dwpw_fwd", "l3d_conv3_fwd", "l3d_convt_fwd", "l3d_dwpw_fwd_rank1", "l3d_dw_c1_fwd"}
 TIMER = KernelTimer()
 
 

@@ -17,6 +17,7 @@ HBM layout (per workspace, i.e. per (N, D, H, W, dtype, training) key):
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -86,9 +87,14 @@ class Workspace:
         n_stats = 0
         for b in plan.blocks:
             d = lv[b.level]
-            buf = {"t1": emp(N, *d, b.cout), "t2": emp(N, *d, b.cout)}
-            if b.cin != b.cout:
-                buf["r"] = emp(N, *d, b.cout)
+            # first block of a 1-channel image at inference: conv1's 16-channel output and the shortcut are rank-1 maps of
+            # single-channel tensors and are never stored (UNetPlan.forward); only the depthwise output u (fp32) is
+            if b.name == "init_conv" and plan.rank1_first(b, dtype, d, training):
+                buf = {"u_r1": torch.empty(N, *d, dtype=torch.float32, device=device), "t2": emp(N, *d, b.cout)}
+            else:
+                buf = {"t1": emp(N, *d, b.cout), "t2": emp(N, *d, b.cout)}
+                if b.cin != b.cout and not plan.rank1_shortcut(b, training):
+                    buf["r"] = emp(N, *d, b.cout)
             if training and b.kind1 == "dws":
                 buf["u1"] = emp(N, *d, b.cin)
             if training and b.kind2 == "dws":
@@ -149,6 +155,15 @@ class UNetPlan:
         self.dws, self.grouped, self.groups = dws, grouped, groups
         self.blocks = make_block_specs(in_channels, enc, dws, grouped, groups)
         self._ws: Dict[tuple, Workspace] = {}
+
+    # first block of a 1-channel image at inference (b.cin == 1, depthwise-separable): the shortcut r = sc (x) x and
+    # conv1's output t1 = pw (x) u are rank-1 maps of single-channel tensors, evaluated on the fly by their consumers
+    def rank1_shortcut(self, b: BlockSpec, training: bool) -> bool:
+        return (not training) and b.name == "init_conv" and b.cin == 1 and b.cin != b.cout and b.kind1 == "dws" and b.cout in (16, 32)
+
+    def rank1_first(self, b: BlockSpec, dtype, dims, training: bool) -> bool:
+        return (self.rank1_shortcut(b, training) and b.kind2 == "dws" and b.cout == 16 and dtype == torch.bfloat16
+                and dims[2] % 4 == 0 and os.environ.get("L3D_NO_RANK1_FIRST", "0") != "1")
 
     # ------------------------------------------------------------------ workspace
     def workspace(self, N, dims, dtype, device, training) -> Workspace:
@@ -228,18 +243,31 @@ class UNetPlan:
             sc_w = P[f"{b.prefix}.shortcut.0.weight"] if has_sc else None
             # inference, first block of a 1-channel image: its 1x1x1 shortcut r[v][c] = w[c] * x[v] is never written -- the
             # conv kernel still produces r's statistics and the merge evaluates r on the fly (64 B / voxel less traffic)
-            rank1 = (not training) and has_sc and b.cin == 1 and b.kind1 == "dws" and b.cout in (16, 32) and b.name == "init_conv"
-            # conv1 (+ shortcut conv) on the block input
-            self._conv(P, b, 1, x_act, ident, N, dims, buf["t1"], s1, sc_w, None if rank1 else buf.get("r"), sr if has_sc else None,
-                       buf.get("u1"), st)
-            # conv2 on lrelu(IN1(t1)) * dropout-mask, applied on load
+            rank1 = self.rank1_shortcut(b, training)
             n1 = nv.norm(s1, P[f"{b.prefix}.norm1.weight"], P[f"{b.prefix}.norm1.bias"], mask, IN_EPS, LEAKY_SLOPE, vox)
-            self._conv(P, b, 2, nv.act(buf["t1"]), n1, N, dims, buf["t2"], s2, None, None, None, buf.get("u2"), st)
+            if "u_r1" in buf:
+                # ... and conv1's output t1[v][c] = pw[c] * u[v] is not written either: one fp32 channel u plus analytic
+                # statistics, then conv2 evaluates lrelu(IN1(t1)) from u on the fly
+                pw1 = P[f"{b.prefix}.conv1.pointwise.weight"]
+                nv.TIMER.tag = f"{b.name}.c1"
+                nv.call("l3d_dw_c1_fwd", x_act, ident, N, *dims, nv.ptr(P[f"{b.prefix}.conv1.depthwise.weight"]), nv.ptr(pw1),
+                        nv.ptr(sc_w), b.cout, nv.ptr(buf["u_r1"]), nv.ptr(s1), nv.ptr(sr), st,
+                        algo_bytes=N * vox * (es + 4))
+                nv.TIMER.tag = f"{b.name}.c2"
+                nv.call("l3d_dwpw_fwd_rank1", nv.ptr(buf["u_r1"]), nv.ptr(pw1), b.cout, n1, N, *dims,
+                        nv.ptr(P[f"{b.prefix}.conv2.depthwise.weight"]), nv.ptr(P[f"{b.prefix}.conv2.pointwise.weight"]),
+                        nv.act(buf["t2"]), nv.ptr(s2), st, algo_bytes=N * vox * (4 + es * b.cout))
+            else:
+                # conv1 (+ shortcut conv) on the block input
+                self._conv(P, b, 1, x_act, ident, N, dims, buf["t1"], s1, sc_w, None if rank1 else buf.get("r"), sr if has_sc else None,
+                           buf.get("u1"), st)
+                # conv2 on lrelu(IN1(t1)) * dropout-mask, applied on load
+                self._conv(P, b, 2, nv.act(buf["t1"]), n1, N, dims, buf["t2"], s2, None, None, None, buf.get("u2"), st)
             # residual merge (+ pool / head)
             nv.TIMER.tag = b.name
             n2 = nv.norm(s2, P[f"{b.prefix}.norm2.weight"], P[f"{b.prefix}.norm2.bias"], None, IN_EPS, 1.0, vox)
             if has_sc:
-                r_act = nv.act(buf["r"])
+                r_act = None if rank1 else nv.act(buf["r"])
                 nr = nv.norm(sr, P[f"{b.prefix}.shortcut.1.weight"], P[f"{b.prefix}.shortcut.1.bias"], None, IN_EPS, 1.0, vox)
             else:
                 r_act, nr = x_act, ident

@@ -154,3 +154,58 @@ def test_conv3_tc_wide_layers_in_output_slices(case, launches):
     """Dense / grouped layers whose 27 weight tiles do not fit shared memory run as several implicit-GEMM launches over
     output-channel slices (grouped: the slice keeps its absolute channel index for the group lookup)."""
     _run(case, {}, launches=launches)
+
+
+@pytest.mark.parametrize("dims", [(16, 16, 16), (20, 19, 24), (9, 33, 8), (12, 10, 20), (48, 48, 48)])
+@pytest.mark.parametrize("tz", [0, 2, 4, 6, 8])
+def test_rank1_first_block_layers(dims, tz):
+    """l3d_dw_c1_fwd (u = dw * x, analytic statistics of pw (x) u and sc (x) x) and l3d_dwpw_fwd_rank1 (the second
+    depthwise-separable conv reading lrelu(IN(pw (x) u)) evaluated on the fly) against torch in fp32."""
+    from light_unet import _native as nv
+    N, C = 2, 16
+    D, H, W = dims
+    vox = D * H * W
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(N, D, H, W, 1, generator=g).to(torch.bfloat16)
+    dw1 = torch.randn(1, 1, 3, 3, 3, generator=g) / np.sqrt(27.0)
+    pw1 = torch.randn(C, 1, 1, 1, 1, generator=g)
+    sc = torch.randn(C, 1, 1, 1, 1, generator=g)
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.3
+    dw2 = torch.randn(C, 1, 3, 3, 3, generator=g) / np.sqrt(27.0)
+    pw2 = torch.randn(C, C, 1, 1, 1, generator=g) / np.sqrt(C)
+    st = nv.stream_ptr(torch.device(DEV))
+    xd, dw1d, pw1d, scd, gd, bd, dw2d, pw2d = (v.to(DEV) for v in (x, dw1, pw1, sc, gamma, beta, dw2, pw2))
+    u = torch.zeros(N, D, H, W, dtype=torch.float32, device=DEV)
+    s1 = torch.zeros(2 * N * C, dtype=torch.float64, device=DEV)
+    sr = torch.zeros(2 * N * C, dtype=torch.float64, device=DEV)
+    nv.call("l3d_dw_c1_fwd", nv.act(xd), nv.norm(), N, D, H, W, nv.ptr(dw1d), nv.ptr(pw1d), nv.ptr(scd), C, nv.ptr(u), nv.ptr(s1), nv.ptr(sr), st)
+    torch.cuda.synchronize()
+    x_ncdhw = x.float().permute(0, 4, 1, 2, 3).contiguous()
+    u_ref = F.conv3d(x_ncdhw, dw1, padding=1)
+    assert _rel(u.cpu()[:, None], u_ref) < 1e-6
+    t1_ref = F.conv3d(u_ref, pw1).double()
+    r_ref = F.conv3d(x_ncdhw, sc).double()
+    for got, ref in ((s1, t1_ref), (sr, r_ref)):
+        want = torch.stack([ref.sum(dim=(2, 3, 4)), (ref * ref).sum(dim=(2, 3, 4))]).reshape(-1)
+        assert float((got.cpu() - want).abs().max() / want.abs().max()) < 1e-5
+    a1 = F.leaky_relu(F.instance_norm(t1_ref.float(), weight=gamma, bias=beta, eps=EPS), SLOPE)
+    t2_ref = F.conv3d(F.conv3d(a1, dw2, padding=1, groups=C), pw2)
+    t2 = torch.zeros(N, D, H, W, C, dtype=torch.bfloat16, device=DEV)
+    s2 = torch.zeros(2 * N * C, dtype=torch.float64, device=DEV)
+    n1 = nv.norm(s1, gd, bd, None, EPS, SLOPE, vox)
+    old = os.environ.get("L3D_C3_TZ")
+    if tz:
+        os.environ["L3D_C3_TZ"] = str(tz)
+    try:
+        nv.call("l3d_dwpw_fwd_rank1", nv.ptr(u), nv.ptr(pw1d), C, n1, N, D, H, W, nv.ptr(dw2d), nv.ptr(pw2d), nv.act(t2), nv.ptr(s2), st)
+        torch.cuda.synchronize()
+    finally:
+        if old is None:
+            os.environ.pop("L3D_C3_TZ", None)
+        else:
+            os.environ["L3D_C3_TZ"] = old
+    got_f = t2.float().cpu()
+    e = _rel(got_f.permute(0, 4, 1, 2, 3), t2_ref)
+    assert e < 4e-3, (dims, tz, e)
+    want = torch.stack([got_f.double().sum(dim=(1, 2, 3)), (got_f.double() ** 2).sum(dim=(1, 2, 3))]).reshape(-1)
+    assert float((s2.cpu() - want).abs().max() / (want.abs().max() + 1e-30)) < 2e-4

@@ -247,3 +247,40 @@ def test_full_size_volume_properties(tmp_path):
     prob, boxes = inf.infer_volume(vol, threshold=0.3)
     assert prob.shape == (128, 128, 320) and prob.dtype == np.float32
     assert boxes == bbox_ref.extract_bboxes(prob, 0.3, 0.5, (4.0, 4.0, 4.0), 3)
+
+
+@pytest.mark.parametrize("dims", [(16, 16, 16), (18, 22, 28), (48, 48, 48), (16, 20, 26)])
+def test_rank1_first_block(dims, monkeypatch):
+    """Inference, first block of a 1-channel image: conv1's 16-channel output is a rank-1 map of the depthwise output u
+    and is evaluated on the fly by conv2 (l3d_dw_c1_fwd + l3d_dwpw_fwd_rank1) instead of being stored.  The result
+    must meet the bf16 bar against the oracle and agree with the stored-tensor path; W % 4 != 0 uses the stored path."""
+    from light_unet import _native as nv
+    cfg = unet_ref.UNetCfg(dropout_p=0.0)
+    sd_np = synth.synth_state_dict(unet_ref.param_shapes(cfg), 11)
+    x, _ = synth.synth_patches(2, dims, 5)
+    with torch.no_grad():
+        ref = unet_ref.forward(unet_ref.to_torch(sd_np), torch.from_numpy(x), cfg).numpy()
+    model = build_model(cfg, sd_np, "bf16").eval()
+    xs = torch.from_numpy(x).to(DEV)
+
+    def run():
+        model._plan._ws.clear()
+        seen = []
+        orig = nv.call
+
+        def spy(name, *a, **k):
+            seen.append(name)
+            return orig(name, *a, **k)
+        monkeypatch.setattr(nv, "call", spy)
+        with torch.no_grad():
+            y = model(xs).cpu().numpy()
+        monkeypatch.setattr(nv, "call", orig)
+        return y, seen
+
+    y1, seen1 = run()
+    assert ("l3d_dwpw_fwd_rank1" in seen1) == (dims[2] % 4 == 0)
+    monkeypatch.setenv("L3D_NO_RANK1_FIRST", "1")
+    y0, seen0 = run()
+    assert "l3d_dwpw_fwd_rank1" not in seen0
+    print(f"{dims}: rank-1 vs oracle {rel_l2(y1, ref):.3e}, stored vs oracle {rel_l2(y0, ref):.3e}, rank-1 vs stored {rel_l2(y1, y0):.3e}")
+    assert rel_l2(y1, ref) < 1e-2 and rel_l2(y0, ref) < 1e-2 and rel_l2(y1, y0) < 1e-2
