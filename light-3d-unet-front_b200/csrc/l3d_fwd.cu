@@ -1098,6 +1098,9 @@ int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int 
                  const float *w, int groups, const float *dw_w, const float *pw_w, const float *sc_w,
                  const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats, int stat_ld, int co0, int cout_total,
                  void *stream);
+int l3d_dwpw_fwd_slab(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int W,
+                      const float *dw_w, const float *pw_w, const float *sc_w,
+                      const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats, void *stream);
 int l3d_convt_fwd_tc(const l3d_act *x, int N, int d, int h, int w_, const float *w, const float *b,
                      const l3d_act *out, int OD, int OH, int OW, int oz, int oy, int ox, void *stream);
 
@@ -1152,6 +1155,11 @@ extern "C" int l3d_dwpw_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, 
                 if (rc >= 0) return rc;
             }
         }
+    }
+    // small volumes (the 12^3 / 6^3 levels of a 48^3 window): whole-plane slabs, no halo or tile padding (l3d_fwd_slab.cu)
+    if (dw_w != nullptr && !has_u && !r_stats_only && (long long)H * W <= 256) {
+        const int rc = l3d_dwpw_fwd_slab(x, xn, N, D, H, W, dw_w, pw_w, sc_w, t, t_stats, r, r_stats, stream);
+        if (rc >= 0) return rc;
     }
     {
         const int rc = l3d_dwpw_fwd_tc(x, xn, N, D, H, W, dw_w, pw_w, sc_w, t, t_stats, r, r_stats, u, stream);

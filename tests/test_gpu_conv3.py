@@ -209,3 +209,55 @@ def test_rank1_first_block_layers(dims, tz):
     assert e < 4e-3, (dims, tz, e)
     want = torch.stack([got_f.double().sum(dim=(1, 2, 3)), (got_f.double() ** 2).sum(dim=(1, 2, 3))]).reshape(-1)
     assert float((s2.cpu() - want).abs().max() / (want.abs().max() + 1e-30)) < 2e-4
+
+
+SLAB_CASES = [  # N, dims, Cin, Cout, shortcut, normed input
+    (3, (12, 12, 12), 32, 64, True, False), (2, (12, 12, 12), 64, 64, False, True), (2, (12, 12, 12), 128, 64, True, False),
+    (3, (6, 6, 6), 64, 128, True, False), (5, (6, 6, 6), 128, 128, False, True),
+    (2, (10, 12, 12), 64, 64, False, True), (1, (7, 8, 4), 64, 64, True, True), (2, (5, 6, 12), 64, 128, False, True),
+    (2, (8, 8, 8), 64, 128, True, False), (1, (3, 16, 16), 48, 80, True, True),
+]
+
+
+@pytest.mark.parametrize("case", SLAB_CASES, ids=lambda c: f"{c[2]}to{c[3]}{'+sc' if c[4] else ''}-{'x'.join(map(str, c[1]))}")
+def test_dwpw_slab_kernel(case):
+    """Small-volume depthwise-separable conv (csrc/l3d_fwd_slab.cu: whole-plane slabs, the 12^3 / 6^3 levels of a 48^3
+    window) through l3d_dwpw_fwd against torch in fp32 on the same bf16-stored inputs."""
+    from light_unet import _native as nv
+    N, dims, Cin, Cout, has_sc, use_norm = case
+    D, H, W = dims
+    x, stats, gamma, beta, a, vox = _inputs(N, dims, Cin, 13)
+    if not use_norm:
+        a = x.float()
+    g = torch.Generator().manual_seed(17)
+    st = nv.stream_ptr(torch.device(DEV))
+    xd = x.to(DEV)
+    xn = nv.norm()
+    if use_norm:
+        sd, gd, bd = stats.to(DEV).contiguous(), gamma.to(DEV), beta.to(DEV)
+        xn = nv.norm(sd, gd, bd, None, EPS, SLOPE, vox)
+    dw = torch.randn(Cin, 1, 3, 3, 3, generator=g) / np.sqrt(27.0)
+    pw = torch.randn(Cout, Cin, 1, 1, 1, generator=g) / np.sqrt(Cin)
+    sc = torch.randn(Cout, Cin, 1, 1, 1, generator=g) / np.sqrt(Cin)
+    dwd, pwd, scd = dw.to(DEV), pw.to(DEV), sc.to(DEV)
+    # outputs are views into wider buffers (ldc > C), as the engine's concat buffers are
+    tb = torch.zeros(N, D, H, W, 2 * Cout, dtype=torch.bfloat16, device=DEV)
+    t = tb[..., Cout:]
+    r = torch.zeros(N, D, H, W, Cout, dtype=torch.bfloat16, device=DEV)
+    t_stats = torch.zeros(2 * N * Cout, dtype=torch.float64, device=DEV)
+    r_stats = torch.zeros(2 * N * Cout, dtype=torch.float64, device=DEV)
+    nv.call("l3d_dwpw_fwd", nv.act(xd), xn, N, D, H, W, nv.ptr(dwd), nv.ptr(pwd), nv.ptr(scd) if has_sc else None, nv.act(tb, Cout, Cout),
+            nv.ptr(t_stats), nv.act(r) if has_sc else nv.act(None), nv.ptr(r_stats) if has_sc else None, nv.act(None), st)
+    torch.cuda.synchronize()
+    assert nv.lib().l3d_last_kernel() == b"dwpw_slab_kernel"
+    assert float(tb[..., :Cout].float().abs().max()) == 0.0          # the other half of the buffer is untouched
+    a_ncdhw = a.permute(0, 4, 1, 2, 3).contiguous()
+    outs = [(t, t_stats, F.conv3d(F.conv3d(a_ncdhw, dw, padding=1, groups=Cin), pw))]
+    if has_sc:
+        outs.append((r, r_stats, F.conv3d(a_ncdhw, sc)))
+    for got, gstats, ref in outs:
+        got_f = got.float().cpu()
+        e = _rel(got_f.permute(0, 4, 1, 2, 3), ref)
+        assert e < 4e-3, (case, e)
+        want = torch.stack([got_f.double().sum(dim=(1, 2, 3)), (got_f.double() ** 2).sum(dim=(1, 2, 3))]).reshape(-1)
+        assert float((gstats.cpu() - want).abs().max() / (want.abs().max() + 1e-30)) < 2e-4, case
