@@ -1128,7 +1128,10 @@ extern "C" int l3d_dwpw_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, 
     // tensor pipe; measured 2.2x faster than the CUDA-core stencil + GEMM kernel at 16/32 channels, on par at 32 -> 32 and
     // slower once the 27 weight tiles (27*Cin*Cout*2 B) crowd the operand buffers out of shared memory: Cin*Cout <= 1024)
     const char *igemm_max_env = getenv("L3D_DWS_IGEMM_MAX");
-    const int igemm_max = (igemm_max_env && igemm_max_env[0]) ? atoi(igemm_max_env) : 1024;
+    int igemm_max = (igemm_max_env && igemm_max_env[0]) ? atoi(igemm_max_env) : 1024;
+    // 64 -> 32 (+ shortcut) at >= 16^3: one launch with a shorter tile (the 27 weight tiles take 110 KB) beats two launches over
+    // 16-channel output slices that each re-read and re-activate the input (measured 974 vs 1162 us for 325 windows at 24^3)
+    if (!(igemm_max_env && igemm_max_env[0]) && D >= 16 && H >= 16 && Cin * Cout <= 2048 && Cout <= 32) igemm_max = 2048;
     if (dw_w != nullptr && !has_u && Cin * Cout <= igemm_max) {
         const int rc = l3d_conv3_tc(x, xn, N, D, H, W, nullptr, 1, dw_w, pw_w, sc_w, t, t_stats, r, r_stats, Cout, 0, Cout, stream);
         if (rc >= 0) return rc;

@@ -30,6 +30,7 @@ struct SlabArgs {
     int SZ, MT, RP, PP;      // slab height, MMA tiles per slab, padded row / plane pitch of the stencil tile (voxels, odd)
     int tmem_cols;
     uint32_t raw_bytes, raw_stride, in_bytes;
+    int dbg;                 // development aid (L3D_SLAB_SKIP): 1 = no activation pass, 2 = no stencil, 4 = no epilogue, 8 = no TMA
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(NT, 2) dwpw_slab_kernel(const __grid_constant_
         z0 = (slab - n * zslabs) * SZ;
     };
     auto issue_tma = [&](int it) {
-        if (it >= n_items) return;
+        if (it >= n_items || (A.dbg & 8)) return;
         int n, z0, ch;
         item_coord(it, n, z0, ch);
         tc::mbar_expect_tx(&s_tma_full[it & 1], A.raw_bytes);
@@ -181,10 +182,10 @@ __global__ void __launch_bounds__(NT, 2) dwpw_slab_kernel(const __grid_constant_
         }
         // ---- activation pass: raw bf16 box [pz][y][x][16] -> fp32 stencil tile (zero outside the volume: the conv pads
         // the ACTIVATED tensor; the x / y borders of the tile are never written and stay zero)
-        tc::mbar_wait(&s_tma_full[buf], (uint32_t)((it >> 1) & 1));
+        if (!(A.dbg & 8)) tc::mbar_wait(&s_tma_full[buf], (uint32_t)((it >> 1) & 1));
         // operand tiles `buf` are free once the MMAs of item it-2 have completed
         if (it >= 2) tc::mbar_wait(&s_mma_done[buf], (uint32_t)(((it >> 1) - 1) & 1));
-        {
+        if (!(A.dbg & 1)) {
             unsigned char *As = sA + (size_t)buf * nacc * a_bytes + a_bytes;
             const unsigned char *Rb = s_raw + (size_t)buf * A.raw_stride;
             const float sl = A.xn.slope;
@@ -224,8 +225,8 @@ __global__ void __launch_bounds__(NT, 2) dwpw_slab_kernel(const __grid_constant_
             }
         }
         __syncthreads();                 // stencil tile complete, raw box consumed
-        // ---- depthwise stencil: 4 channels x XT voxels per task
-        {
+        // ---- depthwise stencil: 4 channels x 2 rows x XT voxels per task
+        if (!(A.dbg & 2)) {
             const float4 *in4 = reinterpret_cast<const float4 *>(s_in);
             const float4 *w4 = reinterpret_cast<const float4 *>(s_dw + buf * 27 * CK) + cq;
             unsigned char *Am = sA + (size_t)buf * nacc * a_bytes;
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(NT, 2) dwpw_slab_kernel(const __grid_constant_
         // ---- epilogue of the slab: TMEM -> bf16 global + statistics
         tc::mbar_wait(&s_mma_done[buf], (uint32_t)((it >> 1) & 1));
         tc::fence_after_sync();
-        {
+        if (!(A.dbg & 4)) {
             const int zv = min(SZ, A.D - z0);
             const int rows_valid = zv * HW;
             const size_t vox0 = ((size_t)n * A.D + z0) * HW;
@@ -420,6 +421,7 @@ int l3d_dwpw_fwd_slab(const l3d_act *x, const l3d_norm *xn, int N, int D, int H,
     A.t = (bf16 *)t->ptr; A.ldt = t->ldc; A.t_stats = t_stats;
     A.r = has_sc ? (bf16 *)r->ptr : nullptr; A.ldr = has_sc ? r->ldc : 0; A.r_stats = r_stats;
     A.SZ = p.SZ; A.MT = p.MT; A.RP = p.RP; A.PP = p.PP; A.tmem_cols = p.cols;
+    { const char *e = getenv("L3D_SLAB_SKIP"); A.dbg = (e && e[0]) ? atoi(e) : 0; }
     A.raw_bytes = p.raw_bytes; A.raw_stride = p.raw_stride; A.in_bytes = p.in_bytes;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

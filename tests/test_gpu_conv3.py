@@ -142,10 +142,13 @@ def test_conv3_tc_pipeline_variants(knobs):
 
 
 def test_conv3_tc_output_channel_halves():
-    """64 -> 32 (+ shortcut) at >= 16^3: two implicit-GEMM launches over output-channel halves (default dispatch), each
-    writing its channel slice of t / r and of the statistics rows."""
-    _run(("dws", 2, (16, 17, 24), 64, 32, 1, True), {}, launches=2)
-    _run(("dws", 1, (24, 24, 24), 64, 32, 1, False), {}, launches=2)
+    """64 -> 32 (+ shortcut) at >= 16^3: one implicit-GEMM launch with a shorter tile (default dispatch), or -- with the
+    weight budget of the narrow layers (L3D_DWS_IGEMM_MAX=1024) -- two launches over output-channel halves, each writing
+    its channel slice of t / r and of the statistics rows."""
+    _run(("dws", 2, (16, 17, 24), 64, 32, 1, True), {}, launches=1)
+    _run(("dws", 1, (24, 24, 24), 64, 32, 1, False), {}, launches=1)
+    _run(("dws", 2, (16, 17, 24), 64, 32, 1, True), {"L3D_DWS_IGEMM_MAX": 1024}, launches=2)
+    _run(("dws", 1, (24, 24, 24), 64, 32, 1, False), {"L3D_DWS_IGEMM_MAX": 1024}, launches=2)
 
 
 @pytest.mark.parametrize("case,launches", [(("dense", 1, (8, 16, 16), 64, 64, 1, True), 4), (("dense", 1, (6, 16, 8), 32, 64, 1, False), 2),
