@@ -6,57 +6,128 @@
 namespace {
 
 // ---------------------------------------------------------------- windows ------------------
+__device__ __forceinline__ void stv8(float *p, const float (&v)[8]) {
+    reinterpret_cast<float4 *>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4 *>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void stv8(bf16 *p, const float (&v)[8]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
+    *reinterpret_cast<uint4 *>(p) = make_uint4(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b),
+                                               *reinterpret_cast<uint32_t *>(&c), *reinterpret_cast<uint32_t *>(&d));
+}
+
+// grid.y = window; one thread = 8 x-consecutive voxels of one window row (32-bit index arithmetic only)
 template <typename T>
 __global__ void __launch_bounds__(256) gather_windows_kernel(const float *__restrict__ vol, int D, int H, int W,
                                                              const int32_t *__restrict__ pos, int nwin,
                                                              int pd, int ph, int pw, T *__restrict__ out) {
-    const size_t per = (size_t)pd * ph * pw;
-    const size_t total = per * nwin;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int wi = (int)(i / per);
-        size_t rem = i % per;
-        const int x = (int)(rem % pw); rem /= pw;
-        const int y = (int)(rem % ph);
-        const int z = (int)(rem / ph);
-        const int gz = pos[wi * 3] + z, gy = pos[wi * 3 + 1] + y, gx = pos[wi * 3 + 2] + x;
-        float v = 0.f;  // zero padding at the far end (utils.py:102-112)
-        if (gz < D && gy < H && gx < W) v = vol[((size_t)gz * H + gy) * W + gx];
-        st1(out + i, v);
+    const int wi = blockIdx.y;
+    const int oz = pos[wi * 3], oy = pos[wi * 3 + 1], ox = pos[wi * 3 + 2];
+    const int xg = (pw + 7) >> 3;                       // 8-voxel groups per row
+    const int groups = pd * ph * xg;
+    T *wout = out + (size_t)wi * pd * ph * pw;
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
+        const int x0 = (g % xg) * 8;
+        const int row = g / xg;
+        const int y = row % ph, z = row / ph;
+        const int gz = oz + z, gy = oy + y;
+        const bool rowok = gz < D && gy < H;
+        const float *src = vol + ((size_t)(rowok ? gz : 0) * H + (rowok ? gy : 0)) * W + ox + x0;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (rowok && ox + x0 + j < W && x0 + j < pw) ? src[j] : 0.f;   // zero padding at the far end (utils.py:102-112)
+        T *dst = wout + (size_t)row * pw + x0;
+        if (x0 + 8 <= pw && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            stv8(dst, v);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (x0 + j < pw) st1(dst + j, v[j]);
+        }
     }
 }
 
 // Per-voxel gather over the windows that cover it, in the reference's z -> y -> x window order.
 // The multiply and the add are rounded separately (numpy computes `pred * weights` into a temporary
 // and then `+=`), so the accumulation is bit-identical to utils.py:133-134 for identical predictions.
+// Per-axis coverage tables (first covering window + count per coordinate; window starts ascend, utils.py:63-81) are
+// built once per CTA in shared memory; a voxel's (<= STITCH_MAXC) candidates are all loaded before the ordered
+// accumulation.  Axes with more than 3 covering windows per coordinate (overlap > 2/3) take the scanning path.
+constexpr int STITCH_MAXC = 27;
 __global__ void __launch_bounds__(256) stitch_kernel(const float *__restrict__ preds,
                                                      const int32_t *__restrict__ zpos, int nz,
                                                      const int32_t *__restrict__ ypos, int ny,
                                                      const int32_t *__restrict__ xpos, int nx,
                                                      int pd, int ph, int pw, const float *__restrict__ imp,
                                                      int D, int H, int W, const uint8_t *__restrict__ body,
-                                                     float *__restrict__ prob, float thr, int32_t *__restrict__ mask) {
+                                                     float *__restrict__ prob, float thr, int32_t *__restrict__ mask, int use_tables) {
+    extern __shared__ int32_t s_tab[];                  // [D + H + W] : first << 8 | count
+    __shared__ int s_over;
     const size_t total = (size_t)D * H * W;
     const size_t per = (size_t)pd * ph * pw;
+    if (threadIdx.x == 0) s_over = 0;
+    __syncthreads();
+    if (use_tables) {
+        for (int i = threadIdx.x; i < D + H + W; i += blockDim.x) {
+            const int32_t *p; int np, ext, c;
+            if (i < D) { p = zpos; np = nz; ext = pd; c = i; }
+            else if (i < D + H) { p = ypos; np = ny; ext = ph; c = i - D; }
+            else { p = xpos; np = nx; ext = pw; c = i - D - H; }
+            int first = 0, cnt = 0;
+            for (int a = 0; a < np; ++a) {
+                const int l = c - p[a];
+                if (l >= 0 && l < ext) { if (cnt == 0) first = a; ++cnt; }
+            }
+            s_tab[i] = (first << 8) | cnt;
+            if (cnt > 3) s_over = 1;                    // more than 3 covering windows on an axis: scanning path (every CTA decides alike)
+        }
+        __syncthreads();
+        if (s_over) use_tables = 0;
+    }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        size_t rem = i;
-        const int x = (int)(rem % W); rem /= W;
-        const int y = (int)(rem % H);
-        const int z = (int)(rem / H);
+        const int x = (int)(i % (size_t)W);
+        const int rem = (int)(i / (size_t)W);
+        const int y = rem % H, z = rem / H;
         float acc = 0.f, cnt = 0.f;
-        for (int a = 0; a < nz; ++a) {
-            const int lz = z - zpos[a];
-            if (lz < 0 || lz >= pd) continue;
-            for (int b = 0; b < ny; ++b) {
-                const int ly = y - ypos[b];
-                if (ly < 0 || ly >= ph) continue;
-                for (int c = 0; c < nx; ++c) {
-                    const int lx = x - xpos[c];
-                    if (lx < 0 || lx >= pw) continue;
-                    const size_t wi = ((size_t)a * ny + b) * nx + c;
-                    const size_t li = ((size_t)lz * ph + ly) * pw + lx;
-                    const float wgt = imp[li];
-                    acc = __fadd_rn(acc, __fmul_rn(preds[wi * per + li], wgt));
-                    cnt = __fadd_rn(cnt, wgt);
+        if (use_tables) {
+            const int tz = s_tab[z], ty = s_tab[D + y], tx = s_tab[D + H + x];
+            const int a0 = tz >> 8, na = tz & 255, b0 = ty >> 8, nb = ty & 255, c0 = tx >> 8, nc = tx & 255;
+            float pv[STITCH_MAXC], wv[STITCH_MAXC];
+#pragma unroll
+            for (int k = 0; k < STITCH_MAXC; ++k) {
+                const int ia = k / 9, ib = (k / 3) % 3, ic = k % 3;
+                pv[k] = 0.f; wv[k] = 0.f;
+                if (ia < na && ib < nb && ic < nc) {
+                    const int a = a0 + ia, b = b0 + ib, c = c0 + ic;
+                    const size_t li = ((size_t)(z - zpos[a]) * ph + (y - ypos[b])) * pw + (x - xpos[c]);
+                    wv[k] = imp[li];
+                    pv[k] = preds[(((size_t)a * ny + b) * nx + c) * per + li];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < STITCH_MAXC; ++k) {
+                const int ia = k / 9, ib = (k / 3) % 3, ic = k % 3;
+                if (ia < na && ib < nb && ic < nc) {
+                    acc = __fadd_rn(acc, __fmul_rn(pv[k], wv[k]));
+                    cnt = __fadd_rn(cnt, wv[k]);
+                }
+            }
+        } else {
+            for (int a = 0; a < nz; ++a) {
+                const int lz = z - zpos[a];
+                if (lz < 0 || lz >= pd) continue;
+                for (int b = 0; b < ny; ++b) {
+                    const int ly = y - ypos[b];
+                    if (ly < 0 || ly >= ph) continue;
+                    for (int c = 0; c < nx; ++c) {
+                        const int lx = x - xpos[c];
+                        if (lx < 0 || lx >= pw) continue;
+                        const size_t wi = ((size_t)a * ny + b) * nx + c;
+                        const size_t li = ((size_t)lz * ph + ly) * pw + lx;
+                        const float wgt = imp[li];
+                        acc = __fadd_rn(acc, __fmul_rn(preds[wi * per + li], wgt));
+                        cnt = __fadd_rn(cnt, wgt);
+                    }
                 }
             }
         }
@@ -365,10 +436,12 @@ static unsigned grid_for(int64_t n, int threads, int cap_blocks) {
 extern "C" int l3d_gather_windows(const float *vol, int D, int H, int W, const int32_t *pos, int nwin,
                                   int pd, int ph, int pw, void *out, int dtype, void *stream) {
     L3D_REQUIRE(vol && pos && out && nwin > 0 && pd > 0 && ph > 0 && pw > 0, "l3d_gather_windows: bad argument");
-    const int64_t total = (int64_t)nwin * pd * ph * pw;
-    const unsigned blocks = grid_for(total, 256, 148 * 32);
+    L3D_REQUIRE(nwin <= 65535, "l3d_gather_windows: at most 65535 windows per call");
+    const int64_t groups = (int64_t)pd * ph * ((pw + 7) / 8);
+    L3D_REQUIRE(groups < (1ll << 31), "l3d_gather_windows: window too large");
+    dim3 grid(grid_for(groups, 256, 64), (unsigned)nwin);
     L3D_DISPATCH_DTYPE(dtype, T, {
-        gather_windows_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>(vol, D, H, W, pos, nwin, pd, ph, pw, (T *)out);
+        gather_windows_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(vol, D, H, W, pos, nwin, pd, ph, pw, (T *)out);
     });
     l3d_count_launch();
     L3D_CUDA_OK("l3d_gather_windows launch");
@@ -381,9 +454,14 @@ extern "C" int l3d_stitch(const float *preds, const int32_t *zpos, int nz, const
                           float threshold, int32_t *mask_out, void *stream) {
     L3D_REQUIRE(preds && zpos && ypos && xpos && importance && prob, "l3d_stitch: null argument");
     L3D_REQUIRE(nz > 0 && ny > 0 && nx > 0 && D > 0 && H > 0 && W > 0, "l3d_stitch: bad dims");
-    const unsigned blocks = grid_for((int64_t)D * H * W, 256, 148 * 32);
-    stitch_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(preds, zpos, nz, ypos, ny, xpos, nx, pd, ph, pw, importance,
-                                                           D, H, W, body_mask, prob, threshold, mask_out);
+    L3D_REQUIRE((int64_t)D * H < (1ll << 31), "l3d_stitch: volume too large");
+    const unsigned blocks = grid_for((int64_t)D * H * W, 256, 148 * 8);
+    // per-axis coverage tables in shared memory when they fit (the kernel itself falls back to scanning the window lists
+    // when some coordinate is covered by more than 3 windows of an axis, i.e. overlap > 2/3)
+    const size_t tab_bytes = sizeof(int32_t) * ((size_t)D + H + W);
+    const int use_tables = (nz < (1 << 23) && ny < (1 << 23) && nx < (1 << 23) && tab_bytes <= 40 * 1024) ? 1 : 0;
+    stitch_kernel<<<blocks, 256, use_tables ? tab_bytes : 0, (cudaStream_t)stream>>>(preds, zpos, nz, ypos, ny, xpos, nx, pd, ph, pw, importance,
+                                                                                   D, H, W, body_mask, prob, threshold, mask_out, use_tables);
     l3d_count_launch();
     L3D_CUDA_OK("l3d_stitch launch");
     return 0;

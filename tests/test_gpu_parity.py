@@ -284,3 +284,28 @@ def test_rank1_first_block(dims, monkeypatch):
     assert "l3d_dwpw_fwd_rank1" not in seen0
     print(f"{dims}: rank-1 vs oracle {rel_l2(y1, ref):.3e}, stored vs oracle {rel_l2(y0, ref):.3e}, rank-1 vs stored {rel_l2(y1, y0):.3e}")
     assert rel_l2(y1, ref) < 1e-2 and rel_l2(y0, ref) < 1e-2 and rel_l2(y1, y0) < 1e-2
+
+
+@pytest.mark.parametrize("dt", ["f32", "bf16"])
+def test_gather_windows_bit_exact(dt):
+    """l3d_gather_windows against numpy slicing + zero padding at the far end (utils.py:94-112), including patch widths that
+    are not a multiple of the 8-voxel store vector and volumes smaller than the patch."""
+    from light_unet import _native as nv
+    from light_unet.utils import window_positions
+    rng = np.random.default_rng(8)
+    tdt = torch.float32 if dt == "f32" else torch.bfloat16
+    for shape, patch, ov in [((20, 28, 36), (16, 16, 16), 0.5), ((12, 9, 21), (16, 16, 12), 0.5), ((30, 22, 45), (10, 12, 20), 0.25),
+                             ((50, 48, 100), (48, 48, 48), 0.5), ((7, 7, 7), (8, 8, 5), 0.5)]:
+        vol = rng.random(shape, dtype=np.float32)
+        pos = window_positions(shape, patch, ov)
+        plist = np.array([(z, y, x) for z in pos[0] for y in pos[1] for x in pos[2]], dtype=np.int32)
+        want = np.zeros((len(plist),) + patch, np.float32)
+        for i, (z, y, x) in enumerate(plist):
+            blk = vol[z:z + patch[0], y:y + patch[1], x:x + patch[2]]
+            want[i, :blk.shape[0], :blk.shape[1], :blk.shape[2]] = blk
+        vd, pd_ = torch.from_numpy(vol).to(DEV), torch.from_numpy(plist).to(DEV)
+        out = torch.full((len(plist),) + patch, -1.0, dtype=tdt, device=DEV)
+        nv.call("l3d_gather_windows", nv.ptr(vd), *shape, nv.ptr(pd_), len(plist), *patch, nv.ptr(out), 0 if dt == "f32" else 1,
+                nv.stream_ptr(torch.device(DEV)))
+        want_t = torch.from_numpy(want).to(tdt)
+        assert torch.equal(out.cpu(), want_t), (shape, patch)
