@@ -54,6 +54,8 @@ struct C3Args {
     int co0, cout_total;     // dense / grouped weights: first output channel of this launch and the layer's full Cout
     int stat_ld;             // channels per (n) row of the statistics arrays (>= Cout: the launch may own a channel slice)
     int tmem_cols, nraw, nsets, merge, merged_cx, dbg;
+    int tma_split;           // z-slices a halo box is requested in (several TMA operations in flight per box)
+    const void *xp; int ldx; // LD (loader warps instead of TMA): the input view / the fp32 tensor u of the rank-1 input
     const float *r1_w;       // rank-1 input (template R1): x[v][c] = r1_w[c] * u[v], u = single-channel fp32 tensor behind the tensor map
 };
 constexpr int R1_BOXW = 16, R1_X0 = 4;                   // rank-1 TMA box: x0 - 4 .. x0 + 11, so that the box starts on a 16-byte boundary
@@ -69,6 +71,10 @@ __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+// 16-byte asynchronous copy global -> shared; src_bytes = 0 zero-fills the destination (out-of-volume halo voxels)
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
 }
 template <int NW>
 __device__ __forceinline__ void worker_bar_n() { asm volatile("bar.sync 1, %0;" ::"n"(NW) : "memory"); }
@@ -90,7 +96,16 @@ __device__ __forceinline__ void worker_bar_n() { asm volatile("bar.sync 1, %0;" 
 // R1 (rank-1 input): the 16-channel input is x[v][c] = r1_w[c] * u[v] with a single-channel fp32 tensor u (the first
 // block of a 1-channel image: conv1's pointwise stage has K = 1, unet3d.py:168,209), so only u is staged -- the TMA box is
 // [z][y][16] fp32 -- and the activation pass evaluates lrelu(u * (scale_c * r1_w[c]) + shift_c) for the 16 channels.
-template <int TZ, bool MERGE, int NWARPS, bool R1 = false>
+//
+// LD (thread-private cp.async staging instead of TMA): measured at 325 windows, the TMA unit needs ~6.2 K cycles for the
+// 180 x 320-byte rows of a 57.6 KB halo box (~14 cycles per row + 1 cycle per 16 bytes; 3.2 K for the 180 x 64-byte rows of
+// the rank-1 box), only ONE box fits next to the two operand tiles at TZ = 8, and the next box can only be requested once
+// the activation pass has consumed the current one -- so the pipeline period was box latency + activation pass (7.7 K
+// cycles) with the tensor pipe and the workers waiting.  In LD mode every worker thread fetches exactly the 16-byte
+// vectors IT will activate (cp.async, zero-filled outside the volume) right after its activation pass and before the
+// epilogue of the previous tile; no barrier is involved (cp.async.wait_all of the own copies).  Measured: faster than TMA
+// only where a tile has many chunks (64 -> 32 at 24^3: -10 %), slower on the 48^3 layers -- the host picks per layer.
+template <int TZ, bool MERGE, int NWARPS, bool R1 = false, bool LD = false>
 __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 : 2)) conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, C3Args A) {
     using G = Geo<TZ>;
     constexpr int NW = NWARPS * 32, NT = NW + 32;          // worker warps + 1 issuer warp
@@ -106,8 +121,9 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
     const uint32_t btile_bytes = (uint32_t)Cout * 3 * 32;                 // one [3*Cout x 16] fp16 operand tile: (chunk, dy, dx)
     const uint32_t bsc_bytes = (uint32_t)Cout * 32;
     const uint32_t b_bytes = (uint32_t)nchunks * 9 * btile_bytes;
-    unsigned char *s_raw = smem_raw;                                       // nraw x RAW_BYTES (TMA destinations)
-    unsigned char *sA = s_raw + (size_t)nraw * G::RAW_BYTES;               // 2 x A_BYTES
+    constexpr int RAW_STRIDE = R1 ? G::HZ * HY * R1_BOXW * 4 : G::RAW_BYTES;   // bytes between the TMA destinations
+    unsigned char *s_raw = smem_raw;                                       // nraw x RAW_STRIDE (TMA destinations)
+    unsigned char *sA = s_raw + (size_t)nraw * RAW_STRIDE;                 // 2 x A_BYTES
     unsigned char *sB = sA + 2 * G::A_BYTES;                               // [chunk][dy*3+dx][3*Cout x 16]
     unsigned char *sB2 = sB + b_bytes;                                     // shortcut: [chunk][Cout x 16]
     float *s_scale = reinterpret_cast<float *>(sB2 + (has_sc ? nchunks * bsc_bytes : 0));
@@ -195,13 +211,19 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
         int pf_item = 0, pf_ch = 0, pf_n, pf_z0, pf_y0, pf_x0;
         tile_coord(tile_begin < tile_end ? tile_begin : 0, pf_n, pf_z0, pf_y0, pf_x0);
         auto issue_tma = [&]() {
-            if (pf_item >= n_items) return;
+            if (LD || pf_item >= n_items) return;
             const int rb = pf_item % nraw;
             if (tc::elect_one()) {
-                tc::mbar_expect_tx(&s_tma_full[rb], R1 ? G::HZ * HY * R1_BOXW * 4 : G::RAW_BYTES);
-                if (R1) tc::tma_load_4d(s_raw + (size_t)rb * G::RAW_BYTES, &tmap, &s_tma_full[rb], pf_x0 - R1_X0, pf_y0 - 1, pf_z0 - 1, pf_n);
-                else if (A.merged_cx) tc::tma_load_4d(s_raw + (size_t)rb * G::RAW_BYTES, &tmap, &s_tma_full[rb], (pf_x0 - 1) * CK, pf_y0 - 1, pf_z0 - 1, pf_n);
-                else tc::tma_load_5d(s_raw + (size_t)rb * G::RAW_BYTES, &tmap, &s_tma_full[rb], pf_ch * CK, pf_x0 - 1, pf_y0 - 1, pf_z0 - 1, pf_n);
+                tc::mbar_expect_tx(&s_tma_full[rb], RAW_STRIDE);
+                const int nsl = A.tma_split, zs = G::HZ / nsl;           // planes per slice
+                const uint32_t sl_bytes = (uint32_t)(RAW_STRIDE / nsl);
+                for (int sl = 0; sl < nsl; ++sl) {
+                    unsigned char *dst = s_raw + (size_t)rb * RAW_STRIDE + (size_t)sl * sl_bytes;
+                    const int zc = pf_z0 - 1 + sl * zs;
+                    if (R1) tc::tma_load_4d(dst, &tmap, &s_tma_full[rb], pf_x0 - R1_X0, pf_y0 - 1, zc, pf_n);
+                    else if (A.merged_cx) tc::tma_load_4d(dst, &tmap, &s_tma_full[rb], (pf_x0 - 1) * CK, pf_y0 - 1, zc, pf_n);
+                    else tc::tma_load_5d(dst, &tmap, &s_tma_full[rb], pf_ch * CK, pf_x0 - 1, pf_y0 - 1, zc, pf_n);
+                }
             }
             ++pf_item;
             if (++pf_ch == nchunks) {
@@ -292,6 +314,39 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
             const int hz = hv / HY;
             act_item[k] = item < G::ACT_ITEMS ? ((uint32_t)hx | ((uint32_t)hy << 8) | ((uint32_t)hz << 16)) : 0xffffffffu;
         }
+        // LD: byte offset of each of this thread's raw vectors from the tile's halo origin in global memory, and the copies
+        uint32_t g_off[LD ? ACT_PER_THREAD : 1];
+        if (LD) {
+#pragma unroll
+            for (int k = 0; k < ACT_PER_THREAD; ++k) {
+                const uint32_t ai = act_item[k];
+                const int hx = ai & 255, hy = (ai >> 8) & 255, hz = ai >> 16;
+                g_off[k] = ai != 0xffffffffu ? (uint32_t)(((hz * A.H + hy) * A.W + hx) * A.ldx * 2 + aq * 16) : 0u;
+            }
+        }
+        auto issue_copies = [&](int tl, int chunk) {
+            int n, z0, y0, x0;
+            tile_coord(tl, n, z0, y0, x0);
+            uint32_t mz = 0, my = 0, mx = 0;
+#pragma unroll
+            for (int i = 0; i < G::HZ; ++i) mz |= (uint32_t)(z0 + i - 1 >= 0 && z0 + i - 1 < A.D) << i;
+#pragma unroll
+            for (int i = 0; i < HY; ++i) my |= (uint32_t)(y0 + i - 1 >= 0 && y0 + i - 1 < A.H) << i;
+#pragma unroll
+            for (int i = 0; i < HX; ++i) mx |= (uint32_t)(x0 + i - 1 >= 0 && x0 + i - 1 < A.W) << i;
+            const char *org = reinterpret_cast<const char *>(A.xp) +
+                              (((((long long)n * A.D + (z0 - 1)) * A.H + (y0 - 1)) * A.W + (x0 - 1)) * A.ldx + chunk * CK) * 2;
+#pragma unroll
+            for (int k = 0; k < ACT_PER_THREAD; ++k) {
+                const uint32_t ai = act_item[k];
+                if ((k + 1) * NW <= G::ACT_ITEMS || ai != 0xffffffffu) {
+                    const int hx = ai & 255, hy = (ai >> 8) & 255, hz = ai >> 16;
+                    const bool ok = ((mx >> hx) & (my >> hy) & (mz >> hz) & 1u) != 0;
+                    cp_async16(s_raw + (size_t)(tid + k * NW) * 16, ok ? org + g_off[k] : reinterpret_cast<const char *>(A.xp), ok ? 16u : 0u);
+                }
+            }
+        };
+        if (LD && tile_begin < tile_end) issue_copies(tile_begin, 0);
         // epilogue role: voxel row of the MMA tiles (planes) em, em + EPG, ...
         const int em = warp >> 2, erow = (warp & 3) * 32 + lane;
         const int elx = erow & 7, ely = erow >> 3;
@@ -398,9 +453,9 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
             for (int i = 0; i < HX; ++i) mx |= (uint32_t)(x0 + i - 1 >= 0 && x0 + i - 1 < A.W) << i;
             const int tj = tile - tile_begin;
             for (int ch = 0; ch < nchunks; ++ch, ++it) {
-                const int buf = it & 1, rb = it % nraw;
+                const int buf = it & 1, rb = LD ? 0 : it % nraw;
                 unsigned char *Ab = sA + (size_t)buf * G::A_BYTES;
-                const unsigned char *Rb = s_raw + (size_t)rb * G::RAW_BYTES;
+                const unsigned char *Rb = s_raw + (size_t)rb * RAW_STRIDE;
                 // scale / shift of this thread's 8 channels
                 const float4 sc0 = *reinterpret_cast<const float4 *>(s_scale + ch * CK + aq * 8);
                 const float4 sc1 = *reinterpret_cast<const float4 *>(s_scale + ch * CK + aq * 8 + 4);
@@ -409,7 +464,8 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
                 const __half2 sl2 = __float2half2_rn(A.xn.slope);
                 const bool ident = A.xn.stats == nullptr;
                 const bool stamp = (A.dbg & 8) && blockIdx.x == 0 && it < 128 && tid == 0;
-                tc::mbar_wait(&s_tma_full[rb], (uint32_t)((it / nraw) & 1));               // raw box of this item landed
+                if (LD) asm volatile("cp.async.wait_all;" ::: "memory");                   // own copies of this item landed
+                else tc::mbar_wait(&s_tma_full[rb], (uint32_t)((it / nraw) & 1));          // raw box of this item landed
                 if (stamp) g_c3_dbg[it * 8 + 0] = clock64();
                 if (it >= 2) tc::mbar_wait(&s_mma_done[buf], (uint32_t)(((it >> 1) - 1) & 1));   // MMAs of item it-2 done: A[buf] free
                 if (stamp) g_c3_dbg[it * 8 + 1] = clock64();
@@ -483,6 +539,11 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
                 __syncwarp();
                 if (stamp) g_c3_dbg[it * 8 + 2] = clock64();
                 if (lane == 0) mbar_arrive(&s_a_full[buf]);
+                if (LD) {
+                    // own raw vectors consumed: fetch the ones of the next work item (they land under the epilogue below)
+                    if (ch + 1 < nchunks) issue_copies(tile, ch + 1);
+                    else if (tile + 1 < tile_end) issue_copies(tile + 1, 0);
+                }
                 // ---- epilogue of the previous tile (its MMAs were issued one work item ago)
                 if (ch == 0 && tile > tile_begin) {
                     const int pit = it - 1;
@@ -508,10 +569,10 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
     if (warp == NW / 32) tc::tmem_dealloc(tmem, (uint32_t)A.tmem_cols);
 }
 
-static size_t c3_smem_bytes(int TZ, int Cin, int Cout, bool has_sc, int nraw) {
+static size_t c3_smem_bytes(int TZ, int Cin, int Cout, bool has_sc, int nraw, bool rank1 = false) {
     const size_t nch = Cin / CK;
     const size_t hvox = (size_t)(TZ + 2) * HY * HX;
-    const size_t raw = hvox * CK * 2, a_bytes = 2 * (hvox * 16 + 64);
+    const size_t raw = rank1 ? (size_t)(TZ + 2) * HY * R1_BOXW * 4 : hvox * CK * 2, a_bytes = 2 * (hvox * 16 + 64);
     return (size_t)nraw * raw + 2 * a_bytes + nch * 27 * (size_t)Cout * 32 + (has_sc ? nch * (size_t)Cout * 32 : 0) +
            sizeof(float) * (2 * (size_t)Cin + 4 * (size_t)Cout);
 }
@@ -573,9 +634,9 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
         if (ns * cols1 > 512) continue;
         // raw TMA boxes in flight: a box has microseconds of latency under load, so as many as fit (up to 4)
         int nr = 1;
-        for (int c = 4; c >= 1; --c) if (c3_smem_bytes(tz, Cin, Cout, has_sc, c) <= 226 * 1024) { nr = c; break; }
+        for (int c = 4; c >= 1; --c) if (c3_smem_bytes(tz, Cin, Cout, has_sc, c, rank1) <= 226 * 1024) { nr = c; break; }
         if (force_nraw) nr = force_nraw;
-        if (c3_smem_bytes(tz, Cin, Cout, has_sc, nr) > 226 * 1024) continue;
+        if (c3_smem_bytes(tz, Cin, Cout, has_sc, nr, rank1) > 226 * 1024) continue;
         // prefer a shorter tile with double-buffered accumulators over a taller single-buffered one
         if (ns == 1 && tz > 2 && !force_tz && !force_sets) {
             const int cols_half = (tz / 2) * Cout * nacc;
@@ -585,7 +646,7 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
         break;
     }
     if (TZ == 0) return -1;
-    const size_t smem = c3_smem_bytes(TZ, Cin, Cout, has_sc, nraw);
+    const size_t smem = c3_smem_bytes(TZ, Cin, Cout, has_sc, nraw, rank1);
     const long long tiles = (long long)N * ((D + TZ - 1) / TZ) * ((H + TY - 1) / TY) * ((W + TX - 1) / TX);
     if (tiles >= (1ll << 30)) return -1;
     int cols = 32;
@@ -594,13 +655,16 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
     // TMA moves one request per innermost box row, and a 16-channel voxel is only 32 B: when the view is a whole
     // 16-channel tensor the (C, W) axes are contiguous and merge into one axis, so a box row is a 320-B x-row
     // (10 voxels) instead of ten 32-B rows (measured: the 5-D box is TMA-issue bound).
+    int tma_split = env_int("L3D_C3_TMASPLIT", 1);   // measured: no effect on the box latency (1, 2, 5 or 10 slices)
+    if (tma_split < 1 || (TZ + 2) % tma_split != 0) tma_split = 1;
+    const cuuint32_t box_z = (cuuint32_t)((TZ + 2) / tma_split);
     const bool merged_cx = !rank1 && Cin == CK && x->ldc == CK && env_int("L3D_C3_NOMERGECX", 0) == 0;
     CUtensorMap tmap;
     if (rank1) {
         const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
         const cuuint64_t rowb = (cuuint64_t)W * 4;
         const cuuint64_t strides[3] = {rowb, (cuuint64_t)H * rowb, (cuuint64_t)D * H * rowb};
-        const cuuint32_t box[4] = {R1_BOXW, HY, (cuuint32_t)(TZ + 2), 1};
+        const cuuint32_t box[4] = {R1_BOXW, HY, box_z, 1};
         const cuuint32_t estr[4] = {1, 1, 1, 1};
         if (l3d_encode_tiled(&tmap, (int)CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x->ptr, (const unsigned long long *)dims,
                              (const unsigned long long *)strides, (const unsigned *)box, (const unsigned *)estr)) return 3;
@@ -608,7 +672,7 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
         const cuuint64_t dims[4] = {(cuuint64_t)W * CK, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
         const cuuint64_t rowb = (cuuint64_t)W * CK * 2;
         const cuuint64_t strides[3] = {rowb, (cuuint64_t)H * rowb, (cuuint64_t)D * H * rowb};
-        const cuuint32_t box[4] = {HX * CK, HY, (cuuint32_t)(TZ + 2), 1};
+        const cuuint32_t box[4] = {HX * CK, HY, box_z, 1};
         const cuuint32_t estr[4] = {1, 1, 1, 1};
         if (l3d_encode_tiled(&tmap, (int)CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x->ptr, (const unsigned long long *)dims,
                              (const unsigned long long *)strides, (const unsigned *)box, (const unsigned *)estr)) return 3;
@@ -616,7 +680,7 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
         const cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
         const cuuint64_t es = 2, ld = (cuuint64_t)x->ldc;
         const cuuint64_t strides[4] = {ld * es, (cuuint64_t)W * ld * es, (cuuint64_t)H * W * ld * es, (cuuint64_t)D * H * W * ld * es};
-        const cuuint32_t box[5] = {CK, HX, HY, (cuuint32_t)(TZ + 2), 1};
+        const cuuint32_t box[5] = {CK, HX, HY, box_z, 1};
         const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
         if (l3d_encode_tiled(&tmap, (int)CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x->ptr, (const unsigned long long *)dims,
                              (const unsigned long long *)strides, (const unsigned *)box, (const unsigned *)estr)) return 3;
@@ -630,7 +694,7 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
     A.stat_ld = stat_ld > 0 ? stat_ld : Cout;
     A.co0 = co0; A.cout_total = cout_total > 0 ? cout_total : Cout;
     A.tmem_cols = cols; A.nraw = nraw; A.nsets = nsets; A.merged_cx = merged_cx ? 1 : 0; A.dbg = env_int("L3D_C3_DEBUG_SKIP", 0);
-    A.r1_w = r1_w;
+    A.r1_w = r1_w; A.tma_split = tma_split; A.xp = x->ptr; A.ldx = x->ldc;
     A.merge = (3 * Cout <= 256 && env_int("L3D_C3_NOMERGE", 0) == 0) ? 1 : 0;
     int occ = (int)((227 * 1024) / (smem + 2048));
     if (occ > 3) occ = 3;
@@ -641,15 +705,21 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     long long grid = (long long)sms * occ;
     if (grid > tiles) grid = tiles;
-#define L3D_C3_LAUNCH_R(TZV, MG, NWV, R1V)                                                                                          \
+#define L3D_C3_LAUNCH_L(TZV, MG, NWV, R1V, LDV)                                                                                     \
     do {                                                                                                                    \
         static bool attr_set = false;                                                                                       \
         if (!attr_set) {                                                                                                    \
-            cudaError_t e = cudaFuncSetAttribute(conv3_tc_kernel<TZV, MG, NWV, R1V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
+            cudaError_t e = cudaFuncSetAttribute(conv3_tc_kernel<TZV, MG, NWV, R1V, LDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
             if (e != cudaSuccess) { l3d_set_error("conv3_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 3; } \
             attr_set = true;                                                                                                \
         }                                                                                                                   \
-        conv3_tc_kernel<TZV, MG, NWV, R1V><<<(unsigned)grid, NWV * 32 + 32, smem, (cudaStream_t)stream>>>(tmap, A);          \
+        conv3_tc_kernel<TZV, MG, NWV, R1V, LDV><<<(unsigned)grid, NWV * 32 + 32, smem, (cudaStream_t)stream>>>(tmap, A); \
+    } while (0)
+    /* thread-private cp.async staging instead of TMA: with 12 worker warps (one CTA per SM), not for the rank-1 input */
+#define L3D_C3_LAUNCH_R(TZV, MG, NWV, R1V)                                                                                          \
+    do {                                                                                                                    \
+        if (NWV == 12 && use_loader && !R1V) L3D_C3_LAUNCH_L(TZV, MG, 12, false, true);                                     \
+        else L3D_C3_LAUNCH_L(TZV, MG, NWV, R1V, false);                                                                     \
     } while (0)
 #define L3D_C3_LAUNCH(TZV, MG, NWV) L3D_C3_LAUNCH_R(TZV, MG, NWV, false)
 #define L3D_C3_TZ(MG, NWV)                                \
@@ -661,6 +731,11 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
     }
     // 12 worker warps (3 per scheduler) hide the latency of the activation pass and the epilogue when one CTA owns the SM
     const int nwarps = env_int("L3D_C3_WARPS", occ == 1 ? 12 : 8);
+    // 1: where only one TMA box fits and a tile has >= 4 channel chunks (measured at 325 windows: 64 -> 32 + shortcut at 24^3
+    // 1033 -> 935 us; slower than TMA on the one- and two-chunk 48^3 layers: 1035 -> 1327 us, 1897 -> 2455 us); 2: wherever
+    // possible; 0: never
+    const int ld_mode = env_int("L3D_C3_LOADER", 1);
+    const bool use_loader = (ld_mode == 2 || (ld_mode == 1 && nraw == 1 && Cin / CK >= 4)) && (long long)(TZ + 2) * H * W * x->ldc * 2 < (1ll << 31);
     if (rank1) {
         // merged MMAs only (3 * Cout <= 256 checked above)
         if (nwarps == 12) {
@@ -684,6 +759,7 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
 #undef L3D_C3_TZ
 #undef L3D_C3_LAUNCH
 #undef L3D_C3_LAUNCH_R
+#undef L3D_C3_LAUNCH_L
     l3d_count_launch();
     l3d_note_kernel("conv3_tc_kernel");
     L3D_CUDA_OK("l3d_conv3 (tcgen05 implicit GEMM) launch");
