@@ -71,14 +71,50 @@ def measured_traffic(kernel: str):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML in-process every 2 ms (a timed region of a few
+    steps is tens of milliseconds -- shorter than one `nvidia-smi -lms` period); nvidia-smi every 200 ms as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
         self.index, self.proc, self.path = index, None, None
+        self.thread, self.stop_flag, self.samples, self.bits, self.max_mhz = None, False, [], 0, None
+        self.nvml, self.handle = None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            try:
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml, self.handle = pynvml, h
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv, h = self.nvml, self.handle
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml is not None:
+            import threading
+            self.stop_flag, self.samples, self.bits = False, [], 0
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
@@ -90,6 +126,14 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            self.thread = None
+            if self.samples:
+                out.update(sm_mhz=float(np.median(self.samples)), sm_max_mhz=self.max_mhz,
+                           reasons=sorted(n for b, n in self.REASONS if self.bits & b), samples=len(self.samples), source="nvml")
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -113,7 +157,7 @@ class ClockSampler:
         except Exception:
             pass
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm), source="nvidia-smi")
         return out
 
 
