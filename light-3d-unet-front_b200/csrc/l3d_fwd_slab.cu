@@ -8,7 +8,7 @@
 //   * no padded tile voxels: every stencil output is a real voxel.
 // Per (slab, 16-channel chunk): TMA raw box (double-buffered, requested one item ahead) -> activation pass (InstanceNorm +
 // LeakyReLU + Dropout3d of the producer) into a zero-bordered fp32 tile -> depthwise 3x3x3 on CUDA cores, each thread
-// 4 channels x 2 rows x XT x-consecutive voxels with 16-byte shared-memory loads -> fp16 K-major operand tile
+// 2 channels x 2 rows x XT x-consecutive voxels with 8-byte shared-memory loads -> fp16 K-major operand tile
 // (double-buffered) -> tcgen05.mma for the pointwise (+ shortcut) stage, accumulating over the chunks in TMEM ->
 // epilogue: tcgen05.ld, bf16 store, InstanceNorm statistics.
 #include <cuda.h>
@@ -18,7 +18,7 @@
 
 namespace {
 
-constexpr int CK = 16, NT = 256;
+constexpr int CK = 16;
 constexpr int ACT_SLOTS = 8;
 
 struct SlabArgs {
@@ -45,8 +45,13 @@ __device__ __forceinline__ void fma4(float4 &a, const float4 &w, const float4 &v
     a.x = fmaf(w.x, v.x, a.x); a.y = fmaf(w.y, v.y, a.y); a.z = fmaf(w.z, v.z, a.z); a.w = fmaf(w.w, v.w, a.w);
 }
 
-template <int XT>
-__global__ void __launch_bounds__(NT, 2) dwpw_slab_kernel(const __grid_constant__ CUtensorMap tmap, SlabArgs A) {
+__device__ __forceinline__ void fma2(float2 &a, const float2 &w, const float2 &v) {
+    a.x = fmaf(w.x, v.x, a.x); a.y = fmaf(w.y, v.y, a.y);
+}
+
+// NT threads: 256 (two CTAs per SM where shared memory allows) or 384 (slabs with more than 256 stencil tasks)
+template <int XT, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) dwpw_slab_kernel(const __grid_constant__ CUtensorMap tmap, SlabArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_tma_full[2], s_mma_done[2];
     __shared__ uint32_t s_tmem;
@@ -129,14 +134,16 @@ __global__ void __launch_bounds__(NT, 2) dwpw_slab_kernel(const __grid_constant_
         }
         act_slot[k] = v;
     }
-    // stencil: task = (xb, y pair, z, channel quad), z fastest: the two tasks of a quarter warp are an odd number of
-    // voxels apart (PP is odd), so their 16-byte loads fall into different bank halves; a thread's tasks all share its
-    // quad cq = tid & 3
-    const int cq = tid & 3;
+    // stencil: task = (xb, y pair, z, channel pair), z fastest: the two tasks of a half warp are an odd number of
+    // voxels apart (PP is odd), so their 8-byte loads fall into different bank halves; a thread's tasks all share its
+    // channel pair cp = tid & 7 (NT is a multiple of 8).  Two channels per task (not four): twice the tasks, so that a
+    // 12^3 slab of 3 planes keeps 9 warps busy instead of 4.5 -- the stencil is latency-bound, not FMA-bound
+    const int cp = tid & 7;
     const int xblocks = W / XT;
-    const int ntasks = SZ * (H / 2) * xblocks * 4;
+    const int ntasks = SZ * (H / 2) * xblocks * 8;
     // epilogue: TMEM lane quarter warp & 3; the two warp groups alternate over the (accumulator, tile, 16-column) jobs
     const int eq = warp & 3, eg = warp >> 2;
+    constexpr int NG = NT / 128;
 
     // depthwise taps of the first chunk (register prefetch, one chunk ahead)
     float dwr0 = A.dw_w[tid], dwr1 = (tid + NT < CK * 27) ? A.dw_w[tid + NT] : 0.f;
@@ -227,48 +234,46 @@ __global__ void __launch_bounds__(NT, 2) dwpw_slab_kernel(const __grid_constant_
         __syncthreads();                 // stencil tile complete, raw box consumed
         // ---- depthwise stencil: 4 channels x 2 rows x XT voxels per task
         if (!(A.dbg & 2)) {
-            const float4 *in4 = reinterpret_cast<const float4 *>(s_in);
-            const float4 *w4 = reinterpret_cast<const float4 *>(s_dw + buf * 27 * CK) + cq;
+            const float2 *in2 = reinterpret_cast<const float2 *>(s_in);
+            const float2 *w2p = reinterpret_cast<const float2 *>(s_dw + buf * 27 * CK) + cp;
             unsigned char *Am = sA + (size_t)buf * nacc * a_bytes;
-            const uint32_t kg_off = (uint32_t)(cq >> 1) * MT * 2048 + (uint32_t)(cq & 1) * 8;
+            const uint32_t kg_off = (uint32_t)(cp >> 2) * MT * 2048 + (uint32_t)(cp & 3) * 4;
 #pragma unroll 1
             for (int tsk = tid; tsk < ntasks; tsk += NT) {
-                int b = tsk >> 2;
+                int b = tsk >> 3;
                 const int z = b % SZ; b /= SZ;
                 const int y = (b % (H / 2)) * 2;
                 const int xb = b / (H / 2);
                 const int vox = z * PP + y * RP + xb * XT, row = (z * H + y) * W + xb * XT;
                 // output rows y and y + 1: every input row is loaded once and feeds both
-                float4 acc0[XT], acc1[XT];
+                float2 acc0[XT], acc1[XT];
 #pragma unroll
-                for (int i = 0; i < XT; ++i) { acc0[i] = make_float4(0.f, 0.f, 0.f, 0.f); acc1[i] = acc0[i]; }
+                for (int i = 0; i < XT; ++i) { acc0[i] = make_float2(0.f, 0.f); acc1[i] = acc0[i]; }
 #pragma unroll
                 for (int dz = 0; dz < 3; ++dz) {
 #pragma unroll
                     for (int hy = 0; hy < 4; ++hy) {
-                        const float4 *rp = in4 + (size_t)(vox + dz * PP + hy * RP) * 4 + cq;
-                        float4 v[XT + 2];
+                        const float2 *rp = in2 + (size_t)(vox + dz * PP + hy * RP) * 8 + cp;
+                        float2 v[XT + 2];
 #pragma unroll
-                        for (int x = 0; x < XT + 2; ++x) v[x] = rp[x * 4];
+                        for (int x = 0; x < XT + 2; ++x) v[x] = rp[x * 8];
                         if (hy <= 2) {
-                            const float4 w0 = w4[((dz * 3 + hy) * 3 + 0) * 4], w1 = w4[((dz * 3 + hy) * 3 + 1) * 4], w2 = w4[((dz * 3 + hy) * 3 + 2) * 4];
+                            const float2 w0 = w2p[((dz * 3 + hy) * 3 + 0) * 8], w1 = w2p[((dz * 3 + hy) * 3 + 1) * 8], w2 = w2p[((dz * 3 + hy) * 3 + 2) * 8];
 #pragma unroll
-                            for (int i = 0; i < XT; ++i) { fma4(acc0[i], w0, v[i]); fma4(acc0[i], w1, v[i + 1]); fma4(acc0[i], w2, v[i + 2]); }
+                            for (int i = 0; i < XT; ++i) { fma2(acc0[i], w0, v[i]); fma2(acc0[i], w1, v[i + 1]); fma2(acc0[i], w2, v[i + 2]); }
                         }
                         if (hy >= 1) {
-                            const float4 w0 = w4[((dz * 3 + hy - 1) * 3 + 0) * 4], w1 = w4[((dz * 3 + hy - 1) * 3 + 1) * 4], w2 = w4[((dz * 3 + hy - 1) * 3 + 2) * 4];
+                            const float2 w0 = w2p[((dz * 3 + hy - 1) * 3 + 0) * 8], w1 = w2p[((dz * 3 + hy - 1) * 3 + 1) * 8], w2 = w2p[((dz * 3 + hy - 1) * 3 + 2) * 8];
 #pragma unroll
-                            for (int i = 0; i < XT; ++i) { fma4(acc1[i], w0, v[i]); fma4(acc1[i], w1, v[i + 1]); fma4(acc1[i], w2, v[i + 2]); }
+                            for (int i = 0; i < XT; ++i) { fma2(acc1[i], w0, v[i]); fma2(acc1[i], w1, v[i + 1]); fma2(acc1[i], w2, v[i + 2]); }
                         }
                     }
                 }
 #pragma unroll
                 for (int i = 0; i < XT; ++i) {
                     const int r0 = row + i, r1 = row + W + i;
-                    *reinterpret_cast<uint2 *>(Am + kg_off + (uint32_t)(r0 >> 3) * 128 + (uint32_t)(r0 & 7) * 16) =
-                        make_uint2(pack_f16x2(acc0[i].x, acc0[i].y), pack_f16x2(acc0[i].z, acc0[i].w));
-                    *reinterpret_cast<uint2 *>(Am + kg_off + (uint32_t)(r1 >> 3) * 128 + (uint32_t)(r1 & 7) * 16) =
-                        make_uint2(pack_f16x2(acc1[i].x, acc1[i].y), pack_f16x2(acc1[i].z, acc1[i].w));
+                    *reinterpret_cast<uint32_t *>(Am + kg_off + (uint32_t)(r0 >> 3) * 128 + (uint32_t)(r0 & 7) * 16) = pack_f16x2(acc0[i].x, acc0[i].y);
+                    *reinterpret_cast<uint32_t *>(Am + kg_off + (uint32_t)(r1 >> 3) * 128 + (uint32_t)(r1 & 7) * 16) = pack_f16x2(acc1[i].x, acc1[i].y);
                 }
             }
         }
@@ -297,7 +302,7 @@ __global__ void __launch_bounds__(NT, 2) dwpw_slab_kernel(const __grid_constant_
             const uint32_t trow = tmem + ((uint32_t)(eq * 32) << 16);
             const int cbn = Cout >> 4;
             const int njobs = nacc * MT * cbn;
-            for (int j = eg; j < njobs; j += 2) {
+            for (int j = eg; j < njobs; j += NG) {
                 const int cb = (j % cbn) * 16;
                 const int m = (j / cbn) % MT, a = j / (cbn * MT);
                 if (m * 128 + eq * 32 >= rows_valid) continue;                  // warp-uniform: no valid row in this quarter
@@ -342,18 +347,22 @@ __global__ void __launch_bounds__(NT, 2) dwpw_slab_kernel(const __grid_constant_
     if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)A.tmem_cols);
 }
 
-struct SlabPlan { int SZ, MT, RP, PP, cols, occ; size_t smem; uint32_t raw_bytes, raw_stride, in_bytes; };
+struct SlabPlan { int SZ, MT, RP, PP, cols, occ, nt; size_t smem; uint32_t raw_bytes, raw_stride, in_bytes; };
 
 static bool slab_plan(int Cin, int Cout, bool has_sc, int D, int H, int W, int XT, SlabPlan &best) {
     const int nacc = has_sc ? 2 : 1;
     double best_score = 0.0;
     bool found = false;
+    const char *fe = getenv("L3D_SLAB_SZ");                       // tuning / test knob: force the slab height
+    const int force_sz = (fe && fe[0]) ? atoi(fe) : 0;
     for (int SZ = (D < 8 ? D : 8); SZ >= 1; --SZ) {
+        if (force_sz && SZ != force_sz) continue;
         const int rows = SZ * H * W;
         const int MT = (rows + 127) / 128;
         if (MT > 4 || MT * Cout * nacc > 512) continue;
-        if ((SZ + 2) * H * W * 2 > ACT_SLOTS * NT) continue;
         SlabPlan p;
+        p.nt = SZ * (H / 2) * (W / XT) * 8 > 256 ? 384 : 256;
+        if ((SZ + 2) * H * W * 2 > ACT_SLOTS * p.nt) continue;
         p.SZ = SZ; p.MT = MT;
         p.RP = (W + 2) | 1;
         p.PP = ((H + 2) * p.RP) | 1;
@@ -368,6 +377,7 @@ static bool slab_plan(int Cin, int Cout, bool has_sc, int D, int H, int W, int X
         while (p.cols < MT * Cout * nacc) p.cols <<= 1;
         p.occ = (int)((227 * 1024) / (p.smem + 2048));
         if (p.occ > 2) p.occ = 2;
+        if (p.nt > 256) p.occ = 1;
         if (p.occ * p.cols > 512) p.occ = 512 / p.cols;
         if (p.occ < 1) continue;
         const int zs = (D + SZ - 1) / SZ;
@@ -428,17 +438,18 @@ int l3d_dwpw_fwd_slab(const l3d_act *x, const l3d_norm *xn, int N, int D, int H,
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     long long grid = (long long)sms * p.occ;
     if (grid > slabs) grid = slabs;
-#define L3D_SLAB_LAUNCH(XTV)                                                                                                  \
+#define L3D_SLAB_LAUNCH(XTV, NTV)                                                                                             \
     do {                                                                                                                      \
         static bool attr_set = false;                                                                                         \
         if (!attr_set) {                                                                                                      \
-            cudaError_t e = cudaFuncSetAttribute(dwpw_slab_kernel<XTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
+            cudaError_t e = cudaFuncSetAttribute(dwpw_slab_kernel<XTV, NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
             if (e != cudaSuccess) { l3d_set_error("dwpw_slab: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 3; }   \
             attr_set = true;                                                                                                  \
         }                                                                                                                     \
-        dwpw_slab_kernel<XTV><<<(unsigned)grid, NT, p.smem, (cudaStream_t)stream>>>(tmap, A);                                 \
+        dwpw_slab_kernel<XTV, NTV><<<(unsigned)grid, NTV, p.smem, (cudaStream_t)stream>>>(tmap, A);                           \
     } while (0)
-    if (XT == 6) L3D_SLAB_LAUNCH(6); else L3D_SLAB_LAUNCH(4);
+    if (XT == 6) { if (p.nt == 384) L3D_SLAB_LAUNCH(6, 384); else L3D_SLAB_LAUNCH(6, 256); }
+    else         { if (p.nt == 384) L3D_SLAB_LAUNCH(4, 384); else L3D_SLAB_LAUNCH(4, 256); }
 #undef L3D_SLAB_LAUNCH
     l3d_count_launch();
     l3d_note_kernel("dwpw_slab_kernel");
