@@ -55,6 +55,7 @@ struct C3Args {
     int stat_ld;             // channels per (n) row of the statistics arrays (>= Cout: the launch may own a channel slice)
     int tmem_cols, nraw, nsets, merge, merged_cx, dbg;
     int tma_split;           // z-slices a halo box is requested in (several TMA operations in flight per box)
+    int rot;                 // three rotating 57 KB slots instead of {raw, A0, A1}: see the kernel comment
     const void *xp; int ldx; // LD (loader warps instead of TMA): the input view / the fp32 tensor u of the rank-1 input
     const float *r1_w;       // rank-1 input (template R1): x[v][c] = r1_w[c] * u[v], u = single-channel fp32 tensor behind the tensor map
 };
@@ -105,6 +106,13 @@ __device__ __forceinline__ void worker_bar_n() { asm volatile("bar.sync 1, %0;" 
 // vectors IT will activate (cp.async, zero-filled outside the volume) right after its activation pass and before the
 // epilogue of the previous tile; no barrier is involved (cp.async.wait_all of the own copies).  Measured: faster than TMA
 // only where a tile has many chunks (64 -> 32 at 24^3: -10 %), slower on the 48^3 layers -- the host picks per layer.
+//
+// rot (three rotating slots; used where only ONE raw box fits): with fixed roles {raw, A0, A1} the box of item it+1 can only
+// be requested after the activation pass of item it has consumed the raw buffer, so the period is box latency (6.2 K
+// cycles) + activation pass (1.4 K).  The three buffers have the same size, so the roles rotate instead: item it lands in
+// slot X(it) and is activated into slot Y(it), with X(it+1) = Y(it-1) and Y(it+1) = X(it).  X(it+1) is free as soon as the
+// MMAs of item it-1 have completed -- BEFORE item it is activated -- so warp 0 of the workers requests box it+1 at the top of
+// iteration it and the TMA unit always has the next box queued.  (Measured slower than the fixed roles, see the host side.)
 template <int TZ, bool MERGE, int NWARPS, bool R1 = false, bool LD = false>
 __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 : 2)) conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, C3Args A) {
     using G = Geo<TZ>;
@@ -123,8 +131,11 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
     const uint32_t b_bytes = (uint32_t)nchunks * 9 * btile_bytes;
     constexpr int RAW_STRIDE = R1 ? G::HZ * HY * R1_BOXW * 4 : G::RAW_BYTES;   // bytes between the TMA destinations
     unsigned char *s_raw = smem_raw;                                       // nraw x RAW_STRIDE (TMA destinations)
-    unsigned char *sA = s_raw + (size_t)nraw * RAW_STRIDE;                 // 2 x A_BYTES
-    unsigned char *sB = sA + 2 * G::A_BYTES;                               // [chunk][dy*3+dx][3*Cout x 16]
+    const bool rot = !R1 && !LD && A.rot != 0;                             // slots k = 0..2 at smem_raw + k * A_BYTES
+    unsigned char *sA = rot ? smem_raw : s_raw + (size_t)nraw * RAW_STRIDE;   // 2 x A_BYTES
+    unsigned char *sB = rot ? smem_raw + 3 * (size_t)G::A_BYTES : sA + 2 * G::A_BYTES;   // [chunk][dy*3+dx][3*Cout x 16]
+    auto slot_x = [](int it) { const int m = it % 3; return m == 0 ? 0 : m == 1 ? 2 : 1; };   // raw slot of item it
+    auto slot_y = [](int it) { const int m = it % 3; return m == 0 ? 1 : m == 1 ? 0 : 2; };   // operand slot of item it
     unsigned char *sB2 = sB + b_bytes;                                     // shortcut: [chunk][Cout x 16]
     float *s_scale = reinterpret_cast<float *>(sB2 + (has_sc ? nchunks * bsc_bytes : 0));
     float *s_shift = s_scale + Cin;
@@ -211,7 +222,7 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
         int pf_item = 0, pf_ch = 0, pf_n, pf_z0, pf_y0, pf_x0;
         tile_coord(tile_begin < tile_end ? tile_begin : 0, pf_n, pf_z0, pf_y0, pf_x0);
         auto issue_tma = [&]() {
-            if (LD || pf_item >= n_items) return;
+            if (LD || rot || pf_item >= n_items) return;
             const int rb = pf_item % nraw;
             if (tc::elect_one()) {
                 tc::mbar_expect_tx(&s_tma_full[rb], RAW_STRIDE);
@@ -246,7 +257,7 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
             if (ch == 0 && tj >= nsets) tc::mbar_wait(&s_acc_free[set], (uint32_t)(((tj / nsets) - 1) & 1));   // epilogue of tile tj-nsets done
             tc::fence_after_sync();
             if (stamp && lane == 0) g_c3_dbg[it * 8 + 6] = clock64();
-            const uint64_t ad0 = tc::smem_desc(sA_u + buf * G::A_BYTES, G::PLANE, ROWPITCH);
+            const uint64_t ad0 = tc::smem_desc(sA_u + (rot ? slot_y(it) : buf) * G::A_BYTES, G::PLANE, ROWPITCH);
             const uint64_t bd0 = tc::smem_desc(sB_u + (uint32_t)(ch * 9) * btile_bytes, 3 * Cout * 16, 128);
             const uint32_t d_t = tmem_u + (uint32_t)(set * acc_cols);
             const bool first = ch == 0;
@@ -347,6 +358,20 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
             }
         };
         if (LD && tile_begin < tile_end) issue_copies(tile_begin, 0);
+        // rot: request the halo box of item j = (tile tl, chunk) into slot X(j)  (one lane)
+        auto rot_issue = [&](int j, int tl, int chunk) {
+            int n, z0, y0, x0;
+            tile_coord(tl, n, z0, y0, x0);
+            const int b3 = j % 3;
+            unsigned char *dst = smem_raw + (size_t)slot_x(j) * G::A_BYTES;
+            tc::mbar_expect_tx(&s_tma_full[b3], G::RAW_BYTES);
+            if (A.merged_cx) tc::tma_load_4d(dst, &tmap, &s_tma_full[b3], (x0 - 1) * CK, y0 - 1, z0 - 1, n);
+            else tc::tma_load_5d(dst, &tmap, &s_tma_full[b3], chunk * CK, x0 - 1, y0 - 1, z0 - 1, n);
+        };
+        if (rot && tid == 0 && n_items > 0) {
+            rot_issue(0, tile_begin, 0);
+            if (n_items > 1) rot_issue(1, nchunks > 1 ? tile_begin : tile_begin + 1, nchunks > 1 ? 1 : 0);
+        }
         // epilogue role: voxel row of the MMA tiles (planes) em, em + EPG, ...
         const int em = warp >> 2, erow = (warp & 3) * 32 + lane;
         const int elx = erow & 7, ely = erow >> 3;
@@ -454,8 +479,17 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
             const int tj = tile - tile_begin;
             for (int ch = 0; ch < nchunks; ++ch, ++it) {
                 const int buf = it & 1, rb = LD ? 0 : it % nraw;
-                unsigned char *Ab = sA + (size_t)buf * G::A_BYTES;
-                const unsigned char *Rb = s_raw + (size_t)rb * RAW_STRIDE;
+                unsigned char *Ab = sA + (size_t)(rot ? slot_y(it) : buf) * G::A_BYTES;
+                const unsigned char *Rb = rot ? smem_raw + (size_t)slot_x(it) * G::A_BYTES : s_raw + (size_t)rb * RAW_STRIDE;
+                if (rot && warp == 0 && it >= 1 && it + 1 < n_items) {
+                    // slot X(it+1) = Y(it-1) is free once the MMAs of item it-1 have completed: request box it+1 now
+                    tc::mbar_wait(&s_mma_done[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) & 1));
+                    if (lane == 0) {
+                        if (ch + 1 < nchunks) rot_issue(it + 1, tile, ch + 1);
+                        else rot_issue(it + 1, tile + 1, 0);
+                    }
+                    __syncwarp();
+                }
                 // scale / shift of this thread's 8 channels
                 const float4 sc0 = *reinterpret_cast<const float4 *>(s_scale + ch * CK + aq * 8);
                 const float4 sc1 = *reinterpret_cast<const float4 *>(s_scale + ch * CK + aq * 8 + 4);
@@ -465,6 +499,11 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
                 const bool ident = A.xn.stats == nullptr;
                 const bool stamp = (A.dbg & 8) && blockIdx.x == 0 && it < 128 && tid == 0;
                 if (LD) asm volatile("cp.async.wait_all;" ::: "memory");                   // own copies of this item landed
+                else if (rot) {
+                    tc::mbar_wait(&s_tma_full[it % 3], (uint32_t)((it / 3) & 1));
+                    // Y(it) = X(it-1): every worker warp must be done reading the raw box of item it-1
+                    if (it >= 1) tc::mbar_wait(&s_a_full[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) & 1));
+                }
                 else tc::mbar_wait(&s_tma_full[rb], (uint32_t)((it / nraw) & 1));          // raw box of this item landed
                 if (stamp) g_c3_dbg[it * 8 + 0] = clock64();
                 if (it >= 2) tc::mbar_wait(&s_mma_done[buf], (uint32_t)(((it >> 1) - 1) & 1));   // MMAs of item it-2 done: A[buf] free
@@ -694,7 +733,7 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
     A.stat_ld = stat_ld > 0 ? stat_ld : Cout;
     A.co0 = co0; A.cout_total = cout_total > 0 ? cout_total : Cout;
     A.tmem_cols = cols; A.nraw = nraw; A.nsets = nsets; A.merged_cx = merged_cx ? 1 : 0; A.dbg = env_int("L3D_C3_DEBUG_SKIP", 0);
-    A.r1_w = r1_w; A.tma_split = tma_split; A.xp = x->ptr; A.ldx = x->ldc;
+    A.r1_w = r1_w; A.tma_split = tma_split; A.xp = x->ptr; A.ldx = x->ldc; A.rot = 0;
     A.merge = (3 * Cout <= 256 && env_int("L3D_C3_NOMERGE", 0) == 0) ? 1 : 0;
     int occ = (int)((227 * 1024) / (smem + 2048));
     if (occ > 3) occ = 3;
@@ -705,6 +744,7 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     long long grid = (long long)sms * occ;
     if (grid > tiles) grid = tiles;
+    size_t smem_launch = smem;
 #define L3D_C3_LAUNCH_L(TZV, MG, NWV, R1V, LDV)                                                                                     \
     do {                                                                                                                    \
         static bool attr_set = false;                                                                                       \
@@ -713,7 +753,7 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
             if (e != cudaSuccess) { l3d_set_error("conv3_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 3; } \
             attr_set = true;                                                                                                \
         }                                                                                                                   \
-        conv3_tc_kernel<TZV, MG, NWV, R1V, LDV><<<(unsigned)grid, NWV * 32 + 32, smem, (cudaStream_t)stream>>>(tmap, A); \
+        conv3_tc_kernel<TZV, MG, NWV, R1V, LDV><<<(unsigned)grid, NWV * 32 + 32, smem_launch, (cudaStream_t)stream>>>(tmap, A); \
     } while (0)
     /* thread-private cp.async staging instead of TMA: with 12 worker warps (one CTA per SM), not for the rank-1 input */
 #define L3D_C3_LAUNCH_R(TZV, MG, NWV, R1V)                                                                                          \
@@ -736,6 +776,14 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
     // possible; 0: never
     const int ld_mode = env_int("L3D_C3_LOADER", 1);
     const bool use_loader = (ld_mode == 2 || (ld_mode == 1 && nraw == 1 && Cin / CK >= 4)) && (long long)(TZ + 2) * H * W * x->ldc * 2 < (1ll << 31);
+    // rotating slots where only one raw box fits (and the box is requested in one piece by TMA).  Off by default: measured
+    // SLOWER at 325 windows (16 -> 16 at 48^3: 1101 -> 1187 us, 32 -> 16 + shortcut: 1912 -> 2195 us, 32 -> 32 at 24^3: 406 -> 446 us)
+    // -- with the next box streaming in under the MMAs, the TMA writes, the operand reads of the tensor core and the
+    // activation pass compete for the same 128 B / clock of shared-memory bandwidth, which is what really bounds the tile
+    if (!rank1 && !(nwarps == 12 && use_loader) && nraw == 1 && tma_split == 1 && env_int("L3D_C3_ROT", 0) != 0 && smem + 128 <= 226 * 1024) {
+        A.rot = 1;
+        smem_launch = smem + 128;
+    }
     if (rank1) {
         // merged MMAs only (3 * Cout <= 256 checked above)
         if (nwarps == 12) {
