@@ -450,8 +450,11 @@ __global__ void __launch_bounds__(NT) conv3_fwd_kernel(
 // vector; grid.y = sample, per-(n,c) scale/shift tables in shared memory; all loads of a cell are issued first.
 // R1: the shortcut tensor is not materialised -- it is the rank-1 map r[v][c] = r1_w[c] * x[v] of a single-channel
 // tensor x (the first block's 1x1x1 shortcut conv of a 1-channel image): `r` then points at x (1 channel, stride ldr).
+// ncu (325 windows): at 97-121 registers only two CTAs (16 warps, 24 % of the SM's warp slots) are resident and the kernel
+// sits on long-scoreboard stalls at 3.7 TB/s.  The rank-1 variant fits three CTAs in 80 registers (0.68 -> 0.63 ms); the
+// two-tensor variant spills 260 B at that bound and gets slower (1.24 -> 1.33 ms), so it keeps two.
 template <typename T, bool R1>
-__global__ void __launch_bounds__(256) merge_fwd_kernel(
+__global__ void __launch_bounds__(256, R1 ? 3 : 2) merge_fwd_kernel(
     const T *__restrict__ t2, int ld2, NormDev n2, const T *__restrict__ r, int ldr, NormDev nr, const float *__restrict__ r1_w,
     int N, int C, int D, int H, int W, float slope,
     T *__restrict__ out, int ldo, T *__restrict__ pooled, int ldp) {
@@ -582,6 +585,74 @@ __global__ void __launch_bounds__(256) merge_head_fwd_kernel(
             const size_t oi = ((size_t)n * OC + oc) * nvox + v;
             if (logits != nullptr) logits[oi] = acc;
             prob[oi] = 1.f / (1.f + expf(-acc));
+        }
+    }
+}
+
+// The same for C = 16 in bf16 storage (the configured model's head, unet3d.py:201-202,220-221): thread = HALF a voxel
+// (8 channels = one 16-byte vector per tensor), so every load / store instruction of a warp covers 512 contiguous bytes,
+// the lane pair adds its two partial head sums with one shuffle, and 40 registers keep the SM's warp slots full (the
+// voxel-per-thread kernel above: 119 registers, 24 % of the warp slots, 3.6 TB/s).  Two voxel halves per thread in flight.
+__global__ void __launch_bounds__(256, 4) merge_head16_fwd_kernel(
+    const bf16 *__restrict__ t2, int ld2, NormDev n2, const bf16 *__restrict__ r, int ldr, NormDev nr,
+    int N, size_t nvox, float slope, bf16 *__restrict__ out, int ldo,
+    const float *__restrict__ head_w, const float *__restrict__ head_b, int OC,
+    float *__restrict__ prob, float *__restrict__ logits) {
+    constexpr int C = 16;
+    __shared__ float s_sc2[C], s_sh2[C], s_scr[C], s_hw[4 * C];
+    const int n = blockIdx.y;
+    if (threadIdx.x < C) {
+        const int c = threadIdx.x;
+        float a, b, cc, d;
+        norm_scale_shift(n2, N, C, n, c, a, b);
+        norm_scale_shift(nr, N, C, n, c, cc, d);
+        s_sc2[c] = a; s_sh2[c] = b + d; s_scr[c] = cc;
+        for (int oc = 0; oc < 4; ++oc) s_hw[oc * C + c] = oc < OC ? head_w[(size_t)oc * C + c] : 0.f;
+    }
+    __syncthreads();
+    const int h = threadIdx.x & 1;
+    const float *sc2 = s_sc2 + h * 8, *sh2 = s_sh2 + h * 8, *scr = s_scr + h * 8;     // read from shared memory in the loop: no spills at 64 registers
+    const size_t total = 2 * nvox, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 2 * stride) {
+        uint4 ra[2], rb[2];
+        bool ok[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const size_t i = i0 + u * stride;
+            ok[u] = i < total;                       // both lanes of a pair share the voxel, so they agree
+            if (ok[u]) {
+                const size_t vox = (size_t)n * nvox + (i >> 1);
+                ra[u] = ldraw(t2 + vox * ld2 + h * 8);
+                rb[u] = ldraw(r + vox * ldr + h * 8);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!ok[u]) continue;
+            const size_t v = (i0 + u * stride) >> 1, vox = (size_t)n * nvox + v;
+            float a[8], b[8], o[8];
+            cvt_raw(t2, ra[u], a);
+            cvt_raw(t2, rb[u], b);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = lrelu(fmaf(a[j], sc2[j], fmaf(b[j], scr[j], sh2[j])), slope);
+            if (out != nullptr) stv(out + vox * ldo + h * 8, o);
+            for (int oc = 0; oc < OC; ++oc) {
+                float acc = 0.f;
+                if (oc < 4) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc = fmaf(round_as(t2, o[j]), s_hw[oc * C + h * 8 + j], acc);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc = fmaf(round_as(t2, o[j]), head_w[(size_t)oc * C + h * 8 + j], acc);
+                }
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                if (h == 0) {
+                    acc += head_b[oc];
+                    const size_t oi = ((size_t)n * OC + oc) * nvox + v;
+                    if (logits != nullptr) logits[oi] = acc;
+                    prob[oi] = 1.f / (1.f + expf(-acc));
+                }
+            }
         }
     }
 }
@@ -1327,6 +1398,17 @@ extern "C" int l3d_merge_fwd(const l3d_act *t2, const l3d_norm *n2, const l3d_ac
         if (gx_ > cap_) gx_ = cap_;
         const unsigned gx = (unsigned)gx_;
         dim3 grid(gx, (unsigned)N);
+        if (C == 16 && t2->dtype == L3D_BF16) {
+            size_t gh = (2 * nvox + 511) / 512;
+            const size_t caph = (148 * 16 + (size_t)N - 1) / (size_t)N;
+            if (gh > caph) gh = caph;
+            dim3 gridh((unsigned)gh, (unsigned)N);
+            merge_head16_fwd_kernel<<<gridh, 256, 0, st>>>((const bf16 *)t2->ptr, t2->ldc, d2, (const bf16 *)r->ptr, r->ldc, dr, N, nvox, slope,
+                                                          has_out ? (bf16 *)out->ptr : nullptr, has_out ? out->ldc : 0, head_w, head_b, OC, prob, logits);
+            l3d_count_launch();
+            L3D_CUDA_OK("l3d_merge_fwd (head) launch");
+            return 0;
+        }
         L3D_DISPATCH_DTYPE(t2->dtype, T, {
             if (C <= 16)
                 merge_head_fwd_kernel<T, 16><<<grid, 256, 0, st>>>((const T *)t2->ptr, t2->ldc, d2, (const T *)r->ptr, r->ldc, dr, N, C, nvox, slope,
