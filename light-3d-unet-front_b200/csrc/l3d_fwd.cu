@@ -451,10 +451,11 @@ __global__ void __launch_bounds__(NT) conv3_fwd_kernel(
 // R1: the shortcut tensor is not materialised -- it is the rank-1 map r[v][c] = r1_w[c] * x[v] of a single-channel
 // tensor x (the first block's 1x1x1 shortcut conv of a 1-channel image): `r` then points at x (1 channel, stride ldr).
 // ncu (325 windows): at 97-121 registers only two CTAs (16 warps, 24 % of the SM's warp slots) are resident and the kernel
-// sits on long-scoreboard stalls at 3.7 TB/s.  The rank-1 variant fits three CTAs in 80 registers (0.68 -> 0.63 ms); the
-// two-tensor variant spills 260 B at that bound and gets slower (1.24 -> 1.33 ms), so it keeps two.
+// sits on long-scoreboard stalls at 3.7 TB/s.  With the scale / shift tables read from shared memory both variants fit
+// three CTAs in 80 registers without spills (rank-1: 0.68 -> 0.57 ms at 4.4 TB/s; four CTAs at 64 registers spill and
+// are no faster).
 template <typename T, bool R1>
-__global__ void __launch_bounds__(256, R1 ? 3 : 2) merge_fwd_kernel(
+__global__ void __launch_bounds__(256, 3) merge_fwd_kernel(
     const T *__restrict__ t2, int ld2, NormDev n2, const T *__restrict__ r, int ldr, NormDev nr, const float *__restrict__ r1_w,
     int N, int C, int D, int H, int W, float slope,
     T *__restrict__ out, int ldo, T *__restrict__ pooled, int ldp) {
@@ -465,6 +466,7 @@ __global__ void __launch_bounds__(256, R1 ? 3 : 2) merge_fwd_kernel(
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         norm_scale_shift(n2, N, C, n, c, s_sc2[c], s_sh2[c]);
         norm_scale_shift(nr, N, C, n, c, s_scr[c], s_shr[c]);
+        s_sh2[c] += s_shr[c];                       // the two shifts only ever appear as their sum
         if (R1) s_scr[c] *= r1_w[c];
     }
     __syncthreads();
@@ -478,12 +480,11 @@ __global__ void __launch_bounds__(256, R1 ? 3 : 2) merge_fwd_kernel(
         const int cy = (int)(rem % CH);
         const int cz = (int)(rem / CH);
         const int c = q * V;
-        float sc2[V], sh2[V], scr[V], mx[V];
+        // scale / shift tables are read from shared memory where they are used (24 registers less: one more CTA per SM)
+        const float *sc2 = s_sc2 + c, *sh2 = s_sh2 + c, *scr = s_scr + c;
+        float mx[V];
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            sc2[j] = s_sc2[c + j]; sh2[j] = s_sh2[c + j] + s_shr[c + j]; scr[j] = s_scr[c + j];
-            mx[j] = -INFINITY;
-        }
+        for (int j = 0; j < V; ++j) mx[j] = -INFINITY;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {        // one z-plane of the cell at a time: 8 raw loads in flight
             uint4 ra[4], rb[4];
