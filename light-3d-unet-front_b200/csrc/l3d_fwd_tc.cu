@@ -588,7 +588,7 @@ int l3d_convt_fwd_tc(const l3d_act *x, int N, int d, int h, int w_, const float 
         attr_set = true;
     }
     int occ = (int)((227 * 1024) / (smem + 2048));
-    if (occ > 2) occ = 2;
+    if (occ > 4) occ = 4;                        // 56 registers; the TMEM columns (8 * Cout per CTA) bound it below
     if (occ < 1) occ = 1;
     if (occ * cols > 512) occ = 512 / cols;
     int dev = 0, sms = 148;
