@@ -676,8 +676,10 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
         for (int c = 4; c >= 1; --c) if (c3_smem_bytes(tz, Cin, Cout, has_sc, c, rank1) <= 226 * 1024) { nr = c; break; }
         if (force_nraw) nr = force_nraw;
         if (c3_smem_bytes(tz, Cin, Cout, has_sc, nr, rank1) > 226 * 1024) continue;
-        // prefer a shorter tile with double-buffered accumulators over a taller single-buffered one
-        if (ns == 1 && tz > 2 && !force_tz && !force_sets) {
+        // prefer a shorter tile with double-buffered accumulators over a taller single-buffered one -- except for single-chunk
+        // layers (Cin = 16), whose MMA phase per tile is short: 16 -> 32 + shortcut at 24^3, 325 windows: TZ 8 / one set 442 us,
+        // TZ 6 482 us, TZ 4 / two sets 541 us
+        if (ns == 1 && tz > 2 && !force_tz && !force_sets && Cin > CK) {
             const int cols_half = (tz / 2) * Cout * nacc;
             if (2 * cols_half <= 512 && tz / 2 >= 2) continue;
         }

@@ -79,7 +79,9 @@ class Workspace:
             raise ValueError(f"input spatial size {dims} is too small for three 2x poolings")
         self.level_dims = lv
         z = lambda *s: torch.zeros(*s, dtype=dtype, device=device)
-        emp = lambda *s: torch.empty(*s, dtype=dtype, device=device)
+        # L3D_DEBUG_POISON=1 (development aid): every workspace buffer starts as NaN, so a read of a never-written element shows up
+        poison = os.environ.get("L3D_DEBUG_POISON", "0") == "1"
+        emp = (lambda *s: torch.full(s, float("nan"), dtype=dtype, device=device)) if poison else (lambda *s: torch.empty(*s, dtype=dtype, device=device))
         # concat buffers [up | skip]; zero-initialised once: the centre-pad rim (odd sizes) stays zero
         self.cat = {0: z(N, *lv[0], 2 * e[0]), 1: z(N, *lv[1], 2 * e[1]), 2: z(N, *lv[2], 2 * e[2])}
         self.pooled = {0: emp(N, *lv[1], e[0]), 1: emp(N, *lv[2], e[1]), 2: emp(N, *lv[3], e[2])}
@@ -112,7 +114,7 @@ class Workspace:
             # gradient tensors are fp32 whatever the activation storage type: the InstanceNorm backward subtracts
             # the per-(n,c) mean of the incoming gradient, and the Focal Tversky gradient is almost constant over
             # the voxels, so bf16 rounding of the gradient (relative to its magnitude) swamps the centred signal
-            emp = lambda *s: torch.empty(*s, dtype=torch.float32, device=device)
+            emp = (lambda *s: torch.full(s, float("nan"), dtype=torch.float32, device=device)) if poison else (lambda *s: torch.empty(*s, dtype=torch.float32, device=device))
             self.g_cat = {k: emp(N, *lv[k], 2 * e[k]) for k in range(3)}      # grad of [up | skip]
             self.g_pooled = {k: emp(N, *lv[k + 1], e[k]) for k in range(3)}   # grad of the pooled block inputs
             self.g_out = {b.name: emp(N, *lv[b.level], b.cout) for b in plan.blocks
