@@ -1,6 +1,7 @@
+"""Development aid: bf16-storage forward parity against the oracle at other patch sizes (64^3, 96^3, 50^3, 40^3)."""
 import os, sys, time
 import numpy as np, torch
-ROOT = "/root/repo"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "light-3d-unet-front_b200")); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle import synth, unet_ref
 from light_unet.models import Lightweight3DUNet

@@ -1,5 +1,8 @@
+"""Development aid: repeats the worst fp32 training-gradient parity case in one process and prints the distribution of the
+worst per-tensor error (see the tolerance note in tests/test_gpu_train.py)."""
 import sys, os, io, contextlib
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests"); sys.path.insert(0, "/root/repo/light-3d-unet-front_b200")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "light-3d-unet-front_b200"))
 import test_gpu_train as T
 vals = []
 for i in range(60):
