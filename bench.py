@@ -2,7 +2,7 @@
 """bench.py -- headline benchmark of the B200-native Light-3D-Unet hot path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--variant dws|grouped|dense] [--dtype bf16|f32] [--skip-train] [--skip-cpu]
+                    [--variant dws|grouped|dense] [--dtype f16|f32] [--skip-train] [--skip-cpu]
 
 One JSON line on stdout (rank 0).  Metric (BASELINE.json): sliding-window inference volume-voxels/s on the
 synthetic whole-body 4 mm PET volume (128x128x320, 48^3 windows, 50 % overlap, Gaussian stitching, threshold
@@ -281,7 +281,7 @@ def bench_ours(args):
             by_kernel[k] = tuple(v)
     top = max(by_kernel.items(), key=lambda kv: kv[1][1])
     pk = peaks()
-    es = 2 if args.dtype == "bf16" else 4
+    es = 2 if args.dtype == "f16" else 4
     achieved = top[1][2] / (top[1][1] * 1e-3) / 1e9 if top[1][1] > 0 else 0.0
     step_ms = ms / args.steps
     roofline = {"bound": "hbm", "kernel": top[0], "achieved": round(achieved, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
@@ -379,7 +379,7 @@ def bench_train(args, device, rank, world):
         step_e2e(i)
     ms_e2e = timed(step_e2e, steps, world, device)
     pk = peaks()
-    es = 2 if args.dtype == "bf16" else 4
+    es = 2 if args.dtype == "f16" else 4
     per_step_s = ms * 1e-3 / steps
     return {"metric": "train 48^3 patches/s", "value": round(world * B * steps / (ms * 1e-3), 1), "unit": "patches/s",
             "ms_per_step": round(ms / steps, 3), "steps": steps, "global_batch": world * B,
@@ -504,7 +504,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variant", default="dws", choices=sorted(VARIANTS))
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--dtype", default="f16", choices=["f16", "f32"])
     ap.add_argument("--skip-train", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()

@@ -30,16 +30,17 @@
 extern "C" {
 #endif
 
-#define L3D_ABI_VERSION 3
+#define L3D_ABI_VERSION 4
 
-enum { L3D_F32 = 0, L3D_BF16 = 1 };
+/* activation storage: fp32, or IEEE fp16 (stores saturate to +-65504); accumulation and statistics are fp32 / double */
+enum { L3D_F32 = 0, L3D_F16 = 1 };
 
 /* A channels-last activation view (spatial dims are passed per call). */
 typedef struct {
     void   *ptr;
     int32_t C;      /* channels in this view */
     int32_t ldc;    /* elements between consecutive voxels */
-    int32_t dtype;  /* L3D_F32 | L3D_BF16 */
+    int32_t dtype;  /* L3D_F32 | L3D_F16 */
     int32_t pad_;
 } l3d_act;
 

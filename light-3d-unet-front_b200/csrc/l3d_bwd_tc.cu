@@ -24,8 +24,8 @@ constexpr int PLANE = TV * 16;          // bytes of one 8-channel group of a til
 
 struct PwTcArgs {
     const float *gz; int ldg;
-    const bf16 *t; int ldt; NormDev nt; const double *red;
-    const bf16 *u; int ldu; NormDev un;
+    const h16 *t; int ldt; NormDev nt; const double *red;
+    const h16 *u; int ldu; NormDev un;
     int N; long long vox;
     int Cg, Cu;
     const float *w; float *g_w;
@@ -65,10 +65,10 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
     for (int i = tid; i < Cg * Cu; i += NT) {               // w[c][k]
         const int k = i % Cu, c = i / Cu;
         const float wv = A.w[i];
-        const bf16 hi = __float2bfloat16_rn(wv);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(wv);
         const uint32_t off = tc::tile_off(k, c, Cu);
-        *reinterpret_cast<bf16 *>(sWh + off) = hi;
-        *reinterpret_cast<bf16 *>(sWl + off) = __float2bfloat16_rn(wv - __bfloat162float(hi));
+        *reinterpret_cast<__nv_bfloat16 *>(sWh + off) = hi;
+        *reinterpret_cast<__nv_bfloat16 *>(sWl + off) = __float2bfloat16_rn(wv - __bfloat162float(hi));
     }
     tc::fence_async_smem();
     tc::fence_before_sync();
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
     tc::fence_after_sync();
     const uint32_t tmem = s_tmem;
     const uint32_t d1 = tmem, d2 = tmem + (uint32_t)Cu;
-    const uint32_t id_k = tc::idesc_16b_m128(Cu, 1, 1, false, false), id_mn = tc::idesc_16b_m128(Cu, 1, 1, true, true);
+    const uint32_t id_k = tc::idesc_16b_m128(Cu, 1, 1, false, false), id_mn = tc::idesc_16b_m128(Cu, 1, 0, true, true);   // A: bf16 gradient hi / lo, B: stored fp16 activation
     const uint32_t sGh_u = tc::smem_u32(sGh), sGl_u = tc::smem_u32(sGl), sU_u = tc::smem_u32(sU), sWh_u = tc::smem_u32(sWh), sWl_u = tc::smem_u32(sWl);
 
     const long long tiles_per_sample = (A.vox + TV - 1) / TV;
@@ -139,8 +139,8 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const int c = q * 8 + 2 * j;
-                            g[2 * j] = fmaf(s_ca[c], g[2 * j], fmaf(s_cb[c], __uint_as_float(tw[j] << 16), s_cd[c]));
-                            g[2 * j + 1] = fmaf(s_ca[c + 1], g[2 * j + 1], fmaf(s_cb[c + 1], __uint_as_float(tw[j] & 0xffff0000u), s_cd[c + 1]));
+                            g[2 * j] = fmaf(s_ca[c], g[2 * j], fmaf(s_cb[c], h16_lo(tw[j]), s_cd[c]));
+                            g[2 * j + 1] = fmaf(s_ca[c + 1], g[2 * j + 1], fmaf(s_cb[c + 1], h16_hi(tw[j]), s_cd[c + 1]));
                         }
                     }
                     split2(g[0], g[1], hi.x, lo.x); split2(g[2], g[3], hi.y, lo.y);
@@ -174,8 +174,8 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const int c = q * 8 + 2 * j;
-                            g[2 * j] = fmaf(s_ca[c], g[2 * j], fmaf(s_cb[c], __uint_as_float(tw[j] << 16), s_cd[c]));
-                            g[2 * j + 1] = fmaf(s_ca[c + 1], g[2 * j + 1], fmaf(s_cb[c + 1], __uint_as_float(tw[j] & 0xffff0000u), s_cd[c + 1]));
+                            g[2 * j] = fmaf(s_ca[c], g[2 * j], fmaf(s_cb[c], h16_lo(tw[j]), s_cd[c]));
+                            g[2 * j + 1] = fmaf(s_ca[c + 1], g[2 * j + 1], fmaf(s_cb[c + 1], h16_hi(tw[j]), s_cd[c + 1]));
                         }
                     }
                     split2(g[0], g[1], hi.x, lo.x); split2(g[2], g[3], hi.y, lo.y);
@@ -197,9 +197,9 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const int k = q * 8 + 2 * j;
-                                const float a0 = lrelu(fmaf(__uint_as_float(w4[j] << 16), s_us[k], s_uh[k]), A.un.slope);
-                                const float a1 = lrelu(fmaf(__uint_as_float(w4[j] & 0xffff0000u), s_us[k + 1], s_uh[k + 1]), A.un.slope);
-                                w4[j] = pack2_bf16(a0, a1);
+                                const float a0 = lrelu(fmaf(h16_lo(w4[j]), s_us[k], s_uh[k]), A.un.slope);
+                                const float a1 = lrelu(fmaf(h16_hi(w4[j]), s_us[k + 1], s_uh[k + 1]), A.un.slope);
+                                w4[j] = pack_h16x2(a0, a1);
                             }
                             o = make_uint4(w4[0], w4[1], w4[2], w4[3]);
                         }
@@ -301,10 +301,10 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
     for (int i = tid; i < Cg * Cu; i += NT) {
         const int k = i % Cu, c = i / Cu;
         const float wv = A.w[i];
-        const bf16 hi = __float2bfloat16_rn(wv);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(wv);
         const uint32_t off = tc::tile_off(k, c, Cu);
-        *reinterpret_cast<bf16 *>(sWh + off) = hi;
-        *reinterpret_cast<bf16 *>(sWl + off) = __float2bfloat16_rn(wv - __bfloat162float(hi));
+        *reinterpret_cast<__nv_bfloat16 *>(sWh + off) = hi;
+        *reinterpret_cast<__nv_bfloat16 *>(sWl + off) = __float2bfloat16_rn(wv - __bfloat162float(hi));
     }
     tc::fence_async_smem();
     tc::fence_before_sync();
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
     tc::fence_after_sync();
     const uint32_t tmem = s_tmem;
     const uint32_t d1 = tmem, d2 = tmem + (uint32_t)Cu;
-    const uint32_t id_k = tc::idesc_16b_m128(Cu, 1, 1, false, false), id_mn = tc::idesc_16b_m128(Cu, 1, 1, true, true);
+    const uint32_t id_k = tc::idesc_16b_m128(Cu, 1, 1, false, false), id_mn = tc::idesc_16b_m128(Cu, 1, 0, true, true);   // A: bf16 gradient hi / lo, B: stored fp16 activation
     const uint32_t smem_u = tc::smem_u32(smem), sWh_u = tc::smem_u32(sWh), sWl_u = tc::smem_u32(sWl);
     const long long tiles_per_sample = (A.vox + TV - 1) / TV;
     const long long total_tiles = tiles_per_sample * A.N;
@@ -366,8 +366,8 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int c = q * 8 + 2 * j;
-                        g[2 * j] = fmaf(s_ca[c], g[2 * j], fmaf(s_cb[c], __uint_as_float(tw[j] << 16), s_cd[c]));
-                        g[2 * j + 1] = fmaf(s_ca[c + 1], g[2 * j + 1], fmaf(s_cb[c + 1], __uint_as_float(tw[j] & 0xffff0000u), s_cd[c + 1]));
+                        g[2 * j] = fmaf(s_ca[c], g[2 * j], fmaf(s_cb[c], h16_lo(tw[j]), s_cd[c]));
+                        g[2 * j + 1] = fmaf(s_ca[c + 1], g[2 * j + 1], fmaf(s_cb[c + 1], h16_hi(tw[j]), s_cd[c + 1]));
                     }
                 }
                 split2(g[0], g[1], hi.x, lo.x); split2(g[2], g[3], hi.y, lo.y);
@@ -479,7 +479,7 @@ int l3d_pw_bwd_tc(const l3d_act *gz, const l3d_act *t, const l3d_norm *nt, const
     { const char *e = getenv("L3D_NO_TC_BWD"); if (e && e[0] == '1') return -1; }
     const int Cg = gz->C, Cu = u->C;
     const bool has_nt = nt != nullptr && nt->stats != nullptr, has_gu = !act_null(g_u);
-    if (u->dtype != L3D_BF16 || gz->dtype != L3D_F32 || (has_nt && t->dtype != L3D_BF16)) return -1;
+    if (u->dtype != L3D_F16 || gz->dtype != L3D_F32 || (has_nt && t->dtype != L3D_F16)) return -1;
     if (Cg % 16 != 0 || Cu % 16 != 0 || Cg > 128 || Cu > 256) return -1;
     auto al = [](const l3d_act *a, int elems, int bytes) { return a->ldc % elems == 0 && reinterpret_cast<uintptr_t>(a->ptr) % bytes == 0; };
     if (!al(gz, 4, 16) || !al(u, 8, 16) || (has_nt && !al(t, 8, 16)) || (has_gu && !al(g_u, 4, 16))) return -1;
@@ -496,8 +496,8 @@ int l3d_pw_bwd_tc(const l3d_act *gz, const l3d_act *t, const l3d_norm *nt, const
     while (cols < 2 * Cu) cols <<= 1;
     PwTcArgs A;
     A.gz = (const float *)gz->ptr; A.ldg = gz->ldc;
-    A.t = has_nt ? (const bf16 *)t->ptr : nullptr; A.ldt = has_nt ? t->ldc : 0; A.nt = norm_dev(nt); A.red = red;
-    A.u = (const bf16 *)u->ptr; A.ldu = u->ldc; A.un = norm_dev(un);
+    A.t = has_nt ? (const h16 *)t->ptr : nullptr; A.ldt = has_nt ? t->ldc : 0; A.nt = norm_dev(nt); A.red = red;
+    A.u = (const h16 *)u->ptr; A.ldu = u->ldc; A.un = norm_dev(un);
     A.N = N; A.vox = vox; A.Cg = Cg; A.Cu = Cu;
     A.w = w; A.g_w = g_w;
     A.g_u = has_gu ? (float *)g_u->ptr : nullptr; A.ldgu = has_gu ? g_u->ldc : 0; A.accumulate = accumulate_gu;
@@ -581,7 +581,7 @@ namespace {
 
 struct CtTcArgs {
     const float *g; int ldg; int OD, OH, OW, oz, oy, ox;
-    const bf16 *x; int ldx; int N, d, h, w;
+    const h16 *x; int ldx; int N, d, h, w;
     int Cin, Cout;
     const float *wgt; float *g_w; float *g_b;
     float *g_x; int ldgx; int accumulate;
@@ -610,17 +610,17 @@ __global__ void __launch_bounds__(NT) convt_bwd_tc_kernel(CtTcArgs A) {
         for (int i = tid; i < Cin * Cout; i += NT) {
             const int co = i % Cout, ci = i / Cout;
             const float wv = A.wgt[(size_t)i * 8 + tap];
-            const bf16 hi = __float2bfloat16_rn(wv);
+            const __nv_bfloat16 hi = __float2bfloat16_rn(wv);
             const uint32_t off = tc::tile_off(ci, co, Cin);
-            *reinterpret_cast<bf16 *>(sWh + slot * wtap_bytes + off) = hi;
-            *reinterpret_cast<bf16 *>(sWl + slot * wtap_bytes + off) = __float2bfloat16_rn(wv - __bfloat162float(hi));
+            *reinterpret_cast<__nv_bfloat16 *>(sWh + slot * wtap_bytes + off) = hi;
+            *reinterpret_cast<__nv_bfloat16 *>(sWl + slot * wtap_bytes + off) = __float2bfloat16_rn(wv - __bfloat162float(hi));
         }
     };
     if (A.w_resident && do_dgrad) for (int tap = 0; tap < 8; ++tap) stage_w(tap, tap);
     // constant part of the X tile: channel Cin = 1, channels Cin+1 .. Cin+15 = 0
     for (int i = tid; i < 2 * TV; i += NT) {
         const int v = i & (TV - 1), q = (Cin >> 3) + (i >> 7);
-        *reinterpret_cast<uint4 *>(sX + (size_t)q * PLANE + (size_t)v * 16) = make_uint4(i < TV ? 0x00003f80u : 0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4 *>(sX + (size_t)q * PLANE + (size_t)v * 16) = make_uint4(i < TV ? 0x00003c00u : 0u, 0u, 0u, 0u)   /* fp16 1.0 */;
     }
     tc::fence_async_smem();
     tc::fence_before_sync();
@@ -629,7 +629,7 @@ __global__ void __launch_bounds__(NT) convt_bwd_tc_kernel(CtTcArgs A) {
     const uint32_t tmem = s_tmem;
     const uint32_t d1 = tmem;                                     // Cin columns
     const uint32_t d2 = tmem + (uint32_t)Cin;                     // TP accumulators of NX columns
-    const uint32_t id_k = tc::idesc_16b_m128(Cin, 1, 1, false, false), id_mn = tc::idesc_16b_m128(NX, 1, 1, true, true);
+    const uint32_t id_k = tc::idesc_16b_m128(Cin, 1, 1, false, false), id_mn = tc::idesc_16b_m128(NX, 1, 0, true, true);   // A: bf16 gradient hi / lo, B: stored fp16 input
     const uint32_t sGh_u = tc::smem_u32(sGh), sGl_u = tc::smem_u32(sGl), sX_u = tc::smem_u32(sX), sWh_u = tc::smem_u32(sWh), sWl_u = tc::smem_u32(sWl);
     const long long nvox = (long long)A.N * A.d * A.h * A.w;
     const long long ntiles = (nvox + TV - 1) / TV;
@@ -755,7 +755,7 @@ int l3d_convt_bwd_tc(const l3d_act *g_out, int OD, int OH, int OW, int oz, int o
     { const char *e = getenv("L3D_NO_TC_BWD"); if (e && e[0] == '1') return -1; }
     const int Cin = x->C, Cout = g_out->C;
     const bool has_gx = !act_null(g_x);
-    if (x->dtype != L3D_BF16 || g_out->dtype != L3D_F32 || g_w == nullptr) return -1;
+    if (x->dtype != L3D_F16 || g_out->dtype != L3D_F32 || g_w == nullptr) return -1;
     if (Cin % 16 != 0 || Cout % 16 != 0 || Cin > 128 || Cout > 128) return -1;
     auto al = [](const l3d_act *a, int elems, int bytes) { return a->ldc % elems == 0 && reinterpret_cast<uintptr_t>(a->ptr) % bytes == 0; };
     if (!al(g_out, 4, 16) || !al(x, 8, 16) || (has_gx && !al(g_x, 4, 16))) return -1;
@@ -774,7 +774,7 @@ int l3d_convt_bwd_tc(const l3d_act *g_out, int OD, int OH, int OW, int oz, int o
     while (cols < TP * NX + Cin) cols <<= 1;
     CtTcArgs A;
     A.g = (const float *)g_out->ptr; A.ldg = g_out->ldc; A.OD = OD; A.OH = OH; A.OW = OW; A.oz = oz; A.oy = oy; A.ox = ox;
-    A.x = (const bf16 *)x->ptr; A.ldx = x->ldc; A.N = N; A.d = d; A.h = h; A.w = w_;
+    A.x = (const h16 *)x->ptr; A.ldx = x->ldc; A.N = N; A.d = d; A.h = h; A.w = w_;
     A.Cin = Cin; A.Cout = Cout; A.wgt = w; A.g_w = g_w; A.g_b = g_b;
     A.g_x = has_gx ? (float *)g_x->ptr : nullptr; A.ldgx = has_gx ? g_x->ldc : 0; A.accumulate = accumulate_gx;
     A.TP = TP; A.w_resident = w_resident; A.tmem_cols = cols;

@@ -49,8 +49,8 @@ struct C3Args {
     const float *dw_w, *pw_w;   // depthwise-separable: [Cin][27], [Cout][Cin]
     const float *sc_w;          // shortcut [Cout][Cin] or NULL
     int Cout;
-    bf16 *t; int ldt; double *t_stats;
-    bf16 *r; int ldr; double *r_stats;
+    h16 *t; int ldt; double *t_stats;
+    h16 *r; int ldr; double *r_stats;
     int co0, cout_total;     // dense / grouped weights: first output channel of this launch and the layer's full Cout
     int stat_ld;             // channels per (n) row of the statistics arrays (>= Cout: the launch may own a channel slice)
     int tmem_cols, nraw, nsets, merge, merged_cx, dbg;
@@ -61,10 +61,6 @@ struct C3Args {
 };
 constexpr int R1_BOXW = 16, R1_X0 = 4;                   // rank-1 TMA box: x0 - 4 .. x0 + 11, so that the box starts on a 16-byte boundary
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t *>(&v);
-}
 __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
     __half2 v = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&v);
@@ -406,7 +402,7 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
             const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(set * acc_cols);
             if (!(A.dbg & 2))
             for (int a = 0; a < nacc; ++a) {
-                bf16 *outb = a == 0 ? A.t : A.r;
+                h16 *outb = a == 0 ? A.t : A.r;
                 const int ldo = a == 0 ? A.ldt : A.ldr;
                 float *stat = s_stat + a * 2 * Cout;
                 for (int cb = 0; cb < Cout; cb += 16) {
@@ -421,9 +417,9 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
                         uint32_t pk[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            pk[j] = valid ? pack_bf16x2(v[2 * j], v[2 * j + 1]) : 0u;
-                            const float r0 = __uint_as_float(pk[j] << 16);
-                            const float r1 = __uint_as_float(pk[j] & 0xffff0000u);
+                            pk[j] = valid ? pack_h16x2(v[2 * j], v[2 * j + 1]) : 0u;
+                            const float r0 = h16_lo(pk[j]);
+                            const float r1 = h16_hi(pk[j]);
                             sv[2 * j] += r0; sv[2 * j + 1] += r1;
                             sv[16 + 2 * j] = fmaf(r0, r0, sv[16 + 2 * j]); sv[16 + 2 * j + 1] = fmaf(r1, r1, sv[16 + 2 * j + 1]);
                         }
@@ -437,8 +433,8 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
                             rcv.x = __shfl_xor_sync(0xffffffffu, snd.x, 1); rcv.y = __shfl_xor_sync(0xffffffffu, snd.y, 1);
                             rcv.z = __shfl_xor_sync(0xffffffffu, snd.z, 1); rcv.w = __shfl_xor_sync(0xffffffffu, snd.w, 1);
                             const bool pvalid = __shfl_xor_sync(0xffffffffu, valid ? 1 : 0, 1) != 0;
-                            bf16 *own = outb + (vox0 + (size_t)p * zstride) * (size_t)ldo + cb + (odd ? 8 : 0);
-                            bf16 *pe = odd ? own - ldo : own, *po = odd ? own : own + ldo;      // even / odd voxel of the pair
+                            h16 *own = outb + (vox0 + (size_t)p * zstride) * (size_t)ldo + cb + (odd ? 8 : 0);
+                            h16 *pe = odd ? own - ldo : own, *po = odd ? own : own + ldo;      // even / odd voxel of the pair
                             if (odd ? pvalid : valid) *reinterpret_cast<uint4 *>(pe) = odd ? rcv : h0;
                             if (odd ? valid : pvalid) *reinterpret_cast<uint4 *>(po) = odd ? h1 : rcv;
                         }
@@ -547,14 +543,14 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
 #pragma unroll
                                     for (int j = 0; j < 8; ++j) f[j] = ru[kk];
                                 } else {
-                                    f[0] = __uint_as_float(r4.x << 16); f[1] = __uint_as_float(r4.x & 0xffff0000u);
-                                    f[2] = __uint_as_float(r4.y << 16); f[3] = __uint_as_float(r4.y & 0xffff0000u);
-                                    f[4] = __uint_as_float(r4.z << 16); f[5] = __uint_as_float(r4.z & 0xffff0000u);
-                                    f[6] = __uint_as_float(r4.w << 16); f[7] = __uint_as_float(r4.w & 0xffff0000u);
+                                    f[0] = h16_lo(r4.x); f[1] = h16_hi(r4.x);
+                                    f[2] = h16_lo(r4.y); f[3] = h16_hi(r4.y);
+                                    f[4] = h16_lo(r4.z); f[5] = h16_hi(r4.z);
+                                    f[6] = h16_lo(r4.w); f[7] = h16_hi(r4.w);
                                 }
                                 uint4 o;
-                                if (!R1 && ident) {        // already-activated input (a block's first conv): bf16 -> fp16 only
-                                    o = make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]), pack_f16x2(f[6], f[7]));
+                                if (!R1 && ident) {        // already-activated input (a block's first conv): the stored fp16 values are the operand
+                                    o = r4;
                                 } else {
                                     f[0] = fmaf(f[0], sc0.x, sh0.x); f[1] = fmaf(f[1], sc0.y, sh0.y); f[2] = fmaf(f[2], sc0.z, sh0.z); f[3] = fmaf(f[3], sc0.w, sh0.w);
                                     f[4] = fmaf(f[4], sc1.x, sh1.x); f[5] = fmaf(f[5], sc1.y, sh1.y); f[6] = fmaf(f[6], sc1.z, sh1.z); f[7] = fmaf(f[7], sc1.w, sh1.w);
@@ -651,7 +647,7 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
     if (disabled) return -1;
     const int Cin = x->C, Cout = t->C;
     const bool has_sc = sc_w != nullptr;
-    if (x->dtype != L3D_BF16 || t->dtype != L3D_BF16) return -1;
+    if (x->dtype != L3D_F16 || t->dtype != L3D_F16) return -1;
     if (Cin % 16 != 0 || Cout % 16 != 0 || Cout > 256) return -1;
     auto aligned = [](const l3d_act *a, int mult) {
         return (a->ldc % mult == 0) && (reinterpret_cast<uintptr_t>(a->ptr) % (2 * mult) == 0);
@@ -715,7 +711,7 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
         const cuuint64_t strides[3] = {rowb, (cuuint64_t)H * rowb, (cuuint64_t)D * H * rowb};
         const cuuint32_t box[4] = {HX * CK, HY, box_z, 1};
         const cuuint32_t estr[4] = {1, 1, 1, 1};
-        if (l3d_encode_tiled(&tmap, (int)CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x->ptr, (const unsigned long long *)dims,
+        if (l3d_encode_tiled(&tmap, (int)CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x->ptr, (const unsigned long long *)dims,
                              (const unsigned long long *)strides, (const unsigned *)box, (const unsigned *)estr)) return 3;
     } else {
         const cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
@@ -723,15 +719,15 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
         const cuuint64_t strides[4] = {ld * es, (cuuint64_t)W * ld * es, (cuuint64_t)H * W * ld * es, (cuuint64_t)D * H * W * ld * es};
         const cuuint32_t box[5] = {CK, HX, HY, box_z, 1};
         const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-        if (l3d_encode_tiled(&tmap, (int)CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x->ptr, (const unsigned long long *)dims,
+        if (l3d_encode_tiled(&tmap, (int)CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, x->ptr, (const unsigned long long *)dims,
                              (const unsigned long long *)strides, (const unsigned *)box, (const unsigned *)estr)) return 3;
     }
     C3Args A;
     A.Cin = Cin; A.xn = norm_dev(xn);
     A.N = N; A.D = D; A.H = H; A.W = W;
     A.w = w; A.groups = w != nullptr ? groups : 1; A.dw_w = dw_w; A.pw_w = pw_w; A.sc_w = sc_w; A.Cout = Cout;
-    A.t = (bf16 *)t->ptr; A.ldt = t->ldc; A.t_stats = t_stats;
-    A.r = has_sc ? (bf16 *)r->ptr : nullptr; A.ldr = has_sc ? r->ldc : 0; A.r_stats = r_stats;
+    A.t = (h16 *)t->ptr; A.ldt = t->ldc; A.t_stats = t_stats;
+    A.r = has_sc ? (h16 *)r->ptr : nullptr; A.ldr = has_sc ? r->ldc : 0; A.r_stats = r_stats;
     A.stat_ld = stat_ld > 0 ? stat_ld : Cout;
     A.co0 = co0; A.cout_total = cout_total > 0 ? cout_total : Cout;
     A.tmem_cols = cols; A.nraw = nraw; A.nsets = nsets; A.merged_cx = merged_cx ? 1 : 0; A.dbg = env_int("L3D_C3_DEBUG_SKIP", 0);

@@ -42,41 +42,35 @@ static inline int64_t num_tiles(int N, int D, int H, int W) {
 // 16-byte channel vectors: 8 bf16 or 4 fp32
 template <typename T> struct VecW;
 template <> struct VecW<float> { static constexpr int V = 4; };
-template <> struct VecW<bf16> { static constexpr int V = 8; };
+template <> struct VecW<h16> { static constexpr int V = 8; };
 __device__ __forceinline__ void ldv(const float *p, float (&v)[4]) {
     const float4 f = *reinterpret_cast<const float4 *>(p);
     v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
 }
-__device__ __forceinline__ void ldv(const bf16 *p, float (&v)[8]) {
+__device__ __forceinline__ void ldv(const h16 *p, float (&v)[8]) {
     const uint4 r = *reinterpret_cast<const uint4 *>(p);
-    v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
-    v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
-    v[4] = __uint_as_float(r.z << 16); v[5] = __uint_as_float(r.z & 0xffff0000u);
-    v[6] = __uint_as_float(r.w << 16); v[7] = __uint_as_float(r.w & 0xffff0000u);
+    v[0] = h16_lo(r.x); v[1] = h16_hi(r.x);
+    v[2] = h16_lo(r.y); v[3] = h16_hi(r.y);
+    v[4] = h16_lo(r.z); v[5] = h16_hi(r.z);
+    v[6] = h16_lo(r.w); v[7] = h16_hi(r.w);
 }
 // raw 16-byte loads (conversion deferred, keeps the register footprint of in-flight loads small)
 __device__ __forceinline__ uint4 ldraw(const float *p) { return *reinterpret_cast<const uint4 *>(p); }
-__device__ __forceinline__ uint4 ldraw(const bf16 *p) { return *reinterpret_cast<const uint4 *>(p); }
+__device__ __forceinline__ uint4 ldraw(const h16 *p) { return *reinterpret_cast<const uint4 *>(p); }
 __device__ __forceinline__ void cvt_raw(const float *, const uint4 &r, float (&v)[4]) {
     v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
 }
-__device__ __forceinline__ void cvt_raw(const bf16 *, const uint4 &r, float (&v)[8]) {
-    v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
-    v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
-    v[4] = __uint_as_float(r.z << 16); v[5] = __uint_as_float(r.z & 0xffff0000u);
-    v[6] = __uint_as_float(r.w << 16); v[7] = __uint_as_float(r.w & 0xffff0000u);
+__device__ __forceinline__ void cvt_raw(const h16 *, const uint4 &r, float (&v)[8]) {
+    v[0] = h16_lo(r.x); v[1] = h16_hi(r.x);
+    v[2] = h16_lo(r.y); v[3] = h16_hi(r.y);
+    v[4] = h16_lo(r.z); v[5] = h16_hi(r.z);
+    v[6] = h16_lo(r.w); v[7] = h16_hi(r.w);
 }
 __device__ __forceinline__ void stv(float *p, const float (&v)[4]) {
     *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
 }
-__device__ __forceinline__ void stv(bf16 *p, const float (&v)[8]) {
-    uint4 r;
-    __nv_bfloat162 a;
-    a = __floats2bfloat162_rn(v[0], v[1]); r.x = *reinterpret_cast<uint32_t *>(&a);
-    a = __floats2bfloat162_rn(v[2], v[3]); r.y = *reinterpret_cast<uint32_t *>(&a);
-    a = __floats2bfloat162_rn(v[4], v[5]); r.z = *reinterpret_cast<uint32_t *>(&a);
-    a = __floats2bfloat162_rn(v[6], v[7]); r.w = *reinterpret_cast<uint32_t *>(&a);
-    *reinterpret_cast<uint4 *>(p) = r;
+__device__ __forceinline__ void stv(h16 *p, const float (&v)[8]) {
+    *reinterpret_cast<uint4 *>(p) = make_uint4(pack_h16x2(v[0], v[1]), pack_h16x2(v[2], v[3]), pack_h16x2(v[4], v[5]), pack_h16x2(v[6], v[7]));
 }
 
 // per-channel prologue scale/shift into shared memory
@@ -595,8 +589,8 @@ __global__ void __launch_bounds__(256) merge_head_fwd_kernel(
 // the lane pair adds its two partial head sums with one shuffle, and 40 registers keep the SM's warp slots full (the
 // voxel-per-thread kernel above: 119 registers, 24 % of the warp slots, 3.6 TB/s).  Two voxel halves per thread in flight.
 __global__ void __launch_bounds__(256, 4) merge_head16_fwd_kernel(
-    const bf16 *__restrict__ t2, int ld2, NormDev n2, const bf16 *__restrict__ r, int ldr, NormDev nr,
-    int N, size_t nvox, float slope, bf16 *__restrict__ out, int ldo,
+    const h16 *__restrict__ t2, int ld2, NormDev n2, const h16 *__restrict__ r, int ldr, NormDev nr,
+    int N, size_t nvox, float slope, h16 *__restrict__ out, int ldo,
     const float *__restrict__ head_w, const float *__restrict__ head_b, int OC,
     float *__restrict__ prob, float *__restrict__ logits) {
     constexpr int C = 16;
@@ -942,7 +936,7 @@ __global__ void __launch_bounds__(256) dw_c1_kernel(const T *__restrict__ x, int
 // bf16, W % 8 == 0, contiguous single-channel input: thread = 8 x-consecutive voxels x ZC1V planes.  One 16-byte load per
 // input row (+ the two x-halo scalars), so ~1.7 loads per voxel instead of 11; lanes run along the flattened (y, x) plane.
 constexpr int ZC1V = 4;
-__global__ void __launch_bounds__(256) dw_c1_vec_kernel(const bf16 *__restrict__ x, NormDev xn, int N, int D, int H, int W,
+__global__ void __launch_bounds__(256) dw_c1_vec_kernel(const h16 *__restrict__ x, NormDev xn, int N, int D, int H, int W,
                                                         const float *__restrict__ dw_w, const float *__restrict__ pw_w,
                                                         const float *__restrict__ sc_w, int Cout, float *__restrict__ u,
                                                         double *__restrict__ t_stats, double *__restrict__ r_stats) {
@@ -974,7 +968,7 @@ __global__ void __launch_bounds__(256) dw_c1_vec_kernel(const bf16 *__restrict__
     for (int zi = 0; zi < ZC1V + 2; ++zi) {
         const int gz = z0 + zi - 1;
         const bool okz = qvalid && gz >= 0 && gz < D;
-        const bf16 *plane = x + (((size_t)n * D + (okz ? gz : 0)) * H) * W;
+        const h16 *plane = x + (((size_t)n * D + (okz ? gz : 0)) * H) * W;
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
             const int gy = y + dy - 1;
@@ -983,14 +977,14 @@ __global__ void __launch_bounds__(256) dw_c1_vec_kernel(const bf16 *__restrict__
 #pragma unroll
             for (int i = 0; i < 10; ++i) v[i] = 0.f;
             if (ok) {
-                const bf16 *row = plane + (size_t)gy * W + x0;
+                const h16 *row = plane + (size_t)gy * W + x0;
                 const uint4 r4 = *reinterpret_cast<const uint4 *>(row);
-                v[1] = __uint_as_float(r4.x << 16); v[2] = __uint_as_float(r4.x & 0xffff0000u);
-                v[3] = __uint_as_float(r4.y << 16); v[4] = __uint_as_float(r4.y & 0xffff0000u);
-                v[5] = __uint_as_float(r4.z << 16); v[6] = __uint_as_float(r4.z & 0xffff0000u);
-                v[7] = __uint_as_float(r4.w << 16); v[8] = __uint_as_float(r4.w & 0xffff0000u);
-                if (okl) v[0] = __bfloat162float(row[-1]);
-                if (okr) v[9] = __bfloat162float(row[8]);
+                v[1] = h16_lo(r4.x); v[2] = h16_hi(r4.x);
+                v[3] = h16_lo(r4.y); v[4] = h16_hi(r4.y);
+                v[5] = h16_lo(r4.z); v[6] = h16_hi(r4.z);
+                v[7] = h16_lo(r4.w); v[8] = h16_hi(r4.w);
+                if (okl) v[0] = __half2float(row[-1]);
+                if (okr) v[9] = __half2float(row[8]);
 #pragma unroll
                 for (int i = 0; i < 10; ++i) v[i] = lrelu(fmaf(v[i], sc, sh), slope);
                 if (!okl) v[0] = 0.f;
@@ -1215,7 +1209,7 @@ extern "C" int l3d_dwpw_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, 
         const char *md = getenv("L3D_DWS_SLICE_MIN_DIM");
         const int min_dim = (md && md[0]) ? atoi(md) : 16;
         if (dw_w != nullptr && !has_u && Cin * Cout > igemm_max && Cin * 16 <= 2 * igemm_max && Cout % 16 == 0 && D >= min_dim && H >= min_dim &&
-            x->dtype == L3D_BF16) {
+            x->dtype == L3D_F16) {
             for (int Cs : {32, 16}) {
                 if (Cout % Cs != 0 || Cout <= Cs || Cin * Cs > igemm_max) continue;
                 int rc = 0;
@@ -1303,7 +1297,7 @@ extern "C" int l3d_conv3_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D,
     }
     // wide layers: the 27 weight tiles of all output channels would crowd the operand buffers out of shared memory, so
     // the layer runs as several launches over output-channel slices (each re-reads the input; still tensor-core bound)
-    if (x->dtype == L3D_BF16 && Cin % 16 == 0 && Cout % 16 == 0) {
+    if (x->dtype == L3D_F16 && Cin % 16 == 0 && Cout % 16 == 0) {
         for (int Cs : {32, 16}) {
             if (Cout % Cs != 0 || Cout <= Cs) continue;
             if (Cs > 16 && (size_t)27 * Cin * Cs * 2 > 60 * 1024) continue;     // leave room for tall operand tiles
@@ -1399,13 +1393,13 @@ extern "C" int l3d_merge_fwd(const l3d_act *t2, const l3d_norm *n2, const l3d_ac
         if (gx_ > cap_) gx_ = cap_;
         const unsigned gx = (unsigned)gx_;
         dim3 grid(gx, (unsigned)N);
-        if (C == 16 && t2->dtype == L3D_BF16) {
+        if (C == 16 && t2->dtype == L3D_F16) {
             size_t gh = (2 * nvox + 511) / 512;
             const size_t caph = (148 * 16 + (size_t)N - 1) / (size_t)N;
             if (gh > caph) gh = caph;
             dim3 gridh((unsigned)gh, (unsigned)N);
-            merge_head16_fwd_kernel<<<gridh, 256, 0, st>>>((const bf16 *)t2->ptr, t2->ldc, d2, (const bf16 *)r->ptr, r->ldc, dr, N, nvox, slope,
-                                                          has_out ? (bf16 *)out->ptr : nullptr, has_out ? out->ldc : 0, head_w, head_b, OC, prob, logits);
+            merge_head16_fwd_kernel<<<gridh, 256, 0, st>>>((const h16 *)t2->ptr, t2->ldc, d2, (const h16 *)r->ptr, r->ldc, dr, N, nvox, slope,
+                                                          has_out ? (h16 *)out->ptr : nullptr, has_out ? out->ldc : 0, head_w, head_b, OC, prob, logits);
             l3d_count_launch();
             L3D_CUDA_OK("l3d_merge_fwd (head) launch");
             return 0;
@@ -1458,10 +1452,10 @@ extern "C" int l3d_dw_c1_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D,
     L3D_REQUIRE(N > 0 && N <= 65535 && D > 0 && H > 0 && W > 0 && Cout > 0, "l3d_dw_c1_fwd: bad dims");
     L3D_REQUIRE(sc_w == nullptr || r_stats != nullptr, "l3d_dw_c1_fwd: shortcut weights without a statistics buffer");
     const NormDev nd = norm_dev(xn);
-    if (x->dtype == L3D_BF16 && W % 8 == 0 && x->ldc == 1 && reinterpret_cast<uintptr_t>(x->ptr) % 16 == 0 &&
+    if (x->dtype == L3D_F16 && W % 8 == 0 && x->ldc == 1 && reinterpret_cast<uintptr_t>(x->ptr) % 16 == 0 &&
         reinterpret_cast<uintptr_t>(u) % 16 == 0) {
         dim3 gridv((unsigned)(((size_t)H * (W / 8) + 255) / 256), (unsigned)((D + ZC1V - 1) / ZC1V), (unsigned)N);
-        dw_c1_vec_kernel<<<gridv, 256, 0, (cudaStream_t)stream>>>((const bf16 *)x->ptr, nd, N, D, H, W, dw_w, pw_w, sc_w, Cout, u, t_stats, r_stats);
+        dw_c1_vec_kernel<<<gridv, 256, 0, (cudaStream_t)stream>>>((const h16 *)x->ptr, nd, N, D, H, W, dw_w, pw_w, sc_w, Cout, u, t_stats, r_stats);
         l3d_count_launch();
         l3d_note_kernel("dw_c1_vec_kernel");
         L3D_CUDA_OK("l3d_dw_c1_fwd launch");
@@ -1482,10 +1476,10 @@ extern "C" int l3d_dwpw_fwd_rank1(const float *u, const float *r1_w, int Cin, co
                                   const float *dw_w, const float *pw_w, const l3d_act *t, double *t_stats, void *stream) {
     L3D_REQUIRE(u && r1_w && dw_w && pw_w && !act_null(t) && t_stats, "l3d_dwpw_fwd_rank1: null argument");
     L3D_REQUIRE(N > 0 && D > 0 && H > 0 && W > 0, "l3d_dwpw_fwd_rank1: bad dims");
-    L3D_REQUIRE(Cin == 16 && W % 4 == 0 && t->dtype == L3D_BF16 && t->C % 16 == 0 && t->C <= 64,
+    L3D_REQUIRE(Cin == 16 && W % 4 == 0 && t->dtype == L3D_F16 && t->C % 16 == 0 && t->C <= 64,
                 "l3d_dwpw_fwd_rank1: needs Cin = 16, W %% 4 == 0, bf16 output with 16..64 channels (got Cin=%d W=%d Cout=%d)", Cin, W, t->C);
     l3d_act xv;
-    xv.ptr = const_cast<float *>(u); xv.C = Cin; xv.ldc = Cin; xv.dtype = L3D_BF16; xv.pad_ = 0;
+    xv.ptr = const_cast<float *>(u); xv.C = Cin; xv.ldc = Cin; xv.dtype = L3D_F16; xv.pad_ = 0;
     const int rc = l3d_conv3_tc_ex(&xv, xn, N, D, H, W, nullptr, 1, dw_w, pw_w, nullptr, t, t_stats, nullptr, nullptr, t->C, 0, t->C, r1_w, stream);
     if (rc < 0) { l3d_set_error("l3d_dwpw_fwd_rank1: the implicit-GEMM kernel does not take this shape / alignment"); return 3; }
     return rc;

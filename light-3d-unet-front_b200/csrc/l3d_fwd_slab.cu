@@ -25,18 +25,14 @@ struct SlabArgs {
     int Cin; NormDev xn;
     int N, D, H, W;
     const float *dw_w, *pw_w, *sc_w; int Cout;
-    bf16 *t; int ldt; double *t_stats;
-    bf16 *r; int ldr; double *r_stats;
+    h16 *t; int ldt; double *t_stats;
+    h16 *r; int ldr; double *r_stats;
     int SZ, MT, RP, PP;      // slab height, MMA tiles per slab, padded row / plane pitch of the stencil tile (voxels, odd)
     int tmem_cols;
     uint32_t raw_bytes, raw_stride, in_bytes;
     int dbg;                 // development aid (L3D_SLAB_SKIP): 1 = no activation pass, 2 = no stencil, 4 = no epilogue, 8 = no TMA
 };
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t *>(&v);
-}
 __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
     __half2 v = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&v);
@@ -210,14 +206,14 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) dwpw_slab_kernel(const 
                         const float4 sc1 = *reinterpret_cast<const float4 *>(s_scale + c0 + q * 8 + 4);
                         const float4 sh0 = *reinterpret_cast<const float4 *>(s_shift + c0 + q * 8);
                         const float4 sh1 = *reinterpret_cast<const float4 *>(s_shift + c0 + q * 8 + 4);
-                        o0.x = lrelu(fmaf(__uint_as_float(rw.x << 16), sc0.x, sh0.x), sl);
-                        o0.y = lrelu(fmaf(__uint_as_float(rw.x & 0xffff0000u), sc0.y, sh0.y), sl);
-                        o0.z = lrelu(fmaf(__uint_as_float(rw.y << 16), sc0.z, sh0.z), sl);
-                        o0.w = lrelu(fmaf(__uint_as_float(rw.y & 0xffff0000u), sc0.w, sh0.w), sl);
-                        o1.x = lrelu(fmaf(__uint_as_float(rw.z << 16), sc1.x, sh1.x), sl);
-                        o1.y = lrelu(fmaf(__uint_as_float(rw.z & 0xffff0000u), sc1.y, sh1.y), sl);
-                        o1.z = lrelu(fmaf(__uint_as_float(rw.w << 16), sc1.z, sh1.z), sl);
-                        o1.w = lrelu(fmaf(__uint_as_float(rw.w & 0xffff0000u), sc1.w, sh1.w), sl);
+                        o0.x = lrelu(fmaf(h16_lo(rw.x), sc0.x, sh0.x), sl);
+                        o0.y = lrelu(fmaf(h16_hi(rw.x), sc0.y, sh0.y), sl);
+                        o0.z = lrelu(fmaf(h16_lo(rw.y), sc0.z, sh0.z), sl);
+                        o0.w = lrelu(fmaf(h16_hi(rw.y), sc0.w, sh0.w), sl);
+                        o1.x = lrelu(fmaf(h16_lo(rw.z), sc1.x, sh1.x), sl);
+                        o1.y = lrelu(fmaf(h16_hi(rw.z), sc1.y, sh1.y), sl);
+                        o1.z = lrelu(fmaf(h16_lo(rw.w), sc1.z, sh1.z), sl);
+                        o1.w = lrelu(fmaf(h16_hi(rw.w), sc1.w, sh1.w), sl);
                     }
                     float *dst = s_in + (as & 0xffffffu);
                     *reinterpret_cast<float4 *>(dst) = o0;
@@ -314,14 +310,14 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) dwpw_slab_kernel(const 
                 uint32_t pk[8];
 #pragma unroll
                 for (int jj = 0; jj < 8; ++jj) {
-                    pk[jj] = valid ? pack_bf16x2(v[2 * jj], v[2 * jj + 1]) : 0u;
-                    const float r0 = __uint_as_float(pk[jj] << 16);
-                    const float r1 = __uint_as_float(pk[jj] & 0xffff0000u);
+                    pk[jj] = valid ? pack_h16x2(v[2 * jj], v[2 * jj + 1]) : 0u;
+                    const float r0 = h16_lo(pk[jj]);
+                    const float r1 = h16_hi(pk[jj]);
                     sv[2 * jj] = r0; sv[2 * jj + 1] = r1;
                     sv[16 + 2 * jj] = r0 * r0; sv[16 + 2 * jj + 1] = r1 * r1;
                 }
                 if (valid) {
-                    bf16 *outp = a == 0 ? A.t + (vox0 + rr) * (size_t)A.ldt : A.r + (vox0 + rr) * (size_t)A.ldr;
+                    h16 *outp = a == 0 ? A.t + (vox0 + rr) * (size_t)A.ldt : A.r + (vox0 + rr) * (size_t)A.ldr;
                     *reinterpret_cast<uint4 *>(outp + cb) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     *reinterpret_cast<uint4 *>(outp + cb + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                 }
@@ -399,7 +395,7 @@ int l3d_dwpw_fwd_slab(const l3d_act *x, const l3d_norm *xn, int N, int D, int H,
     if (disabled) return -1;
     const int Cin = x->C, Cout = t->C;
     const bool has_sc = sc_w != nullptr;
-    if (x->dtype != L3D_BF16 || t->dtype != L3D_BF16 || dw_w == nullptr) return -1;
+    if (x->dtype != L3D_F16 || t->dtype != L3D_F16 || dw_w == nullptr) return -1;
     if (Cin % 16 != 0 || Cout % 16 != 0 || Cout > 256) return -1;
     if (H > 256 || W > 256 || H * W > 1024 || H % 2 != 0) return -1;
     const int XT = (W % 6 == 0) ? 6 : (W % 4 == 0) ? 4 : 0;
@@ -421,15 +417,15 @@ int l3d_dwpw_fwd_slab(const l3d_act *x, const l3d_norm *xn, int N, int D, int H,
         const cuuint64_t strides[4] = {ld * es, (cuuint64_t)W * ld * es, (cuuint64_t)H * W * ld * es, (cuuint64_t)D * H * W * ld * es};
         const cuuint32_t box[5] = {CK, (cuuint32_t)W, (cuuint32_t)H, (cuuint32_t)(p.SZ + 2), 1};
         const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-        if (l3d_encode_tiled(&tmap, (int)CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x->ptr, (const unsigned long long *)dims,
+        if (l3d_encode_tiled(&tmap, (int)CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, x->ptr, (const unsigned long long *)dims,
                              (const unsigned long long *)strides, (const unsigned *)box, (const unsigned *)estr)) return 3;
     }
     SlabArgs A;
     A.Cin = Cin; A.xn = norm_dev(xn);
     A.N = N; A.D = D; A.H = H; A.W = W;
     A.dw_w = dw_w; A.pw_w = pw_w; A.sc_w = sc_w; A.Cout = Cout;
-    A.t = (bf16 *)t->ptr; A.ldt = t->ldc; A.t_stats = t_stats;
-    A.r = has_sc ? (bf16 *)r->ptr : nullptr; A.ldr = has_sc ? r->ldc : 0; A.r_stats = r_stats;
+    A.t = (h16 *)t->ptr; A.ldt = t->ldc; A.t_stats = t_stats;
+    A.r = has_sc ? (h16 *)r->ptr : nullptr; A.ldr = has_sc ? r->ldc : 0; A.r_stats = r_stats;
     A.SZ = p.SZ; A.MT = p.MT; A.RP = p.RP; A.PP = p.PP; A.tmem_cols = p.cols;
     { const char *e = getenv("L3D_SLAB_SKIP"); A.dbg = (e && e[0]) ? atoi(e) : 0; }
     A.raw_bytes = p.raw_bytes; A.raw_stride = p.raw_stride; A.in_bytes = p.in_bytes;

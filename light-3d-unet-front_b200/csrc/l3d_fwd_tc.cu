@@ -31,16 +31,12 @@ struct TcArgs {
     int Cin; NormDev xn;
     int N, D, H, W;
     const float *dw_w, *pw_w, *sc_w; int Cout;
-    bf16 *t; int ldt; double *t_stats;
-    bf16 *r; int ldr; double *r_stats;
-    bf16 *u; int ldu;
+    h16 *t; int ldt; double *t_stats;
+    h16 *r; int ldr; double *r_stats;
+    h16 *u; int ldu;
     int tmem_cols;
 };
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t *>(&v);
-}
 
 __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs A) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -197,14 +193,14 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
                         const float4 sh0 = *reinterpret_cast<const float4 *>(s_shift + c0 + q * 8);
                         const float4 sh1 = *reinterpret_cast<const float4 *>(s_shift + c0 + q * 8 + 4);
                         const float sl = A.xn.slope;
-                        o0.x = lrelu(fmaf(__uint_as_float(rw.x << 16), sc0.x, sh0.x), sl);
-                        o0.y = lrelu(fmaf(__uint_as_float(rw.x & 0xffff0000u), sc0.y, sh0.y), sl);
-                        o0.z = lrelu(fmaf(__uint_as_float(rw.y << 16), sc0.z, sh0.z), sl);
-                        o0.w = lrelu(fmaf(__uint_as_float(rw.y & 0xffff0000u), sc0.w, sh0.w), sl);
-                        o1.x = lrelu(fmaf(__uint_as_float(rw.z << 16), sc1.x, sh1.x), sl);
-                        o1.y = lrelu(fmaf(__uint_as_float(rw.z & 0xffff0000u), sc1.y, sh1.y), sl);
-                        o1.z = lrelu(fmaf(__uint_as_float(rw.w << 16), sc1.z, sh1.z), sl);
-                        o1.w = lrelu(fmaf(__uint_as_float(rw.w & 0xffff0000u), sc1.w, sh1.w), sl);
+                        o0.x = lrelu(fmaf(h16_lo(rw.x), sc0.x, sh0.x), sl);
+                        o0.y = lrelu(fmaf(h16_hi(rw.x), sc0.y, sh0.y), sl);
+                        o0.z = lrelu(fmaf(h16_lo(rw.y), sc0.z, sh0.z), sl);
+                        o0.w = lrelu(fmaf(h16_hi(rw.y), sc0.w, sh0.w), sl);
+                        o1.x = lrelu(fmaf(h16_lo(rw.z), sc1.x, sh1.x), sl);
+                        o1.y = lrelu(fmaf(h16_hi(rw.z), sc1.y, sh1.y), sl);
+                        o1.z = lrelu(fmaf(h16_lo(rw.w), sc1.z, sh1.z), sl);
+                        o1.w = lrelu(fmaf(h16_hi(rw.w), sc1.w, sh1.w), sl);
                     }
                     float *dst = s_in + (it & 0xffffu);
                     *reinterpret_cast<float4 *>(dst) = o0;
@@ -311,14 +307,7 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
                 if (gz < A.D && gy < A.H && gx < A.W) {
                     const uint4 h = *reinterpret_cast<const uint4 *>(sA + (uint32_t)(v >> 7) * 128 * Cin * 2 + (uint32_t)q * 2048 +
                                                                       (uint32_t)((v & 127) >> 3) * 128 + (uint32_t)(v & 7) * 16);
-                    const __half2 *hp = reinterpret_cast<const __half2 *>(&h);
-                    uint4 o;
-                    float2 f;
-                    f = __half22float2(hp[0]); o.x = pack_bf16x2(f.x, f.y);
-                    f = __half22float2(hp[1]); o.y = pack_bf16x2(f.x, f.y);
-                    f = __half22float2(hp[2]); o.z = pack_bf16x2(f.x, f.y);
-                    f = __half22float2(hp[3]); o.w = pack_bf16x2(f.x, f.y);
-                    *reinterpret_cast<uint4 *>(A.u + ((((size_t)n * A.D + gz) * A.H + gy) * A.W + gx) * (size_t)A.ldu + q * 8) = o;
+                    *reinterpret_cast<uint4 *>(A.u + ((((size_t)n * A.D + gz) * A.H + gy) * A.W + gx) * (size_t)A.ldu + q * 8) = h;   // the fp16 operand is the stored value
                 }
             }
         }
@@ -333,7 +322,7 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
             const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
             const int nacc = has_sc ? 2 : 1;
             for (int a = 0; a < nacc; ++a) {
-                bf16 *outp = (a == 0 ? A.t + vox * (size_t)A.ldt : A.r + vox * (size_t)A.ldr);
+                h16 *outp = (a == 0 ? A.t + vox * (size_t)A.ldt : A.r + vox * (size_t)A.ldr);
                 float *stat = s_stat + a * 2 * Cout;
                 for (int cb = 0; cb < Cout; cb += 16) {
                     float v[16];
@@ -342,9 +331,9 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
                     uint32_t pk[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        pk[j] = valid ? pack_bf16x2(v[2 * j], v[2 * j + 1]) : 0u;
-                        const float r0 = __uint_as_float(pk[j] << 16);
-                        const float r1 = __uint_as_float(pk[j] & 0xffff0000u);
+                        pk[j] = valid ? pack_h16x2(v[2 * j], v[2 * j + 1]) : 0u;
+                        const float r0 = h16_lo(pk[j]);
+                        const float r1 = h16_hi(pk[j]);
                         sv[2 * j] = r0; sv[2 * j + 1] = r1;
                         sv[16 + 2 * j] = r0 * r0; sv[16 + 2 * j + 1] = r1 * r1;
                     }
@@ -383,7 +372,7 @@ int l3d_dwpw_fwd_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
     if (disabled) return -1;
     const int Cin = x->C, Cout = t->C;
     const bool has_sc = sc_w != nullptr, has_u = !act_null(u);
-    if (x->dtype != L3D_BF16 || dw_w == nullptr) return -1;
+    if (x->dtype != L3D_F16 || dw_w == nullptr) return -1;
     if (Cin % 16 != 0 || Cout % 16 != 0 || Cout > 256) return -1;
     const int cols_needed = MT * Cout * (has_sc ? 2 : 1);
     if (cols_needed > 512) return -1;
@@ -406,16 +395,16 @@ int l3d_dwpw_fwd_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
         const cuuint64_t strides[4] = {ld * es, (cuuint64_t)W * ld * es, (cuuint64_t)H * W * ld * es, (cuuint64_t)D * H * W * ld * es};
         const cuuint32_t box[5] = {CK, HX, HY, HZ, 1};
         const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-        if (l3d_encode_tiled(&tmap, (int)CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, x->ptr, (const unsigned long long *)dims,
+        if (l3d_encode_tiled(&tmap, (int)CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, x->ptr, (const unsigned long long *)dims,
                              (const unsigned long long *)strides, (const unsigned *)box, (const unsigned *)estr)) return 3;
     }
     TcArgs A;
     A.Cin = Cin; A.xn = norm_dev(xn);
     A.N = N; A.D = D; A.H = H; A.W = W;
     A.dw_w = dw_w; A.pw_w = pw_w; A.sc_w = sc_w; A.Cout = Cout;
-    A.t = (bf16 *)t->ptr; A.ldt = t->ldc; A.t_stats = t_stats;
-    A.r = has_sc ? (bf16 *)r->ptr : nullptr; A.ldr = has_sc ? r->ldc : 0; A.r_stats = r_stats;
-    A.u = has_u ? (bf16 *)u->ptr : nullptr; A.ldu = has_u ? u->ldc : 0;
+    A.t = (h16 *)t->ptr; A.ldt = t->ldc; A.t_stats = t_stats;
+    A.r = has_sc ? (h16 *)r->ptr : nullptr; A.ldr = has_sc ? r->ldc : 0; A.r_stats = r_stats;
+    A.u = has_u ? (h16 *)u->ptr : nullptr; A.ldu = has_u ? u->ldc : 0;
     A.tmem_cols = cols;
     static bool attr_set = false;
     if (!attr_set) {
@@ -447,10 +436,10 @@ int l3d_dwpw_fwd_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
 namespace {
 
 struct CtArgs {
-    const bf16 *x; int ldx; int Cin;
+    const h16 *x; int ldx; int Cin;
     int N, d, h, w;
     const float *wgt, *bias; int Cout;
-    bf16 *out; int ldo; int OD, OH, OW, oz, oy, ox;
+    h16 *out; int ldo; int OD, OH, OW, oz, oy, ox;
     int tmem_cols;
 };
 
@@ -481,15 +470,7 @@ __global__ void __launch_bounds__(NT) convt_tc_kernel(CtArgs A) {
             const int q = item % kq, v = item / kq;
             uint4 o = make_uint4(0u, 0u, 0u, 0u);
             if (v0 + v < nvox) {
-                const uint4 rw = *reinterpret_cast<const uint4 *>(A.x + (size_t)(v0 + v) * A.ldx + q * 8);
-                const uint32_t in[4] = {rw.x, rw.y, rw.z, rw.w};
-                uint32_t pk[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const __half2 hh = __floats2half2_rn(__uint_as_float(in[j] << 16), __uint_as_float(in[j] & 0xffff0000u));
-                    pk[j] = *reinterpret_cast<const uint32_t *>(&hh);
-                }
-                o = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                o = *reinterpret_cast<const uint4 *>(A.x + (size_t)(v0 + v) * A.ldx + q * 8);   // stored fp16 = MMA operand
             }
             *reinterpret_cast<uint4 *>(dst + (uint32_t)q * 2048 + (uint32_t)(v >> 3) * 128 + (uint32_t)(v & 7) * 16) = o;
         }
@@ -535,14 +516,14 @@ __global__ void __launch_bounds__(NT) convt_tc_kernel(CtArgs A) {
             for (int tp = tap0; tp < tap0 + 4; ++tp) {
                 const int Z = A.oz + 2 * iz + (tp >> 2), Y = A.oy + 2 * iy + ((tp >> 1) & 1), X = A.ox + 2 * ix + (tp & 1);
                 const bool ok = row_ok && Z >= 0 && Z < A.OD && Y >= 0 && Y < A.OH && X >= 0 && X < A.OW;
-                bf16 *op = A.out + ((((size_t)n * A.OD + Z) * A.OH + Y) * A.OW + X) * (size_t)A.ldo;
+                h16 *op = A.out + ((((size_t)n * A.OD + Z) * A.OH + Y) * A.OW + X) * (size_t)A.ldo;
                 for (int cb = 0; cb < Cout; cb += 16) {
                     float v[16];
                     tc::tmem_ld16(trow + (uint32_t)(tp * Cout + cb), v);
                     if (ok) {
                         uint32_t pk[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2(v[2 * j] + s_bias[cb + 2 * j], v[2 * j + 1] + s_bias[cb + 2 * j + 1]);
+                        for (int j = 0; j < 8; ++j) pk[j] = pack_h16x2(v[2 * j] + s_bias[cb + 2 * j], v[2 * j + 1] + s_bias[cb + 2 * j + 1]);
                         *reinterpret_cast<uint4 *>(op + cb) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                         *reinterpret_cast<uint4 *>(op + cb + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                     }
@@ -565,7 +546,7 @@ int l3d_convt_fwd_tc(const l3d_act *x, int N, int d, int h, int w_, const float 
     if (disabled < 0) { const char *e = getenv("L3D_NO_TC"); disabled = (e && e[0] == '1') ? 1 : 0; }
     if (disabled) return -1;
     const int Cin = x->C, Cout = out->C;
-    if (x->dtype != L3D_BF16 || Cin % 16 != 0 || Cout % 16 != 0 || 8 * Cout > 512) return -1;
+    if (x->dtype != L3D_F16 || Cin % 16 != 0 || Cout % 16 != 0 || 8 * Cout > 512) return -1;
     if (8 * Cout > 256 && (8 * Cout) % 256 != 0) return -1;
     auto aligned = [](const l3d_act *a, int mult) {
         return (a->ldc % mult == 0) && (reinterpret_cast<uintptr_t>(a->ptr) % (2 * mult) == 0);
@@ -576,10 +557,10 @@ int l3d_convt_fwd_tc(const l3d_act *x, int N, int d, int h, int w_, const float 
     int cols = 32;
     while (cols < 8 * Cout) cols <<= 1;
     CtArgs A;
-    A.x = (const bf16 *)x->ptr; A.ldx = x->ldc; A.Cin = Cin;
+    A.x = (const h16 *)x->ptr; A.ldx = x->ldc; A.Cin = Cin;
     A.N = N; A.d = d; A.h = h; A.w = w_;
     A.wgt = w; A.bias = b; A.Cout = Cout;
-    A.out = (bf16 *)out->ptr; A.ldo = out->ldc; A.OD = OD; A.OH = OH; A.OW = OW; A.oz = oz; A.oy = oy; A.ox = ox;
+    A.out = (h16 *)out->ptr; A.ldo = out->ldc; A.OD = OD; A.OH = OH; A.OW = OW; A.oz = oz; A.oy = oy; A.ox = ox;
     A.tmem_cols = cols;
     static bool attr_set = false;
     if (!attr_set) {

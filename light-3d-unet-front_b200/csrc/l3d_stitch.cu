@@ -10,11 +10,9 @@ __device__ __forceinline__ void stv8(float *p, const float (&v)[8]) {
     reinterpret_cast<float4 *>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
     reinterpret_cast<float4 *>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
 }
-__device__ __forceinline__ void stv8(bf16 *p, const float (&v)[8]) {
-    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
-    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]), d = __floats2bfloat162_rn(v[6], v[7]);
-    *reinterpret_cast<uint4 *>(p) = make_uint4(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b),
-                                               *reinterpret_cast<uint32_t *>(&c), *reinterpret_cast<uint32_t *>(&d));
+__device__ __forceinline__ void stv8(h16 *p, const float (&v)[8]) {
+    const uint32_t a = pack_h16x2(v[0], v[1]), b = pack_h16x2(v[2], v[3]), c = pack_h16x2(v[4], v[5]), d = pack_h16x2(v[6], v[7]);
+    *reinterpret_cast<uint4 *>(p) = make_uint4(a, b, c, d);
 }
 
 // grid.y = window; one thread = 8 x-consecutive voxels of one window row (32-bit index arithmetic only)

@@ -14,8 +14,8 @@ import torch
 _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.environ.get("L3D_LIB", os.path.join(_PKG_DIR, "libl3d.so"))
 
-L3D_F32, L3D_BF16 = 0, 1
-ABI_VERSION = 3
+L3D_F32, L3D_F16 = 0, 1
+ABI_VERSION = 4
 
 
 class Act(Structure):
@@ -178,9 +178,9 @@ def require_cuda(t: torch.Tensor, what: str):
 def dtype_code(dt: torch.dtype) -> int:
     if dt == torch.float32:
         return L3D_F32
-    if dt == torch.bfloat16:
-        return L3D_BF16
-    raise NativeError(f"unsupported activation dtype {dt}")
+    if dt == torch.float16:
+        return L3D_F16
+    raise NativeError(f"unsupported activation dtype {dt}: the 16-bit storage format of libl3d is IEEE fp16 (torch.float16)")
 
 
 def ptr(t) -> c_void_p:

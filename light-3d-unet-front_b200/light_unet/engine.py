@@ -5,7 +5,7 @@ Host-side only: shape bookkeeping, workspace (HBM) layout and kernel ordering.
 All arithmetic happens in libl3d.so; there is no PyTorch fallback.
 
 HBM layout (per workspace, i.e. per (N, D, H, W, dtype, training) key):
-  * activations are channels-last NDHWC, bf16 by default (fp32 optional);
+  * activations are channels-last NDHWC, fp16 by default (fp32 optional);
   * the output of the three encoder blocks that feed a skip connection is
     written straight into the upper channel half of the decoder's concat buffer
     (`cat`), the transposed conv writes the lower half -> torch.cat / F.pad of
@@ -113,7 +113,7 @@ class Workspace:
             cmax = [2 * e[0], 2 * e[1], 2 * e[2], e[3]]
             # gradient tensors are fp32 whatever the activation storage type: the InstanceNorm backward subtracts
             # the per-(n,c) mean of the incoming gradient, and the Focal Tversky gradient is almost constant over
-            # the voxels, so bf16 rounding of the gradient (relative to its magnitude) swamps the centred signal
+            # the voxels, so 16-bit rounding of the gradient (relative to its magnitude) swamps the centred signal
             emp = (lambda *s: torch.full(s, float("nan"), dtype=torch.float32, device=device)) if poison else (lambda *s: torch.empty(*s, dtype=torch.float32, device=device))
             self.g_cat = {k: emp(N, *lv[k], 2 * e[k]) for k in range(3)}      # grad of [up | skip]
             self.g_pooled = {k: emp(N, *lv[k + 1], e[k]) for k in range(3)}   # grad of the pooled block inputs
@@ -164,7 +164,7 @@ class UNetPlan:
         return (not training) and b.name == "init_conv" and b.cin == 1 and b.cin != b.cout and b.kind1 == "dws" and b.cout in (16, 32)
 
     def rank1_first(self, b: BlockSpec, dtype, dims, training: bool) -> bool:
-        return (self.rank1_shortcut(b, training) and b.kind2 == "dws" and b.cout == 16 and dtype == torch.bfloat16
+        return (self.rank1_shortcut(b, training) and b.kind2 == "dws" and b.cout == 16 and dtype == torch.float16
                 and dims[2] % 4 == 0 and os.environ.get("L3D_NO_RANK1_FIRST", "0") != "1")
 
     # ------------------------------------------------------------------ workspace

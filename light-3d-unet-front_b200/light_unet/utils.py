@@ -21,9 +21,9 @@ import torch
 
 from . import _native as nv
 
-WINDOW_BATCH = 325         # windows per forward launch sequence: the whole 128x128x320 volume (325 windows, ~20 GB of bf16
+WINDOW_BATCH = 325         # windows per forward launch sequence: the whole 128x128x320 volume (325 windows, ~20 GB of fp16
                            # workspace out of 180 GB) in one batch -- measured 14.1 ms vs 15.7 ms at 65 per batch
-_BYTES_PER_WINDOW = 70e6   # workspace estimate per 48^3 window (bf16), used to cap the batch by the free HBM
+_BYTES_PER_WINDOW = 70e6   # workspace estimate per 48^3 window (fp16), used to cap the batch by the free HBM
 _GAUSS_CACHE = {}
 _BATCH_CAP = {}
 _POS_CACHE = {}
@@ -100,7 +100,7 @@ def sliding_window_device(volume: torch.Tensor, model, patch_size=(48, 48, 48), 
     preds = torch.empty(nwin, 1, pd, ph, pw, dtype=torch.float32, device=dev)
     wb = int(window_batch or WINDOW_BATCH)
     if window_batch is None:
-        f32 = getattr(model, "compute_dtype", torch.bfloat16) == torch.float32
+        f32 = getattr(model, "compute_dtype", torch.float16) == torch.float32
         key = (str(dev), pd, ph, pw, f32, wb)
         cap = _BATCH_CAP.get(key)
         if cap is None:         # cudaMemGetInfo is a slow call: decided once per configuration (the workspace is cached after that)

@@ -134,11 +134,11 @@ def _inorm(sd, prefix, x):
                            use_input_stats=True, eps=IN_EPS)
 
 
-def bf16_storage(x: torch.Tensor) -> torch.Tensor:
-    """Round to bf16 with a straight-through gradient: models a tensor that the CUDA path *stores* in bf16
+def f16_storage(x: torch.Tensor) -> torch.Tensor:
+    """Round to fp16 with a straight-through gradient: models a tensor that the CUDA path *stores* in fp16
     between kernels (all arithmetic stays fp32).  Used only to separate "kernel bug" from "precision policy"
-    when checking the bf16 storage mode: the CUDA backward is the exact gradient of this rounded forward."""
-    return x + (x.detach().to(torch.bfloat16).to(torch.float32) - x.detach())
+    when checking the 16-bit storage mode: the CUDA backward is the exact gradient of this rounded forward."""
+    return x + (x.detach().to(torch.float16).to(torch.float32) - x.detach())
 
 
 def residual_block(sd, cfg, prefix, x, cin, cout, allow_grouped, mask, taps=None, quant=None):

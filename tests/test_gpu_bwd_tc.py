@@ -1,6 +1,6 @@
 """Layer-level GPU parity of the tensor-core pointwise backward (csrc/l3d_bwd_tc.cu) through the C-ABI entry point
 l3d_pw_bwd: against a float64 torch restatement of the same math (InstanceNorm backward on load, dgrad, wgrad) and
-against the CUDA-core kernel it replaces (L3D_NO_TC_BWD=1) on identical bf16-stored inputs."""
+against the CUDA-core kernel it replaces (L3D_NO_TC_BWD=1) on identical f16-stored inputs."""
 import os
 
 import numpy as np
@@ -18,8 +18,8 @@ def _case(N, dims, Cg, Cu, has_nt, u_norm, seed):
     D, H, W = dims
     vox = D * H * W
     gz = (torch.randn(N, D, H, W, Cg, generator=g) * 1e-3 + 2e-3).float()          # gradient with a common offset
-    t = torch.randn(N, D, H, W, Cg, generator=g).to(torch.bfloat16)
-    u = torch.randn(N, D, H, W, Cu, generator=g).to(torch.bfloat16)
+    t = torch.randn(N, D, H, W, Cg, generator=g).to(torch.float16)
+    u = torch.randn(N, D, H, W, Cu, generator=g).to(torch.float16)
     w = (torch.randn(Cg, Cu, generator=g) / np.sqrt(Cu)).float()
     gam_t, bet_t = torch.rand(Cg, generator=g) + 0.5, torch.randn(Cg, generator=g) * 0.2
     gam_u, bet_u = torch.rand(Cu, generator=g) + 0.5, torch.randn(Cu, generator=g) * 0.2
@@ -95,7 +95,7 @@ def test_pw_bwd_tensor_core(Cg, Cu, has_nt, u_norm, accumulate):
     gu_cc, gw_cc = _run(c, N, dims, has_nt, u_norm, accumulate, {"L3D_NO_TC_BWD": "1"})
     e = dict(gu_tc=_rel(gu_tc, c["ref_gu"]), gw_tc=_rel(gw_tc, c["ref_gw"]), gu_cc=_rel(gu_cc, c["ref_gu"]), gw_cc=_rel(gw_cc, c["ref_gw"]))
     print(Cg, Cu, has_nt, u_norm, accumulate, {k: f"{v:.2e}" for k, v in e.items()})
-    # hi/lo bf16 operand pairs: ~2^-16 per product; the fp32 CUDA-core kernel is the yardstick
+    # hi/lo f16 operand pairs: ~2^-16 per product; the fp32 CUDA-core kernel is the yardstick
     assert e["gu_tc"] < 2e-4 and e["gw_tc"] < 2e-4, e
     assert e["gu_cc"] < 2e-4 and e["gw_cc"] < 2e-4, e
 
@@ -109,7 +109,7 @@ def test_convt_bwd_tensor_core(Cin, Cout, lo, out_dims, accumulate):
     from light_unet import _native as nv
     N = 2
     g = torch.Generator().manual_seed(Cin * 7 + Cout + lo[0])
-    x = torch.randn(N, *lo, Cin, generator=g).to(torch.bfloat16)
+    x = torch.randn(N, *lo, Cin, generator=g).to(torch.float16)
     w = (torch.randn(Cin, Cout, 2, 2, 2, generator=g) / np.sqrt(Cin)).float()
     gcat = (torch.randn(N, *out_dims, 2 * Cout, generator=g) * 1e-3).float()
     off = [(out_dims[k] - 2 * lo[k]) // 2 for k in range(3)]
@@ -160,7 +160,7 @@ def test_dw_bwd_layer(C, dims, has_norm, accumulate):
     vox = D * H * W
     g = torch.Generator().manual_seed(C + D)
     gu = (torch.randn(N, D, H, W, C, generator=g) * 1e-3).float()
-    x = torch.randn(N, D, H, W, C, generator=g).to(torch.bfloat16)
+    x = torch.randn(N, D, H, W, C, generator=g).to(torch.float16)
     dw = (torch.randn(C, 27, generator=g) / 5).float()
     gam, bet = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.2
     drop = (torch.rand(N, C, generator=g) > 0.2).float() / 0.8

@@ -1,0 +1,140 @@
+"""GPU parity on the configurations the benchmark numbers are quoted on (BASELINE.json configs[1], [2], [4]), at full
+size, against the oracle run on the box's CPU in the same test:
+
+  * configs[2]: the 128x128x320 volume, 48^3 windows, 50 % overlap, 325 windows -> stitched probability map, mask, boxes
+    (utils.py:11-139, inferencer.py:62-111), in both storage modes;
+  * configs[4] patch sizes 64^3 / 96^3 (+ the odd sizes 50^3 / 40^3 that go through the centre-pad path, unet3d.py:130-138);
+  * configs[1]: the batch-8 48^3 training step -- loss and EVERY parameter gradient, in the storage mode the training
+    throughput is quoted in.
+
+Tolerances (north_star): 1e-2 relative (16-bit storage) / 1e-4 (fp32 storage) on probabilities and pre-sigmoid logits,
+1e-4 on the loss, masks and boxes bit-exact given identical probabilities.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bbox_ref, loss_ref, stitch_ref, synth, unet_ref
+from test_gpu_parity import DEV, build_model, logit, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(dtype, wseed=3, dropout_p=0.0):
+    cfg = unet_ref.UNetCfg(dropout_p=dropout_p)
+    sd_np = synth.synth_state_dict(unet_ref.param_shapes(cfg), wseed)
+    return cfg, sd_np, build_model(cfg, sd_np, dtype)
+
+
+@pytest.mark.parametrize("dtype,tol_rel,tol_abs", [("f32", 1e-4, 1e-4), ("f16", 1e-2, 1e-2)])
+def test_c3_full_volume_against_oracle(dtype, tol_rel, tol_abs):
+    """BASELINE configs[2] end to end through Inferencer.infer_volume against the oracle's sliding window
+    (stitch_ref.sliding_window over unet_ref.forward, all 325 windows on the host cores)."""
+    from light_unet.core.inferencer import Inferencer
+    cfg, sd_np, model = _model(dtype)
+    inf = Inferencer.__new__(Inferencer)
+    inf.config = {"data": {"bbox_expansion_voxels": 3, "patch_size": [48, 48, 48], "volume_threshold": {"inference_cc": 0.5}},
+                  "validation": {"default_threshold": 0.3}}
+    inf.device = torch.device(DEV)
+    inf.model = model.eval()
+    vol = synth.synth_volume((128, 128, 320), seed=42, n_blobs=6)
+    prob, boxes = inf.infer_volume(vol, threshold=0.3, spacing=(4.0, 4.0, 4.0))
+    sd = unet_ref.to_torch(sd_np)
+
+    def predict(chunk):
+        with torch.no_grad():
+            return unet_ref.forward(sd, torch.from_numpy(chunk), cfg).numpy()
+    want = stitch_ref.sliding_window(vol, predict, (48, 48, 48), 0.5, True)
+    e_rel, e_abs, e_logit = rel_l2(prob, want), float(np.abs(prob - want).max()), rel_l2(logit(prob), logit(want))
+    flips = int(((prob >= np.float32(0.3)) != (want >= np.float32(0.3))).sum())
+    print(f"C3 128x128x320/{dtype}: prob rel-L2 {e_rel:.3e} max-abs {e_abs:.3e} logit rel-L2 {e_logit:.3e}; "
+          f"{flips} of {prob.size} mask voxels differ from the oracle's mask; {len(boxes)} boxes")
+    assert prob.shape == want.shape and prob.dtype == np.float32
+    assert e_rel < tol_rel and e_logit < tol_rel and e_abs < tol_abs
+    # masks / boxes are bit-exact given identical probabilities: the reference algorithm on OUR map
+    assert boxes == bbox_ref.extract_bboxes(prob, 0.3, 0.5, (4.0, 4.0, 4.0), 3)
+    if dtype == "f32":
+        # ... and in fp32 storage the map is close enough to the oracle's that the box lists agree as well, up to voxels
+        # whose probability sits within 1e-4 of the threshold
+        want_boxes = bbox_ref.extract_bboxes(want, 0.3, 0.5, (4.0, 4.0, 4.0), 3)
+        near = int((np.abs(want - np.float32(0.3)) < 1e-4).sum())
+        if near == 0:
+            assert [b["bbox_voxel"] for b in boxes] == [b["bbox_voxel"] for b in want_boxes]
+
+
+@pytest.mark.parametrize("dtype,tol", [("f32", 1e-4), ("f16", 1e-2)])
+@pytest.mark.parametrize("size,batch", [(64, 2), (96, 1), (50, 2), (40, 3), (48, 8)])
+def test_patch_sizes_against_oracle(size, batch, dtype, tol):
+    """configs[4] patch sizes (and configs[1]'s batch of 8) through the nn.Module forward against the oracle."""
+    cfg, sd_np, model = _model(dtype)
+    x, _ = synth.synth_patches(batch, (size, size, size), 7)
+    with torch.no_grad():
+        y = model.eval()(torch.from_numpy(x).to(DEV)).cpu().numpy()
+        ref_logit = unet_ref.forward(unet_ref.to_torch(sd_np), torch.from_numpy(x), cfg, return_logits=True).numpy()
+    ref = 1.0 / (1.0 + np.exp(-ref_logit.astype(np.float64)))
+    e_p, e_l = rel_l2(y, ref), rel_l2(logit(y), ref_logit)
+    print(f"{size}^3 x{batch}/{dtype}: prob rel-L2 {e_p:.3e}, logit rel-L2 {e_l:.3e}")
+    assert e_p < tol and e_l < tol
+
+
+def _train_step(dtype, batch, size, wseed=1, xseed=42):
+    from light_unet.models import FocalTverskyLoss
+    cfg, sd_np, model = _model(dtype, wseed=wseed, dropout_p=0.1)
+    model.train()
+    x, t = synth.synth_patches(batch, (size, size, size), xseed)
+    torch.manual_seed(1234)
+    masks = unet_ref.draw_dropout_masks(cfg, batch)
+    prob = model(torch.from_numpy(x).to(DEV), dropout_masks=[None if m is None else m.to(DEV) for m in masks])
+    loss = FocalTverskyLoss()(prob, torch.from_numpy(t).to(DEV))
+    loss.backward()
+    grads = {k: p.grad.detach().cpu().numpy().astype(np.float64) for k, p in model.named_parameters()}
+    return cfg, sd_np, x, t, masks, prob.detach().cpu().numpy(), float(loss.item()), grads
+
+
+def _oracle_step(cfg, sd_np, x, t, masks, quant=None):
+    sd = {k: v.requires_grad_(True) for k, v in unet_ref.to_torch(sd_np).items()}
+    ref = unet_ref.forward(sd, torch.from_numpy(x), cfg, masks, quant=quant)
+    l = loss_ref.focal_tversky(ref, torch.from_numpy(t))
+    l.backward()
+    return ref.detach().numpy(), float(l.item()), {k: v.grad.numpy().astype(np.float64) for k, v in sd.items()}
+
+
+def _per_tensor_errors(grads, rgrads):
+    """rel-L2 per gradient tensor, measured against ||ref|| + floor with floor = 1e-3 x the largest gradient norm of the
+    model: a conv that feeds an InstanceNorm has analytically zero gradient along its own weight direction (for a
+    1-input-channel conv that is the whole gradient), so such tensors hold only round-off."""
+    gmax = max(np.linalg.norm(v) for v in rgrads.values())
+    floor = 1e-3 * gmax
+    return {k: float(np.linalg.norm(grads[k] - rgrads[k]) / (np.linalg.norm(rgrads[k]) + floor)) for k in grads}
+
+
+@pytest.mark.parametrize("dtype,tol_p,tol_g", [("f32", 1e-4, 2e-3), ("f16", 1e-2, 5e-2)])
+def test_c2_train_step_batch8_48(dtype, tol_p, tol_g):
+    """BASELINE configs[1]: batch 8 of 48^3 patches, dropout 0.1, Focal Tversky .7/.3/.75 -- training-mode
+    probabilities, loss and every one of the 93 parameter gradients against the oracle's autograd (fp32, CPU)."""
+    cfg, sd_np, x, t, masks, prob, loss, grads = _train_step(dtype, 8, 48)
+    rprob, rloss, rgrads = _oracle_step(cfg, sd_np, x, t, masks)
+    errs = _per_tensor_errors(grads, rgrads)
+    worst = max(errs, key=errs.get)
+    g = np.concatenate([grads[k].ravel() for k in grads]); rg = np.concatenate([rgrads[k].ravel() for k in grads])
+    cos = float((g * rg).sum() / (np.linalg.norm(g) * np.linalg.norm(rg)))
+    print(f"C2 8x48^3/{dtype}: prob rel-L2 {rel_l2(prob, rprob):.3e}, |loss - oracle| {abs(loss - rloss):.2e}, whole-gradient cosine {cos:.6f}, "
+          f"worst per-tensor rel-L2 {errs[worst]:.3e} ({worst}), median {np.median(list(errs.values())):.3e}")
+    assert rel_l2(prob, rprob) < tol_p and abs(loss - rloss) < 1e-4
+    assert errs[worst] < tol_g, (worst, errs[worst])
+
+
+@pytest.mark.parametrize("size,batch", [(16, 2), (24, 2), (20, 2)])
+def test_train_step_f16_small_patches(size, batch):
+    """16-bit storage on the small fixtures' shapes (the deepest InstanceNorm sees 8 ... 27 voxels per channel, the worst
+    case for storage rounding).  Reported against two oracles: plain fp32 (the bound) and fp32 with the stored tensors
+    rounded to fp16 at the same points (straight-through gradient), which separates the kernels from the storage policy."""
+    cfg, sd_np, x, t, masks, prob, loss, grads = _train_step("f16", batch, size, wseed=1, xseed=11)
+    rprob, rloss, rgrads = _oracle_step(cfg, sd_np, x, t, masks)
+    _, _, qgrads = _oracle_step(cfg, sd_np, x, t, masks, quant=unet_ref.f16_storage)
+    errs, qerrs = _per_tensor_errors(grads, rgrads), _per_tensor_errors(grads, qgrads)
+    worst, qworst = max(errs, key=errs.get), max(qerrs, key=qerrs.get)
+    print(f"{size}^3 x{batch}/f16: worst per-tensor rel-L2 vs fp32 oracle {errs[worst]:.3e} ({worst}); vs the oracle with fp16-rounded "
+          f"stored tensors {qerrs[qworst]:.3e} ({qworst})")
+    assert abs(loss - rloss) < 1e-4 and rel_l2(prob, rprob) < 1e-2
+    assert errs[worst] < 1e-1, (worst, errs[worst])

@@ -1,6 +1,6 @@
 """Layer-level GPU parity of the tcgen05 implicit-GEMM 3x3x3 conv (csrc/l3d_conv3_tc.cu) through the C-ABI:
 every tile height / accumulator-set / TMA-buffer configuration, ragged volumes, dense, grouped and composed
-depthwise-separable (+ shortcut) weights, against torch conv3d in fp32 on the same bf16-stored inputs."""
+depthwise-separable (+ shortcut) weights, against torch conv3d in fp32 on the same f16-stored inputs."""
 import os
 
 import numpy as np
@@ -21,7 +21,7 @@ def _rel(a, b):
 def _inputs(N, dims, Cin, seed):
     g = torch.Generator().manual_seed(seed)
     D, H, W = dims
-    x = torch.randn(N, D, H, W, Cin, generator=g).to(torch.bfloat16)
+    x = torch.randn(N, D, H, W, Cin, generator=g).to(torch.float16)
     vox = D * H * W
     xf = x.float()
     # statistics of the stored tensor, as the producer's epilogue would have accumulated them: {sum, sumsq}[N][C]
@@ -66,7 +66,7 @@ def _run(case, env, launches=None):
         sd, gd, bd = stats.to(DEV).contiguous(), gamma.to(DEV), beta.to(DEV)
         keep += [sd, gd, bd]
         xn = nv.norm(sd, gd, bd, None, EPS, SLOPE, vox)
-    t = torch.zeros(N, D, H, W, Cout, dtype=torch.bfloat16, device=DEV)
+    t = torch.zeros(N, D, H, W, Cout, dtype=torch.float16, device=DEV)
     t_stats = torch.zeros(2 * N * Cout, dtype=torch.float64, device=DEV)
     a_ncdhw = a.permute(0, 4, 1, 2, 3).contiguous()
     old = {k: os.environ.get(k) for k in env}
@@ -84,7 +84,7 @@ def _run(case, env, launches=None):
             pw = torch.randn(Cout, Cin, 1, 1, 1, generator=g) / np.sqrt(Cin)
             sc = torch.randn(Cout, Cin, 1, 1, 1, generator=g) / np.sqrt(Cin)
             dwd, pwd, scd = dw.to(DEV), pw.to(DEV), sc.to(DEV)
-            r = torch.zeros(N, D, H, W, Cout, dtype=torch.bfloat16, device=DEV)
+            r = torch.zeros(N, D, H, W, Cout, dtype=torch.float16, device=DEV)
             r_stats = torch.zeros(2 * N * Cout, dtype=torch.float64, device=DEV)
             nv.call("l3d_dwpw_fwd", nv.act(xd), xn, N, D, H, W, nv.ptr(dwd), nv.ptr(pwd), nv.ptr(scd), nv.act(t),
                     nv.ptr(t_stats), nv.act(r), nv.ptr(r_stats), nv.act(None), st)
@@ -103,7 +103,7 @@ def _run(case, env, launches=None):
         got_f = got.float().cpu()
         e = _rel(got_f.permute(0, 4, 1, 2, 3), ref)
         assert e < 4e-3, (case, env, e)
-        # the statistics are sums over exactly the stored (bf16-rounded) values
+        # the statistics are sums over exactly the stored (f16-rounded) values
         want = torch.stack([got_f.double().sum(dim=(1, 2, 3)), (got_f.double() ** 2).sum(dim=(1, 2, 3))]).reshape(-1)
         gs = gstats.cpu()
         assert float((gs - want).abs().max() / (want.abs().max() + 1e-30)) < 2e-4, (case, env)
@@ -171,7 +171,7 @@ def test_rank1_first_block_layers(dims, tz):
     D, H, W = dims
     vox = D * H * W
     g = torch.Generator().manual_seed(3)
-    x = torch.rand(N, D, H, W, 1, generator=g).to(torch.bfloat16)
+    x = torch.rand(N, D, H, W, 1, generator=g).to(torch.float16)
     dw1 = torch.randn(1, 1, 3, 3, 3, generator=g) / np.sqrt(27.0)
     pw1 = torch.randn(C, 1, 1, 1, 1, generator=g)
     sc = torch.randn(C, 1, 1, 1, 1, generator=g)
@@ -195,7 +195,7 @@ def test_rank1_first_block_layers(dims, tz):
         assert float((got.cpu() - want).abs().max() / want.abs().max()) < 1e-5
     a1 = F.leaky_relu(F.instance_norm(t1_ref.float(), weight=gamma, bias=beta, eps=EPS), SLOPE)
     t2_ref = F.conv3d(F.conv3d(a1, dw2, padding=1, groups=C), pw2)
-    t2 = torch.zeros(N, D, H, W, C, dtype=torch.bfloat16, device=DEV)
+    t2 = torch.zeros(N, D, H, W, C, dtype=torch.float16, device=DEV)
     s2 = torch.zeros(2 * N * C, dtype=torch.float64, device=DEV)
     n1 = nv.norm(s1, gd, bd, None, EPS, SLOPE, vox)
     old = os.environ.get("L3D_C3_TZ")
@@ -227,7 +227,7 @@ SLAB_CASES = [  # N, dims, Cin, Cout, shortcut, normed input
 @pytest.mark.parametrize("case", SLAB_CASES, ids=lambda c: f"{c[2]}to{c[3]}{'+sc' if c[4] else ''}-{'x'.join(map(str, c[1]))}")
 def test_dwpw_slab_kernel(case):
     """Small-volume depthwise-separable conv (csrc/l3d_fwd_slab.cu: whole-plane slabs, the 12^3 / 6^3 levels of a 48^3
-    window) through l3d_dwpw_fwd against torch in fp32 on the same bf16-stored inputs."""
+    window) through l3d_dwpw_fwd against torch in fp32 on the same f16-stored inputs."""
     from light_unet import _native as nv
     N, dims, Cin, Cout, has_sc, use_norm = case
     D, H, W = dims
@@ -246,9 +246,9 @@ def test_dwpw_slab_kernel(case):
     sc = torch.randn(Cout, Cin, 1, 1, 1, generator=g) / np.sqrt(Cin)
     dwd, pwd, scd = dw.to(DEV), pw.to(DEV), sc.to(DEV)
     # outputs are views into wider buffers (ldc > C), as the engine's concat buffers are
-    tb = torch.zeros(N, D, H, W, 2 * Cout, dtype=torch.bfloat16, device=DEV)
+    tb = torch.zeros(N, D, H, W, 2 * Cout, dtype=torch.float16, device=DEV)
     t = tb[..., Cout:]
-    r = torch.zeros(N, D, H, W, Cout, dtype=torch.bfloat16, device=DEV)
+    r = torch.zeros(N, D, H, W, Cout, dtype=torch.float16, device=DEV)
     t_stats = torch.zeros(2 * N * Cout, dtype=torch.float64, device=DEV)
     r_stats = torch.zeros(2 * N * Cout, dtype=torch.float64, device=DEV)
     nv.call("l3d_dwpw_fwd", nv.act(xd), xn, N, D, H, W, nv.ptr(dwd), nv.ptr(pwd), nv.ptr(scd) if has_sc else None, nv.act(tb, Cout, Cout),

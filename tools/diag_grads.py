@@ -17,7 +17,7 @@ for name in sys.argv[2:] or ["dws_16"]:
     masks = unet_ref.draw_dropout_masks(cfg, meta["batch"])
     prob, loss, grads, _ = run_ours(cfg, sd_np, x, t, masks, dtype)
     sd = {k: v.requires_grad_(True) for k, v in unet_ref.to_torch(sd_np).items()}
-    ref = unet_ref.forward(sd, torch.from_numpy(x), cfg, masks, quant=unet_ref.bf16_storage if os.environ.get('Q') else None)
+    ref = unet_ref.forward(sd, torch.from_numpy(x), cfg, masks, quant=unet_ref.f16_storage if os.environ.get('Q') else None)
     loss_ref.focal_tversky(ref, torch.from_numpy(t)).backward()
     print(f"== {name}/{dtype}: prob rel-L2 {rel_l2(prob, ref.detach().numpy()):.3e} loss {loss:.6f} ref {float(z['loss_train']):.6f}")
     allg, allr = [], []
