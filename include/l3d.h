@@ -213,6 +213,19 @@ int l3d_stitch(const float *preds, const int32_t *zpos, int nz, const int32_t *y
                int D, int H, int W, const uint8_t *body_mask, float *prob,
                float threshold, int32_t *mask_out, void *stream);
 
+/* Slab form of l3d_stitch for window-level sharding of ONE volume over several GPUs (the loop of
+ * utils.py:86-134 split along the longest axis): stitches the voxels x in [x0, x1) only.  Window (a, b, c) of the
+ * (z, y, x) grid lives at preds[(a*wstride_z + b*wstride_y + c*wstride_x) * pd*ph*pw] -- a rank keeps [x-position][z][y]
+ * blocks, the seam positions received from its neighbours first -- and voxel (z, y, x) is written to
+ * prob[(z*H + y) * out_pitch + out_xoff + (x - x0)] (same for mask_out).  xpos holds the nx x-positions present in
+ * `preds`.  Candidate windows are added in the same z -> y -> x order, so the slab is bit-identical to the same voxels of
+ * the single-GPU map given identical predictions.  body_mask is indexed in the full volume. */
+int l3d_stitch_slab(const float *preds, const int32_t *zpos, int nz, const int32_t *ypos, int ny,
+                    const int32_t *xpos, int nx, int64_t wstride_z, int64_t wstride_y, int64_t wstride_x,
+                    int pd, int ph, int pw, const float *importance,
+                    int D, int H, int W, int x0, int x1, int out_pitch, int out_xoff,
+                    const uint8_t *body_mask, float *prob, float threshold, int32_t *mask_out, void *stream);
+
 /* mask[i] = prob[i] >= threshold (inferencer.py:64). */
 int l3d_threshold(const float *prob, int64_t n, float threshold, int32_t *mask, void *stream);
 

@@ -3,7 +3,9 @@
 //
 //   stage   g_t[v][c] = a_c*gz[v][c] + b_c*t[v][c] + d_c   (InstanceNorm backward on load, fp32) and the activated
 //           u[v][k], for 128 voxels, as bf16 in the voxel-planar layout [channel/8][128 voxels][8 channels];
-//           g_t is split into hi + lo bf16 parts (the weights too), so the products carry ~16 mantissa bits
+//           g_t is split into hi + lo bf16 parts (the weights too), so the products carry ~16 mantissa bits; the stored
+//           fp16 activation u (11-bit significand) is split EXACTLY into bf16 hi + lo (a tcgen05.mma.kind::f16 whose A and
+//           B formats differ -- bf16 gradient x fp16 activation -- raises "illegal instruction" on sm_100a, measured)
 //   dgrad   D1[v][k] = sum_c g_t[v][c] * W[c][k]      A = G tile read K-major  (rows = voxels, K = channels)
 //   wgrad   D2[c][k] += sum_v g_t[v][c] * u[v][k]     A = G tile read MN-major (M = channels, K = voxels),
 //                                                     B = U tile read MN-major (N = channels, K = voxels)
@@ -42,6 +44,17 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t &hi, uint32_t 
     hi = pack2_bf16(a, b);
     lo = pack2_bf16(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
 }
+// eight stored fp16 values -> bf16 hi / lo vectors (exact: 11 significand bits fit 8 + 8)
+__device__ __forceinline__ void split_h16x8(const uint4 &r, uint4 &hi, uint4 &lo) {
+    split2(h16_lo(r.x), h16_hi(r.x), hi.x, lo.x); split2(h16_lo(r.y), h16_hi(r.y), hi.y, lo.y);
+    split2(h16_lo(r.z), h16_hi(r.z), hi.z, lo.z); split2(h16_lo(r.w), h16_hi(r.w), hi.w, lo.w);
+}
+__device__ __forceinline__ void store_u_split(unsigned char *sUh, unsigned char *sUl, size_t off, const uint4 &r, bool ok) {
+    uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+    if (ok) split_h16x8(r, hi, lo);
+    *reinterpret_cast<uint4 *>(sUh + off) = hi;
+    *reinterpret_cast<uint4 *>(sUl + off) = lo;
+}
 
 // GI / UI: G / U staging items (one 8-channel group of one voxel) per thread, held in registers one tile ahead so the
 // global loads of tile T+1 are in flight during the MMAs and the epilogue of tile T.  GI == 0: no prefetch (wide layers).
@@ -53,8 +66,9 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
     const int Cg = A.Cg, Cu = A.Cu, gq = Cg >> 3, uq = Cu >> 3;
     unsigned char *sGh = smem;                              // gq planes
     unsigned char *sGl = sGh + (size_t)gq * PLANE;
-    unsigned char *sU = sGl + (size_t)gq * PLANE;           // uq planes
-    unsigned char *sWh = sU + (size_t)uq * PLANE;           // dgrad B operand: [N = Cu][K = Cg] K-major
+    unsigned char *sUh = sGl + (size_t)gq * PLANE;          // uq planes (hi), uq planes (lo)
+    unsigned char *sUl = sUh + (size_t)uq * PLANE;
+    unsigned char *sWh = sUl + (size_t)uq * PLANE;          // dgrad B operand: [N = Cu][K = Cg] K-major
     unsigned char *sWl = sWh + (size_t)Cg * Cu * 2;
     float *s_ca = reinterpret_cast<float *>(sWl + (size_t)Cg * Cu * 2);
     float *s_cb = s_ca + Cg, *s_cd = s_cb + Cg, *s_us = s_cd + Cg, *s_uh = s_us + Cu;
@@ -76,8 +90,8 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
     tc::fence_after_sync();
     const uint32_t tmem = s_tmem;
     const uint32_t d1 = tmem, d2 = tmem + (uint32_t)Cu;
-    const uint32_t id_k = tc::idesc_16b_m128(Cu, 1, 1, false, false), id_mn = tc::idesc_16b_m128(Cu, 1, 0, true, true);   // A: bf16 gradient hi / lo, B: stored fp16 activation
-    const uint32_t sGh_u = tc::smem_u32(sGh), sGl_u = tc::smem_u32(sGl), sU_u = tc::smem_u32(sU), sWh_u = tc::smem_u32(sWh), sWl_u = tc::smem_u32(sWl);
+    const uint32_t id_k = tc::idesc_16b_m128(Cu, 1, 1, false, false), id_mn = tc::idesc_16b_m128(Cu, 1, 1, true, true);
+    const uint32_t sGh_u = tc::smem_u32(sGh), sGl_u = tc::smem_u32(sGl), sUh_u = tc::smem_u32(sUh), sUl_u = tc::smem_u32(sUl), sWh_u = tc::smem_u32(sWh), sWl_u = tc::smem_u32(sWl);
 
     const long long tiles_per_sample = (A.vox + TV - 1) / TV;
     const long long total_tiles = tiles_per_sample * A.N;
@@ -153,7 +167,7 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
 #pragma unroll
                 for (int i = 0; i < UI; ++i) {
                     const int item = tid + i * NT, v = item & (TV - 1), q = item >> 7;
-                    *reinterpret_cast<uint4 *>(sU + (size_t)q * PLANE + (size_t)v * 16) = (v0 + v < A.vox) ? pu[i] : make_uint4(0u, 0u, 0u, 0u);
+                    store_u_split(sUh, sUl, (size_t)q * PLANE + (size_t)v * 16, pu[i], v0 + v < A.vox);
                 }
             }
             // ---- issue the loads of this CTA's next tile
@@ -184,7 +198,7 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
                 *reinterpret_cast<uint4 *>(sGh + (size_t)q * PLANE + (size_t)v * 16) = hi;
                 *reinterpret_cast<uint4 *>(sGl + (size_t)q * PLANE + (size_t)v * 16) = lo;
             }
-            // ---- stage U (activated, bf16)
+            // ---- stage U (activated; bf16 hi / lo of the fp16 value)
             if (has_gw) {
                 for (int item = tid; item < uq * TV; item += NT) {
                     const int v = item & (TV - 1), q = item >> 7;
@@ -204,7 +218,7 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
                             o = make_uint4(w4[0], w4[1], w4[2], w4[3]);
                         }
                     }
-                    *reinterpret_cast<uint4 *>(sU + (size_t)q * PLANE + (size_t)v * 16) = o;
+                    store_u_split(sUh, sUl, (size_t)q * PLANE + (size_t)v * 16, o, true);
                 }
             }
         }
@@ -223,11 +237,13 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
                 }
             }
             if (has_gw) {
-                // D2 += (Gh + Gl)^T . U        (K = 128 voxels in steps of 16 = two 8-voxel groups)
+                // D2 += Gh^T.Uh + Gl^T.Uh + Gh^T.Ul   (K = 128 voxels in steps of 16 = two 8-voxel groups)
                 for (int j = 0; j < TV / 16; ++j) {
-                    const uint64_t bu = tc::smem_desc(sU_u + j * 256, 128, PLANE);
-                    tc::mma_f16(d2, tc::smem_desc(sGh_u + j * 256, 128, PLANE), bu, id_mn, (first && j == 0) ? 0u : 1u);
-                    tc::mma_f16(d2, tc::smem_desc(sGl_u + j * 256, 128, PLANE), bu, id_mn, 1u);
+                    const uint64_t buh = tc::smem_desc(sUh_u + j * 256, 128, PLANE), bul = tc::smem_desc(sUl_u + j * 256, 128, PLANE);
+                    const uint64_t agh = tc::smem_desc(sGh_u + j * 256, 128, PLANE);
+                    tc::mma_f16(d2, agh, buh, id_mn, (first && j == 0) ? 0u : 1u);
+                    tc::mma_f16(d2, tc::smem_desc(sGl_u + j * 256, 128, PLANE), buh, id_mn, 1u);
+                    tc::mma_f16(d2, agh, bul, id_mn, 1u);
                 }
             }
             tc::mma_commit(&s_bar);
@@ -289,7 +305,7 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_tmem;
     const int Cg = A.Cg, Cu = A.Cu, gq = Cg >> 3, uq = Cu >> 3;
-    const uint32_t tile_bytes = (uint32_t)(2 * gq + uq) * PLANE;   // [Gh | Gl | U]
+    const uint32_t tile_bytes = (uint32_t)(2 * gq + 2 * uq) * PLANE;   // [Gh | Gl | Uh | Ul]
     unsigned char *sWh = smem + 2 * tile_bytes;
     unsigned char *sWl = sWh + (size_t)Cg * Cu * 2;
     float *s_ca = reinterpret_cast<float *>(sWl + (size_t)Cg * Cu * 2);
@@ -312,7 +328,7 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
     tc::fence_after_sync();
     const uint32_t tmem = s_tmem;
     const uint32_t d1 = tmem, d2 = tmem + (uint32_t)Cu;
-    const uint32_t id_k = tc::idesc_16b_m128(Cu, 1, 1, false, false), id_mn = tc::idesc_16b_m128(Cu, 1, 0, true, true);   // A: bf16 gradient hi / lo, B: stored fp16 activation
+    const uint32_t id_k = tc::idesc_16b_m128(Cu, 1, 1, false, false), id_mn = tc::idesc_16b_m128(Cu, 1, 1, true, true);
     const uint32_t smem_u = tc::smem_u32(smem), sWh_u = tc::smem_u32(sWh), sWl_u = tc::smem_u32(sWl);
     const long long tiles_per_sample = (A.vox + TV - 1) / TV;
     const long long total_tiles = tiles_per_sample * A.N;
@@ -354,7 +370,7 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
             }
             __syncthreads();
         }
-        unsigned char *sGh = smem + (size_t)b * tile_bytes, *sGl = sGh + (size_t)gq * PLANE, *sU = sGl + (size_t)gq * PLANE;
+        unsigned char *sGh = smem + (size_t)b * tile_bytes, *sGl = sGh + (size_t)gq * PLANE, *sUh = sGl + (size_t)gq * PLANE, *sUl = sUh + (size_t)uq * PLANE;
 #pragma unroll
         for (int i = 0; i < GI; ++i) {
             const int item = tid + i * NT, q = item % gq, v = item / gq;
@@ -380,14 +396,14 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
 #pragma unroll
             for (int i = 0; i < UI; ++i) {
                 const int item = tid + i * NT, q = item % uq, v = item / uq;
-                *reinterpret_cast<uint4 *>(sU + (size_t)q * PLANE + (size_t)v * 16) = (v0 + v < A.vox) ? pu[i] : make_uint4(0u, 0u, 0u, 0u);
+                store_u_split(sUh, sUl, (size_t)q * PLANE + (size_t)v * 16, pu[i], v0 + v < A.vox);
             }
         }
     };
     bool first = true;
     auto issue = [&](int b) {                          // one thread, after a CTA barrier that followed fence_async_smem
         tc::fence_after_sync();
-        const uint32_t sGh_u = smem_u + (uint32_t)b * tile_bytes, sGl_u = sGh_u + (uint32_t)gq * PLANE, sU_u = sGl_u + (uint32_t)gq * PLANE;
+        const uint32_t sGh_u = smem_u + (uint32_t)b * tile_bytes, sGl_u = sGh_u + (uint32_t)gq * PLANE, sUh_u = sGl_u + (uint32_t)gq * PLANE, sUl_u = sUh_u + (uint32_t)uq * PLANE;
         if (has_gu) {
             for (int j = 0; j < Cg / 16; ++j) {
                 const uint64_t agh = tc::smem_desc(sGh_u + 2 * j * PLANE, PLANE, 128), agl = tc::smem_desc(sGl_u + 2 * j * PLANE, PLANE, 128);
@@ -399,9 +415,11 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
         }
         if (has_gw) {
             for (int j = 0; j < TV / 16; ++j) {
-                const uint64_t bu = tc::smem_desc(sU_u + j * 256, 128, PLANE);
-                tc::mma_f16(d2, tc::smem_desc(sGh_u + j * 256, 128, PLANE), bu, id_mn, (first && j == 0) ? 0u : 1u);
-                tc::mma_f16(d2, tc::smem_desc(sGl_u + j * 256, 128, PLANE), bu, id_mn, 1u);
+                const uint64_t buh = tc::smem_desc(sUh_u + j * 256, 128, PLANE), bul = tc::smem_desc(sUl_u + j * 256, 128, PLANE);
+                const uint64_t agh = tc::smem_desc(sGh_u + j * 256, 128, PLANE);
+                tc::mma_f16(d2, agh, buh, id_mn, (first && j == 0) ? 0u : 1u);
+                tc::mma_f16(d2, tc::smem_desc(sGl_u + j * 256, 128, PLANE), buh, id_mn, 1u);
+                tc::mma_f16(d2, agh, bul, id_mn, 1u);
             }
         }
         tc::mma_commit(&s_bar);
@@ -487,7 +505,7 @@ int l3d_pw_bwd_tc(const l3d_act *gz, const l3d_act *t, const l3d_norm *nt, const
     // an activated u is not exactly representable in bf16 (it would need a hi/lo pair like g_t); every caller on the
     // U-Net path passes a stored bf16 tensor with the identity norm, so the general case stays on the CUDA-core kernel
     if (un != nullptr && un->stats != nullptr && g_w != nullptr) return -1;
-    size_t smem = (size_t)(2 * (Cg / 8) + Cu / 8) * PLANE + 2 * (size_t)Cg * Cu * 2 + sizeof(float) * (3 * (size_t)Cg + 2 * (size_t)Cu);
+    size_t smem = (size_t)(2 * (Cg / 8) + 2 * (Cu / 8)) * PLANE + 2 * (size_t)Cg * Cu * 2 + sizeof(float) * (3 * (size_t)Cg + 2 * (size_t)Cu);
     // the MN-major A operand always spans 128 rows (16 channel groups): keep its over-read inside the allocation
     const size_t span = (size_t)(Cg / 8) * PLANE + 16 * (size_t)PLANE + 256;
     if (smem < span) smem = span;
@@ -511,9 +529,9 @@ int l3d_pw_bwd_tc(const l3d_act *gz, const l3d_act *t, const l3d_norm *nt, const
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = ((vox + TV - 1) / TV) * N;
     // pipelined variant: two tile buffers + weights + tables, and the MN-major over-read of the second buffer's G planes
-    size_t smem_p = 2 * (size_t)(2 * (Cg / 8) + Cu / 8) * PLANE + 2 * (size_t)Cg * Cu * 2 + sizeof(float) * 3 * (size_t)Cg;
+    size_t smem_p = 2 * (size_t)(2 * (Cg / 8) + 2 * (Cu / 8)) * PLANE + 2 * (size_t)Cg * Cu * 2 + sizeof(float) * 3 * (size_t)Cg;
     {
-        const size_t span_p = (size_t)(2 * (Cg / 8) + Cu / 8) * PLANE + (size_t)(Cg / 8) * PLANE + 16 * (size_t)PLANE + 256;
+        const size_t span_p = (size_t)(2 * (Cg / 8) + 2 * (Cu / 8)) * PLANE + (size_t)(Cg / 8) * PLANE + 16 * (size_t)PLANE + 256;
         if (smem_p < span_p) smem_p = span_p;
     }
     const bool use_pipe = env_flag_off("L3D_NO_PWB_PIPE");
@@ -595,8 +613,9 @@ __global__ void __launch_bounds__(NT) convt_bwd_tc_kernel(CtTcArgs A) {
     const int Cin = A.Cin, Cout = A.Cout, gq = Cout >> 3, xq = (Cin >> 3) + 2, NX = Cin + 16;
     unsigned char *sGh = smem;                                   // gq planes
     unsigned char *sGl = sGh + (size_t)gq * PLANE;
-    unsigned char *sX = sGl + (size_t)gq * PLANE;                // xq planes: Cin channels + [1, 0 x 15]
-    unsigned char *sWh = sX + (size_t)xq * PLANE;                // dgrad B operand per tap: [N = Cin][K = Cout] K-major
+    unsigned char *sXh = sGl + (size_t)gq * PLANE;               // xq planes: Cin channels + [1, 0 x 15]; bf16 hi, then lo
+    unsigned char *sXl = sXh + (size_t)xq * PLANE;
+    unsigned char *sWh = sXl + (size_t)xq * PLANE;               // dgrad B operand per tap: [N = Cin][K = Cout] K-major
     const size_t wtap_bytes = (size_t)Cin * Cout * 2;
     unsigned char *sWl = sWh + (A.w_resident ? 8 : 1) * wtap_bytes;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -620,7 +639,8 @@ __global__ void __launch_bounds__(NT) convt_bwd_tc_kernel(CtTcArgs A) {
     // constant part of the X tile: channel Cin = 1, channels Cin+1 .. Cin+15 = 0
     for (int i = tid; i < 2 * TV; i += NT) {
         const int v = i & (TV - 1), q = (Cin >> 3) + (i >> 7);
-        *reinterpret_cast<uint4 *>(sX + (size_t)q * PLANE + (size_t)v * 16) = make_uint4(i < TV ? 0x00003c00u : 0u, 0u, 0u, 0u)   /* fp16 1.0 */;
+        *reinterpret_cast<uint4 *>(sXh + (size_t)q * PLANE + (size_t)v * 16) = make_uint4(i < TV ? 0x00003f80u : 0u, 0u, 0u, 0u);   // bf16 1.0
+        *reinterpret_cast<uint4 *>(sXl + (size_t)q * PLANE + (size_t)v * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
     tc::fence_async_smem();
     tc::fence_before_sync();
@@ -629,20 +649,20 @@ __global__ void __launch_bounds__(NT) convt_bwd_tc_kernel(CtTcArgs A) {
     const uint32_t tmem = s_tmem;
     const uint32_t d1 = tmem;                                     // Cin columns
     const uint32_t d2 = tmem + (uint32_t)Cin;                     // TP accumulators of NX columns
-    const uint32_t id_k = tc::idesc_16b_m128(Cin, 1, 1, false, false), id_mn = tc::idesc_16b_m128(NX, 1, 0, true, true);   // A: bf16 gradient hi / lo, B: stored fp16 input
-    const uint32_t sGh_u = tc::smem_u32(sGh), sGl_u = tc::smem_u32(sGl), sX_u = tc::smem_u32(sX), sWh_u = tc::smem_u32(sWh), sWl_u = tc::smem_u32(sWl);
+    const uint32_t id_k = tc::idesc_16b_m128(Cin, 1, 1, false, false), id_mn = tc::idesc_16b_m128(NX, 1, 1, true, true);
+    const uint32_t sGh_u = tc::smem_u32(sGh), sGl_u = tc::smem_u32(sGl), sXh_u = tc::smem_u32(sXh), sXl_u = tc::smem_u32(sXl), sWh_u = tc::smem_u32(sWh), sWl_u = tc::smem_u32(sWl);
     const long long nvox = (long long)A.N * A.d * A.h * A.w;
     const long long ntiles = (nvox + TV - 1) / TV;
     uint32_t phase = 0;
     bool first = true;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long v0 = tile * TV;
-        // ---- X tile (stored bf16, identity norm): one copy per tile
+        // ---- X tile (stored fp16, identity norm -> exact bf16 hi / lo): one copy per tile
         for (int item = tid; item < (Cin >> 3) * TV; item += NT) {
             const int v = item & (TV - 1), q = item >> 7;
             uint4 o = make_uint4(0u, 0u, 0u, 0u);
             if (v0 + v < nvox) o = *reinterpret_cast<const uint4 *>(A.x + (size_t)(v0 + v) * A.ldx + q * 8);
-            *reinterpret_cast<uint4 *>(sX + (size_t)q * PLANE + (size_t)v * 16) = o;
+            store_u_split(sXh, sXl, (size_t)q * PLANE + (size_t)v * 16, o, v0 + v < nvox);
         }
         for (int tap = tap_begin; tap < tap_end; ++tap) {
             // ---- G_tap tile: gather from the up-sampled grid
@@ -685,9 +705,11 @@ __global__ void __launch_bounds__(NT) convt_bwd_tc_kernel(CtTcArgs A) {
                 if (tap >= tap_lo && tap < tap_hi) {
                     const uint32_t dacc = d2 + (uint32_t)((tap - tap_lo) * NX);
                     for (int j = 0; j < TV / 16; ++j) {
-                        const uint64_t bx = tc::smem_desc(sX_u + j * 256, 128, PLANE);
-                        tc::mma_f16(dacc, tc::smem_desc(sGh_u + j * 256, 128, PLANE), bx, id_mn, (first && j == 0) ? 0u : 1u);
-                        tc::mma_f16(dacc, tc::smem_desc(sGl_u + j * 256, 128, PLANE), bx, id_mn, 1u);
+                        const uint64_t bxh = tc::smem_desc(sXh_u + j * 256, 128, PLANE), bxl = tc::smem_desc(sXl_u + j * 256, 128, PLANE);
+                        const uint64_t agh = tc::smem_desc(sGh_u + j * 256, 128, PLANE);
+                        tc::mma_f16(dacc, agh, bxh, id_mn, (first && j == 0) ? 0u : 1u);
+                        tc::mma_f16(dacc, tc::smem_desc(sGl_u + j * 256, 128, PLANE), bxh, id_mn, 1u);
+                        tc::mma_f16(dacc, agh, bxl, id_mn, 1u);
                     }
                 }
                 tc::mma_commit(&s_bar);
@@ -764,7 +786,7 @@ int l3d_convt_bwd_tc(const l3d_act *g_out, int OD, int OH, int OW, int oz, int o
     while (TP > 1 && TP * NX + Cin > 512) TP >>= 1;
     if (TP * NX + Cin > 512) return -1;
     const size_t wtap = (size_t)Cin * Cout * 2;
-    const size_t base = (size_t)(2 * (Cout / 8) + Cin / 8 + 2) * PLANE;
+    const size_t base = (size_t)(2 * (Cout / 8) + 2 * (Cin / 8 + 2)) * PLANE;
     int w_resident = base + 16 * wtap <= 160 * 1024 ? 1 : 0;
     size_t smem = base + (w_resident ? 16 : 2) * wtap;
     const size_t span = (size_t)(Cout / 8) * PLANE + 16 * (size_t)PLANE + 256;     // MN-major A over-read (128 rows)

@@ -51,17 +51,25 @@ __global__ void __launch_bounds__(256) gather_windows_kernel(const float *__rest
 // Per-axis coverage tables (first covering window + count per coordinate; window starts ascend, utils.py:63-81) are
 // built once per CTA in shared memory; a voxel's (<= STITCH_MAXC) candidates are all loaded before the ordered
 // accumulation.  Axes with more than 3 covering windows per coordinate (overlap > 2/3) take the scanning path.
+// Slab form (window-level sharding of one volume over several GPUs): the launch covers the voxels
+// x in [g.x0, g.x1) only, the window (a, b, c) lives at preds[(a * g.wsz + b * g.wsy + c * g.wsx) * per] (so a rank can
+// keep [x-position][z][y] blocks: received seam positions first, then its own), and voxel (z, y, x) is written to
+// prob[(z * H + y) * g.pitch + g.xoff + (x - g.x0)] (rank 0 writes into the full map, the other ranks a packed slab).
+// The candidate order per voxel stays z -> y -> x, so the result is bit-identical to the single-launch form.
 constexpr int STITCH_MAXC = 27;
+struct StitchGeo { long long wsz, wsy, wsx; int x0, x1, pitch, xoff; };
 __global__ void __launch_bounds__(256) stitch_kernel(const float *__restrict__ preds,
                                                      const int32_t *__restrict__ zpos, int nz,
                                                      const int32_t *__restrict__ ypos, int ny,
                                                      const int32_t *__restrict__ xpos, int nx,
                                                      int pd, int ph, int pw, const float *__restrict__ imp,
                                                      int D, int H, int W, const uint8_t *__restrict__ body,
-                                                     float *__restrict__ prob, float thr, int32_t *__restrict__ mask, int use_tables) {
+                                                     float *__restrict__ prob, float thr, int32_t *__restrict__ mask, int use_tables,
+                                                     StitchGeo g) {
     extern __shared__ int32_t s_tab[];                  // [D + H + W] : first << 8 | count
     __shared__ int s_over;
-    const size_t total = (size_t)D * H * W;
+    const int Wl = g.x1 - g.x0;
+    const size_t total = (size_t)D * H * Wl;
     const size_t per = (size_t)pd * ph * pw;
     if (threadIdx.x == 0) s_over = 0;
     __syncthreads();
@@ -83,9 +91,10 @@ __global__ void __launch_bounds__(256) stitch_kernel(const float *__restrict__ p
         if (s_over) use_tables = 0;
     }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int x = (int)(i % (size_t)W);
-        const int rem = (int)(i / (size_t)W);
+        const int x = g.x0 + (int)(i % (size_t)Wl);
+        const int rem = (int)(i / (size_t)Wl);
         const int y = rem % H, z = rem / H;
+        const size_t oi = (size_t)rem * g.pitch + g.xoff + (x - g.x0);     // output element; body mask is indexed in the full volume
         float acc = 0.f, cnt = 0.f;
         if (use_tables) {
             const int tz = s_tab[z], ty = s_tab[D + y], tx = s_tab[D + H + x];
@@ -99,7 +108,7 @@ __global__ void __launch_bounds__(256) stitch_kernel(const float *__restrict__ p
                     const int a = a0 + ia, b = b0 + ib, c = c0 + ic;
                     const size_t li = ((size_t)(z - zpos[a]) * ph + (y - ypos[b])) * pw + (x - xpos[c]);
                     wv[k] = imp[li];
-                    pv[k] = preds[(((size_t)a * ny + b) * nx + c) * per + li];
+                    pv[k] = preds[(size_t)(a * g.wsz + b * g.wsy + c * g.wsx) * per + li];
                 }
             }
 #pragma unroll
@@ -120,7 +129,7 @@ __global__ void __launch_bounds__(256) stitch_kernel(const float *__restrict__ p
                     for (int c = 0; c < nx; ++c) {
                         const int lx = x - xpos[c];
                         if (lx < 0 || lx >= pw) continue;
-                        const size_t wi = ((size_t)a * ny + b) * nx + c;
+                        const size_t wi = (size_t)(a * g.wsz + b * g.wsy + c * g.wsx);
                         const size_t li = ((size_t)lz * ph + ly) * pw + lx;
                         const float wgt = imp[li];
                         acc = __fadd_rn(acc, __fmul_rn(preds[wi * per + li], wgt));
@@ -130,9 +139,9 @@ __global__ void __launch_bounds__(256) stitch_kernel(const float *__restrict__ p
             }
         }
         float pr = cnt > 0.f ? __fdiv_rn(acc, cnt) : acc;   // np.divide(..., where=cnt>0) (utils.py:137)
-        if (body != nullptr) pr = __fmul_rn(pr, body[i] ? 1.f : 0.f);  // inferencer.py:161-162
-        prob[i] = pr;
-        if (mask != nullptr) mask[i] = pr >= thr ? 1 : 0;
+        if (body != nullptr) pr = __fmul_rn(pr, body[(size_t)rem * W + x] ? 1.f : 0.f);  // inferencer.py:161-162
+        prob[oi] = pr;
+        if (mask != nullptr) mask[oi] = pr >= thr ? 1 : 0;
     }
 }
 
@@ -450,16 +459,28 @@ extern "C" int l3d_stitch(const float *preds, const int32_t *zpos, int nz, const
                           const int32_t *xpos, int nx, int pd, int ph, int pw, const float *importance,
                           int D, int H, int W, const uint8_t *body_mask, float *prob,
                           float threshold, int32_t *mask_out, void *stream) {
+    return l3d_stitch_slab(preds, zpos, nz, ypos, ny, xpos, nx, (int64_t)ny * nx, nx, 1, pd, ph, pw, importance, D, H, W, 0, W, W, 0,
+                           body_mask, prob, threshold, mask_out, stream);
+}
+
+extern "C" int l3d_stitch_slab(const float *preds, const int32_t *zpos, int nz, const int32_t *ypos, int ny,
+                               const int32_t *xpos, int nx, int64_t wstride_z, int64_t wstride_y, int64_t wstride_x,
+                               int pd, int ph, int pw, const float *importance,
+                               int D, int H, int W, int x0, int x1, int out_pitch, int out_xoff,
+                               const uint8_t *body_mask, float *prob, float threshold, int32_t *mask_out, void *stream) {
     L3D_REQUIRE(preds && zpos && ypos && xpos && importance && prob, "l3d_stitch: null argument");
     L3D_REQUIRE(nz > 0 && ny > 0 && nx > 0 && D > 0 && H > 0 && W > 0, "l3d_stitch: bad dims");
+    L3D_REQUIRE(0 <= x0 && x0 < x1 && x1 <= W && out_xoff >= 0 && out_pitch >= out_xoff + (x1 - x0), "l3d_stitch: bad slab [%d, %d) of W = %d (pitch %d, offset %d)", x0, x1, W, out_pitch, out_xoff);
     L3D_REQUIRE((int64_t)D * H < (1ll << 31), "l3d_stitch: volume too large");
-    const unsigned blocks = grid_for((int64_t)D * H * W, 256, 148 * 8);
+    StitchGeo g;
+    g.wsz = wstride_z; g.wsy = wstride_y; g.wsx = wstride_x; g.x0 = x0; g.x1 = x1; g.pitch = out_pitch; g.xoff = out_xoff;
+    const unsigned blocks = grid_for((int64_t)D * H * (x1 - x0), 256, 148 * 8);
     // per-axis coverage tables in shared memory when they fit (the kernel itself falls back to scanning the window lists
     // when some coordinate is covered by more than 3 windows of an axis, i.e. overlap > 2/3)
     const size_t tab_bytes = sizeof(int32_t) * ((size_t)D + H + W);
     const int use_tables = (nz < (1 << 23) && ny < (1 << 23) && nx < (1 << 23) && tab_bytes <= 40 * 1024) ? 1 : 0;
     stitch_kernel<<<blocks, 256, use_tables ? tab_bytes : 0, (cudaStream_t)stream>>>(preds, zpos, nz, ypos, ny, xpos, nx, pd, ph, pw, importance,
-                                                                                   D, H, W, body_mask, prob, threshold, mask_out, use_tables);
+                                                                                   D, H, W, body_mask, prob, threshold, mask_out, use_tables, g);
     l3d_count_launch();
     L3D_CUDA_OK("l3d_stitch launch");
     return 0;

@@ -66,6 +66,8 @@ _SIGS = {
     "l3d_gather_windows": [_P, c_int, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, _P],
     "l3d_stitch": [_P, _P, c_int, _P, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P, _P,
                    c_float, _P, _P],
+    "l3d_stitch_slab": [_P, _P, c_int, _P, c_int, _P, c_int, c_int64, c_int64, c_int64, c_int, c_int, c_int, _P,
+                        c_int, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P, c_float, _P, _P],
     "l3d_threshold": [_P, c_int64, c_float, _P, _P],
     "l3d_ccl_label": [_P, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
     "l3d_bbox_init": [_P, c_int, _P],

@@ -112,11 +112,15 @@ class Inferencer:
         return self._bboxes_from_device(prob_d, mask_d, min_volume_cc, spacing)
 
     # ----------------------------------------------------------------- volume
-    def infer_volume(self, image, threshold=0.3, spacing=(4.0, 4.0, 4.0), body_mask=None, return_device=False, prob_out=None):
+    def infer_volume(self, image, threshold=0.3, spacing=(4.0, 4.0, 4.0), body_mask=None, return_device=False, prob_out=None,
+                     shard=None):
         """Device-resident case pipeline: sliding window -> (body mask) -> threshold -> CC -> boxes.
         `image` is a host ndarray or CUDA tensor [D,H,W].  Returns (prob_map, bboxes).  `prob_out`: optional pinned host
         fp32 tensor [D,H,W]; the probability map is then copied into it on a side stream while the connected-component /
-        bounding-box kernels run, and returned instead of a fresh array."""
+        bounding-box kernels run, and returned instead of a fresh array.
+        `shard = (rank, world_size, group)`: the windows of THIS volume are split over the ranks of a torch.distributed
+        group (every rank calls with the same volume; parallel/window_shard.py); rank 0 returns the result, the other
+        ranks (None, [])."""
         if isinstance(image, torch.Tensor):
             vol = image.to(self.device, dtype=torch.float32, non_blocking=True)
         else:
@@ -125,7 +129,9 @@ class Inferencer:
         if body_mask is not None:
             bm = body_mask if isinstance(body_mask, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(body_mask).astype(np.uint8))
         prob_d, mask_d = sliding_window_device(vol, self.model, tuple(self.config["data"]["patch_size"]), 0.5, True,
-                                               body_mask=bm, threshold=threshold)
+                                               body_mask=bm, threshold=threshold, shard=shard)
+        if prob_d is None:                                        # window-sharded call on a rank other than 0
+            return None, []
         copy_done = None
         if prob_out is not None:
             if not (isinstance(prob_out, torch.Tensor) and prob_out.device.type == "cpu" and prob_out.dtype == torch.float32
@@ -187,12 +193,26 @@ class Inferencer:
         """All cases of a split file (inferencer.py:185-201)."""
         with open(split_file, "r") as f:
             case_ids = [line.strip() for line in f if line.strip()]
-        print(f"Performing inference on {len(case_ids)} cases...")
+        # one process per GPU (torch.distributed initialised): cases are independent, so case i goes to rank i mod N and no
+        # data-path collective is needed (SURVEY.md 8(e) partition (1)); only the summary counts are reduced
+        import torch.distributed as dist
+        from ..parallel import shard_cases
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank() if world > 1 else 0
+        mine = shard_cases(case_ids, rank, world)
+        print(f"Performing inference on {len(case_ids)} cases..." + (f" (rank {rank}/{world}: {len(mine)})" if world > 1 else ""))
         successful, failed = 0, []
         threshold = self.config["validation"]["default_threshold"]
-        for case_id in case_ids:
+        for case_id in mine:
             if self.infer_case(case_id, data_dir, threshold=threshold):
                 successful += 1
             else:
                 failed.append(case_id)
+        if world > 1:
+            t = torch.tensor([successful], dtype=torch.int64, device=self.device if dist.get_backend() == "nccl" else "cpu")
+            dist.all_reduce(t)
+            successful = int(t.item())
+            gathered = [None] * world
+            dist.all_gather_object(gathered, failed)
+            failed = [c for part in gathered for c in part]
         print(f"\nInference complete: Successful: {successful}/{len(case_ids)}")

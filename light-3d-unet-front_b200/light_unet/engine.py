@@ -71,6 +71,7 @@ class Workspace:
     def __init__(self, plan: "UNetPlan", N: int, dims: Tuple[int, int, int], dtype: torch.dtype, device,
                  training: bool):
         self.N, self.dims, self.dtype, self.device, self.training = N, dims, dtype, device, training
+        self.cap = N           # samples the buffers were allocated for; an inference workspace is reused for any N <= cap
         e = plan.enc
         lv = [tuple(dims)]
         for _ in range(3):
@@ -126,6 +127,18 @@ class Workspace:
         self.generation = 0
         self.prob_out = None
         self.logits = None
+        self.nbytes = sum(t.numel() * t.element_size() for t in self._tensors())
+
+    def _tensors(self):
+        for v in vars(self).values():
+            if isinstance(v, torch.Tensor):
+                yield v
+            elif isinstance(v, dict):
+                for w in v.values():
+                    if isinstance(w, torch.Tensor):
+                        yield w
+                    elif isinstance(w, dict):
+                        yield from (x for x in w.values() if isinstance(x, torch.Tensor))
 
     def stats_of(self, name: str, which: int, cout: int) -> torch.Tensor:
         off = self.blocks[name]["stats_off"] + which * 2 * self.N * cout
@@ -168,14 +181,43 @@ class UNetPlan:
                 and dims[2] % 4 == 0 and os.environ.get("L3D_NO_RANK1_FIRST", "0") != "1")
 
     # ------------------------------------------------------------------ workspace
+    # Cache policy: ONE inference workspace per (dims, dtype, device), allocated for the largest batch seen and reused for
+    # every smaller one (a sliding-window tail batch, a volume with fewer windows); training workspaces are exact-N (the
+    # backward pass reads them) and at most MAX_TRAIN_WS are kept.  A new allocation first drops whatever would push the
+    # cached total past WS_BUDGET_FRAC of the device memory (a 325-window fp16 workspace is ~20 GB).
+    MAX_TRAIN_WS = 2
+    MAX_INFER_WS = 2
+    WS_BUDGET_FRAC = 0.3
+
+    def inference_capacity(self, dims, dtype, device) -> int:
+        ws = self._ws.get((tuple(dims), dtype, str(device), False))
+        return ws.cap if ws is not None else 0
+
+    def cached_bytes(self) -> int:
+        return sum(w.nbytes for w in self._ws.values())
+
+    def drop_workspaces(self, training=None):
+        for k in [k for k in self._ws if training is None or k[-1] == training]:
+            del self._ws[k]
+
     def workspace(self, N, dims, dtype, device, training) -> Workspace:
-        key = (N, tuple(dims), dtype, str(device), training)
-        ws = self._ws.get(key)
+        dims = tuple(dims)
+        key = (N, dims, dtype, str(device), True) if training else (dims, dtype, str(device), False)
+        ws = self._ws.pop(key, None)
+        if ws is not None and ws.cap < N:
+            ws = None                               # grow: the old buffers are released before the new ones are allocated
         if ws is None:
-            if len(self._ws) > 8:
-                self._ws.clear()
-            ws = Workspace(self, N, tuple(dims), dtype, device, training)
-            self._ws[key] = ws
+            same = [k for k in self._ws if k[-1] == training]
+            limit = (self.MAX_TRAIN_WS if training else self.MAX_INFER_WS) - 1
+            for k in same[:max(0, len(same) - limit)]:         # dicts keep insertion order: oldest first
+                del self._ws[k]
+            if self._ws and torch.device(device).type == "cuda":
+                total = torch.cuda.get_device_properties(device).total_memory
+                if self.cached_bytes() > self.WS_BUDGET_FRAC * total:
+                    self._ws.clear()
+            ws = Workspace(self, N, dims, dtype, device, training)
+        ws.N = N
+        self._ws[key] = ws                          # most recently used last
         return ws
 
     # -------------------------------------------------------------------- forward
@@ -205,6 +247,13 @@ class UNetPlan:
         """x_cl: [N, D, H, W, Cin] channels-last activation-dtype tensor.  Returns the workspace holding
         `prob` ([N, OC, D, H, W] fp32) and, in training mode, everything the backward pass needs."""
         nv.require_cuda(x_cl, "UNetPlan.forward")
+        e = self.enc
+        for k in range(3):
+            # UpBlock: cat([ConvTranspose3d(C, C/2)(x), skip]) feeds ResidualBlock(C, ...) (unet3d.py:119-141): the reference
+            # fails inside that conv when the widths do not add up; say so up front
+            if e[k + 1] // 2 + e[k] != e[k + 1]:
+                raise RuntimeError(f"encoder_channels {e}: up-block {3 - k} concatenates {e[k + 1] // 2} + {e[k]} channels "
+                                   f"but its residual block expects {e[k + 1]} (each width must be twice the previous one)")
         N, D, H, W, _ = x_cl.shape
         ws = self.workspace(N, (D, H, W), x_cl.dtype, x_cl.device, training)
         ws.x = x_cl
@@ -351,13 +400,14 @@ class UNetPlan:
             n2 = nv.norm(s2, P[f"{b.prefix}.norm2.weight"], P[f"{b.prefix}.norm2.bias"], None, IN_EPS, 1.0, vox)
             # ---- where the block input lives, and where its gradient goes
             if b.name == "init_conv":
-                x_act, g_in = nv.act(ws.x), nv.act(None)
+                x_act, g_in_t = nv.act(ws.x), None
             elif b.name.startswith("down"):
-                x_act, g_in = nv.act(ws.pooled[b.level - 1]), nv.act(ws.g_pooled[b.level - 1])
+                x_act, g_in_t = nv.act(ws.pooled[b.level - 1]), ws.g_pooled[b.level - 1]
             elif b.name == "bottleneck":
-                x_act, g_in = nv.act(ws.blocks["down3"]["out"]), nv.act(ws.g_out["down3"])
+                x_act, g_in_t = nv.act(ws.blocks["down3"]["out"]), ws.g_out["down3"]
             else:
-                x_act, g_in = nv.act(ws.cat[b.level]), nv.act(ws.g_cat[b.level])
+                x_act, g_in_t = nv.act(ws.cat[b.level]), ws.g_cat[b.level]
+            g_in = nv.act(g_in_t)
             if has_sc:
                 r_act = nv.act(buf["r"])
                 nr = nv.norm(sr, P[f"{b.prefix}.shortcut.1.weight"], P[f"{b.prefix}.shortcut.1.bias"], None, IN_EPS, 1.0, vox)
@@ -391,7 +441,9 @@ class UNetPlan:
                         nv.ptr(P[f"{b.prefix}.shortcut.0.weight"]), nv.ptr(G[f"{b.prefix}.shortcut.0.weight"]),
                         g_in, 0, st)
             elif need_gin:
-                ws.g_out["down3"].copy_(gz)      # identity shortcut (bottleneck): d(out)/d(x) passes gz through
+                # identity shortcut (cin == cout: the bottleneck, or a down block of an encoder with equal adjacent widths):
+                # d(out)/d(x) passes gz through into the block's OWN input gradient, which conv1's backward then adds to
+                g_in_t[:N].copy_(gz[:N])
             n1b = nv.norm(s1, P[f"{b.prefix}.norm1.weight"], P[f"{b.prefix}.norm1.bias"], None, IN_EPS, 1.0, vox)
             self._conv_bwd(P, G, b, 1, ws, gy, buf["t1"], n1b, r1, x_act, ident, buf.get("u1"), g_in, 1, None,
                            N, dims, st)

@@ -69,57 +69,51 @@ def _is_native_model(model) -> bool:
     return isinstance(model, Lightweight3DUNet)
 
 
-@torch.no_grad()
-def sliding_window_device(volume: torch.Tensor, model, patch_size=(48, 48, 48), overlap: float = 0.5,
-                          use_gaussian: bool = True, body_mask: Optional[torch.Tensor] = None,
-                          threshold: Optional[float] = None, window_batch: Optional[int] = None):
-    """Device-resident core: `volume` is a CUDA fp32 [D, H, W] tensor; returns (prob [D,H,W] fp32 CUDA,
-    mask int32 [D,H,W] or None).  `threshold` fuses `prob >= threshold` (inferencer.py:64) into the stitch."""
-    nv.require_cuda(volume, "sliding_window_device")
-    dev = volume.device
-    D, H, W = volume.shape
-    pd, ph, pw = (int(p) for p in patch_size)
-    zpos, ypos, xpos = window_positions((D, H, W), (pd, ph, pw), overlap)
-    pkey = (str(dev), D, H, W, pd, ph, pw, float(overlap))
-    cached = _POS_CACHE.get(pkey)
-    if cached is None:          # window grid of this volume shape: built and uploaded once
-        pos = torch.tensor([(z, y, x) for z in zpos for y in ypos for x in xpos], dtype=torch.int32)
-        cached = (pos.to(dev), torch.tensor(zpos, dtype=torch.int32).to(dev), torch.tensor(ypos, dtype=torch.int32).to(dev),
-                  torch.tensor(xpos, dtype=torch.int32).to(dev))
-        if len(_POS_CACHE) > 16:
-            _POS_CACHE.clear()
-        _POS_CACHE[pkey] = cached
-    pos_d, zp, yp, xp = cached
-    nwin = pos_d.shape[0]
-    imp = _importance_on_device((pd, ph, pw), use_gaussian, dev)
+def _batch_cap(model, dev, patch, wb: int) -> int:
+    """Windows per forward batch: the requested count capped by the HBM that is free (or already held by this model's
+    cached inference workspace, which a larger batch would replace).  Re-evaluated whenever the workspace would have to
+    grow -- not once per process."""
+    pd, ph, pw = patch
+    dt = getattr(model, "compute_dtype", torch.float16)
+    have = model._plan.inference_capacity((pd, ph, pw), dt, dev)
+    if have >= wb:
+        return wb
+    key = (str(dev), pd, ph, pw, dt, wb, have)
+    cap = _BATCH_CAP.get(key)
+    if cap is None:             # cudaMemGetInfo is a slow call: once per (configuration, current workspace size)
+        free_b, _ = torch.cuda.mem_get_info(dev)
+        free_b += torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev) + model._plan.cached_bytes()
+        scale = (pd * ph * pw) / 48.0 ** 3 * (2.0 if dt == torch.float32 else 1.0)
+        cap = max(1, min(wb, int(0.5 * free_b / (_BYTES_PER_WINDOW * scale))))
+        if len(_BATCH_CAP) > 64:
+            _BATCH_CAP.clear()
+        _BATCH_CAP[key] = cap
+    return max(cap, min(have, wb))
+
+
+def _forward_windows(model, vol, pos_d, nwin, patch, preds, window_batch):
+    """Network forward over `nwin` windows (positions `pos_d`, int32 [nwin][3]) of the device volume into `preds`."""
+    dev = vol.device
+    D, H, W = vol.shape
+    pd, ph, pw = patch
     st = nv.stream_ptr(dev)
-    vol = volume.contiguous()
     native = _is_native_model(model)
-    if native and model.out_channels != 1:
-        raise ValueError("Expected 3D model output, got a multi-channel prediction")     # utils.py:122-123
-    preds = torch.empty(nwin, 1, pd, ph, pw, dtype=torch.float32, device=dev)
     wb = int(window_batch or WINDOW_BATCH)
-    if window_batch is None:
-        f32 = getattr(model, "compute_dtype", torch.float16) == torch.float32
-        key = (str(dev), pd, ph, pw, f32, wb)
-        cap = _BATCH_CAP.get(key)
-        if cap is None:         # cudaMemGetInfo is a slow call: decided once per configuration (the workspace is cached after that)
-            free_b, _ = torch.cuda.mem_get_info(dev)
-            scale = (pd * ph * pw) / 48.0 ** 3 * (2.0 if f32 else 1.0)
-            cap = max(1, min(wb, int(0.5 * free_b / (_BYTES_PER_WINDOW * scale))))
-            _BATCH_CAP[key] = cap
-        wb = cap
-    model.eval()                                     # utils.py:84 (the reference leaves the model in eval mode)
     if native:
+        if window_batch is None:
+            wb = _batch_cap(model, dev, patch, min(wb, nwin))
         P = dict(model.named_parameters())
         dt = model.compute_dtype
         for p in P.values():
             nv.require_cuda(p, "sliding_window_inference_3d: model parameters")
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise nv.NativeError("sliding_window_inference_3d: model parameters must be contiguous float32 tensors "
+                                     f"(got {p.dtype}); the storage type of the activations is set with set_compute_dtype")
         for s in range(0, nwin, wb):
             n = min(wb, nwin - s)
             batch = torch.empty(n, pd, ph, pw, 1, dtype=dt, device=dev)
             nv.call("l3d_gather_windows", nv.ptr(vol), D, H, W, nv.ptr(pos_d[s:]), n, pd, ph, pw, nv.ptr(batch),
-                    nv.dtype_code(dt), st)
+                    nv.dtype_code(dt), st, algo_bytes=n * pd * ph * pw * (4 + batch.element_size()))
             model._plan.forward(P, batch, False, None, prob_out=preds[s:s + n])
     else:
         # any other torch module: batched forward on the device, stitched by the same kernel (its activation footprint is
@@ -135,14 +129,95 @@ def sliding_window_device(volume: torch.Tensor, model, patch_size=(48, 48, 48), 
             if out.dim() != 5 or out.shape[1] != 1:
                 raise ValueError(f"Expected 3D model output, got shape {tuple(out.shape[1:])}")
             preds[s:s + n] = out.float()
-    prob = torch.empty(D, H, W, dtype=torch.float32, device=dev)
-    mask = torch.empty(D, H, W, dtype=torch.int32, device=dev) if threshold is not None else None
+
+
+@torch.no_grad()
+def sliding_window_device(volume: torch.Tensor, model, patch_size=(48, 48, 48), overlap: float = 0.5,
+                          use_gaussian: bool = True, body_mask: Optional[torch.Tensor] = None,
+                          threshold: Optional[float] = None, window_batch: Optional[int] = None, shard=None):
+    """Device-resident core: `volume` is a CUDA fp32 [D, H, W] tensor; returns (prob [D,H,W] fp32 CUDA,
+    mask int32 [D,H,W] or None).  `threshold` fuses `prob >= threshold` (inferencer.py:64) into the stitch.
+
+    `shard = (rank, world_size, group)`: window-level sharding of THIS volume over the ranks of a torch.distributed group
+    (every rank passes the same volume; see parallel/window_shard.py).  Rank 0 returns the assembled map (bit-identical to
+    the single-GPU stitch of the same predictions), the other ranks return (None, None)."""
+    nv.require_cuda(volume, "sliding_window_device")
+    with torch.cuda.device(volume.device):
+        return _sliding_window_device(volume, model, patch_size, overlap, use_gaussian, body_mask, threshold, window_batch, shard)
+
+
+def _sliding_window_device(volume, model, patch_size, overlap, use_gaussian, body_mask, threshold, window_batch, shard):
+    dev = volume.device
+    if volume.dim() != 3:
+        raise ValueError(f"Expected 3D image [D, H, W], got shape {tuple(volume.shape)}")
+    D, H, W = volume.shape
+    pd, ph, pw = (int(p) for p in patch_size)
+    zpos, ypos, xpos = window_positions((D, H, W), (pd, ph, pw), overlap)
+    rank, world, group = (0, 1, None) if shard is None else shard
+    me = None
+    if world > 1:
+        from .parallel.window_shard import exchange_seams, gather_slabs, plan_x_shards
+        shards = plan_x_shards(xpos, pw, W, world)
+        me = shards[rank]
+    pkey = (str(dev), D, H, W, pd, ph, pw, float(overlap), rank, world)
+    cached = _POS_CACHE.get(pkey)
+    if cached is None:          # window grid of this volume shape: built and uploaded once
+        if me is None:
+            plist, xl = [(z, y, x) for z in zpos for y in ypos for x in xpos], xpos
+        else:                   # own windows, x-position major; the stitcher sees the positions in `need`
+            plist, xl = [(z, y, xpos[c]) for c in me.own for z in zpos for y in ypos], [xpos[c] for c in me.need]
+        i32 = lambda v: torch.tensor(v, dtype=torch.int32).to(dev)
+        cached = (i32(plist).reshape(-1, 3), i32(zpos), i32(ypos), i32(xl))
+        if len(_POS_CACHE) > 16:
+            _POS_CACHE.clear()
+        _POS_CACHE[pkey] = cached
+    pos_d, zp, yp, xp = cached
+    nwin = pos_d.shape[0]
+    imp = _importance_on_device((pd, ph, pw), use_gaussian, dev)
+    st = nv.stream_ptr(dev)
+    vol = volume.contiguous()
+    if _is_native_model(model) and model.out_channels != 1:
+        raise ValueError("Expected 3D model output, got a multi-channel prediction")     # utils.py:122-123
     bm = None
     if body_mask is not None:
+        if tuple(body_mask.shape) != (D, H, W):
+            raise ValueError(f"body_mask shape {tuple(body_mask.shape)} does not match the volume {(D, H, W)}")
         bm = body_mask.to(device=dev, dtype=torch.uint8).contiguous()
-    nv.call("l3d_stitch", nv.ptr(preds), nv.ptr(zp), len(zpos), nv.ptr(yp), len(ypos), nv.ptr(xp), len(xpos),
-            pd, ph, pw, nv.ptr(imp), D, H, W, nv.ptr(bm), nv.ptr(prob),
-            float(np.float32(threshold)) if threshold is not None else 0.0, nv.ptr(mask), st)
+    thr = float(np.float32(threshold)) if threshold is not None else 0.0
+    model.eval()                                     # utils.py:84 (the reference leaves the model in eval mode)
+    per = pd * ph * pw
+    if me is None:
+        preds = torch.empty(nwin, 1, pd, ph, pw, dtype=torch.float32, device=dev)
+        _forward_windows(model, vol, pos_d, nwin, (pd, ph, pw), preds, window_batch)
+        prob = torch.empty(D, H, W, dtype=torch.float32, device=dev)
+        mask = torch.empty(D, H, W, dtype=torch.int32, device=dev) if threshold is not None else None
+        nv.call("l3d_stitch", nv.ptr(preds), nv.ptr(zp), len(zpos), nv.ptr(yp), len(ypos), nv.ptr(xp), len(xpos),
+                pd, ph, pw, nv.ptr(imp), D, H, W, nv.ptr(bm), nv.ptr(prob), thr, nv.ptr(mask), st,
+                algo_bytes=nwin * per * 4 + D * H * W * (4 + (4 if mask is not None else 0)))
+        return prob, mask
+    # ---- window-level sharding: own windows -> seam exchange -> slab stitch -> gather on rank 0
+    nzy = len(zpos) * len(ypos)
+    local = torch.empty(len(me.need) * nzy, 1, pd, ph, pw, dtype=torch.float32, device=dev)
+    if nwin:
+        _forward_windows(model, vol, pos_d, nwin, (pd, ph, pw), local[me.n_recv * nzy:], window_batch)
+    if me.need:
+        exchange_seams(local.view(len(me.need), nzy * per), me, group)
+    prob = torch.empty(D, H, W, dtype=torch.float32, device=dev) if rank == 0 else None
+    slab = None
+    if me.own:
+        wl = me.x1 - me.x0
+        out = prob if rank == 0 else torch.empty(D, H, wl, dtype=torch.float32, device=dev)
+        nv.call("l3d_stitch_slab", nv.ptr(local), nv.ptr(zp), len(zpos), nv.ptr(yp), len(ypos), nv.ptr(xp), len(me.need),
+                len(ypos), 1, nzy, pd, ph, pw, nv.ptr(imp), D, H, W, me.x0, me.x1, W if rank == 0 else wl, me.x0 if rank == 0 else 0,
+                nv.ptr(bm), nv.ptr(out), 0.0, None, st, algo_bytes=len(me.need) * nzy * per * 4 + D * H * wl * 4)
+        slab = out
+    gather_slabs(prob, slab, shards, rank, group)
+    if rank != 0:
+        return None, None
+    mask = None
+    if threshold is not None:
+        mask = torch.empty(D, H, W, dtype=torch.int32, device=dev)
+        nv.call("l3d_threshold", nv.ptr(prob), prob.numel(), thr, nv.ptr(mask), st, algo_bytes=prob.numel() * 8)
     return prob, mask
 
 
