@@ -2,7 +2,8 @@
 """bench.py -- headline benchmark of the B200-native Light-3D-Unet hot path.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--variant dws|grouped|dense] [--dtype f16|f32] [--skip-train] [--skip-cpu]
+                    [--variant dws|grouped|dense] [--dtype f16|f32] [--train-dtype f32|f16] [--skip-train] [--skip-cpu]
+                    [--sweep] [--patch P --batch B] [--eager-gpu]
 
 One JSON line on stdout (rank 0).  Metric (BASELINE.json): sliding-window inference volume-voxels/s on the
 synthetic whole-body 4 mm PET volume (128x128x320, 48^3 windows, 50 % overlap, Gaussian stitching, threshold
@@ -14,7 +15,14 @@ A "step" of the headline metric is one whole volume through the hot path.
   e2e   : the same through the reference-facing API, Inferencer.infer_volume(host array): pinned H2D copy of the
           volume and D2H read of the probability map + box table inside the timed region
 N > 1: one process per GPU (torchrun), volumes are independent -> every rank runs its own volumes, no data-path
-collective ("weak" scaling); training is data parallel with the gradient all-reduce over NCCL.
+collective ("weak" scaling); training is data parallel with the gradient all-reduce over NCCL.  The same line also
+carries "latency": ONE volume whose windows are sharded over the N ranks (seam exchange + slab gather over NCCL,
+parallel/window_shard.py) -- single-volume latency, strong scaling.
+--sweep (configs[4]): forward throughput for patch 48^3 / 64^3 / 96^3 x batch 1..64 per GPU, under "sweep".
+--patch P --batch B: one point of that sweep as the headline workload instead of the volume.
+Storage modes: inference is quoted in fp16 storage (1e-2 bar met with margin, tests/test_gpu_configs.py); the training
+step in fp32 storage, the mode whose every parameter gradient matches the reference (--train-dtype f16 for the faster,
+direction-only mode).
 --impl reference: the oracle's CPU restatement of the reference path (torch-CPU ATen kernels, all host threads)
 on a bounded sample of the same workload.
 """
@@ -222,6 +230,42 @@ def make_inferencer(variant, dtype, device):
     return inf
 
 
+def kernel_table(nv, rec):
+    """TIMER records -> (per-kernel, per-entry-point) {name: [launches, ms, algorithmic bytes]}: dispatching entry points
+    (l3d_dwpw_fwd ...) are attributed to the kernel they launched, the others launch one kernel of their own name."""
+    by_name = {}
+    for (name, tag), (n, t, b) in rec.items():
+        a = by_name.setdefault(name, [0, 0.0, 0])
+        a[0] += n; a[1] += t; a[2] += b
+    by_kernel = dict(nv.TIMER.by_kernel)
+    for k, v in by_name.items():
+        if k not in nv._DISPATCHING:
+            by_kernel[k] = tuple(v)
+    return by_kernel, by_name
+
+
+def bench_patches(args, inf, device, world, patch, batch, steps, warmup):
+    """configs[4]: forward of `batch` patches of patch^3 per GPU through the nn.Module (inputs resident, rotating over
+    enough distinct batches to exceed L2)."""
+    from oracle import synth
+    nb = max(2, min(8, int(np.ceil(300e6 / (batch * patch ** 3 * 4)))))
+    xs = [torch.from_numpy(synth.synth_patches(batch, patch, seed=7 + i)[0]).to(device) for i in range(nb)]
+    model = inf.model.eval()
+
+    def step(i):
+        with torch.no_grad():
+            model(xs[i % nb])
+    for i in range(warmup):
+        step(i)
+    ms = timed(step, steps, world, device)
+    es = 2 if args.dtype == "f16" else 4
+    scale = (patch / 48.0) ** 3
+    per_s = world * batch * steps / (ms * 1e-3)
+    return {"patch": patch, "batch_per_gpu": batch, "ms_per_step": round(ms / steps, 4), "patches_per_s": round(per_s, 1),
+            "patch_voxels_per_s": round(per_s * patch ** 3, 1),
+            "frac_hbm": round(per_s / world * scale * ELEMS_PER_PATCH * es * 2 / 1e9 / peaks()["hbm_gbs"], 4)}
+
+
 def bench_ours(args):
     from light_unet import _native as nv
     from oracle import synth
@@ -232,6 +276,26 @@ def bench_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
     inf = make_inferencer(args.variant, args.dtype, device)
+    if args.patch:
+        # one point of the configs[4] sweep as the headline workload
+        l0 = nv.launch_count()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        r = bench_patches(args, inf, device, world, args.patch, args.batch, args.steps, args.warmup)
+        clocks = sampler.stop() if rank == 0 else None
+        if rank == 0:
+            emit({"metric": "patch forward patch-voxels/s", "value": r["patch_voxels_per_s"], "unit": "voxels/s", "n_gpus": world,
+                  "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                  "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                  "config": {"workload": f"configs[4]: forward of {args.batch} patches of {args.patch}^3 per GPU through Lightweight3DUNet.forward",
+                             "variant": args.variant, "patch": args.patch, "batch_per_gpu": args.batch,
+                             "l2": "inputs rotate over enough distinct batches to exceed the 126 MB L2"},
+                  "patches_per_s": r["patches_per_s"], "frac_hbm": r["frac_hbm"], "gpu_launches": int(nv.launch_count() - l0), "clocks": clocks})
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
     # 8 distinct volumes (168 MB > the 126 MB L2) rotated between steps; every step also streams > 10 GB of
     # activations through HBM, so no input survives in L2 from one step to the next
     base = synth.synth_volume(VOLUME, seed=42 + rank, n_blobs=6)
@@ -269,16 +333,7 @@ def bench_ours(args):
     step_resident(0)
     rec = nv.TIMER.stop()
     tot_ms = sum(v[1] for v in rec.values())
-    by_name = {}
-    for (name, tag), (n, t, b) in rec.items():
-        a = by_name.setdefault(name, [0, 0.0, 0])
-        a[0] += n; a[1] += t; a[2] += b
-    # dominant KERNEL: dispatching entry points (l3d_dwpw_fwd ...) are attributed to the kernel they launched; the other
-    # entry points launch one kernel of their own name
-    by_kernel = dict(nv.TIMER.by_kernel)
-    for k, v in by_name.items():
-        if k not in nv._DISPATCHING:
-            by_kernel[k] = tuple(v)
+    by_kernel, by_name = kernel_table(nv, rec)
     top = max(by_kernel.items(), key=lambda kv: kv[1][1])
     pk = peaks()
     es = 2 if args.dtype == "f16" else 4
@@ -289,10 +344,14 @@ def bench_ours(args):
                 "launches_per_step": top[1][0], "avg_launch_us": round(1e3 * top[1][1] / top[1][0], 1),
                 "share_of_step": round(top[1][1] / tot_ms, 3),
                 "algorithmic_bytes_per_launch": int(top[1][2] / top[1][0]),
-                # whole-network view: compulsory activation bytes per volume / step time
-                "network": {"algorithmic_gb_per_step": round(NWIN * ELEMS_PER_PATCH * es / 1e9, 2),
-                            "achieved_gbs": round(NWIN * ELEMS_PER_PATCH * es / (step_ms * 1e-3) / 1e9, 1),
-                            "frac_hbm": round(NWIN * ELEMS_PER_PATCH * es / (step_ms * 1e-3) / 1e9 / pk["hbm_gbs"], 4),
+                # whole-network view: compulsory activation bytes per volume (21.32 M materialised elements per
+                # 48^3 patch, each written once and read once = 85.3 MB in 16-bit storage; 325 windows = 27.7 GB) / step time;
+                # "declared" = the sum of the per-launch algorithmic bytes the engine declares for the kernels it really runs
+                "network": {"algorithmic_gb_per_step": round(NWIN * ELEMS_PER_PATCH * es * 2 / 1e9, 2),
+                            "achieved_gbs": round(NWIN * ELEMS_PER_PATCH * es * 2 / (step_ms * 1e-3) / 1e9, 1),
+                            "frac_hbm": round(NWIN * ELEMS_PER_PATCH * es * 2 / (step_ms * 1e-3) / 1e9 / pk["hbm_gbs"], 4),
+                            "declared_gb_per_step": round(sum(v[2] for v in by_kernel.values()) / 1e9, 2),
+                            "declared_frac_hbm": round(sum(v[2] for v in by_kernel.values()) / (step_ms * 1e-3) / 1e9 / pk["hbm_gbs"], 4),
                             "tflops": round(NWIN * FWD_FLOP[args.variant] / (step_ms * 1e-3) / 1e12, 2),
                             "frac_tensor": round(NWIN * FWD_FLOP[args.variant] / (step_ms * 1e-3) / 1e12 / pk["bf16_tflops"], 4)},
                 "kernels": {k: {"launches": v[0], "ms": round(v[1], 3), "share": round(v[1] / tot_ms, 3),
@@ -301,9 +360,42 @@ def bench_ours(args):
                 "entry_points": {k: {"launches": v[0], "ms": round(v[1], 3), "share": round(v[1] / tot_ms, 3)} for k, v in
                                  sorted(by_name.items(), key=lambda kv: -kv[1][1])}}
 
+    # ---- single-volume latency with the windows of ONE volume sharded over the ranks (strong scaling)
+    latency = None
+    if world > 1 and not args.no_latency:
+        shard = (rank, world, None)
+        shared = torch.from_numpy(synth.synth_volume(VOLUME, seed=42, n_blobs=6)).to(device)     # the same volume on every rank
+
+        def step_sharded(i):
+            inf.infer_volume(shared, threshold=0.3, return_device=True, shard=shard)
+        for i in range(3):
+            step_sharded(i)
+        ms_lat = timed(step_sharded, args.steps, world, device)
+        latency = {"workload": "ONE 128x128x320 volume, its 13 x-positions of windows sharded over the ranks "
+                               "(seam exchange + slab gather over NCCL, threshold -> CC -> boxes on rank 0)",
+                   "ms_per_volume": round(ms_lat / args.steps, 3), "value": round(NVOX * args.steps / (ms_lat * 1e-3), 1),
+                   "unit": "voxels/s", "scaling": "strong", "n_gpus": world, "ms_per_volume_1gpu_volume_sharded": round(step_ms, 3)}
+
+    sweep = None
+    if args.sweep:
+        sweep = []
+        for patch in (48, 64, 96):
+            for batch in (1, 2, 4, 8, 16, 32, 64):
+                if batch * patch ** 3 > 64 * 64 ** 3 * 2:          # 96^3 x 64 (57 M voxels, ~36 GB fp16 workspace) is skipped
+                    continue
+                sweep.append(bench_patches(args, inf, device, world, patch, batch, max(3, args.steps), 3))
+                inf.model._plan.drop_workspaces()
+
     train = None
     if not args.skip_train:
-        train = bench_train(args, device, rank, world)
+        inf.model._plan.drop_workspaces()
+        train = bench_train(args, device, rank, world, args.train_dtype)
+        if args.train_dtype != "f16" and not args.quick:
+            train["fp16_storage"] = bench_train(args, device, rank, world, "f16")
+
+    eager = None
+    if args.eager_gpu and rank == 0:
+        eager = eager_gpu_leg(args.variant, device)
 
     cpu = None
     if rank == 0 and not args.skip_cpu:
@@ -324,10 +416,16 @@ def bench_ours(args):
                         "ms_per_step": round(ms_e2e / args.steps, 3),
                         "h2d_bytes_per_step": NVOX * 4, "d2h_bytes_per_step": NVOX * 4 + 4 + 32 * max(nboxes[0], 1)},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+        if latency is not None:
+            line["latency"] = latency
+        if sweep is not None:
+            line["sweep"] = sweep
         if train is not None:
             line["train"] = train
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if eager is not None:
+            line["eager_gpu"] = eager
         emit(line)
     if world > 1:
         import torch.distributed as dist
@@ -339,7 +437,37 @@ def window_batch():
     return lu.WINDOW_BATCH
 
 
-def bench_train(args, device, rank, world):
+def eager_gpu_leg(variant, device):
+    """Informational: the reference's own path on THIS GPU -- the oracle's restatement of utils.py:86-137 / unet3d.py run
+    with stock ATen / cuDNN kernels (`.cuda()`, fp32, TF32 off), batch-1 forward per window as the reference does, on a
+    bounded sample (65 windows).  SURVEY 0.1: PyTorch eager is the only existing GPU implementation."""
+    from oracle import synth, unet_ref
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg, sd = cpu_reference_setup(variant)
+    sd = {k: v.to(device) for k, v in sd.items()}
+    vol = torch.from_numpy(synth.synth_volume(VOLUME, seed=42, n_blobs=6)).to(device)
+    wins = [vol[0:48, y:y + 48, x:x + 48] for y in (0, 24, 48, 72, 80) for x in list(range(0, 265, 24)) + [272]]   # 65 windows
+
+    def run(batch):
+        with torch.no_grad():
+            for i in range(0, len(wins), batch):
+                unet_ref.forward(sd, torch.stack(wins[i:i + batch])[:, None], cfg)
+    out = {}
+    for batch in (1, 13):
+        run(batch)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); run(batch); e1.record()
+        torch.cuda.synchronize()
+        wps = len(wins) / (e0.elapsed_time(e1) * 1e-3)
+        out[f"batch{batch}"] = {"windows_per_s": round(wps, 1), "voxels_per_s": round(wps * NVOX / NWIN, 1)}
+    out["note"] = ("oracle port on cuda (ATen/cuDNN eager, fp32, TF32 off), forward only, 65 of the 325 windows; batch1 is how "
+                   "the reference runs (utils.py:115-118)")
+    return out
+
+
+def bench_train(args, device, rank, world, dtype):
     """configs[1]/[3]: training step on 48^3 patches, batch 8 per GPU, data parallel over NCCL when world > 1."""
     from light_unet.models import Lightweight3DUNet, FocalTverskyLoss
     from light_unet.engine import UNetPlan
@@ -351,7 +479,7 @@ def bench_train(args, device, rank, world):
     cfg = unet_ref.UNetCfg(dropout_p=0.1, **kw)
     model = Lightweight3DUNet(dropout_p=0.1, **kw)
     model.load_state_dict(unet_ref.to_torch(synth.synth_state_dict(unet_ref.param_shapes(cfg), 1)))
-    model = model.to(device).set_compute_dtype(args.dtype).train()
+    model = model.to(device).set_compute_dtype(dtype).train()
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5, fused=True)     # trainer.py:75-79
     stepper = DataParallelStep(model, FocalTverskyLoss(), opt, world_size=world)
     B = TRAIN_BATCH
@@ -379,16 +507,19 @@ def bench_train(args, device, rank, world):
         step_e2e(i)
     ms_e2e = timed(step_e2e, steps, world, device)
     pk = peaks()
-    es = 2 if args.dtype == "f16" else 4
+    es = 2 if dtype == "f16" else 4
     per_step_s = ms * 1e-3 / steps
+    parity = ("every parameter gradient as close to the float64 oracle as the reference's own fp32 arithmetic (tests/test_gpu_configs.py)"
+              if dtype == "f32" else "loss 1e-4, probabilities 1e-2, whole-gradient cosine > 0.98 (per-tensor parity not claimed)")
     return {"metric": "train 48^3 patches/s", "value": round(world * B * steps / (ms * 1e-3), 1), "unit": "patches/s",
+            "dtype": dtype, "parity": parity,
             "ms_per_step": round(ms / steps, 3), "steps": steps, "global_batch": world * B,
             "workload": "configs[1]: fwd + FocalTversky + bwd + AdamW(lr 1e-4, wd 1e-5), dropout 0.1, batch 8 of 48^3 per GPU",
             "parallelism": f"dp{world}", "loss": float(last[0]) if last[0] is not None else None,
             "e2e": {"value": round(world * B * steps / (ms_e2e * 1e-3), 1), "unit": "patches/s",
                     "h2d_bytes_per_step": 2 * B * 48 ** 3 * 4, "d2h_bytes_per_step": 4},
-            # forward compulsory traffic x3 (fwd + ~2x for bwd), SURVEY 8(d)
-            "frac_hbm": round(3 * B * ELEMS_PER_PATCH * es / per_step_s / 1e9 / pk["hbm_gbs"], 4)}
+            # forward compulsory traffic (write + read) x3 (fwd + ~2x for bwd)
+            "frac_hbm": round(3 * B * ELEMS_PER_PATCH * es * 2 / per_step_s / 1e9 / pk["hbm_gbs"], 4)}
 
 
 # ----------------------------------------------------------------------------------- CPU reference arm
@@ -458,8 +589,8 @@ def bench_reference(args):
     torch.set_num_threads(cores)
     cfg, sd = cpu_reference_setup(args.variant)
     full = synth.synth_volume(VOLUME, seed=42, n_blobs=6)
-    sub = np.ascontiguousarray(full[:48, :48, :144])            # 1 x 1 x 5 = 5 windows per step
-    nwin = 5
+    sub = np.ascontiguousarray(full[:48])                       # one z-slab of the window grid: 1 x 5 x 13 = 65 windows per step
+    nwin = 65
     for _ in range(args.warmup):
         cpu_sample(cfg, sd, sub)
     t0 = time.perf_counter()
@@ -505,6 +636,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--variant", default="dws", choices=sorted(VARIANTS))
     ap.add_argument("--dtype", default="f16", choices=["f16", "f32"])
+    ap.add_argument("--train-dtype", default="f32", choices=["f16", "f32"])
+    ap.add_argument("--sweep", action="store_true", help="configs[4]: patch 48/64/96 x batch 1..64 forward throughput")
+    ap.add_argument("--patch", type=int, default=0, help="with --batch: one sweep point as the headline workload")
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--eager-gpu", action="store_true", help="informational: the oracle port on cuda (ATen/cuDNN eager)")
+    ap.add_argument("--no-latency", action="store_true", help="N > 1: skip the window-sharded single-volume latency leg")
+    ap.add_argument("--quick", action="store_true", help="skip the secondary legs (fp16-storage training)")
     ap.add_argument("--skip-train", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()

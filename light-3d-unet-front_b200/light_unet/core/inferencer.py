@@ -24,6 +24,30 @@ from .config import ConfigManager
 BBOX_TABLE_CAP = 1 << 16
 
 
+def _load_nifti(path):
+    """-> (float32 array in nibabel index order, affine, header with get_zooms()): nibabel as in the reference
+    (inferencer.py:122-125) when it is installed, the built-in NIfTI-1 reader (io_nifti) otherwise."""
+    try:
+        import nibabel as nib
+    except ImportError:
+        from .. import io_nifti
+        data, hdr = io_nifti.load(path)
+        return data, hdr.affine, hdr
+    img = nib.load(path)
+    return img.get_fdata().astype(np.float32), img.affine, img.header
+
+
+def _save_nifti(data, affine, header, path):
+    """inferencer.py:164-165."""
+    try:
+        import nibabel as nib
+    except ImportError:
+        from .. import io_nifti
+        io_nifti.save(data, affine, header if isinstance(header, io_nifti.NiftiHeader) else None, path)
+        return
+    nib.save(nib.Nifti1Image(data, affine, header), path)
+
+
 class Inferencer:
     """Inference class for generating predictions (reference: inferencer.py:18-60)."""
 
@@ -66,7 +90,8 @@ class Inferencer:
         st = nv.stream_ptr(prob_d.device)
         table = torch.empty(BBOX_TABLE_CAP, 8, dtype=torch.int32, device=prob_d.device)
         nv.call("l3d_bbox_init", nv.ptr(table), BBOX_TABLE_CAP, st)
-        nv.call("l3d_bbox_reduce", nv.ptr(labels), nv.ptr(prob_d), D, H, W, nv.ptr(table), BBOX_TABLE_CAP, st)
+        nv.call("l3d_bbox_reduce", nv.ptr(labels), nv.ptr(prob_d), D, H, W, nv.ptr(table), BBOX_TABLE_CAP, st,
+                algo_bytes=8 * D * H * W)                          # labels + probabilities read once
         n = int(n_d.item())
         if n > BBOX_TABLE_CAP:
             cap = n
@@ -155,15 +180,12 @@ class Inferencer:
     # ------------------------------------------------------------- file level
     def infer_case(self, case_id, data_dir, threshold=0.3):
         """Single-case inference with the reference's file layout (inferencer.py:113-183)."""
-        import nibabel as nib   # NIfTI I/O (not part of the accelerated path)
         data_dir = Path(data_dir)
         image_files = find_case_files(data_dir, case_id, file_type="image")
         if len(image_files) == 0:
             print(f"Warning: No image files found for {case_id}")
             return False
-        image_nii = nib.load(image_files[0])
-        image = image_nii.get_fdata().astype(np.float32)
-        affine, header = image_nii.affine, image_nii.header
+        image, affine, header = _load_nifti(image_files[0])
         spacing = [float(s) for s in header.get_zooms()[:3]]
         bm_cfg = self.config.get("data", {}).get("body_mask", {})
         apply_bm = bm_cfg.get("apply_to_inference", False) and bm_cfg.get("enabled", False)
@@ -171,7 +193,7 @@ class Inferencer:
         if apply_bm:
             bm_path = data_dir / "body_masks" / f"{case_id}.nii.gz"
             if bm_path.exists():
-                body_mask = nib.load(bm_path).get_fdata().astype(bool)
+                body_mask = _load_nifti(bm_path)[0].astype(bool)
             else:
                 print(f"Warning: Body mask not found for {case_id}")
         print(f"Running inference on {case_id}...")
@@ -180,7 +202,7 @@ class Inferencer:
         except Exception as e:   # the reference swallows sliding-window failures and reports the case as failed
             print(f"Error during inference execution for {case_id}: {e}")
             return False
-        nib.save(nib.Nifti1Image(prob_map, affine, header), self.prob_maps_dir / f"{case_id}_prob.nii.gz")
+        _save_nifti(prob_map, affine, header, self.prob_maps_dir / f"{case_id}_prob.nii.gz")
         bbox_json = {"case_id": case_id, "processing_path": "B", "orig_spacing": spacing, "threshold": threshold,
                      "num_candidates": len(bboxes), "candidates": bboxes}
         bbox_path = self.bboxes_dir / f"{case_id}_bboxes.json"

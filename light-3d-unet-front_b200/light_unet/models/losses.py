@@ -29,7 +29,7 @@ class _FocalTverskyFn(torch.autograd.Function):
         t = t.contiguous()
         st = nv.stream_ptr(p.device)
         sums = torch.zeros(3, dtype=torch.float64, device=p.device)
-        nv.call("l3d_ftl_sums", nv.ptr(p), nv.ptr(t), p.numel(), nv.ptr(sums), st)
+        nv.call("l3d_ftl_sums", nv.ptr(p), nv.ptr(t), p.numel(), nv.ptr(sums), st, algo_bytes=8 * p.numel())
         if reduce_group is not None:
             # data-parallel: the Tversky index is a ratio of batch-global sums (losses.py:44-49), so the three
             # sums are all-reduced before the ratio
@@ -48,7 +48,8 @@ class _FocalTverskyFn(torch.autograd.Function):
         t, coef = ctx.saved_tensors
         g = g_loss.reshape(1).float().contiguous()
         grad = torch.empty(t.numel(), dtype=torch.float32, device=t.device)
-        nv.call("l3d_ftl_grad", nv.ptr(t), t.numel(), nv.ptr(coef), nv.ptr(g), nv.ptr(grad), nv.stream_ptr(t.device))
+        nv.call("l3d_ftl_grad", nv.ptr(t), t.numel(), nv.ptr(coef), nv.ptr(g), nv.ptr(grad), nv.stream_ptr(t.device),
+                algo_bytes=8 * t.numel())
         return grad.view(ctx.shape), None, None, None, None, None, None
 
 

@@ -28,7 +28,7 @@ def label_device(mask: torch.Tensor, min_size: int = 0):
     labels = torch.empty(D, H, W, dtype=torch.int32, device=m.device)
     n_out = torch.zeros(1, dtype=torch.int32, device=m.device)
     nv.call("l3d_ccl_label", nv.ptr(m), D, H, W, int(min_size), nv.ptr(labels), nv.ptr(n_out), nv.ptr(work),
-            nv.stream_ptr(m.device))
+            nv.stream_ptr(m.device), algo_bytes=8 * nvox)          # mask read once + labels written once
     return labels, n_out
 
 

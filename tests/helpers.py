@@ -28,3 +28,41 @@ def load_unet_case(name):
 
 def sub(a, s):
     return a if not s else a[:, :, ::s, ::s, ::s]
+
+
+def oracle_step(cfg, sd_np, x, t, masks, dtype=torch.float32, quant=None):
+    """One forward + Focal Tversky + backward of the oracle (CPU).  dtype=float64 gives the reference's algorithm without
+    its fp32 round-off: the yardstick the gradient tests measure BOTH the CUDA path and the fp32 oracle against."""
+    from oracle import loss_ref
+    sd = {k: v.to(dtype).requires_grad_(True) for k, v in unet_ref.to_torch(sd_np).items()}
+    m = None if masks is None else [None if k is None else k.to(dtype) for k in masks]
+    ref = unet_ref.forward(sd, torch.from_numpy(x).to(dtype), cfg, m, quant=quant)
+    loss = loss_ref.focal_tversky(ref, torch.from_numpy(t).to(dtype))
+    loss.backward()
+    return ref.detach().numpy(), float(loss.item()), {k: v.grad.numpy().astype(np.float64) for k, v in sd.items()}
+
+
+def per_tensor_errors(grads, rgrads):
+    """rel-L2 per gradient tensor against ||ref|| + floor, floor = 1e-3 x the largest gradient norm of the model: a conv
+    that feeds an InstanceNorm has analytically zero gradient along its own weight direction (for a 1-input-channel conv
+    that is the whole gradient), so such tensors hold only round-off."""
+    gmax = max(np.linalg.norm(v) for v in rgrads.values())
+    floor = 1e-3 * gmax
+    return {k: float(np.linalg.norm(np.asarray(grads[k], dtype=np.float64) - rgrads[k]) / (np.linalg.norm(rgrads[k]) + floor))
+            for k in grads}
+
+
+def check_gradients_like_reference(grads, g32, g64, tag, floor_tol=2e-3, factor=3.0):
+    """The parameter gradients of this network are ill-conditioned (max-pool arg-max routing, LeakyReLU kinks and the
+    InstanceNorm backward's mean subtraction of a nearly constant Focal Tversky gradient): the reference's OWN fp32
+    arithmetic differs from the same algorithm in float64 by up to ~1e-2 relative L2 on individual tensors (measured:
+    7.8e-3 worst / 2.1e-3 median at 4x48^3).  So "equal to the reference" is tested the only way that is well defined --
+    per tensor, the CUDA path must be as close to the float64 result as the fp32 oracle is (within `factor`, with a
+    floor of `floor_tol` for tensors the fp32 oracle happens to get almost exactly)."""
+    e_ours, e_ref = per_tensor_errors(grads, g64), per_tensor_errors(g32, g64)
+    bad = {k: (e_ours[k], e_ref[k]) for k in e_ours if e_ours[k] > max(floor_tol, factor * e_ref[k])}
+    wo, wr = max(e_ours, key=e_ours.get), max(e_ref, key=e_ref.get)
+    print(f"{tag}: per-tensor gradient rel-L2 vs the float64 oracle -- CUDA worst {e_ours[wo]:.3e} ({wo}), median "
+          f"{np.median(list(e_ours.values())):.3e}; fp32 oracle worst {e_ref[wr]:.3e} ({wr}), median {np.median(list(e_ref.values())):.3e}")
+    assert not bad, bad
+    return e_ours, e_ref
