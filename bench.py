@@ -480,8 +480,9 @@ def bench_train(args, device, rank, world, dtype):
     model = Lightweight3DUNet(dropout_p=0.1, **kw)
     model.load_state_dict(unet_ref.to_torch(synth.synth_state_dict(unet_ref.param_shapes(cfg), 1)))
     model = model.to(device).set_compute_dtype(dtype).train()
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5, fused=True)     # trainer.py:75-79
-    stepper = DataParallelStep(model, FocalTverskyLoss(), opt, world_size=world)
+    graph = args.variant == "dws" and not args.no_graph
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5, fused=True, capturable=graph)     # trainer.py:75-79
+    stepper = DataParallelStep(model, FocalTverskyLoss(), opt, world_size=world, use_graph=graph)
     B = TRAIN_BATCH
     hx, ht = [], []
     for i in range(4):
@@ -495,17 +496,21 @@ def bench_train(args, device, rank, world, dtype):
         last[0] = stepper.step(dx[i % 4], dtg[i % 4])
 
     def step_e2e(i):
-        x = hx[i % 4].to(device, non_blocking=True)
-        t = ht[i % 4].to(device, non_blocking=True)
-        last[0] = stepper.step(x, t).item()         # trainer.py:234 reads the loss every step
+        # the batch of step i was staged (pinned host -> device on a side stream) while step i - 1 ran; the loss is read
+        # every step as trainer.py:234 does
+        loss = stepper.step()
+        stepper.prefetch(hx[(i + 1) % 4], ht[(i + 1) % 4])
+        last[0] = loss.item()
 
     steps = max(args.steps * 4, 10)
     for i in range(max(args.warmup, 3)):
         step_resident(i)
     ms = timed(step_resident, steps, world, device)
+    stepper.prefetch(hx[0], ht[0])
     for i in range(2):
         step_e2e(i)
     ms_e2e = timed(step_e2e, steps, world, device)
+    stepper._staged = None
     pk = peaks()
     es = 2 if dtype == "f16" else 4
     per_step_s = ms * 1e-3 / steps
@@ -515,7 +520,8 @@ def bench_train(args, device, rank, world, dtype):
             "dtype": dtype, "parity": parity,
             "ms_per_step": round(ms / steps, 3), "steps": steps, "global_batch": world * B,
             "workload": "configs[1]: fwd + FocalTversky + bwd + AdamW(lr 1e-4, wd 1e-5), dropout 0.1, batch 8 of 48^3 per GPU",
-            "parallelism": f"dp{world}", "loss": float(last[0]) if last[0] is not None else None,
+            "parallelism": f"dp{world}", "cuda_graph": bool(stepper.use_graph and stepper._graph is not None),
+            "loss": float(last[0]) if last[0] is not None else None,
             "e2e": {"value": round(world * B * steps / (ms_e2e * 1e-3), 1), "unit": "patches/s",
                     "h2d_bytes_per_step": 2 * B * 48 ** 3 * 4, "d2h_bytes_per_step": 4},
             # forward compulsory traffic (write + read) x3 (fwd + ~2x for bwd)
@@ -643,6 +649,7 @@ def main():
     ap.add_argument("--eager-gpu", action="store_true", help="informational: the oracle port on cuda (ATen/cuDNN eager)")
     ap.add_argument("--no-latency", action="store_true", help="N > 1: skip the window-sharded single-volume latency leg")
     ap.add_argument("--quick", action="store_true", help="skip the secondary legs (fp16-storage training)")
+    ap.add_argument("--no-graph", action="store_true", help="training step launched eagerly instead of as one CUDA graph")
     ap.add_argument("--skip-train", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()

@@ -243,7 +243,19 @@ int l3d_bbox_init(int32_t *table, int cap, void *stream);
 int l3d_bbox_reduce(const int32_t *labels, const float *prob, int D, int H, int W, int32_t *table, int cap,
                     void *stream);
 
+/* Lesion-matching statistics of two label maps in one pass (metrics.py:127-229, :311-404; replaces np.bincount over
+ * pred_id * (nb + 1) + target_id, the size bincounts and ndimage.center_of_mass): counts[a * (nb + 1) + b] += 1 for voxels
+ * labelled a in A and b in B (both > 0); mom_x[id * 4 + {0, 1, 2, 3}] += {1, z, y, x} per labelled voxel.  counts
+ * (int32 [(na + 1) * (nb + 1)]), mom_a (int64 [(na + 1) * 4]) and mom_b must be zeroed by the caller; labels_b / counts /
+ * mom_b may be NULL (moments of one map only). */
+int l3d_label_pair_stats(const int32_t *labels_a, const int32_t *labels_b, int D, int H, int W, int na, int nb,
+                         int32_t *counts, int64_t *mom_a, int64_t *mom_b, void *stream);
+
 /* ------------------------------------------------------------- diagnostics -- */
+
+/* The library reads its tuning / test knobs (L3D_* environment variables) once per call site; call this after changing
+ * one inside a running process. */
+void l3d_env_refresh(void);
 
 /* Name of the kernel the last dispatching entry point (l3d_dwpw_fwd, l3d_conv3_fwd, l3d_convt_fwd) launched on this
  * thread: "conv3_tc_kernel", "dwpw_tc_kernel", "dwpw_c1_kernel", ... ("" before the first launch). */

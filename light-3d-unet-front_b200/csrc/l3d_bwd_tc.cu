@@ -19,15 +19,14 @@
 
 namespace {
 
-static bool env_flag_off(const char *name) { const char *e = getenv(name); return !(e && e[0] == '1'); }
 
 constexpr int NT = 256, TV = 128;
 constexpr int PLANE = TV * 16;          // bytes of one 8-channel group of a tile
 
 struct PwTcArgs {
     const float *gz; int ldg;
-    const h16 *t; int ldt; NormDev nt; const double *red;
-    const h16 *u; int ldu; NormDev un;
+    const void *t; int ldt; NormDev nt; const double *red;      // stored activations: fp16 or fp32 (template T)
+    const void *u; int ldu; NormDev un;
     int N; long long vox;
     int Cg, Cu;
     const float *w; float *g_w;
@@ -49,17 +48,45 @@ __device__ __forceinline__ void split_h16x8(const uint4 &r, uint4 &hi, uint4 &lo
     split2(h16_lo(r.x), h16_hi(r.x), hi.x, lo.x); split2(h16_lo(r.y), h16_hi(r.y), hi.y, lo.y);
     split2(h16_lo(r.z), h16_hi(r.z), hi.z, lo.z); split2(h16_lo(r.w), h16_hi(r.w), hi.w, lo.w);
 }
-__device__ __forceinline__ void store_u_split(unsigned char *sUh, unsigned char *sUl, size_t off, const uint4 &r, bool ok) {
+// eight consecutive stored channels of one voxel, fp16 (16 bytes) or fp32 (32 bytes)
+template <typename T> struct V8;
+template <> struct V8<h16> {
+    uint4 r;
+    __device__ __forceinline__ void load(const h16 *p) { r = *reinterpret_cast<const uint4 *>(p); }
+    __device__ __forceinline__ void unpack(float (&f)[8]) const {
+        f[0] = h16_lo(r.x); f[1] = h16_hi(r.x); f[2] = h16_lo(r.y); f[3] = h16_hi(r.y);
+        f[4] = h16_lo(r.z); f[5] = h16_hi(r.z); f[6] = h16_lo(r.w); f[7] = h16_hi(r.w);
+    }
+};
+template <> struct V8<float> {
+    float4 a, b;
+    __device__ __forceinline__ void load(const float *p) { a = reinterpret_cast<const float4 *>(p)[0]; b = reinterpret_cast<const float4 *>(p)[1]; }
+    __device__ __forceinline__ void unpack(float (&f)[8]) const {
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
+};
+// eight values -> bf16 hi / lo planes (exact for stored fp16 values, 16 significand bits for fp32)
+__device__ __forceinline__ void store_split8(unsigned char *sh, unsigned char *sl, size_t off, const float (&f)[8], bool ok) {
     uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
-    if (ok) split_h16x8(r, hi, lo);
-    *reinterpret_cast<uint4 *>(sUh + off) = hi;
-    *reinterpret_cast<uint4 *>(sUl + off) = lo;
+    if (ok) {
+        split2(f[0], f[1], hi.x, lo.x); split2(f[2], f[3], hi.y, lo.y);
+        split2(f[4], f[5], hi.z, lo.z); split2(f[6], f[7], hi.w, lo.w);
+    }
+    *reinterpret_cast<uint4 *>(sh + off) = hi;
+    *reinterpret_cast<uint4 *>(sl + off) = lo;
+}
+template <typename T>
+__device__ __forceinline__ void store_u_split(unsigned char *sUh, unsigned char *sUl, size_t off, const V8<T> &r, bool ok) {
+    float f[8];
+    r.unpack(f);
+    store_split8(sUh, sUl, off, f, ok);
 }
 
 // GI / UI: G / U staging items (one 8-channel group of one voxel) per thread, held in registers one tile ahead so the
 // global loads of tile T+1 are in flight during the MMAs and the epilogue of tile T.  GI == 0: no prefetch (wide layers).
-template <int GI, int UI>
+template <typename T, int GI, int UI>
 __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
+    const T *At = reinterpret_cast<const T *>(A.t), *Au = reinterpret_cast<const T *>(A.u);
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_tmem;
@@ -100,7 +127,7 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
     uint32_t phase = 0;
     bool first = true;
     float4 pg0[GI > 0 ? GI : 1], pg1[GI > 0 ? GI : 1];
-    uint4 pt[GI > 0 ? GI : 1], pu[UI > 0 ? UI : 1];
+    V8<T> pt[GI > 0 ? GI : 1], pu[UI > 0 ? UI : 1];
     auto prefetch = [&](long long tl) {
         const int pn = (int)(tl / tiles_per_sample);
         const long long pv0 = (tl % tiles_per_sample) * TV;
@@ -111,14 +138,14 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
                 const size_t gv = (size_t)pn * A.vox + pv0 + v;
                 pg0[i] = *reinterpret_cast<const float4 *>(A.gz + gv * (size_t)A.ldg + q * 8);
                 pg1[i] = *reinterpret_cast<const float4 *>(A.gz + gv * (size_t)A.ldg + q * 8 + 4);
-                if (has_nt) pt[i] = *reinterpret_cast<const uint4 *>(A.t + gv * (size_t)A.ldt + q * 8);
+                if (has_nt) pt[i].load(At + gv * (size_t)A.ldt + q * 8);
             }
         }
         if (has_gw) {
 #pragma unroll
             for (int i = 0; i < UI; ++i) {
                 const int item = tid + i * NT, v = item & (TV - 1), q = item >> 7;
-                if (pv0 + v < A.vox) pu[i] = *reinterpret_cast<const uint4 *>(A.u + ((size_t)pn * A.vox + pv0 + v) * (size_t)A.ldu + q * 8);
+                if (pv0 + v < A.vox) pu[i].load(Au + ((size_t)pn * A.vox + pv0 + v) * (size_t)A.ldu + q * 8);
             }
         }
     };
@@ -149,13 +176,10 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
                 if (v0 + v < A.vox) {
                     float g[8] = {pg0[i].x, pg0[i].y, pg0[i].z, pg0[i].w, pg1[i].x, pg1[i].y, pg1[i].z, pg1[i].w};
                     if (has_nt) {
-                        const uint32_t tw[4] = {pt[i].x, pt[i].y, pt[i].z, pt[i].w};
+                        float tv[8];
+                        pt[i].unpack(tv);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int c = q * 8 + 2 * j;
-                            g[2 * j] = fmaf(s_ca[c], g[2 * j], fmaf(s_cb[c], h16_lo(tw[j]), s_cd[c]));
-                            g[2 * j + 1] = fmaf(s_ca[c + 1], g[2 * j + 1], fmaf(s_cb[c + 1], h16_hi(tw[j]), s_cd[c + 1]));
-                        }
+                        for (int j = 0; j < 8; ++j) g[j] = fmaf(s_ca[q * 8 + j], g[j], fmaf(s_cb[q * 8 + j], tv[j], s_cd[q * 8 + j]));
                     }
                     split2(g[0], g[1], hi.x, lo.x); split2(g[2], g[3], hi.y, lo.y);
                     split2(g[4], g[5], hi.z, lo.z); split2(g[6], g[7], hi.w, lo.w);
@@ -183,14 +207,12 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
                     const float4 g1 = *reinterpret_cast<const float4 *>(A.gz + gv * (size_t)A.ldg + q * 8 + 4);
                     float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
                     if (has_nt) {
-                        const uint4 tr = *reinterpret_cast<const uint4 *>(A.t + gv * (size_t)A.ldt + q * 8);
-                        const uint32_t tw[4] = {tr.x, tr.y, tr.z, tr.w};
+                        V8<T> tr;
+                        tr.load(At + gv * (size_t)A.ldt + q * 8);
+                        float tv[8];
+                        tr.unpack(tv);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int c = q * 8 + 2 * j;
-                            g[2 * j] = fmaf(s_ca[c], g[2 * j], fmaf(s_cb[c], h16_lo(tw[j]), s_cd[c]));
-                            g[2 * j + 1] = fmaf(s_ca[c + 1], g[2 * j + 1], fmaf(s_cb[c + 1], h16_hi(tw[j]), s_cd[c + 1]));
-                        }
+                        for (int j = 0; j < 8; ++j) g[j] = fmaf(s_ca[q * 8 + j], g[j], fmaf(s_cb[q * 8 + j], tv[j], s_cd[q * 8 + j]));
                     }
                     split2(g[0], g[1], hi.x, lo.x); split2(g[2], g[3], hi.y, lo.y);
                     split2(g[4], g[5], hi.z, lo.z); split2(g[6], g[7], hi.w, lo.w);
@@ -202,23 +224,18 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
             if (has_gw) {
                 for (int item = tid; item < uq * TV; item += NT) {
                     const int v = item & (TV - 1), q = item >> 7;
-                    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                    float uf[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                     if (v0 + v < A.vox) {
                         const size_t gv = (size_t)n * A.vox + v0 + v;
-                        o = *reinterpret_cast<const uint4 *>(A.u + gv * (size_t)A.ldu + q * 8);
+                        V8<T> o;
+                        o.load(Au + gv * (size_t)A.ldu + q * 8);
+                        o.unpack(uf);
                         if (!u_ident) {
-                            uint32_t w4[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int k = q * 8 + 2 * j;
-                                const float a0 = lrelu(fmaf(h16_lo(w4[j]), s_us[k], s_uh[k]), A.un.slope);
-                                const float a1 = lrelu(fmaf(h16_hi(w4[j]), s_us[k + 1], s_uh[k + 1]), A.un.slope);
-                                w4[j] = pack_h16x2(a0, a1);
-                            }
-                            o = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                            for (int j = 0; j < 8; ++j) uf[j] = lrelu(fmaf(uf[j], s_us[q * 8 + j], s_uh[q * 8 + j]), A.un.slope);
                         }
                     }
-                    store_u_split(sUh, sUl, (size_t)q * PLANE + (size_t)v * 16, o, true);
+                    store_split8(sUh, sUl, (size_t)q * PLANE + (size_t)v * 16, uf, true);
                 }
             }
         }
@@ -299,8 +316,9 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
 // double-buffered, so while the tensor pipe works on tile T the CTA converts tile T+1 (whose global loads were issued a
 // full iteration earlier) and issues the loads of T+2; the only exposed step per tile is the D1 epilogue.  Tiles are
 // assigned in contiguous ranges (one or two sample changes per CTA).
-template <int GI, int UI>
+template <typename T, int GI, int UI>
 __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
+    const T *At = reinterpret_cast<const T *>(A.t), *Au = reinterpret_cast<const T *>(A.u);
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_tmem;
@@ -335,7 +353,7 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
     const long long per = (total_tiles + gridDim.x - 1) / gridDim.x;
     const long long t_begin = (long long)blockIdx.x * per, t_end = t_begin + per < total_tiles ? t_begin + per : total_tiles;
     float4 pg0[GI], pg1[GI];
-    uint4 pt[GI], pu[UI];
+    V8<T> pt[GI], pu[UI];
     auto prefetch = [&](long long tl) {
         const int pn = (int)(tl / tiles_per_sample);
         const long long pv0 = (tl % tiles_per_sample) * TV;
@@ -346,14 +364,14 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
                 const size_t gv = (size_t)pn * A.vox + pv0 + v;
                 pg0[i] = *reinterpret_cast<const float4 *>(A.gz + gv * (size_t)A.ldg + q * 8);
                 pg1[i] = *reinterpret_cast<const float4 *>(A.gz + gv * (size_t)A.ldg + q * 8 + 4);
-                if (has_nt) pt[i] = *reinterpret_cast<const uint4 *>(A.t + gv * (size_t)A.ldt + q * 8);
+                if (has_nt) pt[i].load(At + gv * (size_t)A.ldt + q * 8);
             }
         }
         if (has_gw) {
 #pragma unroll
             for (int i = 0; i < UI; ++i) {
                 const int item = tid + i * NT, q = item % uq, v = item / uq;
-                if (pv0 + v < A.vox) pu[i] = *reinterpret_cast<const uint4 *>(A.u + ((size_t)pn * A.vox + pv0 + v) * (size_t)A.ldu + q * 8);
+                if (pv0 + v < A.vox) pu[i].load(Au + ((size_t)pn * A.vox + pv0 + v) * (size_t)A.ldu + q * 8);
             }
         }
     };
@@ -378,13 +396,10 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
             if (v0 + v < A.vox) {
                 float g[8] = {pg0[i].x, pg0[i].y, pg0[i].z, pg0[i].w, pg1[i].x, pg1[i].y, pg1[i].z, pg1[i].w};
                 if (has_nt) {
-                    const uint32_t tw[4] = {pt[i].x, pt[i].y, pt[i].z, pt[i].w};
+                    float tv[8];
+                    pt[i].unpack(tv);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int c = q * 8 + 2 * j;
-                        g[2 * j] = fmaf(s_ca[c], g[2 * j], fmaf(s_cb[c], h16_lo(tw[j]), s_cd[c]));
-                        g[2 * j + 1] = fmaf(s_ca[c + 1], g[2 * j + 1], fmaf(s_cb[c + 1], h16_hi(tw[j]), s_cd[c + 1]));
-                    }
+                    for (int j = 0; j < 8; ++j) g[j] = fmaf(s_ca[q * 8 + j], g[j], fmaf(s_cb[q * 8 + j], tv[j], s_cd[q * 8 + j]));
                 }
                 split2(g[0], g[1], hi.x, lo.x); split2(g[2], g[3], hi.y, lo.y);
                 split2(g[4], g[5], hi.z, lo.z); split2(g[6], g[7], hi.w, lo.w);
@@ -494,13 +509,15 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
 int l3d_pw_bwd_tc(const l3d_act *gz, const l3d_act *t, const l3d_norm *nt, const double *red, const l3d_act *u,
                   const l3d_norm *un, int N, long long vox, const float *w, float *g_w, const l3d_act *g_u,
                   int accumulate_gu, void *stream) {
-    { const char *e = getenv("L3D_NO_TC_BWD"); if (e && e[0] == '1') return -1; }
+    if (L3D_ENV_INT("L3D_NO_TC_BWD", 0) == 1) return -1;
     const int Cg = gz->C, Cu = u->C;
     const bool has_nt = nt != nullptr && nt->stats != nullptr, has_gu = !act_null(g_u);
-    if (u->dtype != L3D_F16 || gz->dtype != L3D_F32 || (has_nt && t->dtype != L3D_F16)) return -1;
+    const bool f32 = u->dtype == L3D_F32;                 // storage type of the activations t and u (gradients are always fp32)
+    if (gz->dtype != L3D_F32 || (has_nt && t->dtype != u->dtype)) return -1;
     if (Cg % 16 != 0 || Cu % 16 != 0 || Cg > 128 || Cu > 256) return -1;
     auto al = [](const l3d_act *a, int elems, int bytes) { return a->ldc % elems == 0 && reinterpret_cast<uintptr_t>(a->ptr) % bytes == 0; };
-    if (!al(gz, 4, 16) || !al(u, 8, 16) || (has_nt && !al(t, 8, 16)) || (has_gu && !al(g_u, 4, 16))) return -1;
+    const int sv = f32 ? 4 : 8;
+    if (!al(gz, 4, 16) || !al(u, sv, 16) || (has_nt && !al(t, sv, 16)) || (has_gu && !al(g_u, 4, 16))) return -1;
     if (g_w == nullptr && !has_gu) return -1;
     // an activated u is not exactly representable in bf16 (it would need a hi/lo pair like g_t); every caller on the
     // U-Net path passes a stored bf16 tensor with the identity norm, so the general case stays on the CUDA-core kernel
@@ -514,8 +531,8 @@ int l3d_pw_bwd_tc(const l3d_act *gz, const l3d_act *t, const l3d_norm *nt, const
     while (cols < 2 * Cu) cols <<= 1;
     PwTcArgs A;
     A.gz = (const float *)gz->ptr; A.ldg = gz->ldc;
-    A.t = has_nt ? (const h16 *)t->ptr : nullptr; A.ldt = has_nt ? t->ldc : 0; A.nt = norm_dev(nt); A.red = red;
-    A.u = (const h16 *)u->ptr; A.ldu = u->ldc; A.un = norm_dev(un);
+    A.t = has_nt ? t->ptr : nullptr; A.ldt = has_nt ? t->ldc : 0; A.nt = norm_dev(nt); A.red = red;
+    A.u = u->ptr; A.ldu = u->ldc; A.un = norm_dev(un);
     A.N = N; A.vox = vox; A.Cg = Cg; A.Cu = Cu;
     A.w = w; A.g_w = g_w;
     A.g_u = has_gu ? (float *)g_u->ptr : nullptr; A.ldgu = has_gu ? g_u->ldc : 0; A.accumulate = accumulate_gu;
@@ -534,23 +551,21 @@ int l3d_pw_bwd_tc(const l3d_act *gz, const l3d_act *t, const l3d_norm *nt, const
         const size_t span_p = (size_t)(2 * (Cg / 8) + 2 * (Cu / 8)) * PLANE + (size_t)(Cg / 8) * PLANE + 16 * (size_t)PLANE + 256;
         if (smem_p < span_p) smem_p = span_p;
     }
-    const bool use_pipe = env_flag_off("L3D_NO_PWB_PIPE");
-#define L3D_PWTC(GIV, UIV)                                                                                                     \
+    const bool use_pipe = L3D_ENV_INT("L3D_NO_PWB_PIPE", 0) != 1;
+#define L3D_PWTC_T(TT, GIV, UIV)                                                                                               \
     do {                                                                                                                        \
-        static bool attr_set = false;                                                                                           \
-        if (!attr_set) {                                                                                                        \
-            cudaError_t e = cudaFuncSetAttribute(pw_bwd_tc_kernel<GIV, UIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
-            if (e == cudaSuccess && GIV > 0) e = cudaFuncSetAttribute(pw_bwd_tc_pipe_kernel<(GIV > 0 ? GIV : 1), (UIV > 0 ? UIV : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
+        {                                                                                                                       \
+            cudaError_t e = cudaFuncSetAttribute(pw_bwd_tc_kernel<TT, GIV, UIV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
+            if (e == cudaSuccess && GIV > 0) e = cudaFuncSetAttribute(pw_bwd_tc_pipe_kernel<TT, (GIV > 0 ? GIV : 1), (UIV > 0 ? UIV : 1)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
             if (e != cudaSuccess) { l3d_set_error("pw_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 3; }    \
-            attr_set = true;                                                                                                    \
         }                                                                                                                       \
         static int occ_regs = 0, occ_regs_p = 0;                                                                                \
         if (occ_regs == 0) {                                                                                                    \
             cudaFuncAttributes fa;                                                                                              \
             occ_regs = occ_regs_p = 1;                                                                                          \
-            if (cudaFuncGetAttributes(&fa, pw_bwd_tc_kernel<GIV, UIV>) == cudaSuccess && fa.numRegs > 0)                        \
+            if (cudaFuncGetAttributes(&fa, pw_bwd_tc_kernel<TT, GIV, UIV>) == cudaSuccess && fa.numRegs > 0)                        \
                 occ_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * NT);                                                           \
-            if (cudaFuncGetAttributes(&fa, pw_bwd_tc_pipe_kernel<(GIV > 0 ? GIV : 1), (UIV > 0 ? UIV : 1)>) == cudaSuccess && fa.numRegs > 0) \
+            if (cudaFuncGetAttributes(&fa, pw_bwd_tc_pipe_kernel<TT, (GIV > 0 ? GIV : 1), (UIV > 0 ? UIV : 1)>) == cudaSuccess && fa.numRegs > 0) \
                 occ_regs_p = 65536 / (((fa.numRegs + 7) / 8 * 8) * NT);                                                         \
             if (occ_regs < 1) occ_regs = 1;                                                                                     \
             if (occ_regs_p < 1) occ_regs_p = 1;                                                                                 \
@@ -563,14 +578,15 @@ int l3d_pw_bwd_tc(const l3d_act *gz, const l3d_act *t, const l3d_norm *nt, const
             if (occ_p < 1) occ_p = 1;                                                                                           \
             long long grid_p = (long long)sms * occ_p;                                                                          \
             if (grid_p > tiles) grid_p = tiles;                                                                                 \
-            pw_bwd_tc_pipe_kernel<(GIV > 0 ? GIV : 1), (UIV > 0 ? UIV : 1)><<<(unsigned)grid_p, NT, smem_p, (cudaStream_t)stream>>>(A); \
+            pw_bwd_tc_pipe_kernel<TT, (GIV > 0 ? GIV : 1), (UIV > 0 ? UIV : 1)><<<(unsigned)grid_p, NT, smem_p, (cudaStream_t)stream>>>(A); \
         } else {                                                                                                                \
             const int occ_k = occ_regs < occ ? occ_regs : occ;                                                                  \
             long long grid_k = (long long)sms * occ_k;                                                                          \
             if (grid_k > tiles) grid_k = tiles;                                                                                 \
-            pw_bwd_tc_kernel<GIV, UIV><<<(unsigned)grid_k, NT, smem, (cudaStream_t)stream>>>(A);                                \
+            pw_bwd_tc_kernel<TT, GIV, UIV><<<(unsigned)grid_k, NT, smem, (cudaStream_t)stream>>>(A);                                \
         }                                                                                                                       \
     } while (0)
+#define L3D_PWTC(GIV, UIV) do { if (f32) L3D_PWTC_T(float, GIV, UIV); else L3D_PWTC_T(h16, GIV, UIV); } while (0)
     const int gi = Cg / 16, ui = Cu / 16;            // staging items per thread (TV * C / 8 / NT)
     if (gi == 1 && ui == 1) L3D_PWTC(1, 1);
     else if (gi == 1 && ui == 2) L3D_PWTC(1, 2);
@@ -581,6 +597,7 @@ int l3d_pw_bwd_tc(const l3d_act *gz, const l3d_act *t, const l3d_norm *nt, const
     else if (gi == 4 && ui == 4) L3D_PWTC(4, 4);
     else L3D_PWTC(0, 0);
 #undef L3D_PWTC
+#undef L3D_PWTC_T
     L3D_CUDA_OK("l3d_pw_bwd (tcgen05) launch");
     return 0;
 }
@@ -599,14 +616,16 @@ namespace {
 
 struct CtTcArgs {
     const float *g; int ldg; int OD, OH, OW, oz, oy, ox;
-    const h16 *x; int ldx; int N, d, h, w;
+    const void *x; int ldx; int N, d, h, w;
     int Cin, Cout;
     const float *wgt; float *g_w; float *g_b;
     float *g_x; int ldgx; int accumulate;
     int TP, w_resident, tmem_cols;
 };
 
+template <typename T>
 __global__ void __launch_bounds__(NT) convt_bwd_tc_kernel(CtTcArgs A) {
+    const T *Ax = reinterpret_cast<const T *>(A.x);
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_tmem;
@@ -660,9 +679,12 @@ __global__ void __launch_bounds__(NT) convt_bwd_tc_kernel(CtTcArgs A) {
         // ---- X tile (stored fp16, identity norm -> exact bf16 hi / lo): one copy per tile
         for (int item = tid; item < (Cin >> 3) * TV; item += NT) {
             const int v = item & (TV - 1), q = item >> 7;
-            uint4 o = make_uint4(0u, 0u, 0u, 0u);
-            if (v0 + v < nvox) o = *reinterpret_cast<const uint4 *>(A.x + (size_t)(v0 + v) * A.ldx + q * 8);
-            store_u_split(sXh, sXl, (size_t)q * PLANE + (size_t)v * 16, o, v0 + v < nvox);
+            V8<T> o;
+            const bool ok = v0 + v < nvox;
+            if (ok) o.load(Ax + (size_t)(v0 + v) * A.ldx + q * 8);
+            float xf[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (ok) o.unpack(xf);
+            store_split8(sXh, sXl, (size_t)q * PLANE + (size_t)v * 16, xf, ok);
         }
         for (int tap = tap_begin; tap < tap_end; ++tap) {
             // ---- G_tap tile: gather from the up-sampled grid
@@ -774,13 +796,14 @@ __global__ void __launch_bounds__(NT) convt_bwd_tc_kernel(CtTcArgs A) {
 // Returns -1 when the tensor-core path does not apply.
 int l3d_convt_bwd_tc(const l3d_act *g_out, int OD, int OH, int OW, int oz, int oy, int ox, const l3d_act *x, int N, int d, int h, int w_,
                      const float *w, float *g_w, float *g_b, const l3d_act *g_x, int accumulate_gx, void *stream) {
-    { const char *e = getenv("L3D_NO_TC_BWD"); if (e && e[0] == '1') return -1; }
+    if (L3D_ENV_INT("L3D_NO_TC_BWD", 0) == 1) return -1;
     const int Cin = x->C, Cout = g_out->C;
     const bool has_gx = !act_null(g_x);
-    if (x->dtype != L3D_F16 || g_out->dtype != L3D_F32 || g_w == nullptr) return -1;
+    const bool f32 = x->dtype == L3D_F32;
+    if (g_out->dtype != L3D_F32 || g_w == nullptr) return -1;
     if (Cin % 16 != 0 || Cout % 16 != 0 || Cin > 128 || Cout > 128) return -1;
     auto al = [](const l3d_act *a, int elems, int bytes) { return a->ldc % elems == 0 && reinterpret_cast<uintptr_t>(a->ptr) % bytes == 0; };
-    if (!al(g_out, 4, 16) || !al(x, 8, 16) || (has_gx && !al(g_x, 4, 16))) return -1;
+    if (!al(g_out, 4, 16) || !al(x, f32 ? 4 : 8, 16) || (has_gx && !al(g_x, 4, 16))) return -1;
     const int NX = Cin + 16;
     int TP = 8;
     while (TP > 1 && TP * NX + Cin > 512) TP >>= 1;
@@ -796,15 +819,14 @@ int l3d_convt_bwd_tc(const l3d_act *g_out, int OD, int OH, int OW, int oz, int o
     while (cols < TP * NX + Cin) cols <<= 1;
     CtTcArgs A;
     A.g = (const float *)g_out->ptr; A.ldg = g_out->ldc; A.OD = OD; A.OH = OH; A.OW = OW; A.oz = oz; A.oy = oy; A.ox = ox;
-    A.x = (const h16 *)x->ptr; A.ldx = x->ldc; A.N = N; A.d = d; A.h = h; A.w = w_;
+    A.x = x->ptr; A.ldx = x->ldc; A.N = N; A.d = d; A.h = h; A.w = w_;
     A.Cin = Cin; A.Cout = Cout; A.wgt = w; A.g_w = g_w; A.g_b = g_b;
     A.g_x = has_gx ? (float *)g_x->ptr : nullptr; A.ldgx = has_gx ? g_x->ldc : 0; A.accumulate = accumulate_gx;
     A.TP = TP; A.w_resident = w_resident; A.tmem_cols = cols;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(convt_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    {
+        cudaError_t e = f32 ? cudaFuncSetAttribute(convt_bwd_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)
+                            : cudaFuncSetAttribute(convt_bwd_tc_kernel<h16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) { l3d_set_error("convt_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 3; }
-        attr_set = true;
     }
     int occ = (int)((227 * 1024) / (smem + 2048));
     if (occ > 3) occ = 3;
@@ -819,7 +841,8 @@ int l3d_convt_bwd_tc(const l3d_act *g_out, int OD, int OH, int OW, int oz, int o
     long long gx = ((long long)sms * occ + npass - 1) / npass;
     if (gx > tiles) gx = tiles;
     if (gx < 1) gx = 1;
-    convt_bwd_tc_kernel<<<dim3((unsigned)gx, (unsigned)npass), NT, smem, (cudaStream_t)stream>>>(A);
+    if (f32) convt_bwd_tc_kernel<float><<<dim3((unsigned)gx, (unsigned)npass), NT, smem, (cudaStream_t)stream>>>(A);
+    else convt_bwd_tc_kernel<h16><<<dim3((unsigned)gx, (unsigned)npass), NT, smem, (cudaStream_t)stream>>>(A);
     L3D_CUDA_OK("l3d_convt_bwd (tcgen05) launch");
     return 0;
 }

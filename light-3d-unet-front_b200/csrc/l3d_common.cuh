@@ -34,6 +34,18 @@ void l3d_note_kernel(const char *name);
 int l3d_encode_tiled(void *tmap, int dtype, unsigned rank, void *base, const unsigned long long *dims,
                      const unsigned long long *strides, const unsigned *box, const unsigned *estr);
 
+// Tuning / test knobs from the environment, read ONCE per call site (getenv walks the whole environment block; it used to
+// run on every l3d_dwpw_fwd).  l3d_env_refresh() invalidates the cached values (tests flip knobs between calls).
+int l3d_env_generation();
+int l3d_env_read(const char *name, int dflt);
+#define L3D_ENV_INT(name, dflt)                                                                    \
+    ([]() -> int {                                                                                 \
+        static int v_ = 0, gen_ = -1;                                                              \
+        const int g_ = l3d_env_generation();                                                       \
+        if (gen_ != g_) { v_ = l3d_env_read(name, dflt); gen_ = g_; }                              \
+        return v_;                                                                                 \
+    }())
+
 #define L3D_REQUIRE(cond, ...)                  \
     do {                                        \
         if (!(cond)) {                          \

@@ -612,10 +612,6 @@ static size_t c3_smem_bytes(int TZ, int Cin, int Cout, bool has_sc, int nraw, bo
            sizeof(float) * (2 * (size_t)Cin + 4 * (size_t)Cout);
 }
 
-static int env_int(const char *name, int dflt) {
-    const char *e = getenv(name);
-    return (e && e[0]) ? atoi(e) : dflt;
-}
 
 }  // namespace
 
@@ -641,10 +637,8 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
                     const float *w, int groups, const float *dw_w, const float *pw_w, const float *sc_w,
                     const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats, int stat_ld, int co0, int cout_total,
                     const float *r1_w, void *stream) {
-    static int disabled = -1;
     const bool rank1 = r1_w != nullptr;
-    if (disabled < 0) { const char *e = getenv("L3D_NO_IGEMM"); disabled = (e && e[0] == '1') ? 1 : 0; }
-    if (disabled) return -1;
+    if (L3D_ENV_INT("L3D_NO_IGEMM", 0) == 1) return -1;
     const int Cin = x->C, Cout = t->C;
     const bool has_sc = sc_w != nullptr;
     if (x->dtype != L3D_F16 || t->dtype != L3D_F16) return -1;
@@ -656,7 +650,7 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
     if ((!rank1 && !aligned(x, 8)) || !aligned(t, 8) || (has_sc && (act_null(r) || !aligned(r, 8)))) return -1;
     // ---- tile height: the tallest tile (fewest halo planes and MMAs per voxel) whose accumulators fit TMEM and whose
     // buffers fit shared memory; two accumulator sets (epilogue of tile T under the MMAs of tile T+1) when they fit
-    const int force_tz = env_int("L3D_C3_TZ", 0), force_nraw = env_int("L3D_C3_NRAW", 0), force_sets = env_int("L3D_C3_SETS", 0);   // tuning / test knobs
+    const int force_tz = L3D_ENV_INT("L3D_C3_TZ", 0), force_nraw = L3D_ENV_INT("L3D_C3_NRAW", 0), force_sets = L3D_ENV_INT("L3D_C3_SETS", 0);   // tuning / test knobs
     const int nacc = has_sc ? 2 : 1;
     int TZ = 0, nraw = 0, nsets = 0;
     for (int tz : {8, 6, 4, 2}) {
@@ -692,10 +686,10 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
     // TMA moves one request per innermost box row, and a 16-channel voxel is only 32 B: when the view is a whole
     // 16-channel tensor the (C, W) axes are contiguous and merge into one axis, so a box row is a 320-B x-row
     // (10 voxels) instead of ten 32-B rows (measured: the 5-D box is TMA-issue bound).
-    int tma_split = env_int("L3D_C3_TMASPLIT", 1);   // measured: no effect on the box latency (1, 2, 5 or 10 slices)
+    int tma_split = L3D_ENV_INT("L3D_C3_TMASPLIT", 1);   // measured: no effect on the box latency (1, 2, 5 or 10 slices)
     if (tma_split < 1 || (TZ + 2) % tma_split != 0) tma_split = 1;
     const cuuint32_t box_z = (cuuint32_t)((TZ + 2) / tma_split);
-    const bool merged_cx = !rank1 && Cin == CK && x->ldc == CK && env_int("L3D_C3_NOMERGECX", 0) == 0;
+    const bool merged_cx = !rank1 && Cin == CK && x->ldc == CK && L3D_ENV_INT("L3D_C3_NOMERGECX", 0) == 0;
     CUtensorMap tmap;
     if (rank1) {
         const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
@@ -730,9 +724,9 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
     A.r = has_sc ? (h16 *)r->ptr : nullptr; A.ldr = has_sc ? r->ldc : 0; A.r_stats = r_stats;
     A.stat_ld = stat_ld > 0 ? stat_ld : Cout;
     A.co0 = co0; A.cout_total = cout_total > 0 ? cout_total : Cout;
-    A.tmem_cols = cols; A.nraw = nraw; A.nsets = nsets; A.merged_cx = merged_cx ? 1 : 0; A.dbg = env_int("L3D_C3_DEBUG_SKIP", 0);
+    A.tmem_cols = cols; A.nraw = nraw; A.nsets = nsets; A.merged_cx = merged_cx ? 1 : 0; A.dbg = L3D_ENV_INT("L3D_C3_DEBUG_SKIP", 0);
     A.r1_w = r1_w; A.tma_split = tma_split; A.xp = x->ptr; A.ldx = x->ldc; A.rot = 0;
-    A.merge = (3 * Cout <= 256 && env_int("L3D_C3_NOMERGE", 0) == 0) ? 1 : 0;
+    A.merge = (3 * Cout <= 256 && L3D_ENV_INT("L3D_C3_NOMERGE", 0) == 0) ? 1 : 0;
     int occ = (int)((227 * 1024) / (smem + 2048));
     if (occ > 3) occ = 3;
     if (occ < 1) occ = 1;
@@ -768,17 +762,18 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
         default: L3D_C3_LAUNCH(2, MG, NWV); break;        \
     }
     // 12 worker warps (3 per scheduler) hide the latency of the activation pass and the epilogue when one CTA owns the SM
-    const int nwarps = env_int("L3D_C3_WARPS", occ == 1 ? 12 : 8);
+    const int nwarps_env = L3D_ENV_INT("L3D_C3_WARPS", 0);
+    const int nwarps = nwarps_env > 0 ? nwarps_env : (occ == 1 ? 12 : 8);
     // 1: where only one TMA box fits and a tile has >= 4 channel chunks (measured at 325 windows: 64 -> 32 + shortcut at 24^3
     // 1033 -> 935 us; slower than TMA on the one- and two-chunk 48^3 layers: 1035 -> 1327 us, 1897 -> 2455 us); 2: wherever
     // possible; 0: never
-    const int ld_mode = env_int("L3D_C3_LOADER", 1);
+    const int ld_mode = L3D_ENV_INT("L3D_C3_LOADER", 1);
     const bool use_loader = (ld_mode == 2 || (ld_mode == 1 && nraw == 1 && Cin / CK >= 4)) && (long long)(TZ + 2) * H * W * x->ldc * 2 < (1ll << 31);
     // rotating slots where only one raw box fits (and the box is requested in one piece by TMA).  Off by default: measured
     // SLOWER at 325 windows (16 -> 16 at 48^3: 1101 -> 1187 us, 32 -> 16 + shortcut: 1912 -> 2195 us, 32 -> 32 at 24^3: 406 -> 446 us)
     // -- with the next box streaming in under the MMAs, the TMA writes, the operand reads of the tensor core and the
     // activation pass compete for the same 128 B / clock of shared-memory bandwidth, which is what really bounds the tile
-    if (!rank1 && !(nwarps == 12 && use_loader) && nraw == 1 && tma_split == 1 && env_int("L3D_C3_ROT", 0) != 0 && smem + 128 <= 226 * 1024) {
+    if (!rank1 && !(nwarps == 12 && use_loader) && nraw == 1 && tma_split == 1 && L3D_ENV_INT("L3D_C3_ROT", 0) != 0 && smem + 128 <= 226 * 1024) {
         A.rot = 1;
         smem_launch = smem + 128;
     }

@@ -1193,11 +1193,11 @@ extern "C" int l3d_dwpw_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, 
     // inference, narrow layers: depthwise o pointwise composed into one implicit GEMM (27x the pointwise MACs on the
     // tensor pipe; measured 2.2x faster than the CUDA-core stencil + GEMM kernel at 16/32 channels, on par at 32 -> 32 and
     // slower once the 27 weight tiles (27*Cin*Cout*2 B) crowd the operand buffers out of shared memory: Cin*Cout <= 1024)
-    const char *igemm_max_env = getenv("L3D_DWS_IGEMM_MAX");
-    int igemm_max = (igemm_max_env && igemm_max_env[0]) ? atoi(igemm_max_env) : 1024;
+    const int igemm_max_env = L3D_ENV_INT("L3D_DWS_IGEMM_MAX", 0);
+    int igemm_max = igemm_max_env > 0 ? igemm_max_env : 1024;
     // 64 -> 32 (+ shortcut) at >= 16^3: one launch with a shorter tile (the 27 weight tiles take 110 KB) beats two launches over
     // 16-channel output slices that each re-read and re-activate the input (measured 974 vs 1162 us for 325 windows at 24^3)
-    if (!(igemm_max_env && igemm_max_env[0]) && D >= 16 && H >= 16 && Cin * Cout <= 2048 && Cout <= 32) igemm_max = 2048;
+    if (igemm_max_env <= 0 && D >= 16 && H >= 16 && Cin * Cout <= 2048 && Cout <= 32) igemm_max = 2048;
     if (dw_w != nullptr && !has_u && Cin * Cout <= igemm_max) {
         const int rc = l3d_conv3_tc(x, xn, N, D, H, W, nullptr, 1, dw_w, pw_w, sc_w, t, t_stats, r, r_stats, Cout, 0, Cout, stream);
         if (rc >= 0) return rc;
@@ -1206,8 +1206,7 @@ extern "C" int l3d_dwpw_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, 
     // (the input is re-read per slice).  Measured faster than the stencil kernel at 24^3 (64 -> 32: 1.57 -> 1.24 ms for
     // 325 windows); at 12^3 / 6^3 the 16 x 8-voxel MMA tiles waste too many rows, so small volumes keep the stencil.
     {
-        const char *md = getenv("L3D_DWS_SLICE_MIN_DIM");
-        const int min_dim = (md && md[0]) ? atoi(md) : 16;
+        const int min_dim = L3D_ENV_INT("L3D_DWS_SLICE_MIN_DIM", 16);
         if (dw_w != nullptr && !has_u && Cin * Cout > igemm_max && Cin * 16 <= 2 * igemm_max && Cout % 16 == 0 && D >= min_dim && H >= min_dim &&
             x->dtype == L3D_F16) {
             for (int Cs : {32, 16}) {

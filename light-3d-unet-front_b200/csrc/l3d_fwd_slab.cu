@@ -349,8 +349,7 @@ static bool slab_plan(int Cin, int Cout, bool has_sc, int D, int H, int W, int X
     const int nacc = has_sc ? 2 : 1;
     double best_score = 0.0;
     bool found = false;
-    const char *fe = getenv("L3D_SLAB_SZ");                       // tuning / test knob: force the slab height
-    const int force_sz = (fe && fe[0]) ? atoi(fe) : 0;
+    const int force_sz = L3D_ENV_INT("L3D_SLAB_SZ", 0);           // tuning / test knob: force the slab height
     for (int SZ = (D < 8 ? D : 8); SZ >= 1; --SZ) {
         if (force_sz && SZ != force_sz) continue;
         const int rows = SZ * H * W;
@@ -390,9 +389,7 @@ static bool slab_plan(int Cin, int Cout, bool has_sc, int D, int H, int W, int X
 int l3d_dwpw_fwd_slab(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int W,
                       const float *dw_w, const float *pw_w, const float *sc_w,
                       const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats, void *stream) {
-    static int disabled = -1;
-    if (disabled < 0) { const char *e = getenv("L3D_NO_SLAB"); disabled = (e && e[0] == '1') ? 1 : 0; }
-    if (disabled) return -1;
+    if (L3D_ENV_INT("L3D_NO_SLAB", 0) == 1) return -1;
     const int Cin = x->C, Cout = t->C;
     const bool has_sc = sc_w != nullptr;
     if (x->dtype != L3D_F16 || t->dtype != L3D_F16 || dw_w == nullptr) return -1;
@@ -427,7 +424,7 @@ int l3d_dwpw_fwd_slab(const l3d_act *x, const l3d_norm *xn, int N, int D, int H,
     A.t = (h16 *)t->ptr; A.ldt = t->ldc; A.t_stats = t_stats;
     A.r = has_sc ? (h16 *)r->ptr : nullptr; A.ldr = has_sc ? r->ldc : 0; A.r_stats = r_stats;
     A.SZ = p.SZ; A.MT = p.MT; A.RP = p.RP; A.PP = p.PP; A.tmem_cols = p.cols;
-    { const char *e = getenv("L3D_SLAB_SKIP"); A.dbg = (e && e[0]) ? atoi(e) : 0; }
+    A.dbg = L3D_ENV_INT("L3D_SLAB_SKIP", 0);
     A.raw_bytes = p.raw_bytes; A.raw_stride = p.raw_stride; A.in_bytes = p.in_bytes;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

@@ -1,16 +1,20 @@
-// Tensor-core forward of the depthwise-separable conv (bf16 storage): the hot kernel of the 217K-parameter model.
+// Tensor-core forward of the depthwise-separable conv with the depthwise stage on the CUDA cores: the TRAINING forward
+// (it saves the depthwise output u for the pointwise weight gradient) in fp16 or fp32 storage, and the fp32-storage
+// inference path.
 //
-//   TMA halo tile (raw bf16) -> [InstanceNorm + LeakyReLU + Dropout3d] -> depthwise 3x3x3 (fp32 FMA, CUDA cores)
-//   -> pointwise 1x1x1 (+ the block's 1x1x1 shortcut) as tcgen05.mma (fp16 operands, fp32 accumulate in TMEM)
-//   -> bf16 store + InstanceNorm statistics in the epilogue            (unet3d.py:20-23, 70-72, 80-87)
+//   TMA halo tile (raw) -> [InstanceNorm + LeakyReLU + Dropout3d] -> depthwise 3x3x3 (fp32 FMA, CUDA cores)
+//   -> pointwise 1x1x1 (+ the block's 1x1x1 shortcut) as tcgen05.mma (fp16 operands -- hi + lo pairs in fp32 storage --
+//      fp32 accumulate in TMEM)
+//   -> store + InstanceNorm statistics in the epilogue                  (unet3d.py:20-23, 70-72, 80-87)
 //
 // One persistent CTA (256 threads) walks 4x8x8-voxel tiles = two 128-row MMA tiles, 16 input channels at a time:
 //   * one thread issues a 5-D TMA load of the 6x10x10x16 raw halo box (out-of-volume voxels arrive as zeros) for
 //     the NEXT work item while the CUDA cores work on the current one (mbarrier complete_tx);
 //   * an activation pass turns the raw box into the fp32 stencil tile (norm/act applied once per element, zero
 //     outside the volume: the conv pads the *activated* tensor);
-//   * the stencil writes its output straight into the K-major fp16 operand tile; one thread issues the K=16 MMA
-//     step for that chunk, which runs asynchronously under the next chunk's work;
+//   * the stencil writes its output straight into the K-major fp16 operand tile of the chunk (double-buffered: the MMAs
+//     of chunk i run under the activation pass and the stencil of chunk i + 1, an mbarrier per buffer guards its reuse);
+//     one thread issues the K=16 MMA step(s) for that chunk;
 //   * the epilogue reads the accumulators with tcgen05.ld (thread = voxel row, 16 channels per load).
 #include <cuda.h>
 
@@ -23,34 +27,70 @@ constexpr int TZ = 4, TY = 8, TX = 8, TV = TZ * TY * TX;
 constexpr int HZ = TZ + 2, HY = TY + 2, HX = TX + 2;
 constexpr int HXP = HX + 1, HPLANE = HY * HXP + 1, HVOX = HZ * HPLANE;
 constexpr int CK = 16, NT = 256, MT = 2;
-constexpr int RAW_BYTES = HZ * HY * HX * CK * 2;        // 19200: the TMA box, dense [z][y][x][c] bf16
-constexpr int ACT_ITEMS = HZ * HY * HX * 2;             // 16-byte (8-channel) vectors in the box
+constexpr int ACT_ITEMS = HZ * HY * HX * 2;             // 8-channel vectors in the raw box
 constexpr int ACT_PER_THREAD = (ACT_ITEMS + NT - 1) / NT;
+constexpr int CHUNK_TILE = MT * 128 * CK * 2;           // 8192: one fp16 operand tile of a 16-channel chunk, [m][k/8][128 rows][8]
+
+// Storage traits.  fp16 storage: single fp16 operands (the stored value IS the operand precision).  fp32 storage: every
+// operand -- activations and weights -- is split into fp16 hi + lo (22 significand bits) and each product is three MMAs
+// (hi.hi + lo.hi + hi.lo), so the pointwise GEMM carries ~fp32 accuracy on the tensor cores: this is the mode whose
+// gradients match the reference tensor by tensor (tests/test_gpu_configs.py).
+template <typename T> struct St;
+template <> struct St<h16> { static constexpr int NP = 1, ES = 2; };
+template <> struct St<float> { static constexpr int NP = 2, ES = 4; };
 
 struct TcArgs {
     int Cin; NormDev xn;
     int N, D, H, W;
     const float *dw_w, *pw_w, *sc_w; int Cout;
-    h16 *t; int ldt; double *t_stats;
-    h16 *r; int ldr; double *r_stats;
-    h16 *u; int ldu;
+    void *t; int ldt; double *t_stats;
+    void *r; int ldr; double *r_stats;
+    void *u; int ldu;
     int tmem_cols;
 };
 
+__device__ __forceinline__ void split_f16(float v, __half &hi, __half &lo) {
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
+// 16 accumulator values of one voxel -> global (values as stored are returned in v for the statistics)
+__device__ __forceinline__ void store16(h16 *p, float (&v)[16], bool valid) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        pk[j] = valid ? pack_h16x2(v[2 * j], v[2 * j + 1]) : 0u;
+        v[2 * j] = h16_lo(pk[j]); v[2 * j + 1] = h16_hi(pk[j]);
+    }
+    if (valid) {
+        *reinterpret_cast<uint4 *>(p) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4 *>(p + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    }
+}
+__device__ __forceinline__ void store16(float *p, float (&v)[16], bool valid) {
+    if (valid) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4 *>(p + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+    }
+}
 
+template <typename T>
 __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs A) {
+    constexpr int NP = St<T>::NP, ES = St<T>::ES;
+    constexpr int RAW_BYTES = HZ * HY * HX * CK * ES;      // the TMA box, dense [z][y][x][c]
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t s_bar, s_tma_bar;
+    __shared__ __align__(8) uint64_t s_mma[2], s_tma_bar;
     __shared__ uint32_t s_tmem;
     const int Cin = A.Cin, Cout = A.Cout;
     const bool has_sc = A.sc_w != nullptr;
-    const uint32_t a_bytes = (uint32_t)MT * 128 * Cin * 2, b_bytes = (uint32_t)Cout * Cin * 2;
+    const int nkind = has_sc ? 2 : 1;
+    const uint32_t abuf_bytes = (uint32_t)(nkind * NP) * CHUNK_TILE, b_bytes = (uint32_t)Cout * Cin * 2;
     unsigned char *s_raw = smem_raw;                                           // RAW_BYTES (128-B aligned for TMA)
-    unsigned char *sA = s_raw + RAW_BYTES;
-    unsigned char *sA2 = sA + a_bytes;
-    unsigned char *sB = sA2 + (has_sc ? a_bytes : 0);
-    unsigned char *sB2 = sB + b_bytes;
-    float *s_in = reinterpret_cast<float *>(sB2 + (has_sc ? b_bytes : 0));   // HVOX*CK
+    unsigned char *sA = s_raw + RAW_BYTES;                                     // 2 chunk buffers x [kind][part] operand tiles
+    unsigned char *sB = sA + 2 * abuf_bytes;                                   // [kind][part] weights, K-major [Cout x Cin]
+    float *s_in = reinterpret_cast<float *>(sB + (size_t)(nkind * NP) * b_bytes);   // HVOX*CK
     float *s_dw = s_in + HVOX * CK;                                           // CK*27 (current chunk)
     float *s_scale = s_dw + CK * 27;                                          // Cin
     float *s_shift = s_scale + Cin;
@@ -58,32 +98,18 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) tc::tmem_alloc(&s_tmem, (uint32_t)A.tmem_cols);
-    if (tid == 32) { tc::mbar_init(&s_bar, 1); tc::mbar_init(&s_tma_bar, 1); }
-    // stage the pointwise (+ shortcut) weights once as fp16 K-major operand tiles
-    {
-        // float4 loads, 4 in flight per thread (the weights are the only cold global reads of this kernel)
-        const int nvec = Cout * Cin / 4;
-        const int nsrc = has_sc ? 2 : 1;
-        for (int s = 0; s < nsrc; ++s) {
-            const float4 *src = reinterpret_cast<const float4 *>(s == 0 ? A.pw_w : A.sc_w);
-            unsigned char *dst = s == 0 ? sB : sB2;
-            for (int i0 = tid; i0 < nvec; i0 += 4 * NT) {
-                float4 v[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) if (i0 + j * NT < nvec) v[j] = src[i0 + j * NT];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int i = i0 + j * NT;
-                    if (i < nvec) {
-                        const int k = (i * 4) % Cin, n = (i * 4) / Cin;
-                        const __half2 h0 = __floats2half2_rn(v[j].x, v[j].y), h1 = __floats2half2_rn(v[j].z, v[j].w);
-                        uint2 o;
-                        o.x = *reinterpret_cast<const uint32_t *>(&h0);
-                        o.y = *reinterpret_cast<const uint32_t *>(&h1);
-                        *reinterpret_cast<uint2 *>(dst + tc::tile_off(n, k, Cout)) = o;
-                    }
-                }
-            }
+    if (tid == 32) { tc::mbar_init(&s_mma[0], 1); tc::mbar_init(&s_mma[1], 1); tc::mbar_init(&s_tma_bar, 1); }
+    // stage the pointwise (+ shortcut) weights once as fp16 (hi [+ lo]) K-major operand tiles
+    for (int kd = 0; kd < nkind; ++kd) {
+        const float *src = kd == 0 ? A.pw_w : A.sc_w;
+        unsigned char *dst = sB + (size_t)(kd * NP) * b_bytes;
+        for (int i = tid; i < Cout * Cin; i += NT) {
+            const int k = i % Cin, n = i / Cin;
+            __half hi, lo;
+            split_f16(src[i], hi, lo);
+            const uint32_t off = tc::tile_off(n, k, Cout);
+            *reinterpret_cast<__half *>(dst + off) = hi;
+            if (NP == 2) *reinterpret_cast<__half *>(dst + b_bytes + off) = lo;
         }
     }
     for (int i = tid; i < 4 * Cout; i += NT) s_stat[i] = 0.f;
@@ -93,7 +119,7 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
     tc::fence_after_sync();
     const uint32_t tmem = s_tmem;
     const uint32_t idesc = tc::idesc_f16_m128(Cout);
-    const uint32_t sA_u = tc::smem_u32(sA), sA2_u = tc::smem_u32(sA2), sB_u = tc::smem_u32(sB), sB2_u = tc::smem_u32(sB2);
+    const uint32_t sA_u = tc::smem_u32(sA), sB_u = tc::smem_u32(sB);
 
     const int tilesX = (A.W + TX - 1) / TX, tilesY = (A.H + TY - 1) / TY, tilesZ = (A.D + TZ - 1) / TZ;
     const long long tiles_per_sample = (long long)tilesX * tilesY * tilesZ;
@@ -106,7 +132,7 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
         y0 = (b % tilesY) * TY; b /= tilesY;
         z0 = b * TZ;
     };
-    // activation-pass role: fixed set of 16-byte vectors of the raw box (same for every work item)
+    // activation-pass role: fixed set of 8-channel vectors of the raw box (same for every work item)
     uint32_t act_item[ACT_PER_THREAD];
 #pragma unroll
     for (int k = 0; k < ACT_PER_THREAD; ++k) {
@@ -128,8 +154,9 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
     const int em = warp >> 2, erow = (warp & 3) * 32 + lane;
     const int ev = em * 128 + erow;
     const int elx = ev & 7, ely = (ev >> 3) & 7, elz = ev >> 6;
-    uint32_t phase = 0, tphase = 0;
+    uint32_t tphase = 0;
     int cur_n = -1;
+    int it = 0;                           // work items (tile, chunk) done by this CTA: operand buffer it & 1, its use number it >> 1
 
     auto flush_stats = [&](int n) {
         if (n < 0) return;
@@ -166,9 +193,10 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
             }
             __syncthreads();
         }
-        for (int ch = 0; ch < nchunks; ++ch) {
-            const int c0 = ch * CK;
-            // ---- activation pass: raw bf16 box -> fp32 stencil tile
+        for (int ch = 0; ch < nchunks; ++ch, ++it) {
+            const int c0 = ch * CK, buf = it & 1;
+            unsigned char *Ab = sA + (size_t)buf * abuf_bytes;
+            // ---- activation pass: raw box -> fp32 stencil tile
             // depthwise taps of this chunk were prefetched into registers one chunk ago
             s_dw[tid] = dwr0;
             if (tid + NT < CK * 27) s_dw[tid + NT] = dwr1;
@@ -181,28 +209,33 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
             tphase ^= 1u;
 #pragma unroll
             for (int k = 0; k < ACT_PER_THREAD; ++k) {
-                const uint32_t it = act_item[k];
-                if (it != 0xffffffffu) {
-                    const int hx = (it >> 16) & 15, hy = (it >> 20) & 15, hz = (it >> 24) & 15, q = (it >> 28) & 1;
+                const uint32_t ai = act_item[k];
+                if (ai != 0xffffffffu) {
+                    const int hx = (ai >> 16) & 15, hy = (ai >> 20) & 15, hz = (ai >> 24) & 15, q = (ai >> 28) & 1;
                     const int gz = z0 + hz - 1, gy = y0 + hy - 1, gx = x0 + hx - 1;
                     float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
                     if (gz >= 0 && gz < A.D && gy >= 0 && gy < A.H && gx >= 0 && gx < A.W) {
-                        const uint4 rw = *reinterpret_cast<const uint4 *>(s_raw + (size_t)(tid + k * NT) * 16);
+                        float f[8];
+                        if (NP == 1) {
+                            const uint4 rw = *reinterpret_cast<const uint4 *>(s_raw + (size_t)(tid + k * NT) * 16);
+                            f[0] = h16_lo(rw.x); f[1] = h16_hi(rw.x); f[2] = h16_lo(rw.y); f[3] = h16_hi(rw.y);
+                            f[4] = h16_lo(rw.z); f[5] = h16_hi(rw.z); f[6] = h16_lo(rw.w); f[7] = h16_hi(rw.w);
+                        } else {
+                            const float4 a = *reinterpret_cast<const float4 *>(s_raw + (size_t)(tid + k * NT) * 32);
+                            const float4 b = *reinterpret_cast<const float4 *>(s_raw + (size_t)(tid + k * NT) * 32 + 16);
+                            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+                        }
                         const float4 sc0 = *reinterpret_cast<const float4 *>(s_scale + c0 + q * 8);
                         const float4 sc1 = *reinterpret_cast<const float4 *>(s_scale + c0 + q * 8 + 4);
                         const float4 sh0 = *reinterpret_cast<const float4 *>(s_shift + c0 + q * 8);
                         const float4 sh1 = *reinterpret_cast<const float4 *>(s_shift + c0 + q * 8 + 4);
                         const float sl = A.xn.slope;
-                        o0.x = lrelu(fmaf(h16_lo(rw.x), sc0.x, sh0.x), sl);
-                        o0.y = lrelu(fmaf(h16_hi(rw.x), sc0.y, sh0.y), sl);
-                        o0.z = lrelu(fmaf(h16_lo(rw.y), sc0.z, sh0.z), sl);
-                        o0.w = lrelu(fmaf(h16_hi(rw.y), sc0.w, sh0.w), sl);
-                        o1.x = lrelu(fmaf(h16_lo(rw.z), sc1.x, sh1.x), sl);
-                        o1.y = lrelu(fmaf(h16_hi(rw.z), sc1.y, sh1.y), sl);
-                        o1.z = lrelu(fmaf(h16_lo(rw.w), sc1.z, sh1.z), sl);
-                        o1.w = lrelu(fmaf(h16_hi(rw.w), sc1.w, sh1.w), sl);
+                        o0.x = lrelu(fmaf(f[0], sc0.x, sh0.x), sl); o0.y = lrelu(fmaf(f[1], sc0.y, sh0.y), sl);
+                        o0.z = lrelu(fmaf(f[2], sc0.z, sh0.z), sl); o0.w = lrelu(fmaf(f[3], sc0.w, sh0.w), sl);
+                        o1.x = lrelu(fmaf(f[4], sc1.x, sh1.x), sl); o1.y = lrelu(fmaf(f[5], sc1.y, sh1.y), sl);
+                        o1.z = lrelu(fmaf(f[6], sc1.z, sh1.z), sl); o1.w = lrelu(fmaf(f[7], sc1.w, sh1.w), sl);
                     }
-                    float *dst = s_in + (it & 0xffffu);
+                    float *dst = s_in + (ai & 0xffffu);
                     *reinterpret_cast<float4 *>(dst) = o0;
                     *reinterpret_cast<float4 *>(dst + 4) = o1;
                 }
@@ -223,6 +256,8 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
                     tc::tma_load_5d(s_raw, &tmap, &s_tma_bar, nc, nx - 1, ny - 1, nz - 1, nn);
                 }
             }
+            // the MMAs that read operand buffer `buf` two work items ago must have completed before it is rewritten
+            if (it >= 2) tc::mbar_wait(&s_mma[buf], (uint32_t)(((it >> 1) - 1) & 1));
             // ---- depthwise stencil: 2 rows x 8 voxels of channel c0+c
             {
                 float wreg[27];
@@ -260,21 +295,33 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
                         }
                     }
                 }
-                // operand tiles: row = voxel within the 128-row MMA tile, column = channel
+                // operand tiles of this chunk: [m][k/8][128 rows][8]; row = voxel within the 128-row MMA tile
                 const int m = lz >> 1;
                 const int r0 = ((lz & 1) * TY + ly0) * TX;          // row of (lz, ly0, lx = 0), a multiple of 8
-                const uint32_t base = (uint32_t)m * 128 * Cin * 2 + (uint32_t)((c0 + c) >> 3) * 2048 + (uint32_t)((c0 + c) & 7) * 2;
-                const uint32_t o0 = base + (uint32_t)(r0 >> 3) * 128, o1 = o0 + 128;
+                const uint32_t o0 = (uint32_t)m * 4096 + (uint32_t)(c >> 3) * 2048 + (uint32_t)(r0 >> 3) * 128 + (uint32_t)(c & 7) * 2, o1 = o0 + 128;
 #pragma unroll
                 for (int i = 0; i < TX; ++i) {
-                    *reinterpret_cast<__half *>(sA + o0 + i * 16) = __float2half_rn(acc0[i]);
-                    *reinterpret_cast<__half *>(sA + o1 + i * 16) = __float2half_rn(acc1[i]);
+                    __half h0, l0, h1, l1;
+                    split_f16(acc0[i], h0, l0); split_f16(acc1[i], h1, l1);
+                    *reinterpret_cast<__half *>(Ab + o0 + i * 16) = h0;
+                    *reinterpret_cast<__half *>(Ab + o1 + i * 16) = h1;
+                    if (NP == 2) {
+                        *reinterpret_cast<__half *>(Ab + CHUNK_TILE + o0 + i * 16) = l0;
+                        *reinterpret_cast<__half *>(Ab + CHUNK_TILE + o1 + i * 16) = l1;
+                    }
                 }
                 if (has_sc) {
+                    unsigned char *As = Ab + NP * CHUNK_TILE;
 #pragma unroll
                     for (int i = 0; i < TX; ++i) {
-                        *reinterpret_cast<__half *>(sA2 + o0 + i * 16) = __float2half_rn(ctr0[i]);
-                        *reinterpret_cast<__half *>(sA2 + o1 + i * 16) = __float2half_rn(ctr1[i]);
+                        __half h0, l0, h1, l1;
+                        split_f16(ctr0[i], h0, l0); split_f16(ctr1[i], h1, l1);
+                        *reinterpret_cast<__half *>(As + o0 + i * 16) = h0;
+                        *reinterpret_cast<__half *>(As + o1 + i * 16) = h1;
+                        if (NP == 2) {
+                            *reinterpret_cast<__half *>(As + CHUNK_TILE + o0 + i * 16) = l0;
+                            *reinterpret_cast<__half *>(As + CHUNK_TILE + o1 + i * 16) = l1;
+                        }
                     }
                 }
             }
@@ -282,65 +329,70 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
             __syncthreads();             // operand chunk complete; s_in / s_dw free for the next chunk
             if (tid == 0) {
                 tc::fence_after_sync();
-                const uint32_t acc = ch > 0 ? 1u : 0u;
+                const uint32_t a_u = sA_u + (uint32_t)buf * abuf_bytes;
 #pragma unroll
-                for (int m = 0; m < MT; ++m) {
-                    const uint64_t ad = tc::smem_desc(sA_u + m * 128 * Cin * 2 + 2 * ch * 2048, 2048, 128);
-                    const uint64_t bd = tc::smem_desc(sB_u + 2 * ch * Cout * 16, Cout * 16, 128);
-                    tc::mma_f16(tmem + m * Cout, ad, bd, idesc, acc);
-                    if (has_sc) {
-                        const uint64_t ad2 = tc::smem_desc(sA2_u + m * 128 * Cin * 2 + 2 * ch * 2048, 2048, 128);
-                        const uint64_t bd2 = tc::smem_desc(sB2_u + 2 * ch * Cout * 16, Cout * 16, 128);
-                        tc::mma_f16(tmem + (MT + m) * Cout, ad2, bd2, idesc, acc);
+                for (int kd = 0; kd < 2; ++kd) {
+                    if (kd < nkind) {
+#pragma unroll
+                        for (int m = 0; m < MT; ++m) {
+                            const uint32_t d = tmem + (uint32_t)((kd * MT + m) * Cout);
+                            const uint64_t ah = tc::smem_desc(a_u + (uint32_t)(kd * NP) * CHUNK_TILE + m * 4096, 2048, 128);
+                            const uint64_t bh = tc::smem_desc(sB_u + (uint32_t)(kd * NP) * b_bytes + 2 * ch * Cout * 16, Cout * 16, 128);
+                            tc::mma_f16(d, ah, bh, idesc, ch > 0 ? 1u : 0u);
+                            if (NP == 2) {
+                                const uint64_t al = tc::smem_desc(a_u + (uint32_t)(kd * NP + 1) * CHUNK_TILE + m * 4096, 2048, 128);
+                                const uint64_t bl = tc::smem_desc(sB_u + (uint32_t)(kd * NP + 1) * b_bytes + 2 * ch * Cout * 16, Cout * 16, 128);
+                                tc::mma_f16(d, al, bh, idesc, 1u);
+                                tc::mma_f16(d, ah, bl, idesc, 1u);
+                            }
+                        }
                     }
                 }
-                if (ch + 1 == nchunks) tc::mma_commit(&s_bar);
+                tc::mma_commit(&s_mma[buf]);
             }
-        }
-        // ---- optional save of the depthwise output (bf16) for the backward pass, straight from the operand tile
-        if (A.u != nullptr) {
-            const int kq = Cin >> 3;
-            for (int item = tid; item < TV * kq; item += NT) {
-                const int q = item % kq, v = item / kq;
-                const int lx = v & 7, ly = (v >> 3) & 7, lzz = v >> 6;
-                const int gz = z0 + lzz, gy = y0 + ly, gx = x0 + lx;
-                if (gz < A.D && gy < A.H && gx < A.W) {
-                    const uint4 h = *reinterpret_cast<const uint4 *>(sA + (uint32_t)(v >> 7) * 128 * Cin * 2 + (uint32_t)q * 2048 +
-                                                                      (uint32_t)((v & 127) >> 3) * 128 + (uint32_t)(v & 7) * 16);
-                    *reinterpret_cast<uint4 *>(A.u + ((((size_t)n * A.D + gz) * A.H + gy) * A.W + gx) * (size_t)A.ldu + q * 8) = h;   // the fp16 operand is the stored value
+            // ---- optional save of the depthwise output for the backward pass, straight from the operand tile of this chunk
+            if (A.u != nullptr) {
+#pragma unroll
+                for (int k = 0; k < MT * 128 * 2 / NT; ++k) {
+                    const int item = tid + k * NT, q = item & 1, v = item >> 1;
+                    const int lx = v & 7, ly = (v >> 3) & 7, lzz = v >> 6;
+                    const int gz = z0 + lzz, gy = y0 + ly, gx = x0 + lx;
+                    if (gz < A.D && gy < A.H && gx < A.W) {
+                        const uint32_t off = (uint32_t)(v >> 7) * 4096 + (uint32_t)q * 2048 + (uint32_t)((v & 127) >> 3) * 128 + (uint32_t)(v & 7) * 16;
+                        const uint4 h = *reinterpret_cast<const uint4 *>(Ab + off);
+                        T *up = reinterpret_cast<T *>(A.u) + ((((size_t)n * A.D + gz) * A.H + gy) * A.W + gx) * (size_t)A.ldu + c0 + q * 8;
+                        if (NP == 1) {
+                            *reinterpret_cast<uint4 *>(up) = h;               // the fp16 operand is the stored value
+                        } else {
+                            const uint4 l = *reinterpret_cast<const uint4 *>(Ab + CHUNK_TILE + off);
+                            float4 a, b;
+                            a.x = h16_lo(h.x) + h16_lo(l.x); a.y = h16_hi(h.x) + h16_hi(l.x); a.z = h16_lo(h.y) + h16_lo(l.y); a.w = h16_hi(h.y) + h16_hi(l.y);
+                            b.x = h16_lo(h.z) + h16_lo(l.z); b.y = h16_hi(h.z) + h16_hi(l.z); b.z = h16_lo(h.w) + h16_lo(l.w); b.w = h16_hi(h.w) + h16_hi(l.w);
+                            reinterpret_cast<float4 *>(up)[0] = a;             // hi + lo: the value the pointwise GEMM multiplied
+                            reinterpret_cast<float4 *>(up)[1] = b;
+                        }
+                    }
                 }
             }
         }
-        // ---- epilogue: TMEM -> bf16 global + statistics
-        tc::mbar_wait(&s_bar, phase);
-        phase ^= 1u;
+        // ---- epilogue: TMEM -> global + statistics (the commit of the last chunk covers every MMA of the tile)
+        tc::mbar_wait(&s_mma[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) & 1));
         tc::fence_after_sync();
         {
             const int gz = z0 + elz, gy = y0 + ely, gx = x0 + elx;
             const bool valid = gz < A.D && gy < A.H && gx < A.W;
             const size_t vox = (((size_t)n * A.D + gz) * A.H + gy) * A.W + gx;
             const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-            const int nacc = has_sc ? 2 : 1;
-            for (int a = 0; a < nacc; ++a) {
-                h16 *outp = (a == 0 ? A.t + vox * (size_t)A.ldt : A.r + vox * (size_t)A.ldr);
+            for (int a = 0; a < nkind; ++a) {
+                T *outp = a == 0 ? reinterpret_cast<T *>(A.t) + vox * (size_t)A.ldt : reinterpret_cast<T *>(A.r) + vox * (size_t)A.ldr;
                 float *stat = s_stat + a * 2 * Cout;
                 for (int cb = 0; cb < Cout; cb += 16) {
                     float v[16];
                     tc::tmem_ld16(trow + (uint32_t)((a * MT + em) * Cout + cb), v);
+                    store16(outp + cb, v, valid);
                     float sv[32];
-                    uint32_t pk[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        pk[j] = valid ? pack_h16x2(v[2 * j], v[2 * j + 1]) : 0u;
-                        const float r0 = h16_lo(pk[j]);
-                        const float r1 = h16_hi(pk[j]);
-                        sv[2 * j] = r0; sv[2 * j + 1] = r1;
-                        sv[16 + 2 * j] = r0 * r0; sv[16 + 2 * j + 1] = r1 * r1;
-                    }
-                    if (valid) {
-                        *reinterpret_cast<uint4 *>(outp + cb) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        *reinterpret_cast<uint4 *>(outp + cb + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                    }
+                    for (int j = 0; j < 16; ++j) { sv[j] = v[j]; sv[16 + j] = v[j] * v[j]; }
                     warp_transpose_sum<32>(sv, lane);
                     const int idx = warp_transpose_owner<32>(lane);      // 0..15 sums, 16..31 squares
                     atomicAdd(&stat[(idx >= 16 ? Cout + idx - 16 : idx) + cb], sv[0]);
@@ -348,16 +400,17 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
             }
         }
         tc::fence_before_sync();
-        __syncthreads();                 // TMEM drained, operand tiles free, statistics in s_stat
+        __syncthreads();                 // TMEM drained, statistics in s_stat
     }
     flush_stats(cur_n);
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem, (uint32_t)A.tmem_cols);
 }
 
-static size_t tc_smem_bytes(int Cin, int Cout, bool has_sc) {
-    const size_t a = (size_t)MT * 128 * Cin * 2, b = (size_t)Cout * Cin * 2;
-    return RAW_BYTES + (has_sc ? 2 : 1) * (a + b) + sizeof(float) * ((size_t)HVOX * CK + 27 * CK + 2 * (size_t)Cin + 4 * (size_t)Cout);
+static size_t tc_smem_bytes(int Cin, int Cout, bool has_sc, int NP, int ES) {
+    const size_t nk = (has_sc ? 2 : 1) * (size_t)NP;
+    return (size_t)HZ * HY * HX * CK * ES + 2 * nk * CHUNK_TILE + nk * (size_t)Cout * Cin * 2 +
+           sizeof(float) * ((size_t)HVOX * CK + 27 * CK + 2 * (size_t)Cin + 4 * (size_t)Cout);
 }
 
 }  // namespace
@@ -367,23 +420,21 @@ int l3d_dwpw_fwd_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
                     const float *dw_w, const float *pw_w, const float *sc_w,
                     const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats,
                     const l3d_act *u, void *stream) {
-    static int disabled = -1;
-    if (disabled < 0) { const char *e = getenv("L3D_NO_TC"); disabled = (e && e[0] == '1') ? 1 : 0; }
-    if (disabled) return -1;
+    if (L3D_ENV_INT("L3D_NO_TC", 0) == 1) return -1;
     const int Cin = x->C, Cout = t->C;
     const bool has_sc = sc_w != nullptr, has_u = !act_null(u);
-    if (x->dtype != L3D_F16 || dw_w == nullptr) return -1;
+    const bool f32 = x->dtype == L3D_F32;
+    if (dw_w == nullptr || t->dtype != x->dtype || (has_sc && r->dtype != x->dtype) || (has_u && u->dtype != x->dtype)) return -1;
     if (Cin % 16 != 0 || Cout % 16 != 0 || Cout > 256) return -1;
     const int cols_needed = MT * Cout * (has_sc ? 2 : 1);
     if (cols_needed > 512) return -1;
-    const size_t smem = tc_smem_bytes(Cin, Cout, has_sc);
+    const int es = f32 ? 4 : 2;
+    const size_t smem = tc_smem_bytes(Cin, Cout, has_sc, f32 ? 2 : 1, es);
     if (smem > 226 * 1024) return -1;
-    auto aligned = [](const l3d_act *a, int mult) {
-        return (a->ldc % mult == 0) && (reinterpret_cast<uintptr_t>(a->ptr) % (2 * mult) == 0);
-    };
-    // TMA: 16-byte aligned base and strides
-    if (!aligned(x, 8) || !aligned(t, 8) || (has_sc && !aligned(r, 8)) || (has_u && !aligned(u, 8))) return -1;
-    if ((long long)N * D * H * W * x->ldc * 2 >= (1ll << 40)) return -1;
+    const int vec = 16 / es;            // elements per 16 bytes: TMA needs a 16-byte aligned base and strides, the stores 16-byte vectors
+    auto aligned = [vec](const l3d_act *a) { return (a->ldc % vec == 0) && (reinterpret_cast<uintptr_t>(a->ptr) % 16 == 0); };
+    if (!aligned(x) || !aligned(t) || (has_sc && !aligned(r)) || (has_u && !aligned(u))) return -1;
+    if ((long long)N * D * H * W * x->ldc * es >= (1ll << 40)) return -1;
     int cols = 32;
     while (cols < cols_needed) cols <<= 1;
 
@@ -391,26 +442,25 @@ int l3d_dwpw_fwd_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
     CUtensorMap tmap;
     {
         const cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
-        const cuuint64_t es = 2, ld = (cuuint64_t)x->ldc;
+        const cuuint64_t ld = (cuuint64_t)x->ldc;
         const cuuint64_t strides[4] = {ld * es, (cuuint64_t)W * ld * es, (cuuint64_t)H * W * ld * es, (cuuint64_t)D * H * W * ld * es};
         const cuuint32_t box[5] = {CK, HX, HY, HZ, 1};
         const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-        if (l3d_encode_tiled(&tmap, (int)CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, x->ptr, (const unsigned long long *)dims,
-                             (const unsigned long long *)strides, (const unsigned *)box, (const unsigned *)estr)) return 3;
+        if (l3d_encode_tiled(&tmap, (int)(f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16), 5, x->ptr,
+                             (const unsigned long long *)dims, (const unsigned long long *)strides, (const unsigned *)box, (const unsigned *)estr)) return 3;
     }
     TcArgs A;
     A.Cin = Cin; A.xn = norm_dev(xn);
     A.N = N; A.D = D; A.H = H; A.W = W;
     A.dw_w = dw_w; A.pw_w = pw_w; A.sc_w = sc_w; A.Cout = Cout;
-    A.t = (h16 *)t->ptr; A.ldt = t->ldc; A.t_stats = t_stats;
-    A.r = has_sc ? (h16 *)r->ptr : nullptr; A.ldr = has_sc ? r->ldc : 0; A.r_stats = r_stats;
-    A.u = has_u ? (h16 *)u->ptr : nullptr; A.ldu = has_u ? u->ldc : 0;
+    A.t = t->ptr; A.ldt = t->ldc; A.t_stats = t_stats;
+    A.r = has_sc ? r->ptr : nullptr; A.ldr = has_sc ? r->ldc : 0; A.r_stats = r_stats;
+    A.u = has_u ? u->ptr : nullptr; A.ldu = has_u ? u->ldc : 0;
     A.tmem_cols = cols;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(dwpw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    {
+        cudaError_t e = f32 ? cudaFuncSetAttribute(dwpw_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)
+                            : cudaFuncSetAttribute(dwpw_tc_kernel<h16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) { l3d_set_error("dwpw_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 3; }
-        attr_set = true;
     }
     int occ = (int)((227 * 1024) / (smem + 2048));
     if (occ > 2) occ = 2;                        // 256 threads x ~120 registers
@@ -422,7 +472,8 @@ int l3d_dwpw_fwd_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
     const long long tiles = (long long)N * ((D + TZ - 1) / TZ) * ((H + TY - 1) / TY) * ((W + TX - 1) / TX);
     long long grid = (long long)sms * occ;
     if (grid > tiles) grid = tiles;
-    dwpw_tc_kernel<<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(tmap, A);
+    if (f32) dwpw_tc_kernel<float><<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(tmap, A);
+    else dwpw_tc_kernel<h16><<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(tmap, A);
     l3d_count_launch();
     l3d_note_kernel("dwpw_tc_kernel");
     L3D_CUDA_OK("l3d_dwpw_fwd (tcgen05) launch");
@@ -436,43 +487,71 @@ int l3d_dwpw_fwd_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
 namespace {
 
 struct CtArgs {
-    const h16 *x; int ldx; int Cin;
+    const void *x; int ldx; int Cin;
     int N, d, h, w;
     const float *wgt, *bias; int Cout;
-    h16 *out; int ldo; int OD, OH, OW, oz, oy, ox;
+    void *out; int ldo; int OD, OH, OW, oz, oy, ox;
     int tmem_cols;
 };
 
+// eight fp32 values -> fp16 hi / lo vectors
+__device__ __forceinline__ void split8_f16(const float4 &a, const float4 &b, uint4 &hi, uint4 &lo) {
+    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        __half h0, l0, h1, l1;
+        split_f16(f[2 * j], h0, l0); split_f16(f[2 * j + 1], h1, l1);
+        h[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        l[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]); lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+template <typename T>
 __global__ void __launch_bounds__(NT) convt_tc_kernel(CtArgs A) {
+    constexpr int NP = St<T>::NP;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_tmem;
     const int Cin = A.Cin, Cout = A.Cout, NB = 8 * Cout;
-    const uint32_t a_bytes = 128u * Cin * 2;
-    unsigned char *sB = smem_raw;                         // NB * Cin * 2
-    unsigned char *sA = sB + (size_t)NB * Cin * 2;        // 2 buffers of a_bytes
-    float *s_bias = reinterpret_cast<float *>(sA + 2 * a_bytes);
+    const uint32_t a_bytes = 128u * Cin * 2, b_bytes = (uint32_t)NB * Cin * 2;
+    unsigned char *sB = smem_raw;                         // NP parts of NB * Cin * 2
+    unsigned char *sA = sB + (size_t)NP * b_bytes;        // 2 buffers x NP parts of a_bytes
+    float *s_bias = reinterpret_cast<float *>(sA + 2 * NP * a_bytes);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) tc::tmem_alloc(&s_tmem, (uint32_t)A.tmem_cols);
     if (tid == 32) tc::mbar_init(&s_bar, 1);
     for (int i = tid; i < Cin * Cout * 8; i += NT) {      // wgt[ci][co][tap]
         const int tap = i & 7, co = (i >> 3) % Cout, ci = (i >> 3) / Cout;
-        *reinterpret_cast<__half *>(sB + tc::tile_off(tap * Cout + co, ci, NB)) = __float2half_rn(A.wgt[i]);
+        __half hi, lo;
+        split_f16(A.wgt[i], hi, lo);
+        const uint32_t off = tc::tile_off(tap * Cout + co, ci, NB);
+        *reinterpret_cast<__half *>(sB + off) = hi;
+        if (NP == 2) *reinterpret_cast<__half *>(sB + b_bytes + off) = lo;
     }
     for (int i = tid; i < Cout; i += NT) s_bias[i] = A.bias[i];
     const long long nvox = (long long)A.N * A.d * A.h * A.w;
     const long long ntiles = (nvox + 127) / 128;
     const int kq = Cin >> 3;
+    const T *xin = reinterpret_cast<const T *>(A.x);
     auto load_a = [&](long long tile, int buf) {
-        unsigned char *dst = sA + (size_t)buf * a_bytes;
+        unsigned char *dst = sA + (size_t)buf * NP * a_bytes;
         const long long v0 = tile * 128;
         for (int item = tid; item < 128 * kq; item += NT) {
             const int q = item % kq, v = item / kq;
-            uint4 o = make_uint4(0u, 0u, 0u, 0u);
+            uint4 o = make_uint4(0u, 0u, 0u, 0u), ol = o;
             if (v0 + v < nvox) {
-                o = *reinterpret_cast<const uint4 *>(A.x + (size_t)(v0 + v) * A.ldx + q * 8);   // stored fp16 = MMA operand
+                const T *src = xin + (size_t)(v0 + v) * A.ldx + q * 8;
+                if (NP == 1) {
+                    o = *reinterpret_cast<const uint4 *>(src);   // stored fp16 = MMA operand
+                } else {
+                    split8_f16(reinterpret_cast<const float4 *>(src)[0], reinterpret_cast<const float4 *>(src)[1], o, ol);
+                }
             }
-            *reinterpret_cast<uint4 *>(dst + (uint32_t)q * 2048 + (uint32_t)(v >> 3) * 128 + (uint32_t)(v & 7) * 16) = o;
+            const uint32_t off = (uint32_t)q * 2048 + (uint32_t)(v >> 3) * 128 + (uint32_t)(v & 7) * 16;
+            *reinterpret_cast<uint4 *>(dst + off) = o;
+            if (NP == 2) *reinterpret_cast<uint4 *>(dst + a_bytes + off) = ol;
         }
     };
     if ((long long)blockIdx.x < ntiles) load_a(blockIdx.x, 0);
@@ -487,14 +566,19 @@ __global__ void __launch_bounds__(NT) convt_tc_kernel(CtArgs A) {
     uint32_t phase = 0;
     int buf = 0;
     const int erow = (warp & 3) * 32 + lane, tap0 = (warp >> 2) * 4;
+    T *outp = reinterpret_cast<T *>(A.out);
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
         if (tid == 0) {
             tc::fence_after_sync();
             for (int j = 0; j < Cin / 16; ++j)
                 for (int hN = 0; hN < n_mma; ++hN) {
-                    const uint64_t ad = tc::smem_desc(sA_u + buf * a_bytes + 2 * j * 2048, 2048, 128);
-                    const uint64_t bd = tc::smem_desc(sB_u + 2 * j * NB * 16 + hN * (256 / 8) * 128, NB * 16, 128);
-                    tc::mma_f16(tmem + hN * 256, ad, bd, idesc, j > 0);
+                    const uint32_t a0 = sA_u + (uint32_t)buf * NP * a_bytes + 2 * j * 2048, b0 = sB_u + 2 * j * NB * 16 + hN * (256 / 8) * 128;
+                    const uint64_t ah = tc::smem_desc(a0, 2048, 128), bh = tc::smem_desc(b0, NB * 16, 128);
+                    tc::mma_f16(tmem + hN * 256, ah, bh, idesc, j > 0);
+                    if (NP == 2) {
+                        tc::mma_f16(tmem + hN * 256, tc::smem_desc(a0 + a_bytes, 2048, 128), bh, idesc, 1u);
+                        tc::mma_f16(tmem + hN * 256, ah, tc::smem_desc(b0 + b_bytes, NB * 16, 128), idesc, 1u);
+                    }
                 }
             tc::mma_commit(&s_bar);
         }
@@ -516,17 +600,13 @@ __global__ void __launch_bounds__(NT) convt_tc_kernel(CtArgs A) {
             for (int tp = tap0; tp < tap0 + 4; ++tp) {
                 const int Z = A.oz + 2 * iz + (tp >> 2), Y = A.oy + 2 * iy + ((tp >> 1) & 1), X = A.ox + 2 * ix + (tp & 1);
                 const bool ok = row_ok && Z >= 0 && Z < A.OD && Y >= 0 && Y < A.OH && X >= 0 && X < A.OW;
-                h16 *op = A.out + ((((size_t)n * A.OD + Z) * A.OH + Y) * A.OW + X) * (size_t)A.ldo;
+                T *op = outp + ((((size_t)n * A.OD + Z) * A.OH + Y) * A.OW + X) * (size_t)A.ldo;
                 for (int cb = 0; cb < Cout; cb += 16) {
                     float v[16];
                     tc::tmem_ld16(trow + (uint32_t)(tp * Cout + cb), v);
-                    if (ok) {
-                        uint32_t pk[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) pk[j] = pack_h16x2(v[2 * j] + s_bias[cb + 2 * j], v[2 * j + 1] + s_bias[cb + 2 * j + 1]);
-                        *reinterpret_cast<uint4 *>(op + cb) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                        *reinterpret_cast<uint4 *>(op + cb + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                    }
+                    for (int j = 0; j < 16; ++j) v[j] += s_bias[cb + j];
+                    store16(op + cb, v, ok);
                 }
             }
         }
@@ -542,31 +622,29 @@ __global__ void __launch_bounds__(NT) convt_tc_kernel(CtArgs A) {
 
 int l3d_convt_fwd_tc(const l3d_act *x, int N, int d, int h, int w_, const float *w, const float *b,
                      const l3d_act *out, int OD, int OH, int OW, int oz, int oy, int ox, void *stream) {
-    static int disabled = -1;
-    if (disabled < 0) { const char *e = getenv("L3D_NO_TC"); disabled = (e && e[0] == '1') ? 1 : 0; }
-    if (disabled) return -1;
+    if (L3D_ENV_INT("L3D_NO_TC", 0) == 1) return -1;
     const int Cin = x->C, Cout = out->C;
-    if (x->dtype != L3D_F16 || Cin % 16 != 0 || Cout % 16 != 0 || 8 * Cout > 512) return -1;
+    const bool f32 = x->dtype == L3D_F32;
+    const int np = f32 ? 2 : 1, es = f32 ? 4 : 2;
+    if (out->dtype != x->dtype || Cin % 16 != 0 || Cout % 16 != 0 || 8 * Cout > 512) return -1;
     if (8 * Cout > 256 && (8 * Cout) % 256 != 0) return -1;
-    auto aligned = [](const l3d_act *a, int mult) {
-        return (a->ldc % mult == 0) && (reinterpret_cast<uintptr_t>(a->ptr) % (2 * mult) == 0);
-    };
-    if (!aligned(x, 8) || !aligned(out, 8)) return -1;
-    const size_t smem = (size_t)8 * Cout * Cin * 2 + 2 * (size_t)128 * Cin * 2 + sizeof(float) * Cout;
-    if (smem > 226 * 1024) return -1;
+    const int vec = 16 / es;
+    auto aligned = [vec](const l3d_act *a) { return (a->ldc % vec == 0) && (reinterpret_cast<uintptr_t>(a->ptr) % 16 == 0); };
+    if (!aligned(x) || !aligned(out)) return -1;
+    const size_t smem = (size_t)np * 8 * Cout * Cin * 2 + 2 * (size_t)np * 128 * Cin * 2 + sizeof(float) * Cout;
+    if (smem > 226 * 1024) return -1;           // fp32 storage, 128 -> 64 (1728 voxels per 48^3 patch): generic kernel
     int cols = 32;
     while (cols < 8 * Cout) cols <<= 1;
     CtArgs A;
-    A.x = (const h16 *)x->ptr; A.ldx = x->ldc; A.Cin = Cin;
+    A.x = x->ptr; A.ldx = x->ldc; A.Cin = Cin;
     A.N = N; A.d = d; A.h = h; A.w = w_;
     A.wgt = w; A.bias = b; A.Cout = Cout;
-    A.out = (h16 *)out->ptr; A.ldo = out->ldc; A.OD = OD; A.OH = OH; A.OW = OW; A.oz = oz; A.oy = oy; A.ox = ox;
+    A.out = out->ptr; A.ldo = out->ldc; A.OD = OD; A.OH = OH; A.OW = OW; A.oz = oz; A.oy = oy; A.ox = ox;
     A.tmem_cols = cols;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(convt_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    {
+        cudaError_t e = f32 ? cudaFuncSetAttribute(convt_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)
+                            : cudaFuncSetAttribute(convt_tc_kernel<h16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
         if (e != cudaSuccess) { l3d_set_error("convt_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 3; }
-        attr_set = true;
     }
     int occ = (int)((227 * 1024) / (smem + 2048));
     if (occ > 4) occ = 4;                        // 56 registers; the TMEM columns (8 * Cout per CTA) bound it below
@@ -578,7 +656,8 @@ int l3d_convt_fwd_tc(const l3d_act *x, int N, int d, int h, int w_, const float 
     const long long tiles = ((long long)N * d * h * w_ + 127) / 128;
     long long grid = (long long)sms * occ;
     if (grid > tiles) grid = tiles;
-    convt_tc_kernel<<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(A);
+    if (f32) convt_tc_kernel<float><<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(A);
+    else convt_tc_kernel<h16><<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(A);
     l3d_count_launch();
     l3d_note_kernel("convt_tc_kernel");
     L3D_CUDA_OK("l3d_convt_fwd (tcgen05) launch");

@@ -14,6 +14,14 @@ void l3d_set_error(const char *fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+static int g_env_gen = 0;
+int l3d_env_generation() { return __atomic_load_n(&g_env_gen, __ATOMIC_RELAXED); }
+int l3d_env_read(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return (e && e[0]) ? atoi(e) : dflt;
+}
+extern "C" void l3d_env_refresh(void) { __atomic_fetch_add(&g_env_gen, 1, __ATOMIC_RELAXED); }
+
 void l3d_count_launch(int n) { __atomic_fetch_add(&g_launches, (int64_t)n, __ATOMIC_RELAXED); }
 static thread_local const char *g_last_kernel = "";
 void l3d_note_kernel(const char *name) { g_last_kernel = name; }

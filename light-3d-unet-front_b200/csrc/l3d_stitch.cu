@@ -543,3 +543,48 @@ extern "C" int l3d_bbox_reduce(const int32_t *labels, const float *prob, int D, 
     L3D_CUDA_OK("l3d_bbox_reduce launch");
     return 0;
 }
+
+// ------------------------------------------------------- lesion matching statistics ---------
+// Everything match_components (metrics.py:127-229) and calculate_metrics (:311-404) need from the volumes, in one
+// pass over two label maps: the pair-intersection histogram (np.bincount of pred_id * (nb + 1) + target_id, :153-160),
+// the component sizes (:162-163) and the first moments of the voxel coordinates per component (ndimage.center_of_mass
+// with unit weights, :111-124).  All sums are integers, so the host-side arithmetic on them (IoU in float32, centres and
+// distances in float64, the greedy matching) reproduces the reference bit for bit.  Background-background voxels -- the
+// bulk of a PET volume -- touch no counter.
+namespace {
+__global__ void __launch_bounds__(256) label_pair_stats_kernel(const int32_t *__restrict__ la, const int32_t *__restrict__ lb,
+                                                               int D, int H, int W, int na, int nb, int32_t *__restrict__ counts,
+                                                               unsigned long long *__restrict__ mom_a, unsigned long long *__restrict__ mom_b) {
+    const int64_t total = (int64_t)D * H * W;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int a = la[i], b = lb != nullptr ? lb[i] : 0;
+        if (a == 0 && b == 0) continue;
+        const int x = (int)(i % W);
+        const int64_t rem = i / W;
+        const int y = (int)(rem % H), z = (int)(rem / H);
+        if (a > 0 && a <= na) {
+            atomicAdd(&mom_a[(size_t)a * 4 + 0], 1ull); atomicAdd(&mom_a[(size_t)a * 4 + 1], (unsigned long long)z);
+            atomicAdd(&mom_a[(size_t)a * 4 + 2], (unsigned long long)y); atomicAdd(&mom_a[(size_t)a * 4 + 3], (unsigned long long)x);
+        }
+        if (b > 0 && b <= nb && mom_b != nullptr) {
+            atomicAdd(&mom_b[(size_t)b * 4 + 0], 1ull); atomicAdd(&mom_b[(size_t)b * 4 + 1], (unsigned long long)z);
+            atomicAdd(&mom_b[(size_t)b * 4 + 2], (unsigned long long)y); atomicAdd(&mom_b[(size_t)b * 4 + 3], (unsigned long long)x);
+        }
+        if (counts != nullptr && a > 0 && a <= na && b > 0 && b <= nb) atomicAdd(&counts[(size_t)a * (nb + 1) + b], 1);
+    }
+}
+}  // namespace
+
+extern "C" int l3d_label_pair_stats(const int32_t *labels_a, const int32_t *labels_b, int D, int H, int W, int na, int nb,
+                                    int32_t *counts, int64_t *mom_a, int64_t *mom_b, void *stream) {
+    L3D_REQUIRE(labels_a && mom_a && na >= 0 && nb >= 0, "l3d_label_pair_stats: bad argument");
+    L3D_REQUIRE(labels_b != nullptr || (counts == nullptr && mom_b == nullptr), "l3d_label_pair_stats: counts / mom_b need labels_b");
+    const int64_t n = (int64_t)D * H * W;
+    L3D_REQUIRE(n > 0, "l3d_label_pair_stats: empty volume");
+    label_pair_stats_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, (cudaStream_t)stream>>>(labels_a, labels_b, D, H, W, na, nb, counts,
+                                                                                          reinterpret_cast<unsigned long long *>(mom_a),
+                                                                                          reinterpret_cast<unsigned long long *>(mom_b));
+    l3d_count_launch();
+    L3D_CUDA_OK("l3d_label_pair_stats launch");
+    return 0;
+}

@@ -47,9 +47,13 @@ class DataParallelStep:
     """
 
     def __init__(self, model: torch.nn.Module, loss_fn: torch.nn.Module, optimizer: torch.optim.Optimizer,
-                 world_size: int = 1, group: Optional[dist.ProcessGroup] = None):
+                 world_size: int = 1, group: Optional[dist.ProcessGroup] = None, use_graph: bool = False):
+        """use_graph: capture the whole step (forward, loss, backward, gradient all-reduce, optimiser) in one CUDA graph
+        per input shape and replay it -- the ~100 launches of a step then cost one host call.  Needs an optimiser built
+        with capturable=True; the returned loss is a static tensor that the next step overwrites."""
         self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
         self.world_size, self.group = int(world_size), group
+        self.use_graph, self._graph, self._static, self._staged, self._copy_stream = bool(use_graph), None, None, None, None
         self.params = [p for p in model.parameters() if p.requires_grad]
         if self.world_size > 1:
             if not dist.is_initialized():
@@ -94,7 +98,83 @@ class DataParallelStep:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
         unflatten_into_grads(flat, self.params)
 
-    def step(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    # ------------------------------------------------------------------ CUDA-graph step
+    def _capture(self, images: torch.Tensor, labels: torch.Tensor, key) -> None:
+        dev = images.device
+        sx, st = images.float().clone(), labels.clone()
+        params = list(self.model.parameters())
+        p_snap = [p.detach().clone() for p in params]
+        s_snap = {p: {k: v.clone() for k, v in self.optimizer.state.get(p, {}).items() if torch.is_tensor(v)} for p in params}
+        rng = torch.cuda.get_rng_state(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):                              # warm-up: workspaces, optimiser state, NCCL channels
+            for _ in range(2):
+                self._eager_step(sx, st)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        self.optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(graph):
+            loss = self._eager_step(sx, st)
+        # the warm-up steps were real steps: put parameters, optimiser state and the RNG back where the caller left them
+        with torch.no_grad():
+            for p, q in zip(params, p_snap):
+                p.copy_(q)
+            for p in params:
+                for k, v in self.optimizer.state.get(p, {}).items():
+                    if torch.is_tensor(v):
+                        if k in s_snap[p]:
+                            v.copy_(s_snap[p][k])
+                        else:
+                            v.zero_()
+        torch.cuda.set_rng_state(rng, dev)
+        self._graph, self._static = graph, {"key": key, "x": sx, "t": st, "loss": loss}
+
+    def _graph_step(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        key = (tuple(images.shape), tuple(labels.shape), labels.dtype, str(images.device))
+        if self._graph is None or self._static["key"] != key:
+            dev = next(self.model.parameters()).device
+            self._capture(images.to(dev), labels.to(dev), key)
+        self._static["x"].copy_(images, non_blocking=True)
+        self._static["t"].copy_(labels, non_blocking=True)
+        self._graph.replay()
+        return self._static["loss"]
+
+    def prefetch(self, images: torch.Tensor, labels: torch.Tensor) -> None:
+        """Start the host-to-device copy of the NEXT batch (pinned host tensors) on a side stream, under the current step;
+        `step()` without arguments consumes it."""
+        dev = next(self.model.parameters()).device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(self._copy_stream):
+            x = images.to(dev, non_blocking=True)
+            t = labels.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._staged = (x, t, ev)
+
+    def step(self, images: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if images is None:
+            if self._staged is None:
+                raise RuntimeError("DataParallelStep.step(): no batch given and none prefetched")
+            images, labels, ev = self._staged
+            self._staged = None
+            cur = torch.cuda.current_stream(images.device)
+            cur.wait_event(ev)
+            images.record_stream(cur)
+            labels.record_stream(cur)
+        if self.use_graph:
+            try:
+                return self._graph_step(images, labels)
+            except RuntimeError as e:                              # e.g. a kernel path that synchronises (dense / grouped backward)
+                if self._graph is not None:
+                    raise
+                import warnings
+                warnings.warn(f"DataParallelStep: CUDA-graph capture failed ({e}); running eagerly")
+                self.use_graph = False
+        return self._eager_step(images, labels)
+
+    def _eager_step(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         images = images.float()                                    # trainer.py:225
         outputs = self.model(images)                               # trainer.py:227
         loss = self.loss_fn(outputs, labels)                       # trainer.py:228

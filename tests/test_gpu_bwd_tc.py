@@ -13,13 +13,13 @@ DEV = "cuda:0"
 EPS, SLOPE = 1e-5, 0.01
 
 
-def _case(N, dims, Cg, Cu, has_nt, u_norm, seed):
+def _case(N, dims, Cg, Cu, has_nt, u_norm, seed, store=torch.float16):
     g = torch.Generator().manual_seed(seed)
     D, H, W = dims
     vox = D * H * W
     gz = (torch.randn(N, D, H, W, Cg, generator=g) * 1e-3 + 2e-3).float()          # gradient with a common offset
-    t = torch.randn(N, D, H, W, Cg, generator=g).to(torch.float16)
-    u = torch.randn(N, D, H, W, Cu, generator=g).to(torch.float16)
+    t = torch.randn(N, D, H, W, Cg, generator=g).to(store)
+    u = torch.randn(N, D, H, W, Cu, generator=g).to(store)
     w = (torch.randn(Cg, Cu, generator=g) / np.sqrt(Cu)).float()
     gam_t, bet_t = torch.rand(Cg, generator=g) + 0.5, torch.randn(Cg, generator=g) * 0.2
     gam_u, bet_u = torch.rand(Cu, generator=g) + 0.5, torch.randn(Cu, generator=g) * 0.2
@@ -68,6 +68,7 @@ def _run(c, N, dims, has_nt, u_norm, accumulate, env):
     g_w, g_u = gw0.clone(), gu0.clone()
     old = {k: os.environ.get(k) for k in env}
     os.environ.update(env)
+    nv.refresh_env()
     try:
         nv.call("l3d_pw_bwd", nv.act(dev["gz"]), nv.act(dev["t"]) if has_nt else nv.act(None), nt, nv.ptr(dev["red"]) if has_nt else None,
                 nv.act(dev["u"]), un, N, D, H, W, nv.ptr(dev["w"]), nv.ptr(g_w), nv.act(g_u), 1 if accumulate else 0,
@@ -79,6 +80,7 @@ def _run(c, N, dims, has_nt, u_norm, accumulate, env):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+        nv.refresh_env()
     return (g_u - (gu0 if accumulate else 0)).double().cpu(), (g_w - gw0).double().cpu()
 
 
@@ -86,11 +88,14 @@ def _rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-300))
 
 
+@pytest.mark.parametrize("store", [torch.float16, torch.float32], ids=["f16", "f32"])
 @pytest.mark.parametrize("Cg,Cu", [(16, 16), (16, 32), (32, 16), (64, 32), (64, 128), (128, 128), (32, 64)])
 @pytest.mark.parametrize("has_nt,u_norm,accumulate", [(True, False, False), (True, True, True), (False, False, False)])
-def test_pw_bwd_tensor_core(Cg, Cu, has_nt, u_norm, accumulate):
+def test_pw_bwd_tensor_core(Cg, Cu, has_nt, u_norm, accumulate, store):
+    """store: the storage type of the activations t and u (fp16: split exactly into bf16 hi + lo; fp32: 16 significand
+    bits); the gradient gz is fp32 in both modes."""
     N, dims = 2, (10, 9, 13)          # 1170 voxels per sample: ragged last tile
-    c = _case(N, dims, Cg, Cu, has_nt, u_norm, Cg * 131 + Cu)
+    c = _case(N, dims, Cg, Cu, has_nt, u_norm, Cg * 131 + Cu, store)
     gu_tc, gw_tc = _run(c, N, dims, has_nt, u_norm, accumulate, {})
     gu_cc, gw_cc = _run(c, N, dims, has_nt, u_norm, accumulate, {"L3D_NO_TC_BWD": "1"})
     e = dict(gu_tc=_rel(gu_tc, c["ref_gu"]), gw_tc=_rel(gw_tc, c["ref_gw"]), gu_cc=_rel(gu_cc, c["ref_gu"]), gw_cc=_rel(gw_cc, c["ref_gw"]))
@@ -100,16 +105,17 @@ def test_pw_bwd_tensor_core(Cg, Cu, has_nt, u_norm, accumulate):
     assert e["gu_cc"] < 2e-4 and e["gw_cc"] < 2e-4, e
 
 
+@pytest.mark.parametrize("store", [torch.float16, torch.float32], ids=["f16", "f32"])
 @pytest.mark.parametrize("Cin,Cout", [(32, 16), (64, 32), (128, 64), (16, 16)])
 @pytest.mark.parametrize("lo,out_dims,accumulate", [((5, 6, 7), (10, 12, 14), False), ((3, 4, 5), (7, 9, 10), True)])
-def test_convt_bwd_tensor_core(Cin, Cout, lo, out_dims, accumulate):
+def test_convt_bwd_tensor_core(Cin, Cout, lo, out_dims, accumulate, store):
     """ConvTranspose3d(k=2, s=2) backward: input, weight and bias gradients against torch autograd in float64, for the
     tensor-core kernel and the CUDA-core kernel it replaces; g_out is the lower channel half of a concat-buffer gradient
     and the output volume may be larger than 2x the input (centre-pad path, unet3d.py:130-138)."""
     from light_unet import _native as nv
     N = 2
     g = torch.Generator().manual_seed(Cin * 7 + Cout + lo[0])
-    x = torch.randn(N, *lo, Cin, generator=g).to(torch.float16)
+    x = torch.randn(N, *lo, Cin, generator=g).to(store)
     w = (torch.randn(Cin, Cout, 2, 2, 2, generator=g) / np.sqrt(Cin)).float()
     gcat = (torch.randn(N, *out_dims, 2 * Cout, generator=g) * 1e-3).float()
     off = [(out_dims[k] - 2 * lo[k]) // 2 for k in range(3)]
@@ -131,6 +137,7 @@ def test_convt_bwd_tensor_core(Cin, Cout, lo, out_dims, accumulate):
         g_w, g_b, g_x = gw0.clone(), gb0.clone(), gx0.clone()
         old = {k: os.environ.get(k) for k in env}
         os.environ.update(env)
+        nv.refresh_env()
         try:
             nv.call("l3d_convt_bwd", nv.act(gd, 0, Cout), out_dims[0], out_dims[1], out_dims[2], off[0], off[1], off[2], nv.act(xdv), N,
                     lo[0], lo[1], lo[2], nv.ptr(wdv), nv.ptr(g_w), nv.ptr(g_b), nv.act(g_x), 1 if accumulate else 0,
@@ -142,6 +149,7 @@ def test_convt_bwd_tensor_core(Cin, Cout, lo, out_dims, accumulate):
                     os.environ.pop(k, None)
                 else:
                     os.environ[k] = v
+            nv.refresh_env()
         res[name] = (_rel((g_x - (gx0 if accumulate else 0)).double().cpu(), ref_gx), _rel((g_w - gw0).double().cpu(), wd.grad),
                      _rel((g_b - gb0).double().cpu(), bd.grad))
     print(Cin, Cout, lo, out_dims, {k: tuple(f"{e:.1e}" for e in v) for k, v in res.items()})

@@ -71,6 +71,7 @@ def _run(case, env, launches=None):
     a_ncdhw = a.permute(0, 4, 1, 2, 3).contiguous()
     old = {k: os.environ.get(k) for k in env}
     os.environ.update({k: str(v) for k, v in env.items()})
+    nv.refresh_env()
     try:
         before = nv.launch_count()
         if kind == "dense":
@@ -98,6 +99,7 @@ def _run(case, env, launches=None):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+        nv.refresh_env()
     outs = [(t, t_stats, ref_t)] + ([(r, r_stats, ref_r)] if r is not None else [])
     for got, gstats, ref in outs:
         got_f = got.float().cpu()
@@ -201,6 +203,7 @@ def test_rank1_first_block_layers(dims, tz):
     old = os.environ.get("L3D_C3_TZ")
     if tz:
         os.environ["L3D_C3_TZ"] = str(tz)
+    nv.refresh_env()
     try:
         nv.call("l3d_dwpw_fwd_rank1", nv.ptr(u), nv.ptr(pw1d), C, n1, N, D, H, W, nv.ptr(dw2d), nv.ptr(pw2d), nv.act(t2), nv.ptr(s2), st)
         torch.cuda.synchronize()
@@ -209,6 +212,7 @@ def test_rank1_first_block_layers(dims, tz):
             os.environ.pop("L3D_C3_TZ", None)
         else:
             os.environ["L3D_C3_TZ"] = old
+        nv.refresh_env()
     got_f = t2.float().cpu()
     e = _rel(got_f.permute(0, 4, 1, 2, 3), t2_ref)
     assert e < 4e-3, (dims, tz, e)
@@ -266,3 +270,81 @@ def test_dwpw_slab_kernel(case):
         assert e < 4e-3, (case, e)
         want = torch.stack([got_f.double().sum(dim=(1, 2, 3)), (got_f.double() ** 2).sum(dim=(1, 2, 3))]).reshape(-1)
         assert float((gstats.cpu() - want).abs().max() / (want.abs().max() + 1e-30)) < 2e-4, case
+
+
+TC_CASES = [(2, (9, 17, 13), 16, 16, True, True), (1, (8, 8, 16), 32, 64, True, True), (2, (6, 6, 6), 128, 128, False, True),
+            (1, (12, 12, 12), 128, 64, True, False), (1, (13, 10, 9), 64, 32, True, True), (1, (24, 24, 24), 16, 32, True, True)]
+
+
+@pytest.mark.parametrize("store,tol", [(torch.float16, 2e-3), (torch.float32, 2e-6)], ids=["f16", "f32"])
+@pytest.mark.parametrize("case", TC_CASES, ids=lambda c: f"{c[2]}to{c[3]}{'+sc' if c[4] else ''}-{'x'.join(map(str, c[1]))}")
+def test_dwpw_tc_training_forward(case, store, tol):
+    """The training forward (csrc/l3d_fwd_tc.cu: depthwise stencil on the CUDA cores, pointwise (+ shortcut) GEMM on
+    tcgen05, the depthwise output u saved for the weight gradient) in both storage modes.  fp32 storage carries every MMA
+    operand as an fp16 hi + lo pair: outputs within 2e-6 relative L2 of torch fp32, i.e. tensor cores at fp32-class accuracy."""
+    from light_unet import _native as nv
+    N, dims, Cin, Cout, has_sc, use_norm = case
+    D, H, W = dims
+    x, stats, gamma, beta, a, vox = _inputs(N, dims, Cin, 21)
+    x = x.float().to(store)
+    if store == torch.float32:          # statistics / activated reference of the fp32-stored tensor
+        xf = x.double()
+        stats = torch.stack([xf.sum(dim=(1, 2, 3)), (xf * xf).sum(dim=(1, 2, 3))])
+        a = F.leaky_relu(F.instance_norm(x.permute(0, 4, 1, 2, 3), weight=gamma, bias=beta, eps=EPS), SLOPE).permute(0, 2, 3, 4, 1)
+    if not use_norm:
+        a = x.float()
+    g = torch.Generator().manual_seed(29)
+    st = nv.stream_ptr(torch.device(DEV))
+    xd = x.to(DEV)
+    xn = nv.norm()
+    if use_norm:
+        sd, gd, bd = stats.to(DEV).contiguous(), gamma.to(DEV), beta.to(DEV)
+        xn = nv.norm(sd, gd, bd, None, EPS, SLOPE, vox)
+    dw = torch.randn(Cin, 1, 3, 3, 3, generator=g) / np.sqrt(27.0)
+    pw = torch.randn(Cout, Cin, 1, 1, 1, generator=g) / np.sqrt(Cin)
+    sc = torch.randn(Cout, Cin, 1, 1, 1, generator=g) / np.sqrt(Cin)
+    dwd, pwd, scd = dw.to(DEV), pw.to(DEV), sc.to(DEV)
+    t = torch.zeros(N, D, H, W, Cout, dtype=store, device=DEV)
+    r = torch.zeros(N, D, H, W, Cout, dtype=store, device=DEV)
+    u = torch.zeros(N, D, H, W, Cin, dtype=store, device=DEV)
+    t_stats = torch.zeros(2 * N * Cout, dtype=torch.float64, device=DEV)
+    r_stats = torch.zeros(2 * N * Cout, dtype=torch.float64, device=DEV)
+    nv.call("l3d_dwpw_fwd", nv.act(xd), xn, N, D, H, W, nv.ptr(dwd), nv.ptr(pwd), nv.ptr(scd) if has_sc else None, nv.act(t),
+            nv.ptr(t_stats), nv.act(r) if has_sc else nv.act(None), nv.ptr(r_stats) if has_sc else None, nv.act(u), st)
+    torch.cuda.synchronize()
+    assert nv.lib().l3d_last_kernel() == b"dwpw_tc_kernel"
+    a_ncdhw = a.double().permute(0, 4, 1, 2, 3).contiguous()
+    u_ref = F.conv3d(a_ncdhw, dw.double(), padding=1, groups=Cin)
+    outs = [("u", u, None, u_ref), ("t", t, t_stats, F.conv3d(u_ref, pw.double()))]
+    if has_sc:
+        outs.append(("r", r, r_stats, F.conv3d(a_ncdhw, sc.double())))
+    for name, got, gstats, ref in outs:
+        got_f = got.double().cpu()
+        e = _rel(got_f.permute(0, 4, 1, 2, 3), ref)
+        assert e < tol, (case, name, e)
+        if gstats is not None:
+            want = torch.stack([got_f.sum(dim=(1, 2, 3)), (got_f ** 2).sum(dim=(1, 2, 3))]).reshape(-1)
+            assert float((gstats.cpu() - want).abs().max() / (want.abs().max() + 1e-30)) < 2e-4, (case, name)
+
+
+@pytest.mark.parametrize("store,tol", [(torch.float16, 2e-3), (torch.float32, 2e-6)], ids=["f16", "f32"])
+@pytest.mark.parametrize("Cin,Cout,lo,out_dims", [(32, 16, (5, 6, 7), (10, 12, 14)), (64, 32, (3, 4, 5), (7, 9, 10)), (128, 64, (3, 3, 3), (6, 6, 6))])
+def test_convt_tc_forward(Cin, Cout, lo, out_dims, store, tol):
+    """ConvTranspose3d(k=2, s=2) + bias into the lower half of a concat buffer at the centre-pad offset, both storage
+    modes (fp32 storage, 128 -> 64: the operand tiles do not fit and the generic kernel runs -- same result)."""
+    from light_unet import _native as nv
+    N = 2
+    g = torch.Generator().manual_seed(Cin + Cout)
+    x = torch.randn(N, *lo, Cin, generator=g).to(store)
+    w = (torch.randn(Cin, Cout, 2, 2, 2, generator=g) / np.sqrt(Cin)).float()
+    b = torch.randn(Cout, generator=g).float()
+    off = [(out_dims[k] - 2 * lo[k]) // 2 for k in range(3)]
+    cat = torch.zeros(N, *out_dims, 2 * Cout, dtype=store, device=DEV)
+    xd, wd, bd = x.to(DEV), w.to(DEV), b.to(DEV)
+    nv.call("l3d_convt_fwd", nv.act(xd), N, lo[0], lo[1], lo[2], nv.ptr(wd), nv.ptr(bd), nv.act(cat, 0, Cout), out_dims[0], out_dims[1], out_dims[2],
+            off[0], off[1], off[2], nv.stream_ptr(torch.device(DEV)))
+    torch.cuda.synchronize()
+    ref = F.conv_transpose3d(x.double().permute(0, 4, 1, 2, 3), w.double(), b.double(), stride=2).permute(0, 2, 3, 4, 1)
+    got = cat[:, off[0]:off[0] + 2 * lo[0], off[1]:off[1] + 2 * lo[1], off[2]:off[2] + 2 * lo[2], :Cout].double().cpu()
+    assert _rel(got, ref) < tol
+    assert float(cat[..., Cout:].float().abs().max()) == 0.0

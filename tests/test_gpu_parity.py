@@ -280,6 +280,7 @@ def test_rank1_first_block(dims, monkeypatch):
     y1, seen1 = run()
     assert ("l3d_dwpw_fwd_rank1" in seen1) == (dims[2] % 4 == 0)
     monkeypatch.setenv("L3D_NO_RANK1_FIRST", "1")
+    nv.refresh_env()
     y0, seen0 = run()
     assert "l3d_dwpw_fwd_rank1" not in seen0
     print(f"{dims}: rank-1 vs oracle {rel_l2(y1, ref):.3e}, stored vs oracle {rel_l2(y0, ref):.3e}, rank-1 vs stored {rel_l2(y1, y0):.3e}")

@@ -7,7 +7,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "light-3d-unet-f
 from light_unet import _native as nv
 from light_unet.models import Lightweight3DUNet, FocalTverskyLoss
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-dtype = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+dtype = sys.argv[2] if len(sys.argv) > 2 else "f32"
 torch.manual_seed(0)
 m = Lightweight3DUNet(dropout_p=0.1).cuda().set_compute_dtype(dtype).train()
 opt = torch.optim.AdamW(m.parameters(), lr=1e-4, weight_decay=1e-5, fused=True)
