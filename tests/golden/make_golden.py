@@ -36,7 +36,8 @@ from light_unet.core.inferencer import Inferencer as RefInferencer        # noqa
 
 assert "/root/reference" in sys.modules["light_unet"].__file__, "must import the reference package"
 
-from oracle import unet_ref, loss_ref, stitch_ref, bbox_ref, synth       # noqa: E402
+from oracle import unet_ref, loss_ref, stitch_ref, bbox_ref, synth, metrics_ref   # noqa: E402
+from light_unet.models import metrics as ref_metrics                      # noqa: E402
 
 torch.set_num_threads(8)
 
@@ -301,6 +302,54 @@ def bbox_cases():
     print("bbox: ok")
 
 
+def metrics_cases():
+    """Lesion-wise metrics and the validation threshold sweep: the reference's own calculate_lesion_metrics /
+    calculate_metrics / match_components (metrics.py:127-404) and Trainer._is_better_metric (trainer.py:183-189) on seeded
+    synthetic cases; the oracle restatement must reproduce every number exactly."""
+    from light_unet.core.trainer import Trainer as RefTrainer
+    out = {}
+    thresholds = [0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8]
+    sets = {"small": [((24, 28, 32), 3), ((20, 20, 40), 4), ((32, 24, 24), 5)],
+            "spacing": [((24, 28, 32), 13), ((18, 30, 26), 14)],
+            "empty": [((12, 12, 12), 21)]}
+    for tag, cases in sets.items():
+        pairs = [metrics_ref.synth_case(shape, seed) for shape, seed in cases]
+        if tag == "empty":
+            pairs = [(np.zeros_like(p), np.zeros_like(l)) for p, l in pairs] + [(pairs[0][0], np.zeros_like(pairs[0][1]))]
+        preds, labels = [p for p, _ in pairs], [l for _, l in pairs]
+        spacings = [(4.0, 4.0, 4.0)] * len(preds) if tag != "spacing" else [(2.0, 3.0, 5.0), (4.0, 4.0, 2.5)]
+        rec = {"cases": cases, "spacings": spacings, "per_threshold": {}, "lesion": []}
+        for t in thresholds:
+            ref = ref_metrics.calculate_metrics(preds, labels, threshold=t, spacing=spacings)
+            ora = metrics_ref.calculate_metrics(preds, labels, t, spacings)
+            assert ref == ora, (tag, t, ref, ora)
+            rec["per_threshold"][str(t)] = {k: (int(v) if isinstance(v, (int, np.integer)) else float(v)) for k, v in ref.items()}
+        for p, l, sp in zip(preds, labels, spacings):
+            for ms in (0, 8):
+                ref = ref_metrics.calculate_lesion_metrics(p, l, threshold=0.4, min_size_voxels=ms, spacing=sp)
+                ora = metrics_ref.calculate_lesion_metrics(p, l, 0.4, ms, spacing=sp)
+                assert ref == ora, (tag, ms, ref, ora)
+                rec["lesion"].append({k: (int(v) if isinstance(v, (int, np.integer)) else float(v)) for k, v in ref.items()})
+        # the sweep of Trainer.validate (trainer.py:423-445) with the reference's own comparison
+        tr = RefTrainer.__new__(RefTrainer)
+        for tie in (0.0, 0.05):
+            best_t = thresholds[0]
+            best = ref_metrics.calculate_metrics(preds, labels, threshold=best_t, spacing=spacings)
+            br, bd = best["lesion_wise_recall"], best["voxel_wise_dsc_macro"]
+            for t in thresholds[1:]:
+                m = ref_metrics.calculate_metrics(preds, labels, threshold=t, spacing=spacings)
+                better, _ = tr._is_better_metric(m["lesion_wise_recall"], m["voxel_wise_dsc_macro"], br, bd, tie)
+                if better:
+                    br, bd, best_t, best = m["lesion_wise_recall"], m["voxel_wise_dsc_macro"], t, m
+            ora = metrics_ref.select_threshold(preds, labels, spacings, thresholds, tie)
+            assert ora["best_threshold"] == best_t and ora["best_recall"] == br and ora["best_dsc_macro"] == bd, (tag, tie)
+            rec[f"best_tie{tie}"] = {"best_threshold": best_t, "best_recall": float(br), "best_dsc_macro": float(bd)}
+        out[tag] = rec
+    with open(os.path.join(HERE, "metrics.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("metrics: ok")
+
+
 def default_init_case():
     """Seeded default initialisation of the reference module tree: the drop-in creates the same torch.nn layers
     in the same order, so its parameters must be identical under the same seed."""
@@ -332,6 +381,7 @@ def main():
     gaussian_and_grid_cases()
     sliding_window_cases()
     bbox_cases()
+    metrics_cases()
 
 
 if __name__ == "__main__":

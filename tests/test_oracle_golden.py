@@ -159,3 +159,24 @@ def test_bbox_fixture():
         assert n == c["n"] and int(lab.astype(np.int64).sum()) == c["label_sum"]
         w = np.arange(lab.size, dtype=np.int64) % 1009
         assert int((lab.astype(np.int64).ravel() * w).sum()) == c["label_wsum"]
+
+
+def test_metrics_oracle_against_reference_fixture():
+    """oracle/metrics_ref.py (lesion matching, Dice, the validation threshold sweep) against the numbers the reference's
+    own metrics.py / Trainer._is_better_metric produced (tests/golden/metrics.json)."""
+    import json
+    from oracle import metrics_ref
+    with open(os.path.join(GOLDEN, "metrics.json")) as f:
+        fx = json.load(f)
+    thresholds = [0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8]
+    for tag, rec in fx.items():
+        pairs = [metrics_ref.synth_case(tuple(shape), seed) for shape, seed in rec["cases"]]
+        if tag == "empty":
+            pairs = [(np.zeros_like(p), np.zeros_like(l)) for p, l in pairs] + [(pairs[0][0], np.zeros_like(pairs[0][1]))]
+        preds, labels = [p for p, _ in pairs], [l for _, l in pairs]
+        spacings = [tuple(s) for s in rec["spacings"]]
+        for t in thresholds:
+            assert metrics_ref.calculate_metrics(preds, labels, t, spacings) == rec["per_threshold"][str(t)], (tag, t)
+        for tie in (0.0, 0.05):
+            best = metrics_ref.select_threshold(preds, labels, spacings, thresholds, tie)
+            assert {k: best[k] for k in ("best_threshold", "best_recall", "best_dsc_macro")} == rec[f"best_tie{tie}"], (tag, tie)
