@@ -251,6 +251,31 @@ int l3d_bbox_reduce(const int32_t *labels, const float *prob, int D, int H, int 
 int l3d_label_pair_stats(const int32_t *labels_a, const int32_t *labels_b, int D, int H, int W, int na, int nb,
                          int32_t *counts, int64_t *mom_a, int64_t *mom_b, void *stream);
 
+/* ------------------------------------------------------ training patches -- */
+
+/* Training-patch pipeline on the device (replaces PatchDataset.__getitem__'s disk reads + numpy / scipy work,
+ * patch_dataset.py:114-220).  Patches are fp32 [B][pd][ph][pw]; per-sample parameters are small DEVICE tables.
+ * l3d_patch_extract: img_ptrs / lab_ptrs = device arrays of B device pointers to fp32 [D][H][W] volumes resident in HBM,
+ *   dims / start = int32 [B][3]; the window start..start+p is clipped at the far edge and zero-padded at the end (:136-154).
+ * l3d_patch_flip: axis[b] in {0, 1, 2} or -1 (copy)                                                              (:160-165)
+ * l3d_patch_rotate: scipy.ndimage.rotate(reshape=False, mode='constant'), order 1 for the image and 0 for the label;
+ *   axes[b] = {a0 < a1} or {-1, -1} (copy), coef[b] = {m00, m01, m10, m11, off0, off1} with in = off + m . out          (:167-174)
+ * l3d_patch_zoom: scipy.ndimage.zoom (order 1 / 0, mode='constant') + centre-crop / end-pad back to the patch size;
+ *   geo[b] = {on, zoomed dims[3], crop start[3]}, zf[b] = (n - 1) / (zoomed - 1) per axis                             (:176-208)
+ * l3d_patch_intensity: in place, image = clip(image + shift[b], 0, 1) in fp32 if shift_on[b], then
+ *   image = float(clip(double(image) + noise[b][i], 0, 1)) if noise_on[b] (noise may be NULL)                         (:210-218)
+ * Results are bit-identical to the reference's for the same parameters (tests/test_gpu_patches.py). */
+int l3d_patch_extract(const void *const *img_ptrs, const void *const *lab_ptrs, const int32_t *dims, const int32_t *start,
+                      int B, int pd, int ph, int pw, float *out_img, float *out_lab, void *stream);
+int l3d_patch_flip(const float *in_img, const float *in_lab, float *out_img, float *out_lab, const int32_t *axis,
+                   int B, int pd, int ph, int pw, void *stream);
+int l3d_patch_rotate(const float *in_img, const float *in_lab, float *out_img, float *out_lab, const int32_t *axes,
+                     const double *coef, int B, int pd, int ph, int pw, void *stream);
+int l3d_patch_zoom(const float *in_img, const float *in_lab, float *out_img, float *out_lab, const int32_t *geo,
+                   const double *zf, int B, int pd, int ph, int pw, void *stream);
+int l3d_patch_intensity(float *img, const float *shift, const int32_t *shift_on, const double *noise, const int32_t *noise_on,
+                        int B, int64_t per, void *stream);
+
 /* ------------------------------------------------------------- diagnostics -- */
 
 /* The library reads its tuning / test knobs (L3D_* environment variables) once per call site; call this after changing

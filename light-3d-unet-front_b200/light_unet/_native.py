@@ -73,6 +73,11 @@ _SIGS = {
     "l3d_bbox_init": [_P, c_int, _P],
     "l3d_bbox_reduce": [_P, _P, c_int, c_int, c_int, _P, c_int, _P],
     "l3d_label_pair_stats": [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P],
+    "l3d_patch_extract": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, _P],
+    "l3d_patch_flip": [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P],
+    "l3d_patch_rotate": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P],
+    "l3d_patch_zoom": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P],
+    "l3d_patch_intensity": [_P, _P, _P, _P, _P, c_int, c_int64, _P],
     "l3d_tc_selftest": [_P, _P, c_int, c_int, c_int, _P, _P],
     "l3d_conv3_debug_read": [_P, c_int],
     "l3d_tc_selftest_tf32": [_P, _P, c_int, c_int, c_int, c_int, _P, _P],

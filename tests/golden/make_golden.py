@@ -36,7 +36,7 @@ from light_unet.core.inferencer import Inferencer as RefInferencer        # noqa
 
 assert "/root/reference" in sys.modules["light_unet"].__file__, "must import the reference package"
 
-from oracle import unet_ref, loss_ref, stitch_ref, bbox_ref, synth, metrics_ref   # noqa: E402
+from oracle import unet_ref, loss_ref, stitch_ref, bbox_ref, synth, metrics_ref, augment_ref   # noqa: E402
 from light_unet.models import metrics as ref_metrics                      # noqa: E402
 
 torch.set_num_threads(8)
@@ -350,6 +350,64 @@ def metrics_cases():
     print("metrics: ok")
 
 
+def patch_cases():
+    """The reference's own PatchDataset (patch_dataset.py) on in-memory volumes: nibabel.load is replaced by a table lookup
+    and the case files exist as empty files so that find_case_files finds them.  Stores, per configuration, the SHA-256 of
+    the first items' image / label patches (as float32, which is what trainer.py:225 makes of them)."""
+    import hashlib
+    import tempfile
+    import nibabel
+    from light_unet.datasets.patch_dataset import PatchDataset as RefPatchDataset
+    vols = augment_ref.synth_cases()
+    PATCH_AUG = augment_ref.PATCH_AUG
+    store = {}
+
+    class FakeImg:
+        def __init__(self, a):
+            self.a = a
+
+        def get_fdata(self):
+            return self.a.astype(np.float64)
+    nibabel.load = lambda path: FakeImg(store[str(path)])
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        for sub in ("images", "labels", "body_masks"):
+            os.makedirs(os.path.join(d, sub))
+        ids = []
+        for i, (image, label, body) in enumerate(vols):
+            cid = f"{i + 1:04d}"
+            ids.append(cid)
+            for path, arr in ((os.path.join(d, "images", f"{cid}_0000.nii.gz"), image), (os.path.join(d, "labels", f"{cid}.nii.gz"), label)):
+                open(path, "wb").close()
+                store[path] = arr
+            if body is not None:
+                path = os.path.join(d, "body_masks", f"{cid}.nii.gz")
+                open(path, "wb").close()
+                store[path] = body
+        split = os.path.join(d, "split.txt")
+        with open(split, "w") as f:
+            f.write("\n".join(ids) + "\n")
+        for tag, patch, aug, seed, n in [("plain16", (16, 16, 16), None, 42, 12), ("aug16", (16, 16, 16), PATCH_AUG, 7, 40),
+                                         ("aug24", (24, 20, 28), PATCH_AUG, 11, 24), ("edge48", (48, 48, 48), PATCH_AUG, 3, 10)]:
+            import contextlib
+            import io
+            with contextlib.redirect_stdout(io.StringIO()):
+                ds = RefPatchDataset(d, split, patch_size=patch, lesion_patch_ratio=0.5, augmentation=aug, seed=seed,
+                                     body_mask_config={"enabled": True, "apply_to_training_sampling": False})
+            items = []
+            for k in range(n):
+                img, lab = ds[k]
+                assert tuple(img.shape) == (1,) + patch and tuple(lab.shape) == (1,) + patch
+                a, b = img.numpy().astype(np.float32), lab.numpy().astype(np.float32)
+                items.append({"img_sha": hashlib.sha256(a.tobytes()).hexdigest(), "lab_sha": hashlib.sha256(b.tobytes()).hexdigest(),
+                              "img_sum": float(a.astype(np.float64).sum()), "lab_sum": float(b.sum())})
+            out[tag] = {"patch": list(patch), "seed": seed, "aug": aug is not None, "n_lesion": len(ds.lesion_locations),
+                        "n_background": len(ds.background_locations), "items": items}
+    with open(os.path.join(HERE, "patches.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("patches: ok", {k: (v["n_lesion"], v["n_background"]) for k, v in out.items()})
+
+
 def default_init_case():
     """Seeded default initialisation of the reference module tree: the drop-in creates the same torch.nn layers
     in the same order, so its parameters must be identical under the same seed."""
@@ -382,6 +440,7 @@ def main():
     sliding_window_cases()
     bbox_cases()
     metrics_cases()
+    patch_cases()
 
 
 if __name__ == "__main__":

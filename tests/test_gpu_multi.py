@@ -62,8 +62,14 @@ def _dp_worker(rank, world, port, dtype, ret):
             ropt = torch.optim.AdamW(ref.parameters(), lr=1e-4, weight_decay=1e-5)
             rloss = DataParallelStep(ref, FocalTverskyLoss(), ropt, world_size=1).step(xs, ts)
             rgrads = {k: p.grad.detach() for k, p in ref.named_parameters()}
+            # tensors that are analytically zero (a 1-input-channel conv feeding an InstanceNorm) hold only round-off: they
+            # are bounded absolutely at 1e-4 of the largest gradient norm (as in test_gpu_train.py), the others relatively
             gmax = max(float(v.norm()) for v in rgrads.values())
-            errs = {k: float((grads[k] - rgrads[k]).norm() / (rgrads[k].norm() + 1e-3 * gmax)) for k in grads}
+            floor = 1e-3 * gmax
+            errs = {}
+            for k in grads:
+                d, n = float((grads[k] - rgrads[k]).norm()), float(rgrads[k].norm())
+                errs[k] = d / n if n > floor else (d / (1e-4 * gmax)) * 5e-3      # scaled so that one tolerance covers both tiers
             worst = max(errs, key=errs.get)
             perr = max(float((p - q).abs().max()) for p, q in zip(model.parameters(), ref.parameters()))
             ret.update(loss=float(loss), rloss=float(rloss), worst=worst, werr=errs[worst], perr=perr)
