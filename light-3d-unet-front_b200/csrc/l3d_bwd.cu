@@ -1377,12 +1377,94 @@ extern "C" int l3d_norm_param_grad_batch(int count, const double *const *red, co
     return 0;
 }
 
+// ===========================================================================================
+// Dense / grouped 3x3x3 backward on the tensor cores, tap by tap (unet3d.py:30,49,60):
+//   forward   out[v][co] = sum_t sum_ci a[v + s_t][ci] * w[co][ci][t]
+//   wgrad     g_w[co][ci][t] = sum_v g_t[v][co] * a[v + s_t][ci]        27 voxel-reduction GEMMs  [Cout x Cin]
+//   dgrad     g_a[v + s_t][ci] += sum_co g_t[v][co] * w[co][ci][t]      27 pointwise GEMMs, accumulated at shifted addresses
+// On zero-padded copies of g_t and a (one voxel of halo on every side, flat [N * (D+2)(H+2)(W+2)] voxel rows) a tap shift
+// s_t is a constant pointer offset, so every tap is exactly the pointwise backward problem: both GEMMs of a tap run in
+// ONE launch of pw_bwd_tc_kernel (l3d_bwd_tc.cu: bf16 hi + lo operand pairs on tcgen05, fp32 accumulation in TMEM) from
+// the same staged tiles.  Halo rows of g_t are zero, so they add nothing to either product.
+template <typename T>
+__global__ void __launch_bounds__(NT) c3_pad_kernel(const float *__restrict__ gz, int ldg, const T *__restrict__ t, int ldt, NormDev nt,
+                                                    const double *__restrict__ red, const T *__restrict__ x, int ldx, NormDev xn,
+                                                    int N, int Cout, int Cin, int D, int H, int W,
+                                                    float *__restrict__ gpad, float *__restrict__ apad) {
+    // interior voxels only (the buffers were zeroed): g_t = a*gz + b*t + d and the activated conv input
+    const size_t vox = (size_t)D * H * W;
+    const int C = Cout + Cin;
+    const size_t total = (size_t)N * vox * C;
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < total; i += (size_t)gridDim.x * NT) {
+        const int c = (int)(i % C);
+        const size_t v = i / C;
+        const int n = (int)(v / vox);
+        size_t r = v - (size_t)n * vox;
+        const int xw = (int)(r % W); r /= W;
+        const int yh = (int)(r % H);
+        const int zd = (int)(r / H);
+        const size_t pv = (((size_t)n * (D + 2) + zd + 1) * (H + 2) + yh + 1) * (W + 2) + xw + 1;
+        if (c < Cout) {
+            float a, b, d;
+            in_bwd_coef(nt, red, N, Cout, n, c, a, b, d);
+            const float tv = nt.stats != nullptr ? ld1(t + v * ldt + c) : 0.f;
+            gpad[pv * Cout + c] = a * gz[v * ldg + c] + b * tv + d;
+        } else {
+            const int ci = c - Cout;
+            float sc, sh;
+            norm_scale_shift(xn, N, Cin, n, ci, sc, sh);
+            apad[pv * Cin + ci] = lrelu(ld1(x + v * ldx + ci) * sc + sh, xn.slope);
+        }
+    }
+}
+// wtap[t][co][ci] = w[co][ci - g*cin_g][t] inside the group of co, 0 across groups
+__global__ void c3_tap_weights_kernel(const float *__restrict__ w, int Cin, int Cout, int groups, float *__restrict__ wtap) {
+    const int cin_g = Cin / groups, cout_g = Cout / groups;
+    const int total = 27 * Cout * Cin;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int ci = i % Cin, co = (i / Cin) % Cout, tap = i / (Cin * Cout);
+        const int g = co / cout_g, cil = ci - g * cin_g;
+        wtap[i] = (cil >= 0 && cil < cin_g) ? w[((size_t)co * cin_g + cil) * 27 + tap] : 0.f;
+    }
+}
+__global__ void c3_gw_scatter_kernel(const float *__restrict__ gwtap, int Cin, int Cout, int groups, float *__restrict__ g_w) {
+    const int cin_g = Cin / groups, cout_g = Cout / groups;
+    const int total = Cout * cin_g * 27;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int tap = i % 27, cil = (i / 27) % cin_g, co = i / (27 * cin_g);
+        g_w[i] += gwtap[((size_t)tap * Cout + co) * Cin + (co / cout_g) * cin_g + cil];
+    }
+}
+__global__ void __launch_bounds__(NT) c3_unpad_kernel(const float *__restrict__ gapad, int N, int C, int D, int H, int W, float *__restrict__ ga) {
+    const size_t vox = (size_t)D * H * W, total = (size_t)N * vox * (C / 4);
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < total; i += (size_t)gridDim.x * NT) {
+        const int q = (int)(i % (C / 4));
+        const size_t v = i / (C / 4);
+        const int n = (int)(v / vox);
+        size_t r = v - (size_t)n * vox;
+        const int xw = (int)(r % W); r /= W;
+        const int yh = (int)(r % H);
+        const int zd = (int)(r / H);
+        const size_t pv = (((size_t)n * (D + 2) + zd + 1) * (H + 2) + yh + 1) * (W + 2) + xw + 1;
+        reinterpret_cast<float4 *>(ga + v * C)[q] = reinterpret_cast<const float4 *>(gapad + pv * C)[q];
+    }
+}
+
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+static size_t c3_guard_vox(int H, int W) { return ((size_t)(H + 2) * (W + 2) + (W + 2) + 1 + 127) / 128 * 128; }
+static bool c3_bwd_tc_ok(int Cin, int Cout) {
+    return L3D_ENV_INT("L3D_C3_BWD_TC", 1) != 0 && Cin % 16 == 0 && Cout % 16 == 0 && Cout <= 128 && Cin <= 256;
+}
+static size_t c3_bwd_tc_bytes(int N, int D, int H, int W, int Cin, int Cout) {
+    const size_t vp = (size_t)N * (D + 2) * (H + 2) * (W + 2) + 2 * c3_guard_vox(H, W);
+    return align256(vp * Cout * 4) + 2 * align256(vp * Cin * 4) + 2 * align256((size_t)27 * Cin * Cout * 4);
+}
 extern "C" int64_t l3d_conv3_bwd_workspace_bytes(int N, int D, int H, int W, int Cin, int Cout, int elem_size) {
     const size_t vox = (size_t)N * D * H * W;
     const size_t maxc = (size_t)(Cin > Cout ? Cin : Cout);
     return (int64_t)(align256(vox * Cout * elem_size) + align256(vox * Cin * elem_size) + align256((size_t)Cin * Cout * 27 * 4) +
-                     align256(2 * (size_t)N * maxc * 8) + align256((size_t)((Cout + 7) / 8) * ((Cin + 7) / 8) * 8));
+                     align256(2 * (size_t)N * maxc * 8) + align256((size_t)((Cout + 7) / 8) * ((Cin + 7) / 8) * 8) +
+                     (c3_bwd_tc_ok(Cin, Cout) ? c3_bwd_tc_bytes(N, D, H, W, Cin, Cout) : 0));
 }
 
 extern "C" int l3d_conv3_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int W,
@@ -1408,9 +1490,65 @@ extern "C" int l3d_conv3_bwd(const l3d_act *gz, const l3d_act *t, const l3d_norm
     void *ga = wp; wp += align256((size_t)N * vox * Cin * es);
     float *wT = (float *)wp; wp += align256((size_t)Cin * Cout * 27 * 4);
     double *dummy_stats = (double *)wp; wp += align256(2 * (size_t)N * (Cin > Cout ? Cin : Cout) * 8);
-    int2 *pairs = (int2 *)wp;
+    int2 *pairs = (int2 *)wp; wp += align256((size_t)((Cout + 7) / 8) * ((Cin + 7) / 8) * 8);
     cudaStream_t st = (cudaStream_t)stream;
     const NormDev dnt = norm_dev(nt), dxn = norm_dev(xn);
+    // ---- tensor-core path: 27 tap launches of the pointwise backward kernel over zero-padded copies (see above)
+    if (c3_bwd_tc_ok(Cin, Cout) && (x->dtype == L3D_F32 || x->dtype == L3D_F16) && (!has_nt || t->dtype == x->dtype) &&
+        (!has_gy || (gy->C == Cin && gy->dtype == L3D_F32)) && (long long)N * (D + 2) * (H + 2) * (W + 2) < (1ll << 31)) {
+        const size_t guard = c3_guard_vox(H, W);
+        const size_t vp = (size_t)N * (D + 2) * (H + 2) * (W + 2);
+        float *gpad = (float *)wp; wp += align256((vp + 2 * guard) * Cout * 4);
+        float *apad = (float *)wp; wp += align256((vp + 2 * guard) * Cin * 4);
+        float *gapad = (float *)wp; wp += align256((vp + 2 * guard) * Cin * 4);
+        float *wtap = (float *)wp; wp += align256((size_t)27 * Cin * Cout * 4);
+        float *gwtap = (float *)wp;
+        cudaMemsetAsync(gpad, 0, (vp + 2 * guard) * Cout * 4, st);
+        cudaMemsetAsync(apad, 0, (vp + 2 * guard) * Cin * 4, st);
+        if (has_gy) cudaMemsetAsync(gapad, 0, (vp + 2 * guard) * Cin * 4, st);
+        cudaMemsetAsync(gwtap, 0, (size_t)27 * Cin * Cout * 4, st);
+        {
+            const size_t total = (size_t)N * vox * (Cin + Cout);
+            size_t blocks = (total + NT - 1) / NT;
+            if (blocks > 148 * 16) blocks = 148 * 16;
+            L3D_DISPATCH_DTYPE(x->dtype, T, {
+                c3_pad_kernel<T><<<(unsigned)blocks, NT, 0, st>>>((const float *)gz->ptr, gz->ldc, has_nt ? (const T *)t->ptr : nullptr, has_nt ? t->ldc : 0,
+                                                                  dnt, red, (const T *)x->ptr, x->ldc, dxn, N, Cout, Cin, D, H, W,
+                                                                  gpad + guard * Cout, apad + guard * Cin);
+            });
+            c3_tap_weights_kernel<<<(27 * Cin * Cout + 255) / 256, 256, 0, st>>>(w, Cin, Cout, groups, wtap);
+            l3d_count_launch(2);
+        }
+        for (int tap = 0; tap < 27; ++tap) {
+            const long long sh = ((long long)(tap / 9 - 1) * (H + 2) + (tap / 3 % 3 - 1)) * (W + 2) + (tap % 3 - 1);
+            l3d_act a_g = {gpad + guard * Cout, Cout, Cout, L3D_F32, 0};
+            l3d_act a_u = {apad + (long long)(guard + sh) * Cin, Cin, Cin, L3D_F32, 0};
+            l3d_act a_gu = {has_gy ? gapad + (long long)(guard + sh) * Cin : nullptr, Cin, Cin, L3D_F32, 0};
+            const int rc = l3d_pw_bwd_tc(&a_g, nullptr, nullptr, nullptr, &a_u, nullptr, 1, (long long)vp, wtap + (size_t)tap * Cout * Cin,
+                                         gwtap + (size_t)tap * Cout * Cin, &a_gu, 1, stream);
+            if (rc != 0) { if (rc < 0) l3d_set_error("l3d_conv3_bwd: tensor-core tap launch rejected (Cin=%d Cout=%d)", Cin, Cout); return rc < 0 ? 3 : rc; }
+            l3d_count_launch();
+        }
+        c3_gw_scatter_kernel<<<(Cout * (Cin / groups) * 27 + 255) / 256, 256, 0, st>>>(gwtap, Cin, Cout, groups, g_w);
+        l3d_count_launch();
+        if (has_gy) {
+            size_t blocks = ((size_t)N * vox * (Cin / 4) + NT - 1) / NT;
+            if (blocks > 148 * 16) blocks = 148 * 16;
+            c3_unpad_kernel<<<(unsigned)blocks, NT, 0, st>>>(gapad + guard * Cin, N, Cin, D, H, W, (float *)ga);
+            size_t gx = (vox * Cin + NT - 1) / NT;
+            const size_t cap = (148 * 16 + N - 1) / N;
+            if (gx > cap) gx = cap;
+            dim3 grid((unsigned)gx, (unsigned)N);
+            L3D_DISPATCH_DTYPE(x->dtype, T, {
+                c3_act_bwd_kernel<T><<<grid, NT, sizeof(float) * 7 * Cin, st>>>((const float *)ga, (const T *)x->ptr, x->ldc, dxn, N, Cin, vox,
+                                                                                 (float *)gy->ptr, gy->ldc, accumulate_gy, redx);
+            });
+            l3d_count_launch(2);
+        }
+        l3d_note_kernel("pw_bwd_tc_kernel");
+        L3D_CUDA_OK("l3d_conv3_bwd (tensor-core taps) launch");
+        return 0;
+    }
     // (1) g_t
     {
         const size_t total = (size_t)N * vox * Cout;

@@ -739,11 +739,11 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
     size_t smem_launch = smem;
 #define L3D_C3_LAUNCH_L(TZV, MG, NWV, R1V, LDV)                                                                                     \
     do {                                                                                                                    \
-        static bool attr_set = false;                                                                                       \
-        if (!attr_set) {                                                                                                    \
+        static bool attr_set_[64] = {};  /* the attribute is per device */                                                                                                                 \
+        if (dev < 0 || dev >= 64 || !attr_set_[dev]) {                                                                                                    \
             cudaError_t e = cudaFuncSetAttribute(conv3_tc_kernel<TZV, MG, NWV, R1V, LDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
             if (e != cudaSuccess) { l3d_set_error("conv3_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 3; } \
-            attr_set = true;                                                                                                \
+            if (dev >= 0 && dev < 64) attr_set_[dev] = true;                                                                                                \
         }                                                                                                                   \
         conv3_tc_kernel<TZV, MG, NWV, R1V, LDV><<<(unsigned)grid, NWV * 32 + 32, smem_launch, (cudaStream_t)stream>>>(tmap, A); \
     } while (0)

@@ -433,11 +433,11 @@ int l3d_dwpw_fwd_slab(const l3d_act *x, const l3d_norm *xn, int N, int D, int H,
     if (grid > slabs) grid = slabs;
 #define L3D_SLAB_LAUNCH(XTV, NTV)                                                                                             \
     do {                                                                                                                      \
-        static bool attr_set = false;                                                                                         \
-        if (!attr_set) {                                                                                                      \
+        static bool attr_set_[64] = {};  /* the attribute is per device */                                                                                                                   \
+        if (dev < 0 || dev >= 64 || !attr_set_[dev]) {                                                                                                      \
             cudaError_t e = cudaFuncSetAttribute(dwpw_slab_kernel<XTV, NTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024); \
             if (e != cudaSuccess) { l3d_set_error("dwpw_slab: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 3; }   \
-            attr_set = true;                                                                                                  \
+            if (dev >= 0 && dev < 64) attr_set_[dev] = true;                                                                                                  \
         }                                                                                                                     \
         dwpw_slab_kernel<XTV, NTV><<<(unsigned)grid, NTV, p.smem, (cudaStream_t)stream>>>(tmap, A);                           \
     } while (0)

@@ -71,8 +71,8 @@ def test_device_noise_and_mixed_sampler():
     aug = {"gaussian_noise": {"enabled": True, "prob": 1.0, "sigma": 0.05}}
     s = DevicePatchSampler(cases, (16, 16, 16), 0.5, aug, 1, torch.device(DEV))           # noise drawn on the device
     s0 = DevicePatchSampler(cases, (16, 16, 16), 0.5, None, 1, torch.device(DEV))
-    a, _ = s.sample_batch(64)
     b, _ = s0.sample_batch(64)
+    a, _ = s.sample_batch(64, decisions=[dict(d, noise_sigma=0.05) for d in s0.last_decisions])    # same patches + device noise
     d = (a - b).double()
     inner = (b > 0.2) & (b < 0.8)                                                          # away from the clip at 0 / 1
     assert abs(float(d[inner].std()) - 0.05) < 5e-3 and abs(float(d[inner].mean())) < 5e-3
