@@ -62,6 +62,9 @@ const char *l3d_last_error(void);
 int l3d_abi_version(void);
 /* number of kernel launches issued through this library since load (for bench.py's gpu_launches) */
 int64_t l3d_launch_count(void);
+/* a CUDA graph captured through this library replays its kernels without passing through the entry points: the host adds
+ * the number of launches the capture recorded, once per replay */
+void l3d_add_launch_count(int64_t n);
 
 /* ---------------------------------------------------------------- forward -- */
 

@@ -23,6 +23,7 @@ int l3d_env_read(const char *name, int dflt) {
 extern "C" void l3d_env_refresh(void) { __atomic_fetch_add(&g_env_gen, 1, __ATOMIC_RELAXED); }
 
 void l3d_count_launch(int n) { __atomic_fetch_add(&g_launches, (int64_t)n, __ATOMIC_RELAXED); }
+extern "C" void l3d_add_launch_count(int64_t n) { __atomic_fetch_add(&g_launches, n, __ATOMIC_RELAXED); }
 static thread_local const char *g_last_kernel = "";
 void l3d_note_kernel(const char *name) { g_last_kernel = name; }
 extern "C" const char *l3d_last_kernel(void) { return g_last_kernel; }

@@ -83,7 +83,7 @@ _SIGS = {
     "l3d_tc_selftest_tf32": [_P, _P, c_int, c_int, c_int, c_int, _P, _P],
     "l3d_tc_selftest_mn16": [_P, _P, c_int, c_int, c_int, _P, _P],
 }
-EXPORTS = sorted(list(_SIGS) + ["l3d_env_refresh", "l3d_last_kernel", "l3d_last_error", "l3d_abi_version", "l3d_launch_count", "l3d_ccl_workspace_elems",
+EXPORTS = sorted(list(_SIGS) + ["l3d_add_launch_count", "l3d_env_refresh", "l3d_last_kernel", "l3d_last_error", "l3d_abi_version", "l3d_launch_count", "l3d_ccl_workspace_elems",
                                 "l3d_conv3_bwd_workspace_bytes"])
 
 
@@ -102,6 +102,8 @@ def lib():
     L.l3d_last_kernel.restype = ctypes.c_char_p
     L.l3d_last_kernel.argtypes = []
     L.l3d_abi_version.restype = c_int
+    L.l3d_add_launch_count.restype = None
+    L.l3d_add_launch_count.argtypes = [c_int64]
     L.l3d_env_refresh.restype = None
     L.l3d_env_refresh.argtypes = []
     L.l3d_launch_count.restype = c_int64
@@ -174,6 +176,11 @@ def call(name: str, *args, algo_bytes: int = 0):
 def refresh_env() -> None:
     """libl3d caches its L3D_* environment knobs per call site; call this after changing one in a running process."""
     lib().l3d_env_refresh()
+
+
+def add_launch_count(n: int) -> None:
+    """Launches replayed from a CUDA graph (they do not pass through the entry points that count)."""
+    lib().l3d_add_launch_count(int(n))
 
 
 def launch_count() -> int:

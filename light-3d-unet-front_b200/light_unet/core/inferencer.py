@@ -10,6 +10,7 @@ nibabel, imported lazily because file I/O is off the accelerated path).
 from __future__ import annotations
 
 import json
+import os
 from pathlib import Path
 
 import numpy as np
@@ -80,18 +81,30 @@ class Inferencer:
         self.bboxes_dir.mkdir(parents=True, exist_ok=True)
 
     # ------------------------------------------------------------------ boxes
-    def _bboxes_from_device(self, prob_d: torch.Tensor, mask_d: torch.Tensor, min_volume_cc, spacing):
-        """threshold mask -> labels -> per-component table on the device, then the reference's host-side
-        arithmetic on the resulting integers (inferencer.py:66-108)."""
-        D, H, W = prob_d.shape
+    @staticmethod
+    def _min_voxels(min_volume_cc, spacing):
         voxel_volume_cc = spacing[0] * spacing[1] * spacing[2] / 1000.0
-        min_voxels = int(np.ceil(min_volume_cc / voxel_volume_cc))
+        return int(np.ceil(min_volume_cc / voxel_volume_cc))                      # inferencer.py:66-68
+
+    def _label_and_reduce(self, prob_d: torch.Tensor, mask_d: torch.Tensor, min_voxels: int):
+        """Device part of extract_bboxes: mask -> labels -> per-component table (no host synchronisation)."""
+        D, H, W = prob_d.shape
         labels, n_d = label_device(mask_d, min_voxels if min_voxels > 0 else 0)
         st = nv.stream_ptr(prob_d.device)
         table = torch.empty(BBOX_TABLE_CAP, 8, dtype=torch.int32, device=prob_d.device)
         nv.call("l3d_bbox_init", nv.ptr(table), BBOX_TABLE_CAP, st)
         nv.call("l3d_bbox_reduce", nv.ptr(labels), nv.ptr(prob_d), D, H, W, nv.ptr(table), BBOX_TABLE_CAP, st,
                 algo_bytes=8 * D * H * W)                          # labels + probabilities read once
+        return labels, n_d, table
+
+    def _bboxes_from_device(self, prob_d: torch.Tensor, mask_d: torch.Tensor, min_volume_cc, spacing, reduced=None):
+        """threshold mask -> labels -> per-component table on the device, then the reference's host-side
+        arithmetic on the resulting integers (inferencer.py:66-108)."""
+        D, H, W = prob_d.shape
+        voxel_volume_cc = spacing[0] * spacing[1] * spacing[2] / 1000.0
+        min_voxels = self._min_voxels(min_volume_cc, spacing)
+        labels, n_d, table = reduced if reduced is not None else self._label_and_reduce(prob_d, mask_d, min_voxels)
+        st = nv.stream_ptr(prob_d.device)
         n = int(n_d.item())
         if n > BBOX_TABLE_CAP:
             cap = n
@@ -153,8 +166,15 @@ class Inferencer:
         bm = None
         if body_mask is not None:
             bm = body_mask if isinstance(body_mask, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(body_mask).astype(np.uint8))
-        prob_d, mask_d = sliding_window_device(vol, self.model, tuple(self.config["data"]["patch_size"]), 0.5, True,
-                                               body_mask=bm, threshold=threshold, shard=shard)
+        min_cc = self.config["data"]["volume_threshold"]["inference_cc"]
+        reduced = None
+        if shard is None and not nv.TIMER.enabled and os.environ.get("L3D_INFER_GRAPH", "1") != "0":
+            prob_d, mask_d, reduced = self._graph_pipeline(vol, bm, threshold, self._min_voxels(min_cc, spacing))
+            if return_device:
+                prob_d = prob_d.clone()                           # the graph's output buffer is overwritten by the next call
+        else:
+            prob_d, mask_d = sliding_window_device(vol, self.model, tuple(self.config["data"]["patch_size"]), 0.5, True,
+                                                   body_mask=bm, threshold=threshold, shard=shard)
         if prob_d is None:                                        # window-sharded call on a rank other than 0
             return None, []
         copy_done = None
@@ -171,11 +191,52 @@ class Inferencer:
                 prob_d.record_stream(self._copy_stream)
                 copy_done = torch.cuda.Event()
                 copy_done.record(self._copy_stream)
-        bboxes = self._bboxes_from_device(prob_d, mask_d, self.config["data"]["volume_threshold"]["inference_cc"], spacing)
+        bboxes = self._bboxes_from_device(prob_d, mask_d, min_cc, spacing, reduced)
         if copy_done is not None:
             copy_done.synchronize()
             return prob_out, bboxes
         return (prob_d if return_device else prob_d.cpu().numpy()), bboxes
+
+    # ------------------------------------------------------------- CUDA graph
+    def _graph_pipeline(self, vol, bm, threshold, min_voxels):
+        """Window gather -> network -> stitch / threshold -> labelling -> box table as ONE CUDA graph per (volume shape,
+        threshold, patch, storage type): the ~45 launches of a case cost one host call.  The first call of a configuration
+        runs eagerly (it sizes the workspace and fills the caches the capture must not touch), the second captures, later
+        ones replay.  A graph is dropped when the model's activation workspace was replaced in the meantime."""
+        patch = tuple(self.config["data"]["patch_size"])
+        plan = self.model._plan
+        key = (tuple(vol.shape), float(np.float32(threshold)), bm is not None, patch, self.model.compute_dtype, int(min_voxels), str(vol.device))
+        graphs = self.__dict__.setdefault("_graphs", {})
+        seen = self.__dict__.setdefault("_graph_seen", set())
+        g = graphs.get(key)
+        if g is not None and plan._ws.get((patch, self.model.compute_dtype, str(vol.device), False)) is not g["ws"]:
+            graphs.pop(key)
+            g = None
+        if g is None:
+            def run(v, m):
+                prob_d, mask_d = sliding_window_device(v, self.model, patch, 0.5, True, body_mask=m, threshold=threshold)
+                return prob_d, mask_d, self._label_and_reduce(prob_d, mask_d, min_voxels)
+            if key not in seen:                                   # first call: eager
+                seen.add(key)
+                return run(vol, bm)
+            if len(graphs) >= 4:
+                graphs.pop(next(iter(graphs)))
+            sv = vol.clone()
+            sm = bm.to(device=vol.device, dtype=torch.uint8).clone() if bm is not None else None
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(vol.device)
+            l0 = nv.launch_count()
+            with torch.cuda.graph(graph):
+                outs = run(sv, sm)
+            g = {"graph": graph, "vol": sv, "bm": sm, "outs": outs, "launches": nv.launch_count() - l0,
+                 "ws": plan._ws.get((patch, self.model.compute_dtype, str(vol.device), False))}
+            graphs[key] = g
+        g["vol"].copy_(vol, non_blocking=True)
+        if bm is not None:
+            g["bm"].copy_(bm, non_blocking=True)
+        g["graph"].replay()
+        nv.add_launch_count(g["launches"])
+        return g["outs"]
 
     # ------------------------------------------------------------- file level
     def infer_case(self, case_id, data_dir, threshold=0.3):

@@ -112,10 +112,13 @@ class DataParallelStep:
             for _ in range(2):
                 self._eager_step(sx, st)
         torch.cuda.current_stream(dev).wait_stream(side)
+        from .. import _native as nv
         graph = torch.cuda.CUDAGraph()
         self.optimizer.zero_grad(set_to_none=True)
+        l0 = nv.launch_count()
         with torch.cuda.graph(graph):
             loss = self._eager_step(sx, st)
+        self._graph_launches = nv.launch_count() - l0
         # the warm-up steps were real steps: put parameters, optimiser state and the RNG back where the caller left them
         with torch.no_grad():
             for p, q in zip(params, p_snap):
@@ -138,6 +141,8 @@ class DataParallelStep:
         self._static["x"].copy_(images, non_blocking=True)
         self._static["t"].copy_(labels, non_blocking=True)
         self._graph.replay()
+        from .. import _native as nv
+        nv.add_launch_count(self._graph_launches)
         return self._static["loss"]
 
     def prefetch(self, images: torch.Tensor, labels: torch.Tensor) -> None:
