@@ -327,6 +327,17 @@ def bench_ours(args):
     for i in range(max(1, args.warmup // 2)):
         step_e2e(i)
     ms_e2e = timed(step_e2e, args.steps, world, device)
+    # the same through the streaming form of the public API: Inferencer.infer_volumes uploads volume i + 1 (pinned host ->
+    # device, side stream) under the kernels of volume i; every step still copies its 21 MB in and its 21 MB map out
+    outs2 = [torch.empty(VOLUME, dtype=torch.float32).pin_memory() for _ in range(2)]
+    stream_steps = args.steps + 2
+    gen = inf.infer_volumes((host_vols[i % 8] for i in range(stream_steps)), threshold=0.3, prob_outs=(outs2[i % 2] for i in range(stream_steps)))
+    next(gen); next(gen)                                                 # pipeline primed (2 untimed volumes)
+
+    def step_stream(i):
+        prob, boxes = next(gen)
+        nboxes[0] = len(boxes)
+    ms_stream = timed(step_stream, args.steps, world, device)
 
     # per-kernel device time (CUDA events around every libl3d launch, same stream) over one more volume
     nv.TIMER.start()
@@ -412,8 +423,11 @@ def bench_ours(args):
                            "volumes_per_step_per_gpu": 1, "window_batch": window_batch(),
                            "l2": "inputs rotate over 8 volumes (168 MB) and each step streams >10 GB of activations (> 126 MB L2)",
                            "parallelism": f"volume-sharded x{world}", "boxes_found": nboxes[0]},
-                "e2e": {"value": round(world * NVOX * args.steps / (ms_e2e * 1e-3), 1), "unit": "voxels/s",
-                        "ms_per_step": round(ms_e2e / args.steps, 3),
+                "e2e": {"value": round(world * NVOX * args.steps / (ms_stream * 1e-3), 1), "unit": "voxels/s",
+                        "ms_per_step": round(ms_stream / args.steps, 3),
+                        "api": "Inferencer.infer_volumes(host volumes): upload of volume i+1 overlapped with volume i",
+                        "one_call_per_volume": {"value": round(world * NVOX * args.steps / (ms_e2e * 1e-3), 1),
+                                                "ms_per_step": round(ms_e2e / args.steps, 3), "api": "Inferencer.infer_volume(host volume)"},
                         "h2d_bytes_per_step": NVOX * 4, "d2h_bytes_per_step": NVOX * 4 + 4 + 32 * max(nboxes[0], 1)},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
         if latency is not None:

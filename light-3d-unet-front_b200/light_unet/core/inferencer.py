@@ -197,6 +197,37 @@ class Inferencer:
             return prob_out, bboxes
         return (prob_d if return_device else prob_d.cpu().numpy()), bboxes
 
+    def infer_volumes(self, images, threshold=0.3, spacing=(4.0, 4.0, 4.0), prob_outs=None):
+        """Generator over a sequence of host volumes (pinned tensors copy asynchronously): yields (prob_map, bboxes) per
+        volume like infer_volume, with the host-to-device copy of volume i + 1 issued on a side stream while volume i is
+        being processed.  `prob_outs`: optional sequence of pinned host fp32 tensors receiving the maps."""
+        if getattr(self, "_h2d_stream", None) is None:
+            self._h2d_stream = torch.cuda.Stream(device=self.device)
+        it = iter(images)
+        outs = iter(prob_outs) if prob_outs is not None else None
+
+        def stage(img):
+            host = img if isinstance(img, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(img, dtype=np.float32))
+            with torch.cuda.stream(self._h2d_stream):
+                dev = host.to(self.device, dtype=torch.float32, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._h2d_stream)
+            return dev, ev
+        try:
+            nxt = stage(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            vol, ev = nxt
+            try:
+                nxt = stage(next(it))                              # upload of the next volume overlaps this one's kernels
+            except StopIteration:
+                nxt = None
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(ev)
+            vol.record_stream(cur)
+            yield self.infer_volume(vol, threshold=threshold, spacing=spacing, prob_out=next(outs) if outs is not None else None)
+
     # ------------------------------------------------------------- CUDA graph
     def _graph_pipeline(self, vol, bm, threshold, min_voxels):
         """Window gather -> network -> stitch / threshold -> labelling -> box table as ONE CUDA graph per (volume shape,

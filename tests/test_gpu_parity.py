@@ -218,6 +218,15 @@ def test_inferencer_end_to_end(tmp_path):
     assert boxes2 == bbox_ref.extract_bboxes(out.numpy(), 0.5, 0.5, (4.0, 4.0, 4.0), 3)
     with pytest.raises(ValueError):
         inf.infer_volume(vol, threshold=0.5, prob_out=torch.empty(3, 3, 3))
+    # streaming form: the upload of volume i + 1 overlaps volume i; same maps (to round-off) and boxes, in order
+    vols = [synth.synth_volume((20, 28, 36), seed=9 + k, n_blobs=2) for k in range(4)]
+    outs = [torch.empty(vol.shape, dtype=torch.float32).pin_memory() for _ in range(4)]
+    res = list(inf.infer_volumes([torch.from_numpy(v).pin_memory() for v in vols], threshold=0.5, prob_outs=outs))
+    assert len(res) == 4 and list(inf.infer_volumes([])) == []
+    for k, (p_k, b_k) in enumerate(res):
+        want_p, want_b = inf.infer_volume(vols[k], threshold=0.5)
+        assert p_k is outs[k] and np.abs(p_k.numpy() - want_p).max() < 1e-5
+        assert b_k == bbox_ref.extract_bboxes(p_k.numpy(), 0.5, 0.5, (4.0, 4.0, 4.0), 3)
 
 
 def test_full_size_volume_properties(tmp_path):
