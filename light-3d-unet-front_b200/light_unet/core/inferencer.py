@@ -111,11 +111,23 @@ class Inferencer:
             table = torch.empty(cap, 8, dtype=torch.int32, device=prob_d.device)
             nv.call("l3d_bbox_init", nv.ptr(table), cap, st)
             nv.call("l3d_bbox_reduce", nv.ptr(labels), nv.ptr(prob_d), D, H, W, nv.ptr(table), cap, st)
-        rows = table[:n].cpu().numpy()
+        return self._boxes_from_rows(table[:n].cpu().numpy(), (D, H, W), spacing)
+
+    def _label_table(self, labels, prob_d, n):
+        """A box table large enough for n components from an existing label map."""
+        D, H, W = prob_d.shape
+        st = nv.stream_ptr(prob_d.device)
+        table = torch.empty(max(n, 1), 8, dtype=torch.int32, device=prob_d.device)
+        nv.call("l3d_bbox_init", nv.ptr(table), max(n, 1), st)
+        nv.call("l3d_bbox_reduce", nv.ptr(labels), nv.ptr(prob_d), D, H, W, nv.ptr(table), max(n, 1), st)
+        return labels, torch.tensor([n], dtype=torch.int32, device=prob_d.device), table
+
+    def _boxes_from_rows(self, rows, shape, spacing):
+        """The reference's host-side arithmetic on the per-component integers (inferencer.py:83-108)."""
+        voxel_volume_cc = spacing[0] * spacing[1] * spacing[2] / 1000.0
         expansion = self.config["data"]["bbox_expansion_voxels"]
-        shape = (D, H, W)
         out = []
-        for i in range(n):
+        for i in range(len(rows)):
             row = rows[i]
             if row[6] == 0:
                 continue
@@ -199,34 +211,86 @@ class Inferencer:
 
     def infer_volumes(self, images, threshold=0.3, spacing=(4.0, 4.0, 4.0), prob_outs=None):
         """Generator over a sequence of host volumes (pinned tensors copy asynchronously): yields (prob_map, bboxes) per
-        volume like infer_volume, with the host-to-device copy of volume i + 1 issued on a side stream while volume i is
-        being processed.  `prob_outs`: optional sequence of pinned host fp32 tensors receiving the maps."""
+        volume like infer_volume, in order, as a three-stage pipeline -- the host-to-device copy of volume i + 1 and the
+        device-to-host copy of map i - 1 (+ its box table) run on side streams under the kernels of volume i, so the result
+        of a volume is yielded once the next one has been launched.  `prob_outs`: optional sequence of pinned host fp32
+        tensors receiving the maps (fresh pinned tensors otherwise)."""
+        dev = self.device
         if getattr(self, "_h2d_stream", None) is None:
-            self._h2d_stream = torch.cuda.Stream(device=self.device)
+            self._h2d_stream = torch.cuda.Stream(device=dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
         it = iter(images)
         outs = iter(prob_outs) if prob_outs is not None else None
+        min_cc = self.config["data"]["volume_threshold"]["inference_cc"]
+        min_voxels = self._min_voxels(min_cc, spacing)
+        rows_cap = 4096                                            # box-table rows fetched with the map; more -> second fetch
+        slots = [None, None]
 
         def stage(img):
             host = img if isinstance(img, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(img, dtype=np.float32))
             with torch.cuda.stream(self._h2d_stream):
-                dev = host.to(self.device, dtype=torch.float32, non_blocking=True)
+                d = host.to(dev, dtype=torch.float32, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(self._h2d_stream)
-            return dev, ev
+            return d, ev
+
+        def launch(vol, ev, k):
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(ev)
+            vol.record_stream(cur)
+            if nv.TIMER.enabled or os.environ.get("L3D_INFER_GRAPH", "1") == "0":
+                prob_d, mask_d = sliding_window_device(vol, self.model, tuple(self.config["data"]["patch_size"]), 0.5, True, threshold=threshold)
+                labels, n_d, table = self._label_and_reduce(prob_d, mask_d, min_voxels)
+            else:
+                prob_d, mask_d, (labels, n_d, table) = self._graph_pipeline(vol, None, threshold, min_voxels)
+            sl = slots[k & 1]
+            if sl is None or sl["prob"].shape != prob_d.shape:
+                sl = slots[k & 1] = {"prob": torch.empty_like(prob_d), "labels": torch.empty_like(labels),
+                                     "n": torch.empty(1, dtype=torch.int32).pin_memory(), "rows": torch.empty(rows_cap, 8, dtype=torch.int32).pin_memory()}
+            # the graph's output buffers are overwritten by the next volume: keep device copies (21 MB each, microseconds)
+            sl["prob"].copy_(prob_d, non_blocking=True)
+            sl["labels"].copy_(labels, non_blocking=True)
+            sl["n"].copy_(n_d, non_blocking=True)
+            sl["rows"].copy_(table[:rows_cap], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(cur)
+            host_out = next(outs) if outs is not None else torch.empty(tuple(prob_d.shape), dtype=torch.float32).pin_memory()
+            self._copy_stream.wait_event(done)
+            with torch.cuda.stream(self._copy_stream):
+                host_out.copy_(sl["prob"], non_blocking=True)
+                copied = torch.cuda.Event()
+                copied.record(self._copy_stream)
+            return sl, done, copied, host_out
+
+        def finish(job):
+            sl, done, copied, host_out = job
+            done.synchronize()
+            n = int(sl["n"][0])
+            if n > rows_cap:                                       # rare: more components than fetched rows
+                boxes = self._bboxes_from_device(sl["prob"], None, min_cc, spacing, reduced=self._label_table(sl["labels"], sl["prob"], n))
+            else:
+                boxes = self._boxes_from_rows(sl["rows"][:n].numpy(), tuple(sl["prob"].shape), spacing)
+            copied.synchronize()
+            return host_out, boxes
+
         try:
             nxt = stage(next(it))
         except StopIteration:
             return
+        pending, k = None, 0
         while nxt is not None:
             vol, ev = nxt
             try:
                 nxt = stage(next(it))                              # upload of the next volume overlaps this one's kernels
             except StopIteration:
                 nxt = None
-            cur = torch.cuda.current_stream(self.device)
-            cur.wait_event(ev)
-            vol.record_stream(cur)
-            yield self.infer_volume(vol, threshold=threshold, spacing=spacing, prob_out=next(outs) if outs is not None else None)
+            job = launch(vol, ev, k)
+            k += 1
+            if pending is not None:
+                yield finish(pending)                              # the previous volume's map / boxes, copied under this one
+            pending = job
+        yield finish(pending)
 
     # ------------------------------------------------------------- CUDA graph
     def _graph_pipeline(self, vol, bm, threshold, min_voxels):

@@ -29,7 +29,8 @@ class _FocalTverskyFn(torch.autograd.Function):
         t = t.contiguous()
         st = nv.stream_ptr(p.device)
         sums = torch.zeros(3, dtype=torch.float64, device=p.device)
-        nv.call("l3d_ftl_sums", nv.ptr(p), nv.ptr(t), p.numel(), nv.ptr(sums), st, algo_bytes=8 * p.numel())
+        with torch.cuda.device(p.device):
+            nv.call("l3d_ftl_sums", nv.ptr(p), nv.ptr(t), p.numel(), nv.ptr(sums), st, algo_bytes=8 * p.numel())
         if reduce_group is not None:
             # data-parallel: the Tversky index is a ratio of batch-global sums (losses.py:44-49), so the three
             # sums are all-reduced before the ratio
@@ -37,7 +38,8 @@ class _FocalTverskyFn(torch.autograd.Function):
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=reduce_group if reduce_group is not True else None)
         loss = torch.empty((), dtype=torch.float32, device=p.device)
         coef = torch.empty(2, dtype=torch.float32, device=p.device)
-        nv.call("l3d_ftl_finish", nv.ptr(sums), alpha, beta, gamma, smooth, nv.ptr(loss), nv.ptr(coef), st)
+        with torch.cuda.device(p.device):
+            nv.call("l3d_ftl_finish", nv.ptr(sums), alpha, beta, gamma, smooth, nv.ptr(loss), nv.ptr(coef), st)
         ctx.save_for_backward(t, coef)
         ctx.shape = pred.shape
         ctx.sums = sums
@@ -48,8 +50,9 @@ class _FocalTverskyFn(torch.autograd.Function):
         t, coef = ctx.saved_tensors
         g = g_loss.reshape(1).float().contiguous()
         grad = torch.empty(t.numel(), dtype=torch.float32, device=t.device)
-        nv.call("l3d_ftl_grad", nv.ptr(t), t.numel(), nv.ptr(coef), nv.ptr(g), nv.ptr(grad), nv.stream_ptr(t.device),
-                algo_bytes=8 * t.numel())
+        with torch.cuda.device(t.device):
+            nv.call("l3d_ftl_grad", nv.ptr(t), t.numel(), nv.ptr(coef), nv.ptr(g), nv.ptr(grad), nv.stream_ptr(t.device),
+                    algo_bytes=8 * t.numel())
         return grad.view(ctx.shape), None, None, None, None, None, None
 
 

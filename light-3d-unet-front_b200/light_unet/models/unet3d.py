@@ -109,7 +109,8 @@ class _UNetFunction(torch.autograd.Function):
             x_cl = x.reshape(B, D, H, W, 1).to(dt)
         else:
             x_cl = x.permute(0, 2, 3, 4, 1).contiguous().to(dt)
-        ws = model._plan.forward(P, x_cl, training, masks)
+        with torch.cuda.device(x.device):          # libl3d launches on the CURRENT device: make it the tensors' device
+            ws = model._plan.forward(P, x_cl, training, masks)
         ctx.model, ctx.ws, ctx.P = model, ws, P
         ctx.generation = ws.generation
         return ws.prob_out
@@ -120,7 +121,8 @@ class _UNetFunction(torch.autograd.Function):
         if ws.generation != ctx.generation or not ws.training:
             raise RuntimeError("Lightweight3DUNet: the activation workspace of this forward pass was overwritten by a "
                                "later forward of the same shape before backward() ran (or the pass ran without grad)")
-        grads = ctx.model._plan.backward(ctx.P, ws, g_prob.contiguous())
+        with torch.cuda.device(g_prob.device):
+            grads = ctx.model._plan.backward(ctx.P, ws, g_prob.contiguous())
         return (None, None, None, None) + tuple(grads[n] for n in ctx.model._param_names)
 
 
@@ -185,6 +187,9 @@ class Lightweight3DUNet(nn.Module):
         params = [p for _, p in self.named_parameters()]
         for p in params:
             nv.require_cuda(p, "Lightweight3DUNet parameters")
+            if p.dtype != torch.float32 or not p.is_contiguous() or p.device != x.device:
+                raise nv.NativeError(f"Lightweight3DUNet: parameters must be contiguous float32 tensors on the input's device (got {p.dtype} on "
+                                     f"{p.device}); the activation storage type is set with set_compute_dtype, not model.half()")
         masks = dropout_masks
         if masks is None and self.training and self.dropout_p > 0:
             masks = self.draw_dropout_masks(x.shape[0], x.device)
