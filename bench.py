@@ -331,14 +331,15 @@ def bench_ours(args):
     # device) and downloads map i - 1 + its box table on side streams under the kernels of volume i; every step still copies
     # its 21 MB in and its 21 MB map out, and every result is read on the host (box list built) inside the timed region
     outs2 = [torch.empty(VOLUME, dtype=torch.float32).pin_memory() for _ in range(3)]
-    stream_steps = args.steps + 2
+    stream_steps = args.steps + 3          # two primed + `steps` timed, each of which launches one volume and completes one; one spare
     gen = inf.infer_volumes((host_vols[i % 8] for i in range(stream_steps)), threshold=0.3, prob_outs=(outs2[i % 3] for i in range(stream_steps)))
-    next(gen); next(gen)                                                 # pipeline primed (2 untimed volumes)
+    next(gen); next(gen)                                                 # pipeline primed: 3 volumes launched, 2 completed (untimed)
 
     def step_stream(i):
         prob, boxes = next(gen)
         nboxes[0] = len(boxes)
-    ms_stream = timed(step_stream, args.steps, world, device)
+    ms_stream = timed(step_stream, args.steps, world, device)           # every timed call: stage(i+2), launch(i+1), complete(i)
+    gen.close()
 
     # per-kernel device time (CUDA events around every libl3d launch, same stream) over one more volume
     nv.TIMER.start()
