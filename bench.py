@@ -527,6 +527,30 @@ def bench_train(args, device, rank, world, dtype):
         step_e2e(i)
     ms_e2e = timed(step_e2e, steps, world, device)
     stepper._staged = None
+    # the whole training pipeline on the device: DevicePatchSampler (class-balanced crop + the FL-70 augmentations,
+    # configs/unet_fl70.yaml:12-50, from volumes resident in HBM) feeding the graph step
+    pipeline = None
+    if not args.quick:
+        from light_unet.datasets import DevicePatchSampler
+        aug = {"random_flip": {"enabled": True, "prob": 0.5, "axes": [0, 1, 2]},
+               "random_rotation": {"enabled": True, "prob": 0.5, "angle_range": [-15, 15], "axes": [[0, 1], [0, 2], [1, 2]]},
+               "random_scale": {"enabled": True, "prob": 0.3, "scale_range": [0.9, 1.1]},
+               "intensity_shift": {"enabled": True, "prob": 0.5, "shift_range": [-0.1, 0.1]},
+               "gaussian_noise": {"enabled": True, "prob": 0.3, "sigma": 0.01}}
+        cases = []
+        for i in range(4):
+            v = synth.synth_volume(VOLUME, seed=300 + 7 * rank + i, n_blobs=8)
+            cases.append((v, (v > 0.55).astype(np.float32)))
+        sampler = DevicePatchSampler(cases, PATCH, 0.5, aug, seed=42 + rank, device=device)
+
+        def step_pipeline(i):
+            x, t = sampler.sample_batch(B)
+            last[0] = stepper.step(x, t)
+        for i in range(3):
+            step_pipeline(i)
+        ms_pipe = timed(step_pipeline, steps, world, device)
+        pipeline = {"value": round(world * B * steps / (ms_pipe * 1e-3), 1), "unit": "patches/s", "ms_per_step": round(ms_pipe / steps, 3),
+                    "what": "DevicePatchSampler.sample_batch (4 cached 128x128x320 cases, FL-70 augmentations) + the training step"}
     pk = peaks()
     es = 2 if dtype == "f16" else 4
     per_step_s = ms * 1e-3 / steps
@@ -540,6 +564,7 @@ def bench_train(args, device, rank, world, dtype):
             "loss": float(last[0]) if last[0] is not None else None,
             "e2e": {"value": round(world * B * steps / (ms_e2e * 1e-3), 1), "unit": "patches/s",
                     "h2d_bytes_per_step": 2 * B * 48 ** 3 * 4, "d2h_bytes_per_step": 4},
+            "with_device_sampler": pipeline,
             # forward compulsory traffic (write + read) x3 (fwd + ~2x for bwd)
             "frac_hbm": round(3 * B * ELEMS_PER_PATCH * es * 2 / per_step_s / 1e9 / pk["hbm_gbs"], 4)}
 

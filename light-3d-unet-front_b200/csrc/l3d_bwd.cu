@@ -596,7 +596,7 @@ constexpr int HXP = HX + 1, HPLANE = HY * HXP + 1, HVOX = HZ * HPLANE;
 constexpr int CK = 16;
 
 template <typename T>
-__global__ void __launch_bounds__(NT) dw_bwd_kernel(
+__global__ void __launch_bounds__(NT, 2) dw_bwd_kernel(
     const float *__restrict__ g_u, int ldgu, const T *__restrict__ x, int ldx, NormDev xn, int C,
     int N, int D, int H, int W, const float *__restrict__ dw_w, float *__restrict__ g_dw,
     float *__restrict__ gy, int ldgy, int accumulate, double *__restrict__ redx) {
@@ -658,21 +658,26 @@ __global__ void __launch_bounds__(NT) dw_bwd_kernel(
             {
                 const bool vec = (C % 4 == 0) && (ldx % 4 == 0) && (ldgu % 4 == 0);
                 constexpr int NITEM = HZ * HY * HX * (CK / 4);
+                // item = (halo voxel, 4-channel quad); consecutive items of a thread are NT / 4 = 64 voxels apart, so the halo
+                // coordinates advance by (+6 rows, +4 columns) with carries instead of being re-derived by divisions
+                static_assert(NT / (CK / 4) == 64 && HX == 10 && HY == 10, "incremental halo walk assumes 64 voxels per step of a 10 x 10 plane");
+                const int q = tid & (CK / 4 - 1);
+                int whx = (tid >> 2) % HX, why = ((tid >> 2) / HX) % HY, whz = (tid >> 2) / (HX * HY);
                 for (int item0 = tid; item0 < NITEM; item0 += 4 * NT) {
                     float gv[4][4], xv[4][4];
                     bool inb[4];
+                    int hxs[4], hys[4], hzs[4];
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
                         const int item = item0 + b * NT;
                         gv[b][0] = gv[b][1] = gv[b][2] = gv[b][3] = 0.f;
                         xv[b][0] = xv[b][1] = xv[b][2] = xv[b][3] = 0.f;
                         inb[b] = false;
+                        hxs[b] = whx; hys[b] = why; hzs[b] = whz;
+                        whx += 4; if (whx >= HX) { whx -= HX; ++why; }
+                        why += 6; if (why >= HY) { why -= HY; ++whz; }
                         if (item < NITEM) {
-                            const int q = item & (CK / 4 - 1);
-                            int hv = item / (CK / 4);
-                            const int hx = hv % HX; hv /= HX;
-                            const int hy = hv % HY;
-                            const int hz = hv / HY;
+                            const int hx = hxs[b], hy = hys[b], hz = hzs[b];
                             const int gz_ = z0 + hz - 1, gy_ = y0 + hy - 1, gx_ = x0 + hx - 1;
                             const int cc = c0 + q * 4;
                             if (gz_ >= 0 && gz_ < D && gy_ >= 0 && gy_ < H && gx_ >= 0 && gx_ < W && cc < C) {
@@ -692,11 +697,7 @@ __global__ void __launch_bounds__(NT) dw_bwd_kernel(
                     for (int b = 0; b < 4; ++b) {
                         const int item = item0 + b * NT;
                         if (item < NITEM) {
-                            const int q = item & (CK / 4 - 1);
-                            int hv = item / (CK / 4);
-                            const int hx = hv % HX; hv /= HX;
-                            const int hy = hv % HY;
-                            const int hz = hv / HY;
+                            const int hx = hxs[b], hy = hys[b], hz = hzs[b];
                             const int cc = c0 + q * 4;
                             float4 go = make_float4(0.f, 0.f, 0.f, 0.f), ao = go;
                             if (inb[b]) {
@@ -751,27 +752,27 @@ __global__ void __launch_bounds__(NT) dw_bwd_kernel(
                             // dgrad with the flipped stencil: weight index (2-dz, 2-hy, 2-dx)
                             const float w0 = wreg[(2 - dz) * 9 + (2 - hy) * 3 + 2], w1 = wreg[(2 - dz) * 9 + (2 - hy) * 3 + 1], w2 = wreg[(2 - dz) * 9 + (2 - hy) * 3];
 #pragma unroll
-                            for (int i = 0; i < TX; ++i) ga0[i] += w0 * grow[i] + w1 * grow[i + 1] + w2 * grow[i + 2];
+                            for (int i = 0; i < TX; ++i) ga0[i] = fmaf(w2, grow[i + 2], fmaf(w1, grow[i + 1], fmaf(w0, grow[i], ga0[i])));
                             // wgrad: tap (dz, hy, dx) pairs centre g_u with a at offset
 #pragma unroll
                             for (int dx = 0; dx < 3; ++dx) {
-                                float s = 0.f;
+                                float s = wacc[dz * 9 + hy * 3 + dx];
 #pragma unroll
-                                for (int i = 0; i < TX; ++i) s += gc0[i] * arow[i + dx];
-                                wacc[dz * 9 + hy * 3 + dx] += s;
+                                for (int i = 0; i < TX; ++i) s = fmaf(gc0[i], arow[i + dx], s);
+                                wacc[dz * 9 + hy * 3 + dx] = s;
                             }
                         }
                         if (hy >= 1) {
                             const int dy = hy - 1;
                             const float w0 = wreg[(2 - dz) * 9 + (2 - dy) * 3 + 2], w1 = wreg[(2 - dz) * 9 + (2 - dy) * 3 + 1], w2 = wreg[(2 - dz) * 9 + (2 - dy) * 3];
 #pragma unroll
-                            for (int i = 0; i < TX; ++i) ga1[i] += w0 * grow[i] + w1 * grow[i + 1] + w2 * grow[i + 2];
+                            for (int i = 0; i < TX; ++i) ga1[i] = fmaf(w2, grow[i + 2], fmaf(w1, grow[i + 1], fmaf(w0, grow[i], ga1[i])));
 #pragma unroll
                             for (int dx = 0; dx < 3; ++dx) {
-                                float s = 0.f;
+                                float s = wacc[dz * 9 + dy * 3 + dx];
 #pragma unroll
-                                for (int i = 0; i < TX; ++i) s += gc1[i] * arow[i + dx];
-                                wacc[dz * 9 + dy * 3 + dx] += s;
+                                for (int i = 0; i < TX; ++i) s = fmaf(gc1[i], arow[i + dx], s);
+                                wacc[dz * 9 + dy * 3 + dx] = s;
                             }
                         }
                     }
