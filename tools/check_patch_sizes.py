@@ -1,4 +1,4 @@
-"""Development aid: bf16-storage forward parity against the oracle at other patch sizes (64^3, 96^3, 50^3, 40^3)."""
+"""Development aid: fp16-storage forward parity against the oracle at other patch sizes (64^3, 96^3, 50^3, 40^3)."""
 import os, sys, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -8,7 +8,7 @@ from light_unet.models import Lightweight3DUNet
 from light_unet import _native as nv
 cfg = unet_ref.UNetCfg(dropout_p=0.0)
 sd_np = synth.synth_state_dict(unet_ref.param_shapes(cfg), 3)
-m = Lightweight3DUNet(dropout_p=0.0); m.load_state_dict(unet_ref.to_torch(sd_np)); m = m.to("cuda:0").set_compute_dtype("bf16").eval()
+m = Lightweight3DUNet(dropout_p=0.0); m.load_state_dict(unet_ref.to_torch(sd_np)); m = m.to("cuda:0").set_compute_dtype("f16").eval()
 for S, B in ((64, 2), (96, 1), (50, 2), (40, 3)):
     x, _ = synth.synth_patches(B, (S, S, S), 7)
     with torch.no_grad():

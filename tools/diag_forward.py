@@ -21,7 +21,7 @@ from light_unet.models import Lightweight3DUNet   # noqa: E402
 def main():
     cases = sys.argv[1:] or ["dws_16", "dws_20_pad", "grouped_16", "dense_16"]
     for name in cases:
-        for dtype in ("f32", "bf16"):
+        for dtype in ("f32", "f16"):
             z, meta, cfg, sd_np, x, t = load_unet_case(name)
             m = Lightweight3DUNet(in_channels=cfg.in_channels, out_channels=cfg.out_channels,
                                   encoder_channels=list(cfg.encoder_channels),

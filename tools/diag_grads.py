@@ -11,7 +11,7 @@ from test_gpu_parity import rel_l2
 from test_gpu_train import run_ours
 
 for name in sys.argv[2:] or ["dws_16"]:
-    dtype = sys.argv[1] if len(sys.argv) > 1 else "bf16"
+    dtype = sys.argv[1] if len(sys.argv) > 1 else "f16"
     z, meta, cfg, sd_np, x, t = load_unet_case(name)
     torch.manual_seed(int(z["train_seed"]))
     masks = unet_ref.draw_dropout_masks(cfg, meta["batch"])

@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "light-3d-unet-front_b200"))
 from light_unet.models import Lightweight3DUNet
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-dtype = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+dtype = sys.argv[2] if len(sys.argv) > 2 else "f16"
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 torch.manual_seed(0)
 m = Lightweight3DUNet(dropout_p=0.0).cuda().set_compute_dtype(dtype).eval()

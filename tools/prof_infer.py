@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "light-3d-unet-front_b200"))
 import torch
 import bench
-inf = bench.make_inferencer("dws", "bf16", torch.device("cuda:0"))
+inf = bench.make_inferencer("dws", "f16", torch.device("cuda:0"))
 from oracle import synth
 vol = torch.from_numpy(synth.synth_volume(bench.VOLUME, seed=42, n_blobs=6)).cuda()
 for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 2):

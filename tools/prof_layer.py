@@ -9,7 +9,7 @@ Cin, Cout, sc, S, B = (int(v) for v in sys.argv[1:6])
 normed = len(sys.argv) > 6 and sys.argv[6] == "1"
 DEV = torch.device("cuda:0")
 torch.manual_seed(0)
-x = torch.randn(B, S, S, S, Cin, device=DEV).to(torch.bfloat16)
+x = torch.randn(B, S, S, S, Cin, device=DEV).to(torch.float16)
 vox = S ** 3
 xf = x.float()
 stats = torch.stack([xf.sum(dim=(1, 2, 3)), (xf * xf).sum(dim=(1, 2, 3))]).double().contiguous()
@@ -18,7 +18,7 @@ xn = nv.norm(stats, gamma, beta, None, 1e-5, 0.01, vox) if normed else nv.norm()
 dw = torch.randn(Cin, 27, device=DEV) / 5
 pw = torch.randn(Cout, Cin, device=DEV) / Cin ** 0.5
 scw = torch.randn(Cout, Cin, device=DEV) / Cin ** 0.5 if sc else None
-t = torch.empty(B, S, S, S, Cout, dtype=torch.bfloat16, device=DEV)
+t = torch.empty(B, S, S, S, Cout, dtype=torch.float16, device=DEV)
 r = torch.empty_like(t) if sc else None
 ts = torch.zeros(2 * B * Cout, dtype=torch.float64, device=DEV)
 rs = torch.zeros_like(ts)

@@ -18,7 +18,7 @@ import light_unet.utils as lu                              # noqa: E402
 
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-    dtype = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+    dtype = sys.argv[2] if len(sys.argv) > 2 else "f16"
     kw = {}
     if len(sys.argv) > 3 and sys.argv[3] == "dense":
         kw = dict(use_depthwise_separable=False, use_grouped=False)

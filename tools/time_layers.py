@@ -21,7 +21,7 @@ LAYERS = [  # name, Cin, Cout, shortcut, size, normed input
 def run(layer, env, iters=10):
     name, Cin, Cout, sc, S, normed = layer
     torch.manual_seed(0)
-    x = torch.randn(B, S, S, S, Cin, device=DEV).to(torch.bfloat16)
+    x = torch.randn(B, S, S, S, Cin, device=DEV).to(torch.float16)
     vox = S ** 3
     xf = x.float()
     stats = torch.stack([xf.sum(dim=(1, 2, 3)), (xf * xf).sum(dim=(1, 2, 3))]).double().contiguous()
@@ -30,7 +30,7 @@ def run(layer, env, iters=10):
     dw = torch.randn(Cin, 27, device=DEV) / 5
     pw = torch.randn(Cout, Cin, device=DEV) / Cin ** 0.5
     scw = torch.randn(Cout, Cin, device=DEV) / Cin ** 0.5 if sc else None
-    t = torch.empty(B, S, S, S, Cout, dtype=torch.bfloat16, device=DEV)
+    t = torch.empty(B, S, S, S, Cout, dtype=torch.float16, device=DEV)
     r = torch.empty_like(t) if sc else None
     ts = torch.zeros(2 * B * Cout, dtype=torch.float64, device=DEV)
     rs = torch.zeros_like(ts)

@@ -9,7 +9,7 @@ from light_unet import _native as nv
 N, Cin, Cout, sc, S, normed = (int(v) for v in sys.argv[1:7])
 DEV = torch.device("cuda:0")
 torch.manual_seed(0)
-x = torch.randn(N, S, S, S, Cin, device=DEV).to(torch.bfloat16)
+x = torch.randn(N, S, S, S, Cin, device=DEV).to(torch.float16)
 vox = S ** 3
 xf = x.float()
 stats = torch.stack([xf.sum(dim=(1, 2, 3)), (xf * xf).sum(dim=(1, 2, 3))]).double().contiguous()
@@ -18,7 +18,7 @@ xn = nv.norm(stats, gamma, beta, None, 1e-5, 0.01, vox) if normed else nv.norm()
 dw = torch.randn(Cin, 27, device=DEV) / 5
 pw = torch.randn(Cout, Cin, device=DEV) / Cin ** 0.5
 scw = torch.randn(Cout, Cin, device=DEV) / Cin ** 0.5 if sc else None
-t = torch.empty(N, S, S, S, Cout, dtype=torch.bfloat16, device=DEV)
+t = torch.empty(N, S, S, S, Cout, dtype=torch.float16, device=DEV)
 r = torch.empty_like(t) if sc else None
 ts = torch.zeros(2 * N * Cout, dtype=torch.float64, device=DEV)
 rs = torch.zeros_like(ts)

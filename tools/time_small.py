@@ -16,7 +16,7 @@ LAYERS = [("down2.c1", 32, 64, True, 12, False), ("down2.c2", 64, 64, False, 12,
 tot = 0.0
 for name, Cin, Cout, sc, S, normed in LAYERS:
     torch.manual_seed(0)
-    x = torch.randn(N, S, S, S, Cin, device=DEV).to(torch.bfloat16)
+    x = torch.randn(N, S, S, S, Cin, device=DEV).to(torch.float16)
     vox = S ** 3
     xf = x.float()
     stats = torch.stack([xf.sum(dim=(1, 2, 3)), (xf * xf).sum(dim=(1, 2, 3))]).double().contiguous()
@@ -25,7 +25,7 @@ for name, Cin, Cout, sc, S, normed in LAYERS:
     dw = torch.randn(Cin, 27, device=DEV) / 5
     pw = torch.randn(Cout, Cin, device=DEV) / Cin ** 0.5
     scw = torch.randn(Cout, Cin, device=DEV) / Cin ** 0.5 if sc else None
-    t = torch.empty(N, S, S, S, Cout, dtype=torch.bfloat16, device=DEV)
+    t = torch.empty(N, S, S, S, Cout, dtype=torch.float16, device=DEV)
     r = torch.empty_like(t) if sc else None
     ts = torch.zeros(2 * N * Cout, dtype=torch.float64, device=DEV)
     rs = torch.zeros_like(ts)

@@ -19,7 +19,7 @@ gamma, beta = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
 xn = nv.norm(stats, gamma, beta, None, 1e-5, 0.01, S ** 3)
 dw = torch.randn(C, 27, device=DEV) / 5
 pw = torch.randn(C, C, device=DEV) / 4
-t = torch.empty(N, S, S, S, C, dtype=torch.bfloat16, device=DEV)
+t = torch.empty(N, S, S, S, C, dtype=torch.float16, device=DEV)
 ts = torch.zeros(2 * N * C, dtype=torch.float64, device=DEV)
 st = nv.stream_ptr(DEV)
 for _ in range(3):
