@@ -153,3 +153,20 @@ class DeviceValidator:
                 sp = resolve_spacing_value(spacings, b, self.target_spacing) if spacings is not None else self.target_spacing
                 self.add_case(image, label, sp, bmask)
         return self.result()
+
+
+def use_device_validation(trainer):
+    """Swap the reference Trainer's validate() (trainer.py:349-445) for the device-resident sweep, in place.
+
+        trainer = Trainer(config)                      # the reference's own class (through l3d_overlay)
+        use_device_validation(trainer)
+        trainer.train()                                # every validation epoch now stays on the GPU
+
+    The replacement keeps the contract -- validate(epoch) -> (0.0, metrics dict with best_threshold / best_recall /
+    best_dsc_macro) -- and reads the same attributes (model, config, val_loader, device)."""
+    validator = DeviceValidator(trainer.model, trainer.config, getattr(trainer, "device", None))
+
+    def validate(epoch):
+        return validator.validate(trainer.val_loader)
+    trainer.validate = validate
+    return validator
