@@ -106,6 +106,10 @@ class DataParallelStep:
         p_snap = [p.detach().clone() for p in params]
         s_snap = {p: {k: v.clone() for k, v in self.optimizer.state.get(p, {}).items() if torch.is_tensor(v)} for p in params}
         rng = torch.cuda.get_rng_state(dev)
+        try:        # warm-up runs on a side stream, the capture on another: the AccumulateGrad stream note does not apply
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+        except AttributeError:
+            pass
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):                              # warm-up: workspaces, optimiser state, NCCL channels
