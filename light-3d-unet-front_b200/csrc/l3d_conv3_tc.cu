@@ -56,6 +56,9 @@ struct C3Args {
     int tmem_cols, nraw, nsets, merge, merged_cx, dbg;
     int tma_split;           // z-slices a halo box is requested in (several TMA operations in flight per box)
     int rot;                 // three rotating 57 KB slots instead of {raw, A0, A1}: see the kernel comment
+    int nabuf;               // operand tiles: 2 (activation of item it+1 under the MMAs of item it) or 1 (half the shared memory: two CTAs per SM)
+    int split2;              // prod only: the (single) raw box is requested as two z-halves with their own barriers -- see the producer warp
+    int prod;                // halo boxes are requested by the dedicated producer warp (12-worker TMA variants) instead of the MMA issuer
     const void *xp; int ldx; // LD (loader warps instead of TMA): the input view / the fp32 tensor u of the rank-1 input
     const float *r1_w;       // rank-1 input (template R1): x[v][c] = r1_w[c] * u[v], u = single-channel fp32 tensor behind the tensor map
 };
@@ -110,18 +113,21 @@ __device__ __forceinline__ void worker_bar_n() { asm volatile("bar.sync 1, %0;" 
 // MMAs of item it-1 have completed -- BEFORE item it is activated -- so warp 0 of the workers requests box it+1 at the top of
 // iteration it and the TMA unit always has the next box queued.  (Measured slower than the fixed roles, see the host side.)
 template <int TZ, bool MERGE, int NWARPS, bool R1 = false, bool LD = false>
-__global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 : 2)) conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, C3Args A) {
+__global__ void __launch_bounds__(NWARPS * 32 + 32 + (NWARPS == 12 && !LD ? 32 : 0), (TZ > 6 || NWARPS > 8 ? 1 : 2)) conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, C3Args A) {
     using G = Geo<TZ>;
-    constexpr int NW = NWARPS * 32, NT = NW + 32;          // worker warps + 1 issuer warp
+    constexpr bool PRODW = NWARPS == 12 && !LD;            // a third role: one warp that only requests halo boxes
+    constexpr int NW = NWARPS * 32, NT = NW + 32 + (PRODW ? 32 : 0);   // worker warps + 1 issuer warp (+ 1 producer warp)
     constexpr int ACT_PER_THREAD = (G::ACT_ITEMS + NW - 1) / NW;
     constexpr int EPG = NWARPS / 4;                        // worker warps per TMEM lane quarter: plane stride of the epilogue
     auto worker_bar = [] { worker_bar_n<NW>(); };
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t s_tma_full[4], s_a_full[2], s_mma_done[2], s_acc_free[2];
+    __shared__ __align__(8) uint64_t s_tma_full[4], s_a_full[2], s_mma_done[2], s_acc_free[2], s_raw_free[4];
     __shared__ uint32_t s_tmem;
     const int Cin = A.Cin, Cout = A.Cout;
     const bool has_sc = A.sc_w != nullptr;
     const int nchunks = Cin / CK, nraw = A.nraw, nsets = A.nsets;
+    const int ns_m = nsets - 1;                                            // nsets is 1 or 2: set of tile tj = tj & ns_m, its use count tj >> ns_m
+    const int ab_m = A.nabuf - 1, ab_sh = A.nabuf == 1 ? 0 : 1;             // operand tile of item it: it & ab_m, its use count: it >> ab_sh
     const uint32_t btile_bytes = (uint32_t)Cout * 3 * 32;                 // one [3*Cout x 16] fp16 operand tile: (chunk, dy, dx)
     const uint32_t bsc_bytes = (uint32_t)Cout * 32;
     const uint32_t b_bytes = (uint32_t)nchunks * 9 * btile_bytes;
@@ -129,7 +135,7 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
     unsigned char *s_raw = smem_raw;                                       // nraw x RAW_STRIDE (TMA destinations)
     const bool rot = !R1 && !LD && A.rot != 0;                             // slots k = 0..2 at smem_raw + k * A_BYTES
     unsigned char *sA = rot ? smem_raw : s_raw + (size_t)nraw * RAW_STRIDE;   // 2 x A_BYTES
-    unsigned char *sB = rot ? smem_raw + 3 * (size_t)G::A_BYTES : sA + 2 * G::A_BYTES;   // [chunk][dy*3+dx][3*Cout x 16]
+    unsigned char *sB = rot ? smem_raw + 3 * (size_t)G::A_BYTES : sA + (size_t)A.nabuf * G::A_BYTES;   // [chunk][dy*3+dx][3*Cout x 16]
     auto slot_x = [](int it) { const int m = it % 3; return m == 0 ? 0 : m == 1 ? 2 : 1; };   // raw slot of item it
     auto slot_y = [](int it) { const int m = it % 3; return m == 0 ? 1 : m == 1 ? 0 : 2; };   // operand slot of item it
     unsigned char *sB2 = sB + b_bytes;                                     // shortcut: [chunk][Cout x 16]
@@ -140,7 +146,7 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == NW / 32) tc::tmem_alloc(&s_tmem, (uint32_t)A.tmem_cols);
     if (tid == 0) {
-        for (int i = 0; i < 4; ++i) tc::mbar_init(&s_tma_full[i], 1);
+        for (int i = 0; i < 4; ++i) { tc::mbar_init(&s_tma_full[i], 1); tc::mbar_init(&s_raw_free[i], NW / 32); }
         for (int i = 0; i < 2; ++i) {
             tc::mbar_init(&s_a_full[i], NW / 32);
             tc::mbar_init(&s_mma_done[i], 1); tc::mbar_init(&s_acc_free[i], NW / 32);
@@ -208,49 +214,103 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
         z0 = b * TZ;
     };
 
+    // the tile after (n, z0, y0, x0) in this CTA's raster order (no divisions: the integer divisions of tile_coord cost the
+    // worker warps ~2 K cycles per tile between the end of an epilogue and the next activation pass -- clock stamps)
+    auto tile_next = [&](int &n, int &z0, int &y0, int &x0) {
+        x0 += TX;
+        if (x0 >= A.W) { x0 = 0; y0 += TY; if (y0 >= A.H) { y0 = 0; z0 += TZ; if (z0 >= A.D) { z0 = 0; ++n; } } }
+    };
+    // bit i set <=> halo coordinate c0 - 1 + i lies inside [0, ext)   (i < len <= 18)
+    auto axis_mask = [](int c0, int len, int ext) -> uint32_t {
+        const int lo = c0 >= 1 ? 0 : 1 - c0, hi = min(len, ext - c0 + 1);
+        return hi > lo ? ((1u << hi) - 1u) & ~((1u << lo) - 1u) : 0u;
+    };
+    // TMA cursor (own copy per warp; used by whichever warp requests the boxes): (tile, chunk) of the next box, advanced
+    // incrementally (no divisions on the issue path)
+    int pf_item = 0, pf_ch = 0, pf_rb = 0, pf_n, pf_z0, pf_y0, pf_x0;
+    tile_coord(tile_begin < tile_end ? tile_begin : 0, pf_n, pf_z0, pf_y0, pf_x0);
+    auto issue_tma = [&]() {
+        if (LD || rot || pf_item >= n_items) return;
+        const int rb = pf_rb;
+        if (tc::elect_one()) {
+            tc::mbar_expect_tx(&s_tma_full[rb], RAW_STRIDE);
+            const int nsl = A.tma_split, zs = G::HZ / nsl;           // planes per slice
+            const uint32_t sl_bytes = (uint32_t)(RAW_STRIDE / nsl);
+            for (int sl = 0; sl < nsl; ++sl) {
+                unsigned char *dst = s_raw + (size_t)rb * RAW_STRIDE + (size_t)sl * sl_bytes;
+                const int zc = pf_z0 - 1 + sl * zs;
+                if (R1) tc::tma_load_4d(dst, &tmap, &s_tma_full[rb], pf_x0 - R1_X0, pf_y0 - 1, zc, pf_n);
+                else if (A.merged_cx) tc::tma_load_4d(dst, &tmap, &s_tma_full[rb], (pf_x0 - 1) * CK, pf_y0 - 1, zc, pf_n);
+                else tc::tma_load_5d(dst, &tmap, &s_tma_full[rb], pf_ch * CK, pf_x0 - 1, pf_y0 - 1, zc, pf_n);
+            }
+        }
+        ++pf_item;
+        if (++pf_rb == nraw) pf_rb = 0;
+        if (++pf_ch == nchunks) {
+            pf_ch = 0;
+            pf_x0 += TX;
+            if (pf_x0 >= A.W) { pf_x0 = 0; pf_y0 += TY; if (pf_y0 >= A.H) { pf_y0 = 0; pf_z0 += TZ; if (pf_z0 >= A.D) { pf_z0 = 0; ++pf_n; } } }
+        }
+    };
+    const bool prod = PRODW && A.prod != 0 && !rot;
+    const bool split2 = prod && !R1 && A.split2 != 0;                      // (host: nraw == 1, even halo height)
+    if (PRODW && warp == NW / 32 + 1) {
+        // =============================== producer warp ===============================
+        // Requests the halo boxes as soon as their raw buffer has been consumed.  With the requests on the MMA issuer's
+        // instruction stream the cp.async.bulk.tensor held that warp for ~1.4 K cycles per box (clock stamps) before the
+        // first MMA of the tile went out, and a second box in flight blocked it for the whole TMA service time.
+        //
+        // split2 (one raw buffer): the box travels as two z-halves with their own {tma_full, raw_free} barriers.  The activation
+        // pass walks the box in z order, so the lower half of box it+1 is requested while the upper half of box it is still being
+        // activated, and the workers start on box it+1 as soon as ITS lower half has landed -- the chain "activation pass ->
+        // request -> box latency" (clock stamps: 2.5 K + 4.4 K cycles of a 7.1 K period) no longer bounds the tile.
+        if (prod && split2) {
+            constexpr int HALF_BYTES = G::RAW_BYTES / 2;
+            for (int i = 0; i < n_items; ++i) {
+                for (int h = 0; h < 2; ++h) {
+                    if (i >= 1) tc::mbar_wait(&s_raw_free[h], (uint32_t)((i - 1) & 1));
+                    if (tc::elect_one()) {
+                        tc::mbar_expect_tx(&s_tma_full[h], HALF_BYTES);
+                        unsigned char *dst = s_raw + (size_t)h * HALF_BYTES;
+                        const int zc = pf_z0 - 1 + h * (G::HZ / 2);
+                        if (A.merged_cx) tc::tma_load_4d(dst, &tmap, &s_tma_full[h], (pf_x0 - 1) * CK, pf_y0 - 1, zc, pf_n);
+                        else tc::tma_load_5d(dst, &tmap, &s_tma_full[h], pf_ch * CK, pf_x0 - 1, pf_y0 - 1, zc, pf_n);
+                    }
+                    __syncwarp();
+                }
+                if (++pf_ch == nchunks) { pf_ch = 0; tile_next(pf_n, pf_z0, pf_y0, pf_x0); }
+            }
+        } else if (prod)
+            for (int i = 0; i < n_items; ++i) {
+                if (i >= nraw) tc::mbar_wait(&s_raw_free[i % nraw], (uint32_t)(((i / nraw) - 1) & 1));
+                issue_tma();
+                __syncwarp();
+            }
+        else if (A.dbg & 256)      // development aid: an otherwise idle warp observes when each box lands
+            for (int i = 0; i < n_items; ++i) {
+                tc::mbar_wait(&s_tma_full[i % nraw], (uint32_t)((i / nraw) & 1));
+                if (blockIdx.x == 0 && i < 128 && lane == 0) g_c3_dbg[i * 8 + 2] = clock64();
+            }
+    } else
     if (warp == NW / 32) {
         // =============================== issuer warp ===============================
         // The whole warp runs this loop converged (every value is warp-uniform, so descriptors and TMEM addresses
         // live in uniform registers); one elected lane issues the TMA loads and the tcgen05.mma / commit.  A
         // single-lane branch around the loop makes ptxas wrap every MMA in an ELECT / R2UR.BROADCAST waterfall.
         const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem);    // TMEM base (from shared memory) as a uniform value
-        // TMA cursor: (tile, chunk) of the next box to request, advanced incrementally (no divisions on the issue path)
-        int pf_item = 0, pf_ch = 0, pf_n, pf_z0, pf_y0, pf_x0;
-        tile_coord(tile_begin < tile_end ? tile_begin : 0, pf_n, pf_z0, pf_y0, pf_x0);
-        auto issue_tma = [&]() {
-            if (LD || rot || pf_item >= n_items) return;
-            const int rb = pf_item % nraw;
-            if (tc::elect_one()) {
-                tc::mbar_expect_tx(&s_tma_full[rb], RAW_STRIDE);
-                const int nsl = A.tma_split, zs = G::HZ / nsl;           // planes per slice
-                const uint32_t sl_bytes = (uint32_t)(RAW_STRIDE / nsl);
-                for (int sl = 0; sl < nsl; ++sl) {
-                    unsigned char *dst = s_raw + (size_t)rb * RAW_STRIDE + (size_t)sl * sl_bytes;
-                    const int zc = pf_z0 - 1 + sl * zs;
-                    if (R1) tc::tma_load_4d(dst, &tmap, &s_tma_full[rb], pf_x0 - R1_X0, pf_y0 - 1, zc, pf_n);
-                    else if (A.merged_cx) tc::tma_load_4d(dst, &tmap, &s_tma_full[rb], (pf_x0 - 1) * CK, pf_y0 - 1, zc, pf_n);
-                    else tc::tma_load_5d(dst, &tmap, &s_tma_full[rb], pf_ch * CK, pf_x0 - 1, pf_y0 - 1, zc, pf_n);
-                }
-            }
-            ++pf_item;
-            if (++pf_ch == nchunks) {
-                pf_ch = 0;
-                pf_x0 += TX;
-                if (pf_x0 >= A.W) { pf_x0 = 0; pf_y0 += TY; if (pf_y0 >= A.H) { pf_y0 = 0; pf_z0 += TZ; if (pf_z0 >= A.D) { pf_z0 = 0; ++pf_n; } } }
-            }
-        };
-        for (int i = 0; i < nraw; ++i) issue_tma();
+        if (!prod)
+            for (int i = 0; i < nraw; ++i) issue_tma();
         const uint32_t idesc1 = tc::idesc_f16_m128(Cout), idesc2 = tc::idesc_f16_m128(2 * Cout), idesc3 = tc::idesc_f16_m128(3 * Cout);
         const uint32_t brow = (uint32_t)(Cout >> 3) * 128 >> 4;     // descriptor units (16 B) per Cout rows of a weight tile
         const uint32_t bstep = btile_bytes >> 4;
         int tj = 0, ch = 0;                       // tile index within this CTA's range, chunk
         for (int it = 0; it < n_items; ++it) {
-            const int buf = it & 1, set = tj % nsets;
-            tc::mbar_wait(&s_a_full[buf], (uint32_t)((it >> 1) & 1));        // operand tile written, raw box consumed
+            const int buf = it & ab_m, set = tj & ns_m;
+            tc::mbar_wait(&s_a_full[buf], (uint32_t)((it >> ab_sh) & 1));        // operand tile written, raw box consumed
             const bool stamp = (A.dbg & 8) && blockIdx.x == 0 && it < 128;
             if (stamp && lane == 0) g_c3_dbg[it * 8 + 5] = clock64();
-            issue_tma();                                                     // refill the raw box just consumed
-            if (ch == 0 && tj >= nsets) tc::mbar_wait(&s_acc_free[set], (uint32_t)(((tj / nsets) - 1) & 1));   // epilogue of tile tj-nsets done
+            if (!prod) issue_tma();                                          // refill the raw box just consumed
+            if (ch == 0 && tj >= nsets) tc::mbar_wait(&s_acc_free[set], (uint32_t)(((tj >> ns_m) - 1) & 1));   // epilogue of tile tj-nsets done
             tc::fence_after_sync();
             if (stamp && lane == 0) g_c3_dbg[it * 8 + 6] = clock64();
             const uint64_t ad0 = tc::smem_desc(sA_u + (rot ? slot_y(it) : buf) * G::A_BYTES, G::PLANE, ROWPITCH);
@@ -331,16 +391,8 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
                 g_off[k] = ai != 0xffffffffu ? (uint32_t)(((hz * A.H + hy) * A.W + hx) * A.ldx * 2 + aq * 16) : 0u;
             }
         }
-        auto issue_copies = [&](int tl, int chunk) {
-            int n, z0, y0, x0;
-            tile_coord(tl, n, z0, y0, x0);
-            uint32_t mz = 0, my = 0, mx = 0;
-#pragma unroll
-            for (int i = 0; i < G::HZ; ++i) mz |= (uint32_t)(z0 + i - 1 >= 0 && z0 + i - 1 < A.D) << i;
-#pragma unroll
-            for (int i = 0; i < HY; ++i) my |= (uint32_t)(y0 + i - 1 >= 0 && y0 + i - 1 < A.H) << i;
-#pragma unroll
-            for (int i = 0; i < HX; ++i) mx |= (uint32_t)(x0 + i - 1 >= 0 && x0 + i - 1 < A.W) << i;
+        auto issue_copies = [&](int n, int z0, int y0, int x0, int chunk) {
+            const uint32_t mz = axis_mask(z0, G::HZ, A.D), my = axis_mask(y0, HY, A.H), mx = axis_mask(x0, HX, A.W);
             const char *org = reinterpret_cast<const char *>(A.xp) +
                               (((((long long)n * A.D + (z0 - 1)) * A.H + (y0 - 1)) * A.W + (x0 - 1)) * A.ldx + chunk * CK) * 2;
 #pragma unroll
@@ -353,7 +405,9 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
                 }
             }
         };
-        if (LD && tile_begin < tile_end) issue_copies(tile_begin, 0);
+        int wn, wz0, wy0, wx0;                                  // this warp's tile cursor
+        tile_coord(tile_begin < tile_end ? tile_begin : 0, wn, wz0, wy0, wx0);
+        if (LD && tile_begin < tile_end) issue_copies(wn, wz0, wy0, wx0, 0);
         // rot: request the halo box of item j = (tile tl, chunk) into slot X(j)  (one lane)
         auto rot_issue = [&](int j, int tl, int chunk) {
             int n, z0, y0, x0;
@@ -386,9 +440,7 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
             }
         };
         // epilogue of tile `tile` (accumulator set `set`): TMEM -> bf16 global + statistics
-        auto epilogue = [&](int tile, int set) {
-            int n, z0, y0, x0;
-            tile_coord(tile, n, z0, y0, x0);
+        auto epilogue = [&](int n, int z0, int y0, int x0, int set) {
             if (n != stat_n) {
                 worker_bar();
                 flush_stats(stat_n);
@@ -413,6 +465,7 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
                     for (int p = em; p < TZ; p += EPG) {
                         float v[16];
                         tc::tmem_ld16(trow + (uint32_t)((a * TZ + p) * Cout + cb), v);
+                        
                         const bool valid = valid_yx && (z0 + p < A.D);
                         uint32_t pk[8];
 #pragma unroll
@@ -435,13 +488,17 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
                             const bool pvalid = __shfl_xor_sync(0xffffffffu, valid ? 1 : 0, 1) != 0;
                             h16 *own = outb + (vox0 + (size_t)p * zstride) * (size_t)ldo + cb + (odd ? 8 : 0);
                             h16 *pe = odd ? own - ldo : own, *po = odd ? own : own + ldo;      // even / odd voxel of the pair
+                            {
                             if (odd ? pvalid : valid) *reinterpret_cast<uint4 *>(pe) = odd ? rcv : h0;
                             if (odd ? valid : pvalid) *reinterpret_cast<uint4 *>(po) = odd ? h1 : rcv;
+                            }
                         }
                     }
+                    {
                     warp_transpose_sum<32>(sv, lane);
                     const int idx = warp_transpose_owner<32>(lane);
                     atomicAdd(&stat[(idx >= 16 ? Cout + idx - 16 : idx) + cb], sv[0]);
+                    }
                 }
             }
             tc::fence_before_sync();
@@ -450,9 +507,12 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
         };
 
         int cur_n = -1, it = 0;
+        int w_rb = 0;                                           // raw box of item it and the parity of its use count (it % nraw, (it / nraw) & 1)
+        uint32_t w_rph = 0;
+        int pn = 0, pz0 = 0, py0 = 0, px0 = 0;                  // the previous tile (its epilogue runs one work item later)
         for (int tile = tile_begin; tile < tile_end; ++tile) {
-            int n, z0, y0, x0;
-            tile_coord(tile, n, z0, y0, x0);
+            const int n = wn, z0 = wz0, y0 = wy0, x0 = wx0;
+            tile_next(wn, wz0, wy0, wx0);                       // (wn, ...) is now the next tile
             if (n != cur_n) {
                 cur_n = n;
                 worker_bar();    // nobody still reads the previous sample's scale/shift
@@ -465,16 +525,10 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
                 worker_bar();
             }
             // validity of the halo coordinates of this tile as per-axis bit masks
-            uint32_t mz = 0, my = 0, mx = 0;
-#pragma unroll
-            for (int i = 0; i < G::HZ; ++i) mz |= (uint32_t)(z0 + i - 1 >= 0 && z0 + i - 1 < A.D) << i;
-#pragma unroll
-            for (int i = 0; i < HY; ++i) my |= (uint32_t)(y0 + i - 1 >= 0 && y0 + i - 1 < A.H) << i;
-#pragma unroll
-            for (int i = 0; i < HX; ++i) mx |= (uint32_t)(x0 + i - 1 >= 0 && x0 + i - 1 < A.W) << i;
+            const uint32_t mz = axis_mask(z0, G::HZ, A.D), my = axis_mask(y0, HY, A.H), mx = axis_mask(x0, HX, A.W);
             const int tj = tile - tile_begin;
             for (int ch = 0; ch < nchunks; ++ch, ++it) {
-                const int buf = it & 1, rb = LD ? 0 : it % nraw;
+                const int buf = it & ab_m, rb = LD ? 0 : w_rb;
                 unsigned char *Ab = sA + (size_t)(rot ? slot_y(it) : buf) * G::A_BYTES;
                 const unsigned char *Rb = rot ? smem_raw + (size_t)slot_x(it) * G::A_BYTES : s_raw + (size_t)rb * RAW_STRIDE;
                 if (rot && warp == 0 && it >= 1 && it + 1 < n_items) {
@@ -500,18 +554,24 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
                     // Y(it) = X(it-1): every worker warp must be done reading the raw box of item it-1
                     if (it >= 1) tc::mbar_wait(&s_a_full[(it - 1) & 1], (uint32_t)(((it - 1) >> 1) & 1));
                 }
-                else tc::mbar_wait(&s_tma_full[rb], (uint32_t)((it / nraw) & 1));          // raw box of this item landed
+                else if (split2) tc::mbar_wait(&s_tma_full[0], (uint32_t)(it & 1));       // lower z-half of this item's box landed
+                else tc::mbar_wait(&s_tma_full[rb], w_rph);                                // raw box of this item landed
                 if (stamp) g_c3_dbg[it * 8 + 0] = clock64();
-                if (it >= 2) tc::mbar_wait(&s_mma_done[buf], (uint32_t)(((it >> 1) - 1) & 1));   // MMAs of item it-2 done: A[buf] free
+                if (it > ab_m) tc::mbar_wait(&s_mma_done[buf], (uint32_t)(((it >> ab_sh) - 1) & 1));   // MMAs of the item that used A[buf] done
                 if (stamp) g_c3_dbg[it * 8 + 1] = clock64();
                 // ---- activation pass: raw bf16 [z][y][x][16] -> fp16 planar [q][z][y][x][8]; the shared-memory loads of a
                 // batch of vectors are issued before any of them is used
                 constexpr int ACT_BATCH = 4;
+                constexpr int HALF_ITEMS = (G::HZ / 2) * HY * HX * 2;      // split2: items (16-byte vectors) of the lower z-half
                 if (!(A.dbg & 1))
 #pragma unroll
                 for (int k0 = 0; k0 < ACT_PER_THREAD; k0 += ACT_BATCH) {
                     uint4 rw[ACT_BATCH];
                     float ru[ACT_BATCH];
+                    // split2: the first batch that reaches into the upper half waits for it
+                    if (!R1 && !LD && (k0 + ACT_BATCH) * NW > HALF_ITEMS && k0 * NW <= HALF_ITEMS) {
+                        if (split2) tc::mbar_wait(&s_tma_full[1], (uint32_t)(it & 1));
+                    }
 #pragma unroll
                     for (int kk = 0; kk < ACT_BATCH; ++kk) {
                         const int k = k0 + kk;
@@ -569,32 +629,38 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
                             }
                         }
                     }
+                    // split2: the batch that holds the last vectors of the lower half has them in registers now
+                    if (!R1 && !LD && (k0 + ACT_BATCH) * NW >= HALF_ITEMS && k0 * NW < HALF_ITEMS) {
+                        if (split2) { __syncwarp(); if (lane == 0) mbar_arrive(&s_raw_free[0]); }
+                    }
                 }
                 tc::fence_async_smem();
                 __syncwarp();
-                if (stamp) g_c3_dbg[it * 8 + 2] = clock64();
-                if (lane == 0) mbar_arrive(&s_a_full[buf]);
+                if (stamp && !(A.dbg & 256)) g_c3_dbg[it * 8 + 2] = clock64();
+                if (lane == 0) { mbar_arrive(&s_a_full[buf]); if (prod) mbar_arrive(&s_raw_free[split2 ? 1 : rb]); }
+                if (++w_rb == nraw) { w_rb = 0; w_rph ^= 1u; }
                 if (LD) {
                     // own raw vectors consumed: fetch the ones of the next work item (they land under the epilogue below)
-                    if (ch + 1 < nchunks) issue_copies(tile, ch + 1);
-                    else if (tile + 1 < tile_end) issue_copies(tile + 1, 0);
+                    if (ch + 1 < nchunks) issue_copies(n, z0, y0, x0, ch + 1);
+                    else if (tile + 1 < tile_end) issue_copies(wn, wz0, wy0, wx0, 0);
                 }
                 // ---- epilogue of the previous tile (its MMAs were issued one work item ago)
                 if (ch == 0 && tile > tile_begin) {
                     const int pit = it - 1;
-                    tc::mbar_wait(&s_mma_done[pit & 1], (uint32_t)((pit >> 1) & 1));
+                    tc::mbar_wait(&s_mma_done[pit & ab_m], (uint32_t)((pit >> ab_sh) & 1));
                     tc::fence_after_sync();
                     if (stamp) g_c3_dbg[it * 8 + 3] = clock64();
-                    epilogue(tile - 1, (tj - 1) % nsets);
+                    epilogue(pn, pz0, py0, px0, (tj - 1) & ns_m);
                     if (stamp) g_c3_dbg[it * 8 + 4] = clock64();
                 }
             }
+            pn = n; pz0 = z0; py0 = y0; px0 = x0;
         }
         if (tile_begin < tile_end) {
             const int pit = it - 1;
-            tc::mbar_wait(&s_mma_done[pit & 1], (uint32_t)((pit >> 1) & 1));
+            tc::mbar_wait(&s_mma_done[pit & ab_m], (uint32_t)((pit >> ab_sh) & 1));
             tc::fence_after_sync();
-            epilogue(tile_end - 1, (tile_end - 1 - tile_begin) % nsets);
+            epilogue(pn, pz0, py0, px0, (tile_end - 1 - tile_begin) & ns_m);
         }
         worker_bar();
         flush_stats(stat_n);
@@ -604,11 +670,11 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32, (TZ >= 6 || NWARPS > 8 ? 1 :
     if (warp == NW / 32) tc::tmem_dealloc(tmem, (uint32_t)A.tmem_cols);
 }
 
-static size_t c3_smem_bytes(int TZ, int Cin, int Cout, bool has_sc, int nraw, bool rank1 = false) {
+static size_t c3_smem_bytes(int TZ, int Cin, int Cout, bool has_sc, int nraw, bool rank1 = false, int nabuf = 2) {
     const size_t nch = Cin / CK;
     const size_t hvox = (size_t)(TZ + 2) * HY * HX;
     const size_t raw = rank1 ? (size_t)(TZ + 2) * HY * R1_BOXW * 4 : hvox * CK * 2, a_bytes = 2 * (hvox * 16 + 64);
-    return (size_t)nraw * raw + 2 * a_bytes + nch * 27 * (size_t)Cout * 32 + (has_sc ? nch * (size_t)Cout * 32 : 0) +
+    return (size_t)nraw * raw + (size_t)nabuf * a_bytes + nch * 27 * (size_t)Cout * 32 + (has_sc ? nch * (size_t)Cout * 32 : 0) +
            sizeof(float) * (2 * (size_t)Cin + 4 * (size_t)Cout);
 }
 
@@ -652,14 +718,31 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
     // buffers fit shared memory; two accumulator sets (epilogue of tile T under the MMAs of tile T+1) when they fit
     const int force_tz = L3D_ENV_INT("L3D_C3_TZ", 0), force_nraw = L3D_ENV_INT("L3D_C3_NRAW", 0), force_sets = L3D_ENV_INT("L3D_C3_SETS", 0);   // tuning / test knobs
     const int nacc = has_sc ? 2 : 1;
-    int TZ = 0, nraw = 0, nsets = 0;
+    int TZ = 0, nraw = 0, nsets = 0, nabuf = 2;
+    // L3D_C3_OCC2: two CTAs per SM, each with ONE raw box and ONE operand tile (<= 112 KB of shared memory, <= 256 TMEM columns,
+    // 8 worker warps): inside a CTA the box latency, the activation pass and the MMAs of a tile are then serial, and the two
+    // CTAs fill each other's gaps
+    const int occ2 = rank1 ? L3D_ENV_INT("L3D_C3_OCC2_R1", 0) : L3D_ENV_INT("L3D_C3_OCC2", 0);
+    if (occ2)
+        for (int tz : {6, 4, 2}) {
+            if (force_tz && tz != force_tz) continue;
+            if (!force_tz && tz > 2 && tz > D) continue;
+            const int cols1 = tz * Cout * nacc;
+            int ns = 2 * cols1 <= 256 ? 2 : 1;
+            if (force_sets == 1 || force_sets == 2) ns = force_sets;
+            if (ns * cols1 > 256) continue;
+            if (c3_smem_bytes(tz, Cin, Cout, has_sc, 1, rank1, 1) + 1024 > 113 * 1024) continue;
+            TZ = tz; nraw = 1; nsets = ns; nabuf = 1;
+            break;
+        }
+    if (TZ == 0)
     for (int tz : {8, 6, 4, 2}) {
         if (force_tz && tz != force_tz) continue;
         if (!force_tz && tz > 2 && tz > D) continue;                 // no taller than the volume
         const int cols1 = tz * Cout * nacc;
         if (cols1 > 512) continue;
         int ns = 2 * cols1 <= 512 ? 2 : 1;
-        if (force_sets) ns = force_sets;
+        if (force_sets == 1 || force_sets == 2) ns = force_sets;
         if (ns * cols1 > 512) continue;
         // raw TMA boxes in flight: a box has microseconds of latency under load, so as many as fit (up to 4)
         int nr = 1;
@@ -677,7 +760,7 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
         break;
     }
     if (TZ == 0) return -1;
-    const size_t smem = c3_smem_bytes(TZ, Cin, Cout, has_sc, nraw, rank1);
+    const size_t smem = c3_smem_bytes(TZ, Cin, Cout, has_sc, nraw, rank1, nabuf);
     const long long tiles = (long long)N * ((D + TZ - 1) / TZ) * ((H + TY - 1) / TY) * ((W + TX - 1) / TX);
     if (tiles >= (1ll << 30)) return -1;
     int cols = 32;
@@ -688,7 +771,25 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
     // (10 voxels) instead of ten 32-B rows (measured: the 5-D box is TMA-issue bound).
     int tma_split = L3D_ENV_INT("L3D_C3_TMASPLIT", 1);   // measured: no effect on the box latency (1, 2, 5 or 10 slices)
     if (tma_split < 1 || (TZ + 2) % tma_split != 0) tma_split = 1;
-    const cuuint32_t box_z = (cuuint32_t)((TZ + 2) / tma_split);
+    // CTAs per SM, worker warps and staging mode (needed here: the producer-warp modes shape the TMA box)
+    int occ = (int)((227 * 1024) / (smem + 1024));
+    if (occ > 3) occ = 3;
+    if (nabuf == 1 && occ > 2) occ = 2;
+    if (occ < 1) occ = 1;
+    if (occ * cols > 512) occ = 512 / cols;
+    // 12 worker warps (3 per scheduler) hide the latency of the activation pass and the epilogue when one CTA owns the SM
+    const int nwarps_env = L3D_ENV_INT("L3D_C3_WARPS", 0);
+    const int nwarps = nwarps_env > 0 ? nwarps_env : (occ == 1 ? 12 : 8);
+    // 1: where only one TMA box fits and a tile has >= 4 channel chunks (measured at 325 windows: 64 -> 32 + shortcut at 24^3
+    // 1033 -> 935 us; slower than TMA on the one- and two-chunk 48^3 layers: 1035 -> 1327 us, 1897 -> 2455 us); 2: wherever
+    // possible; 0: never
+    const int ld_mode = L3D_ENV_INT("L3D_C3_LOADER", 1);
+    const bool use_loader = (ld_mode == 2 || (ld_mode == 1 && nraw == 1 && Cin / CK >= 4)) && (long long)(TZ + 2) * H * W * x->ldc * 2 < (1ll << 31);
+    const bool rot_mode = !rank1 && nabuf == 2 && !(nwarps == 12 && use_loader) && nraw == 1 && tma_split == 1 && L3D_ENV_INT("L3D_C3_ROT", 0) != 0 && smem + 128 <= 226 * 1024;
+    // the producer warp exists in the 12-worker TMA variants
+    const bool prod_mode = nwarps == 12 && !(use_loader && !rank1) && !rot_mode && L3D_ENV_INT("L3D_C3_PROD", 1) != 0;
+    const bool split2 = prod_mode && !rank1 && nraw == 1 && tma_split == 1 && (TZ + 2) % 2 == 0 && L3D_ENV_INT("L3D_C3_SPLIT2", 1) != 0;
+    const cuuint32_t box_z = (cuuint32_t)(split2 ? (TZ + 2) / 2 : (TZ + 2) / tma_split);
     const bool merged_cx = !rank1 && Cin == CK && x->ldc == CK && L3D_ENV_INT("L3D_C3_NOMERGECX", 0) == 0;
     CUtensorMap tmap;
     if (rank1) {
@@ -726,16 +827,16 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
     A.co0 = co0; A.cout_total = cout_total > 0 ? cout_total : Cout;
     A.tmem_cols = cols; A.nraw = nraw; A.nsets = nsets; A.merged_cx = merged_cx ? 1 : 0; A.dbg = L3D_ENV_INT("L3D_C3_DEBUG_SKIP", 0);
     A.r1_w = r1_w; A.tma_split = tma_split; A.xp = x->ptr; A.ldx = x->ldc; A.rot = 0;
+    A.prod = prod_mode ? 1 : 0;
+    A.split2 = split2 ? 1 : 0;
+    A.nabuf = nabuf;
     A.merge = (3 * Cout <= 256 && L3D_ENV_INT("L3D_C3_NOMERGE", 0) == 0) ? 1 : 0;
-    int occ = (int)((227 * 1024) / (smem + 2048));
-    if (occ > 3) occ = 3;
-    if (occ < 1) occ = 1;
-    if (occ * cols > 512) occ = 512 / cols;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     long long grid = (long long)sms * occ;
     if (grid > tiles) grid = tiles;
+    { const int g = L3D_ENV_INT("L3D_C3_GRID", 0); if (g > 0 && g < grid) grid = g; }   // development aid: fewer CTAs than SMs
     size_t smem_launch = smem;
 #define L3D_C3_LAUNCH_L(TZV, MG, NWV, R1V, LDV)                                                                                     \
     do {                                                                                                                    \
@@ -745,7 +846,7 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
             if (e != cudaSuccess) { l3d_set_error("conv3_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 3; } \
             if (dev >= 0 && dev < 64) attr_set_[dev] = true;                                                                                                \
         }                                                                                                                   \
-        conv3_tc_kernel<TZV, MG, NWV, R1V, LDV><<<(unsigned)grid, NWV * 32 + 32, smem_launch, (cudaStream_t)stream>>>(tmap, A); \
+        conv3_tc_kernel<TZV, MG, NWV, R1V, LDV><<<(unsigned)grid, NWV * 32 + 32 + ((NWV) == 12 && !(LDV) ? 32 : 0), smem_launch, (cudaStream_t)stream>>>(tmap, A); \
     } while (0)
     /* thread-private cp.async staging instead of TMA: with 12 worker warps (one CTA per SM), not for the rank-1 input */
 #define L3D_C3_LAUNCH_R(TZV, MG, NWV, R1V)                                                                                          \
@@ -761,19 +862,11 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
         case 4: L3D_C3_LAUNCH(4, MG, NWV); break;         \
         default: L3D_C3_LAUNCH(2, MG, NWV); break;        \
     }
-    // 12 worker warps (3 per scheduler) hide the latency of the activation pass and the epilogue when one CTA owns the SM
-    const int nwarps_env = L3D_ENV_INT("L3D_C3_WARPS", 0);
-    const int nwarps = nwarps_env > 0 ? nwarps_env : (occ == 1 ? 12 : 8);
-    // 1: where only one TMA box fits and a tile has >= 4 channel chunks (measured at 325 windows: 64 -> 32 + shortcut at 24^3
-    // 1033 -> 935 us; slower than TMA on the one- and two-chunk 48^3 layers: 1035 -> 1327 us, 1897 -> 2455 us); 2: wherever
-    // possible; 0: never
-    const int ld_mode = L3D_ENV_INT("L3D_C3_LOADER", 1);
-    const bool use_loader = (ld_mode == 2 || (ld_mode == 1 && nraw == 1 && Cin / CK >= 4)) && (long long)(TZ + 2) * H * W * x->ldc * 2 < (1ll << 31);
     // rotating slots where only one raw box fits (and the box is requested in one piece by TMA).  Off by default: measured
     // SLOWER at 325 windows (16 -> 16 at 48^3: 1101 -> 1187 us, 32 -> 16 + shortcut: 1912 -> 2195 us, 32 -> 32 at 24^3: 406 -> 446 us)
     // -- with the next box streaming in under the MMAs, the TMA writes, the operand reads of the tensor core and the
     // activation pass compete for the same 128 B / clock of shared-memory bandwidth, which is what really bounds the tile
-    if (!rank1 && !(nwarps == 12 && use_loader) && nraw == 1 && tma_split == 1 && L3D_ENV_INT("L3D_C3_ROT", 0) != 0 && smem + 128 <= 226 * 1024) {
+    if (rot_mode) {
         A.rot = 1;
         smem_launch = smem + 128;
     }

@@ -8,6 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "light-3d-unet-front_b200"))
 from light_unet import _native as nv
 
+import json
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 325
 DEV = torch.device("cuda:0")
 LAYERS = [("init.c2*", 16, 16, False, 48, True), ("up3.c1", 32, 16, True, 48, False), ("up3.c2", 16, 16, False, 48, True),
@@ -15,6 +16,8 @@ LAYERS = [("init.c2*", 16, 16, False, 48, True), ("up3.c1", 32, 16, True, 48, Fa
           ("up2.c2", 32, 32, False, 24, True)]
 KNOBS = [{}, {"L3D_C3_WARPS": 8}, {"L3D_C3_LOADER": 0}, {"L3D_C3_LOADER": 2, "L3D_C3_WARPS": 12}, {"L3D_C3_TZ": 4}, {"L3D_C3_TZ": 6},
          {"L3D_C3_TZ": 4, "L3D_C3_WARPS": 8}, {"L3D_C3_SETS": 1}, {"L3D_C3_NRAW": 1}, {"L3D_C3_NRAW": 2}]
+if len(sys.argv) > 2:                      # python tools/sweep_conv3_knobs.py 325 '[{"L3D_C3_PROD": 0}, {}]'
+    KNOBS = json.loads(sys.argv[2])
 
 
 def run(layer, env, iters=5):

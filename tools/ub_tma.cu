@@ -7,9 +7,9 @@
 #include <cuda_runtime.h>
 #include "l3d_tc.cuh"
 
-struct P { int N, D, H, W; int tz, ty, tx; int merged; int nbuf; int box_bytes; int strided; };
+struct P { int N, D, H, W; int tz, ty, tx; int merged; int nbuf; int box_bytes; int strided; int busy; };
 
-__global__ void __launch_bounds__(128) tma_kernel(const __grid_constant__ CUtensorMap tmap, P p, unsigned long long *sink) {
+__global__ void __launch_bounds__(512) tma_kernel(const __grid_constant__ CUtensorMap tmap, P p, unsigned long long *sink) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bar[8];
     const int tid = threadIdx.x;
@@ -30,12 +30,72 @@ __global__ void __launch_bounds__(128) tma_kernel(const __grid_constant__ CUtens
         else tc::tma_load_5d(smem + (size_t)b * p.box_bytes, &tmap, &bar[b], 0, x0 - 1, y0 - 1, z0 - 1, n);
     };
     unsigned long long acc = 0;
+    __shared__ volatile int s_stop;
+    if (tid == 0) s_stop = 0;
+    __syncthreads();
+    if (tid >= 32) {
+        // busy warps: a dependent FMA chain (no memory traffic) until thread 0 is done; p.busy = 1: FMA chain, 2: also polls
+        // shared memory every 64 FMAs only (same thing), 0: exit at once
+        if (p.busy && tid < 32 + 32 * p.busy) {
+            float x = (float)tid;
+            while (!s_stop) { for (int i = 0; i < 256; ++i) x = fmaf(x, 1.0001f, 0.5f); }
+            if (x == 1.2345f) sink[1] = 1;
+        }
+        return;
+    }
     if (tid == 0) {
         for (int i = 0; i < p.nbuf && t0 + i < t1; ++i) issue(t0 + i, i);
         for (int t = t0; t < t1; ++t) {
             const int i = t - t0, b = i % p.nbuf;
             tc::mbar_wait(&bar[b], (uint32_t)((i / p.nbuf) & 1));
             acc += *reinterpret_cast<volatile unsigned long long *>(smem + (size_t)b * p.box_bytes);
+            if (t + p.nbuf < t1) issue(t + p.nbuf, b);
+        }
+        if (acc == 0x1234567) sink[0] = acc;
+        s_stop = 1;
+    }
+}
+
+
+// Variant: the same halo box fetched as one cp.async.bulk (1-D bulk copy, 320 contiguous bytes) per (z, y) row, issued by the 32
+// lanes of one warp; coordinates are clamped into the volume so that every row is a full copy (timing only).
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(tc::smem_u32(dst)), "l"(src), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
+}
+__global__ void __launch_bounds__(128) bulk_kernel(const unsigned char *x, P p, unsigned long long *sink) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar[8];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) for (int i = 0; i < p.nbuf; ++i) tc::mbar_init(&bar[i], 1);
+    __syncthreads();
+    const int tilesX = p.W / p.tx, tilesY = p.H / p.ty, tilesZ = p.D / p.tz;
+    const int tps = tilesX * tilesY * tilesZ, total = tps * p.N;
+    const int per = (total + gridDim.x - 1) / gridDim.x;
+    const int t0 = p.strided ? 0 : blockIdx.x * per, t1 = p.strided ? (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : min(total, t0 + per);
+    const int hz = p.tz + 2, hy = p.ty + 2, hx = p.tx + 2, rows = hz * hy;
+    const uint32_t rowb = (uint32_t)hx * 32;
+    auto issue = [&](int tt, int b) {
+        const int t = p.strided ? (int)blockIdx.x + tt * (int)gridDim.x : tt;
+        const int n = t / tps; int r = t - n * tps;
+        const int x0 = (r % tilesX) * p.tx; r /= tilesX;
+        const int y0 = (r % tilesY) * p.ty; const int z0 = (r / tilesY) * p.tz;
+        if (lane == 0) tc::mbar_expect_tx(&bar[b], p.box_bytes);
+        __syncwarp();
+        const int xs = min(max(x0 - 1, 0), p.W - hx);
+        for (int rr = lane; rr < rows; rr += 32) {
+            const int z = min(max(z0 - 1 + rr / hy, 0), p.D - 1), y = min(max(y0 - 1 + rr % hy, 0), p.H - 1);
+            bulk_g2s(smem + (size_t)b * p.box_bytes + (size_t)rr * rowb, x + ((((size_t)n * p.D + z) * p.H + y) * p.W + xs) * 32, rowb, &bar[b]);
+        }
+    };
+    unsigned long long acc = 0;
+    if (tid < 32) {
+        for (int i = 0; i < p.nbuf && t0 + i < t1; ++i) issue(t0 + i, i);
+        for (int t = t0; t < t1; ++t) {
+            const int i = t - t0, b = i % p.nbuf;
+            tc::mbar_wait(&bar[b], (uint32_t)((i / p.nbuf) & 1));
+            acc += *reinterpret_cast<volatile unsigned long long *>(smem + (size_t)b * p.box_bytes);
+            __syncwarp();
             if (t + p.nbuf < t1) issue(t + p.nbuf, b);
         }
         if (acc == 0x1234567) sink[0] = acc;
@@ -58,17 +118,17 @@ int main() {
     void *x; unsigned long long *sink;
     const size_t bytes = (size_t)N * D * H * W * C * 2;
     cudaMalloc(&x, bytes); cudaMemset(x, 0, bytes);
-    if (getenv("UB_RANDOM")) { fill_random<<<1024, 256>>>((uint32_t *)x, bytes / 4); cudaDeviceSynchronize(); printf("random data\n"); } cudaMalloc(&sink, 8);
+    if (getenv("UB_RANDOM")) { fill_random<<<1024, 256>>>((uint32_t *)x, bytes / 4); cudaDeviceSynchronize(); printf("random data\n"); } cudaMalloc(&sink, 64);
     void *fp = nullptr; cudaDriverEntryPointQueryResult q;
     cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q);
     encode_fn enc = (encode_fn)fp;
     cudaFuncSetAttribute(tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    struct S { int tz, ty, tx; } shapes[] = {{6, 16, 8}};
+    struct S { int tz, ty, tx; } shapes[] = {{8, 16, 8}};
     for (auto s : shapes)
-      for (int strided = 0; strided <= 1; ++strided)
-        for (int merged = 0; merged <= 1; ++merged)
-            for (int nbuf : {1, 2, 3, 4})
-                for (int occ : {1}) {
+      for (int strided = 0; strided <= 0; ++strided)
+        for (int merged = 1; merged <= 1; ++merged)
+            for (int nbuf : {1, 2, 3})
+                for (int occ : {1}) for (int busy : {0, 1, 4, 12}) {
                     const int hz = s.tz + 2, hy = s.ty + 2, hx = s.tx + 2;
                     if (!merged && hx > 256) continue;
                     if (merged && hx * 16 > 256) continue;
@@ -91,21 +151,32 @@ int main() {
                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                     }
                     if (cr != CUDA_SUCCESS) { printf("encode failed %d\n", (int)cr); continue; }
-                    P p{N, D, H, W, s.tz, s.ty, s.tx, merged, nbuf, box_bytes, strided};
+                    P p{N, D, H, W, s.tz, s.ty, s.tx, merged, nbuf, box_bytes, strided, busy};
                     const int grid = 148 * occ;
                     // pad dynamic smem so that exactly `occ` CTAs fit per SM
                     const size_t smem_launch = occ == 1 ? (smem > 120 * 1024 ? smem : 120 * 1024) : (smem > 60 * 1024 ? smem : 60 * 1024);
                     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-                    tma_kernel<<<grid, 128, smem_launch>>>(tm, p, sink);
+                    tma_kernel<<<grid, 448, smem_launch>>>(tm, p, sink);
                     cudaEventRecord(e0);
-                    for (int i = 0; i < 5; ++i) tma_kernel<<<grid, 128, smem_launch>>>(tm, p, sink);
+                    for (int i = 0; i < 5; ++i) tma_kernel<<<grid, 448, smem_launch>>>(tm, p, sink);
                     cudaEventRecord(e1);
                     if (cudaDeviceSynchronize() != cudaSuccess) { printf("CUDA error %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
                     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
                     const double tiles = (double)N * (D / s.tz) * (H / s.ty) * (W / s.tx);
-                    printf("%s tile %dx%dx%-2d %s nbuf %d occ %d box %6d B : %7.1f us  box traffic %5.2f TB/s  unique %5.2f TB/s\n", strided ? "strided" : "ranges ", s.tz, s.ty, s.tx,
-                           merged ? "merged(C*W)" : "5-D        ", nbuf, occ, box_bytes, ms * 1e3, tiles * box_bytes / (ms * 1e-3) / 1e12,
+                    printf("%s tile %dx%dx%-2d %s nbuf %d busy warps %2d box %6d B : %7.1f us  box traffic %5.2f TB/s  unique %5.2f TB/s\n", strided ? "strided" : "ranges ", s.tz, s.ty, s.tx,
+                           merged ? "merged(C*W)" : "5-D        ", nbuf, busy, box_bytes, ms * 1e3, tiles * box_bytes / (ms * 1e-3) / 1e12,
                            (double)bytes / (ms * 1e-3) / 1e12);
+                    if (false) {
+                        cudaFuncSetAttribute(bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+                        bulk_kernel<<<grid, 128, smem_launch>>>((const unsigned char *)x, p, sink);
+                        cudaEventRecord(e0);
+                        for (int i = 0; i < 5; ++i) bulk_kernel<<<grid, 128, smem_launch>>>((const unsigned char *)x, p, sink);
+                        cudaEventRecord(e1);
+                        if (cudaDeviceSynchronize() != cudaSuccess) { printf("CUDA error (bulk) %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
+                        cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
+                        printf("%s tile %dx%dx%-2d %s nbuf %d occ %d box %6d B : %7.1f us  box traffic %5.2f TB/s  (%.0f cycles / box @1.965 GHz)\n", strided ? "strided" : "ranges ", s.tz, s.ty, s.tx,
+                               "bulk rows  ", nbuf, occ, box_bytes, ms * 1e3, tiles * box_bytes / (ms * 1e-3) / 1e12, ms * 1e-3 * 1.965e9 / ((tiles + 147) / 148));
+                    }
                 }
     return 0;
 }
