@@ -160,9 +160,28 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) dwpw_slab_kernel(const 
     };
     if (tid == 0) issue_tma(0);
 
+    // the first two stencil tasks of this thread, decoded once (integer divisions by run-time extents cost a few hundred
+    // cycles each and sat between two CTA barriers of every work item): packed {vox, row}
+    int task_vox[2], task_row[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        int b = (tid + k * NT) >> 3;
+        const int z = b % SZ; b /= SZ;
+        const int y = (b % (H / 2)) * 2;
+        const int xb = b / (H / 2);
+        task_vox[k] = z * PP + y * RP + xb * XT;
+        task_row[k] = (z * H + y) * W + xb * XT;
+    }
+    int cur_n = 0, cur_z0 = 0, cur_ch = 0, cur_sl = 0;
+    if (n_items > 0) item_coord(0, cur_n, cur_z0, cur_ch);
     for (int it = 0; it < n_items; ++it) {
-        int n, z0, ch;
-        item_coord(it, n, z0, ch);
+        const int n = cur_n, z0 = cur_z0, ch = cur_ch;
+        if (++cur_ch == nchunks) {          // coordinates of the next item: one division per slab, none per chunk
+            cur_ch = 0; ++cur_sl;
+            const int slab = (int)blockIdx.x + cur_sl * (int)gridDim.x;
+            cur_n = slab / zslabs;
+            cur_z0 = (slab - cur_n * zslabs) * SZ;
+        }
         const int buf = it & 1;
         // request the next item's raw box: its buffer was consumed by the activation pass of item it-1
         if (tid == 0) issue_tma(it + 1);
@@ -235,12 +254,17 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) dwpw_slab_kernel(const 
             unsigned char *Am = sA + (size_t)buf * nacc * a_bytes;
             const uint32_t kg_off = (uint32_t)(cp >> 2) * MT * 2048 + (uint32_t)(cp & 3) * 4;
 #pragma unroll 1
-            for (int tsk = tid; tsk < ntasks; tsk += NT) {
-                int b = tsk >> 3;
-                const int z = b % SZ; b /= SZ;
-                const int y = (b % (H / 2)) * 2;
-                const int xb = b / (H / 2);
-                const int vox = z * PP + y * RP + xb * XT, row = (z * H + y) * W + xb * XT;
+            int tk = 0;
+            for (int tsk = tid; tsk < ntasks; tsk += NT, ++tk) {
+                int vox, row;
+                if (tk < 2) { vox = tk == 0 ? task_vox[0] : task_vox[1]; row = tk == 0 ? task_row[0] : task_row[1]; }
+                else {
+                    int b = tsk >> 3;
+                    const int z = b % SZ; b /= SZ;
+                    const int y = (b % (H / 2)) * 2;
+                    const int xb = b / (H / 2);
+                    vox = z * PP + y * RP + xb * XT; row = (z * H + y) * W + xb * XT;
+                }
                 // output rows y and y + 1: every input row is loaded once and feeds both
                 float2 acc0[XT], acc1[XT];
 #pragma unroll
@@ -298,14 +322,17 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) dwpw_slab_kernel(const 
             const uint32_t trow = tmem + ((uint32_t)(eq * 32) << 16);
             const int cbn = Cout >> 4;
             const int njobs = nacc * MT * cbn;
+            // job j = (a * MT + m) * cbn + cbi, walked in steps of NG with carries (no divisions)
+            int cbi = eg % cbn, m = (eg / cbn) % MT, a = eg / (cbn * MT);
             for (int j = eg; j < njobs; j += NG) {
-                const int cb = (j % cbn) * 16;
-                const int m = (j / cbn) % MT, a = j / (cbn * MT);
-                if (m * 128 + eq * 32 >= rows_valid) continue;                  // warp-uniform: no valid row in this quarter
-                const int rr = m * 128 + eq * 32 + lane;
+                const int cb = cbi * 16, m_ = m, a_ = a;
+#pragma unroll
+                for (int st = 0; st < NG; ++st) if (++cbi == cbn) { cbi = 0; if (++m == MT) { m = 0; ++a; } }
+                if (m_ * 128 + eq * 32 >= rows_valid) continue;                  // warp-uniform: no valid row in this quarter
+                const int rr = m_ * 128 + eq * 32 + lane;
                 const bool valid = rr < rows_valid;
                 float v[16];
-                tc::tmem_ld16(trow + (uint32_t)((a * MT + m) * Cout + cb), v);
+                tc::tmem_ld16(trow + (uint32_t)((a_ * MT + m_) * Cout + cb), v);
                 float sv[32];
                 uint32_t pk[8];
 #pragma unroll
@@ -317,13 +344,13 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) dwpw_slab_kernel(const 
                     sv[16 + 2 * jj] = r0 * r0; sv[16 + 2 * jj + 1] = r1 * r1;
                 }
                 if (valid) {
-                    h16 *outp = a == 0 ? A.t + (vox0 + rr) * (size_t)A.ldt : A.r + (vox0 + rr) * (size_t)A.ldr;
+                    h16 *outp = a_ == 0 ? A.t + (vox0 + rr) * (size_t)A.ldt : A.r + (vox0 + rr) * (size_t)A.ldr;
                     *reinterpret_cast<uint4 *>(outp + cb) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     *reinterpret_cast<uint4 *>(outp + cb + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
                 }
                 warp_transpose_sum<32>(sv, lane);
                 const int idx = warp_transpose_owner<32>(lane);      // 0..15 sums, 16..31 squares
-                atomicAdd(&s_stat[a * 2 * Cout + (idx >= 16 ? Cout + idx - 16 : idx) + cb], sv[0]);
+                atomicAdd(&s_stat[a_ * 2 * Cout + (idx >= 16 ? Cout + idx - 16 : idx) + cb], sv[0]);
             }
         }
         tc::fence_before_sync();
