@@ -76,12 +76,13 @@ __global__ void __launch_bounds__(NT) merge_bwd_kernel(
 #pragma unroll
         for (int j = 0; j < 12; ++j) acc[j] = 0.f;
     };
-    for (size_t idx = (size_t)blockIdx.x * NT + tid; idx < total; idx += (size_t)gridDim.x * NT) {
-        size_t rem = idx;
-        const int q = (int)(rem % CQ); rem /= CQ;
-        const int cx = (int)(rem % CW); rem /= CW;
-        const int cy = (int)(rem % CH);
-        const int cz = (int)(rem / CH);
+    // per-sample cell index: 32-bit arithmetic (host check) instead of four 64-bit divisions per item
+    for (uint32_t idx = blockIdx.x * NT + tid; idx < (uint32_t)total; idx += gridDim.x * NT) {
+        uint32_t rem = idx;
+        const int q = (int)(rem % (uint32_t)CQ); rem /= (uint32_t)CQ;
+        const int cx = (int)(rem % (uint32_t)CW); rem /= (uint32_t)CW;
+        const int cy = (int)(rem % (uint32_t)CH);
+        const int cz = (int)(rem / (uint32_t)CH);
         if (q != cur_q) { flush(); cur_q = q; }
         const int c = q * 4;
         const bool has_pool = pooled_g != nullptr && cz < PD && cy < PH && cx < PW;
@@ -633,14 +634,17 @@ __global__ void __launch_bounds__(NT, 2) dw_bwd_kernel(
     // spread over the CTAs instead of running back to back in one
     const int nchunks = (C + CK - 1) / CK;
     const long long total_items = total_tiles * nchunks;
-    for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const long long tile = item / nchunks;
-        const int c0 = (int)(item - tile * nchunks) * CK;
-        const int n = (int)(tile / tiles_per_sample);
-        int b = (int)(tile % tiles_per_sample);
-        const int x0 = (b % tilesX) * TX; b /= tilesX;
-        const int y0 = (b % tilesY) * TY; b /= tilesY;
-        const int z0 = b * TZ;
+    // 32-bit work-item arithmetic (the host checks total_items < 2^31): the 64-bit divisions this loop started with cost every
+    // thread a few hundred cycles per 256-voxel item
+    const uint32_t n_items32 = (uint32_t)total_items, tps32 = (uint32_t)tiles_per_sample;
+    for (uint32_t item = blockIdx.x; item < n_items32; item += gridDim.x) {
+        const uint32_t tile = item / (uint32_t)nchunks;
+        const int c0 = (int)(item - tile * (uint32_t)nchunks) * CK;
+        const int n = (int)(tile / tps32);
+        uint32_t b = tile - (uint32_t)n * tps32;
+        const int x0 = (int)(b % (uint32_t)tilesX) * TX; b /= (uint32_t)tilesX;
+        const int y0 = (int)(b % (uint32_t)tilesY) * TY; b /= (uint32_t)tilesY;
+        const int z0 = (int)b * TZ;
         __syncthreads();
         flush_red(cur_n);      // per item: keeps the fp32 shared-memory partial sums short (double beyond this point)
         if (n != cur_n) {
@@ -885,11 +889,11 @@ __global__ void __launch_bounds__(256) dw_bwd_c1_wgrad_kernel(const float *__res
     for (int k = 0; k < 27; ++k) acc[k] = 0.f;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const float g = g_u[i * (size_t)ldgu];
-        const int n = (int)(i / vox_per);
-        size_t rem = i - (size_t)n * vox_per;
-        const int xx = (int)(rem % W); rem /= W;
-        const int yy = (int)(rem % H);
-        const int zz = (int)(rem / H);
+        const int n = (int)((uint32_t)i / (uint32_t)vox_per);            // total < 2^31 (host check)
+        uint32_t rem = (uint32_t)i - (uint32_t)n * (uint32_t)vox_per;
+        const int xx = (int)(rem % (uint32_t)W); rem /= (uint32_t)W;
+        const int yy = (int)(rem % (uint32_t)H);
+        const int zz = (int)(rem / (uint32_t)H);
         float sc, sh;
         norm_scale_shift(xn, N, 1, n, 0, sc, sh);
 #pragma unroll
@@ -1197,6 +1201,7 @@ extern "C" int l3d_merge_bwd(const l3d_act *g_out, const l3d_act *pooled_g, cons
     } else {
         L3D_REQUIRE(has_go || has_pg, "l3d_merge_bwd: no incoming gradient");
         const size_t total = (size_t)((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 4);
+        L3D_REQUIRE(total < (1ull << 31), "l3d_merge_bwd: sample too large for 32-bit cell indices");
         size_t gx = (total + NT - 1) / NT;
         const size_t cap = (148 * 16 + N - 1) / N;
         if (gx > cap) gx = cap;
@@ -1328,6 +1333,7 @@ extern "C" int l3d_dw_bwd(const l3d_act *g_u, const l3d_act *x, const l3d_norm *
     if (C == 1 && !has_gy && g_dw_w != nullptr) {
         const NormDev nd1 = norm_dev(xn);
         const long long nv1 = (long long)N * D * H * W;
+        L3D_REQUIRE(nv1 < (1ll << 31), "l3d_dw_bwd (single channel): too many voxels for 32-bit indices");
         const unsigned grid1 = (unsigned)(nv1 / 256 + 1 < 148 * 8 ? nv1 / 256 + 1 : 148 * 8);
         L3D_DISPATCH_DTYPE(x->dtype, T, {
             dw_bwd_c1_wgrad_kernel<T><<<grid1, 256, 0, (cudaStream_t)stream>>>((const float *)g_u->ptr, g_u->ldc, (const T *)x->ptr, x->ldc, nd1, N, D, H, W, g_dw_w);
@@ -1339,6 +1345,7 @@ extern "C" int l3d_dw_bwd(const l3d_act *g_u, const l3d_act *x, const l3d_norm *
     const size_t smem = dw_bwd_smem(C);
     L3D_REQUIRE(smem <= 227 * 1024, "l3d_dw_bwd: C=%d needs %zu B shared memory", C, smem);
     const long long tiles = (long long)N * ((D + TZ - 1) / TZ) * ((H + TY - 1) / TY) * ((W + TX - 1) / TX) * ((C + CK - 1) / CK);
+    L3D_REQUIRE(tiles < (1ll << 31), "l3d_dw_bwd: too many work items for 32-bit indices");
     long long grid = tiles < 148 * 2 ? tiles : 148 * 2;
     const NormDev nd = norm_dev(xn);
     cudaStream_t st = (cudaStream_t)stream;

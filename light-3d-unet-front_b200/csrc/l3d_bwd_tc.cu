@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
     const uint32_t sGh_u = tc::smem_u32(sGh), sGl_u = tc::smem_u32(sGl), sUh_u = tc::smem_u32(sUh), sUl_u = tc::smem_u32(sUl), sWh_u = tc::smem_u32(sWh), sWl_u = tc::smem_u32(sWl);
 
     const long long tiles_per_sample = (A.vox + TV - 1) / TV;
+    const uint32_t tps32 = (uint32_t)tiles_per_sample;
     const long long total_tiles = tiles_per_sample * A.N;
     const bool has_nt = A.nt.stats != nullptr, u_ident = A.un.stats == nullptr;
     int cur_n = -1;
@@ -129,8 +130,8 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
     float4 pg0[GI > 0 ? GI : 1], pg1[GI > 0 ? GI : 1];
     V8<T> pt[GI > 0 ? GI : 1], pu[UI > 0 ? UI : 1];
     auto prefetch = [&](long long tl) {
-        const int pn = (int)(tl / tiles_per_sample);
-        const long long pv0 = (tl % tiles_per_sample) * TV;
+        const int pn = (int)((uint32_t)tl / tps32);                                  // 32-bit: the host checks tiles < 2^31
+        const long long pv0 = (long long)((uint32_t)tl - (uint32_t)pn * tps32) * TV;
 #pragma unroll
         for (int i = 0; i < GI; ++i) {
             const int item = tid + i * NT, v = item & (TV - 1), q = item >> 7;
@@ -151,8 +152,8 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
     };
     if (GI > 0 && (long long)blockIdx.x < total_tiles) prefetch(blockIdx.x);
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n = (int)(tile / tiles_per_sample);
-        const long long v0 = (tile % tiles_per_sample) * TV;
+        const int n = (int)((uint32_t)tile / tps32);
+        const long long v0 = (long long)((uint32_t)tile - (uint32_t)n * tps32) * TV;
         if (n != cur_n) {
             cur_n = n;
             for (int c = tid; c < Cg; c += NT) {
@@ -323,6 +324,8 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_tmem;
     const int Cg = A.Cg, Cu = A.Cu, gq = Cg >> 3, uq = Cu >> 3;
+    // channel-group counts are powers of two in every configured model: shifts instead of run-time divisions per staged vector
+    const int gq_sh = (gq & (gq - 1)) == 0 ? __ffs(gq) - 1 : -1, uq_sh = (uq & (uq - 1)) == 0 ? __ffs(uq) - 1 : -1;
     const uint32_t tile_bytes = (uint32_t)(2 * gq + 2 * uq) * PLANE;   // [Gh | Gl | Uh | Ul]
     unsigned char *sWh = smem + 2 * tile_bytes;
     unsigned char *sWl = sWh + (size_t)Cg * Cu * 2;
@@ -349,17 +352,18 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
     const uint32_t id_k = tc::idesc_16b_m128(Cu, 1, 1, false, false), id_mn = tc::idesc_16b_m128(Cu, 1, 1, true, true);
     const uint32_t smem_u = tc::smem_u32(smem), sWh_u = tc::smem_u32(sWh), sWl_u = tc::smem_u32(sWl);
     const long long tiles_per_sample = (A.vox + TV - 1) / TV;
+    const uint32_t tps32 = (uint32_t)tiles_per_sample;
     const long long total_tiles = tiles_per_sample * A.N;
     const long long per = (total_tiles + gridDim.x - 1) / gridDim.x;
     const long long t_begin = (long long)blockIdx.x * per, t_end = t_begin + per < total_tiles ? t_begin + per : total_tiles;
     float4 pg0[GI], pg1[GI];
     V8<T> pt[GI], pu[UI];
     auto prefetch = [&](long long tl) {
-        const int pn = (int)(tl / tiles_per_sample);
-        const long long pv0 = (tl % tiles_per_sample) * TV;
+        const int pn = (int)((uint32_t)tl / tps32);                                  // 32-bit: the host checks tiles < 2^31
+        const long long pv0 = (long long)((uint32_t)tl - (uint32_t)pn * tps32) * TV;
 #pragma unroll
         for (int i = 0; i < GI; ++i) {
-            const int item = tid + i * NT, q = item % gq, v = item / gq;      // channel group fastest: a warp reads contiguous voxel rows
+            const int item = tid + i * NT, q = gq_sh >= 0 ? (item & (gq - 1)) : item % gq, v = gq_sh >= 0 ? (item >> gq_sh) : item / gq;      // channel group fastest: a warp reads contiguous voxel rows
             if (pv0 + v < A.vox) {
                 const size_t gv = (size_t)pn * A.vox + pv0 + v;
                 pg0[i] = *reinterpret_cast<const float4 *>(A.gz + gv * (size_t)A.ldg + q * 8);
@@ -370,15 +374,15 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
         if (has_gw) {
 #pragma unroll
             for (int i = 0; i < UI; ++i) {
-                const int item = tid + i * NT, q = item % uq, v = item / uq;
+                const int item = tid + i * NT, q = uq_sh >= 0 ? (item & (uq - 1)) : item % uq, v = uq_sh >= 0 ? (item >> uq_sh) : item / uq;
                 if (pv0 + v < A.vox) pu[i].load(Au + ((size_t)pn * A.vox + pv0 + v) * (size_t)A.ldu + q * 8);
             }
         }
     };
     int cur_n = -1;
     auto stage = [&](long long tl, int b) {          // registers (tile tl) -> tile buffer b
-        const int n = (int)(tl / tiles_per_sample);
-        const long long v0 = (tl % tiles_per_sample) * TV;
+        const int n = (int)((uint32_t)tl / tps32);
+        const long long v0 = (long long)((uint32_t)tl - (uint32_t)n * tps32) * TV;
         if (n != cur_n) {                              // uniform over the CTA; the previous stage() ended before a CTA barrier
             cur_n = n;
             for (int c = tid; c < Cg; c += NT) {
@@ -391,7 +395,7 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
         unsigned char *sGh = smem + (size_t)b * tile_bytes, *sGl = sGh + (size_t)gq * PLANE, *sUh = sGl + (size_t)gq * PLANE, *sUl = sUh + (size_t)uq * PLANE;
 #pragma unroll
         for (int i = 0; i < GI; ++i) {
-            const int item = tid + i * NT, q = item % gq, v = item / gq;
+            const int item = tid + i * NT, q = gq_sh >= 0 ? (item & (gq - 1)) : item % gq, v = gq_sh >= 0 ? (item >> gq_sh) : item / gq;
             uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
             if (v0 + v < A.vox) {
                 float g[8] = {pg0[i].x, pg0[i].y, pg0[i].z, pg0[i].w, pg1[i].x, pg1[i].y, pg1[i].z, pg1[i].w};
@@ -410,7 +414,7 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
         if (has_gw) {
 #pragma unroll
             for (int i = 0; i < UI; ++i) {
-                const int item = tid + i * NT, q = item % uq, v = item / uq;
+                const int item = tid + i * NT, q = uq_sh >= 0 ? (item & (uq - 1)) : item % uq, v = uq_sh >= 0 ? (item >> uq_sh) : item / uq;
                 store_u_split(sUh, sUl, (size_t)q * PLANE + (size_t)v * 16, pu[i], v0 + v < A.vox);
             }
         }
@@ -460,8 +464,8 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
         phase ^= 1u;
         tc::fence_after_sync();
         if (has_gu) {
-            const int n = (int)(tile / tiles_per_sample);
-            const long long v0 = (tile % tiles_per_sample) * TV;
+            const int n = (int)((uint32_t)tile / tps32);
+            const long long v0 = (long long)((uint32_t)tile - (uint32_t)n * tps32) * TV;
             const int v = (warp & 3) * 32 + lane;
             const bool ok = v0 + v < A.vox;
             float *op = A.g_u + ((size_t)n * A.vox + v0 + (ok ? v : 0)) * (size_t)A.ldgu;
@@ -545,6 +549,7 @@ int l3d_pw_bwd_tc(const l3d_act *gz, const l3d_act *t, const l3d_norm *nt, const
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = ((vox + TV - 1) / TV) * N;
+    if (tiles >= (1ll << 31)) return -1;          // 32-bit tile arithmetic in the kernels
     // pipelined variant: two tile buffers + weights + tables, and the MN-major over-read of the second buffer's G planes
     size_t smem_p = 2 * (size_t)(2 * (Cg / 8) + 2 * (Cu / 8)) * PLANE + 2 * (size_t)Cg * Cu * 2 + sizeof(float) * 3 * (size_t)Cg;
     {
@@ -692,11 +697,11 @@ __global__ void __launch_bounds__(NT) convt_bwd_tc_kernel(CtTcArgs A) {
                 const int v = item & (TV - 1), q = item >> 7;
                 uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
                 if (v0 + v < nvox) {
-                    long long rem = v0 + v;
-                    const int ix = (int)(rem % A.w); rem /= A.w;
-                    const int iy = (int)(rem % A.h); rem /= A.h;
-                    const int iz = (int)(rem % A.d);
-                    const int n = (int)(rem / A.d);
+                    uint32_t rem = (uint32_t)(v0 + v);             // nvox < 2^31 (host check): 32-bit divisions
+                    const int ix = (int)(rem % (uint32_t)A.w); rem /= (uint32_t)A.w;
+                    const int iy = (int)(rem % (uint32_t)A.h); rem /= (uint32_t)A.h;
+                    const int iz = (int)(rem % (uint32_t)A.d);
+                    const int n = (int)(rem / (uint32_t)A.d);
                     const int Z = A.oz + 2 * iz + (tap >> 2), Y = A.oy + 2 * iy + ((tap >> 1) & 1), X = A.ox + 2 * ix + (tap & 1);
                     if (Z >= 0 && Z < A.OD && Y >= 0 && Y < A.OH && X >= 0 && X < A.OW) {
                         const float *gp = A.g + ((((size_t)n * A.OD + Z) * A.OH + Y) * A.OW + X) * (size_t)A.ldg + q * 8;
@@ -838,6 +843,7 @@ int l3d_convt_bwd_tc(const l3d_act *g_out, int OD, int OH, int OW, int oz, int o
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int npass = 8 / TP;
     const long long tiles = ((long long)N * d * h * w_ + TV - 1) / TV;
+    if (tiles >= (1ll << 24)) return -1;          // 32-bit voxel indices in the kernel
     long long gx = ((long long)sms * occ + npass - 1) / npass;
     if (gx > tiles) gx = tiles;
     if (gx < 1) gx = 1;

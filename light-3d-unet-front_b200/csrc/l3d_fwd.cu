@@ -466,13 +466,15 @@ __global__ void __launch_bounds__(256, 3) merge_fwd_kernel(
     __syncthreads();
     const int CD = (D + 1) / 2, CH = (H + 1) / 2, CW = (W + 1) / 2, CQ = C / V;
     const int PD = D / 2, PH = H / 2, PW = W / 2;
-    const size_t total = (size_t)CD * CH * CW * CQ;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        size_t rem = idx;
-        const int q = (int)(rem % CQ); rem /= CQ;
-        const int cx = (int)(rem % CW); rem /= CW;
-        const int cy = (int)(rem % CH);
-        const int cz = (int)(rem / CH);
+    // per-sample cell count (grid.y = sample): 32-bit index arithmetic (the host checks the range) -- the 64-bit divisions
+    // this loop started with are ~100 instructions each, ahead of the first load
+    const uint32_t total = (uint32_t)CD * CH * CW * CQ;
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        uint32_t rem = idx;
+        const int q = (int)(rem % (uint32_t)CQ); rem /= (uint32_t)CQ;
+        const int cx = (int)(rem % (uint32_t)CW); rem /= (uint32_t)CW;
+        const int cy = (int)(rem % (uint32_t)CH);
+        const int cz = (int)(rem / (uint32_t)CH);
         const int c = q * V;
         // scale / shift tables are read from shared memory where they are used (24 registers less: one more CTA per SM)
         const float *sc2 = s_sc2 + c, *sh2 = s_sh2 + c, *scr = s_scr + c;
@@ -1423,6 +1425,7 @@ extern "C" int l3d_merge_fwd(const l3d_act *t2, const l3d_norm *n2, const l3d_ac
         L3D_REQUIRE(vec_ok(t2) && vec_ok(r) && (!has_out || vec_ok(out)) && (!has_pool || vec_ok(pooled)),
                     "l3d_merge_fwd: views must be 16-byte aligned with C a multiple of %d", V);
         const size_t total = (size_t)((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2) * (C / V);
+        L3D_REQUIRE(total < (1ull << 31), "l3d_merge_fwd: sample too large for 32-bit cell indices");
         size_t blocks = (total + 255) / 256;
         const size_t cap = (148 * 32 + N - 1) / N;
         if (blocks > cap) blocks = cap;
@@ -1497,6 +1500,7 @@ extern "C" int l3d_merge_fwd_rank1(const l3d_act *t2, const l3d_norm *n2, const 
                 (!has_pool || (vec_ok(pooled) && pooled->C == C && pooled->dtype == t2->dtype)), "l3d_merge_fwd_rank1: bad views");
     const NormDev d2 = norm_dev(n2), dr = norm_dev(nr);
     const size_t total = (size_t)((D + 1) / 2) * ((H + 1) / 2) * ((W + 1) / 2) * (C / V);
+    L3D_REQUIRE(total < (1ull << 31), "l3d_merge_fwd_rank1: sample too large for 32-bit cell indices");
     size_t blocks = (total + 255) / 256;
     const size_t cap = (148 * 32 + N - 1) / N;
     if (blocks > cap) blocks = cap;

@@ -125,12 +125,15 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
     const long long tiles_per_sample = (long long)tilesX * tilesY * tilesZ;
     const long long total_tiles = tiles_per_sample * A.N;
     const int nchunks = Cin / CK;
+    // 32-bit arithmetic (the host refuses >= 2^30 tiles): 64-bit divisions are ~100 instructions each, per thread and tile
+    const uint32_t tps32 = (uint32_t)tiles_per_sample;
     auto tile_coord = [&](long long tile, int &n, int &z0, int &y0, int &x0) {
-        n = (int)(tile / tiles_per_sample);
-        int b = (int)(tile % tiles_per_sample);
-        x0 = (b % tilesX) * TX; b /= tilesX;
-        y0 = (b % tilesY) * TY; b /= tilesY;
-        z0 = b * TZ;
+        const uint32_t t32 = (uint32_t)tile;
+        n = (int)(t32 / tps32);
+        uint32_t b = t32 - (uint32_t)n * tps32;
+        x0 = (int)(b % (uint32_t)tilesX) * TX; b /= (uint32_t)tilesX;
+        y0 = (int)(b % (uint32_t)tilesY) * TY; b /= (uint32_t)tilesY;
+        z0 = (int)b * TZ;
     };
     // activation-pass role: fixed set of 8-channel vectors of the raw box (same for every work item)
     uint32_t act_item[ACT_PER_THREAD];
@@ -470,6 +473,7 @@ int l3d_dwpw_fwd_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = (long long)N * ((D + TZ - 1) / TZ) * ((H + TY - 1) / TY) * ((W + TX - 1) / TX);
+    if (tiles >= (1ll << 30)) return -1;
     long long grid = (long long)sms * occ;
     if (grid > tiles) grid = tiles;
     if (f32) dwpw_tc_kernel<float><<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(tmap, A);
@@ -534,12 +538,13 @@ __global__ void __launch_bounds__(NT) convt_tc_kernel(CtArgs A) {
     const long long nvox = (long long)A.N * A.d * A.h * A.w;
     const long long ntiles = (nvox + 127) / 128;
     const int kq = Cin >> 3;
+    const int kq_sh = (kq & (kq - 1)) == 0 ? __ffs(kq) - 1 : -1;      // Cin / 8 is a power of two in every configured model: shifts instead of divisions
     const T *xin = reinterpret_cast<const T *>(A.x);
     auto load_a = [&](long long tile, int buf) {
         unsigned char *dst = sA + (size_t)buf * NP * a_bytes;
         const long long v0 = tile * 128;
         for (int item = tid; item < 128 * kq; item += NT) {
-            const int q = item % kq, v = item / kq;
+            const int q = kq_sh >= 0 ? (item & (kq - 1)) : item % kq, v = kq_sh >= 0 ? (item >> kq_sh) : item / kq;
             uint4 o = make_uint4(0u, 0u, 0u, 0u), ol = o;
             if (v0 + v < nvox) {
                 const T *src = xin + (size_t)(v0 + v) * A.ldx + q * 8;
@@ -591,11 +596,11 @@ __global__ void __launch_bounds__(NT) convt_tc_kernel(CtArgs A) {
             // tcgen05.ld is warp-collective (.sync.aligned): every lane runs the same loads, only the stores are predicated
             const long long gv = tile * 128 + erow;
             const bool row_ok = gv < nvox;
-            long long rem = row_ok ? gv : 0;
-            const int ix = (int)(rem % A.w); rem /= A.w;
-            const int iy = (int)(rem % A.h); rem /= A.h;
-            const int iz = (int)(rem % A.d);
-            const int n = (int)(rem / A.d);
+            uint32_t rem = row_ok ? (uint32_t)gv : 0u;      // nvox < 2^31 (host check)
+            const int ix = (int)(rem % (uint32_t)A.w); rem /= (uint32_t)A.w;
+            const int iy = (int)(rem % (uint32_t)A.h); rem /= (uint32_t)A.h;
+            const int iz = (int)(rem % (uint32_t)A.d);
+            const int n = (int)(rem / (uint32_t)A.d);
             const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
             for (int tp = tap0; tp < tap0 + 4; ++tp) {
                 const int Z = A.oz + 2 * iz + (tp >> 2), Y = A.oy + 2 * iy + ((tp >> 1) & 1), X = A.ox + 2 * ix + (tp & 1);
@@ -654,6 +659,7 @@ int l3d_convt_fwd_tc(const l3d_act *x, int N, int d, int h, int w_, const float 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const long long tiles = ((long long)N * d * h * w_ + 127) / 128;
+    if (tiles >= (1ll << 24)) return -1;             // 32-bit voxel indices in the kernel
     long long grid = (long long)sms * occ;
     if (grid > tiles) grid = tiles;
     if (f32) convt_tc_kernel<float><<<(unsigned)grid, NT, smem, (cudaStream_t)stream>>>(A);
