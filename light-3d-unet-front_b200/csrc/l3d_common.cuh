@@ -186,6 +186,25 @@ __device__ __forceinline__ void warp_transpose_sum(float (&vals)[NV], int lane) 
         }
     }
 }
+// The same over the 16 lanes that share this lane's parity (lane bit 0 is never crossed): NV = 16 values per lane, on return
+// vals[0] of lane l is the total, over the lanes of l's parity, of value index warp_transpose_owner<16>(l).  15 shuffles.
+__device__ __forceinline__ void warp_transpose_sum_parity16(float (&vals)[16], int lane) {
+    int cnt = 16;
+#pragma unroll
+    for (int s = 16; s >= 2; s >>= 1) {
+        const int h = cnt >> 1;
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i < h) {
+                const float send = up ? vals[i] : vals[i + h];
+                const float keep = up ? vals[i + h] : vals[i];
+                vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+            }
+        }
+        cnt = h;
+    }
+}
 // index owned by `lane` after warp_transpose_sum<NV>: the exchange steps consumed the top log2(NV)
 // lane bits, most significant first, each selecting the upper half.
 template <int NV>

@@ -458,46 +458,50 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32 + (NWARPS == 12 && !LD ? 32 :
                 const int ldo = a == 0 ? A.ldt : A.ldr;
                 float *stat = s_stat + a * 2 * Cout;
                 for (int cb = 0; cb < Cout; cb += 16) {
-                    float sv[32];
+                    // Lanes 2j / 2j+1 hold x-adjacent voxels.  After the half swap below the even lane owns channels 0-7 and the odd
+                    // lane channels 8-15 of BOTH voxels -- so that every store instruction fills whole 32-byte sectors, and so that a
+                    // lane accumulates the statistics of 8 channels only (16 accumulators instead of 32: room for the TMEM load of
+                    // the next plane to be in flight under the work on the current one).
+                    float sv[16];                  // [0..7] sums, [8..15] sums of squares of channels (odd ? 8 : 0) + j
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) sv[j] = 0.f;
+                    for (int j = 0; j < 16; ++j) sv[j] = 0.f;
+                    const bool odd = (lane & 1) != 0;
+                    uint32_t vr[16];
+                    if (em < TZ) tc::tmem_ld16_issue(trow + (uint32_t)((a * TZ + em) * Cout + cb), vr);
+                    // this lane's 16-byte store slot in plane em, advanced by EPG planes per step (no 64-bit multiplies in the loop)
+                    h16 *own = outb + (vox0 + (size_t)em * zstride) * (size_t)ldo + cb + (odd ? 8 : 0);
+                    const size_t own_step = (size_t)EPG * zstride * (size_t)ldo;
+                    const int pair_off = odd ? -ldo : ldo;                              // the other voxel of the lane pair
 #pragma unroll 1
-                    for (int p = em; p < TZ; p += EPG) {
-                        float v[16];
-                        tc::tmem_ld16(trow + (uint32_t)((a * TZ + p) * Cout + cb), v);
-                        
+                    for (int p = em; p < TZ; p += EPG, own += own_step) {
+                        tc::tmem_ld_wait16(vr);
                         const bool valid = valid_yx && (z0 + p < A.D);
                         uint32_t pk[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            pk[j] = valid ? pack_h16x2(v[2 * j], v[2 * j + 1]) : 0u;
-                            const float r0 = h16_lo(pk[j]);
-                            const float r1 = h16_hi(pk[j]);
-                            sv[2 * j] += r0; sv[2 * j + 1] += r1;
-                            sv[16 + 2 * j] = fmaf(r0, r0, sv[16 + 2 * j]); sv[16 + 2 * j + 1] = fmaf(r1, r1, sv[16 + 2 * j + 1]);
-                        }
-                        {
-                            // lanes 2j / 2j+1 hold x-adjacent voxels: swap halves so that each store instruction fills whole
-                            // 32-byte sectors (even lane: channels 0-7, odd lane: channels 8-15 of the same voxel)
-                            const bool odd = (lane & 1) != 0;
-                            const uint4 h0 = make_uint4(pk[0], pk[1], pk[2], pk[3]), h1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-                            const uint4 snd = odd ? h0 : h1;
-                            uint4 rcv;
-                            rcv.x = __shfl_xor_sync(0xffffffffu, snd.x, 1); rcv.y = __shfl_xor_sync(0xffffffffu, snd.y, 1);
-                            rcv.z = __shfl_xor_sync(0xffffffffu, snd.z, 1); rcv.w = __shfl_xor_sync(0xffffffffu, snd.w, 1);
-                            const bool pvalid = __shfl_xor_sync(0xffffffffu, valid ? 1 : 0, 1) != 0;
-                            h16 *own = outb + (vox0 + (size_t)p * zstride) * (size_t)ldo + cb + (odd ? 8 : 0);
-                            h16 *pe = odd ? own - ldo : own, *po = odd ? own : own + ldo;      // even / odd voxel of the pair
-                            {
-                            if (odd ? pvalid : valid) *reinterpret_cast<uint4 *>(pe) = odd ? rcv : h0;
-                            if (odd ? valid : pvalid) *reinterpret_cast<uint4 *>(po) = odd ? h1 : rcv;
-                            }
+                        for (int j = 0; j < 8; ++j) pk[j] = valid ? pack_h16x2(__uint_as_float(vr[2 * j]), __uint_as_float(vr[2 * j + 1])) : 0u;
+                        if (p + EPG < TZ) tc::tmem_ld16_issue(trow + (uint32_t)((a * TZ + p + EPG) * Cout + cb), vr);
+                        const uint4 h0 = make_uint4(pk[0], pk[1], pk[2], pk[3]), h1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        const uint4 snd = odd ? h0 : h1, mine = odd ? h1 : h0;
+                        uint4 rcv;
+                        rcv.x = __shfl_xor_sync(0xffffffffu, snd.x, 1); rcv.y = __shfl_xor_sync(0xffffffffu, snd.y, 1);
+                        rcv.z = __shfl_xor_sync(0xffffffffu, snd.z, 1); rcv.w = __shfl_xor_sync(0xffffffffu, snd.w, 1);
+                        const bool pvalid = __shfl_xor_sync(0xffffffffu, valid ? 1 : 0, 1) != 0;
+                        if (valid) *reinterpret_cast<uint4 *>(own) = mine;                   // own voxel, own channel half
+                        if (pvalid) *reinterpret_cast<uint4 *>(own + pair_off) = rcv;       // the partner's voxel, same channel half
+                        // statistics of the stored (fp16-rounded) values; an invalid voxel was packed as zeros
+                        const uint32_t mw[4] = {mine.x, mine.y, mine.z, mine.w}, rw4[4] = {rcv.x, rcv.y, rcv.z, rcv.w};
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) {
+                            const float m0 = h16_lo(mw[w]), m1 = h16_hi(mw[w]), q0 = h16_lo(rw4[w]), q1 = h16_hi(rw4[w]);
+                            sv[2 * w] += m0 + q0; sv[2 * w + 1] += m1 + q1;
+                            sv[8 + 2 * w] = fmaf(m0, m0, fmaf(q0, q0, sv[8 + 2 * w])); sv[8 + 2 * w + 1] = fmaf(m1, m1, fmaf(q1, q1, sv[8 + 2 * w + 1]));
                         }
                     }
+                    warp_transpose_sum_parity16(sv, lane);
                     {
-                    warp_transpose_sum<32>(sv, lane);
-                    const int idx = warp_transpose_owner<32>(lane);
-                    atomicAdd(&stat[(idx >= 16 ? Cout + idx - 16 : idx) + cb], sv[0]);
+                        const int idx = warp_transpose_owner<16>(lane);      // bits 16, 8, 4, 2 of the lane select the value index
+                        const int chn = (odd ? 8 : 0) + (idx & 7);
+                        atomicAdd(&stat[(idx >= 8 ? Cout : 0) + chn + cb], sv[0]);
                     }
                 }
             }
