@@ -628,7 +628,9 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32 + (NWARPS == 12 && !LD ? 32 :
                                     o = make_uint4(*reinterpret_cast<uint32_t *>(&h[0]), *reinterpret_cast<uint32_t *>(&h[1]),
                                                    *reinterpret_cast<uint32_t *>(&h[2]), *reinterpret_cast<uint32_t *>(&h[3]));
                                 }
-                                if (!((mx >> hx) & (my >> hy) & (mz >> hz) & 1u)) o = make_uint4(0u, 0u, 0u, 0u);   // conv zero padding
+                                // conv zero padding of the ACTIVATED tensor.  An identity-norm input needs no test: TMA (and the zero-size
+                                // cp.async of the loader mode) already delivered zeros for the voxels outside the volume
+                                if ((R1 || !ident) && !((mx >> hx) & (my >> hy) & (mz >> hz) & 1u)) o = make_uint4(0u, 0u, 0u, 0u);
                                 *reinterpret_cast<uint4 *>(Ab + (size_t)aq * G::PLANE + (size_t)(item >> 1) * 16) = o;
                             }
                         }
