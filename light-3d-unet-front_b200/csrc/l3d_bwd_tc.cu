@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
     __shared__ uint32_t s_tmem;
     const int Cg = A.Cg, Cu = A.Cu, gq = Cg >> 3, uq = Cu >> 3;
     // channel-group counts are powers of two in every configured model: shifts instead of run-time divisions per staged vector
-    const int gq_sh = (gq & (gq - 1)) == 0 ? __ffs(gq) - 1 : -1, uq_sh = (uq & (uq - 1)) == 0 ? __ffs(uq) - 1 : -1;
+    const int gq_sh = __ffs(gq) - 1, uq_sh = __ffs(uq) - 1;      // powers of two (host check)
     const uint32_t tile_bytes = (uint32_t)(2 * gq + 2 * uq) * PLANE;   // [Gh | Gl | Uh | Ul]
     unsigned char *sWh = smem + 2 * tile_bytes;
     unsigned char *sWl = sWh + (size_t)Cg * Cu * 2;
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
         const long long pv0 = (long long)((uint32_t)tl - (uint32_t)pn * tps32) * TV;
 #pragma unroll
         for (int i = 0; i < GI; ++i) {
-            const int item = tid + i * NT, q = gq_sh >= 0 ? (item & (gq - 1)) : item % gq, v = gq_sh >= 0 ? (item >> gq_sh) : item / gq;      // channel group fastest: a warp reads contiguous voxel rows
+            const int item = tid + i * NT, q = item & (gq - 1), v = item >> gq_sh;      // channel group fastest: a warp reads contiguous voxel rows
             if (pv0 + v < A.vox) {
                 const size_t gv = (size_t)pn * A.vox + pv0 + v;
                 pg0[i] = *reinterpret_cast<const float4 *>(A.gz + gv * (size_t)A.ldg + q * 8);
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
         if (has_gw) {
 #pragma unroll
             for (int i = 0; i < UI; ++i) {
-                const int item = tid + i * NT, q = uq_sh >= 0 ? (item & (uq - 1)) : item % uq, v = uq_sh >= 0 ? (item >> uq_sh) : item / uq;
+                const int item = tid + i * NT, q = item & (uq - 1), v = item >> uq_sh;
                 if (pv0 + v < A.vox) pu[i].load(Au + ((size_t)pn * A.vox + pv0 + v) * (size_t)A.ldu + q * 8);
             }
         }
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
         unsigned char *sGh = smem + (size_t)b * tile_bytes, *sGl = sGh + (size_t)gq * PLANE, *sUh = sGl + (size_t)gq * PLANE, *sUl = sUh + (size_t)uq * PLANE;
 #pragma unroll
         for (int i = 0; i < GI; ++i) {
-            const int item = tid + i * NT, q = gq_sh >= 0 ? (item & (gq - 1)) : item % gq, v = gq_sh >= 0 ? (item >> gq_sh) : item / gq;
+            const int item = tid + i * NT, q = item & (gq - 1), v = item >> gq_sh;
             uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
             if (v0 + v < A.vox) {
                 float g[8] = {pg0[i].x, pg0[i].y, pg0[i].z, pg0[i].w, pg1[i].x, pg1[i].y, pg1[i].z, pg1[i].w};
@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
         if (has_gw) {
 #pragma unroll
             for (int i = 0; i < UI; ++i) {
-                const int item = tid + i * NT, q = uq_sh >= 0 ? (item & (uq - 1)) : item % uq, v = uq_sh >= 0 ? (item >> uq_sh) : item / uq;
+                const int item = tid + i * NT, q = item & (uq - 1), v = item >> uq_sh;
                 store_u_split(sUh, sUl, (size_t)q * PLANE + (size_t)v * 16, pu[i], v0 + v < A.vox);
             }
         }
@@ -556,7 +556,8 @@ int l3d_pw_bwd_tc(const l3d_act *gz, const l3d_act *t, const l3d_norm *nt, const
         const size_t span_p = (size_t)(2 * (Cg / 8) + 2 * (Cu / 8)) * PLANE + (size_t)(Cg / 8) * PLANE + 16 * (size_t)PLANE + 256;
         if (smem_p < span_p) smem_p = span_p;
     }
-    const bool use_pipe = L3D_ENV_INT("L3D_NO_PWB_PIPE", 0) != 1;
+    // the pipelined kernel decodes (voxel, channel group) with shifts: power-of-two channel counts only
+    const bool use_pipe = L3D_ENV_INT("L3D_NO_PWB_PIPE", 0) != 1 && (Cg & (Cg - 1)) == 0 && (Cu & (Cu - 1)) == 0;
 #define L3D_PWTC_T(TT, GIV, UIV)                                                                                               \
     do {                                                                                                                        \
         {                                                                                                                       \

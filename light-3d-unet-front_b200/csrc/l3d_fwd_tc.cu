@@ -538,13 +538,13 @@ __global__ void __launch_bounds__(NT) convt_tc_kernel(CtArgs A) {
     const long long nvox = (long long)A.N * A.d * A.h * A.w;
     const long long ntiles = (nvox + 127) / 128;
     const int kq = Cin >> 3;
-    const int kq_sh = (kq & (kq - 1)) == 0 ? __ffs(kq) - 1 : -1;      // Cin / 8 is a power of two in every configured model: shifts instead of divisions
+    const int kq_sh = __ffs(kq) - 1;                                   // Cin / 8 is a power of two (host check): shifts instead of divisions
     const T *xin = reinterpret_cast<const T *>(A.x);
     auto load_a = [&](long long tile, int buf) {
         unsigned char *dst = sA + (size_t)buf * NP * a_bytes;
         const long long v0 = tile * 128;
         for (int item = tid; item < 128 * kq; item += NT) {
-            const int q = kq_sh >= 0 ? (item & (kq - 1)) : item % kq, v = kq_sh >= 0 ? (item >> kq_sh) : item / kq;
+            const int q = item & (kq - 1), v = item >> kq_sh;
             uint4 o = make_uint4(0u, 0u, 0u, 0u), ol = o;
             if (v0 + v < nvox) {
                 const T *src = xin + (size_t)(v0 + v) * A.ldx + q * 8;
@@ -632,6 +632,7 @@ int l3d_convt_fwd_tc(const l3d_act *x, int N, int d, int h, int w_, const float 
     const bool f32 = x->dtype == L3D_F32;
     const int np = f32 ? 2 : 1, es = f32 ? 4 : 2;
     if (out->dtype != x->dtype || Cin % 16 != 0 || Cout % 16 != 0 || 8 * Cout > 512) return -1;
+    if ((Cin & (Cin - 1)) != 0) return -1;           // the A-tile loader decodes (voxel, channel group) with shifts
     if (8 * Cout > 256 && (8 * Cout) % 256 != 0) return -1;
     const int vec = 16 / es;
     auto aligned = [vec](const l3d_act *a) { return (a->ldc % vec == 0) && (reinterpret_cast<uintptr_t>(a->ptr) % 16 == 0); };
