@@ -117,7 +117,6 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32 + (NWARPS == 12 && !LD ? 32 :
     using G = Geo<TZ>;
     constexpr bool PRODW = NWARPS == 12 && !LD;            // a third role: one warp that only requests halo boxes
     constexpr int NW = NWARPS * 32, NT = NW + 32 + (PRODW ? 32 : 0);   // worker warps + 1 issuer warp (+ 1 producer warp)
-    constexpr int ACT_PER_THREAD = (G::ACT_ITEMS + NW - 1) / NW;
     constexpr int EPG = NWARPS / 4;                        // worker warps per TMEM lane quarter: plane stride of the epilogue
     auto worker_bar = [] { worker_bar_n<NW>(); };
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -369,39 +368,40 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32 + (NWARPS == 12 && !LD ? 32 :
         }
     } else {
         // ===================================== workers =====================================
-        // activation-pass role: fixed 16-byte vectors of the raw box; q (8-channel group) is the same for all of them
-        const int aq = tid & 1;
-        uint32_t act_item[ACT_PER_THREAD];
+        // activation-pass role: a thread owns CPT fixed columns (halo y, halo x, 8-channel half q) of the raw box and walks them
+        // in z: the vector of plane hz sits hz * COLS vectors further on in the box and in the operand tile, so the loop needs no
+        // per-vector coordinates.  (It used a per-thread table of packed (x, y, z) items first: ptxas kept that table in local
+        // memory, and its eleven reloads at the top of every tile missed the small L1 left beside ~200 KB of shared memory --
+        // ~1 K cycles per tile between the end of an epilogue and the next activation pass, clock stamps.)
+        constexpr int COLS = HY * HX * 2;                       // 16-byte vectors per halo plane
+        constexpr int CPT = (COLS + NW - 1) / NW;               // columns per thread (1 with 12 worker warps, 2 with 8)
+        const int aq = tid & 1;                                 // NW is even: all of a thread's columns share the channel half
+        int col_hx[CPT], col_hy[CPT];
 #pragma unroll
-        for (int k = 0; k < ACT_PER_THREAD; ++k) {
-            const int item = tid + k * NW;
-            int hv = item >> 1;
-            const int hx = hv % HX; hv /= HX;
-            const int hy = hv % HY;
-            const int hz = hv / HY;
-            act_item[k] = item < G::ACT_ITEMS ? ((uint32_t)hx | ((uint32_t)hy << 8) | ((uint32_t)hz << 16)) : 0xffffffffu;
+        for (int c = 0; c < CPT; ++c) {
+            const int v2 = (tid + c * NW) >> 1;                 // halo voxel within the plane
+            col_hx[c] = v2 % HX; col_hy[c] = v2 / HX;          // (col_hy >= HY: no such column)
         }
-        // LD: byte offset of each of this thread's raw vectors from the tile's halo origin in global memory, and the copies
-        uint32_t g_off[LD ? ACT_PER_THREAD : 1];
+        // LD: byte offset of each column's plane-0 vector from the tile's halo origin in global memory
+        uint32_t g_off[LD ? CPT : 1];
         if (LD) {
 #pragma unroll
-            for (int k = 0; k < ACT_PER_THREAD; ++k) {
-                const uint32_t ai = act_item[k];
-                const int hx = ai & 255, hy = (ai >> 8) & 255, hz = ai >> 16;
-                g_off[k] = ai != 0xffffffffu ? (uint32_t)(((hz * A.H + hy) * A.W + hx) * A.ldx * 2 + aq * 16) : 0u;
-            }
+            for (int c = 0; c < CPT; ++c) g_off[c] = (uint32_t)((col_hy[c] * A.W + col_hx[c]) * A.ldx * 2 + aq * 16);
         }
         auto issue_copies = [&](int n, int z0, int y0, int x0, int chunk) {
             const uint32_t mz = axis_mask(z0, G::HZ, A.D), my = axis_mask(y0, HY, A.H), mx = axis_mask(x0, HX, A.W);
             const char *org = reinterpret_cast<const char *>(A.xp) +
                               (((((long long)n * A.D + (z0 - 1)) * A.H + (y0 - 1)) * A.W + (x0 - 1)) * A.ldx + chunk * CK) * 2;
+            const uint32_t zstep = (uint32_t)(A.H * A.W * A.ldx * 2);         // bytes between z-planes (host: the box spans < 2^31 bytes)
 #pragma unroll
-            for (int k = 0; k < ACT_PER_THREAD; ++k) {
-                const uint32_t ai = act_item[k];
-                if ((k + 1) * NW <= G::ACT_ITEMS || ai != 0xffffffffu) {
-                    const int hx = ai & 255, hy = (ai >> 8) & 255, hz = ai >> 16;
-                    const bool ok = ((mx >> hx) & (my >> hy) & (mz >> hz) & 1u) != 0;
-                    cp_async16(s_raw + (size_t)(tid + k * NW) * 16, ok ? org + g_off[k] : reinterpret_cast<const char *>(A.xp), ok ? 16u : 0u);
+            for (int c = 0; c < CPT; ++c) {
+                if (CPT * NW == COLS || tid + c * NW < COLS) {
+                    const bool xy_ok = ((mx >> col_hx[c]) & (my >> col_hy[c]) & 1u) != 0;
+#pragma unroll
+                    for (int hz = 0; hz < G::HZ; ++hz) {
+                        const bool ok = xy_ok && ((mz >> hz) & 1u) != 0;
+                        cp_async16(s_raw + (size_t)(hz * COLS + tid + c * NW) * 16, ok ? org + g_off[c] + hz * zstep : reinterpret_cast<const char *>(A.xp), ok ? 16u : 0u);
+                    }
                 }
             }
         };
@@ -552,6 +552,7 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32 + (NWARPS == 12 && !LD ? 32 :
                 const __half2 sl2 = __float2half2_rn(A.xn.slope);
                 const bool ident = A.xn.stats == nullptr;
                 const bool stamp = (A.dbg & 8) && blockIdx.x == 0 && it < 128 && tid == 0;
+                if (stamp && (A.dbg & 512)) g_c3_dbg[it * 8 + 1] = clock64();          // development aid: before the box wait
                 if (LD) asm volatile("cp.async.wait_all;" ::: "memory");                   // own copies of this item landed
                 else if (rot) {
                     tc::mbar_wait(&s_tma_full[it % 3], (uint32_t)((it / 3) & 1));
@@ -562,45 +563,41 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32 + (NWARPS == 12 && !LD ? 32 :
                 else tc::mbar_wait(&s_tma_full[rb], w_rph);                                // raw box of this item landed
                 if (stamp) g_c3_dbg[it * 8 + 0] = clock64();
                 if (it > ab_m) tc::mbar_wait(&s_mma_done[buf], (uint32_t)(((it >> ab_sh) - 1) & 1));   // MMAs of the item that used A[buf] done
-                if (stamp) g_c3_dbg[it * 8 + 1] = clock64();
+                if (stamp && !(A.dbg & 512)) g_c3_dbg[it * 8 + 1] = clock64();
                 // ---- activation pass: raw bf16 [z][y][x][16] -> fp16 planar [q][z][y][x][8]; the shared-memory loads of a
                 // batch of vectors are issued before any of them is used
                 constexpr int ACT_BATCH = 4;
-                constexpr int HALF_ITEMS = (G::HZ / 2) * HY * HX * 2;      // split2: items (16-byte vectors) of the lower z-half
                 if (!(A.dbg & 1))
 #pragma unroll
-                for (int k0 = 0; k0 < ACT_PER_THREAD; k0 += ACT_BATCH) {
-                    uint4 rw[ACT_BATCH];
-                    float ru[ACT_BATCH];
-                    // split2: the first batch that reaches into the upper half waits for it
-                    if (!R1 && !LD && (k0 + ACT_BATCH) * NW > HALF_ITEMS && k0 * NW <= HALF_ITEMS) {
-                        if (split2) tc::mbar_wait(&s_tma_full[1], (uint32_t)(it & 1));
-                    }
+                for (int c = 0; c < CPT; ++c) {
+                    const bool col_ok = CPT * NW == COLS || tid + c * NW < COLS;
+                    // conv zero padding of the ACTIVATED tensor: x / y validity of the column, z validity per plane below
+                    const bool xy_ok = ((mx >> col_hx[c]) & (my >> col_hy[c]) & 1u) != 0;
+                    const unsigned char *Rc = Rb + (size_t)(tid + c * NW) * 16;                               // plane 0 of the column
+                    unsigned char *Ac = Ab + (size_t)aq * G::PLANE + (size_t)((tid + c * NW) >> 1) * 16;
+                    const float *Ru = reinterpret_cast<const float *>(Rb) + col_hy[c] * R1_BOXW + col_hx[c] + (R1_X0 - 1);   // R1
 #pragma unroll
-                    for (int kk = 0; kk < ACT_BATCH; ++kk) {
-                        const int k = k0 + kk;
-                        if (k < ACT_PER_THREAD) {
-                            const int item = tid + k * NW;
+                    for (int k0 = 0; k0 < G::HZ; k0 += ACT_BATCH) {
+                        uint4 rw[ACT_BATCH];
+                        float ru[ACT_BATCH];
+                        // split2: the first batch that reaches into the upper z-half waits for it
+                        if (!R1 && !LD && c == 0 && k0 + ACT_BATCH > G::HZ / 2 && k0 <= G::HZ / 2) {
+                            if (split2) tc::mbar_wait(&s_tma_full[1], (uint32_t)(it & 1));
+                        }
+#pragma unroll
+                        for (int kk = 0; kk < ACT_BATCH; ++kk) {
+                            const int hz = k0 + kk;
                             rw[kk] = make_uint4(0u, 0u, 0u, 0u);
                             ru[kk] = 0.f;
-                            if ((k + 1) * NW <= G::ACT_ITEMS || item < G::ACT_ITEMS) {
-                                if (R1) {
-                                    const uint32_t ai = act_item[k];
-                                    ru[kk] = reinterpret_cast<const float *>(Rb)[(((ai >> 16) * HY + ((ai >> 8) & 255)) * R1_BOXW) + (ai & 255) + (R1_X0 - 1)];
-                                } else {
-                                    rw[kk] = *reinterpret_cast<const uint4 *>(Rb + (size_t)item * 16);
-                                }
+                            if (hz < G::HZ && col_ok) {
+                                if (R1) ru[kk] = Ru[hz * (HY * R1_BOXW)];
+                                else rw[kk] = *reinterpret_cast<const uint4 *>(Rc + (size_t)hz * (COLS * 16));
                             }
                         }
-                    }
 #pragma unroll
-                    for (int kk = 0; kk < ACT_BATCH; ++kk) {
-                        const int k = k0 + kk;
-                        if (k < ACT_PER_THREAD) {
-                            const uint32_t ai = act_item[k];
-                            const int item = tid + k * NW;
-                            if ((k + 1) * NW <= G::ACT_ITEMS || ai != 0xffffffffu) {
-                                const int hx = ai & 255, hy = (ai >> 8) & 255, hz = ai >> 16;
+                        for (int kk = 0; kk < ACT_BATCH; ++kk) {
+                            const int hz = k0 + kk;
+                            if (hz < G::HZ && col_ok) {
                                 const uint4 r4 = rw[kk];
                                 float f[8];
                                 if (R1) {
@@ -627,17 +624,17 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32 + (NWARPS == 12 && !LD ? 32 :
                                     }
                                     o = make_uint4(*reinterpret_cast<uint32_t *>(&h[0]), *reinterpret_cast<uint32_t *>(&h[1]),
                                                    *reinterpret_cast<uint32_t *>(&h[2]), *reinterpret_cast<uint32_t *>(&h[3]));
+                                    // An identity-norm input needs no padding test: TMA (and the zero-size cp.async of the loader mode)
+                                    // already delivered zeros for the voxels outside the volume
+                                    if (!(xy_ok && ((mz >> hz) & 1u))) o = make_uint4(0u, 0u, 0u, 0u);
                                 }
-                                // conv zero padding of the ACTIVATED tensor.  An identity-norm input needs no test: TMA (and the zero-size
-                                // cp.async of the loader mode) already delivered zeros for the voxels outside the volume
-                                if ((R1 || !ident) && !((mx >> hx) & (my >> hy) & (mz >> hz) & 1u)) o = make_uint4(0u, 0u, 0u, 0u);
-                                *reinterpret_cast<uint4 *>(Ab + (size_t)aq * G::PLANE + (size_t)(item >> 1) * 16) = o;
+                                *reinterpret_cast<uint4 *>(Ac + (size_t)hz * (HY * HX * 16)) = o;
                             }
                         }
-                    }
-                    // split2: the batch that holds the last vectors of the lower half has them in registers now
-                    if (!R1 && !LD && (k0 + ACT_BATCH) * NW >= HALF_ITEMS && k0 * NW < HALF_ITEMS) {
-                        if (split2) { __syncwarp(); if (lane == 0) mbar_arrive(&s_raw_free[0]); }
+                        // split2: the batch that holds the last vectors of the lower half has them in registers now
+                        if (!R1 && !LD && c == CPT - 1 && k0 + ACT_BATCH >= G::HZ / 2 && k0 < G::HZ / 2) {
+                            if (split2) { __syncwarp(); if (lane == 0) mbar_arrive(&s_raw_free[0]); }
+                        }
                     }
                 }
                 tc::fence_async_smem();
