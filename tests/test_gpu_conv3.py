@@ -139,7 +139,10 @@ def test_conv3_tc_tile_heights(case, tz):
 @pytest.mark.parametrize("knobs", [{"L3D_C3_SETS": 1}, {"L3D_C3_NRAW": 1}, {"L3D_C3_NOMERGE": 1},
                                    {"L3D_C3_TZ": 4, "L3D_C3_SETS": 1, "L3D_C3_NRAW": 1},
                                    {"L3D_C3_LOADER": 2, "L3D_C3_WARPS": 12}, {"L3D_C3_LOADER": 2, "L3D_C3_WARPS": 12, "L3D_C3_TZ": 4},
-                                   {"L3D_C3_LOADER": 0}, {"L3D_C3_ROT": 1, "L3D_C3_NRAW": 1}, {"L3D_C3_ROT": 1, "L3D_C3_NRAW": 1, "L3D_C3_TZ": 2, "L3D_C3_LOADER": 0}, {"L3D_C3_TMASPLIT": 2}, {"L3D_C3_TMASPLIT": 5, "L3D_C3_TZ": 8}])
+                                   {"L3D_C3_LOADER": 0}, {"L3D_C3_ROT": 1, "L3D_C3_NRAW": 1}, {"L3D_C3_ROT": 1, "L3D_C3_NRAW": 1, "L3D_C3_TZ": 2, "L3D_C3_LOADER": 0}, {"L3D_C3_TMASPLIT": 2}, {"L3D_C3_TMASPLIT": 5, "L3D_C3_TZ": 8},
+                                   # requests by the MMA issuer / the producer warp without the half-box split / with it at every tile height / two CTAs per SM
+                                   {"L3D_C3_PROD": 0}, {"L3D_C3_PROD": 1, "L3D_C3_SPLIT2": 0}, {"L3D_C3_PROD": 1, "L3D_C3_TZ": 2, "L3D_C3_NRAW": 1}, {"L3D_C3_PROD": 1, "L3D_C3_TZ": 4, "L3D_C3_NRAW": 1},
+                                   {"L3D_C3_PROD": 1, "L3D_C3_TZ": 6, "L3D_C3_NRAW": 1}, {"L3D_C3_PROD": 1, "L3D_C3_TZ": 6, "L3D_C3_NRAW": 2}, {"L3D_C3_OCC2": 1}, {"L3D_C3_OCC2": 1, "L3D_C3_TZ": 2}, {"L3D_C3_WARPS": 8}])
 def test_conv3_tc_pipeline_variants(knobs):
     for case in (CASES[0], CASES[5], CASES[6]):
         _run(case, dict(knobs, L3D_DWS_IGEMM_MAX=1 << 20))
