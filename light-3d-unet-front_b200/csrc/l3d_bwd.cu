@@ -45,8 +45,14 @@ __global__ void __launch_bounds__(NT) merge_bwd_kernel(
     const T *__restrict__ t2, int ld2, NormDev n2, const T *__restrict__ r, int ldr, NormDev nr,
     int N, int C, int D, int H, int W, float slope, float *__restrict__ gz, int ldgz,
     double *__restrict__ red2, double *__restrict__ redr) {
-    extern __shared__ float sm[];
-    float *s_mean2 = sm, *s_rstd2 = sm + C, *s_meanr = sm + 2 * C, *s_rstdr = sm + 3 * C, *s_red = sm + 4 * C;  // s_red[3][C]
+    // The two reductions of the InstanceNorm backward (sum g, sum g * xhat) are accumulated in DOUBLE from the first addition on:
+    // sum g * xhat cancels to a small fraction of its terms, the backward of the next norm amplifies what is left, and every
+    // fp32 partial sum combined in atomic (= run-dependent) order showed up as run-to-run differences of up to 2.5e-2 in
+    // individual gradient tensors (8 x 24^3, tools/repro_grad_race.py, tools/diag_bwd_determinism.py: `red` differed by 6e-5
+    // after this kernel).  PyTorch's CPU kernels, which the oracle runs, accumulate these sums in double as well.
+    extern __shared__ __align__(16) float sm[];
+    float *s_mean2 = sm, *s_rstd2 = sm + C, *s_meanr = sm + 2 * C, *s_rstdr = sm + 3 * C;
+    double *s_red = reinterpret_cast<double *>(sm + 4 * C);      // s_red[3][C]  (16 * C bytes in: 8-byte aligned)
     const int n = blockIdx.y, tid = threadIdx.x;
     const bool has_r = nr.stats != nullptr;
     for (int c = tid; c < C; c += NT) {
@@ -55,15 +61,15 @@ __global__ void __launch_bounds__(NT) merge_bwd_kernel(
         s_mean2[c] = m; s_rstd2[c] = rs;
         if (has_r) { norm_mean_rstd(nr, N, C, n, c, m, rs); s_meanr[c] = m; s_rstdr[c] = rs; }
         else { s_meanr[c] = 0.f; s_rstdr[c] = 0.f; }
-        s_red[c] = 0.f; s_red[C + c] = 0.f; s_red[2 * C + c] = 0.f;
+        s_red[c] = 0.0; s_red[C + c] = 0.0; s_red[2 * C + c] = 0.0;
     }
     __syncthreads();
     const int CD = (D + 1) / 2, CH = (H + 1) / 2, CW = (W + 1) / 2, CQ = C / 4;
     const int PD = D / 2, PH = H / 2, PW = W / 2;
     const size_t total = (size_t)CD * CH * CW * CQ;
-    float acc[12];
+    double acc[12];
 #pragma unroll
-    for (int j = 0; j < 12; ++j) acc[j] = 0.f;
+    for (int j = 0; j < 12; ++j) acc[j] = 0.0;
     int cur_q = -1;
     auto flush = [&]() {
         if (cur_q < 0) return;
@@ -74,7 +80,7 @@ __global__ void __launch_bounds__(NT) merge_bwd_kernel(
             if (has_r) atomicAdd(&s_red[2 * C + cur_q * 4 + j], acc[8 + j]);
         }
 #pragma unroll
-        for (int j = 0; j < 12; ++j) acc[j] = 0.f;
+        for (int j = 0; j < 12; ++j) acc[j] = 0.0;
     };
     // per-sample cell index: 32-bit arithmetic (host check) instead of four 64-bit divisions per item
     for (uint32_t idx = blockIdx.x * NT + tid; idx < (uint32_t)total; idx += gridDim.x * NT) {
@@ -112,10 +118,10 @@ __global__ void __launch_bounds__(NT) merge_bwd_kernel(
                 st4(gz + vox * ldgz + c, make_float4(gv[0], gv[1], gv[2], gv[3]));
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float gr = round_as(gz, gv[j]);
+                    const double gr = (double)round_as(gz, gv[j]);
                     acc[j] += gr;
-                    acc[4 + j] += gr * ((a[j] - s_mean2[c + j]) * s_rstd2[c + j]);
-                    acc[8 + j] += gr * ((b[j] - s_meanr[c + j]) * s_rstdr[c + j]);
+                    acc[4 + j] = fma(gr, (double)((a[j] - s_mean2[c + j]) * s_rstd2[c + j]), acc[4 + j]);
+                    acc[8 + j] = fma(gr, (double)((b[j] - s_meanr[c + j]) * s_rstdr[c + j]), acc[8 + j]);
                 }
             }
         }
@@ -123,11 +129,11 @@ __global__ void __launch_bounds__(NT) merge_bwd_kernel(
     flush();
     __syncthreads();
     for (int c = tid; c < C; c += NT) {
-        atomicAdd(&red2[(size_t)n * C + c], (double)s_red[c]);
-        atomicAdd(&red2[(size_t)N * C + (size_t)n * C + c], (double)s_red[C + c]);
+        atomicAdd(&red2[(size_t)n * C + c], s_red[c]);
+        atomicAdd(&red2[(size_t)N * C + (size_t)n * C + c], s_red[C + c]);
         if (has_r) {
-            atomicAdd(&redr[(size_t)n * C + c], (double)s_red[c]);
-            atomicAdd(&redr[(size_t)N * C + (size_t)n * C + c], (double)s_red[2 * C + c]);
+            atomicAdd(&redr[(size_t)n * C + c], s_red[c]);
+            atomicAdd(&redr[(size_t)N * C + (size_t)n * C + c], s_red[2 * C + c]);
         }
     }
 }
@@ -143,6 +149,7 @@ __global__ void __launch_bounds__(NT) merge_head_bwd_kernel(
     float *__restrict__ gz, int ldgz, double *__restrict__ red2, double *__restrict__ redr) {
     __shared__ float s_mean2[CMAX], s_rstd2[CMAX], s_meanr[CMAX], s_rstdr[CMAX], s_hw[OCM * CMAX];
     __shared__ float s_acc[(3 + OCM) * CMAX + OCM];
+    __shared__ double s_accd[3 * CMAX];                 // the InstanceNorm-backward reductions, in double (see merge_bwd_kernel)
     const int n = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     const bool has_r = nr.stats != nullptr;
     for (int c = tid; c < CMAX; c += NT) {
@@ -155,11 +162,13 @@ __global__ void __launch_bounds__(NT) merge_head_bwd_kernel(
         for (int oc = 0; oc < OCM; ++oc) s_hw[oc * CMAX + c] = (c < C && oc < OC) ? head_w[(size_t)oc * C + c] : 0.f;
     }
     for (int i = tid; i < (3 + OCM) * CMAX + OCM; i += NT) s_acc[i] = 0.f;
+    for (int i = tid; i < 3 * CMAX; i += NT) s_accd[i] = 0.0;
     __syncthreads();
-    float a1[CMAX], a2[CMAX], a3[CMAX], ahw[OCM][CMAX], ahb[OCM];
+    double a1[CMAX], a2[CMAX], a3[CMAX];
+    float ahw[OCM][CMAX], ahb[OCM];
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) {
-        a1[c] = a2[c] = a3[c] = 0.f;
+        a1[c] = a2[c] = a3[c] = 0.0;
 #pragma unroll
         for (int oc = 0; oc < OCM; ++oc) ahw[oc][c] = 0.f;
     }
@@ -198,18 +207,18 @@ __global__ void __launch_bounds__(NT) merge_head_bwd_kernel(
                 st4(gz + vox * ldgz + c4, make_float4(gv[0], gv[1], gv[2], gv[3]));
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float gr = round_as(gz, gv[j]);
+                    const double gr = (double)round_as(gz, gv[j]);
                     a1[c4 + j] += gr;
-                    a2[c4 + j] += gr * ((a[j] - s_mean2[c4 + j]) * s_rstd2[c4 + j]);
-                    a3[c4 + j] += gr * ((b[j] - s_meanr[c4 + j]) * s_rstdr[c4 + j]);
+                    a2[c4 + j] = fma(gr, (double)((a[j] - s_mean2[c4 + j]) * s_rstd2[c4 + j]), a2[c4 + j]);
+                    a3[c4 + j] = fma(gr, (double)((b[j] - s_meanr[c4 + j]) * s_rstdr[c4 + j]), a3[c4 + j]);
                 }
             }
         }
     }
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) {
-        const float v1 = warp_sum(a1[c]), v2 = warp_sum(a2[c]), v3 = warp_sum(a3[c]);
-        if (lane == 0) { atomicAdd(&s_acc[c], v1); atomicAdd(&s_acc[CMAX + c], v2); atomicAdd(&s_acc[2 * CMAX + c], v3); }
+        const double v1 = warp_sum(a1[c]), v2 = warp_sum(a2[c]), v3 = warp_sum(a3[c]);
+        if (lane == 0) { atomicAdd(&s_accd[c], v1); atomicAdd(&s_accd[CMAX + c], v2); atomicAdd(&s_accd[2 * CMAX + c], v3); }
 #pragma unroll
         for (int oc = 0; oc < OCM; ++oc) {
             const float vh = warp_sum(ahw[oc][c]);
@@ -223,11 +232,11 @@ __global__ void __launch_bounds__(NT) merge_head_bwd_kernel(
     }
     __syncthreads();
     for (int c = tid; c < C; c += NT) {
-        atomicAdd(&red2[(size_t)n * C + c], (double)s_acc[c]);
-        atomicAdd(&red2[(size_t)N * C + (size_t)n * C + c], (double)s_acc[CMAX + c]);
+        atomicAdd(&red2[(size_t)n * C + c], s_accd[c]);
+        atomicAdd(&red2[(size_t)N * C + (size_t)n * C + c], s_accd[CMAX + c]);
         if (has_r) {
-            atomicAdd(&redr[(size_t)n * C + c], (double)s_acc[c]);
-            atomicAdd(&redr[(size_t)N * C + (size_t)n * C + c], (double)s_acc[2 * CMAX + c]);
+            atomicAdd(&redr[(size_t)n * C + c], s_accd[c]);
+            atomicAdd(&redr[(size_t)N * C + (size_t)n * C + c], s_accd[2 * CMAX + c]);
         }
         for (int oc = 0; oc < OC; ++oc) atomicAdd(&g_head_w[(size_t)oc * C + c], s_acc[(3 + oc) * CMAX + c]);
     }
@@ -264,9 +273,10 @@ __global__ void __launch_bounds__(NT) pw_bwd_kernel(PwBwdArgs A) {
     float *s_w = sm;                                    // Cg*Cu   (16B aligned)
     float *s_g = s_w + (((size_t)Cg * Cu + 3) & ~(size_t)3);   // PB_V*PG
     float *s_u = s_g + (size_t)PB_V * PG;               // PB_V*PU
-    float *s_ca = s_u + (size_t)PB_V * PU;              // Cg x3 : a, b, d
-    float *s_cb = s_ca + Cg, *s_cd = s_cb + Cg;
-    float *s_us = s_cd + Cg, *s_uh = s_us + Cu;         // Cu x2 : prologue scale/shift of u
+    // Cg x3 doubles : a, b, d of the InstanceNorm backward (evaluated in double: in_bwd_apply), 8-byte aligned
+    double *s_ca = reinterpret_cast<double *>(sm + (((s_u + (size_t)PB_V * PU) - sm + 1) & ~(size_t)1));
+    double *s_cb = s_ca + Cg, *s_cd = s_cb + Cg;
+    float *s_us = reinterpret_cast<float *>(s_cd + Cg), *s_uh = s_us + Cu;         // Cu x2 : prologue scale/shift of u
     float *s_gb = s_uh + Cu;                            // Cg : bias gradient (convT)
     const int tid = threadIdx.x;
     const float *gz = (const float *)A.gz;
@@ -301,8 +311,8 @@ __global__ void __launch_bounds__(NT) pw_bwd_kernel(PwBwdArgs A) {
         if (n != cur_n) {
             cur_n = n;
             for (int c = tid; c < Cg; c += NT) {
-                float a = 1.f, b = 0.f, d = 0.f;
-                if (!CONVT) in_bwd_coef(A.nt, A.red, A.N, Cg, n, c, a, b, d);
+                double a = 1.0, b = 0.0, d = 0.0;
+                if (!CONVT) in_bwd_coef_d(A.nt, A.red, A.N, Cg, n, c, a, b, d);
                 s_ca[c] = a; s_cb[c] = b; s_cd[c] = d;
             }
             for (int k = tid; k < Cu; k += NT) {
@@ -399,7 +409,7 @@ __global__ void __launch_bounds__(NT) pw_bwd_kernel(PwBwdArgs A) {
                             const bool inb = v0 + lv < A.vox;
                             for (int j = 0; j < 4; ++j) {
                                 float val = g4[b][j];
-                                if (!CONVT && A.nt.stats != nullptr) val = s_ca[c + j] * g4[b][j] + s_cb[c + j] * t4[b][j] + s_cd[c + j];
+                                if (!CONVT && A.nt.stats != nullptr) val = in_bwd_apply(s_ca[c + j], s_cb[c + j], s_cd[c + j], g4[b][j], t4[b][j]);
                                 s_g[(size_t)lv * PG + c + j] = inb ? val : 0.f;
                             }
                         }
@@ -547,22 +557,24 @@ template <typename T, int CG>
 __global__ void __launch_bounds__(256) pw_bwd_cu1_kernel(const float *__restrict__ gz, int ldg, const T *__restrict__ t, int ldt, NormDev nt,
                                                          const double *__restrict__ red, const T *__restrict__ u, int ldu, NormDev un,
                                                          int N, long long vox, float *__restrict__ g_w) {
-    __shared__ float s_acc[CG];
-    __shared__ float s_ca[CG], s_cb[CG], s_cd[CG];
+    // g_w[c] = sum_v g_t[v][c] * u[v] is, for a conv that feeds an InstanceNorm, the small residue of terms that cancel (IN(w x)
+    // does not depend on |w| but for eps): accumulated in double inside the CTA; one fp32 atomic per CTA and channel at the end
+    __shared__ double s_acc[CG];
+    __shared__ double s_ca[CG], s_cb[CG], s_cd[CG];
     const int n = blockIdx.y;
     if (threadIdx.x < CG) {
-        s_acc[threadIdx.x] = 0.f;
-        float a, b, d;
-        in_bwd_coef(nt, red, N, CG, n, threadIdx.x, a, b, d);
+        s_acc[threadIdx.x] = 0.0;
+        double a, b, d;
+        in_bwd_coef_d(nt, red, N, CG, n, threadIdx.x, a, b, d);
         s_ca[threadIdx.x] = a; s_cb[threadIdx.x] = b; s_cd[threadIdx.x] = d;
     }
     __syncthreads();
     float usc, ush;
     norm_scale_shift(un, N, 1, n, 0, usc, ush);
     const bool has_nt = nt.stats != nullptr;
-    float acc[CG];
+    double acc[CG];
 #pragma unroll
-    for (int c = 0; c < CG; ++c) acc[c] = 0.f;
+    for (int c = 0; c < CG; ++c) acc[c] = 0.0;
     for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < vox; v += (long long)gridDim.x * blockDim.x) {
         const size_t gv = (size_t)n * vox + v;
         const float uv = lrelu(ld1(u + gv * (size_t)ldu) * usc + ush, un.slope);
@@ -572,20 +584,20 @@ __global__ void __launch_bounds__(256) pw_bwd_cu1_kernel(const float *__restrict
             ld4a(gz + gv * (size_t)ldg + c4, g4);
             if (has_nt) ld4a(t + gv * (size_t)ldt + c4, t4);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[c4 + j] = fmaf(fmaf(s_ca[c4 + j], g4[j], fmaf(s_cb[c4 + j], t4[j], s_cd[c4 + j])), uv, acc[c4 + j]);
+            for (int j = 0; j < 4; ++j) acc[c4 + j] = fma(fma(s_ca[c4 + j], (double)g4[j], fma(s_cb[c4 + j], (double)t4[j], s_cd[c4 + j])), (double)uv, acc[c4 + j]);
         }
     }
 #pragma unroll
     for (int c = 0; c < CG; ++c) {
-        const float s = warp_sum(acc[c]);
+        const double s = warp_sum(acc[c]);
         if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[c], s);
     }
     __syncthreads();
-    if (threadIdx.x < CG) atomicAdd(&g_w[threadIdx.x], s_acc[threadIdx.x]);
+    if (threadIdx.x < CG) atomicAdd(&g_w[threadIdx.x], (float)s_acc[threadIdx.x]);
 }
 
 static size_t pw_bwd_smem(int Cg, int Cu) {
-    size_t fl = (((size_t)Cg * Cu + 3) & ~(size_t)3) + (size_t)PB_V * (Cg | 1) + (size_t)PB_V * (Cu | 1) + 4 * (size_t)Cg + 2 * (size_t)Cu;
+    size_t fl = (((size_t)Cg * Cu + 3) & ~(size_t)3) + (size_t)PB_V * (Cg | 1) + (size_t)PB_V * (Cu | 1) + 7 * (size_t)Cg + 2 + 2 * (size_t)Cu;   /* 3 x Cg doubles (+ alignment) + the bias-gradient row */
     return fl * sizeof(float);
 }
 
@@ -608,15 +620,16 @@ __global__ void __launch_bounds__(NT, 2) dw_bwd_kernel(
     float *s_shift = s_scale + C;
     float *s_m = s_shift + C;                // dropout keep-scale
     float *s_mean = s_m + C, *s_rstd = s_mean + C;
-    float *s_red = s_rstd + C;               // 2*C
-    float *s_gdw = s_red + 2 * C;            // C*27 (accumulated over all tiles of this CTA)
+    // 2*C doubles: the reductions of the producer's InstanceNorm backward (double from the first atomic on, see merge_bwd_kernel)
+    double *s_red = reinterpret_cast<double *>(sm + ((2 * HVOX * CK + 5 * C + 1) & ~1));
+    float *s_gdw = reinterpret_cast<float *>(s_red + 2 * C);            // C*27 (accumulated over all tiles of this CTA)
     const int tid = threadIdx.x;
     const bool has_norm = xn.stats != nullptr;
     const int tilesX = (W + TX - 1) / TX, tilesY = (H + TY - 1) / TY, tilesZ = (D + TZ - 1) / TZ;
     const long long tiles_per_sample = (long long)tilesX * tilesY * tilesZ;
     const long long total_tiles = tiles_per_sample * N;
     for (int i = tid; i < C * 27; i += NT) s_gdw[i] = 0.f;
-    for (int i = tid; i < 2 * C; i += NT) s_red[i] = 0.f;
+    for (int i = tid; i < 2 * C; i += NT) s_red[i] = 0.0;
     const int c = tid & 15, g = tid >> 4;
     const int lz = (g & 1) + 2 * (g >> 3);
     const int ly0 = 2 * ((g >> 1) & 3);
@@ -626,8 +639,8 @@ __global__ void __launch_bounds__(NT, 2) dw_bwd_kernel(
         for (int i = tid; i < 2 * C; i += NT) {
             const int isq = i >= C;
             const int cc = isq ? i - C : i;
-            atomicAdd(&redx[(size_t)isq * N * C + (size_t)n * C + cc], (double)s_red[i]);
-            s_red[i] = 0.f;
+            atomicAdd(&redx[(size_t)isq * N * C + (size_t)n * C + cc], s_red[i]);
+            s_red[i] = 0.0;
         }
     };
     // work item = (tile, 16-channel chunk): the deep layers have few tiles and many chunks, so the chunks of one tile
@@ -845,19 +858,19 @@ __global__ void __launch_bounds__(NT, 2) dw_bwd_kernel(
                     }
                 }
                 if (has_norm && redx != nullptr) {
+                    // the thread's own (fixed-order, few-term) fp32 partial sums go on in double: everything combined in a
+                    // run-dependent order is double
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
+                        double ds = (double)rs[j], dx = (double)rx[j];
 #pragma unroll
                         for (int sft = 4; sft <= 16; sft <<= 1) {
-                            rs[j] += __shfl_xor_sync(0xffffffffu, rs[j], sft);
-                            rx[j] += __shfl_xor_sync(0xffffffffu, rx[j], sft);
+                            ds += __shfl_xor_sync(0xffffffffu, ds, sft);
+                            dx += __shfl_xor_sync(0xffffffffu, dx, sft);
                         }
-                    }
-                    if ((tid & 31) < 4) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) if (cc + j < C) {
-                            atomicAdd(&s_red[cc + j], rs[j]);
-                            atomicAdd(&s_red[C + cc + j], rx[j]);
+                        if ((tid & 31) < 4 && cc + j < C) {
+                            atomicAdd(&s_red[cc + j], ds);
+                            atomicAdd(&s_red[C + cc + j], dx);
                         }
                     }
                 }
@@ -919,7 +932,7 @@ __global__ void __launch_bounds__(256) dw_bwd_c1_wgrad_kernel(const float *__res
 }
 
 static size_t dw_bwd_smem(int C) {
-    return sizeof(float) * (2 * (size_t)HVOX * CK + 7 * (size_t)C + 27 * (size_t)C);
+    return sizeof(float) * (2 * (size_t)HVOX * CK + 5 * (size_t)C + 2 + 4 * (size_t)C + 27 * (size_t)C);   /* 2 x C doubles (+ alignment) for the reductions */
 }
 
 __global__ void norm_param_grad_kernel(const double *__restrict__ red, int N, int C, float *__restrict__ g_gamma, float *__restrict__ g_beta) {
@@ -960,10 +973,10 @@ __global__ void __launch_bounds__(NT) c3_gt_kernel(const float *__restrict__ gz,
         const int c = (int)(i % C);
         const size_t v = i / C;
         const int n = (int)(v / vox);
-        float a, b, d;
-        in_bwd_coef(nt, red, N, C, n, c, a, b, d);
+        double a, b, d;
+        in_bwd_coef_d(nt, red, N, C, n, c, a, b, d);
         const float tv = nt.stats != nullptr ? ld1(t + v * ldt + c) : 0.f;
-        st1(gt + i, a * ld1(gz + v * ldg + c) + b * tv + d);
+        st1(gt + i, in_bwd_apply(a, b, d, ld1(gz + v * ldg + c), tv));
     }
 }
 // (2) flipped / transposed weights for the dgrad-as-forward-conv: wT[ci][col][tap] = w[co][cil][26-tap]
@@ -984,11 +997,11 @@ template <typename T>
 __global__ void __launch_bounds__(NT) c3_act_bwd_kernel(const float *__restrict__ ga, const T *__restrict__ x, int ldx, NormDev xn,
                                                         int N, int C, size_t vox, float *__restrict__ gy, int ldgy, int accumulate,
                                                         double *__restrict__ redx) {
-    extern __shared__ float sm[];
-    float *s_red = sm;   // 2*C
-    float *s_mean = sm + 2 * C, *s_rstd = sm + 3 * C, *s_gam = sm + 4 * C, *s_bet = sm + 5 * C, *s_m = sm + 6 * C;
+    extern __shared__ __align__(16) float sm[];
+    double *s_red = reinterpret_cast<double *>(sm);   // 2*C doubles (reductions in double: see merge_bwd_kernel)
+    float *s_mean = sm + 4 * C, *s_rstd = sm + 5 * C, *s_gam = sm + 6 * C, *s_bet = sm + 7 * C, *s_m = sm + 8 * C;
     const int n = blockIdx.y;
-    for (int i = threadIdx.x; i < 2 * C; i += NT) s_red[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * C; i += NT) s_red[i] = 0.0;
     for (int c = threadIdx.x; c < C; c += NT) {
         const NormCoef k = norm_coef(xn, N, C, n, c);
         s_mean[c] = k.mean; s_rstd[c] = k.rstd; s_gam[c] = k.gamma; s_bet[c] = k.beta; s_m[c] = k.m;
@@ -1006,8 +1019,8 @@ __global__ void __launch_bounds__(NT) c3_act_bwd_kernel(const float *__restrict_
             const float y = s_gam[c] * xh + s_bet[c];
             g *= s_m[c] * (y > 0.f ? 1.f : xn.slope);
             const float gr = round_as(gy, g);
-            atomicAdd(&s_red[c], gr);
-            atomicAdd(&s_red[C + c], gr * xh);
+            atomicAdd(&s_red[c], (double)gr);
+            atomicAdd(&s_red[C + c], (double)gr * (double)xh);
         }
         float *op = gy + v * ldgy + c;
         if (accumulate) g += ld1(op);
@@ -1017,7 +1030,7 @@ __global__ void __launch_bounds__(NT) c3_act_bwd_kernel(const float *__restrict_
     if (has_norm && redx != nullptr)
         for (int i = threadIdx.x; i < 2 * C; i += NT) {
             const int isq = i >= C, c = isq ? i - C : i;
-            atomicAdd(&redx[(size_t)isq * N * C + (size_t)n * C + c], (double)s_red[i]);
+            atomicAdd(&redx[(size_t)isq * N * C + (size_t)n * C + c], s_red[i]);
         }
 }
 // (4) wgrad: g_w[co][cil][tap] += sum_vox g_t[vox][co] * a[vox + off(tap)][ci].  A CTA owns an 8x8 block of
@@ -1206,7 +1219,7 @@ extern "C" int l3d_merge_bwd(const l3d_act *g_out, const l3d_act *pooled_g, cons
         const size_t cap = (148 * 16 + N - 1) / N;
         if (gx > cap) gx = cap;
         dim3 grid((unsigned)gx, (unsigned)N);
-        const size_t smem = sizeof(float) * 7 * (size_t)C;
+        const size_t smem = sizeof(float) * 4 * (size_t)C + sizeof(double) * 3 * (size_t)C;
         L3D_DISPATCH_DTYPE(t2->dtype, T, {
             merge_bwd_kernel<T><<<grid, NT, smem, st>>>(has_go ? (const float *)g_out->ptr : nullptr, has_go ? g_out->ldc : 0,
                 has_pg ? (const float *)pooled_g->ptr : nullptr, has_pg ? pooled_g->ldc : 0, (const T *)out->ptr, out->ldc,
@@ -1413,10 +1426,10 @@ __global__ void __launch_bounds__(NT) c3_pad_kernel(const float *__restrict__ gz
         const int zd = (int)(r / H);
         const size_t pv = (((size_t)n * (D + 2) + zd + 1) * (H + 2) + yh + 1) * (W + 2) + xw + 1;
         if (c < Cout) {
-            float a, b, d;
-            in_bwd_coef(nt, red, N, Cout, n, c, a, b, d);
+            double a, b, d;
+            in_bwd_coef_d(nt, red, N, Cout, n, c, a, b, d);
             const float tv = nt.stats != nullptr ? ld1(t + v * ldt + c) : 0.f;
-            gpad[pv * Cout + c] = a * gz[v * ldg + c] + b * tv + d;
+            gpad[pv * Cout + c] = in_bwd_apply(a, b, d, gz[v * ldg + c], tv);
         } else {
             const int ci = c - Cout;
             float sc, sh;
@@ -1552,7 +1565,7 @@ extern "C" int l3d_conv3_bwd(const l3d_act *gz, const l3d_act *t, const l3d_norm
             if (gx > cap) gx = cap;
             dim3 grid((unsigned)gx, (unsigned)N);
             L3D_DISPATCH_DTYPE(x->dtype, T, {
-                c3_act_bwd_kernel<T><<<grid, NT, sizeof(float) * 7 * Cin, st>>>((const float *)ga, (const T *)x->ptr, x->ldc, dxn, N, Cin, vox,
+                c3_act_bwd_kernel<T><<<grid, NT, sizeof(float) * 9 * Cin, st>>>((const float *)ga, (const T *)x->ptr, x->ldc, dxn, N, Cin, vox,
                                                                                  (float *)gy->ptr, gy->ldc, accumulate_gy, redx);
             });
             l3d_count_launch(2);
@@ -1616,7 +1629,7 @@ extern "C" int l3d_conv3_bwd(const l3d_act *gz, const l3d_act *t, const l3d_norm
         if (gx > cap) gx = cap;
         dim3 grid((unsigned)gx, (unsigned)N);
         L3D_DISPATCH_DTYPE(x->dtype, T, {
-            c3_act_bwd_kernel<T><<<grid, NT, sizeof(float) * 7 * Cin, st>>>((const float *)ga, (const T *)x->ptr, x->ldc, dxn, N, Cin, vox,
+            c3_act_bwd_kernel<T><<<grid, NT, sizeof(float) * 9 * Cin, st>>>((const float *)ga, (const T *)x->ptr, x->ldc, dxn, N, Cin, vox,
                                                                              (float *)gy->ptr, gy->ldc, accumulate_gy, redx);
         });
         l3d_count_launch();

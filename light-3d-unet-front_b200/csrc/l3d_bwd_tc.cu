@@ -97,8 +97,9 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
     unsigned char *sUl = sUh + (size_t)uq * PLANE;
     unsigned char *sWh = sUl + (size_t)uq * PLANE;          // dgrad B operand: [N = Cu][K = Cg] K-major
     unsigned char *sWl = sWh + (size_t)Cg * Cu * 2;
-    float *s_ca = reinterpret_cast<float *>(sWl + (size_t)Cg * Cu * 2);
-    float *s_cb = s_ca + Cg, *s_cd = s_cb + Cg, *s_us = s_cd + Cg, *s_uh = s_us + Cu;
+    double *s_ca = reinterpret_cast<double *>(sWl + (size_t)Cg * Cu * 2);       // a, b, d of the InstanceNorm backward, in double (in_bwd_apply)
+    double *s_cb = s_ca + Cg, *s_cd = s_cb + Cg;
+    float *s_us = reinterpret_cast<float *>(s_cd + Cg), *s_uh = s_us + Cu;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool has_gu = A.g_u != nullptr, has_gw = A.g_w != nullptr;
     if (warp == 0) tc::tmem_alloc(&s_tmem, (uint32_t)A.tmem_cols);
@@ -157,8 +158,8 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
         if (n != cur_n) {
             cur_n = n;
             for (int c = tid; c < Cg; c += NT) {
-                float a, b, d;
-                in_bwd_coef(A.nt, A.red, A.N, Cg, n, c, a, b, d);
+                double a, b, d;
+                in_bwd_coef_d(A.nt, A.red, A.N, Cg, n, c, a, b, d);
                 s_ca[c] = a; s_cb[c] = b; s_cd[c] = d;
             }
             for (int k = tid; k < Cu; k += NT) {
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
                         float tv[8];
                         pt[i].unpack(tv);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) g[j] = fmaf(s_ca[q * 8 + j], g[j], fmaf(s_cb[q * 8 + j], tv[j], s_cd[q * 8 + j]));
+                        for (int j = 0; j < 8; ++j) g[j] = in_bwd_apply(s_ca[q * 8 + j], s_cb[q * 8 + j], s_cd[q * 8 + j], g[j], tv[j]);
                     }
                     split2(g[0], g[1], hi.x, lo.x); split2(g[2], g[3], hi.y, lo.y);
                     split2(g[4], g[5], hi.z, lo.z); split2(g[6], g[7], hi.w, lo.w);
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
                         float tv[8];
                         tr.unpack(tv);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) g[j] = fmaf(s_ca[q * 8 + j], g[j], fmaf(s_cb[q * 8 + j], tv[j], s_cd[q * 8 + j]));
+                        for (int j = 0; j < 8; ++j) g[j] = in_bwd_apply(s_ca[q * 8 + j], s_cb[q * 8 + j], s_cd[q * 8 + j], g[j], tv[j]);
                     }
                     split2(g[0], g[1], hi.x, lo.x); split2(g[2], g[3], hi.y, lo.y);
                     split2(g[4], g[5], hi.z, lo.z); split2(g[6], g[7], hi.w, lo.w);
@@ -329,8 +330,8 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
     const uint32_t tile_bytes = (uint32_t)(2 * gq + 2 * uq) * PLANE;   // [Gh | Gl | Uh | Ul]
     unsigned char *sWh = smem + 2 * tile_bytes;
     unsigned char *sWl = sWh + (size_t)Cg * Cu * 2;
-    float *s_ca = reinterpret_cast<float *>(sWl + (size_t)Cg * Cu * 2);
-    float *s_cb = s_ca + Cg, *s_cd = s_cb + Cg;
+    double *s_ca = reinterpret_cast<double *>(sWl + (size_t)Cg * Cu * 2);
+    double *s_cb = s_ca + Cg, *s_cd = s_cb + Cg;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool has_gu = A.g_u != nullptr, has_gw = A.g_w != nullptr, has_nt = A.nt.stats != nullptr;
     if (warp == 0) tc::tmem_alloc(&s_tmem, (uint32_t)A.tmem_cols);
@@ -386,8 +387,8 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
         if (n != cur_n) {                              // uniform over the CTA; the previous stage() ended before a CTA barrier
             cur_n = n;
             for (int c = tid; c < Cg; c += NT) {
-                float a, bb, d;
-                in_bwd_coef(A.nt, A.red, A.N, Cg, n, c, a, bb, d);
+                double a, bb, d;
+                in_bwd_coef_d(A.nt, A.red, A.N, Cg, n, c, a, bb, d);
                 s_ca[c] = a; s_cb[c] = bb; s_cd[c] = d;
             }
             __syncthreads();
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
                     float tv[8];
                     pt[i].unpack(tv);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) g[j] = fmaf(s_ca[q * 8 + j], g[j], fmaf(s_cb[q * 8 + j], tv[j], s_cd[q * 8 + j]));
+                    for (int j = 0; j < 8; ++j) g[j] = in_bwd_apply(s_ca[q * 8 + j], s_cb[q * 8 + j], s_cd[q * 8 + j], g[j], tv[j]);
                 }
                 split2(g[0], g[1], hi.x, lo.x); split2(g[2], g[3], hi.y, lo.y);
                 split2(g[4], g[5], hi.z, lo.z); split2(g[6], g[7], hi.w, lo.w);
@@ -526,7 +527,7 @@ int l3d_pw_bwd_tc(const l3d_act *gz, const l3d_act *t, const l3d_norm *nt, const
     // an activated u is not exactly representable in bf16 (it would need a hi/lo pair like g_t); every caller on the
     // U-Net path passes a stored bf16 tensor with the identity norm, so the general case stays on the CUDA-core kernel
     if (un != nullptr && un->stats != nullptr && g_w != nullptr) return -1;
-    size_t smem = (size_t)(2 * (Cg / 8) + 2 * (Cu / 8)) * PLANE + 2 * (size_t)Cg * Cu * 2 + sizeof(float) * (3 * (size_t)Cg + 2 * (size_t)Cu);
+    size_t smem = (size_t)(2 * (Cg / 8) + 2 * (Cu / 8)) * PLANE + 2 * (size_t)Cg * Cu * 2 + sizeof(double) * 3 * (size_t)Cg + sizeof(float) * 2 * (size_t)Cu;
     // the MN-major A operand always spans 128 rows (16 channel groups): keep its over-read inside the allocation
     const size_t span = (size_t)(Cg / 8) * PLANE + 16 * (size_t)PLANE + 256;
     if (smem < span) smem = span;
@@ -551,7 +552,7 @@ int l3d_pw_bwd_tc(const l3d_act *gz, const l3d_act *t, const l3d_norm *nt, const
     const long long tiles = ((vox + TV - 1) / TV) * N;
     if (tiles >= (1ll << 31)) return -1;          // 32-bit tile arithmetic in the kernels
     // pipelined variant: two tile buffers + weights + tables, and the MN-major over-read of the second buffer's G planes
-    size_t smem_p = 2 * (size_t)(2 * (Cg / 8) + 2 * (Cu / 8)) * PLANE + 2 * (size_t)Cg * Cu * 2 + sizeof(float) * 3 * (size_t)Cg;
+    size_t smem_p = 2 * (size_t)(2 * (Cg / 8) + 2 * (Cu / 8)) * PLANE + 2 * (size_t)Cg * Cu * 2 + sizeof(double) * 3 * (size_t)Cg;
     {
         const size_t span_p = (size_t)(2 * (Cg / 8) + 2 * (Cu / 8)) * PLANE + (size_t)(Cg / 8) * PLANE + 16 * (size_t)PLANE + 256;
         if (smem_p < span_p) smem_p = span_p;

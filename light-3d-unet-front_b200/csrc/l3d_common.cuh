@@ -149,6 +149,30 @@ __device__ __forceinline__ void in_bwd_coef(const NormDev &nd, const double *__r
     d = gr * (mean * rstd * k2 - k1);
 }
 
+// The same coefficients in double, for a double-precision evaluation of g_t (in_bwd_apply).  The three terms cancel: the loss
+// gradient that reaches the last blocks is nearly constant over a window (|mean gz| up to ~1e5 x |gz - mean gz|), so one ulp of
+// an fp32 `d` is a per-cent error of g_t -- and which way the coefficients round depends on the order of the double atomics
+// behind `red`, i.e. on the run (measured, 8 x 24^3: repetitions of one step differed by 2.5e-2 on individual gradient
+// tensors, 8e-3 median, with fp32 coefficients; tools/repro_grad_race.py).  PyTorch's CPU kernels, which the oracle runs,
+// evaluate the same expression with double accumulators (at::acc_type<float, false>).
+__device__ __forceinline__ void in_bwd_coef_d(const NormDev &nd, const double *__restrict__ red, int N, int C, int n, int c,
+                                              double &a, double &b, double &d) {
+    if (nd.stats == nullptr) { a = 1.0; b = 0.0; d = 0.0; return; }
+    const double inv = 1.0 / (double)nd.count;
+    const double mean = nd.stats[(size_t)n * C + c] * inv;
+    double var = nd.stats[(size_t)N * C + (size_t)n * C + c] * inv - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double rstd = 1.0 / sqrt(var + (double)nd.eps);
+    const double k1 = red[(size_t)n * C + c] * inv, k2 = red[(size_t)N * C + (size_t)n * C + c] * inv;
+    const double gr = (double)nd.gamma[c] * rstd;
+    a = gr;
+    b = -gr * rstd * k2;
+    d = gr * (mean * rstd * k2 - k1);
+}
+__device__ __forceinline__ float in_bwd_apply(double a, double b, double d, float gz, float t) {
+    return (float)fma(a, (double)gz, fma(b, (double)t, d));
+}
+
 // ------------------------------------------------------- warp reductions --
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

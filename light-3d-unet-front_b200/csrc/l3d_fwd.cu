@@ -154,7 +154,7 @@ __device__ __forceinline__ void load_center_all(const T *__restrict__ x, int ldc
 // `out` (raw) with {sum, sumsq} accumulated into stats[2][N][Cout].  Each thread owns 2 voxels x CPT outputs.
 template <typename T, int CPT>
 __device__ __forceinline__ void pw_phase(const float *s_u, int P, int Cin, const float *__restrict__ w, int Cout,
-                                         float *s_w, float *s_stat, T *__restrict__ out, int ldo,
+                                         float *s_w, double *s_stat, T *__restrict__ out, int ldo,
                                          double *__restrict__ stats, int N, const TileCoord &tc, int D, int H, int W) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int vp = tid & 127, half = tid >> 7;
@@ -169,7 +169,7 @@ __device__ __forceinline__ void pw_phase(const float *s_u, int P, int Cin, const
         valid[i] = gz < D && gy < H && gx < W;
         goff[i] = ((((size_t)tc.n * D + gz) * H + gy) * W + gx) * (size_t)ldo;
     }
-    for (int i = tid; i < 2 * Cout; i += NT) s_stat[i] = 0.f;
+    for (int i = tid; i < 2 * Cout; i += NT) s_stat[i] = 0.0;
     constexpr int CB = 2 * CPT;  // output channels per pass
     for (int cb = 0; cb < Cout; cb += CB) {
         __syncthreads();  // previous pass done with s_w (and s_u/s_stat initialised on first pass)
@@ -215,7 +215,7 @@ __device__ __forceinline__ void pw_phase(const float *s_u, int P, int Cin, const
                 const int idx = warp_transpose_owner<CB>(lane);  // 0..CB-1
                 const int isq = idx >= CPT;
                 const int c = co + (isq ? idx - CPT : idx);
-                atomicAdd(&s_stat[isq * Cout + c], sv[0]);
+                atomicAdd(&s_stat[isq * Cout + c], (double)sv[0]);      // double from the first run-order-dependent addition on
             }
         }
     }
@@ -223,7 +223,7 @@ __device__ __forceinline__ void pw_phase(const float *s_u, int P, int Cin, const
     for (int i = tid; i < 2 * Cout; i += NT) {
         const int isq = i >= Cout;
         const int c = isq ? i - Cout : i;
-        atomicAdd(&stats[(size_t)isq * N * Cout + (size_t)tc.n * Cout + c], (double)s_stat[i]);
+        atomicAdd(&stats[(size_t)isq * N * Cout + (size_t)tc.n * Cout + c], s_stat[i]);
     }
 }
 
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(NT) dwpw_fwd_kernel(
     s_w = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(s_w) + 15) & ~(uintptr_t)15);
     float *s_scale = s_w + (size_t)Cin * 2 * CPT;
     float *s_shift = s_scale + Cin;
-    float *s_stat = s_shift + Cin;             // 2*Cout
+    double *s_stat = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(s_shift + Cin) + 7) & ~(uintptr_t)7);   // 2*Cout doubles
 
     const TileCoord tc = decode_tile(D, H, W);
     const int tid = threadIdx.x;
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(NT) dwpw_fwd_kernel(
 
 static size_t dwpw_smem_bytes(int Cin, int Cout, int CPT) {
     const size_t P = (size_t)(Cin | 1);
-    size_t fl = (size_t)HVOX * CK + (size_t)TV * P + 4 /*align slack*/ + (size_t)Cin * 2 * CPT + 2 * (size_t)Cin + 2 * (size_t)Cout;
+    size_t fl = (size_t)HVOX * CK + (size_t)TV * P + 4 /*align slack*/ + (size_t)Cin * 2 * CPT + 2 * (size_t)Cin + 2 + 4 * (size_t)Cout;
     return fl * sizeof(float);
 }
 
@@ -338,12 +338,12 @@ __global__ void __launch_bounds__(NT) conv3_fwd_kernel(
     float *s_w = s_in + C3_CK * HZ * HY * HX;             // 27 * C3_CK * CC
     float *s_scale = s_w + 27 * C3_CK * CC;
     float *s_shift = s_scale + Cin;
-    float *s_stat = s_shift + Cin;                        // 2*Cout
+    double *s_stat = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(s_shift + Cin) + 7) & ~(uintptr_t)7);   // 2*Cout doubles
 
     const TileCoord tc = decode_tile(D, H, W);
     const int tid = threadIdx.x, lane = tid & 31;
     setup_prologue(xn, N, Cin, tc.n, s_scale, s_shift);
-    for (int i = tid; i < 2 * Cout; i += NT) s_stat[i] = 0.f;
+    for (int i = tid; i < 2 * Cout; i += NT) s_stat[i] = 0.0;
 
     const int v = tid;
     const int lx = v & 7, ly = (v >> 3) & 7, lz = v >> 6;
@@ -426,8 +426,8 @@ __global__ void __launch_bounds__(NT) conv3_fwd_kernel(
         if ((lane % DUP) == 0) {
             const int c = cb + warp_transpose_owner<CC>(lane);
             if (c < Cout) {
-                atomicAdd(&s_stat[c], sv[0]);
-                atomicAdd(&s_stat[Cout + c], sq[0]);
+                atomicAdd(&s_stat[c], (double)sv[0]);
+                atomicAdd(&s_stat[Cout + c], (double)sq[0]);
             }
         }
     }
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(NT) conv3_fwd_kernel(
     for (int i = tid; i < 2 * Cout; i += NT) {
         const int isq = i >= Cout;
         const int c = isq ? i - Cout : i;
-        atomicAdd(&t_stats[(size_t)isq * N * Cout + (size_t)tc.n * Cout + c], (double)s_stat[i]);
+        atomicAdd(&t_stats[(size_t)isq * N * Cout + (size_t)tc.n * Cout + c], s_stat[i]);
     }
 }
 
@@ -745,12 +745,12 @@ __global__ void __launch_bounds__(NT) dwpw_c1_kernel(
     T *__restrict__ t, int ldt, double *__restrict__ t_stats, T *__restrict__ r, int ldr, double *__restrict__ r_stats,
     T *__restrict__ u, int ldu) {
     __shared__ float s_in[HZ][HY][HX + 1];
-    __shared__ float s_sum[4];
+    __shared__ double s_sum[4];       // double: the warps' partial sums meet in a run-dependent order
     __shared__ float s_w[27 + 2 * COUT];
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < 27; i += NT) s_w[i] = dw_w[i];
     for (int i = tid; i < COUT; i += NT) { s_w[27 + i] = pw_w[i]; s_w[27 + COUT + i] = sc_w != nullptr ? sc_w[i] : 0.f; }
-    if (tid < 4) s_sum[tid] = 0.f;
+    if (tid < 4) s_sum[tid] = 0.0;
     const int tilesX = (W + TX - 1) / TX, tilesY = (H + TY - 1) / TY, tilesZ = (D + TZ - 1) / TZ;
     const int tiles_per_sample = tilesX * tilesY * tilesZ;
     const int total_tiles = tiles_per_sample * N;
@@ -769,7 +769,7 @@ __global__ void __launch_bounds__(NT) dwpw_c1_kernel(
                 atomicAdd(&r_stats[(size_t)isq * N * COUT + (size_t)n * COUT + c], isq ? (double)wr * wr * s_sum[3] : (double)wr * s_sum[2]);
         }
         __syncthreads();
-        if (tid < 4) s_sum[tid] = 0.f;
+        if (tid < 4) s_sum[tid] = 0.0;
     };
     for (int tile = tile_begin; tile < tile_end; ++tile) {
         const int n = tile / tiles_per_sample;
@@ -850,7 +850,7 @@ __global__ void __launch_bounds__(NT) dwpw_c1_kernel(
         float s0 = valid ? uacc : 0.f, s2 = valid ? xc : 0.f;
         float s1 = s0 * s0, s3 = s2 * s2;
         s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
-        if (lane == 0) { atomicAdd(&s_sum[0], s0); atomicAdd(&s_sum[1], s1); atomicAdd(&s_sum[2], s2); atomicAdd(&s_sum[3], s3); }
+        if (lane == 0) { atomicAdd(&s_sum[0], (double)s0); atomicAdd(&s_sum[1], (double)s1); atomicAdd(&s_sum[2], (double)s2); atomicAdd(&s_sum[3], (double)s3); }
     }
     __syncthreads();
     flush(cur_n);
@@ -868,10 +868,10 @@ __global__ void __launch_bounds__(256) dw_c1_kernel(const T *__restrict__ x, int
                                                     const float *__restrict__ sc_w, int Cout, float *__restrict__ u,
                                                     double *__restrict__ t_stats, double *__restrict__ r_stats) {
     __shared__ float s_w[27];
-    __shared__ float s_sum[4];
+    __shared__ double s_sum[4];       // double: the warps' partial sums meet in a run-dependent order
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid < 27) s_w[tid] = dw_w[tid];
-    if (tid < 4) s_sum[tid] = 0.f;
+    if (tid < 4) s_sum[tid] = 0.0;
     __syncthreads();
     const int n = blockIdx.z, z0 = blockIdx.y * ZC1;
     const int p = blockIdx.x * 256 + tid;
@@ -922,7 +922,7 @@ __global__ void __launch_bounds__(256) dw_c1_kernel(const T *__restrict__ x, int
             }
     }
     s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
-    if (lane == 0) { atomicAdd(&s_sum[0], s0); atomicAdd(&s_sum[1], s1); atomicAdd(&s_sum[2], s2); atomicAdd(&s_sum[3], s3); }
+    if (lane == 0) { atomicAdd(&s_sum[0], (double)s0); atomicAdd(&s_sum[1], (double)s1); atomicAdd(&s_sum[2], (double)s2); atomicAdd(&s_sum[3], (double)s3); }
     __syncthreads();
     for (int i = tid; i < 2 * Cout; i += 256) {
         const int isq = i >= Cout, c = isq ? i - Cout : i;
@@ -943,10 +943,10 @@ __global__ void __launch_bounds__(256) dw_c1_vec_kernel(const h16 *__restrict__ 
                                                         const float *__restrict__ sc_w, int Cout, float *__restrict__ u,
                                                         double *__restrict__ t_stats, double *__restrict__ r_stats) {
     __shared__ float s_w[27];
-    __shared__ float s_sum[4];
+    __shared__ double s_sum[4];       // double: the warps' partial sums meet in a run-dependent order
     const int tid = threadIdx.x, lane = tid & 31;
     if (tid < 27) s_w[tid] = dw_w[tid];
-    if (tid < 4) s_sum[tid] = 0.f;
+    if (tid < 4) s_sum[tid] = 0.0;
     __syncthreads();
     const int n = blockIdx.z, z0 = blockIdx.y * ZC1V;
     const int W8 = W >> 3;
@@ -1020,7 +1020,7 @@ __global__ void __launch_bounds__(256) dw_c1_vec_kernel(const h16 *__restrict__ 
             }
     }
     s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
-    if (lane == 0) { atomicAdd(&s_sum[0], s0); atomicAdd(&s_sum[1], s1); atomicAdd(&s_sum[2], s2); atomicAdd(&s_sum[3], s3); }
+    if (lane == 0) { atomicAdd(&s_sum[0], (double)s0); atomicAdd(&s_sum[1], (double)s1); atomicAdd(&s_sum[2], (double)s2); atomicAdd(&s_sum[3], (double)s3); }
     __syncthreads();
     for (int i = tid; i < 2 * Cout; i += 256) {
         const int isq = i >= Cout, c = isq ? i - Cout : i;
@@ -1042,11 +1042,11 @@ __global__ void __launch_bounds__(NT) conv3_c1_kernel(
     T *__restrict__ t, int ldt, double *__restrict__ t_stats, T *__restrict__ r, int ldr, double *__restrict__ r_stats) {
     __shared__ float s_in[HZ][HY][HX + 1];
     __shared__ __align__(16) float s_w[27 * COUT + COUT];        // [tap][co], then the shortcut weights
-    __shared__ float s_stat[4 * COUT];
+    __shared__ double s_stat[4 * COUT];      // double: combined in run-dependent order
     const int tid = threadIdx.x, lane = tid & 31;
     for (int i = tid; i < 27 * COUT; i += NT) { const int tap = i / COUT, co = i % COUT; s_w[i] = wgt[(size_t)co * 27 + tap]; }
     for (int i = tid; i < COUT; i += NT) s_w[27 * COUT + i] = sc_w != nullptr ? sc_w[i] : 0.f;
-    for (int i = tid; i < 4 * COUT; i += NT) s_stat[i] = 0.f;
+    for (int i = tid; i < 4 * COUT; i += NT) s_stat[i] = 0.0;
     const int tilesX = (W + TX - 1) / TX, tilesY = (H + TY - 1) / TY, tilesZ = (D + TZ - 1) / TZ;
     const int tiles_per_sample = tilesX * tilesY * tilesZ;
     const int total_tiles = tiles_per_sample * N;
@@ -1059,11 +1059,11 @@ __global__ void __launch_bounds__(NT) conv3_c1_kernel(
         if (n < 0) return;
         for (int i = tid; i < 2 * COUT; i += NT) {
             const int isq = i >= COUT, c = isq ? i - COUT : i;
-            atomicAdd(&t_stats[(size_t)isq * N * COUT + (size_t)n * COUT + c], (double)s_stat[i]);
-            if (sc_w != nullptr) atomicAdd(&r_stats[(size_t)isq * N * COUT + (size_t)n * COUT + c], (double)s_stat[2 * COUT + i]);
+            atomicAdd(&t_stats[(size_t)isq * N * COUT + (size_t)n * COUT + c], s_stat[i]);
+            if (sc_w != nullptr) atomicAdd(&r_stats[(size_t)isq * N * COUT + (size_t)n * COUT + c], s_stat[2 * COUT + i]);
         }
         __syncthreads();
-        for (int i = tid; i < 4 * COUT; i += NT) s_stat[i] = 0.f;
+        for (int i = tid; i < 4 * COUT; i += NT) s_stat[i] = 0.0;
     };
     for (int tile = tile_begin; tile < tile_end; ++tile) {
         const int n = tile / tiles_per_sample;
@@ -1111,7 +1111,7 @@ __global__ void __launch_bounds__(NT) conv3_c1_kernel(
         for (int a = 0; a < 2; ++a) {
             if (a == 1 && sc_w == nullptr) break;
             T *op = (a == 0 ? t + vox * (size_t)ldt : r + vox * (size_t)ldr);
-            float *stat = s_stat + a * 2 * COUT;
+            double *stat = s_stat + a * 2 * COUT;
 #pragma unroll
             for (int cb = 0; cb < COUT; cb += 16) {
                 float sv[32];
@@ -1132,7 +1132,7 @@ __global__ void __launch_bounds__(NT) conv3_c1_kernel(
                 }
                 warp_transpose_sum<32>(sv, lane);
                 const int idx = warp_transpose_owner<32>(lane);
-                atomicAdd(&stat[(idx >= 16 ? COUT + idx - 16 : idx) + cb], sv[0]);
+                atomicAdd(&stat[(idx >= 16 ? COUT + idx - 16 : idx) + cb], (double)sv[0]);
             }
         }
     }
@@ -1339,7 +1339,7 @@ extern "C" int l3d_conv3_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D,
     }
     l3d_note_kernel("conv3_fwd_kernel");
     const int CC = (Cout % 32 == 0) ? 32 : (Cout % 16 == 0) ? 16 : 8;
-    const size_t smem = sizeof(float) * ((size_t)C3_CK * HZ * HY * HX + 27 * C3_CK * CC + 2 * (size_t)Cin + 2 * (size_t)Cout);
+    const size_t smem = sizeof(float) * ((size_t)C3_CK * HZ * HY * HX + 27 * C3_CK * CC + 2 * (size_t)Cin + 2 + 4 * (size_t)Cout);
     const int64_t tiles = num_tiles(N, D, H, W);
     L3D_REQUIRE(tiles < (1ll << 31), "l3d_conv3_fwd: grid too large");
     const NormDev nd = norm_dev(xn);

@@ -53,6 +53,18 @@ __device__ __forceinline__ void split_f16(float v, __half &hi, __half &lo) {
     hi = __float2half_rn(v);
     lo = __float2half_rn(v - __half2float(hi));
 }
+// fp32 storage: the operands of a product are scaled by powers of two before the hi + lo split and the accumulators scaled
+// back in the epilogue (exact).  An fp16 `lo` part is a NORMAL number only when |v| > 2^-14 * 2^11 = 0.125: below that the pair
+// carries fewer than 22 significand bits, and most weights and many activations are below that.  Unscaled, the forward GEMMs
+// were 2e-6 from fp32 per layer and the parameter gradients 3.3x further from the float64 oracle than the fp32 reference is
+// (median 1.6e-3 vs 4.9e-4 at 8 x 48^3; the CUDA-core forward: 4.8e-4).  Activations x 2^5 (finite up to |v| = 2047, values
+// beyond saturate), weights x 2^8 (|w| < 255).
+constexpr float SPLIT_AS = 32.f, SPLIT_WS = 256.f, SPLIT_INV = 1.f / (32.f * 256.f);
+__device__ __forceinline__ void split_f16_scaled(float v, float s, __half &hi, __half &lo) {
+    v = fminf(fmaxf(v * s, -65504.f), 65504.f);
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
 // 16 accumulator values of one voxel -> global (values as stored are returned in v for the statistics)
 __device__ __forceinline__ void store16(h16 *p, float (&v)[16], bool valid) {
     uint32_t pk[8];
@@ -94,7 +106,12 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
     float *s_dw = s_in + HVOX * CK;                                           // CK*27 (current chunk)
     float *s_scale = s_dw + CK * 27;                                          // Cin
     float *s_shift = s_scale + Cin;
-    float *s_stat = s_shift + Cin;                                            // 2*Cout (t) + 2*Cout (r)
+    // {sum, sum of squares} of t and r, 4*Cout DOUBLES: every partial sum that is combined in a run-dependent order (the
+    // shared-memory atomics of the warps, then the global ones) is double, so that the statistics -- and with them the stored
+    // activations, the LeakyReLU / max-pool decisions of the backward pass and the gradients -- do not depend on the run
+    // (fp32 here: forward tensors differed by 2e-6 between repetitions of one training step, individual gradient tensors by
+    // 1e-3; tools/diag_bwd_determinism.py)
+    double *s_stat = reinterpret_cast<double *>(s_shift + Cin + ((reinterpret_cast<uintptr_t>(s_shift + Cin) & 4) ? 1 : 0));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) tc::tmem_alloc(&s_tmem, (uint32_t)A.tmem_cols);
@@ -106,13 +123,13 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
         for (int i = tid; i < Cout * Cin; i += NT) {
             const int k = i % Cin, n = i / Cin;
             __half hi, lo;
-            split_f16(src[i], hi, lo);
+            if (NP == 2) split_f16_scaled(src[i], SPLIT_WS, hi, lo); else split_f16(src[i], hi, lo);
             const uint32_t off = tc::tile_off(n, k, Cout);
             *reinterpret_cast<__half *>(dst + off) = hi;
             if (NP == 2) *reinterpret_cast<__half *>(dst + b_bytes + off) = lo;
         }
     }
-    for (int i = tid; i < 4 * Cout; i += NT) s_stat[i] = 0.f;
+    for (int i = tid; i < 4 * Cout; i += NT) s_stat[i] = 0.0;
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
@@ -165,11 +182,11 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
         if (n < 0) return;
         for (int i = tid; i < 2 * Cout; i += NT) {
             const int isq = i >= Cout, cc = isq ? i - Cout : i;
-            atomicAdd(&A.t_stats[(size_t)isq * A.N * Cout + (size_t)n * Cout + cc], (double)s_stat[i]);
-            s_stat[i] = 0.f;
+            atomicAdd(&A.t_stats[(size_t)isq * A.N * Cout + (size_t)n * Cout + cc], s_stat[i]);
+            s_stat[i] = 0.0;
             if (has_sc) {
-                atomicAdd(&A.r_stats[(size_t)isq * A.N * Cout + (size_t)n * Cout + cc], (double)s_stat[2 * Cout + i]);
-                s_stat[2 * Cout + i] = 0.f;
+                atomicAdd(&A.r_stats[(size_t)isq * A.N * Cout + (size_t)n * Cout + cc], s_stat[2 * Cout + i]);
+                s_stat[2 * Cout + i] = 0.0;
             }
         }
     };
@@ -305,7 +322,8 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
 #pragma unroll
                 for (int i = 0; i < TX; ++i) {
                     __half h0, l0, h1, l1;
-                    split_f16(acc0[i], h0, l0); split_f16(acc1[i], h1, l1);
+                    if (NP == 2) { split_f16_scaled(acc0[i], SPLIT_AS, h0, l0); split_f16_scaled(acc1[i], SPLIT_AS, h1, l1); }
+                    else { split_f16(acc0[i], h0, l0); split_f16(acc1[i], h1, l1); }
                     *reinterpret_cast<__half *>(Ab + o0 + i * 16) = h0;
                     *reinterpret_cast<__half *>(Ab + o1 + i * 16) = h1;
                     if (NP == 2) {
@@ -318,7 +336,8 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
 #pragma unroll
                     for (int i = 0; i < TX; ++i) {
                         __half h0, l0, h1, l1;
-                        split_f16(ctr0[i], h0, l0); split_f16(ctr1[i], h1, l1);
+                        if (NP == 2) { split_f16_scaled(ctr0[i], SPLIT_AS, h0, l0); split_f16_scaled(ctr1[i], SPLIT_AS, h1, l1); }
+                        else { split_f16(ctr0[i], h0, l0); split_f16(ctr1[i], h1, l1); }
                         *reinterpret_cast<__half *>(As + o0 + i * 16) = h0;
                         *reinterpret_cast<__half *>(As + o1 + i * 16) = h1;
                         if (NP == 2) {
@@ -371,6 +390,8 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
                             float4 a, b;
                             a.x = h16_lo(h.x) + h16_lo(l.x); a.y = h16_hi(h.x) + h16_hi(l.x); a.z = h16_lo(h.y) + h16_lo(l.y); a.w = h16_hi(h.y) + h16_hi(l.y);
                             b.x = h16_lo(h.z) + h16_lo(l.z); b.y = h16_hi(h.z) + h16_hi(l.z); b.z = h16_lo(h.w) + h16_lo(l.w); b.w = h16_hi(h.w) + h16_hi(l.w);
+                            constexpr float ia = 1.f / SPLIT_AS;        // the operand tile holds the scaled values
+                            a.x *= ia; a.y *= ia; a.z *= ia; a.w *= ia; b.x *= ia; b.y *= ia; b.z *= ia; b.w *= ia;
                             reinterpret_cast<float4 *>(up)[0] = a;             // hi + lo: the value the pointwise GEMM multiplied
                             reinterpret_cast<float4 *>(up)[1] = b;
                         }
@@ -388,17 +409,21 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
             const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
             for (int a = 0; a < nkind; ++a) {
                 T *outp = a == 0 ? reinterpret_cast<T *>(A.t) + vox * (size_t)A.ldt : reinterpret_cast<T *>(A.r) + vox * (size_t)A.ldr;
-                float *stat = s_stat + a * 2 * Cout;
+                double *stat = s_stat + a * 2 * Cout;
                 for (int cb = 0; cb < Cout; cb += 16) {
                     float v[16];
                     tc::tmem_ld16(trow + (uint32_t)((a * MT + em) * Cout + cb), v);
+                    if (NP == 2) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] *= SPLIT_INV;
+                    }
                     store16(outp + cb, v, valid);
                     float sv[32];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) { sv[j] = v[j]; sv[16 + j] = v[j] * v[j]; }
                     warp_transpose_sum<32>(sv, lane);
                     const int idx = warp_transpose_owner<32>(lane);      // 0..15 sums, 16..31 squares
-                    atomicAdd(&stat[(idx >= 16 ? Cout + idx - 16 : idx) + cb], sv[0]);
+                    atomicAdd(&stat[(idx >= 16 ? Cout + idx - 16 : idx) + cb], (double)sv[0]);
                 }
             }
         }
@@ -413,7 +438,7 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
 static size_t tc_smem_bytes(int Cin, int Cout, bool has_sc, int NP, int ES) {
     const size_t nk = (has_sc ? 2 : 1) * (size_t)NP;
     return (size_t)HZ * HY * HX * CK * ES + 2 * nk * CHUNK_TILE + nk * (size_t)Cout * Cin * 2 +
-           sizeof(float) * ((size_t)HVOX * CK + 27 * CK + 2 * (size_t)Cin + 4 * (size_t)Cout);
+           sizeof(float) * ((size_t)HVOX * CK + 27 * CK + 2 * (size_t)Cin + 2 + 8 * (size_t)Cout);   /* statistics: 4 x Cout doubles (+ alignment) */
 }
 
 }  // namespace
@@ -505,7 +530,7 @@ __device__ __forceinline__ void split8_f16(const float4 &a, const float4 &b, uin
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         __half h0, l0, h1, l1;
-        split_f16(f[2 * j], h0, l0); split_f16(f[2 * j + 1], h1, l1);
+        split_f16_scaled(f[2 * j], SPLIT_AS, h0, l0); split_f16_scaled(f[2 * j + 1], SPLIT_AS, h1, l1);       // (fp32 storage only)
         h[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
         l[j] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
     }
@@ -529,7 +554,7 @@ __global__ void __launch_bounds__(NT) convt_tc_kernel(CtArgs A) {
     for (int i = tid; i < Cin * Cout * 8; i += NT) {      // wgt[ci][co][tap]
         const int tap = i & 7, co = (i >> 3) % Cout, ci = (i >> 3) / Cout;
         __half hi, lo;
-        split_f16(A.wgt[i], hi, lo);
+        if (NP == 2) split_f16_scaled(A.wgt[i], SPLIT_WS, hi, lo); else split_f16(A.wgt[i], hi, lo);
         const uint32_t off = tc::tile_off(tap * Cout + co, ci, NB);
         *reinterpret_cast<__half *>(sB + off) = hi;
         if (NP == 2) *reinterpret_cast<__half *>(sB + b_bytes + off) = lo;
@@ -610,7 +635,7 @@ __global__ void __launch_bounds__(NT) convt_tc_kernel(CtArgs A) {
                     float v[16];
                     tc::tmem_ld16(trow + (uint32_t)(tp * Cout + cb), v);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += s_bias[cb + j];
+                    for (int j = 0; j < 16; ++j) v[j] = (NP == 2 ? v[j] * SPLIT_INV : v[j]) + s_bias[cb + j];
                     store16(op + cb, v, ok);
                 }
             }

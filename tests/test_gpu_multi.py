@@ -62,22 +62,34 @@ def _dp_worker(rank, world, port, dtype, ret):
             ropt = torch.optim.AdamW(ref.parameters(), lr=1e-4, weight_decay=1e-5)
             rloss = DataParallelStep(ref, FocalTverskyLoss(), ropt, world_size=1).step(xs, ts)
             rgrads = {k: p.grad.detach() for k, p in ref.named_parameters()}
-            # tensors that are analytically zero (a 1-input-channel conv feeding an InstanceNorm) hold only round-off: they
-            # are bounded absolutely at 1e-4 of the largest gradient norm (as in test_gpu_train.py), the others relatively
+            # (1) against the single-process CUDA step: per-tensor rel-L2 (floor: 0.1 % of the largest gradient norm).  The two
+            # runs differ only in the fp32 summation order (4 + 4 samples all-reduced vs 8 in one launch), but this network's
+            # parameter gradients are ill-conditioned (helpers.check_gradients_like_reference): residues of sums that cancel to
+            # ~1 % move by a few per cent with the order (measured worst 2.5e-2, init_conv.shortcut.0.weight).  So this
+            # comparison only guards the SEMANTICS -- a wrong reduction (mean instead of sum, Tversky ratio per rank) shows up
+            # as O(1) differences in every tensor and in the loss -- and
+            # (2) the accuracy claim is made the way it is for the single-GPU step: against the float64 oracle on the
+            # concatenated batch, with the fp32 oracle's own error as the yardstick (fp32 storage only).
             gmax = max(float(v.norm()) for v in rgrads.values())
-            floor = 1e-3 * gmax
             errs = {}
             for k in grads:
                 d, n = float((grads[k] - rgrads[k]).norm()), float(rgrads[k].norm())
-                errs[k] = d / n if n > floor else (d / (1e-4 * gmax)) * 5e-3      # scaled so that one tolerance covers both tiers
+                errs[k] = d / max(n, 1e-3 * gmax)
+            if dtype == "f32":
+                from helpers import check_gradients_like_reference, oracle_step
+                cfg = unet_ref.UNetCfg(dropout_p=0.0)
+                sd_np = synth.synth_state_dict(unet_ref.param_shapes(cfg), 1)
+                _, _, g32 = oracle_step(cfg, sd_np, x, t, None)
+                _, _, g64 = oracle_step(cfg, sd_np, x, t, None, dtype=torch.float64)
+                check_gradients_like_reference({k: v.cpu().numpy() for k, v in grads.items()}, g32, g64, "dp2 8x24^3/f32")
             worst = max(errs, key=errs.get)
-            perr = max(float((p - q).abs().max()) for p, q in zip(model.parameters(), ref.parameters()))
+            perr = max(float((p.detach() - q.detach()).abs().max()) for p, q in zip(model.parameters(), ref.parameters()))
             ret.update(loss=float(loss), rloss=float(rloss), worst=worst, werr=errs[worst], perr=perr)
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("dtype,tol", [("f32", 5e-3), ("f16", 2e-1)])
+@pytest.mark.parametrize("dtype,tol", [("f32", 5e-2), ("f16", 2e-1)])
 def test_data_parallel_step_nccl_equals_single_process(dtype, tol):
     _need_gpus(2)
     with mp.Manager() as mgr:
@@ -108,6 +120,12 @@ def _shard_worker(rank, world, port, ret):
         if rank == 0:
             prob_1, boxes_1 = inf.infer_volume(vol, threshold=0.5, return_device=True)
             out["e2e_maxdiff"] = float((prob_s - prob_1).abs().max())
+            # the two maps differ by the round-off of two forward passes (different window batches -> different summation
+            # order of the InstanceNorm statistics), so a voxel within that distance of the threshold may flip; the box lists
+            # must be equal whenever no voxel flipped, and every flip must lie inside the round-off band
+            flips = (prob_s > 0.5) != (prob_1 > 0.5)
+            out["nflips"] = int(flips.sum())
+            out["flips_in_band"] = bool(((prob_1[flips] - 0.5).abs() <= 1e-5).all()) if out["nflips"] else True
             out["boxes_equal"] = [b["bbox_voxel"] for b in boxes_s] == [b["bbox_voxel"] for b in boxes_1]
             out["nboxes"] = len(boxes_1)
         # (b) identical predictions (a deterministic function of the window position) -> bit-identical maps
@@ -139,5 +157,7 @@ def test_window_sharded_volume_nccl():
         ret = mgr.dict()
         mp.spawn(_shard_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
         print(f"window-sharded x2: bit-identical given identical predictions: {ret['bit_identical']}; end to end max |diff| "
-              f"{ret['e2e_maxdiff']:.3e}, {ret['nboxes']} boxes, box lists equal: {ret['boxes_equal']}")
-        assert ret["bit_identical"] and ret["e2e_maxdiff"] < 1e-5 and ret["boxes_equal"]
+              f"{ret['e2e_maxdiff']:.3e}, {ret['nboxes']} boxes, box lists equal: {ret['boxes_equal']}, threshold flips: {ret['nflips']} "
+              f"(all within 1e-5 of the threshold: {ret['flips_in_band']})")
+        assert ret["bit_identical"] and ret["e2e_maxdiff"] < 1e-5 and ret["flips_in_band"]
+        assert ret["boxes_equal"] or ret["nflips"] > 0
