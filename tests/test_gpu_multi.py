@@ -62,26 +62,19 @@ def _dp_worker(rank, world, port, dtype, ret):
             ropt = torch.optim.AdamW(ref.parameters(), lr=1e-4, weight_decay=1e-5)
             rloss = DataParallelStep(ref, FocalTverskyLoss(), ropt, world_size=1).step(xs, ts)
             rgrads = {k: p.grad.detach() for k, p in ref.named_parameters()}
-            # (1) against the single-process CUDA step: per-tensor rel-L2 (floor: 0.1 % of the largest gradient norm).  The two
-            # runs differ only in the fp32 summation order (4 + 4 samples all-reduced vs 8 in one launch), but this network's
-            # parameter gradients are ill-conditioned (helpers.check_gradients_like_reference): residues of sums that cancel to
-            # ~1 % move by a few per cent with the order (measured worst 2.5e-2, init_conv.shortcut.0.weight).  So this
-            # comparison only guards the SEMANTICS -- a wrong reduction (mean instead of sum, Tversky ratio per rank) shows up
-            # as O(1) differences in every tensor and in the loss -- and
-            # (2) the accuracy claim is made the way it is for the single-GPU step: against the float64 oracle on the
-            # concatenated batch, with the fp32 oracle's own error as the yardstick (fp32 storage only).
+            # Per-tensor rel-L2 against the single-process step (floor: 0.1 % of the largest gradient norm).  The kernels
+            # combine every run-order-dependent partial sum in double, so a sample's forward tensors -- and with them every
+            # LeakyReLU / max-pool decision of its backward pass -- are the same whichever batch it sits in; what is left
+            # between 4 + 4 samples all-reduced and 8 in one launch is the fp32 summation order of the weight gradients
+            # (measured 2e-6).  A wrong reduction (mean instead of sum, Tversky ratio taken per rank) would show up as O(1)
+            # differences in every tensor and in the loss.  [Accuracy against the float64 oracle is the single-GPU tests'
+            # subject (test_gpu_configs.py): per-tensor it is dominated by rare LeakyReLU sign flips between precisions --
+            # ~1e-3 of a downstream gradient tensor each -- which hit this batch's third sample in fp32-storage mode.]
             gmax = max(float(v.norm()) for v in rgrads.values())
             errs = {}
             for k in grads:
                 d, n = float((grads[k] - rgrads[k]).norm()), float(rgrads[k].norm())
                 errs[k] = d / max(n, 1e-3 * gmax)
-            if dtype == "f32":
-                from helpers import check_gradients_like_reference, oracle_step
-                cfg = unet_ref.UNetCfg(dropout_p=0.0)
-                sd_np = synth.synth_state_dict(unet_ref.param_shapes(cfg), 1)
-                _, _, g32 = oracle_step(cfg, sd_np, x, t, None)
-                _, _, g64 = oracle_step(cfg, sd_np, x, t, None, dtype=torch.float64)
-                check_gradients_like_reference({k: v.cpu().numpy() for k, v in grads.items()}, g32, g64, "dp2 8x24^3/f32")
             worst = max(errs, key=errs.get)
             perr = max(float((p.detach() - q.detach()).abs().max()) for p, q in zip(model.parameters(), ref.parameters()))
             ret.update(loss=float(loss), rloss=float(rloss), worst=worst, werr=errs[worst], perr=perr)
@@ -89,7 +82,7 @@ def _dp_worker(rank, world, port, dtype, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("dtype,tol", [("f32", 5e-2), ("f16", 2e-1)])
+@pytest.mark.parametrize("dtype,tol", [("f32", 1e-4), ("f16", 1e-4)])
 def test_data_parallel_step_nccl_equals_single_process(dtype, tol):
     _need_gpus(2)
     with mp.Manager() as mgr:
@@ -98,7 +91,7 @@ def test_data_parallel_step_nccl_equals_single_process(dtype, tol):
         print(f"dp2/{dtype}: loss {ret['loss']:.7f} vs single-process {ret['rloss']:.7f}; worst per-tensor gradient rel-L2 "
               f"{ret['werr']:.3e} ({ret['worst']}); max |param - param_single| after AdamW {ret['perr']:.3e}")
         assert abs(ret["loss"] - ret["rloss"]) < 1e-5
-        assert ret["werr"] < tol and ret["perr"] < 2.1e-4          # one AdamW step moves a parameter by at most lr = 1e-4
+        assert ret["werr"] < tol and ret["perr"] < 1e-5            # same gradient signs: AdamW's first step moves both by the same +-lr
 
 
 def _shard_worker(rank, world, port, ret):
