@@ -526,6 +526,90 @@ __global__ void __launch_bounds__(256, 3) merge_fwd_kernel(
     }
 }
 
+// The same with one thread per x-COLUMN of a cell (its 2 x 2 (z, y) voxels) and 16-byte channel vector: the lanes of a
+// warp then cover CONSECUTIVE voxels of a row, so a load instruction reads 512 contiguous bytes (the cell-per-thread
+// mapping above strides over every other voxel: ncu, 325 windows at 48^3, counted 64 % of the peak LSU wavefront rate
+// at 53 % of the DRAM rate -- half of every 128-byte line requested by an instruction belonged to the next one).  The
+// pooled maximum needs the other x-column of the cell: one shuffle with lane ^ CQ (CQ = C / V lanes per voxel, a power of
+// two <= 16; the host falls back to the cell-per-thread kernel otherwise).
+template <typename T, bool R1>
+__global__ void __launch_bounds__(256, 3) merge_col_fwd_kernel(
+    const T *__restrict__ t2, int ld2, NormDev n2, const T *__restrict__ r, int ldr, NormDev nr, const float *__restrict__ r1_w,
+    int N, int C, int D, int H, int W, float slope,
+    T *__restrict__ out, int ldo, T *__restrict__ pooled, int ldp) {
+    constexpr int V = VecW<T>::V;
+    extern __shared__ float sm[];
+    float *s_sc2 = sm, *s_sh2 = sm + C, *s_scr = sm + 2 * C, *s_shr = sm + 3 * C;
+    const int n = blockIdx.y;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        norm_scale_shift(n2, N, C, n, c, s_sc2[c], s_sh2[c]);
+        norm_scale_shift(nr, N, C, n, c, s_scr[c], s_shr[c]);
+        s_sh2[c] += s_shr[c];
+        if (R1) s_scr[c] *= r1_w[c];
+    }
+    __syncthreads();
+    const int CD = (D + 1) / 2, CH = (H + 1) / 2, CW2 = 2 * ((W + 1) / 2), CQ = C / V;
+    const int PD = D / 2, PH = H / 2, PW = W / 2;
+    const int cq_sh = __ffs(CQ) - 1;
+    const uint32_t total = (uint32_t)CD * CH * CW2 * CQ;             // a multiple of 2 * CQ; rounded up to whole warps below
+    const uint32_t total_round = (total + 31u) & ~31u;
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total_round; idx += gridDim.x * blockDim.x) {
+        const bool in_range = idx < total;
+        uint32_t rem = idx;
+        const int q = (int)(rem & (uint32_t)(CQ - 1)); rem >>= cq_sh;
+        const int xx = (int)(rem % (uint32_t)CW2); rem /= (uint32_t)CW2;
+        const int cy = (int)(rem % (uint32_t)CH);
+        const int cz = (int)(rem / (uint32_t)CH);
+        const int c = q * V;
+        const float *sc2 = s_sc2 + c, *sh2 = s_sh2 + c, *scr = s_scr + c;
+        float mx[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) mx[j] = -INFINITY;
+        uint4 ra[4], rb[4];
+        float xr[4];
+        bool ok[4];
+        size_t vox[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                 // all raw loads of the column are issued first
+            const int z = cz * 2 + (k >> 1), y = cy * 2 + (k & 1);
+            ok[k] = in_range && z < D && y < H && xx < W;
+            vox[k] = (((size_t)n * D + z) * H + y) * W + xx;
+            if (ok[k]) {
+                ra[k] = ldraw(t2 + vox[k] * ld2 + c);
+                if (R1) xr[k] = ld1(r + vox[k] * ldr); else rb[k] = ldraw(r + vox[k] * ldr + c);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (ok[k]) {
+                float a[V], b[V], o[V];
+                cvt_raw(t2, ra[k], a);
+                if (R1) {
+#pragma unroll
+                    for (int j = 0; j < V; ++j) b[j] = xr[k];
+                } else {
+                    cvt_raw(t2, rb[k], b);
+                }
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    o[j] = lrelu(fmaf(a[j], sc2[j], fmaf(b[j], scr[j], sh2[j])), slope);
+                    mx[j] = fmaxf(mx[j], round_as(t2, o[j]));      // pool the values as stored (the backward arg-max sees them)
+                }
+                if (out != nullptr) stv(out + vox[k] * ldo + c, o);
+            }
+        }
+        if (pooled != nullptr) {                        // warp-uniform: every lane takes part in the exchange
+#pragma unroll
+            for (int j = 0; j < V; ++j) mx[j] = fmaxf(mx[j], __shfl_xor_sync(0xffffffffu, mx[j], CQ));
+            const int cx = xx >> 1;
+            if (in_range && (xx & 1) == 0 && cz < PD && cy < PH && cx < PW) {
+                const size_t pv = (((size_t)n * PD + cz) * PH + cy) * PW + cx;
+                stv(pooled + pv * ldp + c, mx);
+            }
+        }
+    }
+}
+
 // Residual merge + 1x1x1 head + sigmoid: one thread = one voxel, all channels (C <= 64).
 template <typename T, int CMAX>
 __global__ void __launch_bounds__(256) merge_head_fwd_kernel(
@@ -590,7 +674,8 @@ __global__ void __launch_bounds__(256) merge_head_fwd_kernel(
 // (8 channels = one 16-byte vector per tensor), so every load / store instruction of a warp covers 512 contiguous bytes,
 // the lane pair adds its two partial head sums with one shuffle, and 40 registers keep the SM's warp slots full (the
 // voxel-per-thread kernel above: 119 registers, 24 % of the warp slots, 3.6 TB/s).  Two voxel halves per thread in flight.
-__global__ void __launch_bounds__(256, 4) merge_head16_fwd_kernel(
+template <int U>
+__global__ void __launch_bounds__(256, (U > 2 ? 3 : 4)) merge_head16_fwd_kernel(
     const h16 *__restrict__ t2, int ld2, NormDev n2, const h16 *__restrict__ r, int ldr, NormDev nr,
     int N, size_t nvox, float slope, h16 *__restrict__ out, int ldo,
     const float *__restrict__ head_w, const float *__restrict__ head_b, int OC,
@@ -610,11 +695,11 @@ __global__ void __launch_bounds__(256, 4) merge_head16_fwd_kernel(
     const int h = threadIdx.x & 1;
     const float *sc2 = s_sc2 + h * 8, *sh2 = s_sh2 + h * 8, *scr = s_scr + h * 8;     // read from shared memory in the loop: no spills at 64 registers
     const size_t total = 2 * nvox, stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 2 * stride) {
-        uint4 ra[2], rb[2];
-        bool ok[2];
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += U * stride) {
+        uint4 ra[U], rb[U];
+        bool ok[U];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) {
             const size_t i = i0 + u * stride;
             ok[u] = i < total;                       // both lanes of a pair share the voxel, so they agree
             if (ok[u]) {
@@ -624,7 +709,7 @@ __global__ void __launch_bounds__(256, 4) merge_head16_fwd_kernel(
             }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) {
             if (!ok[u]) continue;
             const size_t v = (i0 + u * stride) >> 1, vox = (size_t)n * nvox + v;
             float a[8], b[8], o[8];
@@ -1399,7 +1484,11 @@ extern "C" int l3d_merge_fwd(const l3d_act *t2, const l3d_norm *n2, const l3d_ac
             const size_t caph = (148 * 16 + (size_t)N - 1) / (size_t)N;
             if (gh > caph) gh = caph;
             dim3 gridh((unsigned)gh, (unsigned)N);
-            merge_head16_fwd_kernel<<<gridh, 256, 0, st>>>((const h16 *)t2->ptr, t2->ldc, d2, (const h16 *)r->ptr, r->ldc, dr, N, nvox, slope,
+            if (L3D_ENV_INT("L3D_HEAD16_U", 2) == 4)
+                merge_head16_fwd_kernel<4><<<gridh, 256, 0, st>>>((const h16 *)t2->ptr, t2->ldc, d2, (const h16 *)r->ptr, r->ldc, dr, N, nvox, slope,
+                                                              has_out ? (h16 *)out->ptr : nullptr, has_out ? out->ldc : 0, head_w, head_b, OC, prob, logits);
+            else
+            merge_head16_fwd_kernel<2><<<gridh, 256, 0, st>>>((const h16 *)t2->ptr, t2->ldc, d2, (const h16 *)r->ptr, r->ldc, dr, N, nvox, slope,
                                                           has_out ? (h16 *)out->ptr : nullptr, has_out ? out->ldc : 0, head_w, head_b, OC, prob, logits);
             l3d_count_launch();
             L3D_CUDA_OK("l3d_merge_fwd (head) launch");
@@ -1430,6 +1519,18 @@ extern "C" int l3d_merge_fwd(const l3d_act *t2, const l3d_norm *n2, const l3d_ac
         const size_t cap = (148 * 32 + N - 1) / N;
         if (blocks > cap) blocks = cap;
         dim3 grid((unsigned)blocks, (unsigned)N);
+        const int CQ = C / V;
+        if ((CQ & (CQ - 1)) == 0 && CQ <= 16 && L3D_ENV_INT("L3D_MERGE_CELL", 0) <= 0) {
+            // thread = x-column of a cell: twice the threads of the cell mapping (L3D_MERGE_CELL=1: cell per thread)
+            size_t blocks2 = (2 * total + 255) / 256;
+            if (blocks2 > cap) blocks2 = cap;
+            dim3 grid2((unsigned)blocks2, (unsigned)N);
+            L3D_DISPATCH_DTYPE(t2->dtype, T, {
+                merge_col_fwd_kernel<T, false><<<grid2, 256, sizeof(float) * 4 * C, st>>>((const T *)t2->ptr, t2->ldc, d2, (const T *)r->ptr, r->ldc, dr, nullptr, N, C, D, H, W, slope,
+                                                                       has_out ? (T *)out->ptr : nullptr, has_out ? out->ldc : 0,
+                                                                       has_pool ? (T *)pooled->ptr : nullptr, has_pool ? pooled->ldc : 0);
+            });
+        } else
         L3D_DISPATCH_DTYPE(t2->dtype, T, {
             merge_fwd_kernel<T, false><<<grid, 256, sizeof(float) * 4 * C, st>>>((const T *)t2->ptr, t2->ldc, d2, (const T *)r->ptr, r->ldc, dr, nullptr, N, C, D, H, W, slope,
                                                                    has_out ? (T *)out->ptr : nullptr, has_out ? out->ldc : 0,
@@ -1505,6 +1606,19 @@ extern "C" int l3d_merge_fwd_rank1(const l3d_act *t2, const l3d_norm *n2, const 
     const size_t cap = (148 * 32 + N - 1) / N;
     if (blocks > cap) blocks = cap;
     dim3 grid((unsigned)blocks, (unsigned)N);
+    const int CQ = C / V;
+    // column-per-thread mapping: measured SLOWER for the rank-1 shortcut (325 windows of 48^3: 634 vs 568 us; the plain merge
+    // gains 18 %, 730 -> 617 us), so it is opt-in here (L3D_MERGE_CELL=-1) and the default above
+    if ((CQ & (CQ - 1)) == 0 && CQ <= 16 && L3D_ENV_INT("L3D_MERGE_CELL", 0) == -1) {
+        size_t blocks2 = (2 * total + 255) / 256;
+        if (blocks2 > cap) blocks2 = cap;
+        dim3 grid2((unsigned)blocks2, (unsigned)N);
+        L3D_DISPATCH_DTYPE(t2->dtype, T, {
+            merge_col_fwd_kernel<T, true><<<grid2, 256, sizeof(float) * 4 * C, (cudaStream_t)stream>>>(
+                (const T *)t2->ptr, t2->ldc, d2, (const T *)x1->ptr, x1->ldc, dr, r1_w, N, C, D, H, W, slope,
+                has_out ? (T *)out->ptr : nullptr, has_out ? out->ldc : 0, has_pool ? (T *)pooled->ptr : nullptr, has_pool ? pooled->ldc : 0);
+        });
+    } else
     L3D_DISPATCH_DTYPE(t2->dtype, T, {
         merge_fwd_kernel<T, true><<<grid, 256, sizeof(float) * 4 * C, (cudaStream_t)stream>>>(
             (const T *)t2->ptr, t2->ldc, d2, (const T *)x1->ptr, x1->ldc, dr, r1_w, N, C, D, H, W, slope,

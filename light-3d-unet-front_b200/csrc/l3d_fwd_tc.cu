@@ -78,6 +78,18 @@ __device__ __forceinline__ void store16(h16 *p, float (&v)[16], bool valid) {
         *reinterpret_cast<uint4 *>(p + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     }
 }
+// The same as ONE 256-bit store (STG.E.256, sm_100): p must be 32-byte aligned.  A lane's 16 channels are one 32-byte
+// sector; with two 16-byte stores a warp whose lanes write to 32 different 128-byte lines pays 64 LSU wavefronts per
+// voxel row instead of 32 (ConvTranspose pixel shuffle: ncu counted 76 % of the peak LSU wavefront rate at 37 % DRAM).
+__device__ __forceinline__ void store16_256(h16 *p, const float (&v)[16], bool valid) {
+    if (valid) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pk[j] = pack_h16x2(v[2 * j], v[2 * j + 1]);
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]),
+                     "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+    }
+}
 __device__ __forceinline__ void store16(float *p, float (&v)[16], bool valid) {
     if (valid) {
 #pragma unroll
@@ -87,6 +99,8 @@ __device__ __forceinline__ void store16(float *p, float (&v)[16], bool valid) {
         for (int j = 0; j < 16; ++j) v[j] = 0.f;
     }
 }
+
+__device__ __forceinline__ void store16_256(float *p, float (&v)[16], bool valid) { store16(p, v, valid); }
 
 template <typename T>
 __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs A) {
@@ -520,7 +534,7 @@ struct CtArgs {
     int N, d, h, w;
     const float *wgt, *bias; int Cout;
     void *out; int ldo; int OD, OH, OW, oz, oy, ox;
-    int tmem_cols;
+    int tmem_cols, wide_st;
 };
 
 // eight fp32 values -> fp16 hi / lo vectors
@@ -597,6 +611,7 @@ __global__ void __launch_bounds__(NT) convt_tc_kernel(CtArgs A) {
     int buf = 0;
     const int erow = (warp & 3) * 32 + lane, tap0 = (warp >> 2) * 4;
     T *outp = reinterpret_cast<T *>(A.out);
+    const bool wide_st = A.wide_st != 0;                 // 32-byte aligned 16-channel blocks (host check)
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
         if (tid == 0) {
             tc::fence_after_sync();
@@ -636,7 +651,7 @@ __global__ void __launch_bounds__(NT) convt_tc_kernel(CtArgs A) {
                     tc::tmem_ld16(trow + (uint32_t)(tp * Cout + cb), v);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] = (NP == 2 ? v[j] * SPLIT_INV : v[j]) + s_bias[cb + j];
-                    store16(op + cb, v, ok);
+                    if (wide_st) store16_256(op + cb, v, ok); else store16(op + cb, v, ok);
                 }
             }
         }
@@ -672,6 +687,7 @@ int l3d_convt_fwd_tc(const l3d_act *x, int N, int d, int h, int w_, const float 
     A.wgt = w; A.bias = b; A.Cout = Cout;
     A.out = out->ptr; A.ldo = out->ldc; A.OD = OD; A.OH = OH; A.OW = OW; A.oz = oz; A.oy = oy; A.ox = ox;
     A.tmem_cols = cols;
+    A.wide_st = (!f32 && out->ldc % 16 == 0 && reinterpret_cast<uintptr_t>(out->ptr) % 32 == 0 && L3D_ENV_INT("L3D_CONVT_ST256", 1) != 0) ? 1 : 0;
     {
         cudaError_t e = f32 ? cudaFuncSetAttribute(convt_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)
                             : cudaFuncSetAttribute(convt_tc_kernel<h16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
