@@ -92,6 +92,15 @@ int l3d_dw_c1_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int
                   const float *dw_w, const float *pw_w, const float *sc_w, int Cout,
                   float *u, double *t_stats, double *r_stats, void *stream);
 
+/* l3d_dwpw_fwd on the channel concatenation [x_lo | x_hi] of two DENSE 16-channel fp16 tensors (inference): the decoder
+ * block of the top level reads the ConvTranspose3d output and the encoder skip as two tensors, so torch.cat
+ * (unet3d.py:140) is not materialised AND both producers write whole cache lines (an interleaved [up | skip] buffer is
+ * written as 32-byte halves of 64-byte voxels: measured 368 vs 274 us for the transposed conv, 549 vs 476 us for the
+ * encoder merge at 325 windows of 48^3).  Implicit-GEMM kernel only; returns an error when it does not take the shape. */
+int l3d_dwpw_fwd2(const l3d_act *x_lo, const l3d_act *x_hi, const l3d_norm *xn, int N, int D, int H, int W,
+                  const float *dw_w, const float *pw_w, const float *sc_w,
+                  const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats, void *stream);
+
 /* l3d_dwpw_fwd on an input that is never materialised: x[v][c] = r1_w[c] * u[v] (Cin = 16 channels) with u from
  * l3d_dw_c1_fwd and xn the norm of that rank-1 tensor (its statistics come from l3d_dw_c1_fwd).  Replaces the second
  * DepthwiseSeparableConv3d of the first block (unet3d.py:55-63,82-86) without the 16-channel intermediate ever touching

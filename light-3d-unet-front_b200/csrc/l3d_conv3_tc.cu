@@ -113,7 +113,7 @@ __device__ __forceinline__ void worker_bar_n() { asm volatile("bar.sync 1, %0;" 
 // MMAs of item it-1 have completed -- BEFORE item it is activated -- so warp 0 of the workers requests box it+1 at the top of
 // iteration it and the TMA unit always has the next box queued.  (Measured slower than the fixed roles, see the host side.)
 template <int TZ, bool MERGE, int NWARPS, bool R1 = false, bool LD = false>
-__global__ void __launch_bounds__(NWARPS * 32 + 32 + (NWARPS == 12 && !LD ? 32 : 0), (TZ > 6 || NWARPS > 8 ? 1 : 2)) conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, C3Args A) {
+__global__ void __launch_bounds__(NWARPS * 32 + 32 + (NWARPS == 12 && !LD ? 32 : 0), (TZ > 6 || NWARPS > 8 ? 1 : 2)) conv3_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap2, C3Args A) {
     using G = Geo<TZ>;
     constexpr bool PRODW = NWARPS == 12 && !LD;            // a third role: one warp that only requests halo boxes
     constexpr int NW = NWARPS * 32, NT = NW + 32 + (PRODW ? 32 : 0);   // worker warps + 1 issuer warp (+ 1 producer warp)
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32 + (NWARPS == 12 && !LD ? 32 :
                 unsigned char *dst = s_raw + (size_t)rb * RAW_STRIDE + (size_t)sl * sl_bytes;
                 const int zc = pf_z0 - 1 + sl * zs;
                 if (R1) tc::tma_load_4d(dst, &tmap, &s_tma_full[rb], pf_x0 - R1_X0, pf_y0 - 1, zc, pf_n);
-                else if (A.merged_cx) tc::tma_load_4d(dst, &tmap, &s_tma_full[rb], (pf_x0 - 1) * CK, pf_y0 - 1, zc, pf_n);
+                else if (A.merged_cx) tc::tma_load_4d(dst, pf_ch ? &tmap2 : &tmap, &s_tma_full[rb], (pf_x0 - 1) * CK, pf_y0 - 1, zc, pf_n);
                 else tc::tma_load_5d(dst, &tmap, &s_tma_full[rb], pf_ch * CK, pf_x0 - 1, pf_y0 - 1, zc, pf_n);
             }
         }
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32 + (NWARPS == 12 && !LD ? 32 :
                         tc::mbar_expect_tx(&s_tma_full[h], HALF_BYTES);
                         unsigned char *dst = s_raw + (size_t)h * HALF_BYTES;
                         const int zc = pf_z0 - 1 + h * (G::HZ / 2);
-                        if (A.merged_cx) tc::tma_load_4d(dst, &tmap, &s_tma_full[h], (pf_x0 - 1) * CK, pf_y0 - 1, zc, pf_n);
+                        if (A.merged_cx) tc::tma_load_4d(dst, pf_ch ? &tmap2 : &tmap, &s_tma_full[h], (pf_x0 - 1) * CK, pf_y0 - 1, zc, pf_n);
                         else tc::tma_load_5d(dst, &tmap, &s_tma_full[h], pf_ch * CK, pf_x0 - 1, pf_y0 - 1, zc, pf_n);
                     }
                     __syncwarp();
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(NWARPS * 32 + 32 + (NWARPS == 12 && !LD ? 32 :
             const int b3 = j % 3;
             unsigned char *dst = smem_raw + (size_t)slot_x(j) * G::A_BYTES;
             tc::mbar_expect_tx(&s_tma_full[b3], G::RAW_BYTES);
-            if (A.merged_cx) tc::tma_load_4d(dst, &tmap, &s_tma_full[b3], (x0 - 1) * CK, y0 - 1, z0 - 1, n);
+            if (A.merged_cx) tc::tma_load_4d(dst, chunk ? &tmap2 : &tmap, &s_tma_full[b3], (x0 - 1) * CK, y0 - 1, z0 - 1, n);
             else tc::tma_load_5d(dst, &tmap, &s_tma_full[b3], chunk * CK, x0 - 1, y0 - 1, z0 - 1, n);
         };
         if (rot && tid == 0 && n_items > 0) {
@@ -696,6 +696,10 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
                     const float *w, int groups, const float *dw_w, const float *pw_w, const float *sc_w,
                     const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats, int stat_ld, int co0, int cout_total,
                     const float *r1_w, void *stream);
+int l3d_conv3_tc_ex2(const l3d_act *x, const l3d_act *x2, const l3d_norm *xn, int N, int D, int H, int W,
+                     const float *w, int groups, const float *dw_w, const float *pw_w, const float *sc_w,
+                     const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats, int stat_ld, int co0, int cout_total,
+                     const float *r1_w, void *stream);
 int l3d_conv3_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, int W,
                  const float *w, int groups, const float *dw_w, const float *pw_w, const float *sc_w,
                  const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats, int stat_ld, int co0, int cout_total,
@@ -706,9 +710,21 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
                     const float *w, int groups, const float *dw_w, const float *pw_w, const float *sc_w,
                     const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats, int stat_ld, int co0, int cout_total,
                     const float *r1_w, void *stream) {
+    return l3d_conv3_tc_ex2(x, nullptr, xn, N, D, H, W, w, groups, dw_w, pw_w, sc_w, t, t_stats, r, r_stats, stat_ld, co0, cout_total, r1_w, stream);
+}
+// x2 != NULL: the input is the channel concatenation [x | x2] of two DENSE 16-channel tensors (a decoder block reading
+// [ConvTranspose output | skip] without an interleaved concat buffer): one channel chunk per tensor, each fetched through
+// its own tensor map with the merged (C, W) box rows.
+int l3d_conv3_tc_ex2(const l3d_act *x, const l3d_act *x2, const l3d_norm *xn, int N, int D, int H, int W,
+                     const float *w, int groups, const float *dw_w, const float *pw_w, const float *sc_w,
+                     const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats, int stat_ld, int co0, int cout_total,
+                     const float *r1_w, void *stream) {
     const bool rank1 = r1_w != nullptr;
     if (L3D_ENV_INT("L3D_NO_IGEMM", 0) == 1) return -1;
-    const int Cin = x->C, Cout = t->C;
+    const bool split = x2 != nullptr;
+    if (split && (rank1 || x->C != CK || x2->C != CK || x->ldc != CK || x2->ldc != CK || x2->dtype != x->dtype ||
+                  reinterpret_cast<uintptr_t>(x2->ptr) % 16 != 0)) return -1;
+    const int Cin = x->C + (split ? x2->C : 0), Cout = t->C;
     const bool has_sc = sc_w != nullptr;
     if (x->dtype != L3D_F16 || t->dtype != L3D_F16) return -1;
     if (Cin % 16 != 0 || Cout % 16 != 0 || Cout > 256) return -1;
@@ -787,14 +803,14 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
     // 1033 -> 935 us; slower than TMA on the one- and two-chunk 48^3 layers: 1035 -> 1327 us, 1897 -> 2455 us); 2: wherever
     // possible; 0: never
     const int ld_mode = L3D_ENV_INT("L3D_C3_LOADER", 1);
-    const bool use_loader = (ld_mode == 2 || (ld_mode == 1 && nraw == 1 && Cin / CK >= 4)) && (long long)(TZ + 2) * H * W * x->ldc * 2 < (1ll << 31);
+    const bool use_loader = !split && (ld_mode == 2 || (ld_mode == 1 && nraw == 1 && Cin / CK >= 4)) && (long long)(TZ + 2) * H * W * x->ldc * 2 < (1ll << 31);
     const bool rot_mode = !rank1 && nabuf == 2 && !(nwarps == 12 && use_loader) && nraw == 1 && tma_split == 1 && L3D_ENV_INT("L3D_C3_ROT", 0) != 0 && smem + 128 <= 226 * 1024;
     // the producer warp exists in the 12-worker TMA variants
     const bool prod_mode = nwarps == 12 && !(use_loader && !rank1) && !rot_mode && L3D_ENV_INT("L3D_C3_PROD", 1) != 0;
     const bool split2 = prod_mode && !rank1 && nraw == 1 && tma_split == 1 && (TZ + 2) % 2 == 0 && L3D_ENV_INT("L3D_C3_SPLIT2", 1) != 0;
     const cuuint32_t box_z = (cuuint32_t)(split2 ? (TZ + 2) / 2 : (TZ + 2) / tma_split);
-    const bool merged_cx = !rank1 && Cin == CK && x->ldc == CK && L3D_ENV_INT("L3D_C3_NOMERGECX", 0) == 0;
-    CUtensorMap tmap;
+    const bool merged_cx = split || (!rank1 && Cin == CK && x->ldc == CK && L3D_ENV_INT("L3D_C3_NOMERGECX", 0) == 0);
+    CUtensorMap tmap, tmap2;
     if (rank1) {
         const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
         const cuuint64_t rowb = (cuuint64_t)W * 4;
@@ -811,6 +827,8 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
         const cuuint32_t estr[4] = {1, 1, 1, 1};
         if (l3d_encode_tiled(&tmap, (int)CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x->ptr, (const unsigned long long *)dims,
                              (const unsigned long long *)strides, (const unsigned *)box, (const unsigned *)estr)) return 3;
+        if (split && l3d_encode_tiled(&tmap2, (int)CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, x2->ptr, (const unsigned long long *)dims,
+                                      (const unsigned long long *)strides, (const unsigned *)box, (const unsigned *)estr)) return 3;
     } else {
         const cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
         const cuuint64_t es = 2, ld = (cuuint64_t)x->ldc;
@@ -820,6 +838,7 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
         if (l3d_encode_tiled(&tmap, (int)CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, x->ptr, (const unsigned long long *)dims,
                              (const unsigned long long *)strides, (const unsigned *)box, (const unsigned *)estr)) return 3;
     }
+    if (!split) tmap2 = tmap;
     C3Args A;
     A.Cin = Cin; A.xn = norm_dev(xn);
     A.N = N; A.D = D; A.H = H; A.W = W;
@@ -849,7 +868,7 @@ int l3d_conv3_tc_ex(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
             if (e != cudaSuccess) { l3d_set_error("conv3_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 3; } \
             if (dev >= 0 && dev < 64) attr_set_[dev] = true;                                                                                                \
         }                                                                                                                   \
-        conv3_tc_kernel<TZV, MG, NWV, R1V, LDV><<<(unsigned)grid, NWV * 32 + 32 + ((NWV) == 12 && !(LDV) ? 32 : 0), smem_launch, (cudaStream_t)stream>>>(tmap, A); \
+        conv3_tc_kernel<TZV, MG, NWV, R1V, LDV><<<(unsigned)grid, NWV * 32 + 32 + ((NWV) == 12 && !(LDV) ? 32 : 0), smem_launch, (cudaStream_t)stream>>>(tmap, tmap2, A); \
     } while (0)
     /* thread-private cp.async staging instead of TMA: with 12 worker warps (one CTA per SM), not for the rank-1 input */
 #define L3D_C3_LAUNCH_R(TZV, MG, NWV, R1V)                                                                                          \

@@ -739,6 +739,168 @@ __global__ void __launch_bounds__(256, (U > 2 ? 3 : 4)) merge_head16_fwd_kernel(
     }
 }
 
+// ---- 256-bit global accesses (LDG / STG.E.256, sm_100): one instruction moves the 16 fp16 channels of a voxel ----------
+struct U8 { uint32_t w[8]; };
+__device__ __forceinline__ U8 ld256(const h16 *p) {
+    U8 r;
+    asm("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7]) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st256(h16 *p, const U8 &v) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]), "r"(v.w[3]),
+                 "r"(v.w[4]), "r"(v.w[5]), "r"(v.w[6]), "r"(v.w[7]) : "memory");
+}
+
+// Residual merge + head for C = 16, fp16 storage, one thread per VOXEL: two 32-byte loads and (optionally) one 32-byte
+// store per voxel, no lane-pair exchange for the head sum.  Needs 32-byte aligned voxels (host check).
+__global__ void __launch_bounds__(256, 3) merge_head16v_fwd_kernel(
+    const h16 *__restrict__ t2, int ld2, NormDev n2, const h16 *__restrict__ r, int ldr, NormDev nr,
+    int N, size_t nvox, float slope, h16 *__restrict__ out, int ldo,
+    const float *__restrict__ head_w, const float *__restrict__ head_b, int OC,
+    float *__restrict__ prob, float *__restrict__ logits) {
+    constexpr int C = 16;
+    __shared__ __align__(16) float s_sc2[C], s_sh2[C], s_scr[C], s_hw[4 * C];
+    const int n = blockIdx.y;
+    if (threadIdx.x < C) {
+        const int c = threadIdx.x;
+        float a, b, cc, d;
+        norm_scale_shift(n2, N, C, n, c, a, b);
+        norm_scale_shift(nr, N, C, n, c, cc, d);
+        s_sc2[c] = a; s_sh2[c] = b + d; s_scr[c] = cc;
+        for (int oc = 0; oc < 4; ++oc) s_hw[oc * C + c] = oc < OC ? head_w[(size_t)oc * C + c] : 0.f;
+    }
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvox; i0 += 2 * stride) {
+        U8 ra[2], rb[2];
+        bool ok[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const size_t i = i0 + u * stride;
+            ok[u] = i < nvox;
+            if (ok[u]) {
+                const size_t vox = (size_t)n * nvox + i;
+                ra[u] = ld256(t2 + vox * ld2);
+                rb[u] = ld256(r + vox * ldr);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!ok[u]) continue;
+            const size_t v = i0 + u * stride, vox = (size_t)n * nvox + v;
+            float o[16];
+            U8 pk;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float a0 = h16_lo(ra[u].w[j]), a1 = h16_hi(ra[u].w[j]), b0 = h16_lo(rb[u].w[j]), b1 = h16_hi(rb[u].w[j]);
+                const float o0 = lrelu(fmaf(a0, s_sc2[2 * j], fmaf(b0, s_scr[2 * j], s_sh2[2 * j])), slope);
+                const float o1 = lrelu(fmaf(a1, s_sc2[2 * j + 1], fmaf(b1, s_scr[2 * j + 1], s_sh2[2 * j + 1])), slope);
+                pk.w[j] = pack_h16x2(o0, o1);
+                o[2 * j] = h16_lo(pk.w[j]); o[2 * j + 1] = h16_hi(pk.w[j]);      // the head sees the values as stored
+            }
+            if (out != nullptr) st256(out + vox * ldo, pk);
+            for (int oc = 0; oc < OC; ++oc) {
+                float acc = 0.f;
+                if (oc < 4) {
+                    // same summation order as the half-voxel kernel: channels 0-7 and 8-15 separately, then added
+                    float lo = 0.f, hi = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { lo = fmaf(o[j], s_hw[oc * C + j], lo); hi = fmaf(o[8 + j], s_hw[oc * C + 8 + j], hi); }
+                    acc = lo + hi;
+                } else {
+                    float lo = 0.f, hi = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { lo = fmaf(o[j], head_w[(size_t)oc * C + j], lo); hi = fmaf(o[8 + j], head_w[(size_t)oc * C + 8 + j], hi); }
+                    acc = lo + hi;
+                }
+                acc += head_b[oc];
+                const size_t oi = ((size_t)n * OC + oc) * nvox + v;
+                if (logits != nullptr) logits[oi] = acc;
+                prob[oi] = 1.f / (1.f + expf(-acc));
+            }
+        }
+    }
+}
+
+// Rank-1 residual merge (+ MaxPool3d(2)) for C = 16, fp16 storage: one thread per x-column of a cell (its 2 x 2 (z, y)
+// voxels), all 16 channels -- a warp's load covers 32 consecutive voxels (1 KB), every store is a whole 32-byte sector of
+// the concat buffer, and the pooled maximum needs one exchange with the neighbouring lane.
+__global__ void __launch_bounds__(256, 3) merge_col16_r1_fwd_kernel(
+    const h16 *__restrict__ t2, int ld2, NormDev n2, const h16 *__restrict__ x, int ldx, NormDev nr, const float *__restrict__ r1_w,
+    int N, int D, int H, int W, float slope, h16 *__restrict__ out, int ldo, h16 *__restrict__ pooled, int ldp) {
+    constexpr int C = 16;
+    __shared__ __align__(16) float s_sc2[C], s_sh2[C], s_scr[C];
+    const int n = blockIdx.y;
+    if (threadIdx.x < C) {
+        const int c = threadIdx.x;
+        float a, b, cc, d;
+        norm_scale_shift(n2, N, C, n, c, a, b);
+        norm_scale_shift(nr, N, C, n, c, cc, d);
+        s_sc2[c] = a; s_sh2[c] = b + d; s_scr[c] = cc * r1_w[c];
+    }
+    __syncthreads();
+    const int CD = (D + 1) / 2, CH = (H + 1) / 2, CW2 = 2 * ((W + 1) / 2);
+    const int PD = D / 2, PH = H / 2, PW = W / 2;
+    const uint32_t total = (uint32_t)CD * CH * CW2;
+    const uint32_t total_round = (total + 31u) & ~31u;
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total_round; idx += gridDim.x * blockDim.x) {
+        const bool in_range = idx < total;
+        uint32_t rem = idx;
+        const int xx = (int)(rem % (uint32_t)CW2); rem /= (uint32_t)CW2;
+        const int cy = (int)(rem % (uint32_t)CH);
+        const int cz = (int)(rem / (uint32_t)CH);
+        U8 ra[4];
+        float xr[4];
+        bool ok[4];
+        const size_t v00 = (((size_t)n * D + cz * 2) * H + cy * 2) * W + xx;      // voxel k of the column: v00 + (k >> 1) * H * W + (k & 1) * W
+        const uint32_t HW = (uint32_t)H * W;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int z = cz * 2 + (k >> 1), y = cy * 2 + (k & 1);
+            ok[k] = in_range && z < D && y < H && xx < W;
+            const size_t vk = v00 + (k >> 1) * HW + (k & 1) * W;
+            if (ok[k]) {
+                ra[k] = ld256(t2 + vk * ld2);
+                xr[k] = __half2float(x[vk * ldx]);
+            }
+        }
+        __half2 mx[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mx[j] = __float2half2_rn(-INFINITY);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (ok[k]) {
+                U8 pk;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float a0 = h16_lo(ra[k].w[j]), a1 = h16_hi(ra[k].w[j]);
+                    const float o0 = lrelu(fmaf(a0, s_sc2[2 * j], fmaf(xr[k], s_scr[2 * j], s_sh2[2 * j])), slope);
+                    const float o1 = lrelu(fmaf(a1, s_sc2[2 * j + 1], fmaf(xr[k], s_scr[2 * j + 1], s_sh2[2 * j + 1])), slope);
+                    pk.w[j] = pack_h16x2(o0, o1);
+                    mx[j] = __hmax2(mx[j], *reinterpret_cast<const __half2 *>(&pk.w[j]));     // pool the values as stored
+                }
+                if (out != nullptr) st256(out + (v00 + (k >> 1) * HW + (k & 1) * W) * ldo, pk);
+            }
+        }
+        if (pooled != nullptr) {                        // warp-uniform: every lane takes part in the exchange
+            U8 pm;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                uint32_t w = *reinterpret_cast<const uint32_t *>(&mx[j]);
+                const uint32_t o = __shfl_xor_sync(0xffffffffu, w, 1);
+                const __half2 m = __hmax2(mx[j], *reinterpret_cast<const __half2 *>(&o));
+                pm.w[j] = *reinterpret_cast<const uint32_t *>(&m);
+            }
+            const int cx = xx >> 1;
+            if (in_range && (xx & 1) == 0 && cz < PD && cy < PH && cx < PW) {
+                const size_t pv = (((size_t)n * PD + cz) * PH + cy) * PW + cx;
+                st256(pooled + pv * ldp, pm);
+            }
+        }
+    }
+}
+
 // -------------------------------------------------------------------------------------------
 // ConvTranspose3d k=2 s=2: every input voxel produces a 2x2x2 block of outputs.
 constexpr int CT_VOX = 64;  // input voxels per CTA
@@ -1484,6 +1646,14 @@ extern "C" int l3d_merge_fwd(const l3d_act *t2, const l3d_norm *n2, const l3d_ac
             const size_t caph = (148 * 16 + (size_t)N - 1) / (size_t)N;
             if (gh > caph) gh = caph;
             dim3 gridh((unsigned)gh, (unsigned)N);
+            auto al32 = [](const l3d_act *a) { return a->ldc % 16 == 0 && reinterpret_cast<uintptr_t>(a->ptr) % 32 == 0; };
+            if (al32(t2) && al32(r) && (!has_out || al32(out)) && L3D_ENV_INT("L3D_MERGE_256", 1) != 0) {
+                size_t gv = (nvox + 511) / 512;
+                if (gv > caph) gv = caph;
+                dim3 gridv((unsigned)gv, (unsigned)N);
+                merge_head16v_fwd_kernel<<<gridv, 256, 0, st>>>((const h16 *)t2->ptr, t2->ldc, d2, (const h16 *)r->ptr, r->ldc, dr, N, nvox, slope,
+                                                               has_out ? (h16 *)out->ptr : nullptr, has_out ? out->ldc : 0, head_w, head_b, OC, prob, logits);
+            } else
             if (L3D_ENV_INT("L3D_HEAD16_U", 2) == 4)
                 merge_head16_fwd_kernel<4><<<gridh, 256, 0, st>>>((const h16 *)t2->ptr, t2->ldc, d2, (const h16 *)r->ptr, r->ldc, dr, N, nvox, slope,
                                                               has_out ? (h16 *)out->ptr : nullptr, has_out ? out->ldc : 0, head_w, head_b, OC, prob, logits);
@@ -1575,6 +1745,24 @@ extern "C" int l3d_dw_c1_fwd(const l3d_act *x, const l3d_norm *xn, int N, int D,
     return 0;
 }
 
+int l3d_conv3_tc_ex2(const l3d_act *x, const l3d_act *x2, const l3d_norm *xn, int N, int D, int H, int W,
+                     const float *w, int groups, const float *dw_w, const float *pw_w, const float *sc_w,
+                     const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats, int stat_ld, int co0, int cout_total,
+                     const float *r1_w, void *stream);
+
+extern "C" int l3d_dwpw_fwd2(const l3d_act *x_lo, const l3d_act *x_hi, const l3d_norm *xn, int N, int D, int H, int W,
+                             const float *dw_w, const float *pw_w, const float *sc_w,
+                             const l3d_act *t, double *t_stats, const l3d_act *r, double *r_stats, void *stream) {
+    L3D_REQUIRE(!act_null(x_lo) && !act_null(x_hi) && !act_null(t) && dw_w && pw_w && t_stats, "l3d_dwpw_fwd2: null argument");
+    L3D_REQUIRE(N > 0 && D > 0 && H > 0 && W > 0, "l3d_dwpw_fwd2: bad dims");
+    L3D_REQUIRE(x_lo->dtype == L3D_F16 && x_hi->dtype == L3D_F16 && t->dtype == L3D_F16, "l3d_dwpw_fwd2: fp16 storage only");
+    L3D_REQUIRE(x_lo->C == 16 && x_hi->C == 16 && x_lo->ldc == 16 && x_hi->ldc == 16, "l3d_dwpw_fwd2: both inputs must be dense 16-channel tensors");
+    if (sc_w != nullptr) L3D_REQUIRE(!act_null(r) && r_stats && r->C == t->C && r->dtype == t->dtype, "l3d_dwpw_fwd2: bad shortcut output");
+    const int rc = l3d_conv3_tc_ex2(x_lo, x_hi, xn, N, D, H, W, nullptr, 1, dw_w, pw_w, sc_w, t, t_stats, r, r_stats, t->C, 0, t->C, nullptr, stream);
+    if (rc < 0) { l3d_set_error("l3d_dwpw_fwd2: the implicit-GEMM kernel does not take this shape / alignment"); return 3; }
+    return rc;
+}
+
 extern "C" int l3d_dwpw_fwd_rank1(const float *u, const float *r1_w, int Cin, const l3d_norm *xn, int N, int D, int H, int W,
                                   const float *dw_w, const float *pw_w, const l3d_act *t, double *t_stats, void *stream) {
     L3D_REQUIRE(u && r1_w && dw_w && pw_w && !act_null(t) && t_stats, "l3d_dwpw_fwd_rank1: null argument");
@@ -1607,6 +1795,22 @@ extern "C" int l3d_merge_fwd_rank1(const l3d_act *t2, const l3d_norm *n2, const 
     if (blocks > cap) blocks = cap;
     dim3 grid((unsigned)blocks, (unsigned)N);
     const int CQ = C / V;
+    {
+        auto al32 = [](const l3d_act *a) { return a->ldc % 16 == 0 && reinterpret_cast<uintptr_t>(a->ptr) % 32 == 0; };
+        if (C == 16 && t2->dtype == L3D_F16 && al32(t2) && (!has_out || al32(out)) && (!has_pool || al32(pooled)) &&
+            L3D_ENV_INT("L3D_MERGE_256", 1) != 0 && L3D_ENV_INT("L3D_MERGE_CELL", 0) == 0) {
+            const size_t cols = (size_t)((D + 1) / 2) * ((H + 1) / 2) * (2 * ((W + 1) / 2));
+            size_t bl = (cols + 255) / 256;
+            if (bl > cap) bl = cap;
+            dim3 gridc((unsigned)bl, (unsigned)N);
+            merge_col16_r1_fwd_kernel<<<gridc, 256, 0, (cudaStream_t)stream>>>(
+                (const h16 *)t2->ptr, t2->ldc, d2, (const h16 *)x1->ptr, x1->ldc, dr, r1_w, N, D, H, W, slope,
+                has_out ? (h16 *)out->ptr : nullptr, has_out ? out->ldc : 0, has_pool ? (h16 *)pooled->ptr : nullptr, has_pool ? pooled->ldc : 0);
+            l3d_count_launch();
+            L3D_CUDA_OK("l3d_merge_fwd_rank1 launch");
+            return 0;
+        }
+    }
     // column-per-thread mapping: measured SLOWER for the rank-1 shortcut (325 windows of 48^3: 634 vs 568 us; the plain merge
     // gains 18 %, 730 -> 617 us), so it is opt-in here (L3D_MERGE_CELL=-1) and the default above
     if ((CQ & (CQ - 1)) == 0 && CQ <= 16 && L3D_ENV_INT("L3D_MERGE_CELL", 0) == -1) {

@@ -42,6 +42,8 @@ _SIGS = {
                             POINTER(Act), POINTER(Act), _P],
     "l3d_dw_c1_fwd": [POINTER(Act), POINTER(Norm), c_int, c_int, c_int, c_int, _P, _P, _P, c_int, _P, _P, _P, _P],
     "l3d_dwpw_fwd_rank1": [_P, _P, c_int, POINTER(Norm), c_int, c_int, c_int, c_int, _P, _P, POINTER(Act), _P, _P],
+    "l3d_dwpw_fwd2": [POINTER(Act), POINTER(Act), POINTER(Norm), c_int, c_int, c_int, c_int, _P, _P, _P,
+                      POINTER(Act), _P, POINTER(Act), _P, _P],
     "l3d_conv3_fwd": [POINTER(Act), POINTER(Norm), c_int, c_int, c_int, c_int, _P, c_int, POINTER(Act), _P, _P, POINTER(Act), _P, _P],
     "l3d_merge_fwd": [POINTER(Act), POINTER(Norm), POINTER(Act), POINTER(Norm), c_int, c_int, c_int, c_int, c_float,
                       POINTER(Act), POINTER(Act), _P, _P, c_int, _P, _P, _P],
@@ -152,7 +154,7 @@ class KernelTimer:
         return out
 
 
-_DISPATCHING = {"l3d_dwpw_fwd", "l3d_conv3_fwd", "l3d_convt_fwd", "l3d_dwpw_fwd_rank1", "l3d_dw_c1_fwd"}
+_DISPATCHING = {"l3d_dwpw_fwd", "l3d_conv3_fwd", "l3d_convt_fwd", "l3d_dwpw_fwd_rank1", "l3d_dw_c1_fwd", "l3d_dwpw_fwd2"}
 TIMER = KernelTimer()
 
 

@@ -84,7 +84,12 @@ class Workspace:
         poison = os.environ.get("L3D_DEBUG_POISON", "0") == "1"
         emp = (lambda *s: torch.full(s, float("nan"), dtype=dtype, device=device)) if poison else (lambda *s: torch.empty(*s, dtype=dtype, device=device))
         # concat buffers [up | skip]; zero-initialised once: the centre-pad rim (odd sizes) stays zero
-        self.cat = {0: z(N, *lv[0], 2 * e[0]), 1: z(N, *lv[1], 2 * e[1]), 2: z(N, *lv[2], 2 * e[2])}
+        self.cat = {1: z(N, *lv[1], 2 * e[1]), 2: z(N, *lv[2], 2 * e[2])}
+        self.cat0_split = plan.split_cat0(dtype, training)
+        if self.cat0_split:
+            self.cat0_lo, self.cat0_hi = z(N, *lv[0], e[0]), z(N, *lv[0], e[0])      # [up] and [skip] as two dense tensors
+        else:
+            self.cat[0] = z(N, *lv[0], 2 * e[0])
         self.pooled = {0: emp(N, *lv[1], e[0]), 1: emp(N, *lv[2], e[1]), 2: emp(N, *lv[3], e[2])}
         self.blocks: Dict[str, dict] = {}
         n_stats = 0
@@ -175,6 +180,13 @@ class UNetPlan:
     # conv1's output t1 = pw (x) u are rank-1 maps of single-channel tensors, evaluated on the fly by their consumers
     def rank1_shortcut(self, b: BlockSpec, training: bool) -> bool:
         return (not training) and b.name == "init_conv" and b.cin == 1 and b.cin != b.cout and b.kind1 == "dws" and b.cout in (16, 32)
+
+    def split_cat0(self, dtype, training: bool) -> bool:
+        """Inference, fp16 storage, 16 + 16 channels at the top level, depthwise-separable up3.conv1: the decoder block reads
+        [ConvTranspose output | skip] as two dense 16-channel tensors (l3d_dwpw_fwd2) instead of one interleaved buffer."""
+        up3 = self.blocks[-1]
+        return ((not training) and dtype == torch.float16 and up3.kind1 == "dws" and up3.cin == 32 and up3.cout == 16 and self.enc[0] == 16
+                and os.environ.get("L3D_SPLIT_CAT", "1") != "0")
 
     def rank1_first(self, b: BlockSpec, dtype, dims, training: bool) -> bool:
         return (self.rank1_shortcut(b, training) and b.kind2 == "dws" and b.cout == 16 and dtype == torch.float16
@@ -280,14 +292,16 @@ class UNetPlan:
             mask = masks[i] if (masks is not None and masks[i] is not None) else None
             if b.name.startswith("up"):
                 # transposed conv into the lower half of the concat buffer, then the block reads the whole buffer
-                cat = ws.cat[b.level]
+                split = b.level == 0 and ws.cat0_split
+                cat = None if split else ws.cat[b.level]
                 lo = ws.level_dims[b.level + 1]
                 off = [(dims[k] - 2 * lo[k]) // 2 for k in range(3)]
                 nv.call("l3d_convt_fwd", nv.act(cur, cur_off, cur_C), N, lo[0], lo[1], lo[2],
                         nv.ptr(P[f"{b.name}.up.weight"]), nv.ptr(P[f"{b.name}.up.bias"]),
-                        nv.act(cat, 0, b.cin // 2), dims[0], dims[1], dims[2], off[0], off[1], off[2], st,
+                        nv.act(ws.cat0_lo) if split else nv.act(cat, 0, b.cin // 2), dims[0], dims[1], dims[2], off[0], off[1], off[2], st,
                         algo_bytes=es * N * (lo[0] * lo[1] * lo[2] * cur_C + vox * (b.cin // 2)))
-                cur, cur_off, cur_C = cat, 0, b.cin
+                cur, cur_off, cur_C = (ws.cat0_lo, 0, b.cin // 2) if split else (cat, 0, b.cin)
+            split_in = b.name == "up3" and ws.cat0_split
             x_act = nv.act(cur, cur_off, cur_C)
             has_sc = b.cin != b.cout
             s1, s2, sr = (ws.stats_of(b.name, k, b.cout) for k in range(3))
@@ -310,8 +324,15 @@ class UNetPlan:
                         nv.act(buf["t2"]), nv.ptr(s2), st, algo_bytes=N * vox * (4 + es * b.cout))
             else:
                 # conv1 (+ shortcut conv) on the block input
-                self._conv(P, b, 1, x_act, ident, N, dims, buf["t1"], s1, sc_w, None if rank1 else buf.get("r"), sr if has_sc else None,
-                           buf.get("u1"), st)
+                if split_in:
+                    pre = f"{b.prefix}.conv1"
+                    nv.TIMER.tag = f"{b.name}.c1"
+                    nv.call("l3d_dwpw_fwd2", x_act, nv.act(ws.cat0_hi), ident, N, *dims, nv.ptr(P[f"{pre}.depthwise.weight"]),
+                            nv.ptr(P[f"{pre}.pointwise.weight"]), nv.ptr(sc_w), nv.act(buf["t1"]), nv.ptr(s1), nv.act(buf["r"]), nv.ptr(sr), st,
+                            algo_bytes=es * N * vox * (b.cin + 2 * b.cout))
+                else:
+                    self._conv(P, b, 1, x_act, ident, N, dims, buf["t1"], s1, sc_w, None if rank1 else buf.get("r"), sr if has_sc else None,
+                               buf.get("u1"), st)
                 # conv2 on lrelu(IN1(t1)) * dropout-mask, applied on load
                 self._conv(P, b, 2, nv.act(buf["t1"]), n1, N, dims, buf["t2"], s2, None, None, None, buf.get("u2"), st)
             # residual merge (+ pool / head)
@@ -323,15 +344,15 @@ class UNetPlan:
             else:
                 r_act, nr = x_act, ident
             if b.name in ("init_conv", "down1", "down2"):
-                cat = ws.cat[b.level]
-                out_t, out_off = cat, b.cout                      # upper half of the concat buffer
+                # the block output is the skip: upper half of the concat buffer (or the dense skip tensor of the split top level)
+                skip_act = nv.act(ws.cat0_hi) if (b.level == 0 and ws.cat0_split) else nv.act(ws.cat[b.level], b.cout, b.cout)
                 if rank1:
                     nv.call("l3d_merge_fwd_rank1", nv.act(buf["t2"]), n2, x_act, nv.ptr(sc_w), nr, N, *dims, LEAKY_SLOPE,
-                            nv.act(cat, b.cout, b.cout), nv.act(ws.pooled[b.level]), st,
+                            skip_act, nv.act(ws.pooled[b.level]), st,
                             algo_bytes=2 * mbytes + mbytes // 8 + mbytes // b.cout)
                 else:
                     nv.call("l3d_merge_fwd", nv.act(buf["t2"]), n2, r_act, nr, N, *dims, LEAKY_SLOPE,
-                            nv.act(cat, b.cout, b.cout), nv.act(ws.pooled[b.level]), None, None, 0, None, None, st,
+                            skip_act, nv.act(ws.pooled[b.level]), None, None, 0, None, None, st,
                             algo_bytes=3 * mbytes + mbytes // 8)
                 cur, cur_off, cur_C = ws.pooled[b.level], 0, b.cout
             elif b.name == "up3":

@@ -351,3 +351,46 @@ def test_convt_tc_forward(Cin, Cout, lo, out_dims, store, tol):
     got = cat[:, off[0]:off[0] + 2 * lo[0], off[1]:off[1] + 2 * lo[1], off[2]:off[2] + 2 * lo[2], :Cout].double().cpu()
     assert _rel(got, ref) < tol
     assert float(cat[..., Cout:].float().abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dims", [(16, 16, 16), (9, 17, 13), (48, 48, 48)])
+def test_split_concat_input_matches_interleaved(dims):
+    """l3d_dwpw_fwd2: the decoder block of the top level reads [ConvTranspose output | skip] as two dense 16-channel tensors.
+    Same MMAs in the same order as l3d_dwpw_fwd on the interleaved 32-channel buffer: raw outputs bit-identical,
+    statistics equal up to the order of the atomics."""
+    from light_unet import _native as nv
+    N, (D, H, W) = 3, dims
+    g = torch.Generator().manual_seed(3)
+    lo = torch.randn(N, D, H, W, 16, generator=g).to(torch.float16).to(DEV)
+    hi = torch.randn(N, D, H, W, 16, generator=g).to(torch.float16).to(DEV)
+    cat = torch.cat([lo, hi], dim=-1).contiguous()
+    dw = (torch.randn(32, 1, 3, 3, 3, generator=g) / 5).to(DEV)
+    pw = (torch.randn(16, 32, generator=g) / 32 ** 0.5).to(DEV)
+    sc = (torch.randn(16, 32, generator=g) / 32 ** 0.5).to(DEV)
+    st = nv.stream_ptr(torch.device(DEV))
+    outs = []
+    for split in (False, True):
+        t = torch.zeros(N, D, H, W, 16, dtype=torch.float16, device=DEV)
+        r = torch.zeros_like(t)
+        ts = torch.zeros(2 * N * 16, dtype=torch.float64, device=DEV)
+        rs = torch.zeros_like(ts)
+        if split:
+            nv.call("l3d_dwpw_fwd2", nv.act(lo), nv.act(hi), nv.norm(), N, D, H, W, nv.ptr(dw), nv.ptr(pw), nv.ptr(sc), nv.act(t), nv.ptr(ts),
+                    nv.act(r), nv.ptr(rs), st)
+        else:
+            nv.call("l3d_dwpw_fwd", nv.act(cat), nv.norm(), N, D, H, W, nv.ptr(dw), nv.ptr(pw), nv.ptr(sc), nv.act(t), nv.ptr(ts),
+                    nv.act(r), nv.ptr(rs), nv.act(None), st)
+        torch.cuda.synchronize()
+        outs.append((t, r, ts, rs))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    for k in (2, 3):
+        assert torch.allclose(outs[0][k], outs[1][k], rtol=1e-5, atol=1e-4)      # per-CTA partial sums are fp32
+    # against torch: depthwise 3x3x3 then pointwise, and the 1x1x1 shortcut
+    x = cat.float().permute(0, 4, 1, 2, 3)
+    want_t = F.conv3d(F.conv3d(x, dw, padding=1, groups=32), pw.view(16, 32, 1, 1, 1))
+    want_r = F.conv3d(x, sc.view(16, 32, 1, 1, 1))
+    assert _rel(outs[1][0].float().permute(0, 4, 1, 2, 3), want_t) < 2e-3
+    assert _rel(outs[1][1].float().permute(0, 4, 1, 2, 3), want_r) < 2e-3
+    with pytest.raises(nv.NativeError):            # interleaved halves are not dense tensors
+        nv.call("l3d_dwpw_fwd2", nv.act(cat, 0, 16), nv.act(cat, 16, 16), nv.norm(), N, D, H, W, nv.ptr(dw), nv.ptr(pw), nv.ptr(sc),
+                nv.act(outs[0][0]), nv.ptr(outs[0][2]), nv.act(outs[0][1]), nv.ptr(outs[0][3]), st)

@@ -83,7 +83,7 @@ def test_rank1_merge_mappings_agree(dims):
     n2 = nv.norm(s2, g, b, None, 1e-5, 1.0, vox)
     nr = nv.norm(sr, g, b, None, 1e-5, 1.0, vox)
     res = {}
-    for mode in ("0", "-1"):
+    for mode in ("0", "-1", "1"):          # 0: column per thread, 32-byte accesses; -1: column per thread, 16-byte vectors; 1: cell per thread
         os.environ["L3D_MERGE_CELL"] = mode
         nv.lib().l3d_env_refresh()
         try:
@@ -91,9 +91,56 @@ def test_rank1_merge_mappings_agree(dims):
         finally:
             os.environ.pop("L3D_MERGE_CELL", None)
             nv.lib().l3d_env_refresh()
-    assert torch.equal(res["0"][0], res["-1"][0]) and torch.equal(res["0"][1], res["-1"][1])
+    for mode in ("-1", "1"):
+        assert torch.equal(res["0"][0], res[mode][0]) and torch.equal(res["0"][1], res[mode][1])
     a = F.instance_norm(t2.float().permute(0, 4, 1, 2, 3), eps=1e-5)
     bb = F.instance_norm(rr.float().permute(0, 4, 1, 2, 3), eps=1e-5)
     want = F.leaky_relu(a + bb, 0.01)
     got = res["0"][0].float().permute(0, 4, 1, 2, 3)
     assert (got - want).abs().max() <= 4e-3 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("nvox_dims", [(8, 8, 8), (5, 7, 9)])
+def test_head16_voxel_per_thread_matches_half_voxel_kernel(nvox_dims):
+    """Residual merge + 1x1x1 head + sigmoid for C = 16 (unet3d.py:201-202,220-221): the 32-byte-access kernel against the
+    half-voxel kernel bit for bit (same summation order), and against PyTorch."""
+    from light_unet import _native as nv
+    torch.manual_seed(11)
+    B, C = 3, 16
+    D, H, W = nvox_dims
+    vox = D * H * W
+    t2 = torch.randn(B, D, H, W, C, device=DEV).to(torch.float16)
+    r = torch.randn(B, D, H, W, C, device=DEV).to(torch.float16)
+    g, b = torch.rand(C, device=DEV) + 0.5, torch.randn(C, device=DEV) * 0.1
+
+    def stats_of(t):
+        f = t.double()
+        return torch.stack([f.sum(dim=(1, 2, 3)), (f * f).sum(dim=(1, 2, 3))]).contiguous()
+    s2, sr = stats_of(t2), stats_of(r)
+    n2 = nv.norm(s2, g, b, None, 1e-5, 1.0, vox)
+    nr = nv.norm(sr, g, b, None, 1e-5, 1.0, vox)
+    hw, hb = torch.randn(1, C, device=DEV) / 4, torch.randn(1, device=DEV)
+    st = nv.stream_ptr(torch.device(DEV))
+    res = {}
+    for mode in ("1", "0"):
+        os.environ["L3D_MERGE_256"] = mode
+        nv.lib().l3d_env_refresh()
+        try:
+            out = torch.zeros(B, D, H, W, C, dtype=torch.float16, device=DEV)
+            prob = torch.zeros(B, 1, D, H, W, device=DEV)
+            logits = torch.zeros(B, 1, D, H, W, device=DEV)
+            nv.call("l3d_merge_fwd", nv.act(t2), n2, nv.act(r), nr, B, D, H, W, 0.01, nv.act(out), nv.act(None), nv.ptr(hw), nv.ptr(hb), 1,
+                    nv.ptr(prob), nv.ptr(logits), st)
+            torch.cuda.synchronize()
+            res[mode] = (out, prob, logits)
+        finally:
+            os.environ.pop("L3D_MERGE_256", None)
+            nv.lib().l3d_env_refresh()
+    for a, bb in zip(res["1"], res["0"]):
+        assert torch.equal(a, bb)
+    x1 = F.instance_norm(t2.float().permute(0, 4, 1, 2, 3), weight=g, bias=b, eps=1e-5)
+    x2 = F.instance_norm(r.float().permute(0, 4, 1, 2, 3), weight=g, bias=b, eps=1e-5)
+    act = F.leaky_relu(x1 + x2, 0.01)
+    want = F.conv3d(act, hw.view(1, C, 1, 1, 1), hb)
+    assert (res["1"][2] - want).abs().max() < 2e-2          # fp16 storage of the activations the head reads
+    assert torch.equal(res["1"][1], torch.sigmoid(res["1"][2])) or (res["1"][1] - torch.sigmoid(res["1"][2])).abs().max() < 1e-6

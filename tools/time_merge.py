@@ -61,6 +61,16 @@ ctb = torch.zeros(C, device=DEV)
 cases["convT 32 -> 16 into the concat half (24^3 -> 48^3)"] = (
     lambda: nv.call("l3d_convt_fwd", nv.act(xin), B, S // 2, S // 2, S // 2, nv.ptr(ctw), nv.ptr(ctb), nv.act(cat, 0, C), S, S, S, 0, 0, 0, st),
     2 * B * (vox // 8) * 2 * C + mb)
+dense = torch.zeros(B, S, S, S, C, dtype=torch.float16, device=DEV)
+cases["merge rank-1 -> DENSE 16-channel tensor + pooled"] = (
+    lambda: nv.call("l3d_merge_fwd_rank1", nv.act(t2), n2, nv.act(x1), nv.ptr(scw), nr, B, S, S, S, 0.01, nv.act(dense), nv.act(pooled), st),
+    2 * mb + mb // 8 + mb // C)
+cases["merge -> DENSE 16-channel tensor + pooled"] = (
+    lambda: nv.call("l3d_merge_fwd", nv.act(t2), n2, nv.act(r), nr, B, S, S, S, 0.01, nv.act(dense), nv.act(pooled), None, None, 0, None, None, st),
+    3 * mb + mb // 8)
+cases["convT 32 -> 16 into a DENSE 16-channel tensor"] = (
+    lambda: nv.call("l3d_convt_fwd", nv.act(xin), B, S // 2, S // 2, S // 2, nv.ptr(ctw), nv.ptr(ctb), nv.act(dense), S, S, S, 0, 0, 0, st),
+    2 * B * (vox // 8) * 2 * C + mb)
 print("knobs:", {k: v for k, v in os.environ.items() if k.startswith("L3D_")})
 for name, (fn, nbytes) in cases.items():
     us = timeit(fn)
