@@ -23,6 +23,10 @@ __device__ __forceinline__ uint32_t pack_h16x2(float lo, float hi) {
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
+// one 256-bit global store (STG.E.256, sm_100); p must be 32-byte aligned
+__device__ __forceinline__ void st_global_256(void *p, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5, uint32_t w6, uint32_t w7) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w0), "r"(w1), "r"(w2), "r"(w3), "r"(w4), "r"(w5), "r"(w6), "r"(w7) : "memory");
+}
 __device__ __forceinline__ h16 to_h16(float v) { return __ushort_as_half((unsigned short)(pack_h16x2(v, 0.f) & 0xffffu)); }
 
 // ------------------------------------------------------------------ errors --

@@ -30,6 +30,7 @@ struct SlabArgs {
     int SZ, MT, RP, PP;      // slab height, MMA tiles per slab, padded row / plane pitch of the stencil tile (voxels, odd)
     int tmem_cols;
     uint32_t raw_bytes, raw_stride, in_bytes;
+    int wide_st;             // outputs are 32-byte aligned 16-channel blocks: 256-bit stores
     int dbg;                 // development aid (L3D_SLAB_SKIP): 1 = no activation pass, 2 = no stencil, 4 = no epilogue, 8 = no TMA
 };
 
@@ -322,6 +323,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) dwpw_slab_kernel(const 
             const uint32_t trow = tmem + ((uint32_t)(eq * 32) << 16);
             const int cbn = Cout >> 4;
             const int njobs = nacc * MT * cbn;
+            const bool wide_st = A.wide_st != 0;
             // job j = (a * MT + m) * cbn + cbi, walked in steps of NG with carries (no divisions)
             int cbi = eg % cbn, m = (eg / cbn) % MT, a = eg / (cbn * MT);
             for (int j = eg; j < njobs; j += NG) {
@@ -345,8 +347,12 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) dwpw_slab_kernel(const 
                 }
                 if (valid) {
                     h16 *outp = a_ == 0 ? A.t + (vox0 + rr) * (size_t)A.ldt : A.r + (vox0 + rr) * (size_t)A.ldr;
-                    *reinterpret_cast<uint4 *>(outp + cb) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                    *reinterpret_cast<uint4 *>(outp + cb + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    if (wide_st) {        // a lane's 16 channels are one 32-byte sector: one 256-bit store (half the LSU wavefronts)
+                        st_global_256(outp + cb, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+                    } else {
+                        *reinterpret_cast<uint4 *>(outp + cb) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4 *>(outp + cb + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                    }
                 }
                 warp_transpose_sum<32>(sv, lane);
                 const int idx = warp_transpose_owner<32>(lane);      // 0..15 sums, 16..31 squares
@@ -452,6 +458,10 @@ int l3d_dwpw_fwd_slab(const l3d_act *x, const l3d_norm *xn, int N, int D, int H,
     A.r = has_sc ? (h16 *)r->ptr : nullptr; A.ldr = has_sc ? r->ldc : 0; A.r_stats = r_stats;
     A.SZ = p.SZ; A.MT = p.MT; A.RP = p.RP; A.PP = p.PP; A.tmem_cols = p.cols;
     A.dbg = L3D_ENV_INT("L3D_SLAB_SKIP", 0);
+    {
+        auto al32 = [](const l3d_act *a) { return a->ldc % 16 == 0 && reinterpret_cast<uintptr_t>(a->ptr) % 32 == 0; };
+        A.wide_st = (al32(t) && (!has_sc || al32(r)) && L3D_ENV_INT("L3D_ST256", 1) != 0) ? 1 : 0;
+    }
     A.raw_bytes = p.raw_bytes; A.raw_stride = p.raw_stride; A.in_bytes = p.in_bytes;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);

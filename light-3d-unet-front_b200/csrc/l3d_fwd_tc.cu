@@ -46,7 +46,7 @@ struct TcArgs {
     void *t; int ldt; double *t_stats;
     void *r; int ldr; double *r_stats;
     void *u; int ldu;
-    int tmem_cols;
+    int tmem_cols, wide_st;
 };
 
 __device__ __forceinline__ void split_f16(float v, __half &hi, __half &lo) {
@@ -90,6 +90,27 @@ __device__ __forceinline__ void store16_256(h16 *p, const float (&v)[16], bool v
                      "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
     }
 }
+// store16 with 256-bit stores (p 32-byte aligned): fp16 one, fp32 two instructions instead of two / four
+__device__ __forceinline__ void store16_wide(h16 *p, float (&v)[16], bool valid) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        pk[j] = valid ? pack_h16x2(v[2 * j], v[2 * j + 1]) : 0u;
+        v[2 * j] = h16_lo(pk[j]); v[2 * j + 1] = h16_hi(pk[j]);
+    }
+    if (valid) st_global_256(p, pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7]);
+}
+__device__ __forceinline__ void store16_wide(float *p, float (&v)[16], bool valid) {
+    if (valid) {
+        st_global_256(p, __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]),
+                      __float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
+        st_global_256(p + 8, __float_as_uint(v[8]), __float_as_uint(v[9]), __float_as_uint(v[10]), __float_as_uint(v[11]),
+                      __float_as_uint(v[12]), __float_as_uint(v[13]), __float_as_uint(v[14]), __float_as_uint(v[15]));
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+    }
+}
 __device__ __forceinline__ void store16(float *p, float (&v)[16], bool valid) {
     if (valid) {
 #pragma unroll
@@ -100,7 +121,7 @@ __device__ __forceinline__ void store16(float *p, float (&v)[16], bool valid) {
     }
 }
 
-__device__ __forceinline__ void store16_256(float *p, float (&v)[16], bool valid) { store16(p, v, valid); }
+__device__ __forceinline__ void store16_256(float *p, float (&v)[16], bool valid) { store16_wide(p, v, valid); }
 
 template <typename T>
 __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs A) {
@@ -421,6 +442,7 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
             const bool valid = gz < A.D && gy < A.H && gx < A.W;
             const size_t vox = (((size_t)n * A.D + gz) * A.H + gy) * A.W + gx;
             const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+            const bool wide_st = A.wide_st != 0;
             for (int a = 0; a < nkind; ++a) {
                 T *outp = a == 0 ? reinterpret_cast<T *>(A.t) + vox * (size_t)A.ldt : reinterpret_cast<T *>(A.r) + vox * (size_t)A.ldr;
                 double *stat = s_stat + a * 2 * Cout;
@@ -431,7 +453,7 @@ __global__ void __launch_bounds__(NT) dwpw_tc_kernel(const __grid_constant__ CUt
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] *= SPLIT_INV;
                     }
-                    store16(outp + cb, v, valid);
+                    if (wide_st) store16_wide(outp + cb, v, valid); else store16(outp + cb, v, valid);
                     float sv[32];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) { sv[j] = v[j]; sv[16 + j] = v[j] * v[j]; }
@@ -499,6 +521,12 @@ int l3d_dwpw_fwd_tc(const l3d_act *x, const l3d_norm *xn, int N, int D, int H, i
     A.r = has_sc ? r->ptr : nullptr; A.ldr = has_sc ? r->ldc : 0; A.r_stats = r_stats;
     A.u = has_u ? u->ptr : nullptr; A.ldu = has_u ? u->ldc : 0;
     A.tmem_cols = cols;
+    {
+        // 16 output channels of a voxel = 32 (fp16) / 64 (fp32) bytes: 256-bit stores when every block starts on a 32-byte boundary
+        const int per32 = f32 ? 8 : 16;
+        auto al32 = [per32](const l3d_act *a) { return a->ldc % per32 == 0 && reinterpret_cast<uintptr_t>(a->ptr) % 32 == 0; };
+        A.wide_st = (al32(t) && (sc_w == nullptr || al32(r)) && L3D_ENV_INT("L3D_ST256", 1) != 0) ? 1 : 0;
+    }
     {
         cudaError_t e = f32 ? cudaFuncSetAttribute(dwpw_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)
                             : cudaFuncSetAttribute(dwpw_tc_kernel<h16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
@@ -687,7 +715,7 @@ int l3d_convt_fwd_tc(const l3d_act *x, int N, int d, int h, int w_, const float 
     A.wgt = w; A.bias = b; A.Cout = Cout;
     A.out = out->ptr; A.ldo = out->ldc; A.OD = OD; A.OH = OH; A.OW = OW; A.oz = oz; A.oy = oy; A.ox = ox;
     A.tmem_cols = cols;
-    A.wide_st = (!f32 && out->ldc % 16 == 0 && reinterpret_cast<uintptr_t>(out->ptr) % 32 == 0 && L3D_ENV_INT("L3D_CONVT_ST256", 1) != 0) ? 1 : 0;
+    A.wide_st = (out->ldc % (f32 ? 8 : 16) == 0 && reinterpret_cast<uintptr_t>(out->ptr) % 32 == 0 && L3D_ENV_INT("L3D_ST256", 1) != 0) ? 1 : 0;
     {
         cudaError_t e = f32 ? cudaFuncSetAttribute(convt_tc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)
                             : cudaFuncSetAttribute(convt_tc_kernel<h16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
