@@ -280,14 +280,7 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_kernel(PwTcArgs A) {
             for (int cb = (warp >> 2) * 16; cb < Cu; cb += 32) {
                 float r[16];
                 tc::tmem_ld16(trow + (uint32_t)cb, r);
-                if (ok) {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        float4 o = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-                        if (A.accumulate) { const float4 p = *reinterpret_cast<const float4 *>(op + cb + j); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
-                        *reinterpret_cast<float4 *>(op + cb + j) = o;
-                    }
-                }
+                if (ok) store16_f32(op + cb, r, A.accumulate != 0, (reinterpret_cast<uintptr_t>(op) & 31) == 0);
             }
         }
         tc::fence_before_sync();
@@ -474,14 +467,7 @@ __global__ void __launch_bounds__(NT) pw_bwd_tc_pipe_kernel(PwTcArgs A) {
             for (int cb = (warp >> 2) * 16; cb < Cu; cb += 32) {
                 float r[16];
                 tc::tmem_ld16(trow + (uint32_t)cb, r);
-                if (ok) {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        float4 o = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-                        if (A.accumulate) { const float4 pz = *reinterpret_cast<const float4 *>(op + cb + j); o.x += pz.x; o.y += pz.y; o.z += pz.z; o.w += pz.w; }
-                        *reinterpret_cast<float4 *>(op + cb + j) = o;
-                    }
-                }
+                if (ok) store16_f32(op + cb, r, A.accumulate != 0, (reinterpret_cast<uintptr_t>(op) & 31) == 0);
             }
         }
         tc::fence_before_sync();
@@ -757,14 +743,7 @@ __global__ void __launch_bounds__(NT) convt_bwd_tc_kernel(CtTcArgs A) {
             for (int cb = (warp >> 2) * 16; cb < Cin; cb += 32) {
                 float r[16];
                 tc::tmem_ld16(trow + (uint32_t)cb, r);
-                if (ok) {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        float4 o = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-                        if (A.accumulate) { const float4 pz = *reinterpret_cast<const float4 *>(op + cb + j); o.x += pz.x; o.y += pz.y; o.z += pz.z; o.w += pz.w; }
-                        *reinterpret_cast<float4 *>(op + cb + j) = o;
-                    }
-                }
+                if (ok) store16_f32(op + cb, r, A.accumulate != 0, (reinterpret_cast<uintptr_t>(op) & 31) == 0);
             }
         }
         tc::fence_before_sync();

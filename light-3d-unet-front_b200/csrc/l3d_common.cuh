@@ -27,6 +27,34 @@ __device__ __forceinline__ uint32_t pack_h16x2(float lo, float hi) {
 __device__ __forceinline__ void st_global_256(void *p, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4, uint32_t w5, uint32_t w6, uint32_t w7) {
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w0), "r"(w1), "r"(w2), "r"(w3), "r"(w4), "r"(w5), "r"(w6), "r"(w7) : "memory");
 }
+// 16 fp32 values of a voxel row -> global, optionally accumulated onto what is there: two 256-bit accesses per direction when
+// the row is 32-byte aligned (wide), four 128-bit ones otherwise
+__device__ __forceinline__ void store16_f32(float *p, const float (&r)[16], bool accumulate, bool wide) {
+    if (wide) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 8) {
+            float o[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = r[j + k];
+            if (accumulate) {
+                uint32_t q[8];
+                asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                             : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]) : "l"(p + j) : "memory");
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] += __uint_as_float(q[k]);
+            }
+            st_global_256(p + j, __float_as_uint(o[0]), __float_as_uint(o[1]), __float_as_uint(o[2]), __float_as_uint(o[3]),
+                          __float_as_uint(o[4]), __float_as_uint(o[5]), __float_as_uint(o[6]), __float_as_uint(o[7]));
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+            float4 o = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+            if (accumulate) { const float4 q = *reinterpret_cast<const float4 *>(p + j); o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
+            *reinterpret_cast<float4 *>(p + j) = o;
+        }
+    }
+}
 __device__ __forceinline__ h16 to_h16(float v) { return __ushort_as_half((unsigned short)(pack_h16x2(v, 0.f) & 0xffffu)); }
 
 // ------------------------------------------------------------------ errors --
