@@ -752,6 +752,82 @@ __device__ __forceinline__ void st256(h16 *p, const U8 &v) {
                  "r"(v.w[4]), "r"(v.w[5]), "r"(v.w[6]), "r"(v.w[7]) : "memory");
 }
 
+// Column-per-thread residual merge (+ MaxPool3d(2)) in fp16 storage with 32-byte channel vectors: thread = one x-column of a
+// cell (2 x 2 voxels in z, y) x 16 channels, C / 16 lanes per voxel (a power of two <= 16).  Half the load / store
+// instructions of merge_col_fwd_kernel<h16>; same arithmetic, bit-identical results.
+__global__ void __launch_bounds__(256, 2) merge_col32_fwd_kernel(
+    const h16 *__restrict__ t2, int ld2, NormDev n2, const h16 *__restrict__ r, int ldr, NormDev nr,
+    int N, int C, int D, int H, int W, float slope, h16 *__restrict__ out, int ldo, h16 *__restrict__ pooled, int ldp) {
+    extern __shared__ float sm[];
+    float *s_sc2 = sm, *s_sh2 = sm + C, *s_scr = sm + 2 * C, *s_shr = sm + 3 * C;
+    const int n = blockIdx.y;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        norm_scale_shift(n2, N, C, n, c, s_sc2[c], s_sh2[c]);
+        norm_scale_shift(nr, N, C, n, c, s_scr[c], s_shr[c]);
+        s_sh2[c] += s_shr[c];
+    }
+    __syncthreads();
+    const int CD = (D + 1) / 2, CH = (H + 1) / 2, CW2 = 2 * ((W + 1) / 2), CQ = C / 16;
+    const int PD = D / 2, PH = H / 2, PW = W / 2;
+    const int cq_sh = __ffs(CQ) - 1;
+    const uint32_t total = (uint32_t)CD * CH * CW2 * CQ;
+    const uint32_t total_round = (total + 31u) & ~31u;
+    const uint32_t HW = (uint32_t)H * W;
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total_round; idx += gridDim.x * blockDim.x) {
+        const bool in_range = idx < total;
+        uint32_t rem = idx;
+        const int q = (int)(rem & (uint32_t)(CQ - 1)); rem >>= cq_sh;
+        const int xx = (int)(rem % (uint32_t)CW2); rem /= (uint32_t)CW2;
+        const int cy = (int)(rem % (uint32_t)CH);
+        const int cz = (int)(rem / (uint32_t)CH);
+        const int c = q * 16;
+        const float *sc2 = s_sc2 + c, *sh2 = s_sh2 + c, *scr = s_scr + c;
+        const size_t v00 = (((size_t)n * D + cz * 2) * H + cy * 2) * W + xx;
+        U8 ra[4], rb[4];
+        bool ok[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int z = cz * 2 + (k >> 1), y = cy * 2 + (k & 1);
+            ok[k] = in_range && z < D && y < H && xx < W;
+            const size_t vk = v00 + (k >> 1) * HW + (k & 1) * W;
+            if (ok[k]) { ra[k] = ld256(t2 + vk * ld2 + c); rb[k] = ld256(r + vk * ldr + c); }
+        }
+        __half2 mx[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mx[j] = __float2half2_rn(-INFINITY);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (ok[k]) {
+                U8 pk;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float a0 = h16_lo(ra[k].w[j]), a1 = h16_hi(ra[k].w[j]), b0 = h16_lo(rb[k].w[j]), b1 = h16_hi(rb[k].w[j]);
+                    const float o0 = lrelu(fmaf(a0, sc2[2 * j], fmaf(b0, scr[2 * j], sh2[2 * j])), slope);
+                    const float o1 = lrelu(fmaf(a1, sc2[2 * j + 1], fmaf(b1, scr[2 * j + 1], sh2[2 * j + 1])), slope);
+                    pk.w[j] = pack_h16x2(o0, o1);
+                    mx[j] = __hmax2(mx[j], *reinterpret_cast<const __half2 *>(&pk.w[j]));     // pool the values as stored
+                }
+                if (out != nullptr) st256(out + (v00 + (k >> 1) * HW + (k & 1) * W) * ldo + c, pk);
+            }
+        }
+        if (pooled != nullptr) {                        // warp-uniform: every lane takes part in the exchange
+            U8 pm;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t w = *reinterpret_cast<const uint32_t *>(&mx[j]);
+                const uint32_t o = __shfl_xor_sync(0xffffffffu, w, CQ);
+                const __half2 m = __hmax2(mx[j], *reinterpret_cast<const __half2 *>(&o));
+                pm.w[j] = *reinterpret_cast<const uint32_t *>(&m);
+            }
+            const int cx = xx >> 1;
+            if (in_range && (xx & 1) == 0 && cz < PD && cy < PH && cx < PW) {
+                const size_t pv = (((size_t)n * PD + cz) * PH + cy) * PW + cx;
+                st256(pooled + pv * ldp + c, pm);
+            }
+        }
+    }
+}
+
 // Residual merge + head for C = 16, fp16 storage, one thread per VOXEL: two 32-byte loads and (optionally) one 32-byte
 // store per voxel, no lane-pair exchange for the head sum.  Needs 32-byte aligned voxels (host check).
 __global__ void __launch_bounds__(256, 3) merge_head16v_fwd_kernel(
@@ -1690,6 +1766,19 @@ extern "C" int l3d_merge_fwd(const l3d_act *t2, const l3d_norm *n2, const l3d_ac
         if (blocks > cap) blocks = cap;
         dim3 grid((unsigned)blocks, (unsigned)N);
         const int CQ = C / V;
+        auto al32 = [](const l3d_act *a) { return a->ldc % 16 == 0 && reinterpret_cast<uintptr_t>(a->ptr) % 32 == 0; };
+        const int CQ2 = C / 16;
+        if (t2->dtype == L3D_F16 && C % 16 == 0 && (CQ2 & (CQ2 - 1)) == 0 && CQ2 <= 16 && al32(t2) && al32(r) && (!has_out || al32(out)) &&
+            (!has_pool || al32(pooled)) && L3D_ENV_INT("L3D_MERGE_256", 1) != 0 && L3D_ENV_INT("L3D_MERGE_CELL", 0) == 0) {
+            // 32-byte channel vectors: one thread per x-column of a cell and 16 channels
+            const size_t items = (size_t)((D + 1) / 2) * ((H + 1) / 2) * (2 * ((W + 1) / 2)) * CQ2;
+            size_t bl = (items + 255) / 256;
+            if (bl > cap) bl = cap;
+            dim3 grid3((unsigned)bl, (unsigned)N);
+            merge_col32_fwd_kernel<<<grid3, 256, sizeof(float) * 4 * C, st>>>((const h16 *)t2->ptr, t2->ldc, d2, (const h16 *)r->ptr, r->ldc, dr, N, C, D, H, W, slope,
+                                                                              has_out ? (h16 *)out->ptr : nullptr, has_out ? out->ldc : 0,
+                                                                              has_pool ? (h16 *)pooled->ptr : nullptr, has_pool ? pooled->ldc : 0);
+        } else
         if ((CQ & (CQ - 1)) == 0 && CQ <= 16 && L3D_ENV_INT("L3D_MERGE_CELL", 0) <= 0) {
             // thread = x-column of a cell: twice the threads of the cell mapping (L3D_MERGE_CELL=1: cell per thread)
             size_t blocks2 = (2 * total + 255) / 256;

@@ -44,7 +44,7 @@ def test_merge_mappings_agree_and_match_torch(dims, C, dtype):
     n2 = nv.norm(s2, g2, b2, None, 1e-5, 1.0, vox)
     nr = nv.norm(sr, gr, br, None, 1e-5, 1.0, vox)
     res = {}
-    for mode in ("0", "1"):
+    for mode in ("0", "1", "-1"):          # 0: column per thread (32-byte vectors in fp16); 1: cell per thread; -1: column, 16-byte vectors
         os.environ["L3D_MERGE_CELL"] = mode
         nv.lib().l3d_env_refresh()
         try:
@@ -52,7 +52,8 @@ def test_merge_mappings_agree_and_match_torch(dims, C, dtype):
         finally:
             os.environ.pop("L3D_MERGE_CELL", None)
             nv.lib().l3d_env_refresh()
-    assert torch.equal(res["0"][0], res["1"][0]) and torch.equal(res["0"][1], res["1"][1])
+    for mode in ("1", "-1"):
+        assert torch.equal(res["0"][0], res[mode][0]) and torch.equal(res["0"][1], res[mode][1])
     # PyTorch fp32 reference: InstanceNorm3d(affine) of both tensors, add, LeakyReLU(0.01), MaxPool3d(2)
     a = F.instance_norm(t2.float().permute(0, 4, 1, 2, 3), weight=g2, bias=b2, eps=1e-5)
     b = F.instance_norm(r.float().permute(0, 4, 1, 2, 3), weight=gr, bias=br, eps=1e-5)
