@@ -154,30 +154,47 @@ __global__ void __launch_bounds__(256) threshold_kernel(const float *__restrict_
 // ------------------------------------------------------------------- CCL --------------------
 // Union-find over linear voxel indices; the root of a set is always its smallest index, so ranking the
 // roots by index reproduces scipy.ndimage.label's raster numbering.
+// (flatten pass: the forest no longer changes shape -- only links are shortened -- so the hops may come from L1: every find
+// of a large component ends on the same root line, which one L2 slice would otherwise serve to all SMs)
+template <bool L1>
 __device__ __forceinline__ int32_t uf_find(const int32_t *parent, int32_t i) {
-    // L2 loads: L1 is not coherent across SMs, and although a stale (older, larger) link is still a valid
-    // member of the chain, reading at L2 keeps the retry count low
     int32_t p = __ldcg(parent + i);
-    while (p != i) { i = p; p = __ldcg(parent + i); }
+    while (p != i) {
+        i = p;
+        if (L1) asm volatile("ld.global.ca.s32 %0, [%1];" : "=r"(p) : "l"(parent + i) : "memory");
+        else p = __ldcg(parent + i);
+    }
     return i;
 }
 // find with path halving: every visited node is re-pointed at its grandparent (atomicMin keeps the links monotone
 // under concurrent unions: a node only ever points at a smaller index of its own set), so the long row-over-row chains of
 // a large component collapse while the merge pass is still running
+// link loads of the merge pass.  L1: cached in L1 (ld.global.ca) -- a stale link is an older, larger member of the same
+// chain, and uf_union only ever acts on a value that an atomicMin returned, so the forest stays valid; every find of a
+// component of millions of voxels ends at the same root, and read at L2 (ld.global.cg) that one line is served by one slice
+template <bool L1>
+__device__ __forceinline__ int32_t uf_ld(const int32_t *p) {
+    int32_t v;
+    if (L1) asm volatile("ld.global.ca.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    else asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+template <bool L1>
 __device__ __forceinline__ int32_t uf_find_halving(int32_t *parent, int32_t i) {
-    int32_t p = __ldcg(parent + i);
+    int32_t p = uf_ld<L1>(parent + i);
     while (p != i) {
-        const int32_t gp = __ldcg(parent + p);
+        const int32_t gp = uf_ld<L1>(parent + p);
         if (gp != p) atomicMin(&parent[i], gp);
         i = p;
         p = gp;
     }
     return i;
 }
+template <bool L1>
 __device__ __forceinline__ void uf_union(int32_t *parent, int32_t a, int32_t b) {
     while (true) {
-        a = uf_find_halving(parent, a);
-        b = uf_find_halving(parent, b);
+        a = uf_find_halving<L1>(parent, a);
+        b = uf_find_halving<L1>(parent, b);
         if (a == b) return;
         if (a < b) { const int32_t t = a; a = b; b = t; }   // a > b: hook a under b
         const int32_t old = atomicMin(&parent[a], b);
@@ -217,6 +234,7 @@ __global__ void __launch_bounds__(256) ccl_init_kernel(const int32_t *__restrict
 // Unions only where two runs meet for the first time: for the y / z neighbour only at the first voxel of an overlap
 // (if the previous voxel in x and its y / z neighbour are both foreground, that voxel has already joined the same two
 // runs).
+template <bool L1>
 __global__ void __launch_bounds__(256) ccl_merge_kernel(int32_t *__restrict__ parent, int D, int H, int W) {
     const int32_t n = D * H * W;
     const int32_t WH = W * H;
@@ -224,25 +242,39 @@ __global__ void __launch_bounds__(256) ccl_merge_kernel(int32_t *__restrict__ pa
         if (parent[i] < 0) continue;
         const int x = i % W, y = (i / W) % H, z = i / WH;
         const bool left = x > 0 && parent[i - 1] >= 0;
-        if (y > 0 && parent[i - W] >= 0 && !(left && parent[i - W - 1] >= 0)) uf_union(parent, i, i - W);
-        if (z > 0 && parent[i - WH] >= 0 && !(left && parent[i - WH - 1] >= 0)) uf_union(parent, i, i - WH);
+        if (y > 0 && parent[i - W] >= 0 && !(left && parent[i - W - 1] >= 0)) uf_union<L1>(parent, i, i - W);
+        if (z > 0 && parent[i - WH] >= 0 && !(left && parent[i - WH - 1] >= 0)) uf_union<L1>(parent, i, i - WH);
     }
 }
+template <bool L1>
 __global__ void __launch_bounds__(256) ccl_flatten_count_kernel(int32_t *__restrict__ parent, int32_t n, int32_t *__restrict__ size) {
     // warp-uniform trip count so that the lanes can aggregate their size increments per root (a large
     // component would otherwise serialise millions of atomics on one address)
+    // ... and the CTA keeps the count of ONE root (the first it meets) in shared memory: a component of millions of voxels
+    // otherwise sends one global atomic per warp step to a single address (163 K of them for a 128 x 128 x 320 map that is
+    // mostly one component), which the L2 serialises
+    __shared__ int32_t s_hot, s_cnt;
+    if (threadIdx.x == 0) { s_hot = -1; s_cnt = 0; }
+    __syncthreads();
     const int32_t n_round = (n + 31) & ~31;
     for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         int32_t r = -1;
         if (i < n && parent[i] >= 0) {
-            r = uf_find(parent, i);
+            r = uf_find<L1>(parent, i);
             // roots keep parent[r] == r; non-roots may point at the root directly (no thread still needs the chain:
             // every chain ends at r and a concurrent reader following a shortened link still arrives at r)
             if (r != i) parent[i] = r;
         }
         const unsigned peers = __match_any_sync(0xffffffffu, r);
-        if (r >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&size[r], __popc(peers));
+        if (r >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) {
+            int32_t hot = *reinterpret_cast<volatile int32_t *>(&s_hot);
+            if (hot == -1) { const int32_t old = atomicCAS(&s_hot, -1, r); hot = old == -1 ? r : old; }
+            if (hot == r) atomicAdd(&s_cnt, __popc(peers));
+            else atomicAdd(&size[r], __popc(peers));
+        }
     }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_hot >= 0 && s_cnt > 0) atomicAdd(&size[s_hot], s_cnt);
 }
 // flag[i] = 1 iff voxel i is the root of a surviving component
 __global__ void __launch_bounds__(256) ccl_flag_kernel(const int32_t *__restrict__ parent, const int32_t *__restrict__ size,
@@ -511,8 +543,10 @@ extern "C" int l3d_ccl_label(const int32_t *mask, int D, int H, int W, int min_s
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned g = grid_for(n, 256, 148 * 32);
     ccl_init_kernel<<<g, 256, 0, st>>>(mask, n, W, parent, size);
-    ccl_merge_kernel<<<g, 256, 0, st>>>(parent, D, H, W);
-    ccl_flatten_count_kernel<<<g, 256, 0, st>>>(parent, n, size);
+    if (L3D_ENV_INT("L3D_CCL_L1", 1) != 0) ccl_merge_kernel<true><<<g, 256, 0, st>>>(parent, D, H, W);
+    else ccl_merge_kernel<false><<<g, 256, 0, st>>>(parent, D, H, W);
+    if (L3D_ENV_INT("L3D_CCL_L1", 1) != 0) ccl_flatten_count_kernel<true><<<g, 256, 0, st>>>(parent, n, size);
+    else ccl_flatten_count_kernel<false><<<g, 256, 0, st>>>(parent, n, size);
     // metrics.py:52-58 drops components with size < min_size only when min_size > 0; with min_size <= 0 every
     // component (size >= 1) survives, which `size >= min_size` also yields.
     ccl_flag_kernel<<<g, 256, 0, st>>>(parent, size, n, min_size, flag);
