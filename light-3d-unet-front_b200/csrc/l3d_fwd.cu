@@ -1730,10 +1730,7 @@ extern "C" int l3d_merge_fwd(const l3d_act *t2, const l3d_norm *n2, const l3d_ac
                 merge_head16v_fwd_kernel<<<gridv, 256, 0, st>>>((const h16 *)t2->ptr, t2->ldc, d2, (const h16 *)r->ptr, r->ldc, dr, N, nvox, slope,
                                                                has_out ? (h16 *)out->ptr : nullptr, has_out ? out->ldc : 0, head_w, head_b, OC, prob, logits);
             } else
-            if (L3D_ENV_INT("L3D_HEAD16_U", 2) == 4)
-                merge_head16_fwd_kernel<4><<<gridh, 256, 0, st>>>((const h16 *)t2->ptr, t2->ldc, d2, (const h16 *)r->ptr, r->ldc, dr, N, nvox, slope,
-                                                              has_out ? (h16 *)out->ptr : nullptr, has_out ? out->ldc : 0, head_w, head_b, OC, prob, logits);
-            else
+            // (four loads in flight per thread instead of two changed nothing: 537 vs 556 us -- the half-voxel kernel is not latency-bound)
             merge_head16_fwd_kernel<2><<<gridh, 256, 0, st>>>((const h16 *)t2->ptr, t2->ldc, d2, (const h16 *)r->ptr, r->ldc, dr, N, nvox, slope,
                                                           has_out ? (h16 *)out->ptr : nullptr, has_out ? out->ldc : 0, head_w, head_b, OC, prob, logits);
             l3d_count_launch();
