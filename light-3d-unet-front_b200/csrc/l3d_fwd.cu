@@ -1279,6 +1279,7 @@ __global__ void __launch_bounds__(256) dw_c1_vec_kernel(const h16 *__restrict__ 
     float sc, sh;
     norm_scale_shift(xn, N, 1, n, 0, sc, sh);
     const float slope = xn.slope;
+    const bool ident = xn.stats == nullptr && slope == 1.f;
     float wr[27];
 #pragma unroll
     for (int k = 0; k < 27; ++k) wr[k] = s_w[k];
@@ -1310,10 +1311,12 @@ __global__ void __launch_bounds__(256) dw_c1_vec_kernel(const h16 *__restrict__ 
                 v[7] = h16_lo(r4.w); v[8] = h16_hi(r4.w);
                 if (okl) v[0] = __half2float(row[-1]);
                 if (okr) v[9] = __half2float(row[8]);
+                if (!ident) {                  // the network input carries no norm / activation: v * 1 + 0 through lrelu(., 1) is v
 #pragma unroll
-                for (int i = 0; i < 10; ++i) v[i] = lrelu(fmaf(v[i], sc, sh), slope);
-                if (!okl) v[0] = 0.f;
-                if (!okr) v[9] = 0.f;
+                    for (int i = 0; i < 10; ++i) v[i] = lrelu(fmaf(v[i], sc, sh), slope);
+                    if (!okl) v[0] = 0.f;
+                    if (!okr) v[9] = 0.f;
+                }
             }
 #pragma unroll
             for (int dz = 0; dz < 3; ++dz) {
