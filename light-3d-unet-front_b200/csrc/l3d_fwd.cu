@@ -1768,7 +1768,8 @@ extern "C" int l3d_merge_fwd(const l3d_act *t2, const l3d_norm *n2, const l3d_ac
         const int CQ = C / V;
         auto al32 = [](const l3d_act *a) { return a->ldc % 16 == 0 && reinterpret_cast<uintptr_t>(a->ptr) % 32 == 0; };
         const int CQ2 = C / 16;
-        if (t2->dtype == L3D_F16 && C % 16 == 0 && (CQ2 & (CQ2 - 1)) == 0 && CQ2 <= 16 && al32(t2) && al32(r) && (!has_out || al32(out)) &&
+        const bool col_ok = total < (1ull << 29);       // the column kernels count 2x the cells in 32 bits, plus the grid stride
+        if (col_ok && t2->dtype == L3D_F16 && C % 16 == 0 && (CQ2 & (CQ2 - 1)) == 0 && CQ2 <= 16 && al32(t2) && al32(r) && (!has_out || al32(out)) &&
             (!has_pool || al32(pooled)) && L3D_ENV_INT("L3D_MERGE_256", 1) != 0 && L3D_ENV_INT("L3D_MERGE_CELL", 0) == 0) {
             // 32-byte channel vectors: one thread per x-column of a cell and 16 channels
             const size_t items = (size_t)((D + 1) / 2) * ((H + 1) / 2) * (2 * ((W + 1) / 2)) * CQ2;
@@ -1779,7 +1780,7 @@ extern "C" int l3d_merge_fwd(const l3d_act *t2, const l3d_norm *n2, const l3d_ac
                                                                               has_out ? (h16 *)out->ptr : nullptr, has_out ? out->ldc : 0,
                                                                               has_pool ? (h16 *)pooled->ptr : nullptr, has_pool ? pooled->ldc : 0);
         } else
-        if ((CQ & (CQ - 1)) == 0 && CQ <= 16 && L3D_ENV_INT("L3D_MERGE_CELL", 0) <= 0) {
+        if (col_ok && (CQ & (CQ - 1)) == 0 && CQ <= 16 && L3D_ENV_INT("L3D_MERGE_CELL", 0) <= 0) {
             // thread = x-column of a cell: twice the threads of the cell mapping (L3D_MERGE_CELL=1: cell per thread)
             size_t blocks2 = (2 * total + 255) / 256;
             if (blocks2 > cap) blocks2 = cap;
@@ -1886,7 +1887,7 @@ extern "C" int l3d_merge_fwd_rank1(const l3d_act *t2, const l3d_norm *n2, const 
     const int CQ = C / V;
     {
         auto al32 = [](const l3d_act *a) { return a->ldc % 16 == 0 && reinterpret_cast<uintptr_t>(a->ptr) % 32 == 0; };
-        if (C == 16 && t2->dtype == L3D_F16 && al32(t2) && (!has_out || al32(out)) && (!has_pool || al32(pooled)) &&
+        if (total < (1ull << 29) && C == 16 && t2->dtype == L3D_F16 && al32(t2) && (!has_out || al32(out)) && (!has_pool || al32(pooled)) &&
             L3D_ENV_INT("L3D_MERGE_256", 1) != 0 && L3D_ENV_INT("L3D_MERGE_CELL", 0) == 0) {
             const size_t cols = (size_t)((D + 1) / 2) * ((H + 1) / 2) * (2 * ((W + 1) / 2));
             size_t bl = (cols + 255) / 256;
@@ -1902,7 +1903,7 @@ extern "C" int l3d_merge_fwd_rank1(const l3d_act *t2, const l3d_norm *n2, const 
     }
     // column-per-thread mapping: measured SLOWER for the rank-1 shortcut (325 windows of 48^3: 634 vs 568 us; the plain merge
     // gains 18 %, 730 -> 617 us), so it is opt-in here (L3D_MERGE_CELL=-1) and the default above
-    if ((CQ & (CQ - 1)) == 0 && CQ <= 16 && L3D_ENV_INT("L3D_MERGE_CELL", 0) == -1) {
+    if (total < (1ull << 29) && (CQ & (CQ - 1)) == 0 && CQ <= 16 && L3D_ENV_INT("L3D_MERGE_CELL", 0) == -1) {
         size_t blocks2 = (2 * total + 255) / 256;
         if (blocks2 > cap) blocks2 = cap;
         dim3 grid2((unsigned)blocks2, (unsigned)N);
