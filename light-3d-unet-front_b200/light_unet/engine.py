@@ -186,7 +186,7 @@ class UNetPlan:
         [ConvTranspose output | skip] as two dense 16-channel tensors (l3d_dwpw_fwd2) instead of one interleaved buffer."""
         up3 = self.blocks[-1]
         return ((not training) and dtype == torch.float16 and up3.kind1 == "dws" and up3.cin == 32 and up3.cout == 16 and self.enc[0] == 16
-                and os.environ.get("L3D_SPLIT_CAT", "1") != "0")
+                and os.environ.get("L3D_SPLIT_CAT", "1") != "0" and os.environ.get("L3D_NO_IGEMM", "0") != "1")   # needs the implicit-GEMM kernel
 
     def rank1_first(self, b: BlockSpec, dtype, dims, training: bool) -> bool:
         return (self.rank1_shortcut(b, training) and b.kind2 == "dws" and b.cout == 16 and dtype == torch.float16
