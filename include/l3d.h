@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define L3D_ABI_VERSION 4
+#define L3D_ABI_VERSION 5
 
 /* activation storage: fp32, or IEEE fp16 (stores saturate to +-65504); accumulation and statistics are fp32 / double */
 enum { L3D_F32 = 0, L3D_F16 = 1 };

@@ -15,7 +15,7 @@ _PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.environ.get("L3D_LIB", os.path.join(_PKG_DIR, "libl3d.so"))
 
 L3D_F32, L3D_F16 = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class Act(Structure):
