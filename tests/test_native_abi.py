@@ -116,3 +116,25 @@ def test_inferencer_type_error():
     from light_unet.core.inferencer import Inferencer
     with pytest.raises(TypeError):
         Inferencer(42, "x.pth")
+
+
+def test_split_concat_plan_choice(monkeypatch):
+    """The top-level [up | skip] concat is kept as two dense tensors only where l3d_dwpw_fwd2 applies: inference, fp16 storage,
+    depthwise-separable up3.conv1 with 16 + 16 input channels (engine.UNetPlan.split_cat0) -- host logic, no GPU needed."""
+    import torch
+    from light_unet.models.unet3d import Lightweight3DUNet
+    mk = lambda enc, dws: Lightweight3DUNet(in_channels=1, out_channels=1, start_channels=enc[0], encoder_channels=enc,
+                                            use_depthwise_separable=dws, use_grouped=True, groups=8, dropout_p=0.0)._plan
+    monkeypatch.delenv("L3D_SPLIT_CAT", raising=False)
+    monkeypatch.delenv("L3D_NO_IGEMM", raising=False)
+    p = mk([16, 32, 64, 128], True)
+    assert p.split_cat0(torch.float16, False)
+    assert not p.split_cat0(torch.float16, True)          # training reads the interleaved buffer in its backward kernels
+    assert not p.split_cat0(torch.float32, False)
+    assert not mk([16, 32, 64, 128], False).split_cat0(torch.float16, False)      # grouped / dense variants
+    assert not mk([32, 64, 128, 256], True).split_cat0(torch.float16, False)      # 32 + 32 channels: not two 16-channel chunks
+    monkeypatch.setenv("L3D_SPLIT_CAT", "0")
+    assert not p.split_cat0(torch.float16, False)
+    monkeypatch.delenv("L3D_SPLIT_CAT")
+    monkeypatch.setenv("L3D_NO_IGEMM", "1")
+    assert not p.split_cat0(torch.float16, False)
